@@ -1,0 +1,343 @@
+// TEST INFRASTRUCTURE ONLY (oracle). Not part of the product; never linked by it.
+//
+// C wrapper around the UNMODIFIED reference admm::Solver, compiled from the
+// sources where they lie under /root/reference by oracle/Makefile into
+// oracle/_ref/libref_hard.so (-DREF_HARD, admm_anderson_hard_zxu) and
+// oracle/_ref/libref_xzu.so (-DREF_XZU, admm_anderson_xzu).
+//
+// It drives the reference exactly as samples/utils/Application.hpp:232-249 does
+// (sim callback -> Solver::step()), headless, and exposes what the parity tests
+// need: positions, the logged residual trajectory (read back from the file the
+// reference's own save() writes, Solver.hpp:126-151), the protected system
+// matrix and the Eigen LDLT factor (through a Probe subclass, no source edits).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <memory>
+#include <unistd.h>
+#include <sys/stat.h>
+
+#include "Solver.hpp"
+#include "TetEnergyTerm.hpp"
+#include "MCL/TetMesh.hpp"
+#include "MCL/ShapeFactory.hpp"
+#include "MCL/XForm.hpp"
+
+#ifdef REF_HARD
+#define RFN(name) ref_hard_##name
+#else
+#define RFN(name) ref_xzu_##name
+#endif
+
+namespace {
+
+struct Probe : public admm::Solver {
+    const SparseMat &termA() const { return solver_termA; }
+    const SparseMat &D() const { return m_D; }
+    const VecX &x_pin() const { return m_x_pin; }
+    admm::LDLTSolver *ldlt() { return static_cast<admm::LDLTSolver *>(m_linsolver.get()); }
+};
+
+struct Handle {
+    Probe solver;
+    admm::Solver::Settings settings;
+    std::string workdir;
+    std::vector<double> hist;  // rows of the last residual file
+    int hist_cols = 0;
+    double step_wall_ms = 0;
+};
+
+// ProbeTet exposes the protected prox / get_gradient of the LINEAR tet.
+struct ProbeTet : public admm::TetEnergyTerm {
+    using admm::TetEnergyTerm::TetEnergyTerm;
+    void call_prox(double *z9) {
+        VecX zi = Eigen::Map<VecX>(z9, 9);
+        VecX vi = zi;
+        Eigen::Matrix<double, 9, 9> W = Eigen::Matrix<double, 9, 9>::Identity();
+        prox(W, zi, vi);
+        Eigen::Map<VecX>(z9, 9) = zi;
+    }
+    void call_grad(const double *z9, double *g9) {
+        VecX zi = Eigen::Map<const VecX>(z9, 9);
+        VecX g = VecX::Zero(9);
+        get_gradient(zi, g);
+        Eigen::Map<VecX>(g9, 9) = g;
+    }
+    double w() const { return weight; }
+    double vol() const { return volume; }
+    const Eigen::Matrix3d &binv() const { return edges_inv; }
+};
+
+}  // namespace
+
+extern "C" {
+
+void *RFN(new)(const char *workdir) {
+    Handle *h = new Handle();
+    h->workdir = workdir ? workdir : ".";
+    return h;
+}
+
+void RFN(free)(void *hp) { delete static_cast<Handle *>(hp); }
+
+// material: 0 LINEAR (TetEnergyTerm), 1 NEOHOOKEAN, 2 STVK. Mirrors
+// binding::add_tetmesh (samples/utils/AddMeshes.hpp:97-177) with the arrays
+// supplied by the caller (float32 vertices and masses, as the reference has them).
+int RFN(add_tetmesh)(void *hp, const float *verts, int n_verts, const int *tets, int n_tets,
+                     const float *masses, double youngs, double poisson, int material) {
+    Handle *h = static_cast<Handle *>(hp);
+    admm::Solver *s = &h->solver;
+    int prev = s->m_x.rows() / 3;
+    s->m_x.conservativeResize(prev * 3 + n_verts * 3);
+    s->m_masses.conservativeResize(prev * 3 + n_verts * 3);
+    for (int i = 0; i < n_verts; ++i) {
+        int idx = i + prev;
+        Eigen::Vector3f v(verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]);
+        s->m_x.segment<3>(idx * 3) = v.cast<double>();
+        s->m_masses.segment<3>(idx * 3) = Eigen::Vector3d(1, 1, 1) * masses[i];
+    }
+    admm::Lame lame(youngs, poisson);
+    try {
+        if (material == 0)
+            admm::create_tets_from_mesh<float, admm::TetEnergyTerm>(s->energyterms, verts, tets, n_tets, lame, prev);
+        else if (material == 1)
+            admm::create_tets_from_mesh<float, admm::NeoHookeanTet>(s->energyterms, verts, tets, n_tets, lame, prev);
+        else
+            admm::create_tets_from_mesh<float, admm::StVKTet>(s->energyterms, verts, tets, n_tets, lame, prev);
+    } catch (std::exception &e) {
+        fprintf(stderr, "ref add_tetmesh: %s\n", e.what());
+        return -1;
+    }
+    return prev + n_verts;
+}
+
+int RFN(set_pins)(void *hp, const int *idx, const double *pts, int n) {
+    Handle *h = static_cast<Handle *>(hp);
+    std::vector<int> inds(idx, idx + n);
+    std::vector<Eigen::Vector3d> points(n);
+    for (int i = 0; i < n; ++i) points[i] = Eigen::Vector3d(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+    try {
+        h->solver.set_pins(inds, points);
+    } catch (std::exception &e) {
+        fprintf(stderr, "ref set_pins: %s\n", e.what());
+        return -1;
+    }
+    return 0;
+}
+
+int RFN(initialize)(void *hp, double dt, int iters, double gravity, int anderson_m, int accel, double penalty) {
+    Handle *h = static_cast<Handle *>(hp);
+    h->settings.timestep_s = dt;
+    h->settings.admm_iters = iters;
+    h->settings.gravity = gravity;
+    h->settings.Anderson_m = anderson_m;
+    h->settings.verbose = 0;
+    h->settings.acceleration_type =
+        accel ? admm::Solver::Settings::ANDERSON : admm::Solver::Settings::NOACC;
+#ifdef REF_HARD
+    h->settings.penalty = penalty;
+#else
+    (void)penalty;
+#endif
+    try {
+        FILE *saved = nullptr;
+        (void)saved;
+        bool ok = h->solver.initialize(h->settings);
+        return ok ? 0 : -2;
+    } catch (std::exception &e) {
+        fprintf(stderr, "ref initialize: %s\n", e.what());
+        return -1;
+    }
+}
+
+// One Solver::step(). The reference writes ./result/residual-*.txt relative to the
+// cwd (Solver.hpp:126-151): run inside workdir and read the file back.
+int RFN(step)(void *hp) {
+    Handle *h = static_cast<Handle *>(hp);
+    char cwd[4096];
+    if (!getcwd(cwd, sizeof cwd)) return -3;
+    std::string res = h->workdir + "/result";
+    mkdir(h->workdir.c_str(), 0777);
+    mkdir(res.c_str(), 0777);
+    if (chdir(h->workdir.c_str()) != 0) return -3;
+    int rc = 0;
+    try {
+        mcl::MicroTimer t;
+        h->solver.step();
+        h->step_wall_ms = t.elapsed_ms();
+    } catch (std::exception &e) {
+        fprintf(stderr, "ref step: %s\n", e.what());
+        rc = -1;
+    }
+    if (chdir(cwd) != 0) return -3;
+    if (rc) return rc;
+    std::string file = res + "/residual-" +
+                       (h->settings.acceleration_type ? std::to_string(h->settings.Anderson_m) : std::string("no")) +
+                       ".txt";
+    std::ifstream in(file);
+    h->hist.clear();
+    h->hist_cols = 0;
+    std::string line;
+    while (std::getline(in, line)) {
+        std::istringstream ls(line);
+        double v;
+        int c = 0;
+        while (ls >> v) {
+            h->hist.push_back(v);
+            ++c;
+        }
+        if (c) h->hist_cols = c;
+    }
+    return 0;
+}
+
+double RFN(step_wall_ms)(void *hp) { return static_cast<Handle *>(hp)->step_wall_ms; }
+// reference RuntimeData totals of the last step: local, global, acceleration, initialization
+void RFN(runtime)(void *hp, double *out4) {
+    const admm::Solver::RuntimeData &r = static_cast<Handle *>(hp)->solver.runtime_data();
+    out4[0] = r.local_ms;
+    out4[1] = r.global_ms;
+    out4[2] = r.acceleration_ms;
+    out4[3] = r.initialization_ms;
+}
+
+int RFN(hist_rows)(void *hp) {
+    Handle *h = static_cast<Handle *>(hp);
+    return h->hist_cols ? (int)(h->hist.size() / h->hist_cols) : 0;
+}
+int RFN(hist_cols)(void *hp) { return static_cast<Handle *>(hp)->hist_cols; }
+void RFN(hist_copy)(void *hp, double *out) {
+    Handle *h = static_cast<Handle *>(hp);
+    memcpy(out, h->hist.data(), h->hist.size() * sizeof(double));
+}
+
+int RFN(n_dof)(void *hp) { return (int)static_cast<Handle *>(hp)->solver.m_x.rows(); }
+void RFN(get_x)(void *hp, double *out) {
+    Handle *h = static_cast<Handle *>(hp);
+    memcpy(out, h->solver.m_x.data(), h->solver.m_x.rows() * sizeof(double));
+}
+void RFN(get_v)(void *hp, double *out) {
+    Handle *h = static_cast<Handle *>(hp);
+    memcpy(out, h->solver.m_v.data(), h->solver.m_v.rows() * sizeof(double));
+}
+
+// System matrix A = M + rho dt^2 D^T D (3n_free x 3n_free), CSR.
+long RFN(termA_nnz)(void *hp) { return static_cast<Handle *>(hp)->solver.termA().nonZeros(); }
+int RFN(termA_rows)(void *hp) { return static_cast<Handle *>(hp)->solver.termA().rows(); }
+void RFN(termA_copy)(void *hp, int *rowptr, int *col, double *val) {
+    Eigen::SparseMatrix<double, Eigen::RowMajor> A = static_cast<Handle *>(hp)->solver.termA();
+    A.makeCompressed();
+    memcpy(rowptr, A.outerIndexPtr(), (A.rows() + 1) * sizeof(int));
+    memcpy(col, A.innerIndexPtr(), A.nonZeros() * sizeof(int));
+    memcpy(val, A.valuePtr(), A.nonZeros() * sizeof(double));
+}
+
+// Eigen SimplicialLDLT factor of A: strictly-lower L (CSC), D, and perm with
+// perm[new] = old (P A P^T = L D L^T).
+long RFN(factor_nnz)(void *hp) {
+    Handle *h = static_cast<Handle *>(hp);
+    Eigen::SparseMatrix<double> L = h->solver.ldlt()->m_cholesky->matrixL();
+    return (long)L.nonZeros();  // includes the unit diagonal if stored
+}
+int RFN(factor_copy)(void *hp, int *colptr, int *row, double *val, double *D, int *perm, long cap) {
+    Handle *h = static_cast<Handle *>(hp);
+    auto *chol = h->solver.ldlt()->m_cholesky.get();
+    Eigen::SparseMatrix<double> L = chol->matrixL();
+    L.makeCompressed();
+    int n = L.rows();
+    long k = 0;
+    for (int j = 0; j < n; ++j) {
+        colptr[j] = (int)k;
+        for (Eigen::SparseMatrix<double>::InnerIterator it(L, j); it; ++it) {
+            if (it.row() == j) continue;  // unit diagonal
+            if (k >= cap) return -1;
+            row[k] = it.row();
+            val[k] = it.value();
+            ++k;
+        }
+    }
+    colptr[n] = (int)k;
+    Eigen::VectorXd d = chol->vectorD();
+    memcpy(D, d.data(), n * sizeof(double));
+    // Eigen: permutationP() maps old -> new (indices()[old] = new)
+    const auto &P = chol->permutationP();
+    for (int i = 0; i < n; ++i) perm[P.indices()[i]] = i;
+    return (int)k;
+}
+
+// Apply the reference's own solve (LinearSolver.hpp:87-90) to an arbitrary rhs.
+void RFN(solve)(void *hp, const double *b, double *x) {
+    Handle *h = static_cast<Handle *>(hp);
+    int n = h->solver.termA().rows();
+    Eigen::VectorXd bb = Eigen::Map<const Eigen::VectorXd>(b, n), xx(n);
+    h->solver.ldlt()->solve(xx, bb);
+    memcpy(x, xx.data(), n * sizeof(double));
+}
+
+// ---- unit-level access to the reference's per-element code -------------------------------
+// LINEAR tet built from 4 double vertices; returns weight, volume, B^-1 (col-major).
+int RFN(tet_constants)(const double *verts12, double youngs, double poisson, double *w, double *vol,
+                       double *binv9) {
+    std::vector<Eigen::Vector3d> v(4);
+    for (int i = 0; i < 4; ++i) v[i] = Eigen::Vector3d(verts12[3 * i], verts12[3 * i + 1], verts12[3 * i + 2]);
+    try {
+        ProbeTet t(Eigen::Vector4i(0, 1, 2, 3), v, admm::Lame(youngs, poisson));
+        *w = t.w();
+        *vol = t.vol();
+        memcpy(binv9, t.binv().data(), 9 * sizeof(double));
+    } catch (std::exception &e) {
+        return -1;
+    }
+    return 0;
+}
+// TetEnergyTerm::prox on n column-major 3x3 blocks, in place.
+void RFN(tet_prox)(double *z, int n) {
+    std::vector<Eigen::Vector3d> v = {Eigen::Vector3d(0, 0, 0), Eigen::Vector3d(1, 0, 0),
+                                      Eigen::Vector3d(0, 1, 0), Eigen::Vector3d(0, 0, 1)};
+    ProbeTet t(Eigen::Vector4i(0, 1, 2, 3), v, admm::Lame(1e7, 0.399));
+    for (int i = 0; i < n; ++i) t.call_prox(z + 9 * i);
+}
+// TetEnergyTerm::get_gradient / (K vol) on n blocks: out = F - U V^T.
+void RFN(tet_F_minus_UVt)(const double *z, double *out, int n) {
+    std::vector<Eigen::Vector3d> v = {Eigen::Vector3d(0, 0, 0), Eigen::Vector3d(1, 0, 0),
+                                      Eigen::Vector3d(0, 1, 0), Eigen::Vector3d(0, 0, 1)};
+    admm::Lame lame(1e7, 0.399);
+    ProbeTet t(Eigen::Vector4i(0, 1, 2, 3), v, lame);
+    double kv = lame.bulk_modulus() * t.vol();
+    for (int i = 0; i < n; ++i) {
+        t.call_grad(z + 9 * i, out + 9 * i);
+        for (int k = 0; k < 9; ++k) out[9 * i + k] /= kv;
+    }
+}
+
+// The reference's own scene generator (ShapeFactory.hpp:436-497 + TetMesh::refine +
+// weighted_masses, and the centre/scale of beams.cpp:83-90) for validating the O(n)
+// restatement. Returns counts; call with null outputs first.
+int RFN(make_beam)(int cx, int cy, int cz, float y_shift, float density, float *verts, int *tets,
+                   float *masses, int *n_verts, int *n_tets) {
+    std::shared_ptr<mcl::TetMesh> mesh = mcl::factory::make_tet_blocks(cx, cy, cz);
+    Eigen::AlignedBox<float, 3> aabb = mesh->bounds();
+    mcl::XForm<float> center = mcl::xform::make_trans<float>(-aabb.center());
+    float y = aabb.sizes()[1];
+    mcl::XForm<float> scale = mcl::xform::make_scale<float>(1.f / y, 1.f / y, 1.f / y);
+    mesh->apply_xform(scale * center);
+    if (y_shift != 0.f) mesh->apply_xform(mcl::xform::make_trans(0.f, y_shift, 0.f));
+    *n_verts = (int)mesh->vertices.size();
+    *n_tets = (int)mesh->tets.size();
+    if (!verts) return 0;
+    std::vector<float> m;
+    mesh->weighted_masses(m, density);
+    for (int i = 0; i < *n_verts; ++i) {
+        for (int k = 0; k < 3; ++k) verts[3 * i + k] = mesh->vertices[i][k];
+        masses[i] = m[i];
+    }
+    for (int i = 0; i < *n_tets; ++i)
+        for (int k = 0; k < 4; ++k) tets[4 * i + k] = mesh->tets[i][k];
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,300 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes bindings for oracle/_ref (the unmodified reference
+compiled by oracle/Makefile) and for the C restatement oracle/liboracle_port.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module. The product (aa-admm_b200/) never does.
+"""
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+
+c_dp = C.POINTER(C.c_double)
+c_fp = C.POINTER(C.c_float)
+c_ip = C.POINTER(C.c_int)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def _fp(a):
+    return a.ctypes.data_as(c_fp)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_ip)
+
+
+def have_ref():
+    return all(os.path.exists(os.path.join(REF_DIR, f))
+               for f in ("libref_hard.so", "libref_xzu.so", "libref_aa.so"))
+
+
+_libs = {}
+
+
+def _load(name):
+    if name not in _libs:
+        _libs[name] = C.CDLL(os.path.join(REF_DIR, name))
+    return _libs[name]
+
+
+class RefSolver:
+    """The reference admm::Solver (hard_zxu or xzu ordering), driven headless."""
+
+    def __init__(self, variant="hard", workdir=None):
+        assert variant in ("hard", "xzu")
+        self.variant = variant
+        self.lib = _load("libref_%s.so" % variant)
+        self.p = "ref_%s_" % variant
+        self._tmp = None
+        if workdir is None:
+            self._tmp = tempfile.TemporaryDirectory(prefix="refsolver_")
+            workdir = self._tmp.name
+        f = self._f
+        f("new").restype = C.c_void_p
+        f("new").argtypes = [C.c_char_p]
+        self.h = C.c_void_p(f("new")(workdir.encode()))
+        f("free").argtypes = [C.c_void_p]
+        f("add_tetmesh").argtypes = [C.c_void_p, c_fp, C.c_int, c_ip, C.c_int, c_fp, C.c_double, C.c_double, C.c_int]
+        f("set_pins").argtypes = [C.c_void_p, c_ip, c_dp, C.c_int]
+        f("initialize").argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double]
+        f("step").argtypes = [C.c_void_p]
+        f("step_wall_ms").argtypes = [C.c_void_p]
+        f("step_wall_ms").restype = C.c_double
+        f("runtime").argtypes = [C.c_void_p, c_dp]
+        for n in ("hist_rows", "hist_cols", "n_dof", "termA_rows"):
+            f(n).argtypes = [C.c_void_p]
+        f("hist_copy").argtypes = [C.c_void_p, c_dp]
+        f("get_x").argtypes = [C.c_void_p, c_dp]
+        f("get_v").argtypes = [C.c_void_p, c_dp]
+        f("termA_nnz").argtypes = [C.c_void_p]
+        f("termA_nnz").restype = C.c_long
+        f("termA_copy").argtypes = [C.c_void_p, c_ip, c_ip, c_dp]
+        f("factor_nnz").argtypes = [C.c_void_p]
+        f("factor_nnz").restype = C.c_long
+        f("factor_copy").argtypes = [C.c_void_p, c_ip, c_ip, c_dp, c_dp, c_ip, C.c_long]
+        f("solve").argtypes = [C.c_void_p, c_dp, c_dp]
+
+    def _f(self, name):
+        return getattr(self.lib, self.p + name)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self._f("free")(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def add_tetmesh(self, verts, tets, masses, youngs=1e7, poisson=0.399, material=0):
+        verts = np.ascontiguousarray(verts, np.float32)
+        tets = np.ascontiguousarray(tets, np.int32)
+        masses = np.ascontiguousarray(masses, np.float32)
+        r = self._f("add_tetmesh")(self.h, _fp(verts), len(verts), _ip(tets), len(tets), _fp(masses),
+                                   youngs, poisson, material)
+        if r < 0:
+            raise RuntimeError("reference add_tetmesh failed")
+        return r
+
+    def set_pins(self, idx, pts):
+        idx = np.ascontiguousarray(idx, np.int32)
+        pts = np.ascontiguousarray(pts, np.float64)
+        if self._f("set_pins")(self.h, _ip(idx), _dp(pts), len(idx)) != 0:
+            raise RuntimeError("reference set_pins failed")
+
+    def initialize(self, dt=1.0 / 30.0, iters=100, gravity=-9.8, anderson_m=5, accel=True, penalty=1.0):
+        r = self._f("initialize")(self.h, dt, iters, gravity, anderson_m, int(bool(accel)), penalty)
+        if r != 0:
+            raise RuntimeError("reference initialize failed (%d)" % r)
+
+    def step(self):
+        """One Solver::step(); returns the logged trajectory, columns
+        cumulative_ms, prim_residual, comb_residual[, is_reject]."""
+        r = self._f("step")(self.h)
+        if r != 0:
+            raise RuntimeError("reference step failed (%d)" % r)
+        rows, cols = self._f("hist_rows")(self.h), self._f("hist_cols")(self.h)
+        out = np.zeros((rows, cols))
+        if rows:
+            self._f("hist_copy")(self.h, _dp(out))
+        return out
+
+    def step_wall_ms(self):
+        return self._f("step_wall_ms")(self.h)
+
+    def runtime(self):
+        out = np.zeros(4)
+        self._f("runtime")(self.h, _dp(out))
+        return dict(local_ms=out[0], global_ms=out[1], acceleration_ms=out[2], initialization_ms=out[3])
+
+    def x(self):
+        out = np.zeros(self._f("n_dof")(self.h))
+        self._f("get_x")(self.h, _dp(out))
+        return out
+
+    def v(self):
+        out = np.zeros(self._f("n_dof")(self.h))
+        self._f("get_v")(self.h, _dp(out))
+        return out
+
+    def termA(self):
+        n = self._f("termA_rows")(self.h)
+        nnz = self._f("termA_nnz")(self.h)
+        rp, ci, v = np.zeros(n + 1, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz)
+        self._f("termA_copy")(self.h, _ip(rp), _ip(ci), _dp(v))
+        return n, rp, ci, v
+
+    def factor(self):
+        """Eigen's LDL^T factor: (n, colptr, rowidx, Lx) strictly lower CSC, D, perm[new]=old."""
+        n = self._f("termA_rows")(self.h)
+        cap = self._f("factor_nnz")(self.h)
+        cp, ri, v = np.zeros(n + 1, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+        D, perm = np.zeros(n), np.zeros(n, np.int32)
+        k = self._f("factor_copy")(self.h, _ip(cp), _ip(ri), _dp(v), _dp(D), _ip(perm), cap)
+        assert k >= 0
+        return n, cp, ri[:k].copy(), v[:k].copy(), D, perm
+
+    def solve(self, b):
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.zeros_like(b)
+        self._f("solve")(self.h, _dp(b), _dp(x))
+        return x
+
+
+def ref_make_beam(cx, cy, cz, y_shift=0.0, density=1522.0):
+    """The reference's own make_tet_blocks + centre/scale + weighted_masses."""
+    lib = _load("libref_hard.so")
+    fn = lib.ref_hard_make_beam
+    fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, c_fp, c_ip, c_fp, c_ip, c_ip]
+    nv, nt = C.c_int(0), C.c_int(0)
+    fn(cx, cy, cz, y_shift, density, None, None, None, C.byref(nv), C.byref(nt))
+    verts = np.zeros((nv.value, 3), np.float32)
+    tets = np.zeros((nt.value, 4), np.int32)
+    masses = np.zeros(nv.value, np.float32)
+    fn(cx, cy, cz, y_shift, density, _fp(verts), _ip(tets), _fp(masses), C.byref(nv), C.byref(nt))
+    return verts, tets, masses
+
+
+def ref_tet_prox(z):
+    """TetEnergyTerm::prox on (n,9) column-major 3x3 blocks."""
+    lib = _load("libref_hard.so")
+    lib.ref_hard_tet_prox.argtypes = [c_dp, C.c_int]
+    out = np.ascontiguousarray(z, np.float64).copy()
+    lib.ref_hard_tet_prox(_dp(out), out.shape[0])
+    return out
+
+
+def ref_tet_F_minus_UVt(z):
+    lib = _load("libref_xzu.so")
+    lib.ref_xzu_tet_F_minus_UVt.argtypes = [c_dp, c_dp, C.c_int]
+    z = np.ascontiguousarray(z, np.float64)
+    out = np.zeros_like(z)
+    lib.ref_xzu_tet_F_minus_UVt(_dp(z), _dp(out), z.shape[0])
+    return out
+
+
+def ref_tet_constants(verts4, youngs=1e7, poisson=0.399):
+    lib = _load("libref_hard.so")
+    lib.ref_hard_tet_constants.argtypes = [c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp]
+    v = np.ascontiguousarray(verts4, np.float64)
+    w, vol, binv = C.c_double(), C.c_double(), np.zeros(9)
+    if lib.ref_hard_tet_constants(_dp(v), youngs, poisson, C.byref(w), C.byref(vol), _dp(binv)) != 0:
+        raise RuntimeError("inverted tet")
+    return w.value, vol.value, binv
+
+
+class RefAndersonH:
+    """hard/src/AndersonAcceleration.h (== Geometry/AndersonAcceleration.h)."""
+
+    def __init__(self, m, total_dim, effective_dim):
+        self.lib = _load("libref_aa.so")
+        L = self.lib
+        L.ref_aa_h_new.restype = C.c_void_p
+        L.ref_aa_h_new.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.ref_aa_h_free.argtypes = [C.c_void_p]
+        for n in ("init", "reset", "replace"):
+            getattr(L, "ref_aa_h_" + n).argtypes = [C.c_void_p, c_dp, C.c_int]
+        L.ref_aa_h_compute.argtypes = [C.c_void_p, c_dp, c_dp, C.c_int]
+        self.n = total_dim
+        self.h = C.c_void_p(L.ref_aa_h_new(m, total_dim, effective_dim))
+
+    def __del__(self):
+        try:
+            self.lib.ref_aa_h_free(self.h)
+        except Exception:
+            pass
+
+    def init(self, u):
+        u = np.ascontiguousarray(u, np.float64)
+        self.lib.ref_aa_h_init(self.h, _dp(u), u.size)
+
+    def reset(self, u):
+        u = np.ascontiguousarray(u, np.float64)
+        self.lib.ref_aa_h_reset(self.h, _dp(u), u.size)
+
+    def replace(self, u):
+        u = np.ascontiguousarray(u, np.float64)
+        self.lib.ref_aa_h_replace(self.h, _dp(u), u.size)
+
+    def compute(self, g):
+        g = np.ascontiguousarray(g, np.float64)
+        out = np.zeros_like(g)
+        self.lib.ref_aa_h_compute(self.h, _dp(g), _dp(out), g.size)
+        return out
+
+
+class RefAndersonX:
+    """xzu/src/AndersonAcceleration.h."""
+
+    def __init__(self):
+        self.lib = _load("libref_aa.so")
+        L = self.lib
+        L.ref_aa_x_new.restype = C.c_void_p
+        L.ref_aa_x_free.argtypes = [C.c_void_p]
+        L.ref_aa_x_init.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp]
+        L.ref_aa_x_replace.argtypes = [C.c_void_p, c_dp, C.c_int]
+        L.ref_aa_x_compute.argtypes = [C.c_void_p, c_dp, c_dp, C.c_int]
+        self.h = C.c_void_p(L.ref_aa_x_new())
+
+    def __del__(self):
+        try:
+            self.lib.ref_aa_x_free(self.h)
+        except Exception:
+            pass
+
+    def init(self, m, d, g0):
+        g0 = np.ascontiguousarray(g0, np.float64)
+        self.lib.ref_aa_x_init(self.h, m, d, _dp(g0))
+
+    def replace(self, g):
+        g = np.ascontiguousarray(g, np.float64)
+        self.lib.ref_aa_x_replace(self.h, _dp(g), g.size)
+
+    def compute(self, g):
+        g = np.ascontiguousarray(g, np.float64)
+        out = np.zeros_like(g)
+        self.lib.ref_aa_x_compute(self.h, _dp(out), _dp(g), g.size)
+        return out
+
+
+def ref_cod_solve(M, rhs):
+    lib = _load("libref_aa.so")
+    lib.ref_cod_solve.argtypes = [C.c_int, c_dp, c_dp, c_dp]
+    M = np.asfortranarray(M, np.float64)
+    rhs = np.ascontiguousarray(rhs, np.float64)
+    out = np.zeros_like(rhs)
+    lib.ref_cod_solve(M.shape[0], M.ctypes.data_as(c_dp), _dp(rhs), _dp(out))
+    return out
+
+
+def ref_cod_rank(M):
+    lib = _load("libref_aa.so")
+    lib.ref_cod_rank.argtypes = [C.c_int, c_dp]
+    M = np.asfortranarray(M, np.float64)
+    return lib.ref_cod_rank(M.shape[0], M.ctypes.data_as(c_dp))
