@@ -1,0 +1,485 @@
+"""aa-admm_b200: ctypes plumbing over the two native libraries of this repo.
+
+  libaaadmm_b200.so  the C ABI of include/aaadmm.h: sm_100a CUDA kernels for the AA-ADMM hot path
+  libaaadmm_host.so  the host-side C++ mirror of the reference's scene/solver classes
+
+Nothing here computes: every call lands in native code, and the compute entry points fail
+loudly when no CUDA device is present (there is no CPU path in the product).
+Import name: `aa_admm_b200` (the directory name has a dash; aa_admm_b200/__init__.py aliases it).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_CUDA = os.path.join(PKG, "libaaadmm_b200.so")
+LIB_HOST = os.path.join(PKG, "libaaadmm_host.so")
+
+c_dp = C.POINTER(C.c_double)
+c_fp = C.POINTER(C.c_float)
+c_ip = C.POINTER(C.c_int)
+c_lp = C.POINTER(C.c_int64)
+
+ORDER_HARD_ZXU = 0
+ORDER_XZU = 1
+NPROF = 8
+PROF_NAMES = ["update_z", "rhs_gather", "ldlt_apply", "update_u_resid", "aa_pass1", "aa_pass2", "safeguard", "total"]
+
+
+class AaadmmError(RuntimeError):
+    pass
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def _fp(a):
+    return a.ctypes.data_as(c_fp)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_ip)
+
+
+def _lp(a):
+    return a.ctypes.data_as(c_lp)
+
+
+class StepOpts(C.Structure):
+    _fields_ = [("ordering", C.c_int), ("admm_iters", C.c_int), ("anderson_m", C.c_int), ("accel", C.c_int),
+                ("eps", C.c_double), ("log_comb_xzu", C.c_int)]
+
+
+class StepResult(C.Structure):
+    _fields_ = [("iters_logged", C.c_int), ("rejects", C.c_int), ("broke_early", C.c_int), ("loop_ms", C.c_float),
+                ("step_ms", C.c_float), ("kernel_launches", C.c_int)]
+
+
+_cuda = None
+_host = None
+
+
+def build(force=False):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("aaadmm_build", os.path.join(PKG, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build_cuda(force)
+    mod.build_host(force)
+    return mod
+
+
+def cuda_lib():
+    """The C ABI library. Raises if it has not been built (no fallback)."""
+    global _cuda
+    if _cuda is None:
+        if not os.path.exists(LIB_CUDA):
+            raise AaadmmError("libaaadmm_b200.so is missing: run __graft_entry__.build() (no CPU fallback exists)")
+        L = C.CDLL(LIB_CUDA, mode=C.RTLD_GLOBAL)
+        L.aaadmm_last_error.restype = C.c_char_p
+        vp = C.c_void_p
+        L.aaadmm_aa_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int64, C.c_int64]
+        L.aaadmm_aa_destroy.argtypes = [vp]
+        for n in ("init", "reset", "replace"):
+            getattr(L, "aaadmm_aa_" + n).argtypes = [vp, c_dp, C.c_int64]
+        L.aaadmm_aa_compute.argtypes = [vp, c_dp, c_dp, C.c_int64]
+        L.aaadmm_aa_state.argtypes = [vp, c_ip, c_ip]
+        L.aaadmm_ldlt_create.argtypes = [C.POINTER(vp), C.c_int, c_lp, c_ip, c_dp, c_dp, c_ip, C.c_int]
+        L.aaadmm_ldlt_destroy.argtypes = [vp]
+        L.aaadmm_ldlt_solve.argtypes = [vp, c_dp, c_dp]
+        L.aaadmm_ldlt_stats.argtypes = [vp, c_dp]
+        L.aaadmm_tetscene_step_resident.argtypes = [vp, C.POINTER(StepOpts), C.POINTER(StepResult)]
+        L.aaadmm_tetscene_profile.argtypes = [vp, C.POINTER(StepOpts), C.c_int, c_fp]
+        L.aaadmm_tetscene_algo_bytes.argtypes = [vp, C.c_int, c_dp]
+        L.aaadmm_tetscene_read_zu.argtypes = [vp, c_dp, c_dp]
+        L.aaadmm_tet_prox_linear.argtypes = [c_dp, C.c_int64]
+        L.aaadmm_tet_f_minus_uvt.argtypes = [c_dp, c_dp, C.c_int64]
+        L.aaadmm_cod_solve.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_ip]
+        _cuda = L
+    return _cuda
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        cuda_lib()
+        if not os.path.exists(LIB_HOST):
+            raise AaadmmError("libaaadmm_host.so is missing: run __graft_entry__.build()")
+        H = C.CDLL(LIB_HOST)
+        vp = C.c_void_p
+        H.aaadmm_host_last_error.restype = C.c_char_p
+        H.aaadmm_host_beam_new.restype = vp
+        H.aaadmm_host_beam_free.argtypes = [vp]
+        H.aaadmm_host_beam_add.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
+        H.aaadmm_host_beam_counts.argtypes = [vp, c_ip, c_ip, c_ip]
+        H.aaadmm_host_beam_copy.argtypes = [vp, c_fp, c_ip, c_fp, c_ip, c_dp, c_ip]
+        H.aaadmm_host_beam_stretch.argtypes = [vp, C.c_double]
+        H.aaadmm_host_factor_new.restype = vp
+        H.aaadmm_host_factor_new.argtypes = [C.c_int, c_lp, c_ip, c_dp, c_dp, C.c_int, C.c_int]
+        H.aaadmm_host_factor_free.argtypes = [vp]
+        H.aaadmm_host_factor_nnz.restype = C.c_int64
+        H.aaadmm_host_factor_nnz.argtypes = [vp]
+        H.aaadmm_host_factor_copy.argtypes = [vp, c_lp, c_ip, c_dp, c_dp, c_ip]
+        H.aaadmm_host_factor_solve.argtypes = [vp, c_dp, c_dp, C.c_int]
+        H.aaadmm_host_factor_stats.argtypes = [vp, c_dp]
+        H.aaadmm_host_solver_new.restype = vp
+        H.aaadmm_host_solver_free.argtypes = [vp]
+        H.aaadmm_host_solver_add_tetmesh.argtypes = [vp, c_fp, C.c_int, c_ip, C.c_int, c_fp, C.c_double, C.c_double, C.c_int]
+        H.aaadmm_host_solver_set_pins.argtypes = [vp, c_ip, c_dp, C.c_int]
+        H.aaadmm_host_solver_initialize.argtypes = [vp, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
+                                                    C.c_int, C.c_int]
+        H.aaadmm_host_solver_step.argtypes = [vp]
+        H.aaadmm_host_solver_set_iters.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        H.aaadmm_host_solver_n_dof.argtypes = [vp]
+        H.aaadmm_host_solver_get_x.argtypes = [vp, c_dp]
+        H.aaadmm_host_solver_get_v.argtypes = [vp, c_dp]
+        H.aaadmm_host_solver_hist_rows.argtypes = [vp]
+        H.aaadmm_host_solver_hist_copy.argtypes = [vp, c_dp, c_dp, c_ip]
+        H.aaadmm_host_solver_info.argtypes = [vp, c_dp]
+        H.aaadmm_host_solver_factor_info.argtypes = [vp, c_dp]
+        H.aaadmm_host_solver_device_scene.restype = vp
+        H.aaadmm_host_solver_device_scene.argtypes = [vp]
+        H.aaadmm_host_solver_device_factor.restype = vp
+        H.aaadmm_host_solver_device_factor.argtypes = [vp]
+        H.aaadmm_host_tet_constants.argtypes = [c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp]
+        _host = H
+    return _host
+
+
+def _ck(rc):
+    if rc != 0:
+        raise AaadmmError(cuda_lib().aaadmm_last_error().decode() or "aaadmm call failed (%d)" % rc)
+
+
+def _hk(rc):
+    if rc != 0:
+        msg = host_lib().aaadmm_host_last_error().decode()
+        raise AaadmmError(msg or cuda_lib().aaadmm_last_error().decode() or "host call failed (%d)" % rc)
+
+
+def device_count():
+    return cuda_lib().aaadmm_device_count()
+
+
+def set_device(i):
+    _ck(cuda_lib().aaadmm_set_device(int(i)))
+
+
+# ---------------------------------------------------------------------------------------------
+class AndersonAcceleration:
+    """Device Anderson accelerator with the reference's variant-H interface
+    (hard/src/AndersonAcceleration.h): ctor(m,total_dim,effective_dim), init/reset/replace/compute.
+    Variant X (xzu) is the same object with effective_dim == total_dim."""
+
+    def __init__(self, m, total_dim, effective_dim=None):
+        self.L = cuda_lib()
+        self.n = int(total_dim)
+        self.h = C.c_void_p()
+        _ck(self.L.aaadmm_aa_create(C.byref(self.h), int(m), self.n,
+                                    int(total_dim if effective_dim is None else effective_dim)))
+
+    def close(self):
+        if self.h:
+            self.L.aaadmm_aa_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _vec(self, u):
+        return np.ascontiguousarray(u, np.float64).reshape(-1)
+
+    def init(self, u):
+        u = self._vec(u)
+        _ck(self.L.aaadmm_aa_init(self.h, _dp(u), u.size))
+
+    def reset(self, u):
+        u = self._vec(u)
+        _ck(self.L.aaadmm_aa_reset(self.h, _dp(u), u.size))
+
+    def replace(self, u):
+        u = self._vec(u)
+        _ck(self.L.aaadmm_aa_replace(self.h, _dp(u), u.size))
+
+    def compute(self, g):
+        g = self._vec(g)
+        out = np.empty_like(g)
+        _ck(self.L.aaadmm_aa_compute(self.h, _dp(g), _dp(out), g.size))
+        return out
+
+    def state(self):
+        it, col = C.c_int(), C.c_int()
+        _ck(self.L.aaadmm_aa_state(self.h, C.byref(it), C.byref(col)))
+        return it.value, col.value
+
+
+class Ldlt:
+    """Device-resident LDL^T factor (strictly-lower CSC L, D, perm[new]=old)."""
+
+    def __init__(self, n, Lp, Li, Lx, D, perm, nrhs=3):
+        self.L = cuda_lib()
+        self.n, self.nrhs = int(n), int(nrhs)
+        Lp = np.ascontiguousarray(Lp, np.int64)
+        Li = np.ascontiguousarray(Li, np.int32)
+        Lx = np.ascontiguousarray(Lx, np.float64)
+        D = np.ascontiguousarray(D, np.float64)
+        perm = np.ascontiguousarray(perm, np.int32)
+        self.h = C.c_void_p()
+        _ck(self.L.aaadmm_ldlt_create(C.byref(self.h), self.n, _lp(Lp), _ip(Li), _dp(Lx), _dp(D), _ip(perm), self.nrhs))
+
+    def close(self):
+        if self.h:
+            self.L.aaadmm_ldlt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve(self, b):
+        b = np.ascontiguousarray(b, np.float64).reshape(-1)
+        assert b.size == self.n * self.nrhs
+        x = np.empty_like(b)
+        _ck(self.L.aaadmm_ldlt_solve(self.h, _dp(b), _dp(x)))
+        return x
+
+    def stats(self):
+        s = np.zeros(8)
+        _ck(self.L.aaadmm_ldlt_stats(self.h, _dp(s)))
+        return dict(n=int(s[0]), blocks=int(s[1]), levels=int(s[2]), max_block=int(s[3]), nnz_L=int(s[4]),
+                    nnz_offblock=int(s[5]), dense_diag_entries=int(s[6]), bytes_per_solve=float(s[7]))
+
+
+def tet_prox_linear(z):
+    z = np.ascontiguousarray(z, np.float64).copy()
+    _ck(cuda_lib().aaadmm_tet_prox_linear(_dp(z), z.shape[0]))
+    return z
+
+
+def tet_f_minus_uvt(z):
+    z = np.ascontiguousarray(z, np.float64)
+    out = np.empty_like(z)
+    _ck(cuda_lib().aaadmm_tet_f_minus_uvt(_dp(z), _dp(out), z.shape[0]))
+    return out
+
+
+def cod_solve(M, rhs):
+    M = np.asfortranarray(M, np.float64)
+    rhs = np.ascontiguousarray(rhs, np.float64)
+    x = np.zeros_like(rhs)
+    rank = C.c_int()
+    _ck(cuda_lib().aaadmm_cod_solve(M.shape[0], M.ctypes.data_as(c_dp), _dp(rhs), _dp(x), C.byref(rank)))
+    return x, rank.value
+
+
+# ---------------------------------------------------------------------------------------------
+class HostFactor:
+    """Nested-dissection + multifrontal LDL^T computed on the host (setup)."""
+
+    def __init__(self, n, Ap, Ai, Ax, coords=None, leaf_size=96, n_threads=0):
+        self.H = host_lib()
+        Ap = np.ascontiguousarray(Ap, np.int64)
+        Ai = np.ascontiguousarray(Ai, np.int32)
+        Ax = np.ascontiguousarray(Ax, np.float64)
+        cp = None
+        if coords is not None:
+            coords = np.ascontiguousarray(coords, np.float64)
+            cp = _dp(coords)
+        self.n = int(n)
+        self.h = self.H.aaadmm_host_factor_new(self.n, _lp(Ap), _ip(Ai), _dp(Ax), cp, leaf_size, n_threads)
+        if not self.h:
+            raise AaadmmError(self.H.aaadmm_host_last_error().decode())
+        self.h = C.c_void_p(self.h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.H.aaadmm_host_factor_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def arrays(self):
+        nnz = self.H.aaadmm_host_factor_nnz(self.h)
+        Lp = np.zeros(self.n + 1, np.int64)
+        Li = np.zeros(nnz, np.int32)
+        Lx = np.zeros(nnz)
+        D = np.zeros(self.n)
+        perm = np.zeros(self.n, np.int32)
+        self.H.aaadmm_host_factor_copy(self.h, _lp(Lp), _ip(Li), _dp(Lx), _dp(D), _ip(perm))
+        return Lp, Li, Lx, D, perm
+
+    def solve(self, b, nrhs=1):
+        b = np.ascontiguousarray(b, np.float64).reshape(-1)
+        x = np.zeros_like(b)
+        self.H.aaadmm_host_factor_solve(self.h, _dp(b), _dp(x), nrhs)
+        return x
+
+    def stats(self):
+        s = np.zeros(6)
+        self.H.aaadmm_host_factor_stats(self.h, _dp(s))
+        return dict(supernodes=int(s[0]), flops=s[1], seconds_symbolic=s[3], seconds_numeric=s[4], nnz_L=int(s[5]))
+
+
+class BeamScene:
+    """Beams of the reference's samples (make_tet_blocks + centre/scale + pins), O(n)."""
+
+    def __init__(self):
+        self.H = host_lib()
+        self.h = C.c_void_p(self.H.aaadmm_host_beam_new())
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.H.aaadmm_host_beam_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def add(self, cx, cy, cz, y_shift=0.0, density=1522.0):
+        _hk(0 if self.H.aaadmm_host_beam_add(self.h, cx, cy, cz, y_shift, density) >= 0 else -1)
+        return self
+
+    def counts(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self.H.aaadmm_host_beam_counts(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def arrays(self):
+        nv, nt, npin = self.counts()
+        verts = np.zeros((nv, 3), np.float32)
+        tets = np.zeros((nt, 4), np.int32)
+        masses = np.zeros(nv, np.float32)
+        pidx = np.zeros(npin, np.int32)
+        ppts = np.zeros((npin, 3))
+        pside = np.zeros(npin, np.int32)
+        self.H.aaadmm_host_beam_copy(self.h, _fp(verts), _ip(tets), _fp(masses), _ip(pidx), _dp(ppts), _ip(pside))
+        return verts, tets, masses, pidx, ppts, pside
+
+    def stretch(self, dt):
+        """stretch_beams(): returns the new pin targets."""
+        self.H.aaadmm_host_beam_stretch(self.h, dt)
+        return self.arrays()[4]
+
+
+class Solver:
+    """admm::Solver mirror (host C++ class over the C ABI)."""
+
+    def __init__(self):
+        self.H = host_lib()
+        self.h = C.c_void_p(self.H.aaadmm_host_solver_new())
+
+    def close(self):
+        if self.h:
+            self.H.aaadmm_host_solver_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_tetmesh(self, verts, tets, masses, youngs=1e7, poisson=0.399, material=0):
+        verts = np.ascontiguousarray(verts, np.float32)
+        tets = np.ascontiguousarray(tets, np.int32)
+        masses = np.ascontiguousarray(masses, np.float32)
+        r = self.H.aaadmm_host_solver_add_tetmesh(self.h, _fp(verts), len(verts), _ip(tets), len(tets), _fp(masses),
+                                                  youngs, poisson, material)
+        if r < 0:
+            _hk(r)
+        return r
+
+    def set_pins(self, idx, pts):
+        idx = np.ascontiguousarray(idx, np.int32)
+        pts = np.ascontiguousarray(pts, np.float64)
+        _hk(self.H.aaadmm_host_solver_set_pins(self.h, _ip(idx), _dp(pts), len(idx)))
+
+    def initialize(self, dt=1.0 / 30.0, iters=100, gravity=-9.8, anderson_m=5, accel=True, penalty=1.0,
+                   ordering=ORDER_HARD_ZXU, nd_leaf=0):
+        _hk(self.H.aaadmm_host_solver_initialize(self.h, dt, iters, gravity, anderson_m, int(bool(accel)), penalty,
+                                                 ordering, nd_leaf))
+
+    def set_iters(self, iters, anderson_m, accel):
+        self.H.aaadmm_host_solver_set_iters(self.h, iters, anderson_m, int(bool(accel)))
+
+    def step(self):
+        """One Solver::step(); returns rows (prim_residual, comb_residual, is_reject)."""
+        _hk(self.H.aaadmm_host_solver_step(self.h))
+        n = self.H.aaadmm_host_solver_hist_rows(self.h)
+        prim, comb, rej = np.zeros(max(n, 1)), np.zeros(max(n, 1)), np.zeros(max(n, 1), np.int32)
+        if n:
+            self.H.aaadmm_host_solver_hist_copy(self.h, _dp(prim), _dp(comb), _ip(rej))
+        return np.stack([prim[:n], comb[:n], rej[:n].astype(np.float64)], axis=1)
+
+    def x(self):
+        out = np.zeros(self.H.aaadmm_host_solver_n_dof(self.h))
+        self.H.aaadmm_host_solver_get_x(self.h, _dp(out))
+        return out
+
+    def v(self):
+        out = np.zeros(self.H.aaadmm_host_solver_n_dof(self.h))
+        self.H.aaadmm_host_solver_get_v(self.h, _dp(out))
+        return out
+
+    def info(self):
+        s = np.zeros(8)
+        self.H.aaadmm_host_solver_info(self.h, _dp(s))
+        return dict(loop_ms=s[0], step_ms=s[1], kernel_launches=int(s[2]), init_ms=s[3], iter_num=int(s[4]),
+                    rejects=int(s[5]), n_free=int(s[6]), n_tets=int(s[7]))
+
+    def factor_info(self):
+        s = np.zeros(6)
+        self.H.aaadmm_host_solver_factor_info(self.h, _dp(s))
+        return dict(nnz_L=int(s[0]), supernodes=int(s[1]), flops=s[2], seconds_symbolic=s[3], seconds_numeric=s[4],
+                    nnz_A_lower=int(s[5]))
+
+    def ldlt_stats(self):
+        L = cuda_lib()
+        f = C.c_void_p(self.H.aaadmm_host_solver_device_factor(self.h))
+        s = np.zeros(8)
+        _ck(L.aaadmm_ldlt_stats(f, _dp(s)))
+        return dict(n=int(s[0]), blocks=int(s[1]), levels=int(s[2]), max_block=int(s[3]), nnz_L=int(s[4]),
+                    nnz_offblock=int(s[5]), dense_diag_entries=int(s[6]), bytes_per_solve=float(s[7]))
+
+    # --- measurement helpers over the device scene of this solver ---
+    def _scene(self):
+        return C.c_void_p(self.H.aaadmm_host_solver_device_scene(self.h))
+
+    def step_resident(self, iters, anderson_m=5, accel=True, ordering=ORDER_HARD_ZXU, eps=1e-20):
+        o = StepOpts(ordering, iters, anderson_m, int(bool(accel)), eps, 1)
+        r = StepResult()
+        _ck(cuda_lib().aaadmm_tetscene_step_resident(self._scene(), C.byref(o), C.byref(r)))
+        return dict(iters_logged=r.iters_logged, rejects=r.rejects, broke_early=r.broke_early, loop_ms=r.loop_ms,
+                    step_ms=r.step_ms, kernel_launches=r.kernel_launches)
+
+    def profile(self, iters, anderson_m=5, accel=True, ordering=ORDER_HARD_ZXU):
+        o = StepOpts(ordering, iters, anderson_m, int(bool(accel)), 1e-20, 1)
+        ms = np.zeros(NPROF, np.float32)
+        _ck(cuda_lib().aaadmm_tetscene_profile(self._scene(), C.byref(o), iters, _fp(ms)))
+        by = np.zeros(NPROF)
+        _ck(cuda_lib().aaadmm_tetscene_algo_bytes(self._scene(), anderson_m, _dp(by)))
+        return {n: dict(ms=float(ms[i]), bytes=float(by[i])) for i, n in enumerate(PROF_NAMES)}
+
+
+def make_beam_solver(cx, cy, cz, n_beams=1, dt=1.0 / 30.0, iters=100, anderson_m=5, accel=True, penalty=1.0,
+                     ordering=ORDER_HARD_ZXU, youngs=1e7, poisson=0.399, gravity=-9.8):
+    """The beams.cpp scene with LINEAR tets: returns (solver, scene). Pins are stretched once
+    before initialize, as beams.cpp:126 does."""
+    scene = BeamScene()
+    shifts = {1: [0.0], 3: [1.75, 0.0, -1.75]}.get(n_beams, [1.75 * (n_beams // 2 - i) for i in range(n_beams)])
+    for s in shifts:
+        scene.add(cx, cy, cz, s)
+    verts, tets, masses, pidx, ppts, pside = scene.arrays()
+    solver = Solver()
+    solver.add_tetmesh(verts, tets, masses, youngs, poisson, 0)
+    solver.set_pins(pidx, scene.stretch(dt))
+    solver.initialize(dt, iters, gravity, anderson_m, accel, penalty, ordering)
+    return solver, scene

@@ -1,0 +1,161 @@
+// Anderson mixing on the device (K8-K11 of SURVEY 2b), two streaming passes per call.
+//
+// Restates AndersonAcceleration::compute_impl (hard/src/AndersonAcceleration.h:154-211; variant X:
+// xzu/src/AndersonAcceleration.h:138-200) with the history kept RAW in HBM:
+//   the reference normalises the newest dF column in place (dF(:,c) /= scale) and keeps the
+//   normalised columns; here the columns stay unscaled and the scales live in the m x m Gram
+//   matrix instead:  M(c,j) = <dF_c,dF_j>/(s_c s_j),  rhs_j = <dF_j,F>/s_j  - the same numbers
+//   up to rounding, one full read+write pass over the Ne x 1 column cheaper.  As in the
+//   reference only the row/column of the newest column is refreshed per call.
+//   pass 1: F = G - u_cur (effective part); dF(:,c) += F; dG(:,c) += G; all 2 m_k dot products
+//           in the same pass (warp shuffle -> CTA -> fixed-order last-CTA reduction); the last
+//           CTA then solves the m_k x m_k system in one thread (cod_small.cuh).
+//   pass 2: u_cur = G - dG(:,0:mk) (theta./scale); start the next column with -F / -G.
+#pragma once
+#include "cod_small.cuh"
+#include "common.cuh"
+
+namespace aaadmm {
+
+constexpr int AA_BLOCK = 256;
+
+// Runs in thread 0 of the finishing CTA of pass 1. acc[0..M) = <dF_c, dF_j> (acc[c] = |dF_c|^2),
+// acc[M..2M) = <dF_j, F>, all raw.
+template <int M>
+__device__ void aa_finish(SolveState *st, const double *acc) {
+    const int iter = st->aa_iter, c = st->aa_col, m = st->aa_m;
+    if (iter == 0) {
+        st->aa_mk = 0;
+        st->aa_iter = 1;
+        return;
+    }
+    const double eps = 1e-14;
+    const int mk = iter < m ? iter : m;
+    const double nrm2 = acc[c];
+    const double scale = fmax(eps, sqrt(nrm2));
+    st->aa_scale[c] = scale;
+    double theta[AA_MAX_M];
+    if (mk == 1) {
+        theta[0] = 0.0;
+        const double sq = nrm2 / (scale * scale);
+        st->aa_M[0] = sq;
+        const double dF_norm = sqrt(sq);
+        if (dF_norm > eps) theta[0] = ((acc[M + c] / scale) / dF_norm) / dF_norm;
+    } else {
+        double A[AA_MAX_M * AA_MAX_M], rhs[AA_MAX_M];
+        for (int j = 0; j < mk; ++j) {
+            const double g = (j == c) ? nrm2 / (scale * scale) : acc[j] / (scale * st->aa_scale[j]);
+            st->aa_M[c * AA_MAX_M + j] = g;
+            st->aa_M[j * AA_MAX_M + c] = g;
+        }
+        for (int j = 0; j < mk; ++j) {
+            rhs[j] = acc[M + j] / st->aa_scale[j];
+            for (int i = 0; i < mk; ++i) A[j * mk + i] = st->aa_M[j * AA_MAX_M + i];
+        }
+        cod_solve(A, mk, rhs, theta);
+    }
+    for (int j = 0; j < mk; ++j) st->aa_coef[j] = theta[j] / st->aa_scale[j];
+    st->aa_mk = mk;
+    st->aa_col = (c + 1) % m;
+    st->aa_iter = iter + 1;
+}
+
+// G = [g_u (Ne) | g_x (Nt-Ne)]; when gx_dst != nullptr the x part is also copied there
+// (the solver hands the fresh solve result in and keeps it as default_x).
+template <int M>
+__global__ void __launch_bounds__(AA_BLOCK)
+k_aa_pass1(const double *__restrict__ g_u, const double *__restrict__ g_x, double *__restrict__ gx_dst,
+           double *__restrict__ ucur, double *__restrict__ dF, double *__restrict__ dG, int64_t Ne, int64_t Nt,
+           SolveState *st, double *partials) {
+    if (st->done) return;
+    const int iter = st->aa_iter, c = st->aa_col, m = st->aa_m;
+    const int64_t stride = (int64_t)gridDim.x * AA_BLOCK;
+    const int64_t i0 = (int64_t)blockIdx.x * AA_BLOCK + threadIdx.x;
+    if (iter == 0) {
+        for (int64_t i = i0; i < Nt; i += stride) {
+            double g;
+            if (i < Ne) {
+                g = g_u[i];
+                dF[i] = -(g - ucur[i]);
+            } else {
+                g = g_x[i - Ne];
+                if (gx_dst) gx_dst[i - Ne] = g;
+            }
+            dG[i] = -g;
+            ucur[i] = g;
+        }
+        // state changes only after every CTA has read it: last-CTA election as in grid_reduce
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int t = atomicAdd(&st->ticket, 1u);
+            if (t == gridDim.x - 1) {
+                st->ticket = 0u;
+                aa_finish<M>(st, nullptr);
+            }
+        }
+        return;
+    }
+    const int mk = iter < m ? iter : m;
+    double acc[2 * M];
+#pragma unroll
+    for (int q = 0; q < 2 * M; ++q) acc[q] = 0.0;
+    double *dFc = dF + (size_t)c * Ne;
+    double *dGc = dG + (size_t)c * Nt;
+    for (int64_t i = i0; i < Ne; i += stride) {
+        const double g = g_u[i];
+        const double F = g - ucur[i];
+        const double a = dFc[i] + F;
+        dFc[i] = a;
+        dGc[i] += g;
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            if (j < mk) {
+                const double v = (j == c) ? a : dF[(size_t)j * Ne + i];
+                acc[j] += a * v;
+                acc[M + j] += v * F;
+            }
+        }
+    }
+    for (int64_t i = Ne + i0; i < Nt; i += stride) {
+        const double g = g_x[i - Ne];
+        if (gx_dst) gx_dst[i - Ne] = g;
+        dGc[i] += g;
+    }
+    double out[2 * M];
+    if (grid_reduce<2 * M, AA_BLOCK>(acc, partials, &st->ticket, out)) {
+        if (threadIdx.x == 0) aa_finish<M>(st, out);
+    }
+}
+
+template <int M>
+__global__ void __launch_bounds__(AA_BLOCK)
+k_aa_pass2(const double *__restrict__ g_u, const double *__restrict__ g_x, double *__restrict__ ucur,
+           double *__restrict__ dF, double *__restrict__ dG, int64_t Ne, int64_t Nt, const SolveState *st) {
+    if (st->done) return;
+    const int mk = st->aa_mk;
+    if (mk == 0) return;
+    const int cn = st->aa_col;  // already advanced by pass 1
+    double coef[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) coef[j] = (j < mk) ? st->aa_coef[j] : 0.0;
+    const int64_t stride = (int64_t)gridDim.x * AA_BLOCK;
+    for (int64_t i = (int64_t)blockIdx.x * AA_BLOCK + threadIdx.x; i < Nt; i += stride) {
+        const double g = (i < Ne) ? g_u[i] : g_x[i - Ne];
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+            if (j < mk) s += dG[(size_t)j * Nt + i] * coef[j];
+        if (i < Ne) dF[(size_t)cn * Ne + i] = -(g - ucur[i]);
+        dG[(size_t)cn * Nt + i] = -g;
+        ucur[i] = g - s;
+    }
+}
+
+// Host-side dispatch on the window size m (compile-time accumulator count).
+int launch_aa_pass1(int m, int grid, cudaStream_t s, const double *g_u, const double *g_x, double *gx_dst,
+                    double *ucur, double *dF, double *dG, int64_t Ne, int64_t Nt, SolveState *st, double *partials);
+int launch_aa_pass2(int m, int grid, cudaStream_t s, const double *g_u, const double *g_x, double *ucur,
+                    double *dF, double *dG, int64_t Ne, int64_t Nt, const SolveState *st);
+
+}  // namespace aaadmm

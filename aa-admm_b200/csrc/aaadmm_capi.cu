@@ -1,0 +1,783 @@
+// C ABI of libaaadmm_b200.so (include/aaadmm.h): handle management and the stream-ordered
+// launch sequences of the ADMM loops.  All numerics live in the kernels
+// (tet_kernels.cuh, aa_kernels.cuh, ldlt_apply.cu); nothing here computes on the host.
+#include "../../include/aaadmm.h"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "aa_kernels.cuh"
+#include "common.cuh"
+#include "ldlt_apply.cuh"
+#include "tet_kernels.cuh"
+
+namespace aaadmm {
+
+static thread_local std::string g_err;
+void set_last_error(const std::string &msg) { g_err = msg; }
+
+int sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaDeviceProp p;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess)
+            sms = p.multiProcessorCount;
+        else
+            sms = 148;
+    }
+    return sms;
+}
+int stream_grid(int ctas_per_sm) { return std::min(RED_MAX_BLOCKS, sm_count() * ctas_per_sm); }
+
+#define AA_DISPATCH(m, CALL)                 \
+    switch (m) {                             \
+        case 1: { constexpr int MM = 1; CALL; } break;  \
+        case 2: { constexpr int MM = 2; CALL; } break;  \
+        case 3: { constexpr int MM = 3; CALL; } break;  \
+        case 4: { constexpr int MM = 4; CALL; } break;  \
+        case 5: { constexpr int MM = 5; CALL; } break;  \
+        case 6: { constexpr int MM = 6; CALL; } break;  \
+        case 7: { constexpr int MM = 7; CALL; } break;  \
+        case 8: { constexpr int MM = 8; CALL; } break;  \
+        default: { constexpr int MM = AA_MAX_M; CALL; } break; \
+    }
+
+int launch_aa_pass1(int m, int grid, cudaStream_t s, const double *g_u, const double *g_x, double *gx_dst,
+                    double *ucur, double *dF, double *dG, int64_t Ne, int64_t Nt, SolveState *st, double *partials) {
+    AA_DISPATCH(m, (k_aa_pass1<MM><<<grid, AA_BLOCK, 0, s>>>(g_u, g_x, gx_dst, ucur, dF, dG, Ne, Nt, st, partials)));
+    AAADMM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int launch_aa_pass2(int m, int grid, cudaStream_t s, const double *g_u, const double *g_x, double *ucur,
+                    double *dF, double *dG, int64_t Ne, int64_t Nt, const SolveState *st) {
+    AA_DISPATCH(m, (k_aa_pass2<MM><<<grid, AA_BLOCK, 0, s>>>(g_u, g_x, ucur, dF, dG, Ne, Nt, st)));
+    AAADMM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+__global__ void k_prox_batch(double *z, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double zi[9];
+    for (int k = 0; k < 9; ++k) zi[k] = z[9 * i + k];
+    tet_prox_linear(zi);
+    for (int k = 0; k < 9; ++k) z[9 * i + k] = zi[k];
+}
+__global__ void k_fmuvt_batch(const double *z, double *out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double zi[9], g[9];
+    for (int k = 0; k < 9; ++k) zi[k] = z[9 * i + k];
+    tet_grad_linear(zi, 1.0, g);
+    for (int k = 0; k < 9; ++k) out[9 * i + k] = g[k];
+}
+__global__ void k_cod(int m, const double *M, const double *rhs, double *x, int *rank) {
+    double A[AA_MAX_M * AA_MAX_M], b[AA_MAX_M], xx[AA_MAX_M];
+    for (int i = 0; i < m * m; ++i) A[i] = M[i];
+    for (int i = 0; i < m; ++i) b[i] = rhs[i];
+    *rank = cod_solve(A, m, b, xx);
+    for (int i = 0; i < m; ++i) x[i] = xx[i];
+}
+
+// AoS (9 consecutive doubles per tet, reference layout) <-> SoA planes
+__global__ void k_soa_to_aos9(const double *__restrict__ soa, double *__restrict__ aos, int T) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    for (int k = 0; k < 9; ++k) aos[9 * (size_t)t + k] = soa[(size_t)k * T + t];
+}
+
+__global__ void k_init_state(SolveState *st, int accel, int m, double eps) {
+    st->prim2 = 0.0;
+    st->prev_prim = 1e+20;
+    st->comb = 0.0;
+    st->eps = eps;
+    st->reject = 0;
+    st->done = 0;
+    st->iter = 0;
+    st->n_rejects = 0;
+    st->accel = accel;
+    st->aa_iter = 0;
+    st->aa_col = 0;
+    st->aa_m = m;
+    st->aa_mk = 0;
+    st->ticket = 0u;
+}
+__global__ void k_aa_set_counters(SolveState *st, int iter, int col) {
+    st->aa_iter = iter;
+    st->aa_col = col;
+}
+
+}  // namespace aaadmm
+
+using namespace aaadmm;
+
+#define API_TRY_BEGIN try {
+#define API_TRY_END                                     \
+    }                                                   \
+    catch (const std::exception &e) {                   \
+        set_last_error(std::string("exception: ") + e.what()); \
+        return -2;                                      \
+    }
+
+struct aaadmm_aa {
+    int m = 0;
+    int64_t Nt = 0, Ne = 0;
+    double *ucur = nullptr, *dF = nullptr, *dG = nullptr, *partials = nullptr, *gtmp = nullptr;
+    SolveState *st = nullptr;
+    cudaStream_t stream = nullptr;
+    int grid = 0;
+};
+
+struct aaadmm_ldlt {
+    LdltDev *f = nullptr;
+    cudaStream_t stream = nullptr;
+    double *b_dev = nullptr, *x_dev = nullptr;
+};
+
+struct aaadmm_tetscene {
+    int T = 0, V = 0, NF = 0, NP = 0;
+    double rho_dt2 = 0;
+    aaadmm_ldlt *factor = nullptr;
+    cudaStream_t stream = nullptr;
+    // constants
+    int4 *idx = nullptr;
+    double *binv = nullptr, *w = nullptr, *kvol = nullptr, *mass = nullptr;
+    int64_t *inc_ptr = nullptr;
+    int *inc = nullptr;
+    // state
+    int64_t Ne = 0, Nt = 0, Nbuf = 0;  // Nbuf = 9T + 3V (pinned tail rides along)
+    double *Ubuf = nullptr, *Gbuf = nullptr, *xs = nullptr, *z = nullptr, *contrib = nullptr;
+    double *bconst = nullptr, *xbar = nullptr, *xpin = nullptr;
+    double *dF = nullptr, *dG = nullptr;
+    int hist_cap = 0, m_cap = 0;
+    double *hist_prim = nullptr, *hist_comb = nullptr;
+    int *hist_rej = nullptr;
+    double *partials = nullptr;
+    SolveState *st = nullptr;
+    double *pin_h = nullptr, *xbar_h = nullptr, *xout_h = nullptr;  // pinned host staging
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int launches = 0;
+    bool has_inputs = false;
+};
+
+extern "C" {
+
+const char *aaadmm_last_error(void) { return g_err.c_str(); }
+
+int aaadmm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int aaadmm_set_device(int device) {
+    AAADMM_CUDA_OK(cudaSetDevice(device));
+    return 0;
+}
+int aaadmm_device_sms(void) { return sm_count(); }
+
+// ------------------------------------------------------------------------------------------
+// Anderson acceleration object
+// ------------------------------------------------------------------------------------------
+int aaadmm_aa_create(aaadmm_aa **out, int m, int64_t total_dim, int64_t effective_dim) {
+    API_TRY_BEGIN
+    if (m <= 0 || m > AA_MAX_M || total_dim <= 0 || effective_dim <= 0 || effective_dim > total_dim) {
+        set_last_error("aa_create: need 0 < m <= 16 and 0 < effective_dim <= total_dim");
+        return -1;
+    }
+    if (aaadmm_device_count() <= 0) {
+        set_last_error("aa_create: no CUDA device (this library has no CPU path)");
+        return -1;
+    }
+    aaadmm_aa *a = new aaadmm_aa();
+    a->m = m;
+    a->Nt = total_dim;
+    a->Ne = effective_dim;
+    a->grid = stream_grid(4);
+    AAADMM_CUDA_OK(cudaStreamCreate(&a->stream));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&a->ucur, sizeof(double) * total_dim));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&a->gtmp, sizeof(double) * total_dim));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&a->dF, sizeof(double) * effective_dim * m));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&a->dG, sizeof(double) * total_dim * m));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&a->partials, sizeof(double) * RED_MAX_Q * RED_MAX_BLOCKS));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&a->st, sizeof(SolveState)));
+    AAADMM_CUDA_OK(cudaMemsetAsync(a->st, 0, sizeof(SolveState), a->stream));
+    AAADMM_CUDA_OK(cudaMemsetAsync(a->dF, 0, sizeof(double) * effective_dim * m, a->stream));
+    AAADMM_CUDA_OK(cudaMemsetAsync(a->dG, 0, sizeof(double) * total_dim * m, a->stream));
+    k_init_state<<<1, 1, 0, a->stream>>>(a->st, 1, m, 0.0);
+    k_aa_set_counters<<<1, 1, 0, a->stream>>>(a->st, -1, -1);
+    AAADMM_CUDA_OK(cudaStreamSynchronize(a->stream));
+    *out = a;
+    return 0;
+    API_TRY_END
+}
+
+int aaadmm_aa_destroy(aaadmm_aa *a) {
+    if (!a) return 0;
+    cudaFree(a->ucur);
+    cudaFree(a->gtmp);
+    cudaFree(a->dF);
+    cudaFree(a->dG);
+    cudaFree(a->partials);
+    cudaFree(a->st);
+    if (a->stream) cudaStreamDestroy(a->stream);
+    delete a;
+    return 0;
+}
+
+static int aa_set_u(aaadmm_aa *a, const double *u, int64_t n, bool host, bool reset_counters) {
+    if (n != a->Nt) {
+        set_last_error("aa: vector size != total_dim");
+        return -1;
+    }
+    AAADMM_CUDA_OK(cudaMemcpyAsync(a->ucur, u, sizeof(double) * n, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                                   a->stream));
+    if (reset_counters) k_aa_set_counters<<<1, 1, 0, a->stream>>>(a->st, 0, 0);
+    AAADMM_CUDA_OK(cudaStreamSynchronize(a->stream));
+    return 0;
+}
+int aaadmm_aa_init(aaadmm_aa *a, const double *u, int64_t n) { return aa_set_u(a, u, n, true, true); }
+int aaadmm_aa_reset(aaadmm_aa *a, const double *u, int64_t n) { return aa_set_u(a, u, n, true, true); }
+int aaadmm_aa_replace(aaadmm_aa *a, const double *u, int64_t n) { return aa_set_u(a, u, n, true, false); }
+int aaadmm_aa_init_dev(aaadmm_aa *a, const double *u, int64_t n) { return aa_set_u(a, u, n, false, true); }
+int aaadmm_aa_reset_dev(aaadmm_aa *a, const double *u, int64_t n) { return aa_set_u(a, u, n, false, true); }
+int aaadmm_aa_replace_dev(aaadmm_aa *a, const double *u, int64_t n) { return aa_set_u(a, u, n, false, false); }
+
+static int aa_compute_impl(aaadmm_aa *a, const double *d_g, double *accel, int64_t n, bool host_out) {
+    if (n != a->Nt) {
+        set_last_error("aa_compute: vector size != total_dim");
+        return -1;
+    }
+    if (launch_aa_pass1(a->m, a->grid, a->stream, d_g, d_g + a->Ne, nullptr, a->ucur, a->dF, a->dG, a->Ne, a->Nt, a->st,
+                        a->partials))
+        return -1;
+    if (launch_aa_pass2(a->m, a->grid, a->stream, d_g, d_g + a->Ne, a->ucur, a->dF, a->dG, a->Ne, a->Nt, a->st))
+        return -1;
+    AAADMM_CUDA_OK(cudaMemcpyAsync(accel, a->ucur, sizeof(double) * n,
+                                   host_out ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, a->stream));
+    AAADMM_CUDA_OK(cudaStreamSynchronize(a->stream));
+    return 0;
+}
+int aaadmm_aa_compute(aaadmm_aa *a, const double *g, double *accel_u, int64_t n) {
+    if (n != a->Nt) {
+        set_last_error("aa_compute: vector size != total_dim");
+        return -1;
+    }
+    AAADMM_CUDA_OK(cudaMemcpyAsync(a->gtmp, g, sizeof(double) * n, cudaMemcpyHostToDevice, a->stream));
+    return aa_compute_impl(a, a->gtmp, accel_u, n, true);
+}
+int aaadmm_aa_compute_dev(aaadmm_aa *a, const double *d_g, double *d_accel_u, int64_t n) {
+    return aa_compute_impl(a, d_g, d_accel_u, n, false);
+}
+int aaadmm_aa_state(aaadmm_aa *a, int *iter, int *col) {
+    SolveState h;
+    AAADMM_CUDA_OK(cudaMemcpy(&h, a->st, sizeof(SolveState), cudaMemcpyDeviceToHost));
+    if (iter) *iter = h.aa_iter;
+    if (col) *col = h.aa_col;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// LDL^T
+// ------------------------------------------------------------------------------------------
+int aaadmm_ldlt_create(aaadmm_ldlt **out, int n, const int64_t *Lp, const int *Li, const double *Lx,
+                       const double *D, const int *perm, int nrhs) {
+    API_TRY_BEGIN
+    if (aaadmm_device_count() <= 0) {
+        set_last_error("ldlt_create: no CUDA device (this library has no CPU path)");
+        return -1;
+    }
+    if (n <= 0 || !Lp || !D || !perm) {
+        set_last_error("ldlt_create: bad arguments");
+        return -1;
+    }
+    aaadmm_ldlt *h = new aaadmm_ldlt();
+    if (ldlt_dev_create(&h->f, n, Lp, Li, Lx, D, perm, nrhs)) {
+        delete h;
+        return -1;
+    }
+    AAADMM_CUDA_OK(cudaStreamCreate(&h->stream));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&h->b_dev, sizeof(double) * n * nrhs));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&h->x_dev, sizeof(double) * n * nrhs));
+    *out = h;
+    return 0;
+    API_TRY_END
+}
+int aaadmm_ldlt_destroy(aaadmm_ldlt *h) {
+    if (!h) return 0;
+    ldlt_dev_destroy(h->f);
+    cudaFree(h->b_dev);
+    cudaFree(h->x_dev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+int aaadmm_ldlt_solve_dev(aaadmm_ldlt *h, const double *d_b, double *d_x) {
+    if (ldlt_dev_apply(h->f, d_b, d_x, h->stream, nullptr)) return -1;
+    AAADMM_CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int aaadmm_ldlt_solve(aaadmm_ldlt *h, const double *b, double *x) {
+    const size_t bytes = sizeof(double) * (size_t)h->f->n * h->f->nrhs;
+    AAADMM_CUDA_OK(cudaMemcpyAsync(h->b_dev, b, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (ldlt_dev_apply(h->f, h->b_dev, h->x_dev, h->stream, nullptr)) return -1;
+    AAADMM_CUDA_OK(cudaMemcpyAsync(x, h->x_dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+    AAADMM_CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int aaadmm_ldlt_stats(aaadmm_ldlt *h, double *s) {
+    const LdltStats &t = h->f->stats;
+    s[0] = t.n;
+    s[1] = t.n_blocks;
+    s[2] = t.n_levels;
+    s[3] = t.max_block;
+    s[4] = (double)t.nnz_L;
+    s[5] = (double)t.nnz_offdiag;
+    s[6] = (double)t.nnz_diag_dense;
+    s[7] = t.bytes_per_solve;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Tet scene
+// ------------------------------------------------------------------------------------------
+int aaadmm_tetscene_destroy(aaadmm_tetscene *s) {
+    if (!s) return 0;
+    cudaFree(s->idx);
+    cudaFree(s->binv);
+    cudaFree(s->w);
+    cudaFree(s->kvol);
+    cudaFree(s->mass);
+    cudaFree(s->inc_ptr);
+    cudaFree(s->inc);
+    cudaFree(s->Ubuf);
+    cudaFree(s->Gbuf);
+    cudaFree(s->xs);
+    cudaFree(s->z);
+    cudaFree(s->contrib);
+    cudaFree(s->bconst);
+    cudaFree(s->xbar);
+    cudaFree(s->xpin);
+    cudaFree(s->dF);
+    cudaFree(s->dG);
+    cudaFree(s->hist_prim);
+    cudaFree(s->hist_comb);
+    cudaFree(s->hist_rej);
+    cudaFree(s->partials);
+    cudaFree(s->st);
+    if (s->pin_h) cudaFreeHost(s->pin_h);
+    if (s->xbar_h) cudaFreeHost(s->xbar_h);
+    if (s->xout_h) cudaFreeHost(s->xout_h);
+    for (auto &e : s->ev)
+        if (e) cudaEventDestroy(e);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return 0;
+}
+
+int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *d, aaadmm_ldlt *factor) {
+    API_TRY_BEGIN
+    if (aaadmm_device_count() <= 0) {
+        set_last_error("tetscene_create: no CUDA device (this library has no CPU path)");
+        return -1;
+    }
+    if (!d || !factor || d->n_tets <= 0 || d->n_free <= 0 || d->n_free > d->n_verts) {
+        set_last_error("tetscene_create: bad arguments");
+        return -1;
+    }
+    if (factor->f->n != d->n_free || factor->f->nrhs != 3) {
+        set_last_error("tetscene_create: factor must be n_free x n_free with nrhs = 3");
+        return -1;
+    }
+    if (d->material) {
+        for (int t = 0; t < d->n_tets; ++t)
+            if (d->material[t] != 0) {
+                set_last_error("tetscene_create: only LINEAR tets are implemented on the device in this round");
+                return -1;
+            }
+    }
+    aaadmm_tetscene *s = new aaadmm_tetscene();
+    const int T = d->n_tets, V = d->n_verts, NF = d->n_free;
+    s->T = T;
+    s->V = V;
+    s->NF = NF;
+    s->NP = V - NF;
+    s->rho_dt2 = d->rho_dt2;
+    s->factor = factor;
+    s->Ne = 9 * (int64_t)T;
+    s->Nt = s->Ne + 3 * (int64_t)NF;
+    s->Nbuf = s->Ne + 3 * (int64_t)V;
+    AAADMM_CUDA_OK(cudaStreamCreate(&s->stream));
+    for (auto &e : s->ev) AAADMM_CUDA_OK(cudaEventCreate(&e));
+    // constants: AoS -> SoA on the host once
+    std::vector<double> binv_soa((size_t)9 * T);
+    for (int t = 0; t < T; ++t)
+        for (int k = 0; k < 9; ++k) binv_soa[(size_t)k * T + t] = d->binv[9 * (size_t)t + k];
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->idx, sizeof(int4) * T));
+    AAADMM_CUDA_OK(cudaMemcpy(s->idx, d->tet, sizeof(int) * 4 * T, cudaMemcpyHostToDevice));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->binv, sizeof(double) * 9 * T));
+    AAADMM_CUDA_OK(cudaMemcpy(s->binv, binv_soa.data(), sizeof(double) * 9 * T, cudaMemcpyHostToDevice));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->w, sizeof(double) * T));
+    AAADMM_CUDA_OK(cudaMemcpy(s->w, d->weight, sizeof(double) * T, cudaMemcpyHostToDevice));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->kvol, sizeof(double) * T));
+    AAADMM_CUDA_OK(cudaMemcpy(s->kvol, d->kvol, sizeof(double) * T, cudaMemcpyHostToDevice));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->mass, sizeof(double) * NF));
+    AAADMM_CUDA_OK(cudaMemcpy(s->mass, d->mass_free, sizeof(double) * NF, cudaMemcpyHostToDevice));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->inc_ptr, sizeof(int64_t) * (NF + 1)));
+    AAADMM_CUDA_OK(cudaMemcpy(s->inc_ptr, d->inc_ptr, sizeof(int64_t) * (NF + 1), cudaMemcpyHostToDevice));
+    const int64_t ninc = d->inc_ptr[NF];
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->inc, sizeof(int) * std::max<int64_t>(ninc, 1)));
+    AAADMM_CUDA_OK(cudaMemcpy(s->inc, d->inc, sizeof(int) * ninc, cudaMemcpyHostToDevice));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->Ubuf, sizeof(double) * s->Nbuf));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->Gbuf, sizeof(double) * s->Nbuf));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->xs, sizeof(double) * 3 * V));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->z, sizeof(double) * 9 * T));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->contrib, sizeof(double) * 12 * T));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->bconst, sizeof(double) * 3 * NF));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->xbar, sizeof(double) * 3 * NF));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->xpin, sizeof(double) * 3 * std::max(1, s->NP)));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->partials, sizeof(double) * RED_MAX_Q * RED_MAX_BLOCKS));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->st, sizeof(SolveState)));
+    AAADMM_CUDA_OK(cudaMemset(s->st, 0, sizeof(SolveState)));
+    AAADMM_CUDA_OK(cudaMallocHost((void **)&s->pin_h, sizeof(double) * 3 * std::max(1, s->NP)));
+    AAADMM_CUDA_OK(cudaMallocHost((void **)&s->xbar_h, sizeof(double) * 3 * NF));
+    AAADMM_CUDA_OK(cudaMallocHost((void **)&s->xout_h, sizeof(double) * 3 * NF));
+    *out = s;
+    return 0;
+    API_TRY_END
+}
+
+static int scene_reserve(aaadmm_tetscene *s, int iters, int m) {
+    if (iters > s->hist_cap) {
+        cudaFree(s->hist_prim);
+        cudaFree(s->hist_comb);
+        cudaFree(s->hist_rej);
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->hist_prim, sizeof(double) * iters));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->hist_comb, sizeof(double) * iters));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->hist_rej, sizeof(int) * iters));
+        s->hist_cap = iters;
+    }
+    if (m > s->m_cap) {
+        cudaFree(s->dF);
+        cudaFree(s->dG);
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->dF, sizeof(double) * s->Ne * m));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->dG, sizeof(double) * s->Nt * m));
+        s->m_cap = m;
+    }
+    return 0;
+}
+
+namespace {
+struct PhaseProf {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;  // start/stop pairs
+    std::vector<int> phase;
+    cudaStream_t s;
+    void begin(int p) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        ev.push_back(e);
+        phase.push_back(p);
+    }
+    void end() {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        ev.push_back(e);
+    }
+};
+}  // namespace
+
+// hard_zxu ordering: hard/src/Solver.cpp:74-214 from "Initialize ADMM vars" to the end of the loop.
+static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *prof, int iters, bool init_frame) {
+    cudaStream_t st = s->stream;
+    LdltDev *f = s->factor->f;
+    const int T = s->T, NF = s->NF;
+    const bool accel = o->accel && o->anderson_m > 0;
+    const int m = accel ? o->anderson_m : 1;
+    TetArrays A{T, NF, s->V, s->idx, s->binv, s->w, s->kvol, s->rho_dt2};
+    const int gt = std::min((T + TET_BLOCK - 1) / TET_BLOCK, stream_grid(8));
+    const int gv = (NF + 127) / 128;
+    const int gs = stream_grid(4);
+    double *Uu = s->Ubuf, *Ux = s->Ubuf + s->Ne;
+    double *Gu = s->Gbuf, *Gx = s->Gbuf + s->Ne;
+    int &L = s->launches;
+    PhaseProf none;
+    if (!prof) prof = &none;
+
+    if (init_frame) {
+        k_init_state<<<1, 1, 0, st>>>(s->st, accel ? 1 : 0, m, o->eps);
+        // pinned tails of the three position arrays; x = x_bar; u = 0
+        if (s->NP > 0) {
+            const size_t pb = sizeof(double) * 3 * s->NP;
+            AAADMM_CUDA_OK(cudaMemcpyAsync(Ux + 3 * (size_t)NF, s->xpin, pb, cudaMemcpyDeviceToDevice, st));
+            AAADMM_CUDA_OK(cudaMemcpyAsync(Gx + 3 * (size_t)NF, s->xpin, pb, cudaMemcpyDeviceToDevice, st));
+            AAADMM_CUDA_OK(cudaMemcpyAsync(s->xs + 3 * (size_t)NF, s->xpin, pb, cudaMemcpyDeviceToDevice, st));
+        }
+        AAADMM_CUDA_OK(cudaMemcpyAsync(Ux, s->xbar, sizeof(double) * 3 * NF, cudaMemcpyDeviceToDevice, st));
+        AAADMM_CUDA_OK(cudaMemsetAsync(Uu, 0, sizeof(double) * s->Ne, st));
+        k_bconst<<<gv, 128, 0, st>>>(A, s->inc_ptr, s->inc, Ux, s->mass, s->xbar, s->bconst);
+        // warm start (hard/src/Solver.cpp:99-114)
+        k_update_z_hard<MODE_WARM><<<gt, TET_BLOCK, 0, st>>>(A, Ux, Uu, s->z, s->contrib, s->st, s->partials);
+        k_rhs_gather<<<gv, 128, 0, st>>>(NF, s->inc_ptr, s->inc, s->contrib, s->bconst, f->iperm, f->W, s->st);
+        if (ldlt_dev_apply_permuted(f, s->xs, st, &s->st->done)) return -1;
+        k_update_u_hard<MODE_WARM><<<gt, TET_BLOCK, 0, st>>>(A, s->xs, Ux, s->z, Uu, Gu, s->st, s->partials, s->hist_prim,
+                                                             s->hist_comb, s->hist_rej);
+        AAADMM_CUDA_OK(cudaMemcpyAsync(Gx, s->xs, sizeof(double) * 3 * NF, cudaMemcpyDeviceToDevice, st));
+        // default_(u,x) = curr_(u,x); accelerator->init(curr_u, curr_x)
+        AAADMM_CUDA_OK(cudaMemcpyAsync(s->Ubuf, s->Gbuf, sizeof(double) * s->Nt, cudaMemcpyDeviceToDevice, st));
+        L += 6 + 4 * f->n_levels;
+    }
+    for (int it = 0; it < iters; ++it) {
+        prof->begin(0);
+        k_update_z_hard<MODE_ITER><<<gt, TET_BLOCK, 0, st>>>(A, Ux, Uu, s->z, s->contrib, s->st, s->partials);
+        prof->end();
+        ++L;
+        if (accel) {
+            prof->begin(6);
+            k_restore_if_reject<<<gs, 256, 0, st>>>(s->Ubuf, s->Gbuf, s->Nt, s->st);
+            k_update_z_hard<MODE_REDO><<<gt, TET_BLOCK, 0, st>>>(A, Ux, Uu, s->z, s->contrib, s->st, s->partials);
+            prof->end();
+            L += 2;
+        }
+        prof->begin(1);
+        k_rhs_gather<<<gv, 128, 0, st>>>(NF, s->inc_ptr, s->inc, s->contrib, s->bconst, f->iperm, f->W, s->st);
+        prof->end();
+        prof->begin(2);
+        if (ldlt_dev_apply_permuted(f, s->xs, st, &s->st->done)) return -1;
+        prof->end();
+        L += 1 + 4 * f->n_levels;
+        prof->begin(3);
+        if (accel)
+            k_update_u_hard<MODE_ITER><<<gt, TET_BLOCK, 0, st>>>(A, s->xs, Ux, s->z, Uu, Gu, s->st, s->partials,
+                                                                 s->hist_prim, s->hist_comb, s->hist_rej);
+        else
+            k_update_u_hard<MODE_ITER><<<gt, TET_BLOCK, 0, st>>>(A, s->xs, Ux, s->z, Uu, Uu, s->st, s->partials,
+                                                                 s->hist_prim, s->hist_comb, s->hist_rej);
+        prof->end();
+        ++L;
+        if (accel) {
+            prof->begin(4);
+            if (launch_aa_pass1(m, gs, st, Gu, s->xs, Gx, s->Ubuf, s->dF, s->dG, s->Ne, s->Nt, s->st, s->partials)) return -1;
+            prof->end();
+            prof->begin(5);
+            if (launch_aa_pass2(m, gs, st, Gu, Gx, s->Ubuf, s->dF, s->dG, s->Ne, s->Nt, s->st)) return -1;
+            prof->end();
+            L += 2;
+        } else {
+            prof->begin(4);
+            k_copy_if_not_done<<<gv, 128, 0, st>>>(Ux, s->xs, 3 * (int64_t)NF, s->st);
+            prof->end();
+            ++L;
+        }
+    }
+    AAADMM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int step_common(aaadmm_tetscene *s, const aaadmm_step_opts *o, bool host_io, const double *x_bar,
+                       const double *x_pin, double *x_out, double *hp, double *hc, int *hr, aaadmm_step_result *res) {
+    if (!o || o->admm_iters < 0 || (o->accel && (o->anderson_m <= 0 || o->anderson_m > AA_MAX_M))) {
+        set_last_error("tetscene_step: bad options (Anderson_m must be in 1..16 when accel is on)");
+        return -1;
+    }
+    if (o->ordering != AAADMM_ORDER_HARD_ZXU) {
+        set_last_error("tetscene_step: xzu ordering is not implemented on the device yet");
+        return -1;
+    }
+    if (!host_io && !s->has_inputs) {
+        set_last_error("tetscene_step_resident: call aaadmm_tetscene_step once first");
+        return -1;
+    }
+    const bool accel = o->accel && o->anderson_m > 0;
+    if (scene_reserve(s, std::max(1, o->admm_iters), accel ? o->anderson_m : 1)) return -1;
+    cudaStream_t st = s->stream;
+    const int NF = s->NF;
+    s->launches = 0;
+    AAADMM_CUDA_OK(cudaEventRecord(s->ev[0], st));
+    if (host_io) {
+        memcpy(s->xbar_h, x_bar, sizeof(double) * 3 * NF);
+        if (s->NP > 0) memcpy(s->pin_h, x_pin, sizeof(double) * 3 * s->NP);
+        AAADMM_CUDA_OK(cudaMemcpyAsync(s->xbar, s->xbar_h, sizeof(double) * 3 * NF, cudaMemcpyHostToDevice, st));
+        if (s->NP > 0)
+            AAADMM_CUDA_OK(cudaMemcpyAsync(s->xpin, s->pin_h, sizeof(double) * 3 * s->NP, cudaMemcpyHostToDevice, st));
+        s->has_inputs = true;
+    }
+    AAADMM_CUDA_OK(cudaEventRecord(s->ev[1], st));
+    if (run_hard(s, o, nullptr, o->admm_iters, true)) return -1;
+    AAADMM_CUDA_OK(cudaEventRecord(s->ev[2], st));
+    SolveState hs;
+    if (host_io) {
+        // hard: default_x when ANDERSON, curr_x otherwise (hard/src/Solver.cpp:216-223)
+        const double *xfinal = accel ? (s->Gbuf + s->Ne) : s->xs;
+        AAADMM_CUDA_OK(cudaMemcpyAsync(s->xout_h, xfinal, sizeof(double) * 3 * NF, cudaMemcpyDeviceToHost, st));
+    }
+    AAADMM_CUDA_OK(cudaMemcpyAsync(&hs, s->st, sizeof(SolveState), cudaMemcpyDeviceToHost, st));
+    AAADMM_CUDA_OK(cudaEventRecord(s->ev[3], st));
+    AAADMM_CUDA_OK(cudaStreamSynchronize(st));
+    if (host_io) {
+        memcpy(x_out, s->xout_h, sizeof(double) * 3 * NF);
+        const int rows = hs.iter;
+        if (hp && rows) AAADMM_CUDA_OK(cudaMemcpy(hp, s->hist_prim, sizeof(double) * rows, cudaMemcpyDeviceToHost));
+        if (hc && rows) AAADMM_CUDA_OK(cudaMemcpy(hc, s->hist_comb, sizeof(double) * rows, cudaMemcpyDeviceToHost));
+        if (hr && rows) AAADMM_CUDA_OK(cudaMemcpy(hr, s->hist_rej, sizeof(int) * rows, cudaMemcpyDeviceToHost));
+    }
+    if (res) {
+        res->iters_logged = hs.iter;
+        res->rejects = hs.n_rejects;
+        res->broke_early = hs.done;
+        cudaEventElapsedTime(&res->loop_ms, s->ev[1], s->ev[2]);
+        cudaEventElapsedTime(&res->step_ms, s->ev[0], s->ev[3]);
+        res->kernel_launches = s->launches;
+    }
+    return 0;
+}
+
+int aaadmm_tetscene_step(aaadmm_tetscene *s, const aaadmm_step_opts *o, const double *x_bar, const double *x_pin,
+                         double *x_out, double *hp, double *hc, int *hr, aaadmm_step_result *res) {
+    API_TRY_BEGIN
+    if (!x_bar || !x_out || (s->NP > 0 && !x_pin)) {
+        set_last_error("tetscene_step: null buffer");
+        return -1;
+    }
+    return step_common(s, o, true, x_bar, x_pin, x_out, hp, hc, hr, res);
+    API_TRY_END
+}
+int aaadmm_tetscene_step_resident(aaadmm_tetscene *s, const aaadmm_step_opts *o, aaadmm_step_result *res) {
+    API_TRY_BEGIN
+    return step_common(s, o, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, res);
+    API_TRY_END
+}
+
+int aaadmm_tetscene_read_zu(aaadmm_tetscene *s, double *z, double *u) {
+    double *tmp = nullptr;
+    AAADMM_CUDA_OK(cudaMalloc((void **)&tmp, sizeof(double) * 9 * s->T));
+    const int g = (s->T + 255) / 256;
+    if (z) {
+        k_soa_to_aos9<<<g, 256, 0, s->stream>>>(s->z, tmp, s->T);
+        AAADMM_CUDA_OK(cudaMemcpyAsync(z, tmp, sizeof(double) * 9 * s->T, cudaMemcpyDeviceToHost, s->stream));
+        AAADMM_CUDA_OK(cudaStreamSynchronize(s->stream));
+    }
+    if (u) {
+        k_soa_to_aos9<<<g, 256, 0, s->stream>>>(s->Gbuf, tmp, s->T);
+        AAADMM_CUDA_OK(cudaMemcpyAsync(u, tmp, sizeof(double) * 9 * s->T, cudaMemcpyDeviceToHost, s->stream));
+        AAADMM_CUDA_OK(cudaStreamSynchronize(s->stream));
+    }
+    cudaFree(tmp);
+    return 0;
+}
+
+int aaadmm_tetscene_profile(aaadmm_tetscene *s, const aaadmm_step_opts *o, int iters, float *ms) {
+    API_TRY_BEGIN
+    if (!s->has_inputs) {
+        set_last_error("tetscene_profile: call aaadmm_tetscene_step once first");
+        return -1;
+    }
+    const bool accel = o->accel && o->anderson_m > 0;
+    if (scene_reserve(s, std::max(1, iters), accel ? o->anderson_m : 1)) return -1;
+    PhaseProf prof;
+    prof.on = true;
+    prof.s = s->stream;
+    aaadmm_step_opts oo = *o;
+    oo.eps = -1.0;  // never break: every phase runs in every iteration
+    if (run_hard(s, &oo, nullptr, 0, true)) return -1;
+    if (run_hard(s, &oo, &prof, iters, false)) return -1;
+    AAADMM_CUDA_OK(cudaStreamSynchronize(s->stream));
+    double sum[AAADMM_NPROF] = {0};
+    for (size_t k = 0; k < prof.phase.size(); ++k) {
+        float t = 0;
+        cudaEventElapsedTime(&t, prof.ev[2 * k], prof.ev[2 * k + 1]);
+        sum[prof.phase[k]] += t;
+        sum[AAADMM_NPROF - 1] += t;
+    }
+    for (auto e : prof.ev) cudaEventDestroy(e);
+    for (int p = 0; p < AAADMM_NPROF; ++p) ms[p] = (float)(sum[p] / std::max(1, iters));
+    return 0;
+    API_TRY_END
+}
+
+int aaadmm_tetscene_algo_bytes(aaadmm_tetscene *s, int m, double *b) {
+    const double T = s->T, V = s->V, NF = s->NF, Ne = (double)s->Ne, Nt = (double)s->Nt;
+    const double ninc = 4.0 * T;  // upper bound: incidences of free vertices
+    b[0] = T * (16 + 72 + 8 + 72 + 72 + 96) + 24 * V;           // update_z: idx,B^-1,w,u in; z,contrib out; positions
+    b[1] = T * 96 + 4 * ninc + NF * (8 + 24 + 24 + 4);          // rhs gather: contrib, inc, ptr, bconst, out, iperm
+    b[2] = s->factor->f->stats.bytes_per_solve;                 // ldlt apply
+    b[3] = T * (16 + 72 + 8 + 72 + 72 + 72) + 2 * 24 * V;       // update_u + residuals
+    b[4] = 8.0 * ((m + 2) * Ne + 3 * Nt);                       // aa pass 1
+    b[5] = 8.0 * ((m + 3) * Nt + 2 * Ne);                       // aa pass 2
+    b[6] = 0;
+    b[7] = b[0] + b[1] + b[2] + b[3] + b[4] + b[5];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Batched element kernels (unit parity)
+// ------------------------------------------------------------------------------------------
+int aaadmm_tet_prox_linear(double *z, int64_t n) {
+    if (aaadmm_device_count() <= 0) {
+        set_last_error("no CUDA device (this library has no CPU path)");
+        return -1;
+    }
+    double *d = nullptr;
+    AAADMM_CUDA_OK(cudaMalloc((void **)&d, sizeof(double) * 9 * n));
+    AAADMM_CUDA_OK(cudaMemcpy(d, z, sizeof(double) * 9 * n, cudaMemcpyHostToDevice));
+    k_prox_batch<<<(unsigned)((n + 127) / 128), 128>>>(d, n);
+    AAADMM_CUDA_OK(cudaGetLastError());
+    AAADMM_CUDA_OK(cudaMemcpy(z, d, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return 0;
+}
+int aaadmm_tet_f_minus_uvt(const double *z, double *out, int64_t n) {
+    if (aaadmm_device_count() <= 0) {
+        set_last_error("no CUDA device (this library has no CPU path)");
+        return -1;
+    }
+    double *d = nullptr, *o = nullptr;
+    AAADMM_CUDA_OK(cudaMalloc((void **)&d, sizeof(double) * 9 * n));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&o, sizeof(double) * 9 * n));
+    AAADMM_CUDA_OK(cudaMemcpy(d, z, sizeof(double) * 9 * n, cudaMemcpyHostToDevice));
+    k_fmuvt_batch<<<(unsigned)((n + 127) / 128), 128>>>(d, o, n);
+    AAADMM_CUDA_OK(cudaGetLastError());
+    AAADMM_CUDA_OK(cudaMemcpy(out, o, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    cudaFree(o);
+    return 0;
+}
+int aaadmm_cod_solve(int m, const double *M, const double *rhs, double *x, int *rank) {
+    if (aaadmm_device_count() <= 0) {
+        set_last_error("no CUDA device (this library has no CPU path)");
+        return -1;
+    }
+    if (m <= 0 || m > AA_MAX_M) {
+        set_last_error("cod_solve: m out of range");
+        return -1;
+    }
+    double *dM = nullptr, *dr = nullptr, *dx = nullptr;
+    int *dk = nullptr;
+    AAADMM_CUDA_OK(cudaMalloc((void **)&dM, sizeof(double) * m * m));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&dr, sizeof(double) * m));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&dx, sizeof(double) * m));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&dk, sizeof(int)));
+    AAADMM_CUDA_OK(cudaMemcpy(dM, M, sizeof(double) * m * m, cudaMemcpyHostToDevice));
+    AAADMM_CUDA_OK(cudaMemcpy(dr, rhs, sizeof(double) * m, cudaMemcpyHostToDevice));
+    k_cod<<<1, 1>>>(m, dM, dr, dx, dk);
+    AAADMM_CUDA_OK(cudaGetLastError());
+    AAADMM_CUDA_OK(cudaMemcpy(x, dx, sizeof(double) * m, cudaMemcpyDeviceToHost));
+    if (rank) AAADMM_CUDA_OK(cudaMemcpy(rank, dk, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(dM);
+    cudaFree(dr);
+    cudaFree(dx);
+    cudaFree(dk);
+    return 0;
+}
+
+}  // extern "C"

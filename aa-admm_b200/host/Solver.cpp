@@ -1,0 +1,314 @@
+#include "Solver.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+
+namespace admm {
+
+namespace {
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+
+TetEnergyTerm::TetEnergyTerm(const Vec4i &tet_, const std::vector<Vec3> &verts, const Lame &lame_, int material_)
+    : tet(tet_), lame(lame_), material(material_) {
+    double rest12[12], binv[9];
+    for (int k = 0; k < 4; ++k) {
+        rest[k] = verts[k];
+        for (int j = 0; j < 3; ++j) rest12[3 * k + j] = verts[k][j];
+    }
+    if (!aaadmm::tet_constants(rest12, lame.youngs, lame.poisson, binv, &volume, &weight))
+        throw std::runtime_error("**TetEnergyTerm Error: Inverted initial tet");
+}
+
+Solver::Solver() : initialized(false) {}
+
+Solver::~Solver() {
+    if (m_scene) aaadmm_tetscene_destroy(m_scene);
+    if (m_ldlt) aaadmm_ldlt_destroy(m_ldlt);
+}
+
+// hard/src/Solver.cpp:280-315
+void Solver::set_pins(const std::vector<int> &inds, const std::vector<Vec3> &points) {
+    const int n_pins = (int)inds.size();
+    const int dof = (int)m_x.size();
+    const bool pin_in_place = (int)points.size() != n_pins;
+    if ((dof == 0 && pin_in_place) || (pin_in_place && points.size() > 0))
+        throw std::runtime_error("**Solver::set_pins Error: Bad input.");
+    if (initialized) {
+        // the pinned index set may not change after initialize (the factor depends on it)
+        bool same = (size_t)n_pins == m_pins.size();
+        for (int i = 0; same && i < n_pins; ++i) same = m_pins.count(inds[i]) > 0;
+        if (!same) throw std::runtime_error("**Solver::set_pins Error: pinned vertex set changed after initialize.");
+    }
+    if (m_x_pin.empty()) m_x_pin.resize((size_t)n_pins * 3);
+    m_pins.clear();
+    for (int i = 0; i < n_pins; ++i) {
+        const int idx = inds[i];
+        Vec3 p;
+        if (pin_in_place)
+            p = {m_x[idx * 3 + 0], m_x[idx * 3 + 1], m_x[idx * 3 + 2]};
+        else
+            p = points[i];
+        m_pins[idx] = p;
+        for (int j = 0; j < 3; ++j) m_x_pin[(size_t)i * 3 + j] = p[j];
+    }
+}
+
+// hard/src/Solver.cpp:361-491 / xzu/src/Solver.cpp:373-498
+bool Solver::initialize(const Settings &settings_) {
+    m_settings = settings_;
+    const double t0 = now_ms();
+    const int dof = (int)m_x.size();
+    if (m_settings.verbose > 0) std::cout << "Solver::initialize: " << std::endl;
+    if (m_settings.timestep_s <= 0.0) {
+        std::cerr << "\n**Solver Error: timestep set to " << m_settings.timestep_s << "s, changing to 1/24s." << std::endl;
+        m_settings.timestep_s = 1.0 / 24.0;
+    }
+    if (!((int)m_masses.size() == dof && dof >= 3)) {
+        std::cerr << "\n**Solver Error: Problem with node data!" << std::endl;
+        return false;
+    }
+    if ((int)m_v.size() != dof) m_v.resize(dof);
+    std::fill(m_v.begin(), m_v.end(), 0.0);
+
+    const int n_verts = dof / 3;
+    const int n_tets = (int)energyterms.size();
+    std::vector<double> rest12((size_t)12 * n_tets), youngs(n_tets), poisson(n_tets);
+    std::vector<int> tets((size_t)4 * n_tets), material(n_tets);
+    for (int t = 0; t < n_tets; ++t) {
+        const TetEnergyTerm *e = dynamic_cast<const TetEnergyTerm *>(energyterms[t].get());
+        if (!e) throw std::runtime_error("admm::Solver (B200): only tet energy terms are supported on the device path");
+        if (e->get_weight() <= 0.0) throw std::runtime_error("**EnergyTerm::get_reduction Error: Some weight leq 0");
+        for (int k = 0; k < 4; ++k) {
+            tets[4 * (size_t)t + k] = e->tet[k];
+            for (int j = 0; j < 3; ++j) rest12[12 * (size_t)t + 3 * k + j] = e->rest[k][j];
+        }
+        youngs[t] = e->lame.youngs;
+        poisson[t] = e->lame.poisson;
+        material[t] = e->material;
+    }
+    std::vector<double> masses(n_verts);
+    for (int v = 0; v < n_verts; ++v) masses[v] = m_masses[3 * (size_t)v];
+    std::vector<int> pinned;
+    positive_pin.assign(n_verts, 1);
+    for (auto &kv : m_pins) {
+        pinned.push_back(kv.first);
+        positive_pin[kv.first] = 0;
+    }
+    const double dt2 = m_settings.timestep_s * m_settings.timestep_s;
+    const double rho = (m_settings.ordering == Settings::HARD_ZXU) ? m_settings.penalty : 1.0;
+    if (!aaadmm::build_tet_system(m_sys, n_verts, rest12.data(), n_tets, tets.data(), material.data(), youngs.data(),
+                                  poisson.data(), masses.data(), pinned, rho * dt2))
+        throw std::runtime_error(m_sys.error);
+
+    // factor Ahat once on the host (nested dissection + multifrontal LDL^T)
+    std::vector<double> coords((size_t)3 * m_sys.n_free);
+    for (int k = 0; k < m_sys.n_free; ++k)
+        for (int j = 0; j < 3; ++j) coords[3 * (size_t)k + j] = m_x[3 * (size_t)m_sys.dev_to_vert[k] + j];
+    std::vector<int> perm = aaadmm::nested_dissection(m_sys.Ahat, coords.data(), m_settings.nd_leaf_size);
+    m_factor = aaadmm::ldlt_factorize(m_sys.Ahat, perm);
+    if (!m_factor.ok) {
+        std::cerr << "\n**Solver Error: LDLT factorization failed" << std::endl;
+        return false;
+    }
+    if (m_scene) aaadmm_tetscene_destroy(m_scene), m_scene = nullptr;
+    if (m_ldlt) aaadmm_ldlt_destroy(m_ldlt), m_ldlt = nullptr;
+    if (aaadmm_ldlt_create(&m_ldlt, m_factor.n, m_factor.Lp.data(), m_factor.Li.data(), m_factor.Lx.data(),
+                           m_factor.D.data(), m_factor.perm.data(), 3) != 0)
+        throw std::runtime_error(std::string("aaadmm_ldlt_create: ") + aaadmm_last_error());
+    aaadmm_tetscene_desc d;
+    d.n_verts = m_sys.n_verts;
+    d.n_free = m_sys.n_free;
+    d.n_tets = m_sys.n_tets;
+    d.tet = m_sys.tet_dev.data();
+    d.binv = m_sys.binv.data();
+    d.weight = m_sys.weight.data();
+    d.kvol = m_sys.kvol.data();
+    d.material = m_sys.material.data();
+    d.mu = m_sys.mu.data();
+    d.lambda = m_sys.lambda.data();
+    d.mass_free = m_sys.mass_free.data();
+    d.inc_ptr = m_sys.inc_ptr.data();
+    d.inc = m_sys.inc.data();
+    d.rho_dt2 = rho * dt2;
+    if (aaadmm_tetscene_create(&m_scene, &d, m_ldlt) != 0)
+        throw std::runtime_error(std::string("aaadmm_tetscene_create: ") + aaadmm_last_error());
+    m_xbar.resize((size_t)3 * m_sys.n_free);
+    m_xout.resize((size_t)3 * m_sys.n_free);
+    if (m_settings.verbose >= 1)
+        std::cout << m_x.size() / 3 << " nodes, " << energyterms.size() << " energy terms" << std::endl;
+    m_runtime.initialization_ms = now_ms() - t0;
+    initialized = true;
+    return true;
+}
+
+// hard/src/Solver.cpp:34-234 / xzu/src/Solver.cpp:34-263: the explicit part stays on the host
+// (O(n) per frame), the ADMM loop is one C-ABI call.
+void Solver::step() {
+    if (!initialized) throw std::runtime_error("**Solver::step Error: not initialized");
+    const double t0 = now_ms();
+    const int n_nodes = (int)m_x.size() / 3;
+    const double dt = m_settings.timestep_s;
+    const double init_ms = m_runtime.initialization_ms;
+    m_runtime = RuntimeData();
+    m_runtime.initialization_ms = init_ms;
+
+    if (std::abs(m_settings.gravity) > 0)
+        for (int i = 0; i < n_nodes; ++i)
+            if (positive_pin[i] > 0) m_v[i * 3 + 1] += dt * m_settings.gravity;
+    int count = 0;
+    for (int i = 0; i < n_nodes; ++i)
+        if (positive_pin[i] > 0) {
+            for (int j = 0; j < 3; ++j) m_xbar[3 * (size_t)count + j] = m_x[3 * (size_t)i + j] + dt * m_v[3 * (size_t)i + j];
+            ++count;
+        }
+
+    aaadmm_step_opts o;
+    o.ordering = (int)m_settings.ordering;
+    o.admm_iters = m_settings.admm_iters;
+    o.anderson_m = m_settings.Anderson_m;
+    o.accel = (m_settings.acceleration_type == Settings::ANDERSON) ? 1 : 0;
+    o.eps = 1e-20;
+    o.log_comb_xzu = 1;
+    if (o.accel && o.anderson_m <= 0)
+        throw std::runtime_error("**Solver::step Error: ANDERSON needs Anderson_m > 0");  // reference: null deref
+    m_hist_prim.assign(std::max(1, o.admm_iters), 0.0);
+    m_hist_comb.assign(std::max(1, o.admm_iters), 0.0);
+    m_hist_rej.assign(std::max(1, o.admm_iters), 0);
+    aaadmm_step_result r;
+    if (aaadmm_tetscene_step(m_scene, &o, m_xbar.data(), m_x_pin.data(), m_xout.data(), m_hist_prim.data(),
+                             m_hist_comb.data(), m_hist_rej.data(), &r) != 0)
+        throw std::runtime_error(std::string("aaadmm_tetscene_step: ") + aaadmm_last_error());
+
+    // actual_x = S_free x + S_fix x_pin; v = (actual_x - x)/dt
+    count = 0;
+    int pcount = 0;
+    for (int i = 0; i < n_nodes; ++i) {
+        double nx[3];
+        if (positive_pin[i] > 0) {
+            for (int j = 0; j < 3; ++j) nx[j] = m_xout[3 * (size_t)count + j];
+            ++count;
+        } else {
+            for (int j = 0; j < 3; ++j) nx[j] = m_x_pin[3 * (size_t)pcount + j];
+            ++pcount;
+        }
+        for (int j = 0; j < 3; ++j) {
+            m_v[3 * (size_t)i + j] = (nx[j] - m_x[3 * (size_t)i + j]) * (1.0 / dt);
+            m_x[3 * (size_t)i + j] = nx[j];
+        }
+    }
+    step_prim_residual.assign(m_hist_prim.begin(), m_hist_prim.begin() + r.iters_logged);
+    step_comb_residual.assign(m_hist_comb.begin(), m_hist_comb.begin() + r.iters_logged);
+    is_reject.assign(m_hist_rej.begin(), m_hist_rej.begin() + r.iters_logged);
+    reject_num = r.rejects;
+    iter_num = r.broke_early ? r.iters_logged + 1 : r.iters_logged;
+    m_runtime.loop_ms = r.loop_ms;
+    m_runtime.step_ms = r.step_ms;
+    m_runtime.kernel_launches = r.kernel_launches;
+    // the device loop is not split into the reference's three timers; report it as one figure
+    m_runtime.global_ms = 0;
+    m_runtime.local_ms = r.loop_ms;
+    m_runtime.step_time.assign(r.iters_logged, 0.0);
+    for (int i = 0; i < r.iters_logged; ++i) m_runtime.step_time[i] = r.loop_ms * (i + 1) / std::max(1, r.iters_logged);
+    (void)t0;
+    if (m_settings.verbose > 0) m_runtime.print(m_settings);
+    if (m_settings.write_residual_file) save();
+}
+
+// hard/src/Solver.hpp:126-156
+void Solver::save() {
+    std::string file;
+    if (m_settings.acceleration_type)
+        file = "./result/residual-" + std::to_string(m_settings.Anderson_m) + ".txt";
+    else
+        file = "./result/residual-no.txt";
+    std::ofstream ofs;
+    ofs.open(file, std::ios::out | std::ios::ate);
+    if (!ofs.is_open()) {
+        std::cout << "Cannot open: " << file << std::endl;
+        return;
+    }
+    ofs << std::setprecision(16);
+    for (size_t i = 0; i < step_prim_residual.size(); i++) {
+        ofs << m_runtime.step_time[i] << '\t' << step_prim_residual[i] << '\t' << step_comb_residual[i];
+        if (m_settings.ordering == Settings::HARD_ZXU) ofs << '\t' << is_reject[i];
+        ofs << std::endl;
+    }
+    ofs.close();
+}
+
+bool Solver::Settings::parse_args(int argc, char **argv) {
+    for (int i = 1; i < argc - 1; ++i) {
+        std::string arg(argv[i]);
+        std::stringstream val(argv[i + 1]);
+        if (arg == "-help" || arg == "--help" || arg == "-h") {
+            help();
+            return true;
+        } else if (arg == "-dt") {
+            val >> timestep_s;
+        } else if (arg == "-v") {
+            val >> verbose;
+        } else if (arg == "-it") {
+            val >> admm_iters;
+        } else if (arg == "-g") {
+            val >> gravity;
+        } else if (arg == "-ck") {
+            val >> constraint_w;
+        } else if (arg == "-a") {
+            int acc;
+            val >> acc;
+            acceleration_type = (acc == 0) ? NOACC : ANDERSON;
+        } else if (arg == "-am") {
+            val >> Anderson_m;
+            acceleration_type = ANDERSON;
+        } else if (arg == "-ap") {
+            val >> penalty;
+        } else if (arg == "-ab") {
+            val >> beta;
+        }
+    }
+    if (argc > 0) {
+        std::string arg(argv[argc - 1]);
+        if (arg == "-help" || arg == "--help" || arg == "-h") {
+            help();
+            return true;
+        }
+    }
+    return false;
+}
+
+void Solver::Settings::help() {
+    std::stringstream ss;
+    ss << "\n==========================================\nArgs:\n"
+       << "\t-dt: time step (s)\n"
+       << "\t-v: verbosity (higher -> show more)\n"
+       << "\t-it: # admm iters\n"
+       << "\t-g: gravity (m/s^2)\n"
+       << "\t-ck: constraint weights (-1 = auto) \n"
+       << "\t-a: acceleration type (0=NoAcc, 1=Anderson) \n"
+       << "\t-am: anderson window size (>0, int) \n"
+       << "\t-ap: ADMM penalty (hard_zxu ordering) \n"
+       << "==========================================\n";
+    printf("%s", ss.str().c_str());
+}
+
+void Solver::RuntimeData::print(const Settings &settings) {
+    std::cout << "\nTotal device loop: " << loop_ms << "ms";
+    std::cout << "\nTotal step incl. copies: " << step_ms << "ms";
+    std::cout << "\nTotal Initialization time: " << initialization_ms << "ms";
+    std::cout << "\nADMM Iters: " << settings.admm_iters;
+    std::cout << "\nAnderson M: " << settings.Anderson_m;
+    std::cout << "\nKernel launches: " << kernel_launches;
+    std::cout << std::endl;
+}
+
+}  // namespace admm

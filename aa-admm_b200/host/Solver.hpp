@@ -1,0 +1,185 @@
+// Host-side mirror of the reference's admm::Solver for the tet ADMM path, over the C ABI.
+//
+// Same public surface as admm_anderson_hard_zxu/src/Solver.hpp:38-261 and
+// admm_anderson_xzu/src/Solver.hpp (add_nodes, set_pins, initialize, step, runtime_data,
+// settings, public m_x / m_v / m_masses / energyterms, nested Settings and RuntimeData);
+// the two reference projects are one class here, selected by Settings::ordering.
+// Eigen types are replaced by std::vector<double> / Vec3 (no Eigen in this image).
+// Error behaviour follows the reference: initialize() returns false on bad node data and
+// throws std::runtime_error for weight <= 0 / inverted rest tets; set_pins throws on bad input.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/aaadmm.h"
+#include "sparse_ldlt.hpp"
+#include "tet_system.hpp"
+
+namespace admm {
+
+typedef std::array<double, 3> Vec3;
+typedef std::array<int, 4> Vec4i;
+
+// admm::Lame (src/EnergyTerm.hpp:33-59)
+class Lame {
+public:
+    static Lame rubber() { return Lame(10000000, 0.499); }
+    static Lame soft_rubber() { return Lame(10000000, 0.399); }
+    static Lame very_soft_rubber() { return Lame(1000000, 0.299); }
+    double mu, lambda;
+    double youngs, poisson;
+    double bulk_modulus() const { return lambda + (2.0 / 3.0) * mu; }
+    double limit_min, limit_max;
+    Lame(double k, double v)
+        : mu(k / (2.0 * (1.0 + v))), lambda(k * v / ((1.0 + v) * (1.0 - 2.0 * v))), youngs(k), poisson(v),
+          limit_min(-100.0), limit_max(100.0) {}
+};
+
+// Element description. The reference's virtual prox/update_z/update_u run per element on the
+// CPU; here elements only carry their constants and initialize() turns them into SoA batches.
+class EnergyTerm {
+public:
+    virtual ~EnergyTerm() {}
+    virtual int get_dim() const = 0;
+    virtual double get_weight() const = 0;
+    virtual double get_volume() const = 0;
+};
+
+class TetEnergyTerm : public EnergyTerm {
+public:
+    Vec4i tet;
+    Lame lame;
+    std::array<Vec3, 4> rest;  // rest vertices (doubles cast from the caller's scalars)
+    int material;              // aaadmm::TetMaterial
+    double volume = 0, weight = 0;
+    int get_dim() const { return 9; }
+    double get_weight() const { return weight; }
+    double get_volume() const { return volume; }
+    // throws std::runtime_error("**TetEnergyTerm Error: Inverted initial tet") like the reference ctor
+    TetEnergyTerm(const Vec4i &tet_, const std::vector<Vec3> &verts, const Lame &lame_, int material_ = 0);
+};
+class NeoHookeanTet : public TetEnergyTerm {
+public:
+    NeoHookeanTet(const Vec4i &t, const std::vector<Vec3> &v, const Lame &l) : TetEnergyTerm(t, v, l, 1) {}
+};
+class StVKTet : public TetEnergyTerm {
+public:
+    StVKTet(const Vec4i &t, const std::vector<Vec3> &v, const Lame &l) : TetEnergyTerm(t, v, l, 2) {}
+};
+
+// src/TetEnergyTerm.hpp:35-51
+template <typename IN_SCALAR, typename TYPE>
+inline void create_tets_from_mesh(std::vector<std::shared_ptr<EnergyTerm>> &energyterms, const IN_SCALAR *verts,
+                                  const int *inds, int n_tets, const Lame &lame, const int vertex_offset) {
+    for (int i = 0; i < n_tets; ++i) {
+        Vec4i tet = {inds[i * 4 + 0], inds[i * 4 + 1], inds[i * 4 + 2], inds[i * 4 + 3]};
+        std::vector<Vec3> tetverts(4);
+        for (int k = 0; k < 4; ++k)
+            tetverts[k] = {(double)verts[tet[k] * 3 + 0], (double)verts[tet[k] * 3 + 1], (double)verts[tet[k] * 3 + 2]};
+        for (int k = 0; k < 4; ++k) tet[k] += vertex_offset;
+        energyterms.emplace_back(std::make_shared<TYPE>(tet, tetverts, lame));
+    }
+}
+
+class Solver {
+public:
+    struct Settings {
+        enum AccelationType { NOACC = 0, ANDERSON = 1 };
+        enum Ordering { HARD_ZXU = AAADMM_ORDER_HARD_ZXU, XZU = AAADMM_ORDER_XZU };
+        bool parse_args(int argc, char **argv);  // returns true if help()
+        void help();
+        double timestep_s;    // -dt
+        int verbose;          // -v
+        int admm_iters;       // -it
+        double gravity;       // -g
+        double constraint_w;  // -ck
+        int Anderson_m;       // -am
+        double penalty;       // -ap (hard_zxu)
+        double beta;          // -ab (xzu; parsed, unused, as in the reference)
+        AccelationType acceleration_type;  // -a
+        Ordering ordering;                 // which reference project's loop to run
+        bool write_residual_file;          // save() to ./result/residual-*.txt like the reference
+        int nd_leaf_size;                  // nested-dissection leaf size of the setup factorisation
+        Settings()
+            : timestep_s(1.0 / 30.0), verbose(1), admm_iters(500), gravity(-9.8), constraint_w(-1), Anderson_m(2),
+              penalty(1.0), beta(1.0), acceleration_type(NOACC), ordering(HARD_ZXU), write_residual_file(true),
+              nd_leaf_size(96) {}
+    };
+    struct RuntimeData {
+        double global_ms, local_ms, acceleration_ms, initialization_ms;
+        int inner_iters;
+        std::vector<double> step_time;
+        // device-side figures of the last step
+        double loop_ms, step_ms;
+        int kernel_launches;
+        RuntimeData()
+            : global_ms(0), local_ms(0), acceleration_ms(0), initialization_ms(0), inner_iters(0), loop_ms(0),
+              step_ms(0), kernel_launches(0) {}
+        void print(const Settings &settings);
+    };
+
+    Solver();
+    ~Solver();
+    Solver(const Solver &) = delete;
+    Solver &operator=(const Solver &) = delete;
+
+    std::vector<double> m_x, m_v, m_masses;  // per node x3
+    std::vector<std::shared_ptr<EnergyTerm>> energyterms;
+
+    template <typename T>
+    int add_nodes(T *x, T *m, int n_verts) {
+        const size_t prev_n = m_x.size();
+        const int n3 = n_verts * 3;
+        m_x.resize(prev_n + n3);
+        m_v.resize(prev_n + n3);
+        m_masses.resize(prev_n + n3);
+        for (int i = 0; i < n3; ++i) {
+            m_x[prev_n + i] = x[i];
+            m_v[prev_n + i] = 0.0;
+            m_masses[prev_n + i] = m[i];
+        }
+        return (int)((prev_n + n3) / 3);
+    }
+
+    void set_pins(const std::vector<int> &inds, const std::vector<Vec3> &points = std::vector<Vec3>());
+    bool initialize(const Settings &settings_ = Settings());
+    void step();
+    const RuntimeData &runtime_data() { return m_runtime; }
+    const Settings &settings() { return m_settings; }
+    void save();
+
+    // Logged trajectory of the last step (the reference keeps these protected and writes them
+    // to ./result/residual-*.txt in save()).
+    std::vector<double> step_prim_residual, step_comb_residual;
+    std::vector<int> is_reject;
+    int iter_num = 0;
+    int reject_num = 0;
+
+    // setup statistics
+    const aaadmm::LdltFactor &factor() const { return m_factor; }
+    aaadmm_ldlt *device_factor() { return m_ldlt; }
+    aaadmm_tetscene *device_scene() { return m_scene; }
+    const aaadmm::TetSystem &system() const { return m_sys; }
+
+    Settings m_settings;
+
+protected:
+    RuntimeData m_runtime;
+    bool initialized;
+    std::map<int, Vec3> m_pins;
+    std::vector<double> m_x_pin;  // in the order set_pins received them (reference: m_x_pin)
+    std::vector<int> positive_pin;
+    aaadmm::TetSystem m_sys;
+    aaadmm::LdltFactor m_factor;
+    aaadmm_ldlt *m_ldlt = nullptr;
+    aaadmm_tetscene *m_scene = nullptr;
+    std::vector<double> m_xbar, m_xout, m_hist_prim, m_hist_comb;
+    std::vector<int> m_hist_rej;
+};
+
+}  // namespace admm

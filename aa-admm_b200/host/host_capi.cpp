@@ -1,0 +1,257 @@
+// C entry points of libaaadmm_host.so: the host-side mirror classes (admm::Solver, the beam
+// scene builder, the setup factorisation) made callable from ctypes for tests, bench.py and
+// smoke(). The compute entry points live in libaaadmm_b200.so (include/aaadmm.h).
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/aaadmm_host.h"
+#include "Solver.hpp"
+#include "beam_scene.hpp"
+#include "sparse_ldlt.hpp"
+#include "tet_system.hpp"
+
+namespace {
+thread_local std::string g_err;
+struct SolverHandle {
+    admm::Solver solver;
+    admm::Solver::Settings settings;
+};
+struct FactorHandle {
+    aaadmm::LdltFactor F;
+};
+struct BeamHandle {
+    aaadmm::BeamMesh mesh;
+    aaadmm::BeamPins pins;
+};
+}  // namespace
+
+#define HOST_TRY try {
+#define HOST_CATCH                      \
+    }                                   \
+    catch (const std::exception &e) {   \
+        g_err = e.what();               \
+        return -1;                      \
+    }
+
+extern "C" {
+
+const char *aaadmm_host_last_error(void) { return g_err.c_str(); }
+
+// ---- beam scenes ---------------------------------------------------------------------------
+void *aaadmm_host_beam_new(void) { return new BeamHandle(); }
+void aaadmm_host_beam_free(void *h) { delete static_cast<BeamHandle *>(h); }
+int aaadmm_host_beam_add(void *h, int cx, int cy, int cz, float y_shift, float density) {
+    HOST_TRY
+    BeamHandle *b = static_cast<BeamHandle *>(h);
+    aaadmm::BeamMesh m = aaadmm::make_beam(cx, cy, cz, y_shift, density);
+    const int off = b->mesh.n_verts();
+    aaadmm::find_pins(m, off, b->pins);
+    aaadmm::append_mesh(b->mesh, m);
+    return b->mesh.n_verts();
+    HOST_CATCH
+}
+int aaadmm_host_beam_counts(void *h, int *n_verts, int *n_tets, int *n_pins) {
+    BeamHandle *b = static_cast<BeamHandle *>(h);
+    *n_verts = b->mesh.n_verts();
+    *n_tets = b->mesh.n_tets();
+    *n_pins = (int)b->pins.idx.size();
+    return 0;
+}
+int aaadmm_host_beam_copy(void *h, float *verts, int *tets, float *masses, int *pin_idx, double *pin_pts, int *pin_side) {
+    BeamHandle *b = static_cast<BeamHandle *>(h);
+    if (verts) memcpy(verts, b->mesh.verts.data(), b->mesh.verts.size() * sizeof(float));
+    if (tets) memcpy(tets, b->mesh.tets.data(), b->mesh.tets.size() * sizeof(int));
+    if (masses) memcpy(masses, b->mesh.masses.data(), b->mesh.masses.size() * sizeof(float));
+    if (pin_idx) memcpy(pin_idx, b->pins.idx.data(), b->pins.idx.size() * sizeof(int));
+    if (pin_pts) memcpy(pin_pts, b->pins.points.data(), b->pins.points.size() * sizeof(double));
+    if (pin_side) memcpy(pin_side, b->pins.side.data(), b->pins.side.size() * sizeof(int));
+    return 0;
+}
+int aaadmm_host_beam_stretch(void *h, double dt) {
+    aaadmm::stretch_pins(static_cast<BeamHandle *>(h)->pins, dt);
+    return 0;
+}
+
+// ---- setup factorisation ---------------------------------------------------------------------
+void *aaadmm_host_factor_new(int n, const int64_t *Ap, const int *Ai, const double *Ax, const double *coords,
+                             int leaf_size, int n_threads) {
+    try {
+        aaadmm::SymLower A;
+        A.n = n;
+        A.p.assign(Ap, Ap + n + 1);
+        A.i.assign(Ai, Ai + Ap[n]);
+        A.x.assign(Ax, Ax + Ap[n]);
+        std::vector<int> perm = aaadmm::nested_dissection(A, coords, leaf_size > 0 ? leaf_size : 96);
+        FactorHandle *f = new FactorHandle();
+        f->F = aaadmm::ldlt_factorize(A, perm, n_threads);
+        if (!f->F.ok) {
+            g_err = "ldlt_factorize: zero or non-finite pivot";
+            delete f;
+            return nullptr;
+        }
+        return f;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void aaadmm_host_factor_free(void *h) { delete static_cast<FactorHandle *>(h); }
+int64_t aaadmm_host_factor_nnz(void *h) {
+    FactorHandle *f = static_cast<FactorHandle *>(h);
+    return f->F.Lp[f->F.n];
+}
+int aaadmm_host_factor_copy(void *h, int64_t *Lp, int *Li, double *Lx, double *D, int *perm) {
+    FactorHandle *f = static_cast<FactorHandle *>(h);
+    const int n = f->F.n;
+    memcpy(Lp, f->F.Lp.data(), sizeof(int64_t) * (n + 1));
+    memcpy(Li, f->F.Li.data(), sizeof(int) * f->F.Li.size());
+    memcpy(Lx, f->F.Lx.data(), sizeof(double) * f->F.Lx.size());
+    memcpy(D, f->F.D.data(), sizeof(double) * n);
+    memcpy(perm, f->F.perm.data(), sizeof(int) * n);
+    return 0;
+}
+int aaadmm_host_factor_solve(void *h, const double *b, double *x, int nrhs) {
+    aaadmm::ldlt_solve_host(static_cast<FactorHandle *>(h)->F, b, x, nrhs);
+    return 0;
+}
+int aaadmm_host_factor_stats(void *h, double *s6) {
+    FactorHandle *f = static_cast<FactorHandle *>(h);
+    s6[0] = f->F.n_supernodes;
+    s6[1] = f->F.flops;
+    s6[2] = f->F.seconds_order;
+    s6[3] = f->F.seconds_symbolic;
+    s6[4] = f->F.seconds_numeric;
+    s6[5] = (double)f->F.Lp[f->F.n];
+    return 0;
+}
+
+// ---- admm::Solver ---------------------------------------------------------------------------
+void *aaadmm_host_solver_new(void) { return new SolverHandle(); }
+void aaadmm_host_solver_free(void *h) { delete static_cast<SolverHandle *>(h); }
+
+// binding::add_tetmesh (samples/utils/AddMeshes.hpp:97-177): float32 vertices and masses.
+int aaadmm_host_solver_add_tetmesh(void *h, const float *verts, int n_verts, const int *tets, int n_tets,
+                                   const float *masses, double youngs, double poisson, int material) {
+    HOST_TRY
+    admm::Solver &s = static_cast<SolverHandle *>(h)->solver;
+    const int prev = (int)s.m_x.size() / 3;
+    s.m_x.resize((size_t)(prev + n_verts) * 3);
+    s.m_v.resize((size_t)(prev + n_verts) * 3, 0.0);
+    s.m_masses.resize((size_t)(prev + n_verts) * 3);
+    for (int i = 0; i < n_verts; ++i)
+        for (int j = 0; j < 3; ++j) {
+            s.m_x[(size_t)(prev + i) * 3 + j] = (double)verts[3 * (size_t)i + j];
+            s.m_masses[(size_t)(prev + i) * 3 + j] = (double)masses[i];
+        }
+    admm::Lame lame(youngs, poisson);
+    if (material == 0)
+        admm::create_tets_from_mesh<float, admm::TetEnergyTerm>(s.energyterms, verts, tets, n_tets, lame, prev);
+    else if (material == 1)
+        admm::create_tets_from_mesh<float, admm::NeoHookeanTet>(s.energyterms, verts, tets, n_tets, lame, prev);
+    else
+        admm::create_tets_from_mesh<float, admm::StVKTet>(s.energyterms, verts, tets, n_tets, lame, prev);
+    return prev + n_verts;
+    HOST_CATCH
+}
+int aaadmm_host_solver_set_pins(void *h, const int *idx, const double *pts, int n) {
+    HOST_TRY
+    std::vector<int> inds(idx, idx + n);
+    std::vector<admm::Vec3> points(n);
+    for (int i = 0; i < n; ++i) points[i] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    static_cast<SolverHandle *>(h)->solver.set_pins(inds, points);
+    return 0;
+    HOST_CATCH
+}
+int aaadmm_host_solver_initialize(void *h, double dt, int iters, double gravity, int anderson_m, int accel,
+                                  double penalty, int ordering, int nd_leaf) {
+    HOST_TRY
+    SolverHandle *sh = static_cast<SolverHandle *>(h);
+    admm::Solver::Settings &st = sh->settings;
+    st.timestep_s = dt;
+    st.admm_iters = iters;
+    st.gravity = gravity;
+    st.Anderson_m = anderson_m;
+    st.acceleration_type = accel ? admm::Solver::Settings::ANDERSON : admm::Solver::Settings::NOACC;
+    st.penalty = penalty;
+    st.ordering = ordering ? admm::Solver::Settings::XZU : admm::Solver::Settings::HARD_ZXU;
+    st.verbose = 0;
+    st.write_residual_file = false;
+    if (nd_leaf > 0) st.nd_leaf_size = nd_leaf;
+    return sh->solver.initialize(st) ? 0 : -2;
+    HOST_CATCH
+}
+int aaadmm_host_solver_step(void *h) {
+    HOST_TRY
+    static_cast<SolverHandle *>(h)->solver.step();
+    return 0;
+    HOST_CATCH
+}
+int aaadmm_host_solver_set_iters(void *h, int iters, int anderson_m, int accel) {
+    admm::Solver &s = static_cast<SolverHandle *>(h)->solver;
+    s.m_settings.admm_iters = iters;
+    s.m_settings.Anderson_m = anderson_m;
+    s.m_settings.acceleration_type = accel ? admm::Solver::Settings::ANDERSON : admm::Solver::Settings::NOACC;
+    return 0;
+}
+int aaadmm_host_solver_n_dof(void *h) { return (int)static_cast<SolverHandle *>(h)->solver.m_x.size(); }
+int aaadmm_host_solver_get_x(void *h, double *x) {
+    admm::Solver &s = static_cast<SolverHandle *>(h)->solver;
+    memcpy(x, s.m_x.data(), s.m_x.size() * sizeof(double));
+    return 0;
+}
+int aaadmm_host_solver_get_v(void *h, double *v) {
+    admm::Solver &s = static_cast<SolverHandle *>(h)->solver;
+    memcpy(v, s.m_v.data(), s.m_v.size() * sizeof(double));
+    return 0;
+}
+int aaadmm_host_solver_hist_rows(void *h) {
+    return (int)static_cast<SolverHandle *>(h)->solver.step_prim_residual.size();
+}
+int aaadmm_host_solver_hist_copy(void *h, double *prim, double *comb, int *rej) {
+    admm::Solver &s = static_cast<SolverHandle *>(h)->solver;
+    const size_t n = s.step_prim_residual.size();
+    memcpy(prim, s.step_prim_residual.data(), n * sizeof(double));
+    memcpy(comb, s.step_comb_residual.data(), n * sizeof(double));
+    memcpy(rej, s.is_reject.data(), n * sizeof(int));
+    return 0;
+}
+// out[0..7] = loop_ms, step_ms, kernel_launches, init_ms, iter_num, reject_num, n_free, n_tets
+int aaadmm_host_solver_info(void *h, double *out8) {
+    admm::Solver &s = static_cast<SolverHandle *>(h)->solver;
+    const admm::Solver::RuntimeData &r = s.runtime_data();
+    out8[0] = r.loop_ms;
+    out8[1] = r.step_ms;
+    out8[2] = r.kernel_launches;
+    out8[3] = r.initialization_ms;
+    out8[4] = s.iter_num;
+    out8[5] = s.reject_num;
+    out8[6] = s.system().n_free;
+    out8[7] = s.system().n_tets;
+    return 0;
+}
+// setup statistics: out[0..5] = nnz(L), supernodes, flops, symbolic s, numeric s, nnz(Ahat lower)
+int aaadmm_host_solver_factor_info(void *h, double *out6) {
+    admm::Solver &s = static_cast<SolverHandle *>(h)->solver;
+    const aaadmm::LdltFactor &F = s.factor();
+    out6[0] = (double)F.Lp[F.n];
+    out6[1] = F.n_supernodes;
+    out6[2] = F.flops;
+    out6[3] = F.seconds_symbolic;
+    out6[4] = F.seconds_numeric;
+    out6[5] = (double)s.system().Ahat.p[s.system().n_free];
+    return 0;
+}
+void *aaadmm_host_solver_device_scene(void *h) { return static_cast<SolverHandle *>(h)->solver.device_scene(); }
+void *aaadmm_host_solver_device_factor(void *h) { return static_cast<SolverHandle *>(h)->solver.device_factor(); }
+
+// Host-only pieces of initialize() for CPU tests: tet constants and the scalar system matrix.
+int aaadmm_host_tet_constants(const double *rest12, double youngs, double poisson, double *binv9, double *vol,
+                              double *weight) {
+    return aaadmm::tet_constants(rest12, youngs, poisson, binv9, vol, weight) ? 0 : -1;
+}
+
+}  // extern "C"

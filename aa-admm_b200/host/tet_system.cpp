@@ -1,0 +1,169 @@
+#include "tet_system.hpp"
+
+#include <algorithm>
+#include <cmath>
+
+namespace aaadmm {
+
+namespace {
+// 3x3 cofactor / inverse / determinant in the operation order of the fixed-size Eigen code
+// the reference's TetEnergyTerm ctor runs (Eigen/src/LU/InverseImpl.h:120-170,
+// Determinant.h bruteforce_det3_helper), m is column-major m[c*3+r].
+inline double M(const double *m, int r, int c) { return m[c * 3 + r]; }
+inline double cofactor(const double *m, int i, int j) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return M(m, i1, j1) * M(m, i2, j2) - M(m, i1, j2) * M(m, i2, j1);
+}
+inline void inverse3(const double *m, double *inv) {
+    const double c0 = cofactor(m, 0, 0), c1 = cofactor(m, 1, 0), c2 = cofactor(m, 2, 0);
+    const double det = c0 * M(m, 0, 0) + (c1 * M(m, 1, 0) + c2 * M(m, 2, 0));
+    const double invdet = 1.0 / det;
+    inv[0 * 3 + 0] = c0 * invdet;  // row 0
+    inv[1 * 3 + 0] = c1 * invdet;
+    inv[2 * 3 + 0] = c2 * invdet;
+    inv[0 * 3 + 1] = cofactor(m, 0, 1) * invdet;  // (1,0)
+    inv[1 * 3 + 1] = cofactor(m, 1, 1) * invdet;  // (1,1)
+    inv[2 * 3 + 1] = cofactor(m, 2, 1) * invdet;  // (1,2)
+    inv[0 * 3 + 2] = cofactor(m, 0, 2) * invdet;  // (2,0)
+    inv[1 * 3 + 2] = cofactor(m, 1, 2) * invdet;  // (2,1)
+    inv[2 * 3 + 2] = cofactor(m, 2, 2) * invdet;  // (2,2)
+}
+inline double det3_helper(const double *m, int a, int b, int c) {
+    return M(m, 0, a) * (M(m, 1, b) * M(m, 2, c) - M(m, 1, c) * M(m, 2, b));
+}
+inline double det3(const double *m) {
+    return det3_helper(m, 0, 1, 2) - det3_helper(m, 1, 0, 2) + det3_helper(m, 2, 0, 1);
+}
+}  // namespace
+
+bool tet_constants(const double *rest12, double youngs, double poisson, double *binv9, double *vol, double *weight) {
+    double e[9];
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) e[c * 3 + r] = rest12[3 * (c + 1) + r] - rest12[r];
+    inverse3(e, binv9);
+    *vol = det3(e) / 6.0;
+    if (*vol < 0) return false;
+    Lame lame(youngs, poisson);
+    *weight = std::sqrt(lame.bulk_modulus() * (*vol));
+    return true;
+}
+
+bool build_tet_system(TetSystem &S, int n_verts, const double *rest12, int n_tets, const int *tets,
+                      const int *material, const double *youngs, const double *poisson,
+                      const double *masses, const std::vector<int> &pinned, double rho_dt2) {
+    S = TetSystem();
+    S.n_verts = n_verts;
+    S.n_tets = n_tets;
+    std::vector<char> is_pin(n_verts, 0);
+    for (int p : pinned) {
+        if (p < 0 || p >= n_verts) {
+            S.error = "pin index out of range";
+            return false;
+        }
+        is_pin[p] = 1;
+    }
+    S.vert_to_dev.assign(n_verts, -1);
+    S.dev_to_vert.assign(n_verts, -1);
+    int nf = 0;
+    for (int v = 0; v < n_verts; ++v)
+        if (!is_pin[v]) {
+            S.vert_to_dev[v] = nf;
+            S.dev_to_vert[nf] = v;
+            ++nf;
+        }
+    S.n_free = nf;
+    int np = 0;
+    for (int v = 0; v < n_verts; ++v)
+        if (is_pin[v]) {
+            S.vert_to_dev[v] = nf + np;
+            S.dev_to_vert[nf + np] = v;
+            ++np;
+        }
+    S.n_pin = np;
+    S.mass_free.resize(nf);
+    for (int k = 0; k < nf; ++k) S.mass_free[k] = masses[S.dev_to_vert[k]];
+
+    S.tet_dev.resize((size_t)4 * n_tets);
+    S.binv.resize((size_t)9 * n_tets);
+    S.weight.resize(n_tets);
+    S.volume.resize(n_tets);
+    S.kvol.resize(n_tets);
+    S.material.resize(n_tets);
+    S.mu.resize(n_tets);
+    S.lambda.resize(n_tets);
+    for (int t = 0; t < n_tets; ++t) {
+        const int *tv = tets + 4 * (size_t)t;
+        double vol, w;
+        if (!tet_constants(rest12 + 12 * (size_t)t, youngs[t], poisson[t], &S.binv[9 * (size_t)t], &vol, &w)) {
+            S.error = "**TetEnergyTerm Error: Inverted initial tet";
+            return false;
+        }
+        Lame lame(youngs[t], poisson[t]);
+        const double k = lame.bulk_modulus();
+        if (!(w > 0.0)) {
+            S.error = "**EnergyTerm::get_reduction Error: Some weight leq 0";
+            return false;
+        }
+        S.volume[t] = vol;
+        S.weight[t] = w;
+        S.kvol[t] = k * vol;
+        S.material[t] = material ? material[t] : 0;
+        S.mu[t] = lame.mu;
+        S.lambda[t] = lame.lambda;
+        for (int c = 0; c < 4; ++c) S.tet_dev[4 * (size_t)t + c] = S.vert_to_dev[tv[c]];
+    }
+
+    // incidence lists over free vertices
+    S.inc_ptr.assign(nf + 1, 0);
+    for (size_t k = 0; k < S.tet_dev.size(); ++k)
+        if (S.tet_dev[k] < nf) S.inc_ptr[S.tet_dev[k] + 1]++;
+    for (int v = 0; v < nf; ++v) S.inc_ptr[v + 1] += S.inc_ptr[v];
+    S.inc.resize(S.inc_ptr[nf]);
+    {
+        std::vector<int64_t> pos(S.inc_ptr.begin(), S.inc_ptr.end() - 1);
+        for (size_t k = 0; k < S.tet_dev.size(); ++k)
+            if (S.tet_dev[k] < nf) S.inc[pos[S.tet_dev[k]]++] = (int)k;
+    }
+
+    // Ahat = M + rho dt^2 sum_t w_t^2 G_t^T G_t, G_t(r,c) = sum_k Sel(c,k) Binv(k,r)
+    std::vector<int> tr, tc;
+    std::vector<double> tv;
+    tr.reserve((size_t)10 * n_tets + nf);
+    tc.reserve((size_t)10 * n_tets + nf);
+    tv.reserve((size_t)10 * n_tets + nf);
+    for (int v = 0; v < nf; ++v) {
+        tr.push_back(v);
+        tc.push_back(v);
+        tv.push_back(S.mass_free[v]);
+    }
+    for (int t = 0; t < n_tets; ++t) {
+        const double *bi = &S.binv[9 * (size_t)t];
+        double G[3][4];
+        for (int r = 0; r < 3; ++r) {
+            // Binv column-major: Binv(k,r) = bi[r*3+k]
+            G[r][1] = bi[r * 3 + 0];
+            G[r][2] = bi[r * 3 + 1];
+            G[r][3] = bi[r * 3 + 2];
+            G[r][0] = -G[r][1] - G[r][2] - G[r][3];
+        }
+        const double w = S.weight[t];
+        for (int a = 0; a < 4; ++a) {
+            const int va = S.tet_dev[4 * (size_t)t + a];
+            if (va >= nf) continue;
+            for (int b = 0; b <= a; ++b) {
+                const int vb = S.tet_dev[4 * (size_t)t + b];
+                if (vb >= nf) continue;
+                double s = 0;
+                for (int r = 0; r < 3; ++r) s += (rho_dt2 * (w * G[r][a])) * (w * G[r][b]);
+                int rr = std::max(va, vb), cc = std::min(va, vb);
+                tr.push_back(rr);
+                tc.push_back(cc);
+                tv.push_back(s);
+            }
+        }
+    }
+    S.Ahat = sym_from_triplets(nf, tr, tc, tv, false);
+    return true;
+}
+
+}  // namespace aaadmm

@@ -1,0 +1,158 @@
+/* aaadmm.h - C ABI of libaaadmm_b200.so: the B200 (sm_100a) implementation of AA-ADMM's
+ * per-iteration hot path (local projections, pre-factored global solve, Anderson mixing,
+ * safeguard).  Plain pointers and sizes only; every entry point returns 0 on success and a
+ * negative value on failure (aaadmm_last_error() holds the message).  Nothing throws across
+ * this boundary; the C++ mirror classes in aa-admm_b200/host translate to the reference's
+ * throw / `return false` conventions.  All device state is owned by the handles.  One CUDA
+ * stream per handle, no internal host threads, re-entrant across handles.
+ *
+ * The reference has no FFI layer (header-only / static library); each group below
+ * names the reference interface it replaces.
+ */
+#ifndef AAADMM_H_
+#define AAADMM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AAADMM_MAX_M 16
+
+const char *aaadmm_last_error(void);
+int aaadmm_device_count(void);          /* number of CUDA devices, <=0 if none / no driver   */
+int aaadmm_set_device(int device);      /* cudaSetDevice for the calling host thread          */
+int aaadmm_device_sms(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Anderson acceleration.
+ * Replaces class AndersonAcceleration:
+ *   variant H  admm_anderson_hard_zxu/src/AndersonAcceleration.h:38-212 (== Geometry/AndersonAcceleration.h)
+ *              ctor(m,total_dim,effective_dim) :40-56, replace :58-71, reset :73-91,
+ *              compute :93-114, init :116-135, compute_impl :154-211
+ *   variant X  admm_anderson_xzu/src/AndersonAcceleration.h: init(m,d,g0) :279-295,
+ *              compute(curr_g,g) :138-200, replace(g) :51-54      (= variant H with total==effective)
+ * Vectors are flat FP64; "host" calls copy in/out, "dev" calls take device pointers.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct aaadmm_aa aaadmm_aa;
+int aaadmm_aa_create(aaadmm_aa **out, int m, int64_t total_dim, int64_t effective_dim);
+int aaadmm_aa_destroy(aaadmm_aa *aa);
+int aaadmm_aa_init(aaadmm_aa *aa, const double *u, int64_t n);          /* host u */
+int aaadmm_aa_reset(aaadmm_aa *aa, const double *u, int64_t n);
+int aaadmm_aa_replace(aaadmm_aa *aa, const double *u, int64_t n);
+int aaadmm_aa_compute(aaadmm_aa *aa, const double *g, double *accel_u, int64_t n);
+int aaadmm_aa_init_dev(aaadmm_aa *aa, const double *d_u, int64_t n);    /* device u */
+int aaadmm_aa_reset_dev(aaadmm_aa *aa, const double *d_u, int64_t n);
+int aaadmm_aa_replace_dev(aaadmm_aa *aa, const double *d_u, int64_t n);
+int aaadmm_aa_compute_dev(aaadmm_aa *aa, const double *d_g, double *d_accel_u, int64_t n);
+/* iteration count since init/reset and next history column (iter_, col_idx_) */
+int aaadmm_aa_state(aaadmm_aa *aa, int *iter, int *col);
+
+/* ------------------------------------------------------------------------------------------
+ * Sparse LDL^T apply.
+ * Replaces LDLTSolver::solve (admm_anderson_xzu/src/LinearSolver.hpp:87-90) and
+ * SimplicialLDLTSolver::solve (Geometry/SPDSolver.h:88-91).  The factor is computed ONCE on
+ * the host (by the caller: Eigen::SimplicialLDLT matrixL()/vectorD()/permutationP() in the
+ * reference, aa-admm_b200/host/sparse_ldlt in this repo) and handed over as:
+ *   L  strictly lower triangle, CSC, row indices ascending per column, unit diagonal implied
+ *   D  n pivots;  perm[new] = old  (P A P^T = L D L^T)
+ * nrhs is 1 or 3 right-hand sides, interleaved (b[i*nrhs + r]).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct aaadmm_ldlt aaadmm_ldlt;
+int aaadmm_ldlt_create(aaadmm_ldlt **out, int n, const int64_t *Lp, const int *Li, const double *Lx,
+                       const double *D, const int *perm, int nrhs);
+int aaadmm_ldlt_destroy(aaadmm_ldlt *f);
+int aaadmm_ldlt_solve(aaadmm_ldlt *f, const double *b, double *x);          /* host vectors */
+int aaadmm_ldlt_solve_dev(aaadmm_ldlt *f, const double *d_b, double *d_x);  /* device vectors */
+/* stats[0..7] = n, blocks, levels, max_block, nnz_L, nnz_offblock, dense_diag_entries, bytes_per_solve */
+int aaadmm_ldlt_stats(aaadmm_ldlt *f, double *stats8);
+
+/* ------------------------------------------------------------------------------------------
+ * Tet-mesh ADMM step.
+ * Replaces the loop of admm::Solver::step():
+ *   hard_zxu ordering  admm_anderson_hard_zxu/src/Solver.cpp:74-226  (z -> x -> u, AA on (u,x))
+ *   xzu ordering       admm_anderson_xzu/src/Solver.cpp:78-257       (x -> z -> u, AA on z)
+ * with EnergyTerm::update_z/update_u/get_all_gradient (src/EnergyTerm.hpp:156-207) and
+ * TetEnergyTerm::prox/get_gradient (src/TetEnergyTerm.cpp:101-123,156-165) as batched kernels.
+ * Vertices are numbered free-first (reference free order), pinned vertices last.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct aaadmm_tetscene aaadmm_tetscene;
+
+typedef struct {
+    int n_verts, n_free, n_tets;
+    const int *tet;          /* 4*n_tets vertex ids in the free-first numbering              */
+    const double *binv;      /* 9*n_tets column-major inverse rest edge matrices              */
+    const double *weight;    /* n_tets ADMM weights sqrt(K vol)                                */
+    const double *kvol;      /* n_tets K*vol (xzu gradient)                                    */
+    const int *material;     /* n_tets: 0 linear, 1 neo-hookean, 2 stvk (may be NULL = linear) */
+    const double *mu;        /* n_tets (hyper-elastic only, may be NULL)                       */
+    const double *lambda;    /* n_tets (hyper-elastic only, may be NULL)                       */
+    const double *mass_free; /* n_free scalar lumped masses                                    */
+    const int64_t *inc_ptr;  /* n_free+1: incidence CSR over free vertices                     */
+    const int *inc;          /* entries tet*4+corner                                           */
+    double rho_dt2;          /* penalty * dt^2 (hard) or dt^2 (xzu)                            */
+} aaadmm_tetscene_desc;
+
+#define AAADMM_ORDER_HARD_ZXU 0
+#define AAADMM_ORDER_XZU 1
+
+typedef struct {
+    int ordering;       /* AAADMM_ORDER_*                                   */
+    int admm_iters;     /* Settings::admm_iters                             */
+    int anderson_m;     /* Settings::Anderson_m                             */
+    int accel;          /* 0 NOACC, 1 ANDERSON                              */
+    double eps;         /* break threshold on the combined residual (1e-20) */
+    int log_comb_xzu;   /* xzu: also run the extra solve+local step that the reference uses only to
+                           log the combined residual (xzu/src/Solver.cpp:217-233); 1 = as reference */
+} aaadmm_step_opts;
+
+typedef struct {
+    int iters_logged;   /* rows written to the history arrays                          */
+    int rejects;        /* rejected (reset) accelerated iterates                       */
+    int broke_early;    /* combined residual fell below eps                            */
+    float loop_ms;      /* device time of the iteration loop (CUDA events)             */
+    float step_ms;      /* device time including uploads/downloads of this call        */
+    int kernel_launches;
+} aaadmm_step_result;
+
+/* `factor` is borrowed (must outlive the scene) and must have nrhs == 3 and n == n_free. */
+int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *desc, aaadmm_ldlt *factor);
+int aaadmm_tetscene_destroy(aaadmm_tetscene *s);
+/* One time step of the ADMM loop.
+ *   x_bar   3*n_free  predicted free positions x + dt v (host)
+ *   x_pin   3*(n_verts-n_free) pinned positions (host)
+ *   x_out   3*n_free  resulting free positions (host)
+ *   hist_prim/hist_comb/hist_reject: admm_iters entries each (host, may be NULL) */
+int aaadmm_tetscene_step(aaadmm_tetscene *s, const aaadmm_step_opts *opts, const double *x_bar,
+                         const double *x_pin, double *x_out, double *hist_prim, double *hist_comb,
+                         int *hist_reject, aaadmm_step_result *result);
+/* Same loop with inputs already resident (the x_bar / x_pin of the last aaadmm_tetscene_step
+ * call are reused) and nothing copied back: used to time the HBM-resident rate. */
+int aaadmm_tetscene_step_resident(aaadmm_tetscene *s, const aaadmm_step_opts *opts, aaadmm_step_result *result);
+/* Debug/parity access: copies z (9*n_tets, reference layout: 9 consecutive doubles per tet)
+ * and u of the last step to the host. */
+int aaadmm_tetscene_read_zu(aaadmm_tetscene *s, double *z, double *u);
+/* Per-kernel device timings of the last profiled step (see aaadmm_tetscene_profile). */
+#define AAADMM_NPROF 8
+/* Runs `iters` iterations of the hard_zxu loop from the current state with CUDA events around
+ * every phase; ms[AAADMM_NPROF] receives the average per-iteration time of
+ * {update_z, rhs, ldlt_apply, update_u_resid, aa_pass1, aa_pass2, safeguard, total}. */
+int aaadmm_tetscene_profile(aaadmm_tetscene *s, const aaadmm_step_opts *opts, int iters, float *ms);
+/* Algorithmic bytes per launch of the same phases, for the roofline report. */
+int aaadmm_tetscene_algo_bytes(aaadmm_tetscene *s, int anderson_m, double *bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched element kernels exposed for unit parity (same device code the step uses).
+ *   prox_linear : TetEnergyTerm::prox on n column-major 3x3 blocks (in place, host array)
+ *   grad_linear : out = F - U V^T  (TetEnergyTerm::get_gradient / (K vol))
+ *   cod_solve   : Eigen COD least-squares solve of an m x m column-major system
+ * ------------------------------------------------------------------------------------------ */
+int aaadmm_tet_prox_linear(double *z, int64_t n);
+int aaadmm_tet_f_minus_uvt(const double *z, double *out, int64_t n);
+int aaadmm_cod_solve(int m, const double *M, const double *rhs, double *x, int *rank);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AAADMM_H_ */

@@ -1,0 +1,61 @@
+/* aaadmm_host.h - C entry points of libaaadmm_host.so: the host-side mirror of the reference's
+ * scene/solver classes (aa-admm_b200/host), exposed for ctypes (tests, bench.py, smoke()).
+ * The compute boundary is include/aaadmm.h; nothing in this library computes the hot path.
+ * Every function returns 0 (or a handle) on success, <0 / NULL on failure
+ * (aaadmm_host_last_error()).
+ */
+#ifndef AAADMM_HOST_H_
+#define AAADMM_HOST_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char *aaadmm_host_last_error(void);
+
+/* Beam scenes: mcl::factory::make_tet_blocks + beams.cpp centre/scale/offset + find_pins /
+ * stretch_beams (admm_anderson_hard_zxu/samples/Asia2019/beams.cpp:66-160) restated in O(n). */
+void *aaadmm_host_beam_new(void);
+void aaadmm_host_beam_free(void *h);
+int aaadmm_host_beam_add(void *h, int cx, int cy, int cz, float y_shift, float density);
+int aaadmm_host_beam_counts(void *h, int *n_verts, int *n_tets, int *n_pins);
+int aaadmm_host_beam_copy(void *h, float *verts, int *tets, float *masses, int *pin_idx, double *pin_pts, int *pin_side);
+int aaadmm_host_beam_stretch(void *h, double dt);
+
+/* Setup factorisation (role of LDLTSolver::update_system, LinearSolver.hpp:79-84):
+ * A lower CSC incl. diagonal; coords 3 per node or NULL. */
+void *aaadmm_host_factor_new(int n, const int64_t *Ap, const int *Ai, const double *Ax, const double *coords,
+                             int leaf_size, int n_threads);
+void aaadmm_host_factor_free(void *h);
+int64_t aaadmm_host_factor_nnz(void *h);
+int aaadmm_host_factor_copy(void *h, int64_t *Lp, int *Li, double *Lx, double *D, int *perm);
+int aaadmm_host_factor_solve(void *h, const double *b, double *x, int nrhs);
+int aaadmm_host_factor_stats(void *h, double *s6);
+
+/* admm::Solver mirror (hard_zxu/src/Solver.hpp:38-261): add_tetmesh = binding::add_tetmesh
+ * (samples/utils/AddMeshes.hpp:97-177), set_pins, initialize, step. ordering 0 = hard_zxu, 1 = xzu. */
+void *aaadmm_host_solver_new(void);
+void aaadmm_host_solver_free(void *h);
+int aaadmm_host_solver_add_tetmesh(void *h, const float *verts, int n_verts, const int *tets, int n_tets,
+                                   const float *masses, double youngs, double poisson, int material);
+int aaadmm_host_solver_set_pins(void *h, const int *idx, const double *pts, int n);
+int aaadmm_host_solver_initialize(void *h, double dt, int iters, double gravity, int anderson_m, int accel,
+                                  double penalty, int ordering, int nd_leaf);
+int aaadmm_host_solver_step(void *h);
+int aaadmm_host_solver_set_iters(void *h, int iters, int anderson_m, int accel);
+int aaadmm_host_solver_n_dof(void *h);
+int aaadmm_host_solver_get_x(void *h, double *x);
+int aaadmm_host_solver_get_v(void *h, double *v);
+int aaadmm_host_solver_hist_rows(void *h);
+int aaadmm_host_solver_hist_copy(void *h, double *prim, double *comb, int *rej);
+int aaadmm_host_solver_info(void *h, double *out8);
+int aaadmm_host_solver_factor_info(void *h, double *out6);
+void *aaadmm_host_solver_device_scene(void *h);
+void *aaadmm_host_solver_device_factor(void *h);
+int aaadmm_host_tet_constants(const double *rest12, double youngs, double poisson, double *binv9, double *vol,
+                              double *weight);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,130 @@
+"""First GPU parity pass: device kernels vs the compiled reference (oracle/_ref)."""
+import numpy as np
+import pytest
+
+from scenes import beam_arrays, run_product, run_reference
+
+pytestmark = pytest.mark.gpu
+
+
+def test_prox_linear_vs_reference(gpu, ref):
+    rng = np.random.default_rng(0)
+    F = np.eye(3).reshape(1, 9) + 0.3 * rng.standard_normal((4096, 9))
+    F[:64] *= -1.0            # inverted
+    F[64:128, 6:] = 0.0       # flat (rank 2)
+    F[128] = 0.0              # zero matrix
+    got = gpu.tet_prox_linear(F)
+    exp = ref.ref_tet_prox(F)
+    assert np.abs(got - exp).max() < 1e-13
+    # orthogonality invariant of 2*z - F
+    R = (2 * got - F)[256:].reshape(-1, 3, 3)
+    assert np.abs(np.einsum("nij,nkj->nik", R, R) - np.eye(3)).max() < 1e-12
+
+
+def test_grad_linear_vs_reference(gpu, ref):
+    rng = np.random.default_rng(1)
+    F = np.eye(3).reshape(1, 9) + 0.3 * rng.standard_normal((1024, 9))
+    assert np.abs(gpu.tet_f_minus_uvt(F) - ref.ref_tet_F_minus_UVt(F)).max() < 1e-12
+
+
+@pytest.mark.parametrize("m", [2, 3, 5, 6])
+def test_cod_solve_vs_eigen(gpu, ref, m):
+    rng = np.random.default_rng(m)
+    for trial in range(20):
+        B = rng.standard_normal((m + 3, m))
+        if trial % 3 == 1:
+            B[:, -1] = B[:, 0]                     # rank deficient
+        if trial % 3 == 2:
+            B[:, 1] = B[:, 0] * (1 + 1e-9)         # nearly dependent
+        M = B.T @ B
+        rhs = rng.standard_normal(m)
+        x, rank = gpu.cod_solve(M, rhs)
+        assert rank == ref.ref_cod_rank(M)
+        exp = ref.ref_cod_solve(M, rhs)
+        assert np.abs(x - exp).max() <= 1e-9 * max(1.0, np.abs(exp).max())
+
+
+@pytest.mark.parametrize("m,n,ne", [(5, 5000, 5000), (3, 4097, 3000), (1, 100, 100), (6, 20000, 12345)])
+def test_anderson_vs_reference(gpu, ref, m, n, ne):
+    rng = np.random.default_rng(7)
+    Aop = rng.standard_normal((64, 64)) * 0.05
+
+    def g(u):  # a contractive fixed-point map on the first 64 entries, damping on the rest
+        v = 0.5 * u + 1.0
+        v[:64] = Aop @ u[:64] + 1.0
+        return v
+
+    u0 = rng.standard_normal(n)
+    a = gpu.AndersonAcceleration(m, n, ne)
+    r = ref.RefAndersonH(m, n, ne)
+    a.init(u0)
+    r.init(u0)
+    ua, ur = u0.copy(), u0.copy()
+    for it in range(12):
+        if it == 7:
+            a.reset(ua)
+            r.reset(ur)
+        if it == 9:
+            a.replace(ua * 0.5)
+            r.replace(ur * 0.5)
+            ua, ur = ua * 0.5, ur * 0.5
+        ua = a.compute(g(ua))
+        ur = r.compute(g(ur))
+        assert np.abs(ua - ur).max() <= 1e-9 * np.abs(ur).max(), it
+
+
+def test_ldlt_apply_vs_host_factor(gpu):
+    A = gpu
+    rng = np.random.default_rng(3)
+    # 3-D grid Laplacian + mass
+    nx, ny, nz = 9, 8, 7
+    n = nx * ny * nz
+    idx = np.arange(n).reshape(nx, ny, nz)
+    rows, cols, vals = [], [], []
+    coords = np.stack(np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij"), -1).reshape(-1, 3).astype(float)
+    Afull = np.zeros((n, n))
+    for d in range(3):
+        a = np.take(idx, np.arange(idx.shape[d] - 1), axis=d).ravel()
+        b = np.take(idx, np.arange(1, idx.shape[d]), axis=d).ravel()
+        w = rng.uniform(0.5, 2.0, a.size)
+        Afull[a, b] -= w
+        Afull[b, a] -= w
+        Afull[a, a] += w
+        Afull[b, b] += w
+    Afull += np.diag(rng.uniform(0.1, 1.0, n))
+    L = np.tril(Afull)
+    Ap, Ai, Ax = [0], [], []
+    for j in range(n):
+        r = np.nonzero(L[:, j])[0]
+        Ai += list(r)
+        Ax += list(L[r, j])
+        Ap.append(len(Ai))
+    hf = A.HostFactor(n, Ap, Ai, Ax, coords, leaf_size=16)
+    Lp, Li, Lx, D, perm = hf.arrays()
+    for nrhs in (1, 3):
+        dev = A.Ldlt(n, Lp, Li, Lx, D, perm, nrhs)
+        b = rng.standard_normal(n * nrhs)
+        x = dev.solve(b)
+        xe = np.linalg.solve(Afull, b.reshape(n, nrhs)).reshape(-1)
+        assert np.abs(x - xe).max() < 1e-10 * np.abs(xe).max()
+        assert np.abs(x - hf.solve(b, nrhs)).max() < 1e-11 * np.abs(xe).max()
+        print(dev.stats())
+
+
+@pytest.mark.parametrize("dims,m,accel", [((12, 3, 3), 5, True), ((12, 3, 3), 0, False), ((16, 4, 4), 5, True)])
+def test_hard_step_vs_reference(gpu, ref, dims, m, accel):
+    frames = 2
+    _, hg, xg = run_product(gpu, beam_arrays(gpu, *dims), frames, m=max(m, 1), accel=accel)
+    _, hr, xr = run_reference(ref, gpu, beam_arrays(gpu, *dims), frames, m=max(m, 1), accel=accel)
+    for f in range(frames):
+        n = min(len(hg[f]), len(hr[f]))
+        rel = np.abs(hg[f][:n, 1] - hr[f][:n, 2]) / hr[f][:n, 2]
+        print("frame", f, "rows", len(hg[f]), len(hr[f]), "rel comb diff first 12:", rel[:12], "max", rel.max())
+        print("rejects gpu/ref", hg[f][:, 2].sum(), hr[f][:, 3].sum())
+        assert abs(len(hg[f]) - len(hr[f])) <= 2
+        assert rel[:8].max() < 1e-9
+        if not accel:
+            assert rel[:50].max() < 1e-9
+        xerr = np.abs(xg[f] - xr[f]).max() / np.abs(xr[f]).max()
+        print("final position rel err", xerr)
+        assert xerr < 1e-6
