@@ -12,7 +12,9 @@ LIB_CUDA = os.path.join(PKG, "libaaadmm_b200.so")
 LIB_HOST = os.path.join(PKG, "libaaadmm_host.so")
 GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
-CUDA_SOURCES = ["aaadmm_capi.cu", "ldlt_apply.cu"]
+CUDA_SOURCES = ["aaadmm_capi.cu", "ldlt_apply.cu", "tet_kernels.cu"]
+# per-element local-step math follows the reference operation by operation: no FMA contraction
+CUDA_NO_FMAD = {"tet_kernels.cu"}
 CUDA_HEADERS = ["common.cuh", "svd3.cuh", "cod_small.cuh", "aa_kernels.cuh", "tet_kernels.cuh", "ldlt_apply.cuh"]
 HOST_SOURCES = ["beam_scene.cpp", "sparse_ldlt.cpp", "tet_system.cpp", "Solver.cpp", "host_capi.cpp"]
 HOST_HEADERS = ["beam_scene.hpp", "sparse_ldlt.hpp", "tet_system.hpp", "Solver.hpp", "AndersonAcceleration.hpp"]
@@ -38,13 +40,26 @@ def build_cuda(force=False, verbose=False):
     deps = srcs + [os.path.join(CSRC, h) for h in CUDA_HEADERS] + [os.path.join(ROOT, "include", "aaadmm.h")]
     if not force and not _stale(LIB_CUDA, deps):
         return LIB_CUDA
-    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB_CUDA] + srcs
+    objdir = os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+    base = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+            "-Xcompiler", "-fPIC"]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    out = _run(cmd)
-    if verbose:
-        print(out)
+        base += ["-Xptxas", "-v"]
+    objs, procs = [], []
+    for s in CUDA_SOURCES:
+        o = os.path.join(objdir, s.replace(".cu", ".o"))
+        cmd = base + (["-fmad=false"] if s in CUDA_NO_FMAD else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError("build failed: " + " ".join(cmd))
+        if verbose:
+            print(out)
+    _run(["nvcc", "-shared", "-o", LIB_CUDA] + objs)
     return LIB_CUDA
 
 

@@ -59,22 +59,6 @@ int launch_aa_pass2(int m, int grid, cudaStream_t s, const double *g_u, const do
     return 0;
 }
 
-__global__ void k_prox_batch(double *z, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double zi[9];
-    for (int k = 0; k < 9; ++k) zi[k] = z[9 * i + k];
-    tet_prox_linear(zi);
-    for (int k = 0; k < 9; ++k) z[9 * i + k] = zi[k];
-}
-__global__ void k_fmuvt_batch(const double *z, double *out, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double zi[9], g[9];
-    for (int k = 0; k < 9; ++k) zi[k] = z[9 * i + k];
-    tet_grad_linear(zi, 1.0, g);
-    for (int k = 0; k < 9; ++k) out[9 * i + k] = g[k];
-}
 __global__ void k_cod(int m, const double *M, const double *rhs, double *x, int *rank) {
     double A[AA_MAX_M * AA_MAX_M], b[AA_MAX_M], xx[AA_MAX_M];
     for (int i = 0; i < m * m; ++i) A[i] = M[i];
@@ -525,13 +509,13 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
         }
         AAADMM_CUDA_OK(cudaMemcpyAsync(Ux, s->xbar, sizeof(double) * 3 * NF, cudaMemcpyDeviceToDevice, st));
         AAADMM_CUDA_OK(cudaMemsetAsync(Uu, 0, sizeof(double) * s->Ne, st));
-        k_bconst<<<gv, 128, 0, st>>>(A, s->inc_ptr, s->inc, Ux, s->mass, s->xbar, s->bconst);
+        launch_bconst(st, A, s->inc_ptr, s->inc, Ux, s->mass, s->xbar, s->bconst);
         // warm start (hard/src/Solver.cpp:99-114)
-        k_update_z_hard<MODE_WARM><<<gt, TET_BLOCK, 0, st>>>(A, Ux, Uu, s->z, s->contrib, s->st, s->partials);
-        k_rhs_gather<<<gv, 128, 0, st>>>(NF, s->inc_ptr, s->inc, s->contrib, s->bconst, f->iperm, f->W, s->st);
+        launch_update_z_hard(MODE_WARM, gt, st, A, Ux, Uu, s->z, s->contrib, s->st, s->partials);
+        launch_rhs_gather(st, NF, s->inc_ptr, s->inc, s->contrib, s->bconst, f->iperm, f->W, s->st);
         if (ldlt_dev_apply_permuted(f, s->xs, st, &s->st->done)) return -1;
-        k_update_u_hard<MODE_WARM><<<gt, TET_BLOCK, 0, st>>>(A, s->xs, Ux, s->z, Uu, Gu, s->st, s->partials, s->hist_prim,
-                                                             s->hist_comb, s->hist_rej);
+        launch_update_u_hard(MODE_WARM, gt, st, A, s->xs, Ux, s->z, Uu, Gu, s->st, s->partials, s->hist_prim,
+                             s->hist_comb, s->hist_rej);
         AAADMM_CUDA_OK(cudaMemcpyAsync(Gx, s->xs, sizeof(double) * 3 * NF, cudaMemcpyDeviceToDevice, st));
         // default_(u,x) = curr_(u,x); accelerator->init(curr_u, curr_x)
         AAADMM_CUDA_OK(cudaMemcpyAsync(s->Ubuf, s->Gbuf, sizeof(double) * s->Nt, cudaMemcpyDeviceToDevice, st));
@@ -539,18 +523,18 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
     }
     for (int it = 0; it < iters; ++it) {
         prof->begin(0);
-        k_update_z_hard<MODE_ITER><<<gt, TET_BLOCK, 0, st>>>(A, Ux, Uu, s->z, s->contrib, s->st, s->partials);
+        launch_update_z_hard(MODE_ITER, gt, st, A, Ux, Uu, s->z, s->contrib, s->st, s->partials);
         prof->end();
         ++L;
         if (accel) {
             prof->begin(6);
-            k_restore_if_reject<<<gs, 256, 0, st>>>(s->Ubuf, s->Gbuf, s->Nt, s->st);
-            k_update_z_hard<MODE_REDO><<<gt, TET_BLOCK, 0, st>>>(A, Ux, Uu, s->z, s->contrib, s->st, s->partials);
+            launch_restore_if_reject(gs, st, s->Ubuf, s->Gbuf, s->Nt, s->st);
+            launch_update_z_hard(MODE_REDO, gt, st, A, Ux, Uu, s->z, s->contrib, s->st, s->partials);
             prof->end();
             L += 2;
         }
         prof->begin(1);
-        k_rhs_gather<<<gv, 128, 0, st>>>(NF, s->inc_ptr, s->inc, s->contrib, s->bconst, f->iperm, f->W, s->st);
+        launch_rhs_gather(st, NF, s->inc_ptr, s->inc, s->contrib, s->bconst, f->iperm, f->W, s->st);
         prof->end();
         prof->begin(2);
         if (ldlt_dev_apply_permuted(f, s->xs, st, &s->st->done)) return -1;
@@ -558,11 +542,11 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
         L += 1 + 4 * f->n_levels;
         prof->begin(3);
         if (accel)
-            k_update_u_hard<MODE_ITER><<<gt, TET_BLOCK, 0, st>>>(A, s->xs, Ux, s->z, Uu, Gu, s->st, s->partials,
-                                                                 s->hist_prim, s->hist_comb, s->hist_rej);
+            launch_update_u_hard(MODE_ITER, gt, st, A, s->xs, Ux, s->z, Uu, Gu, s->st, s->partials, s->hist_prim,
+                                 s->hist_comb, s->hist_rej);
         else
-            k_update_u_hard<MODE_ITER><<<gt, TET_BLOCK, 0, st>>>(A, s->xs, Ux, s->z, Uu, Uu, s->st, s->partials,
-                                                                 s->hist_prim, s->hist_comb, s->hist_rej);
+            launch_update_u_hard(MODE_ITER, gt, st, A, s->xs, Ux, s->z, Uu, Uu, s->st, s->partials, s->hist_prim,
+                                 s->hist_comb, s->hist_rej);
         prof->end();
         ++L;
         if (accel) {
@@ -575,7 +559,7 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
             L += 2;
         } else {
             prof->begin(4);
-            k_copy_if_not_done<<<gv, 128, 0, st>>>(Ux, s->xs, 3 * (int64_t)NF, s->st);
+            launch_copy_if_not_done(st, Ux, s->xs, 3 * (int64_t)NF, s->st);
             prof->end();
             ++L;
         }
@@ -730,7 +714,7 @@ int aaadmm_tet_prox_linear(double *z, int64_t n) {
     double *d = nullptr;
     AAADMM_CUDA_OK(cudaMalloc((void **)&d, sizeof(double) * 9 * n));
     AAADMM_CUDA_OK(cudaMemcpy(d, z, sizeof(double) * 9 * n, cudaMemcpyHostToDevice));
-    k_prox_batch<<<(unsigned)((n + 127) / 128), 128>>>(d, n);
+    launch_prox_batch(d, n);
     AAADMM_CUDA_OK(cudaGetLastError());
     AAADMM_CUDA_OK(cudaMemcpy(z, d, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost));
     cudaFree(d);
@@ -745,7 +729,7 @@ int aaadmm_tet_f_minus_uvt(const double *z, double *out, int64_t n) {
     AAADMM_CUDA_OK(cudaMalloc((void **)&d, sizeof(double) * 9 * n));
     AAADMM_CUDA_OK(cudaMalloc((void **)&o, sizeof(double) * 9 * n));
     AAADMM_CUDA_OK(cudaMemcpy(d, z, sizeof(double) * 9 * n, cudaMemcpyHostToDevice));
-    k_fmuvt_batch<<<(unsigned)((n + 127) / 128), 128>>>(d, o, n);
+    launch_fmuvt_batch(d, o, n);
     AAADMM_CUDA_OK(cudaGetLastError());
     AAADMM_CUDA_OK(cudaMemcpy(out, o, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost));
     cudaFree(d);

@@ -7,7 +7,6 @@
 //   D^T(.)      = per-vertex gather over incident (tet, corner) pairs, fixed order, no atomics.
 #pragma once
 #include "common.cuh"
-#include "svd3.cuh"
 
 namespace aaadmm {
 
@@ -24,260 +23,21 @@ struct TetArrays {
 
 enum { MODE_WARM = 0, MODE_ITER = 1, MODE_REDO = 2 };
 
-// F = Ds * Binv, column-major F[r*3+j]; Ds columns are x_{k+1} - x_0.
-__device__ __forceinline__ void deformation_gradient(const double *__restrict__ pos, const int4 id,
-                                                     const double (&b)[9], double (&F)[9]) {
-    double x0[3], d[9];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) x0[j] = pos[3 * (size_t)id.x + j];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        d[0 * 3 + j] = pos[3 * (size_t)id.y + j] - x0[j];
-        d[1 * 3 + j] = pos[3 * (size_t)id.z + j] - x0[j];
-        d[2 * 3 + j] = pos[3 * (size_t)id.w + j] - x0[j];
-    }
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-            F[r * 3 + j] = d[0 * 3 + j] * b[r * 3 + 0] + d[1 * 3 + j] * b[r * 3 + 1] + d[2 * 3 + j] * b[r * 3 + 2];
-}
-
-// Same for a difference of two position sets (dual residual D (x - x_last)).
-__device__ __forceinline__ void deformation_gradient_diff(const double *__restrict__ pa, const double *__restrict__ pb,
-                                                          const int4 id, const double (&b)[9], double (&F)[9]) {
-    double x0[3], d[9];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) x0[j] = pa[3 * (size_t)id.x + j] - pb[3 * (size_t)id.x + j];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        d[0 * 3 + j] = (pa[3 * (size_t)id.y + j] - pb[3 * (size_t)id.y + j]) - x0[j];
-        d[1 * 3 + j] = (pa[3 * (size_t)id.z + j] - pb[3 * (size_t)id.z + j]) - x0[j];
-        d[2 * 3 + j] = (pa[3 * (size_t)id.w + j] - pb[3 * (size_t)id.w + j]) - x0[j];
-    }
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-            F[r * 3 + j] = d[0 * 3 + j] * b[r * 3 + 0] + d[1 * 3 + j] * b[r * 3 + 1] + d[2 * 3 + j] * b[r * 3 + 2];
-}
-
-// Corner contributions of D^T W (W z - u) scaled by rho dt^2: q[c*3+j], c = 0..3.
-__device__ __forceinline__ void corner_contrib(const double (&b)[9], double w, double rho_dt2, const double (&y)[9],
-                                               double (&q)[12]) {
-#pragma unroll
-    for (int c = 1; c < 4; ++c)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            // G(r,c) = Binv(c-1, r) = b[r*3 + c-1]
-            q[c * 3 + j] = (rho_dt2 * (w * b[0 * 3 + c - 1])) * y[0 * 3 + j] +
-                           (rho_dt2 * (w * b[1 * 3 + c - 1])) * y[1 * 3 + j] +
-                           (rho_dt2 * (w * b[2 * 3 + c - 1])) * y[2 * 3 + j];
-        }
-#pragma unroll
-    for (int j = 0; j < 3; ++j) q[j] = -(q[3 + j] + q[6 + j] + q[9 + j]);
-}
-
-// hard_zxu local step (hard/src/Solver.cpp:133-140 + EnergyTerm::update_z + TetEnergyTerm::prox):
-//   z = prox((D x - c + u)/w), prim^2 = |D x - W z - c|^2, and the per-corner D^T W(Wz - u)
-//   contributions for the following x-update.  The finishing CTA takes the accept/reject
-//   decision of hard/src/Solver.cpp:146 on the device.
-template <int MODE>
-__global__ void __launch_bounds__(TET_BLOCK)
-k_update_z_hard(TetArrays A, const double *__restrict__ pos, const double *__restrict__ u, double *__restrict__ z,
-                double *__restrict__ contrib, SolveState *st, double *partials) {
-    if (st->done) return;
-    if (MODE == MODE_REDO && !st->reject) return;
-    const int T = A.n_tets;
-    double acc[1] = {0.0};
-    for (int t = blockIdx.x * TET_BLOCK + threadIdx.x; t < T; t += gridDim.x * TET_BLOCK) {
-        const int4 id = A.idx[t];
-        double b[9], F[9], zi[9], ui[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) b[k] = A.binv[(size_t)k * T + t];
-        const double w = A.w[t];
-        deformation_gradient(pos, id, b, F);
-        const double winv = 1.0 / w;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            ui[k] = u[(size_t)k * T + t];
-            F[k] = w * F[k];               // D_i x - c_i
-            zi[k] = (F[k] + ui[k]) * winv;  // W^-1 (D_i x + u_i - c_i)
-        }
-        tet_prox_linear(zi);
-        double y[9], q[12];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            z[(size_t)k * T + t] = zi[k];
-            const double wz = w * zi[k];
-            const double r = F[k] - wz;
-            acc[0] += r * r;
-            y[k] = wz - ui[k];
-        }
-        corner_contrib(b, w, A.rho_dt2, y, q);
-        double *qo = contrib + (size_t)t * 12;
-#pragma unroll
-        for (int k = 0; k < 12; k += 2) *reinterpret_cast<double2 *>(qo + k) = make_double2(q[k], q[k + 1]);
-    }
-    double out[1];
-    if (grid_reduce<1, TET_BLOCK>(acc, partials, &st->ticket, out)) {
-        if (threadIdx.x == 0) {
-            const double prim = sqrt(out[0]);
-            st->prim2 = out[0];
-            if (MODE == MODE_ITER) {
-                if (st->accel && st->prev_prim < prim) {
-                    st->reject = 1;
-                } else {
-                    st->reject = 0;
-                    st->prev_prim = prim;
-                }
-            } else if (MODE == MODE_REDO) {
-                st->prev_prim = prim;
-                st->n_rejects += 1;
-            }
-        }
-    }
-}
-
-// (u,x) <- default (u,x) and AndersonAcceleration::reset (hard/src/Solver.cpp:151-155).
-__global__ void k_restore_if_reject(double *__restrict__ ucur, const double *__restrict__ gdef, int64_t n,
-                                    SolveState *st) {
-    if (st->done || !st->reject) return;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) ucur[i] = gdef[i];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        st->aa_iter = 0;
-        st->aa_col = 0;
-    }
-}
-
-// b = M x_bar + rho dt^2 D^T (W z + C_fix - u), written in the factor's elimination order.
-__global__ void k_rhs_gather(int n_free, const int64_t *__restrict__ inc_ptr, const int *__restrict__ inc,
-                             const double *__restrict__ contrib, const double *__restrict__ bconst,
-                             const int *__restrict__ iperm, double *__restrict__ W, const SolveState *st) {
-    if (st->done) return;
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_free) return;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    const int64_t p1 = inc_ptr[v + 1];
-    for (int64_t p = inc_ptr[v]; p < p1; ++p) {
-        const int e = inc[p];  // tet*4 + corner
-        const double *q = contrib + (size_t)(e >> 2) * 12 + (e & 3) * 3;
-        s0 += q[0];
-        s1 += q[1];
-        s2 += q[2];
-    }
-    const size_t o = (size_t)iperm[v] * 3;
-    W[o + 0] = bconst[3 * (size_t)v + 0] + s0;
-    W[o + 1] = bconst[3 * (size_t)v + 1] + s1;
-    W[o + 2] = bconst[3 * (size_t)v + 2] + s2;
-}
-
-// Per frame: bconst = M x_bar + rho dt^2 D^T C_fix, C_fix = m_C x_pin (hard/src/Solver.cpp:79,83).
-__global__ void k_bconst(TetArrays A, const int64_t *__restrict__ inc_ptr, const int *__restrict__ inc,
-                         const double *__restrict__ pos, const double *__restrict__ mass,
-                         const double *__restrict__ xbar, double *__restrict__ bconst) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= A.n_free) return;
-    const int T = A.n_tets;
-    double s[3] = {0.0, 0.0, 0.0};
-    const int64_t p1 = inc_ptr[v + 1];
-    for (int64_t p = inc_ptr[v]; p < p1; ++p) {
-        const int e = inc[p];
-        const int t = e >> 2, c = e & 3;
-        const int4 id = A.idx[t];
-        const int ids[4] = {id.x, id.y, id.z, id.w};
-        if (ids[0] < A.n_free && ids[1] < A.n_free && ids[2] < A.n_free && ids[3] < A.n_free) continue;
-        double b[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) b[k] = A.binv[(size_t)k * T + t];
-        const double w = A.w[t];
-        // G(r,k): k=0 -> -(sum), k>=1 -> b[r*3+k-1]
-        double cf[9];  // C_fix block, cf[r*3+j] = -w sum_{k pinned} G(r,k) xpin_k[j]
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                double a = 0.0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (ids[k] >= A.n_free) {
-                        const double g = (k == 0) ? -(b[r * 3 + 0] + b[r * 3 + 1] + b[r * 3 + 2]) : b[r * 3 + k - 1];
-                        a += (w * g) * pos[3 * (size_t)ids[k] + j];
-                    }
-                }
-                cf[r * 3 + j] = -a;
-            }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            double a = 0.0;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const double g = (c == 0) ? -(b[r * 3 + 0] + b[r * 3 + 1] + b[r * 3 + 2]) : b[r * 3 + c - 1];
-                a += (A.rho_dt2 * (w * g)) * cf[r * 3 + j];
-            }
-            s[j] += a;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 3; ++j) bconst[3 * (size_t)v + j] = mass[v] * xbar[3 * (size_t)v + j] + s[j];
-}
-
-// hard_zxu: u += D x - W z - c, comb = |D x - W z - c|^2 + |D (x - x_last)|^2
-// (hard/src/Solver.cpp:183-196 + EnergyTerm::update_u).  The finishing CTA applies the break test
-// and logs the iteration on the device.
-template <int MODE>
-__global__ void __launch_bounds__(TET_BLOCK)
-k_update_u_hard(TetArrays A, const double *__restrict__ pos_new, const double *__restrict__ pos_last,
-                const double *__restrict__ z, const double *__restrict__ u_in, double *__restrict__ u_out,
-                SolveState *st, double *partials, double *hist_prim, double *hist_comb, int *hist_rej) {
-    if (st->done) return;
-    const int T = A.n_tets;
-    double acc[2] = {0.0, 0.0};
-    for (int t = blockIdx.x * TET_BLOCK + threadIdx.x; t < T; t += gridDim.x * TET_BLOCK) {
-        const int4 id = A.idx[t];
-        double b[9], F[9], dFm[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) b[k] = A.binv[(size_t)k * T + t];
-        const double w = A.w[t];
-        deformation_gradient(pos_new, id, b, F);
-        if (MODE == MODE_ITER) deformation_gradient_diff(pos_new, pos_last, id, b, dFm);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const double r = w * F[k] - w * z[(size_t)k * T + t];
-            u_out[(size_t)k * T + t] = u_in[(size_t)k * T + t] + r;
-            if (MODE == MODE_ITER) {
-                acc[0] += r * r;
-                const double d = w * dFm[k];
-                acc[1] += d * d;
-            }
-        }
-    }
-    if (MODE != MODE_ITER) return;
-    double out[2];
-    if (grid_reduce<2, TET_BLOCK>(acc, partials, &st->ticket, out)) {
-        if (threadIdx.x == 0) {
-            const double comb = out[0] + out[1];
-            st->comb = comb;
-            if (comb < st->eps) {
-                st->done = 1;
-            } else {
-                const int it = st->iter;
-                hist_prim[it] = st->prev_prim;
-                hist_comb[it] = comb;
-                hist_rej[it] = st->reject;
-                st->iter = it + 1;
-            }
-            st->reject = 0;
-        }
-    }
-}
-
-__global__ void k_copy_if_not_done(double *__restrict__ dst, const double *__restrict__ src, int64_t n,
-                                   const SolveState *st) {
-    if (st->done) return;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
-}
+// Host launchers (tet_kernels.cu is compiled with -fmad=false: the per-element arithmetic follows
+// the reference operation by operation, and fused multiply-adds would change its rounding and,
+// for degenerate elements, its branch decisions).
+void launch_update_z_hard(int mode, int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *u,
+                          double *z, double *contrib, SolveState *st, double *partials);
+void launch_update_u_hard(int mode, int grid, cudaStream_t s, const TetArrays &A, const double *pos_new,
+                          const double *pos_last, const double *z, const double *u_in, double *u_out, SolveState *st,
+                          double *partials, double *hist_prim, double *hist_comb, int *hist_rej);
+void launch_restore_if_reject(int grid, cudaStream_t s, double *ucur, const double *gdef, int64_t n, SolveState *st);
+void launch_rhs_gather(cudaStream_t s, int n_free, const int64_t *inc_ptr, const int *inc, const double *contrib,
+                       const double *bconst, const int *iperm, double *W, const SolveState *st);
+void launch_bconst(cudaStream_t s, const TetArrays &A, const int64_t *inc_ptr, const int *inc, const double *pos,
+                   const double *mass, const double *xbar, double *bconst);
+void launch_copy_if_not_done(cudaStream_t s, double *dst, const double *src, int64_t n, const SolveState *st);
+void launch_prox_batch(double *d_z, int64_t n);
+void launch_fmuvt_batch(const double *d_z, double *d_out, int64_t n);
 
 }  // namespace aaadmm
