@@ -32,29 +32,79 @@ __device__ __forceinline__ void warp_sum(double (&a)[NR]) {
     }
 }
 
+// Work distribution shared by the four sweep kernels: the first n_long CTAs take one LONG row
+// each (all 8 warps stride over it, fixed-shape combine through shared memory); the remaining
+// CTAs take 8 SHORT rows each, one warp per row. Either way one row is summed by one fixed set
+// of lanes in a fixed order: the result is deterministic and needs no atomics.
+struct RowLists {
+    const int *long_rows;
+    int n_long;
+    const int *short_rows;
+    int n_short;
+};
+
+template <int NR>
+__device__ __forceinline__ bool pick_row(const RowLists &L, int &row, int &tid, int &nthr) {
+    if ((int)blockIdx.x < L.n_long) {
+        row = L.long_rows[blockIdx.x];
+        tid = threadIdx.x;
+        nthr = WARPS_PER_CTA * 32;
+        return true;
+    }
+    const int wid = ((int)blockIdx.x - L.n_long) * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (wid >= L.n_short) return false;
+    row = L.short_rows[wid];
+    tid = threadIdx.x & 31;
+    nthr = 32;
+    return true;
+}
+
+// Reduces acc over the lanes that worked on the row; returns true in the one thread holding it.
+template <int NR>
+__device__ __forceinline__ bool row_reduce(const RowLists &L, double (&acc)[NR]) {
+    warp_sum<NR>(acc);
+    if ((int)blockIdx.x >= L.n_long) return (threadIdx.x & 31) == 0;
+    __shared__ double s_part[WARPS_PER_CTA][NR];
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) s_part[warp][r] = acc[r];
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return false;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        double x = 0.0;
+#pragma unroll
+        for (int w = 0; w < WARPS_PER_CTA; ++w) x += s_part[w][r];
+        acc[r] = x;
+    }
+    return true;
+}
+
 // W[row] -= sum_{off-block cols c} L(row,c) * Y[c]
 template <int NR>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_fwd_off(const int *__restrict__ rows, int nrows, const int64_t *__restrict__ ptr, const int *__restrict__ col,
-          const double *__restrict__ val, const double *__restrict__ Y, double *__restrict__ W, const int *skip) {
+k_fwd_off(RowLists L, const int64_t *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val,
+          const double *__restrict__ Y, double *__restrict__ W, const int *skip) {
     if (skip && *skip) return;
-    const int wid = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (wid >= nrows) return;
-    const int lane = threadIdx.x & 31;
-    const int row = rows[wid];
-    const int64_t p0 = ptr[row], p1 = ptr[row + 1];
+    int row, tid, nthr;
+    const bool active = pick_row<NR>(L, row, tid, nthr);
     double acc[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) acc[r] = 0.0;
+    if (active) {
+        const int64_t p0 = ptr[row], p1 = ptr[row + 1];
 #pragma unroll 4
-    for (int64_t p = p0 + lane; p < p1; p += 32) {
-        const int c = __ldg(col + p);
-        const double v = __ldg(val + p);
+        for (int64_t p = p0 + tid; p < p1; p += nthr) {
+            const int c = __ldg(col + p);
+            const double v = __ldg(val + p);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) acc[r] += v * Y[(size_t)c * NR + r];
+            for (int r = 0; r < NR; ++r) acc[r] += v * Y[(size_t)c * NR + r];
+        }
     }
-    warp_sum<NR>(acc);
-    if (lane == 0) {
+    if ((int)blockIdx.x >= L.n_long && !active) return;
+    if (row_reduce<NR>(L, acc)) {
 #pragma unroll
         for (int r = 0; r < NR; ++r) W[(size_t)row * NR + r] -= acc[r];
     }
@@ -63,30 +113,30 @@ k_fwd_off(const int *__restrict__ rows, int nrows, const int64_t *__restrict__ p
 // Y[row] = sum_{j<=i} Linv(i,j) W[first+j]     (dense inverse of the unit-lower diagonal block)
 template <int NR>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_fwd_diag(const int *__restrict__ rows, int nrows, const int *__restrict__ blk_of, const int *__restrict__ blk_first,
+k_fwd_diag(RowLists L, const int *__restrict__ blk_of, const int *__restrict__ blk_first,
            const int64_t *__restrict__ linv_off, const double *__restrict__ Linv, const double *__restrict__ W,
            double *__restrict__ Y, const int *skip) {
     if (skip && *skip) return;
-    const int wid = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (wid >= nrows) return;
-    const int lane = threadIdx.x & 31;
-    const int row = rows[wid];
-    const int b = blk_of[row];
-    const int first = blk_first[b];
-    const int ns = blk_first[b + 1] - first;
-    const int i = row - first;
-    const double *Lrow = Linv + linv_off[b] + (size_t)i * ns;
+    int row, tid, nthr;
+    const bool active = pick_row<NR>(L, row, tid, nthr);
     double acc[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) acc[r] = 0.0;
+    if (active) {
+        const int b = blk_of[row];
+        const int first = blk_first[b];
+        const int ns = blk_first[b + 1] - first;
+        const int i = row - first;
+        const double *Lrow = Linv + linv_off[b] + (size_t)i * ns;
 #pragma unroll 4
-    for (int j = lane; j <= i; j += 32) {
-        const double v = __ldg(Lrow + j);
+        for (int j = tid; j <= i; j += nthr) {
+            const double v = __ldg(Lrow + j);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) acc[r] += v * W[(size_t)(first + j) * NR + r];
+            for (int r = 0; r < NR; ++r) acc[r] += v * W[(size_t)(first + j) * NR + r];
+        }
     }
-    warp_sum<NR>(acc);
-    if (lane == 0) {
+    if ((int)blockIdx.x >= L.n_long && !active) return;
+    if (row_reduce<NR>(L, acc)) {
 #pragma unroll
         for (int r = 0; r < NR; ++r) Y[(size_t)row * NR + r] = acc[r];
     }
@@ -95,27 +145,27 @@ k_fwd_diag(const int *__restrict__ rows, int nrows, const int *__restrict__ blk_
 // W[j] = Y[j]/D[j] - sum_{off-block rows i} L(i,j) X[i]
 template <int NR>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_bwd_off(const int *__restrict__ rows, int nrows, const int64_t *__restrict__ ptr, const int *__restrict__ rowidx,
-          const double *__restrict__ val, const double *__restrict__ dinv, const double *__restrict__ Y,
-          const double *__restrict__ X, double *__restrict__ W, const int *skip) {
+k_bwd_off(RowLists L, const int64_t *__restrict__ ptr, const int *__restrict__ rowidx, const double *__restrict__ val,
+          const double *__restrict__ dinv, const double *__restrict__ Y, const double *__restrict__ X,
+          double *__restrict__ W, const int *skip) {
     if (skip && *skip) return;
-    const int wid = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (wid >= nrows) return;
-    const int lane = threadIdx.x & 31;
-    const int j = rows[wid];
-    const int64_t p0 = ptr[j], p1 = ptr[j + 1];
+    int j, tid, nthr;
+    const bool active = pick_row<NR>(L, j, tid, nthr);
     double acc[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) acc[r] = 0.0;
+    if (active) {
+        const int64_t p0 = ptr[j], p1 = ptr[j + 1];
 #pragma unroll 4
-    for (int64_t p = p0 + lane; p < p1; p += 32) {
-        const int i = __ldg(rowidx + p);
-        const double v = __ldg(val + p);
+        for (int64_t p = p0 + tid; p < p1; p += nthr) {
+            const int i = __ldg(rowidx + p);
+            const double v = __ldg(val + p);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) acc[r] += v * X[(size_t)i * NR + r];
+            for (int r = 0; r < NR; ++r) acc[r] += v * X[(size_t)i * NR + r];
+        }
     }
-    warp_sum<NR>(acc);
-    if (lane == 0) {
+    if ((int)blockIdx.x >= L.n_long && !active) return;
+    if (row_reduce<NR>(L, acc)) {
         const double di = dinv[j];
 #pragma unroll
         for (int r = 0; r < NR; ++r) W[(size_t)j * NR + r] = Y[(size_t)j * NR + r] * di - acc[r];
@@ -125,30 +175,30 @@ k_bwd_off(const int *__restrict__ rows, int nrows, const int64_t *__restrict__ p
 // X[row] = sum_{j>=i} LinvT(i,j) W[first+j]; also scatter to the caller's ordering.
 template <int NR>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_bwd_diag(const int *__restrict__ rows, int nrows, const int *__restrict__ blk_of, const int *__restrict__ blk_first,
+k_bwd_diag(RowLists L, const int *__restrict__ blk_of, const int *__restrict__ blk_first,
            const int64_t *__restrict__ linv_off, const double *__restrict__ LinvT, const double *__restrict__ W,
            double *__restrict__ X, const int *__restrict__ perm, double *__restrict__ x_out, const int *skip) {
     if (skip && *skip) return;
-    const int wid = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (wid >= nrows) return;
-    const int lane = threadIdx.x & 31;
-    const int row = rows[wid];
-    const int b = blk_of[row];
-    const int first = blk_first[b];
-    const int ns = blk_first[b + 1] - first;
-    const int i = row - first;
-    const double *Lrow = LinvT + linv_off[b] + (size_t)i * ns;
+    int row, tid, nthr;
+    const bool active = pick_row<NR>(L, row, tid, nthr);
     double acc[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) acc[r] = 0.0;
+    if (active) {
+        const int b = blk_of[row];
+        const int first = blk_first[b];
+        const int ns = blk_first[b + 1] - first;
+        const int i = row - first;
+        const double *Lrow = LinvT + linv_off[b] + (size_t)i * ns;
 #pragma unroll 4
-    for (int j = i + lane; j < ns; j += 32) {
-        const double v = __ldg(Lrow + j);
+        for (int j = i + tid; j < ns; j += nthr) {
+            const double v = __ldg(Lrow + j);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) acc[r] += v * W[(size_t)(first + j) * NR + r];
+            for (int r = 0; r < NR; ++r) acc[r] += v * W[(size_t)(first + j) * NR + r];
+        }
     }
-    warp_sum<NR>(acc);
-    if (lane == 0) {
+    if ((int)blockIdx.x >= L.n_long && !active) return;
+    if (row_reduce<NR>(L, acc)) {
         const int o = perm[row];
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
@@ -235,7 +285,6 @@ void ldlt_dev_destroy(LdltDev *f) {
     cudaFree(f->bc_row);
     cudaFree(f->bc_val);
     cudaFree(f->lev_rows);
-    cudaFree(f->lev_off_rows);
     cudaFree(f->W);
     cudaFree(f->Y);
     cudaFree(f->X);
@@ -254,7 +303,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     const int64_t nnz = Lp[n];
 
     // ---- block partition: elimination-tree chains with nested patterns ----
-    const int kSmall = 32, kCap = 6144;
+    const int kSmall = 96, kCap = 6144;
     std::vector<int> blk_of(n), blk_first;
     for (int j = 0; j < n; ++j) {
         bool join = false;
@@ -333,28 +382,26 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         }
     }
 
-    // ---- level lists ----
-    std::vector<int> lev_cnt(nlev + 1, 0), lev_off_cnt(nlev + 1, 0);
+    // ---- level lists: per level and per sweep kernel, LONG rows (one CTA each) and SHORT rows ----
+    // kinds: 0 fwd_off (rows with off-block entries), 1 fwd_diag, 2 bwd_off, 3 bwd_diag
+    const int64_t kLong = 128;
+    std::vector<std::vector<int>> lists((size_t)nlev * 8);
     for (int j = 0; j < n; ++j) {
-        const int l = level[blk_of[j]];
-        lev_cnt[l + 1]++;
-        if (fr_ptr[j + 1] > fr_ptr[j]) lev_off_cnt[l + 1]++;
+        const int b = blk_of[j];
+        const int l = level[b];
+        const int i = j - blk_first[b], ns = blk_first[b + 1] - blk_first[b];
+        const int64_t fo = fr_ptr[j + 1] - fr_ptr[j], bo = bc_ptr[j + 1] - bc_ptr[j];
+        if (fo > 0) lists[(size_t)l * 8 + 0 + (fo > kLong ? 0 : 1)].push_back(j);
+        lists[(size_t)l * 8 + 2 + (i + 1 > kLong ? 0 : 1)].push_back(j);
+        lists[(size_t)l * 8 + 4 + (bo > kLong ? 0 : 1)].push_back(j);
+        lists[(size_t)l * 8 + 6 + (ns - i > kLong ? 0 : 1)].push_back(j);
     }
-    for (int l = 0; l < nlev; ++l) {
-        lev_cnt[l + 1] += lev_cnt[l];
-        lev_off_cnt[l + 1] += lev_off_cnt[l];
+    std::vector<int> lev_rows;
+    f->list_ptr.assign((size_t)nlev * 8 + 1, 0);
+    for (size_t k = 0; k < lists.size(); ++k) {
+        lev_rows.insert(lev_rows.end(), lists[k].begin(), lists[k].end());
+        f->list_ptr[k + 1] = (int)lev_rows.size();
     }
-    std::vector<int> lev_rows(n), lev_off_rows(std::max(1, lev_off_cnt[nlev]));
-    {
-        std::vector<int> p0(lev_cnt.begin(), lev_cnt.end() - 1), p1(lev_off_cnt.begin(), lev_off_cnt.end() - 1);
-        for (int j = 0; j < n; ++j) {
-            const int l = level[blk_of[j]];
-            lev_rows[p0[l]++] = j;
-            if (fr_ptr[j + 1] > fr_ptr[j]) lev_off_rows[p1[l]++] = j;
-        }
-    }
-    f->lev_ptr = lev_cnt;
-    f->lev_off_ptr = lev_off_cnt;
 
     std::vector<int> permv(perm, perm + n), iperm(n);
     for (int k = 0; k < n; ++k) iperm[perm[k]] = k;
@@ -376,7 +423,6 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     rc |= upload(&f->bc_row, bc_row);
     rc |= upload(&f->bc_val, bc_val);
     rc |= upload(&f->lev_rows, lev_rows);
-    rc |= upload(&f->lev_off_rows, lev_off_rows);
     rc |= upload(&f->LinvT, Tdense);  // holds T until the inversion below has run
     if (rc) {
         ldlt_dev_destroy(f);
@@ -433,24 +479,31 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
 template <int NR>
 static int apply_impl(LdltDev *f, double *x_out, cudaStream_t s, const int *skip) {
     const int nlev = f->n_levels;
+    auto lists = [&](int l, int kind) {
+        RowLists L;
+        const int a = f->list_ptr[(size_t)l * 8 + 2 * kind], b = f->list_ptr[(size_t)l * 8 + 2 * kind + 1],
+                  c = f->list_ptr[(size_t)l * 8 + 2 * kind + 2];
+        L.long_rows = f->lev_rows + a;
+        L.n_long = b - a;
+        L.short_rows = f->lev_rows + b;
+        L.n_short = c - b;
+        return L;
+    };
+    auto grid = [](const RowLists &L) { return L.n_long + (L.n_short + WARPS_PER_CTA - 1) / WARPS_PER_CTA; };
+    const int T = WARPS_PER_CTA * 32;
     for (int l = 0; l < nlev; ++l) {
-        const int o0 = f->lev_off_ptr[l], o1 = f->lev_off_ptr[l + 1];
-        if (o1 > o0)
-            k_fwd_off<NR><<<(o1 - o0 + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, s>>>(
-                f->lev_off_rows + o0, o1 - o0, f->fr_ptr, f->fr_col, f->fr_val, f->Y, f->W, skip);
-        const int r0 = f->lev_ptr[l], r1 = f->lev_ptr[l + 1];
-        if (r1 > r0)
-            k_fwd_diag<NR><<<(r1 - r0 + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, s>>>(
-                f->lev_rows + r0, r1 - r0, f->blk_of, f->blk_first, f->linv_off, f->Linv, f->W, f->Y, skip);
+        RowLists a = lists(l, 0), b = lists(l, 1);
+        if (grid(a) > 0) k_fwd_off<NR><<<grid(a), T, 0, s>>>(a, f->fr_ptr, f->fr_col, f->fr_val, f->Y, f->W, skip);
+        if (grid(b) > 0)
+            k_fwd_diag<NR><<<grid(b), T, 0, s>>>(b, f->blk_of, f->blk_first, f->linv_off, f->Linv, f->W, f->Y, skip);
     }
     for (int l = nlev - 1; l >= 0; --l) {
-        const int r0 = f->lev_ptr[l], r1 = f->lev_ptr[l + 1];
-        if (r1 <= r0) continue;
-        const int g = (r1 - r0 + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        k_bwd_off<NR><<<g, WARPS_PER_CTA * 32, 0, s>>>(f->lev_rows + r0, r1 - r0, f->bc_ptr, f->bc_row, f->bc_val,
-                                                       f->dinv, f->Y, f->X, f->W, skip);
-        k_bwd_diag<NR><<<g, WARPS_PER_CTA * 32, 0, s>>>(f->lev_rows + r0, r1 - r0, f->blk_of, f->blk_first,
-                                                        f->linv_off, f->LinvT, f->W, f->X, f->perm, x_out, skip);
+        RowLists a = lists(l, 2), b = lists(l, 3);
+        if (grid(a) > 0)
+            k_bwd_off<NR><<<grid(a), T, 0, s>>>(a, f->bc_ptr, f->bc_row, f->bc_val, f->dinv, f->Y, f->X, f->W, skip);
+        if (grid(b) > 0)
+            k_bwd_diag<NR><<<grid(b), T, 0, s>>>(b, f->blk_of, f->blk_first, f->linv_off, f->LinvT, f->W, f->X,
+                                                 f->perm, x_out, skip);
     }
     AAADMM_CUDA_OK(cudaGetLastError());
     return 0;

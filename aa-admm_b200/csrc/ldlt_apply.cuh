@@ -34,11 +34,10 @@ struct LdltDev {
     int64_t *bc_ptr = nullptr;
     int *bc_row = nullptr;
     double *bc_val = nullptr;
-    // per level: all rows, and the rows that have off-block entries
-    std::vector<int> lev_ptr;      // host copy [n_levels+1] into lev_rows
-    std::vector<int> lev_off_ptr;  // host copy [n_levels+1] into lev_off_rows
+    // per level and sweep kernel (fwd_off, fwd_diag, bwd_off, bwd_diag): LONG rows then SHORT rows;
+    // list_ptr[(level*4 + kind)*2 + {0,1,2}] delimit them inside lev_rows
+    std::vector<int> list_ptr;
     int *lev_rows = nullptr;
-    int *lev_off_rows = nullptr;
     // work vectors n x nrhs
     double *W = nullptr, *Y = nullptr, *X = nullptr;
     LdltStats stats;
