@@ -74,7 +74,9 @@ __global__ void k_soa_to_aos9(const double *__restrict__ soa, double *__restrict
     for (int k = 0; k < 9; ++k) aos[9 * (size_t)t + k] = soa[(size_t)k * T + t];
 }
 
-__global__ void k_init_state(SolveState *st, int accel, int m, double eps) {
+__global__ void k_init_state(SolveState *st, int accel, int m, double eps, int max_iters) {
+    st->loop_it = 0;
+    st->max_iters = max_iters;
     st->prim2 = 0.0;
     st->prev_prim = 1e+20;
     st->comb = 0.0;
@@ -89,6 +91,13 @@ __global__ void k_init_state(SolveState *st, int accel, int m, double eps) {
     st->aa_m = m;
     st->aa_mk = 0;
     st->ticket = 0u;
+}
+// Tail of one loop turn inside the graph WHILE node: advance the device-side iteration counter and
+// decide whether the body runs again (hard/src/Solver.cpp:130 `for` bound and :188 `break`).
+__global__ void k_loop_cond(cudaGraphConditionalHandle h, SolveState *st) {
+    const int it = st->loop_it + 1;
+    st->loop_it = it;
+    cudaGraphSetConditional(h, (!st->done && it < st->max_iters) ? 1u : 0u);
 }
 __global__ void k_aa_set_counters(SolveState *st, int iter, int col) {
     st->aa_iter = iter;
@@ -146,6 +155,11 @@ struct aaadmm_tetscene {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int launches = 0;
     bool has_inputs = false;
+    // the whole iteration loop as ONE graph launch: a conditional WHILE node whose body is one loop turn
+    cudaGraph_t loop_graph = nullptr;
+    cudaGraphExec_t loop_exec = nullptr;
+    int loop_key = -1;  // accel * 64 + m the graph was built for
+    int body_launches = 0;
 };
 
 extern "C" {
@@ -194,7 +208,7 @@ int aaadmm_aa_create(aaadmm_aa **out, int m, int64_t total_dim, int64_t effectiv
     AAADMM_CUDA_OK(cudaMemsetAsync(a->st, 0, sizeof(SolveState), a->stream));
     AAADMM_CUDA_OK(cudaMemsetAsync(a->dF, 0, sizeof(double) * effective_dim * m, a->stream));
     AAADMM_CUDA_OK(cudaMemsetAsync(a->dG, 0, sizeof(double) * total_dim * m, a->stream));
-    k_init_state<<<1, 1, 0, a->stream>>>(a->st, 1, m, 0.0);
+    k_init_state<<<1, 1, 0, a->stream>>>(a->st, 1, m, 0.0, 0);
     k_aa_set_counters<<<1, 1, 0, a->stream>>>(a->st, -1, -1);
     AAADMM_CUDA_OK(cudaStreamSynchronize(a->stream));
     *out = a;
@@ -360,6 +374,8 @@ int aaadmm_tetscene_destroy(aaadmm_tetscene *s) {
     if (s->xout_h) cudaFreeHost(s->xout_h);
     for (auto &e : s->ev)
         if (e) cudaEventDestroy(e);
+    if (s->loop_exec) cudaGraphExecDestroy(s->loop_exec);
+    if (s->loop_graph) cudaGraphDestroy(s->loop_graph);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return 0;
@@ -446,6 +462,7 @@ static int scene_reserve(aaadmm_tetscene *s, int iters, int m) {
         AAADMM_CUDA_OK(cudaMalloc((void **)&s->hist_comb, sizeof(double) * iters));
         AAADMM_CUDA_OK(cudaMalloc((void **)&s->hist_rej, sizeof(int) * iters));
         s->hist_cap = iters;
+        s->loop_key = -1;
     }
     if (m > s->m_cap) {
         cudaFree(s->dF);
@@ -453,6 +470,7 @@ static int scene_reserve(aaadmm_tetscene *s, int iters, int m) {
         AAADMM_CUDA_OK(cudaMalloc((void **)&s->dF, sizeof(double) * s->Ne * m));
         AAADMM_CUDA_OK(cudaMalloc((void **)&s->dG, sizeof(double) * s->Nt * m));
         s->m_cap = m;
+        s->loop_key = -1;
     }
     return 0;
 }
@@ -482,7 +500,8 @@ struct PhaseProf {
 }  // namespace
 
 // hard_zxu ordering: hard/src/Solver.cpp:74-214 from "Initialize ADMM vars" to the end of the loop.
-static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *prof, int iters, bool init_frame) {
+static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *prof, int iters, bool init_frame,
+                    bool use_graph = false) {
     cudaStream_t st = s->stream;
     LdltDev *f = s->factor->f;
     const int T = s->T, NF = s->NF;
@@ -499,7 +518,7 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
     if (!prof) prof = &none;
 
     if (init_frame) {
-        k_init_state<<<1, 1, 0, st>>>(s->st, accel ? 1 : 0, m, o->eps);
+        k_init_state<<<1, 1, 0, st>>>(s->st, accel ? 1 : 0, m, o->eps, iters);
         // pinned tails of the three position arrays; x = x_bar; u = 0
         if (s->NP > 0) {
             const size_t pb = sizeof(double) * 3 * s->NP;
@@ -521,6 +540,33 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
         AAADMM_CUDA_OK(cudaMemcpyAsync(s->Ubuf, s->Gbuf, sizeof(double) * s->Nt, cudaMemcpyDeviceToDevice, st));
         L += 6 + 4 * f->n_levels;
     }
+    // ---- the loop: one graph launch (WHILE node, device-side break), or plain launches when profiling ----
+    cudaGraphConditionalHandle cond_handle = 0;
+    bool capturing = false;
+    if (use_graph && iters > 0) {
+        const int key = (accel ? 64 : 0) + m;
+        if (s->loop_key == key && s->loop_exec) {
+            AAADMM_CUDA_OK(cudaGraphLaunch(s->loop_exec, st));
+            return 0;
+        }
+        if (s->loop_exec) cudaGraphExecDestroy(s->loop_exec), s->loop_exec = nullptr;
+        if (s->loop_graph) cudaGraphDestroy(s->loop_graph), s->loop_graph = nullptr;
+        AAADMM_CUDA_OK(cudaGraphCreate(&s->loop_graph, 0));
+        AAADMM_CUDA_OK(cudaGraphConditionalHandleCreate(&cond_handle, s->loop_graph, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = cond_handle;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        AAADMM_CUDA_OK(cudaGraphAddNode(&node, s->loop_graph, nullptr, 0, &np));
+        AAADMM_CUDA_OK(cudaStreamBeginCaptureToGraph(st, np.conditional.phGraph_out[0], nullptr, nullptr, 0,
+                                                     cudaStreamCaptureModeThreadLocal));
+        capturing = true;
+        iters = 1;
+        s->loop_key = key;
+    }
+    const int L_before = L;
     for (int it = 0; it < iters; ++it) {
         prof->begin(0);
         launch_update_z_hard(MODE_ITER, gt, st, A, Ux, Uu, s->z, s->contrib, s->st, s->partials);
@@ -564,6 +610,25 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
             ++L;
         }
     }
+    if (capturing) {
+        k_loop_cond<<<1, 1, 0, st>>>(cond_handle, s->st);
+        s->body_launches = L - L_before + 1;
+        L = L_before;
+        cudaError_t e = cudaStreamEndCapture(st, nullptr);
+        if (e != cudaSuccess) {
+            s->loop_key = -1;
+            set_last_error(std::string("loop graph capture failed: ") + cudaGetErrorString(e));
+            return -1;
+        }
+        e = cudaGraphInstantiate(&s->loop_exec, s->loop_graph, 0);
+        if (e != cudaSuccess) {
+            s->loop_key = -1;
+            set_last_error(std::string("loop graph instantiate failed: ") + cudaGetErrorString(e));
+            return -1;
+        }
+        AAADMM_CUDA_OK(cudaGraphLaunch(s->loop_exec, st));
+        return 0;
+    }
     AAADMM_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -597,7 +662,7 @@ static int step_common(aaadmm_tetscene *s, const aaadmm_step_opts *o, bool host_
         s->has_inputs = true;
     }
     AAADMM_CUDA_OK(cudaEventRecord(s->ev[1], st));
-    if (run_hard(s, o, nullptr, o->admm_iters, true)) return -1;
+    if (run_hard(s, o, nullptr, o->admm_iters, true, true)) return -1;
     AAADMM_CUDA_OK(cudaEventRecord(s->ev[2], st));
     SolveState hs;
     if (host_io) {
@@ -621,7 +686,7 @@ static int step_common(aaadmm_tetscene *s, const aaadmm_step_opts *o, bool host_
         res->broke_early = hs.done;
         cudaEventElapsedTime(&res->loop_ms, s->ev[1], s->ev[2]);
         cudaEventElapsedTime(&res->step_ms, s->ev[0], s->ev[3]);
-        res->kernel_launches = s->launches;
+        res->kernel_launches = s->launches + hs.loop_it * s->body_launches;
     }
     return 0;
 }

@@ -50,6 +50,7 @@ struct SolveState {
     double aa_M[AA_MAX_M * AA_MAX_M];  // scaled Gram matrix, column-major with ld = AA_MAX_M
     double aa_coef[AA_MAX_M];          // theta ./ scale of the current call
     unsigned int ticket;               // last-block election counter of the reducing kernels
+    int loop_it, max_iters;            // device-side loop control of the graph WHILE node
 };
 
 // ---------------------------------------------------------------------------------------

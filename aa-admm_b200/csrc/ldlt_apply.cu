@@ -303,7 +303,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     const int64_t nnz = Lp[n];
 
     // ---- block partition: elimination-tree chains with nested patterns ----
-    const int kSmall = 96, kCap = 6144;
+    const int kSmall = 32, kCap = 6144;
     std::vector<int> blk_of(n), blk_first;
     for (int j = 0; j < n; ++j) {
         bool join = false;
@@ -384,7 +384,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
 
     // ---- level lists: per level and per sweep kernel, LONG rows (one CTA each) and SHORT rows ----
     // kinds: 0 fwd_off (rows with off-block entries), 1 fwd_diag, 2 bwd_off, 3 bwd_diag
-    const int64_t kLong = 128;
+    const int64_t kLong = 1024;
     std::vector<std::vector<int>> lists((size_t)nlev * 8);
     for (int j = 0; j < n; ++j) {
         const int b = blk_of[j];
