@@ -16,7 +16,7 @@ inline double cofactor(const double *m, int i, int j) {
 }
 inline void inverse3(const double *m, double *inv) {
     const double c0 = cofactor(m, 0, 0), c1 = cofactor(m, 1, 0), c2 = cofactor(m, 2, 0);
-    const double det = c0 * M(m, 0, 0) + (c1 * M(m, 1, 0) + c2 * M(m, 2, 0));
+    const double det = (c0 * M(m, 0, 0) + c1 * M(m, 1, 0)) + c2 * M(m, 2, 0);  // packet (a0,a1) reduced first, then the tail
     const double invdet = 1.0 / det;
     inv[0 * 3 + 0] = c0 * invdet;  // row 0
     inv[1 * 3 + 0] = c1 * invdet;

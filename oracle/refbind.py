@@ -298,3 +298,140 @@ def ref_cod_rank(M):
     lib.ref_cod_rank.argtypes = [C.c_int, c_dp]
     M = np.asfortranarray(M, np.float64)
     return lib.ref_cod_rank(M.shape[0], M.ctypes.data_as(c_dp))
+
+
+# ---------------------------------------------------------------------------------------------
+# The C restatement (oracle/port/aaadmm_port.c -> oracle/liboracle_port.so)
+# ---------------------------------------------------------------------------------------------
+PORT_LIB = os.path.join(HERE, "liboracle_port.so")
+_port = None
+
+
+def port_lib():
+    global _port
+    if _port is None:
+        P = C.CDLL(PORT_LIB)
+        P.port_tet_prox.argtypes = [c_dp, C.c_int]
+        P.port_tet_fmuvt.argtypes = [c_dp, c_dp, C.c_int]
+        P.port_cod_solve.argtypes = [C.c_int, c_dp, c_dp, c_dp]
+        P.port_aa_new.restype = C.c_void_p
+        P.port_aa_new.argtypes = [C.c_int, C.c_int, C.c_int]
+        P.port_aa_free.argtypes = [C.c_void_p]
+        for n in ("init", "reset", "replace"):
+            getattr(P, "port_aa_" + n).argtypes = [C.c_void_p, c_dp]
+        P.port_aa_compute.argtypes = [C.c_void_p, c_dp, c_dp]
+        P.port_scene_new.restype = C.c_void_p
+        P.port_scene_new.argtypes = [C.c_int, c_dp, C.c_int, c_ip, c_dp, C.c_double, C.c_double, C.c_int, c_ip,
+                                     C.c_double, C.c_double, C.c_int]
+        P.port_scene_free.argtypes = [C.c_void_p]
+        P.port_scene_nfree.argtypes = [C.c_void_p]
+        P.port_scene_step.argtypes = [C.c_void_p, c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_double, c_dp, c_dp, c_ip]
+        _port = P
+    return _port
+
+
+def port_tet_prox(z):
+    out = np.ascontiguousarray(z, np.float64).copy()
+    port_lib().port_tet_prox(_dp(out), out.shape[0])
+    return out
+
+
+def port_tet_F_minus_UVt(z):
+    z = np.ascontiguousarray(z, np.float64)
+    out = np.zeros_like(z)
+    port_lib().port_tet_fmuvt(_dp(z), _dp(out), z.shape[0])
+    return out
+
+
+def port_cod_solve(M, rhs):
+    M = np.asfortranarray(M, np.float64)
+    rhs = np.ascontiguousarray(rhs, np.float64)
+    out = np.zeros_like(rhs)
+    rank = port_lib().port_cod_solve(M.shape[0], M.ctypes.data_as(c_dp), _dp(rhs), _dp(out))
+    return out, rank
+
+
+class PortAnderson:
+    def __init__(self, m, total_dim, effective_dim=None):
+        self.P = port_lib()
+        self.n = total_dim
+        self.h = C.c_void_p(self.P.port_aa_new(m, total_dim, total_dim if effective_dim is None else effective_dim))
+
+    def __del__(self):
+        try:
+            self.P.port_aa_free(self.h)
+        except Exception:
+            pass
+
+    def init(self, u):
+        u = np.ascontiguousarray(u, np.float64)
+        self.P.port_aa_init(self.h, _dp(u))
+
+    def reset(self, u):
+        u = np.ascontiguousarray(u, np.float64)
+        self.P.port_aa_reset(self.h, _dp(u))
+
+    def replace(self, u):
+        u = np.ascontiguousarray(u, np.float64)
+        self.P.port_aa_replace(self.h, _dp(u))
+
+    def compute(self, g):
+        g = np.ascontiguousarray(g, np.float64)
+        out = np.zeros_like(g)
+        self.P.port_aa_compute(self.h, _dp(g), _dp(out))
+        return out
+
+
+class PortSolver:
+    """The C restatement of admm::Solver (LINEAR tets), ordering 'hard' or 'xzu'."""
+
+    def __init__(self, variant="hard"):
+        self.P = port_lib()
+        self.ordering = 0 if variant == "hard" else 1
+        self.h = None
+        self.verts = None
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.P.port_scene_free(self.h)
+        except Exception:
+            pass
+
+    def add_tetmesh(self, verts, tets, masses, youngs=1e7, poisson=0.399, material=0):
+        assert material == 0 and self.verts is None
+        self.verts = np.ascontiguousarray(verts, np.float32).astype(np.float64)
+        self.tets = np.ascontiguousarray(tets, np.int32)
+        self.masses = np.ascontiguousarray(masses, np.float32).astype(np.float64)
+        self.youngs, self.poisson = youngs, poisson
+        self._x = self.verts.reshape(-1).copy()
+        self._v = np.zeros_like(self._x)
+
+    def set_pins(self, idx, pts):
+        self.pin_idx = np.ascontiguousarray(idx, np.int32)
+        order = np.argsort(self.pin_idx, kind="stable")
+        # the reference pairs the k-th pinned vertex (ascending id) with the k-th point handed over
+        self.pin_pts = np.ascontiguousarray(pts, np.float64).copy()
+        self._pin_sorted = self.pin_idx[order]
+
+    def initialize(self, dt=1.0 / 30.0, iters=100, gravity=-9.8, anderson_m=5, accel=True, penalty=1.0):
+        self.dt, self.iters, self.gravity, self.m, self.accel = dt, iters, gravity, anderson_m, accel
+        h = self.P.port_scene_new(len(self.verts), _dp(self.verts), len(self.tets), _ip(self.tets), _dp(self.masses),
+                                  self.youngs, self.poisson, len(self.pin_idx), _ip(self.pin_idx), dt, penalty, self.ordering)
+        if not h:
+            raise RuntimeError("port: inverted rest tet")
+        self.h = C.c_void_p(h)
+        self._v[:] = 0.0
+
+    def step(self):
+        n = max(1, self.iters)
+        prim, comb, rej = np.zeros(n), np.zeros(n), np.zeros(n, np.int32)
+        rows = self.P.port_scene_step(self.h, _dp(self._x), _dp(self._v), _dp(self.pin_pts), self.iters, self.m,
+                                      int(bool(self.accel)), self.gravity, _dp(prim), _dp(comb), _ip(rej))
+        return np.stack([np.zeros(rows), prim[:rows], comb[:rows], rej[:rows].astype(np.float64)], axis=1)
+
+    def x(self):
+        return self._x.copy()
+
+    def v(self):
+        return self._v.copy()

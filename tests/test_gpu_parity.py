@@ -141,3 +141,88 @@ def test_hard_step_vs_reference(gpu, ref, dims, m, accel):
         xerr = np.abs(xg[f] - xr[f]).max() / np.abs(xr[f]).max()
         print("final position rel err", xerr)
         assert xerr < 1e-6
+
+
+# ---- the same checks against the committed golden vectors and the C restatement -------------
+import os  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_prox_and_cod_vs_golden(gpu):
+    g = np.load(os.path.join(GOLD, "tet_element.npz"))
+    assert np.abs(gpu.tet_prox_linear(g["F"]) - g["prox"]).max() < 1e-15
+    assert np.abs(gpu.tet_f_minus_uvt(g["F"]) - g["fmuvt"]).max() < 1e-15
+    c = np.load(os.path.join(GOLD, "cod.npz"))
+    for M, rhs, sol, (m, rank) in zip(c["M"], c["rhs"], c["sol"], c["m_rank"]):
+        x, rk = gpu.cod_solve(M[:m, :m], rhs[:m])
+        assert rk == rank
+        assert np.abs(x - sol[:m]).max() <= 1e-9 * max(1.0, np.abs(sol).max())
+
+
+def test_anderson_vs_golden_streams(gpu):
+    g = np.load(os.path.join(GOLD, "anderson.npz"))
+    for tag in ("a", "b", "c"):
+        m, n, ne = (int(v) for v in g["H%s_dims" % tag])
+        a = gpu.AndersonAcceleration(m, n, ne)
+        a.init(g["H%s_u0" % tag])
+        u = g["H%s_u0" % tag].copy()
+        for it, (gi, ui) in enumerate(zip(g["H%s_G" % tag], g["H%s_U" % tag])):
+            if it == 6:
+                a.reset(u)
+            if it == 8:
+                u = u * 0.5
+                a.replace(u)
+            u = a.compute(gi)
+            assert np.abs(u - ui).max() <= 1e-9 * np.abs(ui).max(), (tag, it)
+            u = ui.copy()
+            a.replace(u)  # follow the reference stream
+
+
+@pytest.mark.parametrize("name", ["hard_beam_12x3x3_m5", "hard_beam_12x3x3_noacc", "hard_beam_8x2x2_m3",
+                                  "hard_3beams_6x2x2_m5"])
+def test_hard_step_vs_golden(gpu, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    dims = tuple(int(d) for d in g["dims"])
+    _, hg, xg = run_product(gpu, beam_arrays(gpu, *dims, n_beams=int(g["n_beams"])), 2, m=max(int(g["m"]), 1),
+                            accel=bool(g["accel"]))
+    for f in range(2):
+        rows = int(g["rows"][f])
+        n = min(rows, len(hg[f]))
+        rel = np.abs(hg[f][:n, 1] - g["comb"][f][:n]) / g["comb"][f][:n]
+        floor = np.abs(hg[f][:n, 1] - g["comb"][f][:n]) / g["comb"][f][0]
+        assert rel[:8].max() < 1e-9
+        assert floor.max() < 1e-9
+        assert abs(len(hg[f]) - rows) <= max(2, 0.25 * rows)
+        assert np.array_equal(hg[f][:8, 2], g["rej"][f][:8])
+        assert np.abs(xg[f] - g["x"][f]).max() / np.abs(g["x"][f]).max() < 1e-6
+
+
+def test_hard_step_vs_port_larger_beam(gpu):
+    """30,720-tet beam (three times the largest golden scene) against the C restatement."""
+    from oracle import refbind as R
+    dims = (32, 8, 8)
+    _, hg, xg = run_product(gpu, beam_arrays(gpu, *dims), 1, m=5, accel=True)
+    scene = beam_arrays(gpu, *dims)
+    verts, tets, masses, pidx, ppts, pside = scene.arrays()
+    s = R.PortSolver("hard")
+    s.add_tetmesh(verts, tets, masses)
+    dt = 1.0 / 30.0
+    s.set_pins(pidx, scene.stretch(dt))
+    s.initialize(dt, 100, -9.8, 5, True, 1.0)
+    s.set_pins(pidx, scene.stretch(dt))
+    hp = s.step()
+    n = min(len(hp), len(hg[0]))
+    rel = np.abs(hg[0][:n, 1] - hp[:n, 2]) / hp[:n, 2]
+    assert rel[:8].max() < 1e-9
+    assert (np.abs(hg[0][:n, 1] - hp[:n, 2]) / hp[0, 2]).max() < 1e-9
+    assert np.abs(xg[0] - s.x()).max() / np.abs(s.x()).max() < 1e-6
+
+
+def test_step_is_deterministic_and_resident_path_matches(gpu):
+    """Two identical runs give bit-identical trajectories (fixed-order reductions, no float atomics)."""
+    _, h1, x1 = run_product(gpu, beam_arrays(gpu, 16, 4, 4), 2, m=5, accel=True)
+    _, h2, x2 = run_product(gpu, beam_arrays(gpu, 16, 4, 4), 2, m=5, accel=True)
+    for f in range(2):
+        assert np.array_equal(h1[f], h2[f])
+        assert np.array_equal(x1[f], x2[f])

@@ -1,0 +1,170 @@
+"""CPU suite, part 2: host-side logic of the product (no compute calls: there is no GPU here) and
+the C-ABI surface."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def test_beam_scene_matches_reference_generator_bitwise(A):
+    g = np.load(os.path.join(G, "beam_scene.npz"))
+    for dims in [(12, 3, 3), (5, 2, 4), (7, 7, 1)]:
+        k = "%dx%dx%d" % dims
+        v, t, m, pidx, ppts, pside = A.BeamScene().add(*dims, 1.75).arrays()
+        assert np.array_equal(v, g["verts_" + k])
+        assert np.array_equal(t, g["tets_" + k])
+        assert np.array_equal(m, g["masses_" + k])
+        lo, hi = v[:, 0].min(), v[:, 0].max()
+        assert set(pidx) == set(np.nonzero((v[:, 0] < lo + np.float32(1e-2)) | (v[:, 0] > hi - np.float32(1e-2)))[0])
+
+
+def test_beam_stretch_moves_pins_like_beams_cpp(A):
+    sc = A.BeamScene().add(4, 2, 2, 0.0)
+    _, _, _, pidx, p0, side = sc.arrays()
+    dt = 1.0 / 30.0
+    p1 = sc.stretch(dt)
+    assert np.allclose(p1[:, 0] - p0[:, 0], np.where(side == 0, -dt, dt), rtol=0, atol=1e-15)
+    assert np.array_equal(p1[:, 1:], p0[:, 1:])
+
+
+def test_tet_constants_match_reference_bitwise(A):
+    g = np.load(os.path.join(G, "tet_element.npz"))
+    H = A.host_lib()
+    for tv, c in zip(g["tet_verts"], g["tet_consts"]):
+        binv, vol, w = np.zeros(9), C.c_double(), C.c_double()
+        r12 = np.ascontiguousarray(tv.reshape(-1))
+        assert H.aaadmm_host_tet_constants(r12.ctypes.data_as(A.c_dp), 1e7, 0.399, binv.ctypes.data_as(A.c_dp),
+                                           C.byref(vol), C.byref(w)) == 0
+        assert w.value == c[0] and vol.value == c[1]
+        assert np.array_equal(binv, c[2:])
+    inv = np.array([[0, 0, 0], [1, 0, 0], [0, 0, 1], [0, 1, 0.0]]).reshape(-1)  # inverted rest tet
+    assert H.aaadmm_host_tet_constants(inv.ctypes.data_as(A.c_dp), 1e7, 0.399, binv.ctypes.data_as(A.c_dp),
+                                       C.byref(vol), C.byref(w)) != 0
+
+
+def _grid_spd(nx, ny, nz, rng):
+    n = nx * ny * nz
+    idx = np.arange(n).reshape(nx, ny, nz)
+    Afull = np.zeros((n, n))
+    for d in range(3):
+        a = np.take(idx, np.arange(idx.shape[d] - 1), axis=d).ravel()
+        b = np.take(idx, np.arange(1, idx.shape[d]), axis=d).ravel()
+        w = rng.uniform(0.5, 2.0, a.size)
+        Afull[a, b] -= w
+        Afull[b, a] -= w
+        Afull[a, a] += w
+        Afull[b, b] += w
+    Afull += np.diag(rng.uniform(0.1, 1.0, n))
+    coords = np.stack(np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij"), -1).reshape(-1, 3).astype(float)
+    L = np.tril(Afull)
+    Ap, Ai, Ax = [0], [], []
+    for j in range(n):
+        r = np.nonzero(L[:, j])[0]
+        Ai += list(r)
+        Ax += list(L[r, j])
+        Ap.append(len(Ai))
+    return Afull, coords, Ap, Ai, Ax
+
+
+@pytest.mark.parametrize("with_coords", [True, False])
+def test_host_nested_dissection_ldlt(A, with_coords):
+    rng = np.random.default_rng(5)
+    Afull, coords, Ap, Ai, Ax = _grid_spd(8, 7, 6, rng)
+    n = Afull.shape[0]
+    hf = A.HostFactor(n, Ap, Ai, Ax, coords if with_coords else None, leaf_size=12)
+    Lp, Li, Lx, D, perm = hf.arrays()
+    assert sorted(perm) == list(range(n))
+    # L D L^T == P A P^T
+    Ld = np.eye(n)
+    for j in range(n):
+        Ld[Li[Lp[j]:Lp[j + 1]], j] = Lx[Lp[j]:Lp[j + 1]]
+        assert np.all(np.diff(Li[Lp[j]:Lp[j + 1]]) > 0) and np.all(Li[Lp[j]:Lp[j + 1]] > j)
+    assert np.abs(Ld @ np.diag(D) @ Ld.T - Afull[np.ix_(perm, perm)]).max() < 1e-11
+    for nrhs in (1, 3):
+        b = rng.standard_normal(n * nrhs)
+        x = hf.solve(b, nrhs)
+        assert np.abs(x.reshape(n, nrhs) - np.linalg.solve(Afull, b.reshape(n, nrhs))).max() < 1e-10
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(aaadmm_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_c_abi_exports_every_declared_symbol(A):
+    for header, lib in (("aaadmm.h", A.LIB_CUDA), ("aaadmm_host.h", A.LIB_HOST)):
+        out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
+        exported = set(l.split()[-1] for l in out.splitlines() if " T " in l)
+        names = _declared(header)
+        assert len(names) > 10
+        missing = [n for n in names if n not in exported]
+        assert not missing, missing
+
+
+def test_no_cpu_fallback_without_a_gpu(A):
+    if A.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(A.AaadmmError, match="no CUDA device"):
+        A.AndersonAcceleration(3, 10, 10)
+    with pytest.raises(A.AaadmmError, match="no CUDA device"):
+        A.tet_prox_linear(np.eye(3).reshape(1, 9))
+    with pytest.raises(A.AaadmmError, match="no CUDA device"):
+        A.make_beam_solver(4, 2, 2)
+
+
+def test_product_never_imports_the_oracle():
+    for d, _, files in os.walk(os.path.join(ROOT, "aa-admm_b200")):
+        for f in files:
+            # build.py only BUILDS the checker (make -C oracle); nothing in the package loads or calls it
+            if f.endswith((".py", ".cpp", ".hpp", ".cu", ".cuh", ".h")) and f != "build.py":
+                txt = open(os.path.join(d, f), errors="ignore").read()
+                assert "oracle" not in txt and "refbind" not in txt, os.path.join(d, f)
+
+
+def _ensemble_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    from aa_admm_b200 import ensemble as E
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = E.scenes_of_rank(7, rank, world)
+    recs = [E.make_record(s, 10 + s, s % 2, 1e-3 * s, 1e-6 * s, 2.0 * s, 3.0 * s, rank) for s in mine]
+    table = E.gather_records(np.array(recs).reshape(-1, 8), dist)
+    q.put((rank, table))
+    dist.destroy_process_group()
+
+
+def test_ensemble_sharding_and_gather_gloo_world2(A):
+    import socket
+    import torch.multiprocessing as mp
+    from aa_admm_b200 import ensemble as E
+    assert E.scenes_of_rank(64, 3, 8) == list(range(3, 64, 8))
+    e0, n0 = E.scene_material(0)
+    e63, n63 = E.scene_material(63)
+    assert e0 == 1e6 and abs(n0 - 0.30) < 1e-15 and abs(e63 - 1e8) < 1e-3 and abs(n63 - 0.44) < 1e-12
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_ensemble_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+    for r in (0, 1):
+        t = res[r]
+        assert t.shape == (7, 8)
+        assert list(t[:, 0]) == list(range(7))
+        assert list(t[:, 7]) == [s % 2 for s in range(7)]
+        assert np.allclose(t[:, 1], 10 + np.arange(7))
