@@ -4,6 +4,7 @@
 #include "../../include/aaadmm.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -662,7 +663,10 @@ static int step_common(aaadmm_tetscene *s, const aaadmm_step_opts *o, bool host_
         s->has_inputs = true;
     }
     AAADMM_CUDA_OK(cudaEventRecord(s->ev[1], st));
-    if (run_hard(s, o, nullptr, o->admm_iters, true, true)) return -1;
+    // AAADMM_NO_GRAPH=1: plain stream launches instead of the graph WHILE node (for profilers that
+    // want every kernel as its own launch); same kernels, same order.
+    static const bool no_graph = getenv("AAADMM_NO_GRAPH") != nullptr;
+    if (run_hard(s, o, nullptr, o->admm_iters, true, !no_graph)) return -1;
     AAADMM_CUDA_OK(cudaEventRecord(s->ev[2], st));
     SolveState hs;
     if (host_io) {
