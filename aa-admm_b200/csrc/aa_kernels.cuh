@@ -18,6 +18,7 @@
 namespace aaadmm {
 
 constexpr int AA_BLOCK = 256;
+constexpr int AA_ILP = 2;  // elements per thread and loop turn in the streaming passes
 
 // Runs in thread 0 of the finishing CTA of pass 1. acc[0..M) = <dF_c, dF_j> (acc[c] = |dF_c|^2),
 // acc[M..2M) = <dF_j, F>, all raw.
@@ -102,18 +103,40 @@ k_aa_pass1(const double *__restrict__ g_u, const double *__restrict__ g_x, doubl
     for (int q = 0; q < 2 * M; ++q) acc[q] = 0.0;
     double *dFc = dF + (size_t)c * Ne;
     double *dGc = dG + (size_t)c * Nt;
-    for (int64_t i = i0; i < Ne; i += stride) {
-        const double g = g_u[i];
-        const double F = g - ucur[i];
-        const double a = dFc[i] + F;
-        dFc[i] = a;
-        dGc[i] += g;
+    // AA_ILP elements per thread and turn: all loads are issued before the first store (the stores
+    // to column c alias the loads of the other columns for the compiler, which would otherwise
+    // serialise the turns and leave one element's worth of loads in flight).
+    for (int64_t base = i0; base < Ne; base += stride * AA_ILP) {
+        double g[AA_ILP], uc[AA_ILP], fc[AA_ILP], gc[AA_ILP], h[AA_ILP][M];
 #pragma unroll
-        for (int j = 0; j < M; ++j) {
-            if (j < mk) {
-                const double v = (j == c) ? a : dF[(size_t)j * Ne + i];
-                acc[j] += a * v;
-                acc[M + j] += v * F;
+        for (int e = 0; e < AA_ILP; ++e) {
+            const int64_t i = base + e * stride;
+            if (i < Ne) {
+                g[e] = g_u[i];
+                uc[e] = ucur[i];
+                fc[e] = dFc[i];
+                gc[e] = dGc[i];
+#pragma unroll
+                for (int j = 0; j < M; ++j)
+                    if (j < mk && j != c) h[e][j] = dF[(size_t)j * Ne + i];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < AA_ILP; ++e) {
+            const int64_t i = base + e * stride;
+            if (i < Ne) {
+                const double F = g[e] - uc[e];
+                const double a = fc[e] + F;
+                dFc[i] = a;
+                dGc[i] = gc[e] + g[e];
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    if (j < mk) {
+                        const double v = (j == c) ? a : h[e][j];
+                        acc[j] += a * v;
+                        acc[M + j] += v * F;
+                    }
+                }
             }
         }
     }
@@ -140,15 +163,29 @@ k_aa_pass2(const double *__restrict__ g_u, const double *__restrict__ g_x, doubl
 #pragma unroll
     for (int j = 0; j < M; ++j) coef[j] = (j < mk) ? st->aa_coef[j] : 0.0;
     const int64_t stride = (int64_t)gridDim.x * AA_BLOCK;
-    for (int64_t i = (int64_t)blockIdx.x * AA_BLOCK + threadIdx.x; i < Nt; i += stride) {
-        const double g = (i < Ne) ? g_u[i] : g_x[i - Ne];
-        double s = 0.0;
+    for (int64_t base = (int64_t)blockIdx.x * AA_BLOCK + threadIdx.x; base < Nt; base += stride * AA_ILP) {
+        double g[AA_ILP], uc[AA_ILP], s[AA_ILP];
 #pragma unroll
-        for (int j = 0; j < M; ++j)
-            if (j < mk) s += dG[(size_t)j * Nt + i] * coef[j];
-        if (i < Ne) dF[(size_t)cn * Ne + i] = -(g - ucur[i]);
-        dG[(size_t)cn * Nt + i] = -g;
-        ucur[i] = g - s;
+        for (int e = 0; e < AA_ILP; ++e) {
+            const int64_t i = base + e * stride;
+            s[e] = 0.0;
+            if (i < Nt) {
+                g[e] = (i < Ne) ? g_u[i] : g_x[i - Ne];
+                uc[e] = (i < Ne) ? ucur[i] : 0.0;
+#pragma unroll
+                for (int j = 0; j < M; ++j)
+                    if (j < mk) s[e] += dG[(size_t)j * Nt + i] * coef[j];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < AA_ILP; ++e) {
+            const int64_t i = base + e * stride;
+            if (i < Nt) {
+                if (i < Ne) dF[(size_t)cn * Ne + i] = -(g[e] - uc[e]);
+                dG[(size_t)cn * Nt + i] = -g[e];
+                ucur[i] = g[e] - s[e];
+            }
+        }
     }
 }
 

@@ -72,36 +72,44 @@ __device__ __forceinline__ void corner_contrib(const double (&b)[9], double w, d
 //   contributions for the following x-update.  The finishing CTA takes the accept/reject
 //   decision of hard/src/Solver.cpp:146 on the device.
 template <int MODE>
-__global__ void __launch_bounds__(TET_BLOCK)
+__global__ void __launch_bounds__(TET_BLOCK, 4)
 k_update_z_hard(TetArrays A, const double *__restrict__ pos, const double *__restrict__ u, double *__restrict__ z,
                 double *__restrict__ contrib, SolveState *st, double *partials) {
     if (st->done) return;
     if (MODE == MODE_REDO && !st->reject) return;
     const int T = A.n_tets;
     double acc[1] = {0.0};
+    // B^-1 and u are parked in shared memory while the Jacobi SVD runs: 36 fewer live registers
+    __shared__ double s_park[18][TET_BLOCK];
     for (int t = blockIdx.x * TET_BLOCK + threadIdx.x; t < T; t += gridDim.x * TET_BLOCK) {
         const int4 id = A.idx[t];
-        double b[9], F[9], zi[9], ui[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) b[k] = A.binv[(size_t)k * T + t];
+        double zi[9], F[9];
         const double w = A.w[t];
-        deformation_gradient(pos, id, b, F);
-        const double winv = 1.0 / w;
+        {
+            double b[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            ui[k] = u[(size_t)k * T + t];
-            F[k] = w * F[k];               // D_i x - c_i
-            zi[k] = (F[k] + ui[k]) * winv;  // W^-1 (D_i x + u_i - c_i)
+            for (int k = 0; k < 9; ++k) b[k] = A.binv[(size_t)k * T + t];
+            deformation_gradient(pos, id, b, F);
+            const double winv = 1.0 / w;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const double ui = u[(size_t)k * T + t];
+                F[k] = w * F[k];              // D_i x - c_i
+                zi[k] = (F[k] + ui) * winv;   // W^-1 (D_i x + u_i - c_i)
+                s_park[k][threadIdx.x] = b[k];
+                s_park[9 + k][threadIdx.x] = ui;
+            }
         }
         tet_prox_linear(zi);
-        double y[9], q[12];
+        double b[9], y[9], q[12];
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
             z[(size_t)k * T + t] = zi[k];
             const double wz = w * zi[k];
             const double r = F[k] - wz;
             acc[0] += r * r;
-            y[k] = wz - ui[k];
+            y[k] = wz - s_park[9 + k][threadIdx.x];
+            b[k] = s_park[k][threadIdx.x];
         }
         corner_contrib(b, w, A.rho_dt2, y, q);
         double *qo = contrib + (size_t)t * 12;
