@@ -78,6 +78,7 @@ __global__ void k_soa_to_aos9(const double *__restrict__ soa, double *__restrict
 __global__ void k_init_state(SolveState *st, int accel, int m, double eps, int max_iters) {
     st->loop_it = 0;
     st->max_iters = max_iters;
+    st->skip_redo = 1;
     st->prim2 = 0.0;
     st->prev_prim = 1e+20;
     st->comb = 0.0;
@@ -147,6 +148,7 @@ struct aaadmm_tetscene {
     double *Ubuf = nullptr, *Gbuf = nullptr, *xs = nullptr, *z = nullptr, *contrib = nullptr;
     double *bconst = nullptr, *xbar = nullptr, *xpin = nullptr;
     double *dF = nullptr, *dG = nullptr;
+    double *xz_a = nullptr, *xz_b = nullptr;  // xzu ordering: default_u and comb_z / last_z
     int hist_cap = 0, m_cap = 0;
     double *hist_prim = nullptr, *hist_comb = nullptr;
     int *hist_rej = nullptr;
@@ -365,6 +367,8 @@ int aaadmm_tetscene_destroy(aaadmm_tetscene *s) {
     cudaFree(s->xpin);
     cudaFree(s->dF);
     cudaFree(s->dG);
+    cudaFree(s->xz_a);
+    cudaFree(s->xz_b);
     cudaFree(s->hist_prim);
     cudaFree(s->hist_comb);
     cudaFree(s->hist_rej);
@@ -500,6 +504,51 @@ struct PhaseProf {
 };
 }  // namespace
 
+// Graph WHILE-loop plumbing shared by the two orderings. begin: returns 1 if a cached graph for
+// `key` was launched, 0 if capture of one loop turn has started, -1 on error.
+static int loop_graph_begin(aaadmm_tetscene *s, int key, cudaGraphConditionalHandle *cond_handle) {
+    cudaStream_t st = s->stream;
+    if (s->loop_key == key && s->loop_exec) {
+        AAADMM_CUDA_OK(cudaGraphLaunch(s->loop_exec, st));
+        return 1;
+    }
+    if (s->loop_exec) cudaGraphExecDestroy(s->loop_exec), s->loop_exec = nullptr;
+    if (s->loop_graph) cudaGraphDestroy(s->loop_graph), s->loop_graph = nullptr;
+    AAADMM_CUDA_OK(cudaGraphCreate(&s->loop_graph, 0));
+    AAADMM_CUDA_OK(cudaGraphConditionalHandleCreate(cond_handle, s->loop_graph, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams np = {};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = *cond_handle;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    AAADMM_CUDA_OK(cudaGraphAddNode(&node, s->loop_graph, nullptr, 0, &np));
+    AAADMM_CUDA_OK(cudaStreamBeginCaptureToGraph(st, np.conditional.phGraph_out[0], nullptr, nullptr, 0,
+                                                 cudaStreamCaptureModeThreadLocal));
+    s->loop_key = key;
+    return 0;
+}
+static int loop_graph_end(aaadmm_tetscene *s, cudaGraphConditionalHandle cond_handle, int &L, int L_before) {
+    cudaStream_t st = s->stream;
+    k_loop_cond<<<1, 1, 0, st>>>(cond_handle, s->st);
+    s->body_launches = L - L_before + 1;
+    L = L_before;
+    cudaError_t e = cudaStreamEndCapture(st, nullptr);
+    if (e != cudaSuccess) {
+        s->loop_key = -1;
+        set_last_error(std::string("loop graph capture failed: ") + cudaGetErrorString(e));
+        return -1;
+    }
+    e = cudaGraphInstantiate(&s->loop_exec, s->loop_graph, 0);
+    if (e != cudaSuccess) {
+        s->loop_key = -1;
+        set_last_error(std::string("loop graph instantiate failed: ") + cudaGetErrorString(e));
+        return -1;
+    }
+    AAADMM_CUDA_OK(cudaGraphLaunch(s->loop_exec, st));
+    return 0;
+}
+
 // hard_zxu ordering: hard/src/Solver.cpp:74-214 from "Initialize ADMM vars" to the end of the loop.
 static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *prof, int iters, bool init_frame,
                     bool use_graph = false) {
@@ -545,27 +594,11 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
     cudaGraphConditionalHandle cond_handle = 0;
     bool capturing = false;
     if (use_graph && iters > 0) {
-        const int key = (accel ? 64 : 0) + m;
-        if (s->loop_key == key && s->loop_exec) {
-            AAADMM_CUDA_OK(cudaGraphLaunch(s->loop_exec, st));
-            return 0;
-        }
-        if (s->loop_exec) cudaGraphExecDestroy(s->loop_exec), s->loop_exec = nullptr;
-        if (s->loop_graph) cudaGraphDestroy(s->loop_graph), s->loop_graph = nullptr;
-        AAADMM_CUDA_OK(cudaGraphCreate(&s->loop_graph, 0));
-        AAADMM_CUDA_OK(cudaGraphConditionalHandleCreate(&cond_handle, s->loop_graph, 1, cudaGraphCondAssignDefault));
-        cudaGraphNodeParams np = {};
-        np.type = cudaGraphNodeTypeConditional;
-        np.conditional.handle = cond_handle;
-        np.conditional.type = cudaGraphCondTypeWhile;
-        np.conditional.size = 1;
-        cudaGraphNode_t node;
-        AAADMM_CUDA_OK(cudaGraphAddNode(&node, s->loop_graph, nullptr, 0, &np));
-        AAADMM_CUDA_OK(cudaStreamBeginCaptureToGraph(st, np.conditional.phGraph_out[0], nullptr, nullptr, 0,
-                                                     cudaStreamCaptureModeThreadLocal));
+        const int rc = loop_graph_begin(s, (accel ? 64 : 0) + m, &cond_handle);
+        if (rc < 0) return -1;
+        if (rc == 1) return 0;  // cached graph launched
         capturing = true;
         iters = 1;
-        s->loop_key = key;
     }
     const int L_before = L;
     for (int it = 0; it < iters; ++it) {
@@ -611,25 +644,98 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
             ++L;
         }
     }
-    if (capturing) {
-        k_loop_cond<<<1, 1, 0, st>>>(cond_handle, s->st);
-        s->body_launches = L - L_before + 1;
-        L = L_before;
-        cudaError_t e = cudaStreamEndCapture(st, nullptr);
-        if (e != cudaSuccess) {
-            s->loop_key = -1;
-            set_last_error(std::string("loop graph capture failed: ") + cudaGetErrorString(e));
-            return -1;
-        }
-        e = cudaGraphInstantiate(&s->loop_exec, s->loop_graph, 0);
-        if (e != cudaSuccess) {
-            s->loop_key = -1;
-            set_last_error(std::string("loop graph instantiate failed: ") + cudaGetErrorString(e));
-            return -1;
-        }
-        AAADMM_CUDA_OK(cudaGraphLaunch(s->loop_exec, st));
+    if (capturing) return loop_graph_end(s, cond_handle, L, L_before);
+    AAADMM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// xzu ordering: admm_anderson_xzu/src/Solver.cpp:78-257. Anderson variable = z (Ne = Nt = 9T).
+//   Zcur = Ubuf[0:9T] (accelerator's current_u_ = curr_z), Zdef = Gbuf[0:9T] (default_z),
+//   curr_x = xs, default_x = Gbuf x-part, comb_x = Ubuf x-part, curr_u = s->z, default_u = xz_a,
+//   comb_z / last_z = xz_b.
+static int run_xzu(aaadmm_tetscene *s, const aaadmm_step_opts *o, int iters, bool use_graph) {
+    cudaStream_t st = s->stream;
+    LdltDev *f = s->factor->f;
+    const int T = s->T, NF = s->NF;
+    const bool accel = o->accel && o->anderson_m > 0;
+    const int m = o->anderson_m > 0 ? o->anderson_m : 1;
+    TetArrays A{T, NF, s->V, s->idx, s->binv, s->w, s->kvol, s->rho_dt2};
+    const int gt = std::min((T + TET_BLOCK - 1) / TET_BLOCK, stream_grid(8));
+    const int gs = stream_grid(4);
+    const int64_t NZ = s->Ne, NX = 3 * (int64_t)NF;
+    double *Zcur = s->Ubuf, *Zdef = s->Gbuf, *cx = s->xs, *dx = s->Gbuf + s->Ne, *combx = s->Ubuf + s->Ne;
+    double *u = s->z, *du = s->xz_a, *combz = s->xz_b;
+    int &L = s->launches;
+    auto solve = [&](const double *zz, double *xout, int when) -> int {
+        launch_contrib(gt, st, A, zz, u, s->contrib, s->st, when);
+        launch_rhs_gather(st, NF, s->inc_ptr, s->inc, s->contrib, s->bconst, f->iperm, f->W, s->st, when);
+        if (ldlt_dev_apply_permuted(f, xout, st, when ? &s->st->skip_redo : &s->st->done)) return -1;
+        L += 2 + 4 * f->n_levels;
         return 0;
+    };
+    // ---- frame init + warm start (Solver.cpp:78-117) ----
+    k_init_state<<<1, 1, 0, st>>>(s->st, accel ? 1 : 0, m, o->eps, iters);
+    if (s->NP > 0) {
+        const size_t pb = sizeof(double) * 3 * s->NP;
+        AAADMM_CUDA_OK(cudaMemcpyAsync(cx + NX, s->xpin, pb, cudaMemcpyDeviceToDevice, st));
+        AAADMM_CUDA_OK(cudaMemcpyAsync(dx + NX, s->xpin, pb, cudaMemcpyDeviceToDevice, st));
+        AAADMM_CUDA_OK(cudaMemcpyAsync(combx + NX, s->xpin, pb, cudaMemcpyDeviceToDevice, st));
     }
+    AAADMM_CUDA_OK(cudaMemcpyAsync(cx, s->xbar, sizeof(double) * NX, cudaMemcpyDeviceToDevice, st));
+    AAADMM_CUDA_OK(cudaMemsetAsync(u, 0, sizeof(double) * NZ, st));
+    launch_bconst(st, A, s->inc_ptr, s->inc, cx, s->mass, s->xbar, s->bconst);
+    launch_z_from_x(gt, st, A, cx, Zcur);
+    if (solve(Zcur, cx, 0)) return -1;
+    launch_update_z_plain(gt, st, A, cx, u, Zcur, s->st);
+    // default_(z,x,u) = curr; accelerator.init(m, z_size, curr_z)
+    AAADMM_CUDA_OK(cudaMemcpyAsync(Zdef, Zcur, sizeof(double) * NZ, cudaMemcpyDeviceToDevice, st));
+    AAADMM_CUDA_OK(cudaMemcpyAsync(dx, cx, sizeof(double) * NX, cudaMemcpyDeviceToDevice, st));
+    AAADMM_CUDA_OK(cudaMemsetAsync(du, 0, sizeof(double) * NZ, st));
+    L += 5;
+
+    cudaGraphConditionalHandle cond_handle = 0;
+    bool capturing = false;
+    if (use_graph && iters > 0) {
+        const int rc = loop_graph_begin(s, 1024 + (accel ? 64 : 0) + m, &cond_handle);
+        if (rc < 0) return -1;
+        if (rc == 1) return 0;
+        capturing = true;
+        iters = 1;
+    }
+    const int L_before = L;
+    for (int it = 0; it < iters; ++it) {
+        if (accel) {
+            launch_grad_u_xzu(gt, st, A, Zcur, u, s->st);                                  // :125-133
+        } else {
+            launch_update_u_plain(gt, st, A, cx, Zcur, u, s->st, 0);                       // :135-141
+        }
+        if (solve(Zcur, cx, 0)) return -1;                                                 // :147-149
+        launch_prim_xzu(MODE_ITER, gt, st, A, cx, Zcur, s->st, s->partials);               // :153-159
+        L += 2;
+        if (accel) {
+            launch_restore_xzu(gs, st, u, du, Zcur, Zdef, NZ, cx, dx, NX, s->st);          // :162-166
+            launch_update_u_plain(gt, st, A, cx, Zcur, u, s->st, 1);                       // :168-172
+            if (solve(Zcur, cx, 1)) return -1;                                             // :174-176
+            launch_prim_xzu(MODE_REDO, gt, st, A, cx, Zcur, s->st, s->partials);           // :178-180
+            // default_x = curr_x; default_u = curr_u; default_z = update_z(curr_x, curr_u)   :192-201
+            launch_copy2_if_not_done(gs, st, dx, cx, NX, du, u, NZ, s->st);
+            launch_update_z_plain(gt, st, A, cx, u, Zdef, s->st);
+            if (launch_aa_pass1(m, gs, st, Zdef, nullptr, nullptr, Zcur, s->dF, s->dG, NZ, NZ, s->st, s->partials)) return -1;
+            if (launch_aa_pass2(m, gs, st, Zdef, nullptr, Zcur, s->dF, s->dG, NZ, NZ, s->st)) return -1;
+            // combined residual "for drawing figures": extra solve + local step on copies     :217-233
+            if (solve(Zdef, combx, 0)) return -1;
+            launch_update_z_plain(gt, st, A, combx, u, combz, s->st);
+            launch_comb_xzu(gt, st, A, combx, combz, Zdef, s->st, s->partials, s->hist_prim, s->hist_comb, s->hist_rej);
+            L += 10;
+        } else {
+            // last_z = curr_z; curr_z = update_z(curr_x, curr_u)                               :205-213, :234-238
+            launch_copy2_if_not_done(gs, st, combz, Zcur, NZ, nullptr, nullptr, 0, s->st);
+            launch_update_z_plain(gt, st, A, cx, u, Zcur, s->st);
+            launch_comb_xzu(gt, st, A, cx, Zcur, combz, s->st, s->partials, s->hist_prim, s->hist_comb, s->hist_rej);
+            L += 3;
+        }
+    }
+    if (capturing) return loop_graph_end(s, cond_handle, L, L_before);
     AAADMM_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -640,16 +746,21 @@ static int step_common(aaadmm_tetscene *s, const aaadmm_step_opts *o, bool host_
         set_last_error("tetscene_step: bad options (Anderson_m must be in 1..16 when accel is on)");
         return -1;
     }
-    if (o->ordering != AAADMM_ORDER_HARD_ZXU) {
-        set_last_error("tetscene_step: xzu ordering is not implemented on the device yet");
+    if (o->ordering != AAADMM_ORDER_HARD_ZXU && o->ordering != AAADMM_ORDER_XZU) {
+        set_last_error("tetscene_step: unknown ordering");
         return -1;
+    }
+    const bool xzu = o->ordering == AAADMM_ORDER_XZU;
+    if (xzu && !s->xz_a) {
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->xz_a, sizeof(double) * s->Ne));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->xz_b, sizeof(double) * s->Ne));
     }
     if (!host_io && !s->has_inputs) {
         set_last_error("tetscene_step_resident: call aaadmm_tetscene_step once first");
         return -1;
     }
     const bool accel = o->accel && o->anderson_m > 0;
-    if (scene_reserve(s, std::max(1, o->admm_iters), accel ? o->anderson_m : 1)) return -1;
+    if (scene_reserve(s, std::max(1, o->admm_iters), (accel || xzu) ? std::max(1, o->anderson_m) : 1)) return -1;
     cudaStream_t st = s->stream;
     const int NF = s->NF;
     s->launches = 0;
@@ -666,12 +777,13 @@ static int step_common(aaadmm_tetscene *s, const aaadmm_step_opts *o, bool host_
     // AAADMM_NO_GRAPH=1: plain stream launches instead of the graph WHILE node (for profilers that
     // want every kernel as its own launch); same kernels, same order.
     static const bool no_graph = getenv("AAADMM_NO_GRAPH") != nullptr;
-    if (run_hard(s, o, nullptr, o->admm_iters, true, !no_graph)) return -1;
+    if (xzu ? run_xzu(s, o, o->admm_iters, !no_graph) : run_hard(s, o, nullptr, o->admm_iters, true, !no_graph)) return -1;
     AAADMM_CUDA_OK(cudaEventRecord(s->ev[2], st));
     SolveState hs;
     if (host_io) {
         // hard: default_x when ANDERSON, curr_x otherwise (hard/src/Solver.cpp:216-223)
-        const double *xfinal = accel ? (s->Gbuf + s->Ne) : s->xs;
+        // xzu: curr_x (xzu/src/Solver.cpp:255)
+        const double *xfinal = xzu ? s->xs : (accel ? (s->Gbuf + s->Ne) : s->xs);
         AAADMM_CUDA_OK(cudaMemcpyAsync(s->xout_h, xfinal, sizeof(double) * 3 * NF, cudaMemcpyDeviceToHost, st));
     }
     AAADMM_CUDA_OK(cudaMemcpyAsync(&hs, s->st, sizeof(SolveState), cudaMemcpyDeviceToHost, st));

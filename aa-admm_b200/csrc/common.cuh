@@ -51,6 +51,7 @@ struct SolveState {
     double aa_coef[AA_MAX_M];          // theta ./ scale of the current call
     unsigned int ticket;               // last-block election counter of the reducing kernels
     int loop_it, max_iters;            // device-side loop control of the graph WHILE node
+    int skip_redo;                     // xzu: 1 unless the current iterate was rejected (guards the redo solve)
 };
 
 // ---------------------------------------------------------------------------------------

@@ -151,8 +151,8 @@ __global__ void k_restore_if_reject(double *__restrict__ ucur, const double *__r
 // b = M x_bar + rho dt^2 D^T (W z + C_fix - u), written in the factor's elimination order.
 __global__ void k_rhs_gather(int n_free, const int64_t *__restrict__ inc_ptr, const int *__restrict__ inc,
                              const double *__restrict__ contrib, const double *__restrict__ bconst,
-                             const int *__restrict__ iperm, double *__restrict__ W, const SolveState *st) {
-    if (st->done) return;
+                             const int *__restrict__ iperm, double *__restrict__ W, const SolveState *st, int when) {
+    if (st->done || (when == 1 && !st->reject)) return;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_free) return;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -278,6 +278,206 @@ __global__ void k_copy_if_not_done(double *__restrict__ dst, const double *__res
 }
 
 
+// =========================================================================================
+// xzu ordering (admm_anderson_xzu/src/Solver.cpp:78-257): kernels that differ from hard_zxu
+// =========================================================================================
+
+// u = W^-1 * get_all_gradient(z):  u_i = (1/w) K vol (z_i - U V^T)      (Solver.cpp:125-133)
+__global__ void __launch_bounds__(TET_BLOCK, 4)
+k_grad_u_xzu(TetArrays A, const double *__restrict__ z, double *__restrict__ u, const SolveState *st) {
+    if (st->done) return;
+    const int T = A.n_tets;
+    for (int t = blockIdx.x * TET_BLOCK + threadIdx.x; t < T; t += gridDim.x * TET_BLOCK) {
+        double zi[9], g[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) zi[k] = z[(size_t)k * T + t];
+        tet_grad_linear(zi, A.kvol[t], g);
+        const double winv = 1.0 / A.w[t];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) u[(size_t)k * T + t] = winv * g[k];
+    }
+}
+
+// z0 = W^-1 (D x - C_fix): the unweighted deformation gradient                (Solver.cpp:80-82)
+__global__ void k_z_from_x(TetArrays A, const double *__restrict__ pos, double *__restrict__ z) {
+    const int T = A.n_tets;
+    for (int t = blockIdx.x * TET_BLOCK + threadIdx.x; t < T; t += gridDim.x * TET_BLOCK) {
+        const int4 id = A.idx[t];
+        double b[9], F[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) b[k] = A.binv[(size_t)k * T + t];
+        deformation_gradient(pos, id, b, F);
+        const double w = A.w[t], winv = 1.0 / w;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) z[(size_t)k * T + t] = (w * F[k]) * winv;
+    }
+}
+
+// corner contributions of rho dt^2 D^T W (W z - u) for given z, u
+// `when`: 0 always, 1 only if st->reject (the redo path of a rejected iterate)
+__global__ void k_contrib(TetArrays A, const double *__restrict__ z, const double *__restrict__ u,
+                          double *__restrict__ contrib, const SolveState *st, int when) {
+    if (st->done || (when == 1 && !st->reject)) return;
+    const int T = A.n_tets;
+    for (int t = blockIdx.x * TET_BLOCK + threadIdx.x; t < T; t += gridDim.x * TET_BLOCK) {
+        double b[9], y[9], q[12];
+        const double w = A.w[t];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            b[k] = A.binv[(size_t)k * T + t];
+            y[k] = w * z[(size_t)k * T + t] - u[(size_t)k * T + t];
+        }
+        corner_contrib(b, w, A.rho_dt2, y, q);
+        double *qo = contrib + (size_t)t * 12;
+#pragma unroll
+        for (int k = 0; k < 12; k += 2) *reinterpret_cast<double2 *>(qo + k) = make_double2(q[k], q[k + 1]);
+    }
+}
+
+// prim = |D x - W z - C_fix|; finishing CTA: accept/reject decision (Solver.cpp:154-159) or, on the
+// redo path, just prev_prim = prim (:177-183)
+template <int MODE>
+__global__ void __launch_bounds__(TET_BLOCK)
+k_prim_xzu(TetArrays A, const double *__restrict__ pos, const double *__restrict__ z, SolveState *st, double *partials) {
+    if (st->done) return;
+    if (MODE == MODE_REDO && !st->reject) return;
+    const int T = A.n_tets;
+    double acc[1] = {0.0};
+    for (int t = blockIdx.x * TET_BLOCK + threadIdx.x; t < T; t += gridDim.x * TET_BLOCK) {
+        const int4 id = A.idx[t];
+        double b[9], F[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) b[k] = A.binv[(size_t)k * T + t];
+        deformation_gradient(pos, id, b, F);
+        const double w = A.w[t];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const double r = w * F[k] - w * z[(size_t)k * T + t];
+            acc[0] += r * r;
+        }
+    }
+    double out[1];
+    if (grid_reduce<1, TET_BLOCK>(acc, partials, &st->ticket, out)) {
+        if (threadIdx.x == 0) {
+            const double prim = sqrt(out[0]);
+            st->prim2 = out[0];
+            if (MODE == MODE_ITER) {
+                if (st->accel && st->prev_prim < prim) {
+                    st->reject = 1;
+                    st->n_rejects += 1;
+                } else {
+                    st->reject = 0;
+                    st->prev_prim = prim;
+                }
+                st->skip_redo = !st->reject;
+            } else {
+                st->prev_prim = prim;
+            }
+        }
+    }
+}
+
+// restore (u, x, z) = default_(u, x, z) and accelerator.replace(z) on a rejected iterate (:162-166)
+__global__ void k_restore_xzu(double *__restrict__ u, const double *__restrict__ u_def, double *__restrict__ z,
+                              const double *__restrict__ z_def, int64_t nz, double *__restrict__ x,
+                              const double *__restrict__ x_def, int64_t nx, const SolveState *st) {
+    if (st->done || !st->reject) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nz; i += stride) {
+        u[i] = u_def[i];
+        z[i] = z_def[i];
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += stride) x[i] = x_def[i];
+}
+
+// z_out = prox((D x - c + u)/w)  (EnergyTerm::update_z), no residual, no contributions
+__global__ void __launch_bounds__(TET_BLOCK, 4)
+k_update_z_plain(TetArrays A, const double *__restrict__ pos, const double *__restrict__ u, double *__restrict__ z_out,
+                 const SolveState *st) {
+    if (st && st->done) return;
+    const int T = A.n_tets;
+    for (int t = blockIdx.x * TET_BLOCK + threadIdx.x; t < T; t += gridDim.x * TET_BLOCK) {
+        const int4 id = A.idx[t];
+        double b[9], F[9], zi[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) b[k] = A.binv[(size_t)k * T + t];
+        deformation_gradient(pos, id, b, F);
+        const double w = A.w[t], winv = 1.0 / w;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) zi[k] = (w * F[k] + u[(size_t)k * T + t]) * winv;
+        tet_prox_linear(zi);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) z_out[(size_t)k * T + t] = zi[k];
+    }
+}
+
+// u += D x - W z - c, predicated variants for the xzu loop (when: 0 always, 1 only if reject)
+__global__ void __launch_bounds__(TET_BLOCK)
+k_update_u_plain(TetArrays A, const double *__restrict__ pos, const double *__restrict__ z, double *__restrict__ u,
+                 const SolveState *st, int when) {
+    if (st->done || (when == 1 && !st->reject)) return;
+    const int T = A.n_tets;
+    for (int t = blockIdx.x * TET_BLOCK + threadIdx.x; t < T; t += gridDim.x * TET_BLOCK) {
+        const int4 id = A.idx[t];
+        double b[9], F[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) b[k] = A.binv[(size_t)k * T + t];
+        deformation_gradient(pos, id, b, F);
+        const double w = A.w[t];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) u[(size_t)k * T + t] += w * F[k] - w * z[(size_t)k * T + t];
+    }
+}
+
+// combined residual |W (z_a - z_b)|^2 + |D x - W z_a - C_fix|^2 (Solver.cpp:217-238); the finishing
+// CTA logs the iteration and applies the break test (:240-250)
+__global__ void __launch_bounds__(TET_BLOCK)
+k_comb_xzu(TetArrays A, const double *__restrict__ pos, const double *__restrict__ za, const double *__restrict__ zb,
+           SolveState *st, double *partials, double *hist_prim, double *hist_comb, int *hist_rej) {
+    if (st->done) return;
+    const int T = A.n_tets;
+    double acc[2] = {0.0, 0.0};
+    for (int t = blockIdx.x * TET_BLOCK + threadIdx.x; t < T; t += gridDim.x * TET_BLOCK) {
+        const int4 id = A.idx[t];
+        double b[9], F[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) b[k] = A.binv[(size_t)k * T + t];
+        deformation_gradient(pos, id, b, F);
+        const double w = A.w[t];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const double a = za[(size_t)k * T + t];
+            const double d = w * (a - zb[(size_t)k * T + t]);
+            const double r = w * F[k] - w * a;
+            acc[0] += d * d;
+            acc[1] += r * r;
+        }
+    }
+    double out[2];
+    if (grid_reduce<2, TET_BLOCK>(acc, partials, &st->ticket, out)) {
+        if (threadIdx.x == 0) {
+            const double comb = out[0] + out[1];
+            st->comb = comb;
+            const int it = st->iter;
+            hist_prim[it] = st->prev_prim;
+            hist_comb[it] = comb;
+            hist_rej[it] = st->reject;
+            st->iter = it + 1;
+            st->reject = 0;
+            if (comb < st->eps) st->done = 1;
+        }
+    }
+}
+
+__global__ void k_copy2_if_not_done(double *__restrict__ d0, const double *__restrict__ s0, int64_t n0,
+                                    double *__restrict__ d1, const double *__restrict__ s1, int64_t n1,
+                                    const SolveState *st) {
+    if (st->done) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n0; i += stride) d0[i] = s0[i];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += stride) d1[i] = s1[i];
+}
+
 // ---- batched element kernels (unit parity) ----
 __global__ void k_prox_batch(double *z, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -320,8 +520,8 @@ void launch_restore_if_reject(int grid, cudaStream_t s, double *ucur, const doub
     k_restore_if_reject<<<grid, 256, 0, s>>>(ucur, gdef, n, st);
 }
 void launch_rhs_gather(cudaStream_t s, int n_free, const int64_t *inc_ptr, const int *inc, const double *contrib,
-                       const double *bconst, const int *iperm, double *W, const SolveState *st) {
-    k_rhs_gather<<<(n_free + 127) / 128, 128, 0, s>>>(n_free, inc_ptr, inc, contrib, bconst, iperm, W, st);
+                       const double *bconst, const int *iperm, double *W, const SolveState *st, int when) {
+    k_rhs_gather<<<(n_free + 127) / 128, 128, 0, s>>>(n_free, inc_ptr, inc, contrib, bconst, iperm, W, st, when);
 }
 void launch_bconst(cudaStream_t s, const TetArrays &A, const int64_t *inc_ptr, const int *inc, const double *pos,
                    const double *mass, const double *xbar, double *bconst) {
@@ -333,6 +533,45 @@ void launch_copy_if_not_done(cudaStream_t s, double *dst, const double *src, int
 void launch_prox_batch(double *d_z, int64_t n) { k_prox_batch<<<(unsigned)((n + 127) / 128), 128>>>(d_z, n); }
 void launch_fmuvt_batch(const double *d_z, double *d_out, int64_t n) {
     k_fmuvt_batch<<<(unsigned)((n + 127) / 128), 128>>>(d_z, d_out, n);
+}
+
+void launch_grad_u_xzu(int grid, cudaStream_t s, const TetArrays &A, const double *z, double *u, const SolveState *st) {
+    k_grad_u_xzu<<<grid, TET_BLOCK, 0, s>>>(A, z, u, st);
+}
+void launch_z_from_x(int grid, cudaStream_t s, const TetArrays &A, const double *pos, double *z) {
+    k_z_from_x<<<grid, TET_BLOCK, 0, s>>>(A, pos, z);
+}
+void launch_contrib(int grid, cudaStream_t s, const TetArrays &A, const double *z, const double *u, double *contrib,
+                    const SolveState *st, int when) {
+    k_contrib<<<grid, TET_BLOCK, 0, s>>>(A, z, u, contrib, st, when);
+}
+void launch_prim_xzu(int mode, int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *z,
+                     SolveState *st, double *partials) {
+    if (mode == MODE_ITER)
+        k_prim_xzu<MODE_ITER><<<grid, TET_BLOCK, 0, s>>>(A, pos, z, st, partials);
+    else
+        k_prim_xzu<MODE_REDO><<<grid, TET_BLOCK, 0, s>>>(A, pos, z, st, partials);
+}
+void launch_restore_xzu(int grid, cudaStream_t s, double *u, const double *u_def, double *z, const double *z_def,
+                        int64_t nz, double *x, const double *x_def, int64_t nx, const SolveState *st) {
+    k_restore_xzu<<<grid, 256, 0, s>>>(u, u_def, z, z_def, nz, x, x_def, nx, st);
+}
+void launch_update_z_plain(int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *u,
+                           double *z_out, const SolveState *st) {
+    k_update_z_plain<<<grid, TET_BLOCK, 0, s>>>(A, pos, u, z_out, st);
+}
+void launch_update_u_plain(int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *z, double *u,
+                           const SolveState *st, int when) {
+    k_update_u_plain<<<grid, TET_BLOCK, 0, s>>>(A, pos, z, u, st, when);
+}
+void launch_comb_xzu(int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *za,
+                     const double *zb, SolveState *st, double *partials, double *hist_prim, double *hist_comb,
+                     int *hist_rej) {
+    k_comb_xzu<<<grid, TET_BLOCK, 0, s>>>(A, pos, za, zb, st, partials, hist_prim, hist_comb, hist_rej);
+}
+void launch_copy2_if_not_done(int grid, cudaStream_t s, double *d0, const double *s0, int64_t n0, double *d1,
+                              const double *s1, int64_t n1, const SolveState *st) {
+    k_copy2_if_not_done<<<grid, 256, 0, s>>>(d0, s0, n0, d1, s1, n1, st);
 }
 
 }  // namespace aaadmm

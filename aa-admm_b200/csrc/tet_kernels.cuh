@@ -33,10 +33,28 @@ void launch_update_u_hard(int mode, int grid, cudaStream_t s, const TetArrays &A
                           double *partials, double *hist_prim, double *hist_comb, int *hist_rej);
 void launch_restore_if_reject(int grid, cudaStream_t s, double *ucur, const double *gdef, int64_t n, SolveState *st);
 void launch_rhs_gather(cudaStream_t s, int n_free, const int64_t *inc_ptr, const int *inc, const double *contrib,
-                       const double *bconst, const int *iperm, double *W, const SolveState *st);
+                       const double *bconst, const int *iperm, double *W, const SolveState *st, int when = 0);
 void launch_bconst(cudaStream_t s, const TetArrays &A, const int64_t *inc_ptr, const int *inc, const double *pos,
                    const double *mass, const double *xbar, double *bconst);
 void launch_copy_if_not_done(cudaStream_t s, double *dst, const double *src, int64_t n, const SolveState *st);
+// xzu ordering (admm_anderson_xzu/src/Solver.cpp:78-257); `when` = 1 runs only on a rejected iterate
+void launch_grad_u_xzu(int grid, cudaStream_t s, const TetArrays &A, const double *z, double *u, const SolveState *st);
+void launch_z_from_x(int grid, cudaStream_t s, const TetArrays &A, const double *pos, double *z);
+void launch_contrib(int grid, cudaStream_t s, const TetArrays &A, const double *z, const double *u, double *contrib,
+                    const SolveState *st, int when);
+void launch_prim_xzu(int mode, int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *z,
+                     SolveState *st, double *partials);
+void launch_restore_xzu(int grid, cudaStream_t s, double *u, const double *u_def, double *z, const double *z_def,
+                        int64_t nz, double *x, const double *x_def, int64_t nx, const SolveState *st);
+void launch_update_z_plain(int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *u,
+                           double *z_out, const SolveState *st);
+void launch_update_u_plain(int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *z, double *u,
+                           const SolveState *st, int when);
+void launch_comb_xzu(int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *za,
+                     const double *zb, SolveState *st, double *partials, double *hist_prim, double *hist_comb,
+                     int *hist_rej);
+void launch_copy2_if_not_done(int grid, cudaStream_t s, double *d0, const double *s0, int64_t n0, double *d1,
+                              const double *s1, int64_t n1, const SolveState *st);
 void launch_prox_batch(double *d_z, int64_t n);
 void launch_fmuvt_batch(const double *d_z, double *d_out, int64_t n);
 

@@ -226,3 +226,36 @@ def test_step_is_deterministic_and_resident_path_matches(gpu):
     for f in range(2):
         assert np.array_equal(h1[f], h2[f])
         assert np.array_equal(x1[f], x2[f])
+
+
+# ---- xzu ordering (admm_anderson_xzu/src/Solver.cpp:78-257) ------------------------------------
+@pytest.mark.parametrize("name", ["xzu_beam_12x3x3_m5", "xzu_beam_12x3x3_noacc", "xzu_beam_8x2x2_m3"])
+def test_xzu_step_vs_golden(gpu, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    dims = tuple(int(d) for d in g["dims"])
+    _, hg, xg = run_product(gpu, beam_arrays(gpu, *dims), 2, m=max(int(g["m"]), 1), accel=bool(g["accel"]),
+                            ordering=gpu.ORDER_XZU)
+    for f in range(2):
+        rows = int(g["rows"][f])
+        n = min(rows, len(hg[f]))
+        rel = np.abs(hg[f][:n, 1] - g["comb"][f][:n]) / g["comb"][f][:n]
+        relp = np.abs(hg[f][:n, 0] - g["prim"][f][:n]) / g["prim"][f][:n]
+        floor = np.abs(hg[f][:n, 1] - g["comb"][f][:n]) / g["comb"][f][0]
+        print(name, "frame", f, "rows", len(hg[f]), rows, "rel8 %.2e" % rel[:8].max(), "floor %.2e" % floor.max())
+        assert rel[:8].max() < 1e-9 and relp[:8].max() < 1e-9
+        assert floor.max() < 1e-9
+        assert abs(len(hg[f]) - rows) <= max(2, 0.25 * rows)
+        if not g["accel"]:
+            assert len(hg[f]) == rows
+        assert np.abs(xg[f] - g["x"][f]).max() / np.abs(g["x"][f]).max() < 1e-6
+
+
+def test_xzu_step_vs_reference_16x4x4(gpu, ref):
+    _, hg, xg = run_product(gpu, beam_arrays(gpu, 16, 4, 4), 2, m=5, accel=True, ordering=gpu.ORDER_XZU)
+    _, hr, xr = run_reference(ref, gpu, beam_arrays(gpu, 16, 4, 4), 2, m=5, accel=True, variant="xzu")
+    for f in range(2):
+        n = min(len(hg[f]), len(hr[f]))
+        rel = np.abs(hg[f][:n, 1] - hr[f][:n, 2]) / hr[f][:n, 2]
+        assert rel[:8].max() < 1e-9
+        assert (np.abs(hg[f][:n, 1] - hr[f][:n, 2]) / hr[f][0, 2]).max() < 1e-9
+        assert np.abs(xg[f] - xr[f]).max() / np.abs(xr[f]).max() < 1e-6
