@@ -483,3 +483,120 @@ def make_beam_solver(cx, cy, cz, n_beams=1, dt=1.0 / 30.0, iters=100, anderson_m
     solver.set_pins(pidx, scene.stretch(dt))
     solver.initialize(dt, iters, gravity, anderson_m, accel, penalty, ordering)
     return solver, scene
+
+
+# ---------------------------------------------------------------------------------------------
+# Geometry (ALMGeometrySolver<3> mirror)
+# ---------------------------------------------------------------------------------------------
+def _geo_host():
+    H = host_lib()
+    if not hasattr(H, "_geo_ready"):
+        vp = C.c_void_p
+        H.aaadmm_host_geo_new.restype = vp
+        H.aaadmm_host_geo_free.argtypes = [vp]
+        H.aaadmm_host_geo_add_plane.argtypes = [vp, c_ip, C.c_int, C.c_double]
+        H.aaadmm_host_geo_add_edge.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double]
+        H.aaadmm_host_geo_add_angle.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+        H.aaadmm_host_geo_add_ref_surface.argtypes = [vp, C.c_int, C.c_double, c_dp, C.c_int, c_ip, C.c_int]
+        H.aaadmm_host_geo_add_relative_uniform_laplacian.argtypes = [vp, c_ip, C.c_int, C.c_double, c_dp, C.c_int]
+        H.aaadmm_host_geo_add_uniform_laplacian.argtypes = [vp, c_ip, C.c_int, C.c_double]
+        H.aaadmm_host_geo_add_closeness.argtypes = [vp, C.c_int, C.c_double, c_dp]
+        H.aaadmm_host_geo_setup.argtypes = [vp, C.c_int, C.c_double]
+        H.aaadmm_host_geo_solve.argtypes = [vp, c_dp, C.c_int, C.c_int, C.c_int]
+        H.aaadmm_host_geo_history.argtypes = [vp, c_dp]
+        H.aaadmm_host_geo_solution.argtypes = [vp, c_dp, C.c_int]
+        H.aaadmm_host_geo_info.argtypes = [vp, c_dp]
+        H._geo_ready = True
+    return H
+
+
+class GeometrySolver:
+    """ALMGeometrySolver<3> mirror: hard plane / edge / angle constraints, soft closest-point-to-
+    reference-surface constraint, Laplacian / closeness regularisation."""
+
+    def __init__(self):
+        self.H = _geo_host()
+        self.h = C.c_void_p(self.H.aaadmm_host_geo_new())
+        self.n_points = 0
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.H.aaadmm_host_geo_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def add_plane(self, idx, weight=1.0):
+        idx = np.ascontiguousarray(idx, np.int32)
+        self.H.aaadmm_host_geo_add_plane(self.h, _ip(idx), len(idx), weight)
+
+    def add_edge(self, i0, i1, weight, length):
+        self.H.aaadmm_host_geo_add_edge(self.h, int(i0), int(i1), weight, length)
+
+    def add_angle(self, tip, s1, s2, weight, amin, amax):
+        self.H.aaadmm_host_geo_add_angle(self.h, int(tip), int(s1), int(s2), weight, amin, amax)
+
+    def add_ref_surface(self, n_points, weight, V, F):
+        V = np.ascontiguousarray(V, np.float64)
+        F = np.ascontiguousarray(F, np.int32)
+        self.H.aaadmm_host_geo_add_ref_surface(self.h, n_points, weight, _dp(V), len(V), _ip(F), len(F))
+
+    def add_relative_uniform_laplacian(self, idx, weight, ref_pts):
+        idx = np.ascontiguousarray(idx, np.int32)
+        ref_pts = np.ascontiguousarray(ref_pts, np.float64)
+        self.H.aaadmm_host_geo_add_relative_uniform_laplacian(self.h, _ip(idx), len(idx), weight, _dp(ref_pts), len(ref_pts))
+
+    def add_uniform_laplacian(self, idx, weight):
+        idx = np.ascontiguousarray(idx, np.int32)
+        self.H.aaadmm_host_geo_add_uniform_laplacian(self.h, _ip(idx), len(idx), weight)
+
+    def add_closeness(self, idx, weight, target):
+        target = np.ascontiguousarray(target, np.float64)
+        self.H.aaadmm_host_geo_add_closeness(self.h, int(idx), weight, _dp(target))
+
+    def setup(self, n_points, rho):
+        self.n_points = n_points
+        _hk(self.H.aaadmm_host_geo_setup(self.h, n_points, rho))
+
+    def solve(self, init_x, max_iter, anderson_m):
+        """init_x: (n_points, 3). Returns (combined-residual history of the accepted iterations, solution)."""
+        x0 = np.ascontiguousarray(init_x, np.float64)
+        n = self.H.aaadmm_host_geo_solve(self.h, _dp(x0), self.n_points, max_iter, anderson_m)
+        if n < 0:
+            _hk(n)
+        hist = np.zeros(max(n, 1))
+        self.H.aaadmm_host_geo_history(self.h, _dp(hist))
+        x = np.zeros((self.n_points, 3))
+        self.H.aaadmm_host_geo_solution(self.h, _dp(x), self.n_points)
+        return hist[:n], x
+
+    def info(self):
+        s = np.zeros(4)
+        self.H.aaadmm_host_geo_info(self.h, _dp(s))
+        return dict(loop_ms=s[0], kernel_launches=int(s[1]), rejects=int(s[2]), iters=int(s[3]))
+
+
+def geo_project(kind, cols, params=(0.0, 0.0, 0.0, 0.0)):
+    """cols: (n, k, 3) already transformed columns of n constraints of one kind (0 plane, 1 edge, 2 angle)."""
+    L = cuda_lib()
+    L.aaadmm_geo_project.argtypes = [C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp]
+    cols = np.ascontiguousarray(cols, np.float64)
+    n, kc = cols.shape[0], cols.shape[1]
+    k = kc if kind == 0 else kc + 1
+    prm = np.ascontiguousarray(params, np.float64)
+    out = np.zeros_like(cols)
+    _ck(L.aaadmm_geo_project(kind, n, k, _dp(cols), _dp(prm), _dp(out)))
+    return out
+
+
+def geo_closest_points(V, F, Q):
+    L = cuda_lib()
+    L.aaadmm_geo_closest_points.argtypes = [c_dp, C.c_int, c_ip, C.c_int, c_dp, C.c_int, c_dp, c_ip]
+    V = np.ascontiguousarray(V, np.float64)
+    F = np.ascontiguousarray(F, np.int32)
+    Q = np.ascontiguousarray(Q, np.float64)
+    Cp = np.zeros_like(Q)
+    tri = np.zeros(len(Q), np.int32)
+    _ck(L.aaadmm_geo_closest_points(_dp(V), len(V), _ip(F), len(F), _dp(Q), len(Q), _dp(Cp), _ip(tri)))
+    return Cp, tri

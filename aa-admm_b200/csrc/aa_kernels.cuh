@@ -67,8 +67,8 @@ template <int M>
 __global__ void __launch_bounds__(AA_BLOCK)
 k_aa_pass1(const double *__restrict__ g_u, const double *__restrict__ g_x, double *__restrict__ gx_dst,
            double *__restrict__ ucur, double *__restrict__ dF, double *__restrict__ dG, int64_t Ne, int64_t Nt,
-           SolveState *st, double *partials) {
-    if (st->done) return;
+           SolveState *st, double *partials, double *__restrict__ g_copy) {
+    if (st->done || st->aa_skip) return;
     const int iter = st->aa_iter, c = st->aa_col, m = st->aa_m;
     const int64_t stride = (int64_t)gridDim.x * AA_BLOCK;
     const int64_t i0 = (int64_t)blockIdx.x * AA_BLOCK + threadIdx.x;
@@ -82,6 +82,7 @@ k_aa_pass1(const double *__restrict__ g_u, const double *__restrict__ g_x, doubl
                 g = g_x[i - Ne];
                 if (gx_dst) gx_dst[i - Ne] = g;
             }
+            if (g_copy) g_copy[i] = g;
             dG[i] = -g;
             ucur[i] = g;
         }
@@ -129,6 +130,7 @@ k_aa_pass1(const double *__restrict__ g_u, const double *__restrict__ g_x, doubl
                 const double a = fc[e] + F;
                 dFc[i] = a;
                 dGc[i] = gc[e] + g[e];
+                if (g_copy) g_copy[i] = g[e];
 #pragma unroll
                 for (int j = 0; j < M; ++j) {
                     if (j < mk) {
@@ -143,6 +145,7 @@ k_aa_pass1(const double *__restrict__ g_u, const double *__restrict__ g_x, doubl
     for (int64_t i = Ne + i0; i < Nt; i += stride) {
         const double g = g_x[i - Ne];
         if (gx_dst) gx_dst[i - Ne] = g;
+        if (g_copy) g_copy[i] = g;
         dGc[i] += g;
     }
     double out[2 * M];
@@ -155,7 +158,7 @@ template <int M>
 __global__ void __launch_bounds__(AA_BLOCK)
 k_aa_pass2(const double *__restrict__ g_u, const double *__restrict__ g_x, double *__restrict__ ucur,
            double *__restrict__ dF, double *__restrict__ dG, int64_t Ne, int64_t Nt, const SolveState *st) {
-    if (st->done) return;
+    if (st->done || st->aa_skip) return;
     const int mk = st->aa_mk;
     if (mk == 0) return;
     const int cn = st->aa_col;  // already advanced by pass 1
@@ -191,7 +194,8 @@ k_aa_pass2(const double *__restrict__ g_u, const double *__restrict__ g_x, doubl
 
 // Host-side dispatch on the window size m (compile-time accumulator count).
 int launch_aa_pass1(int m, int grid, cudaStream_t s, const double *g_u, const double *g_x, double *gx_dst,
-                    double *ucur, double *dF, double *dG, int64_t Ne, int64_t Nt, SolveState *st, double *partials);
+                    double *ucur, double *dF, double *dG, int64_t Ne, int64_t Nt, SolveState *st, double *partials,
+                    double *g_copy = nullptr);
 int launch_aa_pass2(int m, int grid, cudaStream_t s, const double *g_u, const double *g_x, double *ucur,
                     double *dF, double *dG, int64_t Ne, int64_t Nt, const SolveState *st);
 

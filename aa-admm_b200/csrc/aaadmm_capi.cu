@@ -48,8 +48,9 @@ int stream_grid(int ctas_per_sm) { return std::min(RED_MAX_BLOCKS, sm_count() * 
     }
 
 int launch_aa_pass1(int m, int grid, cudaStream_t s, const double *g_u, const double *g_x, double *gx_dst,
-                    double *ucur, double *dF, double *dG, int64_t Ne, int64_t Nt, SolveState *st, double *partials) {
-    AA_DISPATCH(m, (k_aa_pass1<MM><<<grid, AA_BLOCK, 0, s>>>(g_u, g_x, gx_dst, ucur, dF, dG, Ne, Nt, st, partials)));
+                    double *ucur, double *dF, double *dG, int64_t Ne, int64_t Nt, SolveState *st, double *partials,
+                    double *g_copy) {
+    AA_DISPATCH(m, (k_aa_pass1<MM><<<grid, AA_BLOCK, 0, s>>>(g_u, g_x, gx_dst, ucur, dF, dG, Ne, Nt, st, partials, g_copy)));
     AAADMM_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -79,6 +80,7 @@ __global__ void k_init_state(SolveState *st, int accel, int m, double eps, int m
     st->loop_it = 0;
     st->max_iters = max_iters;
     st->skip_redo = 1;
+    st->aa_skip = 0;
     st->prim2 = 0.0;
     st->prev_prim = 1e+20;
     st->comb = 0.0;
@@ -943,6 +945,473 @@ int aaadmm_cod_solve(int m, const double *M, const double *rhs, double *x, int *
     cudaFree(dx);
     cudaFree(dk);
     return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// Geometry ADMM
+// ------------------------------------------------------------------------------------------
+#include "geo_kernels.cuh"
+
+#include <cfloat>
+#include <numeric>
+
+namespace {
+
+// Median-split BVH over triangle centroids (built once on the host; the mesh is static).
+struct BvhBuild {
+    std::vector<BvhNode> nodes;
+    std::vector<int> order;
+    const double *tri;
+    int build(int lo, int hi) {
+        const int id = (int)nodes.size();
+        nodes.emplace_back();
+        BvhNode nd;
+        for (int r = 0; r < 3; ++r) nd.lo[r] = DBL_MAX, nd.hi[r] = -DBL_MAX;
+        double clo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, chi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+        for (int k = lo; k < hi; ++k) {
+            const double *t = tri + 9 * (size_t)order[k];
+            for (int r = 0; r < 3; ++r) {
+                double c = 0;
+                for (int v = 0; v < 3; ++v) {
+                    nd.lo[r] = std::min(nd.lo[r], t[3 * v + r]);
+                    nd.hi[r] = std::max(nd.hi[r], t[3 * v + r]);
+                    c += t[3 * v + r];
+                }
+                clo[r] = std::min(clo[r], c);
+                chi[r] = std::max(chi[r], c);
+            }
+        }
+        if (hi - lo <= 4) {
+            nd.left = -(lo + 1);
+            nd.right = hi - lo;
+            nodes[id] = nd;
+            return id;
+        }
+        int ax = 0;
+        if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
+        if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
+        const int mid = (lo + hi) / 2;
+        const double *T = tri;
+        std::nth_element(order.begin() + lo, order.begin() + mid, order.begin() + hi, [T, ax](int a, int b) {
+            const double ca = T[9 * (size_t)a + ax] + T[9 * (size_t)a + 3 + ax] + T[9 * (size_t)a + 6 + ax];
+            const double cb = T[9 * (size_t)b + ax] + T[9 * (size_t)b + 3 + ax] + T[9 * (size_t)b + 6 + ax];
+            return ca < cb || (ca == cb && a < b);
+        });
+        const int l = build(lo, mid), r = build(mid, hi);
+        nd.left = l;
+        nd.right = r;
+        nodes[id] = nd;
+        return id;
+    }
+};
+
+struct RefMeshDev {
+    BvhNode *nodes = nullptr;
+    int *order = nullptr;
+    double *tri = nullptr;
+    int n_tris = 0;
+    int upload(const double *verts, int nv, const int *tris, int nt) {
+        (void)nv;
+        std::vector<double> T((size_t)9 * std::max(nt, 1));
+        for (int t = 0; t < nt; ++t)
+            for (int v = 0; v < 3; ++v)
+                for (int r = 0; r < 3; ++r) T[9 * (size_t)t + 3 * v + r] = verts[3 * (size_t)tris[3 * t + v] + r];
+        BvhBuild B;
+        B.tri = T.data();
+        B.order.resize(nt);
+        std::iota(B.order.begin(), B.order.end(), 0);
+        if (nt > 0) B.build(0, nt);
+        n_tris = nt;
+        AAADMM_CUDA_OK(cudaMalloc((void **)&nodes, sizeof(BvhNode) * std::max<size_t>(B.nodes.size(), 1)));
+        AAADMM_CUDA_OK(cudaMemcpy(nodes, B.nodes.data(), sizeof(BvhNode) * B.nodes.size(), cudaMemcpyHostToDevice));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&order, sizeof(int) * std::max(nt, 1)));
+        AAADMM_CUDA_OK(cudaMemcpy(order, B.order.data(), sizeof(int) * nt, cudaMemcpyHostToDevice));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&tri, sizeof(double) * T.size()));
+        AAADMM_CUDA_OK(cudaMemcpy(tri, T.data(), sizeof(double) * T.size(), cudaMemcpyHostToDevice));
+        return 0;
+    }
+    void release() {
+        cudaFree(nodes);
+        cudaFree(order);
+        cudaFree(tri);
+    }
+};
+
+template <typename T>
+int up(T **dst, const T *src, size_t n) {
+    AAADMM_CUDA_OK(cudaMalloc((void **)dst, sizeof(T) * std::max<size_t>(n, 1)));
+    if (n) AAADMM_CUDA_OK(cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+__global__ void k_geo_init_state(SolveState *st, int m, int max_iters) {
+    st->prim2 = 0.0;
+    st->prev_prim = DBL_MAX;  // prev_residual
+    st->comb = 0.0;
+    st->eps = 0.0;
+    st->reject = 0;  // reset
+    st->done = 0;
+    st->iter = 0;
+    st->n_rejects = 0;
+    st->accel = m > 0;
+    st->aa_iter = 0;
+    st->aa_col = 0;
+    st->aa_m = m > 0 ? m : 1;
+    st->aa_mk = 0;
+    st->ticket = 0u;
+    st->loop_it = 0;
+    st->max_iters = max_iters;
+    st->skip_redo = 1;
+    st->aa_skip = 0;
+}
+// ALMGeometrySolver.h:258-263: the loop ends when iter_count >= max_iter (accepted iterations)
+__global__ void k_geo_loop_cond(cudaGraphConditionalHandle h, SolveState *st) {
+    st->loop_it += 1;
+    cudaGraphSetConditional(h, (st->iter < st->max_iters && st->loop_it < 4 * st->max_iters + 8) ? 1u : 0u);
+}
+
+}  // namespace
+
+struct aaadmm_geo {
+    int P = 0, n_hard = 0, zc = 0, n_soft = 0;
+    aaadmm_ldlt *factor = nullptr;
+    cudaStream_t stream = nullptr;
+    int *type = nullptr, *idx_ptr = nullptr, *idx = nullptr, *col0 = nullptr, *dt_col = nullptr, *soft_point = nullptr,
+        *soft_of_point = nullptr, *last_tri = nullptr;
+    int64_t *dt_ptr = nullptr;
+    double *param = nullptr, *dt_val = nullptr, *rhs_fixed = nullptr;
+    double soft_weight = 0;
+    RefMeshDev mesh;
+    int64_t N = 0;  // 3 zc + 3 P: the Anderson variable (u | x)
+    double *Ubuf = nullptr, *Nbuf = nullptr, *Dbuf = nullptr, *z = nullptr, *prev_dx = nullptr, *cp = nullptr;
+    double *dF = nullptr, *dG = nullptr, *hist = nullptr, *partials = nullptr;
+    int m_cap = 0, hist_cap = 0;
+    SolveState *st = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int graph_key = -1;
+    int body_launches = 0;
+};
+
+extern "C" {
+
+int aaadmm_geo_destroy(aaadmm_geo *g) {
+    if (!g) return 0;
+    cudaFree(g->type);
+    cudaFree(g->idx_ptr);
+    cudaFree(g->idx);
+    cudaFree(g->col0);
+    cudaFree(g->dt_col);
+    cudaFree(g->soft_point);
+    cudaFree(g->soft_of_point);
+    cudaFree(g->last_tri);
+    cudaFree(g->dt_ptr);
+    cudaFree(g->param);
+    cudaFree(g->dt_val);
+    cudaFree(g->rhs_fixed);
+    g->mesh.release();
+    cudaFree(g->Ubuf);
+    cudaFree(g->Nbuf);
+    cudaFree(g->Dbuf);
+    cudaFree(g->z);
+    cudaFree(g->prev_dx);
+    cudaFree(g->cp);
+    cudaFree(g->dF);
+    cudaFree(g->dG);
+    cudaFree(g->hist);
+    cudaFree(g->partials);
+    cudaFree(g->st);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    if (g->stream) cudaStreamDestroy(g->stream);
+    delete g;
+    return 0;
+}
+
+int aaadmm_geo_create(aaadmm_geo **out, const aaadmm_geo_desc *d, aaadmm_ldlt *factor) {
+    API_TRY_BEGIN
+    if (aaadmm_device_count() <= 0) {
+        set_last_error("geo_create: no CUDA device (this library has no CPU path)");
+        return -1;
+    }
+    if (!d || !factor || d->n_points <= 0 || factor->f->n != d->n_points || factor->f->nrhs != 3) {
+        set_last_error("geo_create: bad arguments (factor must be n_points x n_points with nrhs = 3)");
+        return -1;
+    }
+    std::vector<int> col0(std::max(d->n_hard, 1));
+    int zc = 0;
+    for (int c = 0; c < d->n_hard; ++c) {
+        const int k = d->idx_ptr[c + 1] - d->idx_ptr[c];
+        if (d->type[c] < 0 || d->type[c] > 2 || k < 2 || k > GEO_MAX_K || (d->type[c] == GEO_EDGE && k != 2) ||
+            (d->type[c] == GEO_ANGLE && k != 3)) {
+            set_last_error("geo_create: unsupported constraint (type must be plane/edge/angle, plane size <= 16)");
+            return -1;
+        }
+        col0[c] = zc;
+        zc += d->type[c] == GEO_PLANE ? k : k - 1;
+    }
+    if (zc != d->n_zcols) {
+        set_last_error("geo_create: n_zcols does not match the constraint list");
+        return -1;
+    }
+    aaadmm_geo *g = new aaadmm_geo();
+    g->P = d->n_points;
+    g->n_hard = d->n_hard;
+    g->zc = zc;
+    g->n_soft = d->n_soft;
+    g->soft_weight = d->soft_weight;
+    g->factor = factor;
+    g->N = 3 * (int64_t)zc + 3 * (int64_t)g->P;
+    AAADMM_CUDA_OK(cudaStreamCreate(&g->stream));
+    int rc = 0;
+    rc |= up(&g->type, d->type, d->n_hard);
+    rc |= up(&g->idx_ptr, d->idx_ptr, d->n_hard + 1);
+    rc |= up(&g->idx, d->idx, d->n_hard ? d->idx_ptr[d->n_hard] : 0);
+    rc |= up(&g->col0, col0.data(), d->n_hard);
+    rc |= up(&g->param, d->param, (size_t)4 * d->n_hard);
+    rc |= up(&g->dt_ptr, d->dt_ptr, (size_t)g->P + 1);
+    rc |= up(&g->dt_col, d->dt_col, (size_t)d->dt_ptr[g->P]);
+    rc |= up(&g->dt_val, d->dt_val, (size_t)d->dt_ptr[g->P]);
+    rc |= up(&g->rhs_fixed, d->rhs_fixed, (size_t)3 * g->P);
+    rc |= up(&g->soft_point, d->soft_point, d->n_soft);
+    std::vector<int> sop(g->P, -1), lt(std::max(d->n_soft, 1), -1);
+    for (int i = 0; i < d->n_soft; ++i) sop[d->soft_point[i]] = i;
+    rc |= up(&g->soft_of_point, sop.data(), g->P);
+    rc |= up(&g->last_tri, lt.data(), d->n_soft);
+    if (d->n_soft > 0) rc |= g->mesh.upload(d->ref_verts, d->n_ref_verts, d->ref_tris, d->n_ref_tris);
+    if (rc) {
+        aaadmm_geo_destroy(g);
+        return -1;
+    }
+    AAADMM_CUDA_OK(cudaMalloc((void **)&g->Ubuf, sizeof(double) * g->N));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&g->Nbuf, sizeof(double) * g->N));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&g->Dbuf, sizeof(double) * g->N));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&g->z, sizeof(double) * 3 * std::max(zc, 1)));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&g->prev_dx, sizeof(double) * 3 * std::max(zc, 1)));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&g->cp, sizeof(double) * 3 * std::max(d->n_soft, 1)));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&g->partials, sizeof(double) * RED_MAX_Q * RED_MAX_BLOCKS));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&g->st, sizeof(SolveState)));
+    AAADMM_CUDA_OK(cudaMemset(g->st, 0, sizeof(SolveState)));
+    *out = g;
+    return 0;
+    API_TRY_END
+}
+
+static void geo_views(aaadmm_geo *g, GeoConstraints &C, GeoSoft &S) {
+    C.n = g->n_hard;
+    C.type = g->type;
+    C.idx_ptr = g->idx_ptr;
+    C.idx = g->idx;
+    C.col0 = g->col0;
+    C.param = g->param;
+    S.n = g->n_soft;
+    S.point = g->soft_point;
+    S.weight = g->soft_weight;
+    S.nodes = g->mesh.nodes;
+    S.tri_order = g->mesh.order;
+    S.tri = g->mesh.tri;
+    S.last_tri = g->last_tri;
+}
+
+// one turn of the while loop of ALMGeometrySolver.h:197-268
+static int geo_enqueue_turn(aaadmm_geo *g, int m, int &L) {
+    cudaStream_t st = g->stream;
+    LdltDev *f = g->factor->f;
+    GeoConstraints C;
+    GeoSoft S;
+    geo_views(g, C, S);
+    const int64_t NU = 3 * (int64_t)g->zc;
+    double *cu = g->Ubuf, *cx = g->Ubuf + NU, *nu = g->Nbuf, *nx = g->Nbuf + NU;
+    const bool accel = m > 0;
+    launch_geo_local(st, C, cx, cu, g->prev_dx, g->z, g->st);
+    launch_geo_soft(st, S, cx, g->cp, g->st);
+    launch_geo_rhs(st, g->P, g->dt_ptr, g->dt_col, g->dt_val, g->z, cu, g->rhs_fixed, g->n_soft ? g->soft_of_point : nullptr,
+                   g->soft_weight, g->cp, f->iperm, f->W, g->st);
+    if (ldlt_dev_apply_permuted(f, nx, st, &g->st->done)) return -1;
+    launch_geo_u_resid(st, C, nx, cu, g->z, g->prev_dx, nu, g->st, g->partials, g->hist, accel ? 1 : 0);
+    L += 4 + 4 * f->n_levels;
+    if (accel) {
+        const int gs = stream_grid(4);
+        if (launch_aa_pass1(m, gs, st, g->Nbuf, nullptr, nullptr, g->Ubuf, g->dF, g->dG, g->N, g->N, g->st, g->partials, g->Dbuf))
+            return -1;
+        if (launch_aa_pass2(m, gs, st, g->Nbuf, nullptr, g->Ubuf, g->dF, g->dG, g->N, g->N, g->st)) return -1;
+        L += 2;
+    }
+    launch_geo_select(st, g->Ubuf, g->Dbuf, g->Nbuf, g->N, g->st, accel ? 1 : 0);
+    L += 1;
+    return 0;
+}
+
+int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int anderson_m, double *x_out, double *hist,
+                     aaadmm_step_result *res) {
+    API_TRY_BEGIN
+    if (!g || !init_x || !x_out || max_iter < 0 || anderson_m > AA_MAX_M) {
+        set_last_error("geo_solve: bad arguments");
+        return -1;
+    }
+    const int m = anderson_m > 0 ? anderson_m : 0;
+    cudaStream_t st = g->stream;
+    if (max_iter > g->hist_cap) {
+        cudaFree(g->hist);
+        AAADMM_CUDA_OK(cudaMalloc((void **)&g->hist, sizeof(double) * std::max(1, max_iter)));
+        g->hist_cap = max_iter;
+        g->graph_key = -1;
+    }
+    if (m > g->m_cap) {
+        cudaFree(g->dF);
+        cudaFree(g->dG);
+        AAADMM_CUDA_OK(cudaMalloc((void **)&g->dF, sizeof(double) * g->N * m));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&g->dG, sizeof(double) * g->N * m));
+        g->m_cap = m;
+        g->graph_key = -1;
+    }
+    const int64_t NU = 3 * (int64_t)g->zc;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    // init_variables (ALMGeometrySolver.h:404-409) + aa->init(current_u, current_x)
+    AAADMM_CUDA_OK(cudaMemsetAsync(g->Ubuf, 0, sizeof(double) * g->N, st));
+    AAADMM_CUDA_OK(cudaMemsetAsync(g->Dbuf, 0, sizeof(double) * g->N, st));
+    AAADMM_CUDA_OK(cudaMemcpyAsync(g->Ubuf + NU, init_x, sizeof(double) * 3 * g->P, cudaMemcpyHostToDevice, st));
+    AAADMM_CUDA_OK(cudaMemcpyAsync(g->Dbuf + NU, init_x, sizeof(double) * 3 * g->P, cudaMemcpyHostToDevice, st));
+    if (g->n_soft) AAADMM_CUDA_OK(cudaMemsetAsync(g->last_tri, 0xff, sizeof(int) * g->n_soft, st));
+    k_geo_init_state<<<1, 1, 0, st>>>(g->st, m, max_iter);
+    int launches = 0;
+    AAADMM_CUDA_OK(cudaEventRecord(e0, st));
+    static const bool no_graph = getenv("AAADMM_NO_GRAPH") != nullptr;
+    SolveState hs;
+    if (max_iter > 0 && !no_graph) {
+        const int key = m;
+        if (g->graph_key != key || !g->exec) {
+            if (g->exec) cudaGraphExecDestroy(g->exec), g->exec = nullptr;
+            if (g->graph) cudaGraphDestroy(g->graph), g->graph = nullptr;
+            cudaGraphConditionalHandle h;
+            AAADMM_CUDA_OK(cudaGraphCreate(&g->graph, 0));
+            AAADMM_CUDA_OK(cudaGraphConditionalHandleCreate(&h, g->graph, 1, cudaGraphCondAssignDefault));
+            cudaGraphNodeParams np = {};
+            np.type = cudaGraphNodeTypeConditional;
+            np.conditional.handle = h;
+            np.conditional.type = cudaGraphCondTypeWhile;
+            np.conditional.size = 1;
+            cudaGraphNode_t node;
+            AAADMM_CUDA_OK(cudaGraphAddNode(&node, g->graph, nullptr, 0, &np));
+            AAADMM_CUDA_OK(cudaStreamBeginCaptureToGraph(st, np.conditional.phGraph_out[0], nullptr, nullptr, 0,
+                                                         cudaStreamCaptureModeThreadLocal));
+            int L = 0;
+            const int rc = geo_enqueue_turn(g, m, L);
+            k_geo_loop_cond<<<1, 1, 0, st>>>(h, g->st);
+            cudaError_t e = cudaStreamEndCapture(st, nullptr);
+            if (rc || e != cudaSuccess) {
+                set_last_error(std::string("geo loop graph capture failed: ") + cudaGetErrorString(e));
+                return -1;
+            }
+            AAADMM_CUDA_OK(cudaGraphInstantiate(&g->exec, g->graph, 0));
+            g->graph_key = key;
+            g->body_launches = L + 1;
+        }
+        AAADMM_CUDA_OK(cudaGraphLaunch(g->exec, st));
+    } else if (max_iter > 0) {
+        for (int turn = 0; turn < 4 * max_iter + 8; ++turn) {
+            if (geo_enqueue_turn(g, m, launches)) return -1;
+            AAADMM_CUDA_OK(cudaMemcpyAsync(&hs, g->st, sizeof(SolveState), cudaMemcpyDeviceToHost, st));
+            AAADMM_CUDA_OK(cudaStreamSynchronize(st));
+            if (hs.iter >= max_iter) break;
+        }
+    }
+    AAADMM_CUDA_OK(cudaEventRecord(e1, st));
+    AAADMM_CUDA_OK(cudaMemcpyAsync(x_out, g->Dbuf + NU, sizeof(double) * 3 * g->P, cudaMemcpyDeviceToHost, st));
+    AAADMM_CUDA_OK(cudaMemcpyAsync(&hs, g->st, sizeof(SolveState), cudaMemcpyDeviceToHost, st));
+    AAADMM_CUDA_OK(cudaStreamSynchronize(st));
+    if (hist && hs.iter > 0) AAADMM_CUDA_OK(cudaMemcpy(hist, g->hist, sizeof(double) * hs.iter, cudaMemcpyDeviceToHost));
+    if (res) {
+        res->iters_logged = hs.iter;
+        res->rejects = hs.n_rejects;
+        res->broke_early = 0;
+        cudaEventElapsedTime(&res->loop_ms, e0, e1);
+        res->step_ms = res->loop_ms;
+        res->kernel_launches = launches + hs.loop_it * g->body_launches;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return 0;
+    API_TRY_END
+}
+
+int aaadmm_geo_project(int type, int n, int k, const double *cols, const double *param4, double *out) {
+    API_TRY_BEGIN
+    if (aaadmm_device_count() <= 0) {
+        set_last_error("no CUDA device (this library has no CPU path)");
+        return -1;
+    }
+    const int kc = type == GEO_PLANE ? k : k - 1;
+    std::vector<int> types(n, type), ptr(n + 1), idx((size_t)n * k, 0), col0(n);
+    std::vector<double> prm((size_t)4 * n);
+    for (int c = 0; c <= n; ++c) ptr[c] = c * k;
+    for (int c = 0; c < n; ++c) {
+        col0[c] = c * kc;
+        for (int q = 0; q < 4; ++q) prm[4 * (size_t)c + q] = param4[q];
+    }
+    GeoConstraints C;
+    int *dt = nullptr, *dp = nullptr, *di = nullptr, *dc = nullptr;
+    double *dprm = nullptr, *dv = nullptr, *dz = nullptr;
+    if (up(&dt, types.data(), n) || up(&dp, ptr.data(), n + 1) || up(&di, idx.data(), idx.size()) || up(&dc, col0.data(), n) ||
+        up(&dprm, prm.data(), prm.size()) || up(&dv, cols, (size_t)3 * n * kc))
+        return -1;
+    AAADMM_CUDA_OK(cudaMalloc((void **)&dz, sizeof(double) * 3 * n * kc));
+    C.n = n;
+    C.type = dt;
+    C.idx_ptr = dp;
+    C.idx = di;
+    C.col0 = dc;
+    C.param = dprm;
+    launch_geo_project_only(C, dv, dz);
+    AAADMM_CUDA_OK(cudaGetLastError());
+    AAADMM_CUDA_OK(cudaMemcpy(out, dz, sizeof(double) * 3 * n * kc, cudaMemcpyDeviceToHost));
+    cudaFree(dt);
+    cudaFree(dp);
+    cudaFree(di);
+    cudaFree(dc);
+    cudaFree(dprm);
+    cudaFree(dv);
+    cudaFree(dz);
+    return 0;
+    API_TRY_END
+}
+
+int aaadmm_geo_closest_points(const double *verts, int nv, const int *tris, int nt, const double *q, int nq,
+                              double *closest, int *tri) {
+    API_TRY_BEGIN
+    if (aaadmm_device_count() <= 0) {
+        set_last_error("no CUDA device (this library has no CPU path)");
+        return -1;
+    }
+    RefMeshDev M;
+    if (M.upload(verts, nv, tris, nt)) return -1;
+    double *dq = nullptr, *dc = nullptr;
+    int *dt = nullptr;
+    if (up(&dq, q, (size_t)3 * nq)) return -1;
+    AAADMM_CUDA_OK(cudaMalloc((void **)&dc, sizeof(double) * 3 * std::max(nq, 1)));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&dt, sizeof(int) * std::max(nq, 1)));
+    GeoSoft S;
+    S.n = nq;
+    S.point = nullptr;
+    S.weight = 1.0;
+    S.nodes = M.nodes;
+    S.tri_order = M.order;
+    S.tri = M.tri;
+    S.last_tri = nullptr;
+    launch_geo_closest_only(S, dq, dc, dt);
+    AAADMM_CUDA_OK(cudaGetLastError());
+    AAADMM_CUDA_OK(cudaMemcpy(closest, dc, sizeof(double) * 3 * nq, cudaMemcpyDeviceToHost));
+    if (tri) AAADMM_CUDA_OK(cudaMemcpy(tri, dt, sizeof(int) * nq, cudaMemcpyDeviceToHost));
+    cudaFree(dq);
+    cudaFree(dc);
+    cudaFree(dt);
+    M.release();
+    return 0;
+    API_TRY_END
 }
 
 }  // extern "C"

@@ -52,6 +52,7 @@ struct SolveState {
     unsigned int ticket;               // last-block election counter of the reducing kernels
     int loop_it, max_iters;            // device-side loop control of the graph WHILE node
     int skip_redo;                     // xzu: 1 unless the current iterate was rejected (guards the redo solve)
+    int aa_skip;                       // geometry: 1 on a rejected turn (the Anderson passes do not run)
 };
 
 // ---------------------------------------------------------------------------------------

@@ -255,3 +255,82 @@ int aaadmm_host_tet_constants(const double *rest12, double youngs, double poisso
 }
 
 }  // extern "C"
+
+// ---- ALMGeometrySolver<3> (Geometry/ALMGeometrySolver.h) ---------------------------------------
+#include "GeometrySolver.hpp"
+namespace {
+struct GeoHandle {
+    aaadmm::ALMGeometrySolver<3> solver;
+};
+}  // namespace
+extern "C" {
+void *aaadmm_host_geo_new(void) { return new GeoHandle(); }
+void aaadmm_host_geo_free(void *h) { delete static_cast<GeoHandle *>(h); }
+int aaadmm_host_geo_add_plane(void *h, const int *idx, int k, double weight) {
+    static_cast<GeoHandle *>(h)->solver.add_hard_constraint(new aaadmm::PlaneConstraint(std::vector<int>(idx, idx + k), weight));
+    return 0;
+}
+int aaadmm_host_geo_add_edge(void *h, int i0, int i1, double weight, double len) {
+    static_cast<GeoHandle *>(h)->solver.add_hard_constraint(new aaadmm::EdgeLengthConstraint<3>(i0, i1, weight, len));
+    return 0;
+}
+int aaadmm_host_geo_add_angle(void *h, int tip, int s1, int s2, double weight, double amin, double amax) {
+    static_cast<GeoHandle *>(h)->solver.add_hard_constraint(new aaadmm::AngleConstraint<3>(tip, s1, s2, weight, amin, amax));
+    return 0;
+}
+int aaadmm_host_geo_add_ref_surface(void *h, int n_points, double weight, const double *V, int nv, const int *F, int nf) {
+    aaadmm::Matrix3X Vm(nv);
+    memcpy(Vm.data(), V, sizeof(double) * 3 * nv);
+    static_cast<GeoHandle *>(h)->solver.add_soft_constraint(
+        new aaadmm::ReferenceSurfceConstraint(n_points, weight, Vm, std::vector<int>(F, F + 3 * (size_t)nf)));
+    return 0;
+}
+int aaadmm_host_geo_add_relative_uniform_laplacian(void *h, const int *idx, int n, double weight, const double *ref_pts, int n_pts) {
+    aaadmm::Matrix3X R(n_pts);
+    memcpy(R.data(), ref_pts, sizeof(double) * 3 * n_pts);
+    static_cast<GeoHandle *>(h)->solver.add_relative_uniform_laplacian(std::vector<int>(idx, idx + n), weight, R);
+    return 0;
+}
+int aaadmm_host_geo_add_uniform_laplacian(void *h, const int *idx, int n, double weight) {
+    static_cast<GeoHandle *>(h)->solver.add_uniform_laplacian(std::vector<int>(idx, idx + n), weight);
+    return 0;
+}
+int aaadmm_host_geo_add_closeness(void *h, int idx, double weight, const double *target3) {
+    static_cast<GeoHandle *>(h)->solver.add_closeness(idx, weight, target3);
+    return 0;
+}
+int aaadmm_host_geo_setup(void *h, int n_points, double rho) {
+    HOST_TRY
+    return static_cast<GeoHandle *>(h)->solver.setup_ADMM(n_points, rho) ? 0 : -2;
+    HOST_CATCH
+}
+int aaadmm_host_geo_solve(void *h, const double *init_x, int n_points, int max_iter, int anderson_m) {
+    HOST_TRY
+    aaadmm::Matrix3X x0(n_points);
+    memcpy(x0.data(), init_x, sizeof(double) * 3 * n_points);
+    GeoHandle *g = static_cast<GeoHandle *>(h);
+    g->solver.function_values_.clear();
+    g->solver.elapsed_time_.clear();
+    g->solver.solve_ADMM(x0, 1e-8, max_iter, anderson_m);
+    return (int)g->solver.function_values_.size();
+    HOST_CATCH
+}
+int aaadmm_host_geo_history(void *h, double *values) {
+    GeoHandle *g = static_cast<GeoHandle *>(h);
+    memcpy(values, g->solver.function_values_.data(), sizeof(double) * g->solver.function_values_.size());
+    return 0;
+}
+int aaadmm_host_geo_solution(void *h, double *x, int n_points) {
+    memcpy(x, static_cast<GeoHandle *>(h)->solver.get_solution().data(), sizeof(double) * 3 * n_points);
+    return 0;
+}
+// out[0..3] = loop_ms, kernel_launches, rejects (resets), accepted iterations
+int aaadmm_host_geo_info(void *h, double *out4) {
+    GeoHandle *g = static_cast<GeoHandle *>(h);
+    out4[0] = g->solver.last_result.loop_ms;
+    out4[1] = g->solver.last_result.kernel_launches;
+    out4[2] = g->solver.last_result.rejects;
+    out4[3] = g->solver.last_result.iters_logged;
+    return 0;
+}
+}  // extern "C"

@@ -143,6 +143,55 @@ int aaadmm_tetscene_profile(aaadmm_tetscene *s, const aaadmm_step_opts *opts, in
 int aaadmm_tetscene_algo_bytes(aaadmm_tetscene *s, int anderson_m, double *bytes);
 
 /* ------------------------------------------------------------------------------------------
+ * Geometry ADMM (planar-quad and wire-mesh optimisation).
+ * Replaces ALMGeometrySolver<3>::solve_ADMM (Geometry/ALMGeometrySolver.h:163-283) with the shipped
+ * Constraint<3> subclasses as device batches (Geometry/Constraint.h): PlaneConstraint :396-414,
+ * EdgeLengthConstraint :194-218, AngleConstraint :220-296, and the closest-point soft constraints
+ * PointToRefSurfaceConstraint :328-349 / ReferenceSurfceConstraint :351-394 (igl::AABB).
+ * setup_ADMM (:81-161) stays on the host: it builds rho*D_hard^T, the constant rhs and the P x P
+ * system matrix, factors it once and hands the factor over (aaadmm_ldlt, nrhs = 3).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct aaadmm_geo aaadmm_geo;
+
+#define AAADMM_GEO_PLANE 0 /* MEAN_CENTERING, k output columns      */
+#define AAADMM_GEO_EDGE 1  /* SUBTRACT_FIRST, 1 output column       */
+#define AAADMM_GEO_ANGLE 2 /* SUBTRACT_FIRST, 2 output columns      */
+
+typedef struct {
+    int n_points;
+    int n_hard;             /* hard constraints in insertion order (their output columns follow it)  */
+    const int *type;        /* n_hard: AAADMM_GEO_*                                                  */
+    const int *idx_ptr;     /* n_hard+1 offsets into idx                                             */
+    const int *idx;         /* point ids (idI_)                                                      */
+    const double *param;    /* 4 per constraint: edge {length}; angle {min, max, cos min, cos max}   */
+    int n_zcols;            /* columns of z_hard / u                                                 */
+    const int64_t *dt_ptr;  /* n_points+1: CSR of rho * D_hard^T (rows = points, cols = z columns)   */
+    const int *dt_col;
+    const double *dt_val;
+    int n_soft;             /* closest-point soft constraints, one point each                        */
+    const int *soft_point;  /* n_soft point ids                                                      */
+    double soft_weight;     /* their weight (D_soft^T z_soft = weight * closest point)               */
+    int n_ref_verts;        /* reference triangle mesh                                               */
+    const double *ref_verts; /* 3 per vertex                                                         */
+    int n_ref_tris;
+    const int *ref_tris;    /* 3 per triangle                                                        */
+    const double *rhs_fixed; /* 3 per point: L^T * regularisation targets                            */
+} aaadmm_geo_desc;
+
+/* `factor` (nrhs = 3, n = n_points) is borrowed. */
+int aaadmm_geo_create(aaadmm_geo **out, const aaadmm_geo_desc *desc, aaadmm_ldlt *factor);
+int aaadmm_geo_destroy(aaadmm_geo *g);
+/* init_x / x_out: 3 per point; hist: max_iter combined residuals of the accepted iterations.
+ * anderson_m <= 0 runs plain ADMM. result->iters_logged = accepted iterations, ->rejects = resets. */
+int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int anderson_m, double *x_out, double *hist,
+                     aaadmm_step_result *result);
+/* unit parity: project `n` constraints of one type on already transformed columns (3 per column, host) */
+int aaadmm_geo_project(int type, int n, int k, const double *cols, const double *param4, double *out);
+/* unit parity: nearest points on a triangle mesh for nq host queries */
+int aaadmm_geo_closest_points(const double *verts, int nv, const int *tris, int nt, const double *q, int nq,
+                              double *closest, int *tri);
+
+/* ------------------------------------------------------------------------------------------
  * Batched element kernels exposed for unit parity (same device code the step uses).
  *   prox_linear : TetEnergyTerm::prox on n column-major 3x3 blocks (in place, host array)
  *   grad_linear : out = F - U V^T  (TetEnergyTerm::get_gradient / (K vol))

@@ -55,6 +55,24 @@ void *aaadmm_host_solver_device_factor(void *h);
 int aaadmm_host_tet_constants(const double *rest12, double youngs, double poisson, double *binv9, double *vol,
                               double *weight);
 
+/* ALMGeometrySolver<3> mirror (Geometry/ALMGeometrySolver.h:52-287) with the shipped constraints
+ * (Geometry/Constraint.h): planes/edges/angles are hard constraints, the reference-surface closest-point
+ * constraint is soft, Laplacian / closeness rows are regularisation. */
+void *aaadmm_host_geo_new(void);
+void aaadmm_host_geo_free(void *h);
+int aaadmm_host_geo_add_plane(void *h, const int *idx, int k, double weight);
+int aaadmm_host_geo_add_edge(void *h, int i0, int i1, double weight, double len);
+int aaadmm_host_geo_add_angle(void *h, int tip, int s1, int s2, double weight, double amin, double amax);
+int aaadmm_host_geo_add_ref_surface(void *h, int n_points, double weight, const double *V, int nv, const int *F, int nf);
+int aaadmm_host_geo_add_relative_uniform_laplacian(void *h, const int *idx, int n, double weight, const double *ref_pts, int n_pts);
+int aaadmm_host_geo_add_uniform_laplacian(void *h, const int *idx, int n, double weight);
+int aaadmm_host_geo_add_closeness(void *h, int idx, double weight, const double *target3);
+int aaadmm_host_geo_setup(void *h, int n_points, double rho);
+int aaadmm_host_geo_solve(void *h, const double *init_x, int n_points, int max_iter, int anderson_m);
+int aaadmm_host_geo_history(void *h, double *values);
+int aaadmm_host_geo_solution(void *h, double *x, int n_points);
+int aaadmm_host_geo_info(void *h, double *out4);
+
 #ifdef __cplusplus
 }
 #endif

@@ -435,3 +435,110 @@ class PortSolver:
 
     def v(self):
         return self._v.copy()
+
+
+# ---------------------------------------------------------------------------------------------
+# Reference Geometry solver (oracle/_ref/libref_geo.so)
+# ---------------------------------------------------------------------------------------------
+def have_ref_geo():
+    return os.path.exists(os.path.join(REF_DIR, "libref_geo.so"))
+
+
+class RefGeometrySolver:
+    """The reference ALMGeometrySolver<3> (use_alm=True) or GeometrySolver<3> with its own Constraint
+    classes, built from plain arrays."""
+
+    def __init__(self, use_alm=True):
+        self.L = _load("libref_geo.so")
+        L = self.L
+        vp = C.c_void_p
+        L.ref_geo_new.restype = vp
+        L.ref_geo_new.argtypes = [C.c_int]
+        L.ref_geo_free.argtypes = [vp]
+        L.ref_geo_add_plane.argtypes = [vp, c_ip, C.c_int, C.c_double, C.c_int]
+        L.ref_geo_add_edge.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
+        L.ref_geo_add_angle.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.ref_geo_add_ref_surface.argtypes = [vp, C.c_int, C.c_double, c_dp, C.c_int, c_ip, C.c_int, C.c_int]
+        L.ref_geo_add_relative_uniform_laplacian.argtypes = [vp, c_ip, C.c_int, C.c_double, c_dp, C.c_int]
+        L.ref_geo_add_uniform_laplacian.argtypes = [vp, c_ip, C.c_int, C.c_double]
+        L.ref_geo_add_closeness.argtypes = [vp, C.c_int, C.c_double, c_dp]
+        L.ref_geo_setup.argtypes = [vp, C.c_int, C.c_double]
+        L.ref_geo_solve.argtypes = [vp, c_dp, C.c_int, C.c_int, C.c_int]
+        L.ref_geo_history.argtypes = [vp, c_dp, c_dp]
+        L.ref_geo_solution.argtypes = [vp, c_dp, C.c_int]
+        self.h = vp(L.ref_geo_new(int(use_alm)))
+        self.n_points = 0
+
+    def __del__(self):
+        try:
+            self.L.ref_geo_free(self.h)
+        except Exception:
+            pass
+
+    def add_plane(self, idx, weight=1.0):
+        idx = np.ascontiguousarray(idx, np.int32)
+        self.L.ref_geo_add_plane(self.h, _ip(idx), len(idx), weight, 0)
+
+    def add_edge(self, i0, i1, weight, length):
+        self.L.ref_geo_add_edge(self.h, int(i0), int(i1), weight, length, 0)
+
+    def add_angle(self, tip, s1, s2, weight, amin, amax):
+        self.L.ref_geo_add_angle(self.h, int(tip), int(s1), int(s2), weight, amin, amax, 0)
+
+    def add_ref_surface(self, n_points, weight, V, F):
+        V = np.ascontiguousarray(V, np.float64)
+        F = np.ascontiguousarray(F, np.int32)
+        self.L.ref_geo_add_ref_surface(self.h, n_points, weight, _dp(V), len(V), _ip(F), len(F), 1)
+
+    def add_relative_uniform_laplacian(self, idx, weight, ref_pts):
+        idx = np.ascontiguousarray(idx, np.int32)
+        ref_pts = np.ascontiguousarray(ref_pts, np.float64)
+        self.L.ref_geo_add_relative_uniform_laplacian(self.h, _ip(idx), len(idx), weight, _dp(ref_pts), len(ref_pts))
+
+    def add_uniform_laplacian(self, idx, weight):
+        idx = np.ascontiguousarray(idx, np.int32)
+        self.L.ref_geo_add_uniform_laplacian(self.h, _ip(idx), len(idx), weight)
+
+    def add_closeness(self, idx, weight, target):
+        target = np.ascontiguousarray(target, np.float64)
+        self.L.ref_geo_add_closeness(self.h, int(idx), weight, _dp(target))
+
+    def setup(self, n_points, rho):
+        self.n_points = n_points
+        if self.L.ref_geo_setup(self.h, n_points, rho) != 0:
+            raise RuntimeError("reference setup_ADMM failed")
+
+    def solve(self, init_x, max_iter, anderson_m):
+        x0 = np.ascontiguousarray(init_x, np.float64)
+        n = self.L.ref_geo_solve(self.h, _dp(x0), self.n_points, max_iter, anderson_m)
+        hist, secs = np.zeros(max(n, 1)), np.zeros(max(n, 1))
+        self.L.ref_geo_history(self.h, _dp(hist), _dp(secs))
+        x = np.zeros((self.n_points, 3))
+        self.L.ref_geo_solution(self.h, _dp(x), self.n_points)
+        self.secs = secs[:n]
+        return hist[:n], x
+
+
+def ref_geo_project(kind, cols, a=0.0, b=0.0):
+    """cols: (n, kc, 3) transformed columns; kind 0 plane, 1 edge (a = length), 2 angle (a, b = min, max)."""
+    L = _load("libref_geo.so")
+    L.ref_geo_project.argtypes = [C.c_int, C.c_int, c_dp, c_dp, C.c_double, C.c_double]
+    cols = np.ascontiguousarray(cols, np.float64)
+    out = np.zeros_like(cols)
+    for i in range(cols.shape[0]):
+        ci = np.ascontiguousarray(cols[i])
+        oi = np.zeros_like(ci)
+        L.ref_geo_project(kind, cols.shape[1], _dp(ci), _dp(oi), a, b)
+        out[i] = oi
+    return out
+
+
+def ref_geo_closest_points(V, F, Q):
+    L = _load("libref_geo.so")
+    L.ref_geo_closest_points.argtypes = [c_dp, C.c_int, c_ip, C.c_int, c_dp, C.c_int, c_dp, c_ip, c_dp]
+    V = np.ascontiguousarray(V, np.float64)
+    F = np.ascontiguousarray(F, np.int32)
+    Q = np.ascontiguousarray(Q, np.float64)
+    Cp, I, d = np.zeros_like(Q), np.zeros(len(Q), np.int32), np.zeros(len(Q))
+    L.ref_geo_closest_points(_dp(V), len(V), _ip(F), len(F), _dp(Q), len(Q), _dp(Cp), _ip(I), _dp(d))
+    return Cp, I, d

@@ -1,0 +1,72 @@
+"""GPU parity of the Geometry path against the reference classes compiled into oracle/_ref/libref_geo.so."""
+import numpy as np
+import pytest
+
+from geo_scenes import build_planarity, build_wiremesh, ref_surface, wavy_grid
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def refgeo():
+    from oracle import refbind
+    if not refbind.have_ref_geo():
+        pytest.skip("oracle/_ref/libref_geo.so not present")
+    return refbind
+
+
+def test_projections_vs_reference(gpu, refgeo):
+    rng = np.random.default_rng(0)
+    # planes: mean-centred quads and hexagons, some nearly planar already
+    for k in (4, 6):
+        A = rng.standard_normal((300, k, 3))
+        A[:100, :, 2] *= 1e-3
+        A -= A.mean(axis=1, keepdims=True)
+        got = gpu.geo_project(0, A)
+        exp = refgeo.ref_geo_project(0, A)
+        assert np.abs(got - exp).max() < 1e-12
+    v = rng.standard_normal((500, 1, 3))
+    assert np.abs(gpu.geo_project(1, v, (0.7, 0, 0, 0)) - refgeo.ref_geo_project(1, v, 0.7)).max() < 1e-15
+    w = rng.standard_normal((2000, 2, 3))
+    w[:200, 1] = w[:200, 0] * 1.3 + 1e-3 * rng.standard_normal((200, 3))  # small angles
+    amin, amax = np.pi * 0.25, np.pi * 0.75
+    prm = (amin, amax, np.cos(amin), np.cos(amax))
+    assert np.abs(gpu.geo_project(2, w, prm) - refgeo.ref_geo_project(2, w, amin, amax)).max() < 1e-12
+
+
+def test_closest_points_vs_igl(gpu, refgeo):
+    V, F = ref_surface(12, 9, sub=3)
+    rng = np.random.default_rng(1)
+    Q = np.concatenate([V[rng.integers(0, len(V), 400)] + 0.3 * rng.standard_normal((400, 3)),
+                        rng.uniform(-3, 14, (400, 3))])
+    C, tri = gpu.geo_closest_points(V, F, Q)
+    Cr, Ir, dr = refgeo.ref_geo_closest_points(V, F, Q)
+    d = ((Q - C) ** 2).sum(1)
+    assert np.abs(d - dr).max() <= 1e-12 * max(1.0, dr.max())
+    same = np.abs(C - Cr).max(axis=1) < 1e-12
+    assert same.mean() > 0.99  # equal distances on shared edges may pick the other triangle's copy
+    assert np.abs(d[~same] - dr[~same]).max(initial=0.0) < 1e-12
+
+
+@pytest.mark.parametrize("kind,m,rho", [("planarity", 5, 1e5), ("planarity", 0, 1e5), ("wiremesh", 5, 1e3), ("wiremesh", 0, 1e3)])
+def test_alm_solve_vs_reference(gpu, refgeo, kind, m, rho):
+    nx, ny = 14, 11
+    P, quads, vid = wavy_grid(nx, ny)
+    V, F = ref_surface(nx, ny)
+    build = build_planarity if kind == "planarity" else build_wiremesh
+    g = gpu.GeometrySolver()
+    build(g, P, quads, vid, V, F)
+    g.setup(len(P), rho)
+    hg, xg = g.solve(P, 60, m)
+    r = refgeo.RefGeometrySolver(True)
+    build(r, P, quads, vid, V, F)
+    r.setup(len(P), rho)
+    hr, xr = r.solve(P, 60, m)
+    n = min(len(hg), len(hr))
+    rel = np.abs(hg[:n] - hr[:n]) / hr[:n]
+    floor = np.abs(hg[:n] - hr[:n]) / hr[0]
+    print(kind, m, "iters", len(hg), len(hr), "rel8 %.2e" % rel[:8].max(), "floor %.2e" % floor.max(), g.info())
+    assert len(hg) == len(hr) == 60
+    assert rel[:8].max() < 1e-9
+    assert floor.max() < 1e-9 if m == 0 else floor.max() < 1e-6
+    assert np.abs(xg - xr).max() / np.abs(xr).max() < 1e-6
