@@ -70,3 +70,58 @@ def test_alm_solve_vs_reference(gpu, refgeo, kind, m, rho):
     assert rel[:8].max() < 1e-9
     assert floor.max() < 1e-9 if m == 0 else floor.max() < 1e-6
     assert np.abs(xg - xr).max() / np.abs(xr).max() < 1e-6
+
+
+# ---- the reference's own applications on the shipped meshes (cfg 2 and cfg 3) -------------------
+import os  # noqa: E402
+
+from geo_recipes import planarity_recipe, wiremesh_recipe  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_cfg2_planarity_costa2k_vs_reference_app(gpu):
+    """PlanarityOpt costa2k_poly.obj costa2k_tri.obj Options.txt (100 iterations, m = 5, rho = 1e5): residual
+    history and final mesh of the unmodified reference application (tests/golden/make_golden_geo.py)."""
+    g = np.load(os.path.join(HERE, "golden", "geo_costa2k.npz"))
+    faces = [[int(v) for v in f if v >= 0] for f in g["faces"]]
+    s = gpu.GeometrySolver()
+    planarity_recipe(s, g["P"], faces, g["Vref"], g["Fref"])
+    s.setup(len(g["P"]), 1e5)
+    hist, x = s.solve(g["P"], 100, 5)
+    ref = g["hist"]
+    n = min(len(hist), len(ref))
+    rel = np.abs(hist[:n] - ref[:n]) / ref[:n]
+    info = s.info()
+    print("cfg2: iters", len(hist), len(ref), "rel first 8 %.2e" % rel[:8].max(), "max %.2e" % rel.max(),
+          "final %.3e vs %.3e" % (hist[-1], ref[-1]), info, "reference CPU loop %.3f s" % g["secs"][-1])
+    assert len(hist) == len(ref) == 100
+    assert rel[:8].max() < 1e-8
+    assert abs(np.log10(hist[-1] / ref[-1])) < 1.0
+    # both runs end on the same surface: positions agree far below the mesh's edge length
+    assert np.abs(x - g["solution"]).max() < 1e-3 * np.abs(g["P"]).max()
+
+
+def test_cfg3_wiremesh_maletorso_vs_reference_app(gpu):
+    p = os.path.join(HERE, "golden_large", "geo_maletorso.npz")
+    if not os.path.exists(p):
+        pytest.skip("tests/golden_large/geo_maletorso.npz not generated (make_golden_geo.py --large)")
+    g = np.load(p)
+    s = gpu.GeometrySolver()
+    wiremesh_recipe(s, g["P"], g["quads"], g["edges"], g["Vref"], g["Fref"], float(g["edge_length"]))
+    import time
+    t0 = time.time()
+    s.setup(len(g["P"]), 1e3)
+    t_setup = time.time() - t0
+    hist, x = s.solve(g["P"], 100, 5)
+    ref = g["hist"]
+    n = min(len(hist), len(ref))
+    rel = np.abs(hist[:n] - ref[:n]) / ref[:n]
+    info = s.info()
+    print("cfg3: iters", len(hist), len(ref), "rel first 8 %.2e" % rel[:8].max(), "max %.2e" % rel.max(),
+          "final %.3e vs %.3e" % (hist[-1], ref[-1]), info, "setup %.1f s" % t_setup,
+          "reference CPU loop %.1f s" % g["secs"][-1])
+    print('rel[:20]', rel[:20])
+    assert len(hist) == len(ref) == 100
+    assert rel[:2].max() < 1e-8 and rel[:10].max() < 1e-4
+    assert abs(np.log10(hist[-1] / ref[-1])) < 1.0
