@@ -270,6 +270,16 @@ def tet_f_minus_uvt(z):
     return out
 
 
+def tet_prox_hyper(material, mu, lam, vol, z):
+    """Returns (prox(z), vol * dPsi/dF(z)) for NeoHookean (1) / StVK (2) blocks."""
+    L = cuda_lib()
+    L.aaadmm_tet_prox_hyper.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, c_dp, c_dp, C.c_int64]
+    z = np.ascontiguousarray(z, np.float64).copy()
+    g = np.zeros_like(z)
+    _ck(L.aaadmm_tet_prox_hyper(material, mu, lam, vol, _dp(z), _dp(g), z.shape[0]))
+    return z, g
+
+
 def cod_solve(M, rhs):
     M = np.asfortranarray(M, np.float64)
     rhs = np.ascontiguousarray(rhs, np.float64)

@@ -82,6 +82,7 @@ __global__ void k_init_state(SolveState *st, int accel, int m, double eps, int m
     st->skip_redo = 1;
     st->aa_skip = 0;
     st->prim2 = 0.0;
+    st->hyper_prim2 = 0.0;
     st->prev_prim = 1e+20;
     st->comb = 0.0;
     st->eps = eps;
@@ -143,6 +144,9 @@ struct aaadmm_tetscene {
     // constants
     int4 *idx = nullptr;
     double *binv = nullptr, *w = nullptr, *kvol = nullptr, *mass = nullptr;
+    int *material = nullptr, *hyper_ids = nullptr;
+    double *mu = nullptr, *lambda = nullptr, *volume = nullptr;
+    int n_hyper = 0;
     int64_t *inc_ptr = nullptr;
     int *inc = nullptr;
     // state
@@ -357,6 +361,11 @@ int aaadmm_tetscene_destroy(aaadmm_tetscene *s) {
     cudaFree(s->w);
     cudaFree(s->kvol);
     cudaFree(s->mass);
+    cudaFree(s->material);
+    cudaFree(s->hyper_ids);
+    cudaFree(s->mu);
+    cudaFree(s->lambda);
+    cudaFree(s->volume);
     cudaFree(s->inc_ptr);
     cudaFree(s->inc);
     cudaFree(s->Ubuf);
@@ -402,12 +411,19 @@ int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *d,
         set_last_error("tetscene_create: factor must be n_free x n_free with nrhs = 3");
         return -1;
     }
+    std::vector<int> hyper_ids;
     if (d->material) {
-        for (int t = 0; t < d->n_tets; ++t)
-            if (d->material[t] != 0) {
-                set_last_error("tetscene_create: only LINEAR tets are implemented on the device in this round");
+        for (int t = 0; t < d->n_tets; ++t) {
+            if (d->material[t] < 0 || d->material[t] > 2) {
+                set_last_error("tetscene_create: material must be 0 (linear), 1 (neo-hookean) or 2 (stvk)");
                 return -1;
             }
+            if (d->material[t] != 0) hyper_ids.push_back(t);
+        }
+        if (!hyper_ids.empty() && (!d->mu || !d->lambda || !d->volume)) {
+            set_last_error("tetscene_create: hyper-elastic tets need mu, lambda and volume");
+            return -1;
+        }
     }
     aaadmm_tetscene *s = new aaadmm_tetscene();
     const int T = d->n_tets, V = d->n_verts, NF = d->n_free;
@@ -434,6 +450,19 @@ int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *d,
     AAADMM_CUDA_OK(cudaMemcpy(s->w, d->weight, sizeof(double) * T, cudaMemcpyHostToDevice));
     AAADMM_CUDA_OK(cudaMalloc((void **)&s->kvol, sizeof(double) * T));
     AAADMM_CUDA_OK(cudaMemcpy(s->kvol, d->kvol, sizeof(double) * T, cudaMemcpyHostToDevice));
+    s->n_hyper = (int)hyper_ids.size();
+    if (s->n_hyper > 0) {
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->material, sizeof(int) * T));
+        AAADMM_CUDA_OK(cudaMemcpy(s->material, d->material, sizeof(int) * T, cudaMemcpyHostToDevice));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->hyper_ids, sizeof(int) * s->n_hyper));
+        AAADMM_CUDA_OK(cudaMemcpy(s->hyper_ids, hyper_ids.data(), sizeof(int) * s->n_hyper, cudaMemcpyHostToDevice));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->mu, sizeof(double) * T));
+        AAADMM_CUDA_OK(cudaMemcpy(s->mu, d->mu, sizeof(double) * T, cudaMemcpyHostToDevice));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->lambda, sizeof(double) * T));
+        AAADMM_CUDA_OK(cudaMemcpy(s->lambda, d->lambda, sizeof(double) * T, cudaMemcpyHostToDevice));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->volume, sizeof(double) * T));
+        AAADMM_CUDA_OK(cudaMemcpy(s->volume, d->volume, sizeof(double) * T, cudaMemcpyHostToDevice));
+    }
     AAADMM_CUDA_OK(cudaMalloc((void **)&s->mass, sizeof(double) * NF));
     AAADMM_CUDA_OK(cudaMemcpy(s->mass, d->mass_free, sizeof(double) * NF, cudaMemcpyHostToDevice));
     AAADMM_CUDA_OK(cudaMalloc((void **)&s->inc_ptr, sizeof(int64_t) * (NF + 1)));
@@ -559,7 +588,7 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
     const int T = s->T, NF = s->NF;
     const bool accel = o->accel && o->anderson_m > 0;
     const int m = accel ? o->anderson_m : 1;
-    TetArrays A{T, NF, s->V, s->idx, s->binv, s->w, s->kvol, s->rho_dt2};
+    TetArrays A{T, NF, s->V, s->idx, s->binv, s->w, s->kvol, s->rho_dt2, s->material, s->mu, s->lambda, s->volume, s->hyper_ids, s->n_hyper};
     const int gt = std::min((T + TET_BLOCK - 1) / TET_BLOCK, stream_grid(8));
     const int gv = (NF + 127) / 128;
     const int gs = stream_grid(4);
@@ -661,7 +690,7 @@ static int run_xzu(aaadmm_tetscene *s, const aaadmm_step_opts *o, int iters, boo
     const int T = s->T, NF = s->NF;
     const bool accel = o->accel && o->anderson_m > 0;
     const int m = o->anderson_m > 0 ? o->anderson_m : 1;
-    TetArrays A{T, NF, s->V, s->idx, s->binv, s->w, s->kvol, s->rho_dt2};
+    TetArrays A{T, NF, s->V, s->idx, s->binv, s->w, s->kvol, s->rho_dt2, s->material, s->mu, s->lambda, s->volume, s->hyper_ids, s->n_hyper};
     const int gt = std::min((T + TET_BLOCK - 1) / TET_BLOCK, stream_grid(8));
     const int gs = stream_grid(4);
     const int64_t NZ = s->Ne, NX = 3 * (int64_t)NF;
@@ -919,6 +948,23 @@ int aaadmm_tet_f_minus_uvt(const double *z, double *out, int64_t n) {
     cudaFree(o);
     return 0;
 }
+int aaadmm_tet_prox_hyper(int material, double mu, double lambda, double vol, double *z, double *grad, int64_t n) {
+    if (aaadmm_device_count() <= 0) {
+        set_last_error("no CUDA device (this library has no CPU path)");
+        return -1;
+    }
+    double *d = nullptr, *g = nullptr;
+    AAADMM_CUDA_OK(cudaMalloc((void **)&d, sizeof(double) * 9 * n));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&g, sizeof(double) * 9 * n));
+    AAADMM_CUDA_OK(cudaMemcpy(d, z, sizeof(double) * 9 * n, cudaMemcpyHostToDevice));
+    launch_prox_hyper_batch(material, mu, lambda, vol, d, g, n);
+    AAADMM_CUDA_OK(cudaGetLastError());
+    AAADMM_CUDA_OK(cudaMemcpy(z, d, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost));
+    if (grad) AAADMM_CUDA_OK(cudaMemcpy(grad, g, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    cudaFree(g);
+    return 0;
+}
 int aaadmm_cod_solve(int m, const double *M, const double *rhs, double *x, int *rank) {
     if (aaadmm_device_count() <= 0) {
         set_last_error("no CUDA device (this library has no CPU path)");
@@ -1048,6 +1094,7 @@ int up(T **dst, const T *src, size_t n) {
 
 __global__ void k_geo_init_state(SolveState *st, int m, int max_iters) {
     st->prim2 = 0.0;
+    st->hyper_prim2 = 0.0;
     st->prev_prim = DBL_MAX;  // prev_residual
     st->comb = 0.0;
     st->eps = 0.0;

@@ -38,6 +38,7 @@ struct SolveState {
     double prev_prim;  // prev_prim_residual (norm)
     double comb;       // latest combined residual
     double eps;        // break threshold on comb (1e-20 in the reference)
+    double hyper_prim2;  // residual share of the hyper-elastic tets (0 for linear scenes)
     int reject;        // decision of the current iteration
     int done;          // comb < eps reached: the remaining launches of this step are no-ops
     int iter;          // rows logged so far

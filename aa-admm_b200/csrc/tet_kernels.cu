@@ -9,6 +9,7 @@
 
 #include <algorithm>
 
+#include "lbfgs_prox.cuh"
 #include "svd3.cuh"
 
 namespace aaadmm {
@@ -82,6 +83,7 @@ k_update_z_hard(TetArrays A, const double *__restrict__ pos, const double *__res
     // B^-1 and u are parked in shared memory while the Jacobi SVD runs: 36 fewer live registers
     __shared__ double s_park[18][TET_BLOCK];
     for (int t = blockIdx.x * TET_BLOCK + threadIdx.x; t < T; t += gridDim.x * TET_BLOCK) {
+        if (A.material && A.material[t] != 0) continue;  // handled by k_hyper
         const int4 id = A.idx[t];
         double zi[9], F[9];
         const double w = A.w[t];
@@ -119,8 +121,9 @@ k_update_z_hard(TetArrays A, const double *__restrict__ pos, const double *__res
     double out[1];
     if (grid_reduce<1, TET_BLOCK>(acc, partials, &st->ticket, out)) {
         if (threadIdx.x == 0) {
-            const double prim = sqrt(out[0]);
-            st->prim2 = out[0];
+            const double tot = out[0] + st->hyper_prim2;
+            const double prim = sqrt(tot);
+            st->prim2 = tot;
             if (MODE == MODE_ITER) {
                 if (st->accel && st->prev_prim < prim) {
                     st->reject = 1;
@@ -288,6 +291,7 @@ k_grad_u_xzu(TetArrays A, const double *__restrict__ z, double *__restrict__ u, 
     if (st->done) return;
     const int T = A.n_tets;
     for (int t = blockIdx.x * TET_BLOCK + threadIdx.x; t < T; t += gridDim.x * TET_BLOCK) {
+        if (A.material && A.material[t] != 0) continue;  // handled by k_hyper
         double zi[9], g[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) zi[k] = z[(size_t)k * T + t];
@@ -397,6 +401,7 @@ k_update_z_plain(TetArrays A, const double *__restrict__ pos, const double *__re
     if (st && st->done) return;
     const int T = A.n_tets;
     for (int t = blockIdx.x * TET_BLOCK + threadIdx.x; t < T; t += gridDim.x * TET_BLOCK) {
+        if (A.material && A.material[t] != 0) continue;  // handled by k_hyper
         const int4 id = A.idx[t];
         double b[9], F[9], zi[9];
 #pragma unroll
@@ -478,6 +483,71 @@ __global__ void k_copy2_if_not_done(double *__restrict__ d0, const double *__res
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += stride) d1[i] = s1[i];
 }
 
+// =========================================================================================
+// Hyper-elastic tets (HyperElasticTet::prox / get_gradient, xzu/src/TetEnergyTerm.cpp:171-215):
+// one thread per listed tet; runs BEFORE the linear kernel of the same step, which then adds
+// st->hyper_prim2 to its own residual sum.
+//   KIND 0: hard_zxu local step (z, contributions, residual)   `mode` as k_update_z_hard
+//   KIND 1: z_out = prox((D x - c + u)/w)
+//   KIND 2: u = W^-1 * vol * dPsi(z)
+// =========================================================================================
+template <int KIND>
+__global__ void __launch_bounds__(TET_BLOCK)
+k_hyper(TetArrays A, const double *__restrict__ pos, const double *__restrict__ uz_in, double *__restrict__ out,
+        double *__restrict__ contrib, SolveState *st, double *partials, int mode) {
+    if (st->done) return;
+    if (KIND == 0 && mode == MODE_REDO && !st->reject) return;
+    const int T = A.n_tets;
+    double acc[1] = {0.0};
+    for (int h = blockIdx.x * TET_BLOCK + threadIdx.x; h < A.n_hyper; h += gridDim.x * TET_BLOCK) {
+        const int t = A.hyper_ids[h];
+        HyperParams P;
+        P.mu = A.mu[t];
+        P.lambda = A.lambda[t];
+        P.k = P.lambda + (2.0 / 3.0) * P.mu;
+        P.vol = A.volume[t];
+        P.material = A.material[t];
+        const double w = A.w[t];
+        if (KIND == 2) {
+            double zi[9], g[9];
+            for (int k = 0; k < 9; ++k) zi[k] = uz_in[(size_t)k * T + t];
+            tet_grad_hyper(P, zi, g);
+            const double winv = 1.0 / w;
+            for (int k = 0; k < 9; ++k) out[(size_t)k * T + t] = winv * g[k];
+            continue;
+        }
+        const int4 id = A.idx[t];
+        double b[9], F[9], zi[9], ui[9];
+        for (int k = 0; k < 9; ++k) b[k] = A.binv[(size_t)k * T + t];
+        deformation_gradient(pos, id, b, F);
+        const double winv = 1.0 / w;
+        for (int k = 0; k < 9; ++k) {
+            ui[k] = uz_in[(size_t)k * T + t];
+            F[k] = w * F[k];
+            zi[k] = (F[k] + ui[k]) * winv;
+        }
+        tet_prox_lbfgs(P, zi);
+        for (int k = 0; k < 9; ++k) out[(size_t)k * T + t] = zi[k];
+        if (KIND == 0) {
+            double y[9], q[12];
+            for (int k = 0; k < 9; ++k) {
+                const double wz = w * zi[k];
+                const double r = F[k] - wz;
+                acc[0] += r * r;
+                y[k] = wz - ui[k];
+            }
+            corner_contrib(b, w, A.rho_dt2, y, q);
+            double *qo = contrib + (size_t)t * 12;
+            for (int k = 0; k < 12; ++k) qo[k] = q[k];
+        }
+    }
+    if (KIND != 0) return;
+    double o[1];
+    if (grid_reduce<1, TET_BLOCK>(acc, partials, &st->ticket, o)) {
+        if (threadIdx.x == 0) st->hyper_prim2 = o[0];
+    }
+}
+
 // ---- batched element kernels (unit parity) ----
 __global__ void k_prox_batch(double *z, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -496,9 +566,24 @@ __global__ void k_fmuvt_batch(const double *z, double *out, int64_t n) {
     for (int k = 0; k < 9; ++k) out[9 * i + k] = g[k];
 }
 
+__global__ void k_prox_hyper_batch(HyperParams P, double *z, double *g, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double zi[9], gi[9];
+    for (int k = 0; k < 9; ++k) zi[k] = z[9 * i + k];
+    tet_grad_hyper(P, zi, gi);
+    tet_prox_lbfgs(P, zi);
+    for (int k = 0; k < 9; ++k) {
+        z[9 * i + k] = zi[k];
+        g[9 * i + k] = gi[k];
+    }
+}
+
 // ---- host launchers (this translation unit is compiled with -fmad=false) ----
 void launch_update_z_hard(int mode, int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *u,
                           double *z, double *contrib, SolveState *st, double *partials) {
+    if (A.n_hyper > 0)
+        k_hyper<0><<<(A.n_hyper + TET_BLOCK - 1) / TET_BLOCK, TET_BLOCK, 0, s>>>(A, pos, u, z, contrib, st, partials, mode);
     if (mode == MODE_WARM)
         k_update_z_hard<MODE_WARM><<<grid, TET_BLOCK, 0, s>>>(A, pos, u, z, contrib, st, partials);
     else if (mode == MODE_ITER)
@@ -530,12 +615,19 @@ void launch_bconst(cudaStream_t s, const TetArrays &A, const int64_t *inc_ptr, c
 void launch_copy_if_not_done(cudaStream_t s, double *dst, const double *src, int64_t n, const SolveState *st) {
     k_copy_if_not_done<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(dst, src, n, st);
 }
+void launch_prox_hyper_batch(int material, double mu, double lambda, double vol, double *d_z, double *d_g, int64_t n) {
+    HyperParams P{mu, lambda, lambda + (2.0 / 3.0) * mu, vol, material};
+    k_prox_hyper_batch<<<(unsigned)((n + 127) / 128), 128>>>(P, d_z, d_g, n);
+}
 void launch_prox_batch(double *d_z, int64_t n) { k_prox_batch<<<(unsigned)((n + 127) / 128), 128>>>(d_z, n); }
 void launch_fmuvt_batch(const double *d_z, double *d_out, int64_t n) {
     k_fmuvt_batch<<<(unsigned)((n + 127) / 128), 128>>>(d_z, d_out, n);
 }
 
 void launch_grad_u_xzu(int grid, cudaStream_t s, const TetArrays &A, const double *z, double *u, const SolveState *st) {
+    if (A.n_hyper > 0)
+        k_hyper<2><<<(A.n_hyper + TET_BLOCK - 1) / TET_BLOCK, TET_BLOCK, 0, s>>>(A, nullptr, z, u, nullptr,
+                                                                               const_cast<SolveState *>(st), nullptr, 0);
     k_grad_u_xzu<<<grid, TET_BLOCK, 0, s>>>(A, z, u, st);
 }
 void launch_z_from_x(int grid, cudaStream_t s, const TetArrays &A, const double *pos, double *z) {
@@ -558,6 +650,9 @@ void launch_restore_xzu(int grid, cudaStream_t s, double *u, const double *u_def
 }
 void launch_update_z_plain(int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *u,
                            double *z_out, const SolveState *st) {
+    if (A.n_hyper > 0)
+        k_hyper<1><<<(A.n_hyper + TET_BLOCK - 1) / TET_BLOCK, TET_BLOCK, 0, s>>>(A, pos, u, z_out, nullptr,
+                                                                               const_cast<SolveState *>(st), nullptr, 0);
     k_update_z_plain<<<grid, TET_BLOCK, 0, s>>>(A, pos, u, z_out, st);
 }
 void launch_update_u_plain(int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *z, double *u,

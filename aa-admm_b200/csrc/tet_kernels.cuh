@@ -19,6 +19,11 @@ struct TetArrays {
     const double *w;      // [T]
     const double *kvol;   // [T]
     double rho_dt2;
+    // hyper-elastic tets (Neo-Hookean / StVK prox by per-tet L-BFGS); all null / 0 for linear scenes
+    const int *material;   // [T] 0 linear, 1 NH, 2 StVK
+    const double *mu, *lambda, *volume;  // [T]
+    const int *hyper_ids;  // tets with material != 0
+    int n_hyper;
 };
 
 enum { MODE_WARM = 0, MODE_ITER = 1, MODE_REDO = 2 };
@@ -55,6 +60,7 @@ void launch_comb_xzu(int grid, cudaStream_t s, const TetArrays &A, const double 
                      int *hist_rej);
 void launch_copy2_if_not_done(int grid, cudaStream_t s, double *d0, const double *s0, int64_t n0, double *d1,
                               const double *s1, int64_t n1, const SolveState *st);
+void launch_prox_hyper_batch(int material, double mu, double lambda, double vol, double *d_z, double *d_g, int64_t n);
 void launch_prox_batch(double *d_z, int64_t n);
 void launch_fmuvt_batch(const double *d_z, double *d_out, int64_t n);
 

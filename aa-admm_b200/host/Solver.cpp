@@ -140,6 +140,7 @@ bool Solver::initialize(const Settings &settings_) {
     d.inc_ptr = m_sys.inc_ptr.data();
     d.inc = m_sys.inc.data();
     d.rho_dt2 = rho * dt2;
+    d.volume = m_sys.volume.data();
     if (aaadmm_tetscene_create(&m_scene, &d, m_ldlt) != 0)
         throw std::runtime_error(std::string("aaadmm_tetscene_create: ") + aaadmm_last_error());
     m_xbar.resize((size_t)3 * m_sys.n_free);

@@ -92,6 +92,7 @@ typedef struct {
     const int64_t *inc_ptr;  /* n_free+1: incidence CSR over free vertices                     */
     const int *inc;          /* entries tet*4+corner                                           */
     double rho_dt2;          /* penalty * dt^2 (hard) or dt^2 (xzu)                            */
+    const double *volume;    /* n_tets rest volumes (hyper-elastic only, may be NULL)          */
 } aaadmm_tetscene_desc;
 
 #define AAADMM_ORDER_HARD_ZXU 0
@@ -199,6 +200,10 @@ int aaadmm_geo_closest_points(const double *verts, int nv, const int *tris, int 
  * ------------------------------------------------------------------------------------------ */
 int aaadmm_tet_prox_linear(double *z, int64_t n);
 int aaadmm_tet_f_minus_uvt(const double *z, double *out, int64_t n);
+/* HyperElasticTet::prox (xzu/src/TetEnergyTerm.cpp:171-183; material 1 NeoHookean, 2 StVK; L-BFGS of
+ * deps/mcloptlib/include/MCL/LBFGS.hpp:205-305) in place on n blocks; grad (may be NULL) receives
+ * get_gradient = vol * dPsi/dF of the INPUT blocks. */
+int aaadmm_tet_prox_hyper(int material, double mu, double lambda, double vol, double *z, double *grad, int64_t n);
 int aaadmm_cod_solve(int m, const double *M, const double *rhs, double *x, int *rank);
 
 #ifdef __cplusplus

@@ -72,6 +72,24 @@ struct ProbeTet : public admm::TetEnergyTerm {
     const Eigen::Matrix3d &binv() const { return edges_inv; }
 };
 
+template <typename TET>
+struct ProbeHyper : public TET {
+    using TET::TET;
+    void call_prox(double *z9) {
+        typename TET::VecX zi = Eigen::Map<typename TET::VecX>(z9, 9);
+        typename TET::VecX vi = zi;
+        Eigen::Matrix<double, 9, 9> W = Eigen::Matrix<double, 9, 9>::Identity();
+        this->prox(W, zi, vi);
+        Eigen::Map<typename TET::VecX>(z9, 9) = zi;
+    }
+    void call_grad(const double *z9, double *g9) {
+        typename TET::VecX zi = Eigen::Map<const typename TET::VecX>(z9, 9);
+        typename TET::VecX g = TET::VecX::Zero(9);
+        this->get_gradient(zi, g);
+        Eigen::Map<typename TET::VecX>(g9, 9) = g;
+    }
+};
+
 }  // namespace
 
 extern "C" {
@@ -312,6 +330,26 @@ void RFN(tet_F_minus_UVt)(const double *z, double *out, int n) {
         t.call_grad(z + 9 * i, out + 9 * i);
         for (int k = 0; k < 9; ++k) out[9 * i + k] /= kv;
     }
+}
+
+// HyperElasticTet::prox (NeoHookeanTet material 1 / StVKTet material 2) on n blocks for the tet with the
+// given rest vertices; in place. Also get_gradient (vol * dPsi/dF).
+int RFN(tet_prox_hyper)(int material, const double *verts12, double youngs, double poisson, double *z, double *grad_out, int n) {
+    std::vector<Eigen::Vector3d> v(4);
+    for (int i = 0; i < 4; ++i) v[i] = Eigen::Vector3d(verts12[3 * i], verts12[3 * i + 1], verts12[3 * i + 2]);
+    try {
+        if (material == 1) {
+            ProbeHyper<admm::NeoHookeanTet> t(Eigen::Vector4i(0, 1, 2, 3), v, admm::Lame(youngs, poisson));
+            for (int i = 0; i < n; ++i) { if (grad_out) t.call_grad(z + 9 * i, grad_out + 9 * i); t.call_prox(z + 9 * i); }
+        } else {
+            ProbeHyper<admm::StVKTet> t(Eigen::Vector4i(0, 1, 2, 3), v, admm::Lame(youngs, poisson));
+            for (int i = 0; i < n; ++i) { if (grad_out) t.call_grad(z + 9 * i, grad_out + 9 * i); t.call_prox(z + 9 * i); }
+        }
+    } catch (std::exception &e) {
+        fprintf(stderr, "ref tet_prox_hyper: %s\n", e.what());
+        return -1;
+    }
+    return 0;
 }
 
 // The reference's own scene generator (ShapeFactory.hpp:436-497 + TetMesh::refine +

@@ -259,3 +259,53 @@ def test_xzu_step_vs_reference_16x4x4(gpu, ref):
         assert rel[:8].max() < 1e-9
         assert (np.abs(hg[f][:n, 1] - hr[f][:n, 2]) / hr[f][0, 2]).max() < 1e-9
         assert np.abs(xg[f] - xr[f]).max() / np.abs(xr[f]).max() < 1e-6
+
+
+# ---- hyper-elastic tets: per-tet L-BFGS prox (row H) and BASELINE configs[0] ---------------------
+def test_hyper_prox_vs_reference(gpu, ref):
+    import ctypes as C
+    L = ref._load("libref_xzu.so")
+    dp = C.POINTER(C.c_double)
+    L.ref_xzu_tet_prox_hyper.argtypes = [C.c_int, dp, C.c_double, C.c_double, dp, dp, C.c_int]
+    verts = np.array([[0, 0, 0], [0.08, 0, 0], [0, 0.09, 0], [0, 0, 0.085]], float).reshape(-1)
+    E, nu = 1e7, 0.399
+    mu, lam = E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu))
+    _, vol, _ = ref.ref_tet_constants(verts.reshape(4, 3), E, nu)
+    rng = np.random.default_rng(0)
+    F = np.eye(3).reshape(1, 9) + 0.15 * rng.standard_normal((2000, 9))
+    for mat in (1, 2):
+        zr, gr = F.copy(), np.zeros_like(F)
+        assert L.ref_xzu_tet_prox_hyper(mat, verts.ctypes.data_as(dp), E, nu, zr.ctypes.data_as(dp), gr.ctypes.data_as(dp), len(F)) == 0
+        zg, gg = gpu.tet_prox_hyper(mat, mu, lam, vol, F)
+        # the L-BFGS stopping rules (1e-6 on the gradient, 1e-16 on the objective change) make the iteration
+        # count round-off dependent: most blocks agree to the last bits, a few stop one step apart
+        d = np.abs(zr - zg).max(axis=1)
+        assert np.median(d) < 1e-15
+        assert d.max() < 1e-7
+        assert np.abs(gr - gg).max() <= 1e-13 * np.abs(gr).max()
+
+
+def test_cfg1_three_material_beams_xzu_vs_reference(gpu, ref):
+    """BASELINE configs[0]: admm_anderson_xzu on the 3-beam LINEAR / NeoHookean / StVK scene, m = 5."""
+    from scenes import run_cfg1
+    hg, xg = run_cfg1(gpu.Solver, gpu, frames=1, ordering=gpu.ORDER_XZU)
+    hr, xr = run_cfg1(lambda: ref.RefSolver("xzu"), gpu, frames=1, ordering=None)
+    n = min(len(hg[0]), len(hr[0]))
+    rel = np.abs(hg[0][:n, 1] - hr[0][:n, 2]) / hr[0][:n, 2]
+    relp = np.abs(hg[0][:n, 0] - hr[0][:n, 1]) / hr[0][:n, 1]
+    print("cfg1 rows", len(hg[0]), len(hr[0]), "comb rel first 5", rel[:5], "prim rel first 5", relp[:5])
+    # SURVEY 7.3-7: two builds of the reference already differ by 3e-9 at iteration 1 on this scene
+    assert rel[:3].max() < 1e-6 and relp[:3].max() < 1e-6
+    assert abs(len(hg[0]) - len(hr[0])) <= max(2, 0.25 * len(hr[0]))
+    assert np.abs(xg[0] - xr[0]).max() / np.abs(xr[0]).max() < 1e-6
+
+
+def test_cfg1_three_material_beams_hard_vs_reference(gpu, ref):
+    from scenes import run_cfg1
+    hg, xg = run_cfg1(gpu.Solver, gpu, frames=1, ordering=gpu.ORDER_HARD_ZXU)
+    hr, xr = run_cfg1(lambda: ref.RefSolver("hard"), gpu, frames=1, ordering=None)
+    n = min(len(hg[0]), len(hr[0]))
+    rel = np.abs(hg[0][:n, 1] - hr[0][:n, 2]) / hr[0][:n, 2]
+    print("cfg1(hard) rows", len(hg[0]), len(hr[0]), "comb rel first 5", rel[:5])
+    assert rel[:3].max() < 1e-6
+    assert np.abs(xg[0] - xr[0]).max() / np.abs(xr[0]).max() < 1e-6
