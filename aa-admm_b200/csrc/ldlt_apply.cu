@@ -15,6 +15,7 @@
 #include "ldlt_apply.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace aaadmm {
@@ -37,33 +38,61 @@ __device__ __forceinline__ void warp_sum(double (&a)[NR]) {
 // CTAs take 8 SHORT rows each, one warp per row. Either way one row is summed by one fixed set
 // of lanes in a fixed order: the result is deterministic and needs no atomics.
 struct RowLists {
-    const int *long_rows;
+    const int *long_rows;   // one CTA per row
     int n_long;
-    const int *short_rows;
+    const int *short_rows;  // one warp per row
     int n_short;
+    const int *tiny_rows;   // 8 lanes per row (rows of <= TINY_ROW entries: the leaf levels)
+    int n_tiny;
 };
+constexpr int TINY_LANES = 8;
+constexpr int TINY_PER_CTA = WARPS_PER_CTA * 32 / TINY_LANES;
 
+__host__ __device__ __forceinline__ int short_ctas(const RowLists &L) { return (L.n_short + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
+
+// cls: 0 long, 1 short, 2 tiny. Inactive lanes of a tiny CTA keep running (their warp still shuffles).
 template <int NR>
-__device__ __forceinline__ bool pick_row(const RowLists &L, int &row, int &tid, int &nthr) {
-    if ((int)blockIdx.x < L.n_long) {
-        row = L.long_rows[blockIdx.x];
+__device__ __forceinline__ bool pick_row(const RowLists &L, int &row, int &tid, int &nthr, int &cls) {
+    const int b = (int)blockIdx.x;
+    if (b < L.n_long) {
+        cls = 0;
+        row = L.long_rows[b];
         tid = threadIdx.x;
         nthr = WARPS_PER_CTA * 32;
         return true;
     }
-    const int wid = ((int)blockIdx.x - L.n_long) * WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (wid >= L.n_short) return false;
-    row = L.short_rows[wid];
-    tid = threadIdx.x & 31;
-    nthr = 32;
+    const int ns = short_ctas(L);
+    if (b < L.n_long + ns) {
+        cls = 1;
+        const int wid = (b - L.n_long) * WARPS_PER_CTA + (threadIdx.x >> 5);
+        tid = threadIdx.x & 31;
+        nthr = 32;
+        if (wid >= L.n_short) return false;
+        row = L.short_rows[wid];
+        return true;
+    }
+    cls = 2;
+    const int gid = (b - L.n_long - ns) * TINY_PER_CTA + (threadIdx.x / TINY_LANES);
+    tid = threadIdx.x & (TINY_LANES - 1);
+    nthr = TINY_LANES;
+    if (gid >= L.n_tiny) return false;
+    row = L.tiny_rows[gid];
     return true;
 }
 
 // Reduces acc over the lanes that worked on the row; returns true in the one thread holding it.
 template <int NR>
-__device__ __forceinline__ bool row_reduce(const RowLists &L, double (&acc)[NR]) {
+__device__ __forceinline__ bool row_reduce(int cls, bool active, double (&acc)[NR]) {
+    if (cls == 2) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+#pragma unroll
+            for (int o = TINY_LANES / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+        }
+        return active && (threadIdx.x & (TINY_LANES - 1)) == 0;
+    }
     warp_sum<NR>(acc);
-    if ((int)blockIdx.x >= L.n_long) return (threadIdx.x & 31) == 0;
+    if (cls == 1) return active && (threadIdx.x & 31) == 0;
     __shared__ double s_part[WARPS_PER_CTA][NR];
     const int warp = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) {
@@ -88,8 +117,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 k_fwd_off(RowLists L, const int64_t *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val,
           const double *__restrict__ Y, double *__restrict__ W, const int *skip) {
     if (skip && *skip) return;
-    int row, tid, nthr;
-    const bool active = pick_row<NR>(L, row, tid, nthr);
+    int row = 0, tid, nthr, cls;
+    const bool active = pick_row<NR>(L, row, tid, nthr, cls);
     double acc[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) acc[r] = 0.0;
@@ -103,8 +132,7 @@ k_fwd_off(RowLists L, const int64_t *__restrict__ ptr, const int *__restrict__ c
             for (int r = 0; r < NR; ++r) acc[r] += v * Y[(size_t)c * NR + r];
         }
     }
-    if ((int)blockIdx.x >= L.n_long && !active) return;
-    if (row_reduce<NR>(L, acc)) {
+    if (row_reduce<NR>(cls, active, acc)) {
 #pragma unroll
         for (int r = 0; r < NR; ++r) W[(size_t)row * NR + r] -= acc[r];
     }
@@ -117,8 +145,8 @@ k_fwd_diag(RowLists L, const int *__restrict__ blk_of, const int *__restrict__ b
            const int64_t *__restrict__ linv_off, const double *__restrict__ Linv, const double *__restrict__ W,
            double *__restrict__ Y, const int *skip) {
     if (skip && *skip) return;
-    int row, tid, nthr;
-    const bool active = pick_row<NR>(L, row, tid, nthr);
+    int row = 0, tid, nthr, cls;
+    const bool active = pick_row<NR>(L, row, tid, nthr, cls);
     double acc[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) acc[r] = 0.0;
@@ -135,8 +163,7 @@ k_fwd_diag(RowLists L, const int *__restrict__ blk_of, const int *__restrict__ b
             for (int r = 0; r < NR; ++r) acc[r] += v * W[(size_t)(first + j) * NR + r];
         }
     }
-    if ((int)blockIdx.x >= L.n_long && !active) return;
-    if (row_reduce<NR>(L, acc)) {
+    if (row_reduce<NR>(cls, active, acc)) {
 #pragma unroll
         for (int r = 0; r < NR; ++r) Y[(size_t)row * NR + r] = acc[r];
     }
@@ -149,8 +176,8 @@ k_bwd_off(RowLists L, const int64_t *__restrict__ ptr, const int *__restrict__ r
           const double *__restrict__ dinv, const double *__restrict__ Y, const double *__restrict__ X,
           double *__restrict__ W, const int *skip) {
     if (skip && *skip) return;
-    int j, tid, nthr;
-    const bool active = pick_row<NR>(L, j, tid, nthr);
+    int j = 0, tid, nthr, cls;
+    const bool active = pick_row<NR>(L, j, tid, nthr, cls);
     double acc[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) acc[r] = 0.0;
@@ -164,8 +191,7 @@ k_bwd_off(RowLists L, const int64_t *__restrict__ ptr, const int *__restrict__ r
             for (int r = 0; r < NR; ++r) acc[r] += v * X[(size_t)i * NR + r];
         }
     }
-    if ((int)blockIdx.x >= L.n_long && !active) return;
-    if (row_reduce<NR>(L, acc)) {
+    if (row_reduce<NR>(cls, active, acc)) {
         const double di = dinv[j];
 #pragma unroll
         for (int r = 0; r < NR; ++r) W[(size_t)j * NR + r] = Y[(size_t)j * NR + r] * di - acc[r];
@@ -179,8 +205,8 @@ k_bwd_diag(RowLists L, const int *__restrict__ blk_of, const int *__restrict__ b
            const int64_t *__restrict__ linv_off, const double *__restrict__ LinvT, const double *__restrict__ W,
            double *__restrict__ X, const int *__restrict__ perm, double *__restrict__ x_out, const int *skip) {
     if (skip && *skip) return;
-    int row, tid, nthr;
-    const bool active = pick_row<NR>(L, row, tid, nthr);
+    int row = 0, tid, nthr, cls;
+    const bool active = pick_row<NR>(L, row, tid, nthr, cls);
     double acc[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) acc[r] = 0.0;
@@ -197,8 +223,7 @@ k_bwd_diag(RowLists L, const int *__restrict__ blk_of, const int *__restrict__ b
             for (int r = 0; r < NR; ++r) acc[r] += v * W[(size_t)(first + j) * NR + r];
         }
     }
-    if ((int)blockIdx.x >= L.n_long && !active) return;
-    if (row_reduce<NR>(L, acc)) {
+    if (row_reduce<NR>(cls, active, acc)) {
         const int o = perm[row];
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
@@ -303,7 +328,9 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     const int64_t nnz = Lp[n];
 
     // ---- block partition: elimination-tree chains with nested patterns ----
-    const int kSmall = 32, kCap = 6144;
+    // tuning knobs (environment overrides are for experiments only)
+    auto env_int = [](const char *name, int dflt) { const char *v = getenv(name); return v ? atoi(v) : dflt; };
+    const int kSmall = env_int("AAADMM_KSMALL", 96), kCap = 6144;
     std::vector<int> blk_of(n), blk_first;
     for (int j = 0; j < n; ++j) {
         bool join = false;
@@ -384,20 +411,21 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
 
     // ---- level lists: per level and per sweep kernel, LONG rows (one CTA each) and SHORT rows ----
     // kinds: 0 fwd_off (rows with off-block entries), 1 fwd_diag, 2 bwd_off, 3 bwd_diag
-    const int64_t kLong = 1024;
-    std::vector<std::vector<int>> lists((size_t)nlev * 8);
+    const int64_t kLong = env_int("AAADMM_KLONG", 1024), kTiny = env_int("AAADMM_KTINY", 64);
+    auto cls_of = [&](int64_t len) { return len > kLong ? 0 : (len > kTiny ? 1 : 2); };
+    std::vector<std::vector<int>> lists((size_t)nlev * 12);
     for (int j = 0; j < n; ++j) {
         const int b = blk_of[j];
         const int l = level[b];
         const int i = j - blk_first[b], ns = blk_first[b + 1] - blk_first[b];
         const int64_t fo = fr_ptr[j + 1] - fr_ptr[j], bo = bc_ptr[j + 1] - bc_ptr[j];
-        if (fo > 0) lists[(size_t)l * 8 + 0 + (fo > kLong ? 0 : 1)].push_back(j);
-        lists[(size_t)l * 8 + 2 + (i + 1 > kLong ? 0 : 1)].push_back(j);
-        lists[(size_t)l * 8 + 4 + (bo > kLong ? 0 : 1)].push_back(j);
-        lists[(size_t)l * 8 + 6 + (ns - i > kLong ? 0 : 1)].push_back(j);
+        if (fo > 0) lists[(size_t)l * 12 + 0 + cls_of(fo)].push_back(j);
+        lists[(size_t)l * 12 + 3 + cls_of(i + 1)].push_back(j);
+        lists[(size_t)l * 12 + 6 + cls_of(bo)].push_back(j);
+        lists[(size_t)l * 12 + 9 + cls_of(ns - i)].push_back(j);
     }
     std::vector<int> lev_rows;
-    f->list_ptr.assign((size_t)nlev * 8 + 1, 0);
+    f->list_ptr.assign((size_t)nlev * 12 + 1, 0);
     for (size_t k = 0; k < lists.size(); ++k) {
         lev_rows.insert(lev_rows.end(), lists[k].begin(), lists[k].end());
         f->list_ptr[k + 1] = (int)lev_rows.size();
@@ -481,15 +509,16 @@ static int apply_impl(LdltDev *f, double *x_out, cudaStream_t s, const int *skip
     const int nlev = f->n_levels;
     auto lists = [&](int l, int kind) {
         RowLists L;
-        const int a = f->list_ptr[(size_t)l * 8 + 2 * kind], b = f->list_ptr[(size_t)l * 8 + 2 * kind + 1],
-                  c = f->list_ptr[(size_t)l * 8 + 2 * kind + 2];
-        L.long_rows = f->lev_rows + a;
-        L.n_long = b - a;
-        L.short_rows = f->lev_rows + b;
-        L.n_short = c - b;
+        const int *p = &f->list_ptr[(size_t)l * 12 + 3 * kind];
+        L.long_rows = f->lev_rows + p[0];
+        L.n_long = p[1] - p[0];
+        L.short_rows = f->lev_rows + p[1];
+        L.n_short = p[2] - p[1];
+        L.tiny_rows = f->lev_rows + p[2];
+        L.n_tiny = p[3] - p[2];
         return L;
     };
-    auto grid = [](const RowLists &L) { return L.n_long + (L.n_short + WARPS_PER_CTA - 1) / WARPS_PER_CTA; };
+    auto grid = [](const RowLists &L) { return L.n_long + short_ctas(L) + (L.n_tiny + TINY_PER_CTA - 1) / TINY_PER_CTA; };
     const int T = WARPS_PER_CTA * 32;
     for (int l = 0; l < nlev; ++l) {
         RowLists a = lists(l, 0), b = lists(l, 1);

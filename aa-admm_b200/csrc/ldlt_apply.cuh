@@ -34,8 +34,8 @@ struct LdltDev {
     int64_t *bc_ptr = nullptr;
     int *bc_row = nullptr;
     double *bc_val = nullptr;
-    // per level and sweep kernel (fwd_off, fwd_diag, bwd_off, bwd_diag): LONG rows then SHORT rows;
-    // list_ptr[(level*4 + kind)*2 + {0,1,2}] delimit them inside lev_rows
+    // per level and sweep kernel (fwd_off, fwd_diag, bwd_off, bwd_diag): LONG, SHORT and TINY rows;
+    // list_ptr[(level*4 + kind)*3 + {0,1,2,3}] delimit them inside lev_rows
     std::vector<int> list_ptr;
     int *lev_rows = nullptr;
     // work vectors n x nrhs

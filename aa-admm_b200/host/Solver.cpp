@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
@@ -114,7 +115,8 @@ bool Solver::initialize(const Settings &settings_) {
     std::vector<double> coords((size_t)3 * m_sys.n_free);
     for (int k = 0; k < m_sys.n_free; ++k)
         for (int j = 0; j < 3; ++j) coords[3 * (size_t)k + j] = m_x[3 * (size_t)m_sys.dev_to_vert[k] + j];
-    std::vector<int> perm = aaadmm::nested_dissection(m_sys.Ahat, coords.data(), m_settings.nd_leaf_size);
+    const char *leaf_env = getenv("AAADMM_ND_LEAF");  // experiments only
+    std::vector<int> perm = aaadmm::nested_dissection(m_sys.Ahat, coords.data(), leaf_env ? atoi(leaf_env) : m_settings.nd_leaf_size);
     m_factor = aaadmm::ldlt_factorize(m_sys.Ahat, perm);
     if (!m_factor.ok) {
         std::cerr << "\n**Solver Error: LDLT factorization failed" << std::endl;
