@@ -503,6 +503,8 @@ def _geo_host():
     if not hasattr(H, "_geo_ready"):
         vp = C.c_void_p
         H.aaadmm_host_geo_new.restype = vp
+        H.aaadmm_host_geo_new_variant.restype = vp
+        H.aaadmm_host_geo_new_variant.argtypes = [C.c_int]
         H.aaadmm_host_geo_free.argtypes = [vp]
         H.aaadmm_host_geo_add_plane.argtypes = [vp, c_ip, C.c_int, C.c_double]
         H.aaadmm_host_geo_add_edge.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double]
@@ -522,11 +524,15 @@ def _geo_host():
 
 class GeometrySolver:
     """ALMGeometrySolver<3> mirror: hard plane / edge / angle constraints, soft closest-point-to-
-    reference-surface constraint, Laplacian / closeness regularisation."""
+    reference-surface constraint, Laplacian / closeness regularisation.
+    variant="gs" selects the older GeometrySolver<3> loop (Geometry/GeometrySolver.h:156-263)."""
 
-    def __init__(self):
+    def __init__(self, variant="alm"):
         self.H = _geo_host()
-        self.h = C.c_void_p(self.H.aaadmm_host_geo_new())
+        if variant not in ("alm", "gs"):
+            raise ValueError("variant must be 'alm' or 'gs'")
+        self.variant = variant
+        self.h = C.c_void_p(self.H.aaadmm_host_geo_new_variant(1 if variant == "gs" else 0))
         self.n_points = 0
 
     def __del__(self):

@@ -1122,14 +1122,15 @@ __global__ void k_geo_loop_cond(cudaGraphConditionalHandle h, SolveState *st) {
 }  // namespace
 
 struct aaadmm_geo {
-    int P = 0, n_hard = 0, zc = 0, n_soft = 0;
+    int P = 0, n_hard = 0, zc = 0, n_soft = 0, variant = 0;
+    int zc_all = 0;  // z / u columns: zc (ALM) or zc + n_soft (GS)
     aaadmm_ldlt *factor = nullptr;
     cudaStream_t stream = nullptr;
     int *type = nullptr, *idx_ptr = nullptr, *idx = nullptr, *col0 = nullptr, *dt_col = nullptr, *soft_point = nullptr,
         *soft_of_point = nullptr, *last_tri = nullptr;
     int64_t *dt_ptr = nullptr;
     double *param = nullptr, *dt_val = nullptr, *rhs_fixed = nullptr;
-    double soft_weight = 0;
+    double soft_weight = 0, rho = 1.0;
     RefMeshDev mesh;
     int64_t N = 0;  // 3 zc + 3 P: the Anderson variable (u | x)
     double *Ubuf = nullptr, *Nbuf = nullptr, *Dbuf = nullptr, *z = nullptr, *prev_dx = nullptr, *cp = nullptr;
@@ -1210,7 +1211,10 @@ int aaadmm_geo_create(aaadmm_geo **out, const aaadmm_geo_desc *d, aaadmm_ldlt *f
     g->n_soft = d->n_soft;
     g->soft_weight = d->soft_weight;
     g->factor = factor;
-    g->N = 3 * (int64_t)zc + 3 * (int64_t)g->P;
+    g->variant = d->variant == AAADMM_GEO_GS ? AAADMM_GEO_GS : AAADMM_GEO_ALM;
+    g->rho = d->rho;
+    g->zc_all = zc + (g->variant == AAADMM_GEO_GS ? d->n_soft : 0);
+    g->N = 3 * (int64_t)g->zc_all + 3 * (int64_t)g->P;
     AAADMM_CUDA_OK(cudaStreamCreate(&g->stream));
     int rc = 0;
     rc |= up(&g->type, d->type, d->n_hard);
@@ -1235,8 +1239,8 @@ int aaadmm_geo_create(aaadmm_geo **out, const aaadmm_geo_desc *d, aaadmm_ldlt *f
     AAADMM_CUDA_OK(cudaMalloc((void **)&g->Ubuf, sizeof(double) * g->N));
     AAADMM_CUDA_OK(cudaMalloc((void **)&g->Nbuf, sizeof(double) * g->N));
     AAADMM_CUDA_OK(cudaMalloc((void **)&g->Dbuf, sizeof(double) * g->N));
-    AAADMM_CUDA_OK(cudaMalloc((void **)&g->z, sizeof(double) * 3 * std::max(zc, 1)));
-    AAADMM_CUDA_OK(cudaMalloc((void **)&g->prev_dx, sizeof(double) * 3 * std::max(zc, 1)));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&g->z, sizeof(double) * 3 * std::max(g->zc_all, 1)));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&g->prev_dx, sizeof(double) * 3 * std::max(g->zc_all, 1)));
     AAADMM_CUDA_OK(cudaMalloc((void **)&g->cp, sizeof(double) * 3 * std::max(d->n_soft, 1)));
     AAADMM_CUDA_OK(cudaMalloc((void **)&g->partials, sizeof(double) * RED_MAX_Q * RED_MAX_BLOCKS));
     AAADMM_CUDA_OK(cudaMalloc((void **)&g->st, sizeof(SolveState)));
@@ -1291,6 +1295,69 @@ static int geo_enqueue_turn(aaadmm_geo *g, int m, int &L) {
     return 0;
 }
 
+// GeometrySolver<3>: the warm-up turn of ADMM_init_variables (Geometry/GeometrySolver.h:383-407)
+static int gs_enqueue_x_u(aaadmm_geo *g, const GeoConstraints &C, const GeoSoft &S, int &L) {
+    cudaStream_t st = g->stream;
+    LdltDev *f = g->factor->f;
+    const int64_t NU = 3 * (int64_t)g->zc_all;
+    double *cu = g->Ubuf, *du = g->Dbuf, *dx = g->Dbuf + NU;
+    // x_update: default_x = solve(rhs_fixed + rho D^T (z - current_u))   (:436-443)
+    launch_geo_rhs(st, g->P, g->dt_ptr, g->dt_col, g->dt_val, g->z, cu, g->rhs_fixed, nullptr, 0.0, nullptr, f->iperm,
+                   f->W, g->st);
+    if (ldlt_dev_apply_permuted(f, dx, st, &g->st->done)) return -1;
+    launch_gs_dx(st, C, S, g->zc, dx, g->prev_dx, g->st, 0);
+    launch_gs_u(st, cu, g->prev_dx, g->z, du, NU, g->st);
+    L += 3 + 4 * f->n_levels;
+    return 0;
+}
+static int gs_enqueue_warmup(aaadmm_geo *g, int &L) {
+    cudaStream_t st = g->stream;
+    GeoConstraints C;
+    GeoSoft S;
+    geo_views(g, C, S);
+    const int64_t NU = 3 * (int64_t)g->zc_all;
+    launch_gs_dx(st, C, S, g->zc, g->Ubuf + NU, g->prev_dx, g->st, 0);
+    launch_gs_z(st, 0, C, S, g->zc, g->rho, g->prev_dx, g->Ubuf, g->z, nullptr, g->st, g->partials, g->hist);
+    if (gs_enqueue_x_u(g, C, S, L)) return -1;
+    launch_gs_take_default(st, g->Ubuf, g->Dbuf, g->N, g->st, 0);
+    L += 3;
+    return 0;
+}
+// one turn of the while loop of GeometrySolver.h:181-254; Dx of current_x is in prev_dx on entry
+static int gs_enqueue_turn(aaadmm_geo *g, int m, int &L) {
+    cudaStream_t st = g->stream;
+    GeoConstraints C;
+    GeoSoft S;
+    geo_views(g, C, S);
+    const int64_t NU = 3 * (int64_t)g->zc_all;
+    double *cu = g->Ubuf, *cx = g->Ubuf + NU;
+    launch_gs_z(st, 1, C, S, g->zc, g->rho, g->prev_dx, cu, g->z, nullptr, g->st, g->partials, g->hist);
+    L += 1;
+    if (m > 0) {  // need_reset: back to the un-accelerated iterate, z again
+        launch_gs_take_default(st, g->Ubuf, g->Dbuf, g->N, g->st, 1);
+        launch_gs_dx(st, C, S, g->zc, cx, g->prev_dx, g->st, 1);
+        launch_gs_z(st, 2, C, S, g->zc, g->rho, g->prev_dx, cu, g->z, nullptr, g->st, g->partials, g->hist);
+        L += 3;
+    }
+    if (gs_enqueue_x_u(g, C, S, L)) return -1;
+    if (m > 0) {
+        const int gs = stream_grid(4);
+        if (launch_aa_pass1(m, gs, st, g->Dbuf, g->Dbuf + NU, nullptr, g->Ubuf, g->dF, g->dG, NU, g->N, g->st, g->partials))
+            return -1;
+        if (launch_aa_pass2(m, gs, st, g->Dbuf, g->Dbuf + NU, g->Ubuf, g->dF, g->dG, NU, g->N, g->st)) return -1;
+        L += 2;
+    } else {
+        launch_gs_take_default(st, g->Ubuf, g->Dbuf, g->N, g->st, 0);
+        L += 1;
+    }
+    launch_gs_dx(st, C, S, g->zc, cx, g->prev_dx, g->st, 0);
+    L += 1;
+    return 0;
+}
+static int geo_enqueue_any(aaadmm_geo *g, int m, int &L) {
+    return g->variant == AAADMM_GEO_GS ? gs_enqueue_turn(g, m, L) : geo_enqueue_turn(g, m, L);
+}
+
 int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int anderson_m, double *x_out, double *hist,
                      aaadmm_step_result *res) {
     API_TRY_BEGIN
@@ -1314,7 +1381,7 @@ int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int ande
         g->m_cap = m;
         g->graph_key = -1;
     }
-    const int64_t NU = 3 * (int64_t)g->zc;
+    const int64_t NU = 3 * (int64_t)g->zc_all;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -1327,6 +1394,7 @@ int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int ande
     k_geo_init_state<<<1, 1, 0, st>>>(g->st, m, max_iter);
     int launches = 0;
     AAADMM_CUDA_OK(cudaEventRecord(e0, st));
+    if (g->variant == AAADMM_GEO_GS && gs_enqueue_warmup(g, launches)) return -1;
     static const bool no_graph = getenv("AAADMM_NO_GRAPH") != nullptr;
     SolveState hs;
     if (max_iter > 0 && !no_graph) {
@@ -1347,7 +1415,7 @@ int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int ande
             AAADMM_CUDA_OK(cudaStreamBeginCaptureToGraph(st, np.conditional.phGraph_out[0], nullptr, nullptr, 0,
                                                          cudaStreamCaptureModeThreadLocal));
             int L = 0;
-            const int rc = geo_enqueue_turn(g, m, L);
+            const int rc = geo_enqueue_any(g, m, L);
             k_geo_loop_cond<<<1, 1, 0, st>>>(h, g->st);
             cudaError_t e = cudaStreamEndCapture(st, nullptr);
             if (rc || e != cudaSuccess) {
@@ -1361,14 +1429,16 @@ int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int ande
         AAADMM_CUDA_OK(cudaGraphLaunch(g->exec, st));
     } else if (max_iter > 0) {
         for (int turn = 0; turn < 4 * max_iter + 8; ++turn) {
-            if (geo_enqueue_turn(g, m, launches)) return -1;
+            if (geo_enqueue_any(g, m, launches)) return -1;
             AAADMM_CUDA_OK(cudaMemcpyAsync(&hs, g->st, sizeof(SolveState), cudaMemcpyDeviceToHost, st));
             AAADMM_CUDA_OK(cudaStreamSynchronize(st));
             if (hs.iter >= max_iter) break;
         }
     }
     AAADMM_CUDA_OK(cudaEventRecord(e1, st));
-    AAADMM_CUDA_OK(cudaMemcpyAsync(x_out, g->Dbuf + NU, sizeof(double) * 3 * g->P, cudaMemcpyDeviceToHost, st));
+    // the solution is default_x (ALMGeometrySolver.h:285) resp. current_x (GeometrySolver.h:265)
+    AAADMM_CUDA_OK(cudaMemcpyAsync(x_out, (g->variant == AAADMM_GEO_GS ? g->Ubuf : g->Dbuf) + NU, sizeof(double) * 3 * g->P,
+                                   cudaMemcpyDeviceToHost, st));
     AAADMM_CUDA_OK(cudaMemcpyAsync(&hs, g->st, sizeof(SolveState), cudaMemcpyDeviceToHost, st));
     AAADMM_CUDA_OK(cudaStreamSynchronize(st));
     if (hist && hs.iter > 0) AAADMM_CUDA_OK(cudaMemcpy(hist, g->hist, sizeof(double) * hs.iter, cudaMemcpyDeviceToHost));

@@ -440,7 +440,139 @@ __global__ void k_geo_select(double *__restrict__ cur, double *__restrict__ def,
     }
 }
 
+// ---- GeometrySolver<3> (older variant) -----------------------------------------------------------
+// when: 0 always, 1 only on a rejected iterate
+__global__ void __launch_bounds__(GEO_BLOCK)
+k_gs_dx(GeoConstraints C, GeoSoft S, int zc_hard, const double *__restrict__ x, double *__restrict__ dx,
+        const SolveState *st, int when) {
+    if (st->done || (when == 1 && !st->reject)) return;
+    const int c = blockIdx.x * GEO_BLOCK + threadIdx.x;
+    if (c < C.n) {
+        const int type = C.type[c], p0 = C.idx_ptr[c], k = C.idx_ptr[c + 1] - p0;
+        double d[GEO_MAX_K * 3];
+        const int kc = geo_transform(type, C.idx + p0, k, x, d);
+        const size_t o = 3 * (size_t)C.col0[c];
+        for (int j = 0; j < kc * 3; ++j) dx[o + j] = d[j];
+    } else if (c < C.n + S.n) {
+        const int i = c - C.n;
+        const int pt = S.point ? S.point[i] : i;
+        const size_t o = 3 * ((size_t)zc_hard + i);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) dx[o + r] = x[3 * (size_t)pt + r];
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(GEO_BLOCK)
+k_gs_z(GeoConstraints C, GeoSoft S, int zc_hard, double rho, const double *__restrict__ dx,
+       const double *__restrict__ u, double *__restrict__ z, SolveState *st, double *partials, double *hist) {
+    if (st->done) return;
+    if (MODE == 2 && !st->reject) return;
+    double acc[1] = {0.0};
+    const int total = C.n + S.n;
+    for (int c = blockIdx.x * GEO_BLOCK + threadIdx.x; c < total; c += gridDim.x * GEO_BLOCK) {
+        if (c < C.n) {
+            const int type = C.type[c], k = C.idx_ptr[c + 1] - C.idx_ptr[c];
+            const int kc = type == GEO_PLANE ? k : k - 1;
+            const size_t o = 3 * (size_t)C.col0[c];
+            double v[GEO_MAX_K * 3], zz[GEO_MAX_K * 3];
+            for (int j = 0; j < kc * 3; ++j) v[j] = dx[o + j] + u[o + j];
+            geo_project(type, v, kc, C.param + 4 * (size_t)c, zz);
+            for (int j = 0; j < kc * 3; ++j) {
+                z[o + j] = zz[j];
+                const double r = dx[o + j] - zz[j];
+                acc[0] += r * r;
+            }
+        } else {
+            const int i = c - C.n;
+            const size_t o = 3 * ((size_t)zc_hard + i);
+            double v[3], cp[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) v[r] = dx[o + r] + u[o + r];
+            int tri;
+            bvh_closest(S, v, S.last_tri ? S.last_tri[i] : -1, cp, &tri);
+            if (S.last_tri) S.last_tri[i] = tri;
+            // Constraint::project_and_combine (Constraint.h:118-130): a = rho / (w + rho)
+            const double a = rho / (S.weight + rho);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const double zz = v[r] * a + cp[r] * (1 - a);
+                z[o + r] = zz;
+                const double d = dx[o + r] - zz;
+                acc[0] += d * d;
+            }
+        }
+    }
+    if (MODE == 0) return;  // warm-up turn of ADMM_init_variables: no residual
+    double out[1];
+    if (grid_reduce<1, GEO_BLOCK>(acc, partials, &st->ticket, out)) {
+        if (threadIdx.x == 0) {
+            const double res = sqrt(out[0]);  // get_ADMM_residual: (Dx - z).norm()
+            st->comb = res;
+            bool log = true;
+            if (MODE == 1) {
+                st->reject = (st->accel && res > st->prev_prim) ? 1 : 0;  // need_reset
+                if (st->reject) {
+                    st->n_rejects += 1;
+                    log = false;  // logged after the redo
+                }
+            }
+            if (log) {
+                const int it = st->iter;
+                hist[it] = res;
+                st->iter = it + 1;
+                st->prev_prim = res;
+                if (st->iter >= st->max_iters) st->done = 1;  // end_iteration: the rest of this turn is skipped
+            }
+        }
+    }
+}
+
+// when = 1: the reset of GeometrySolver.h:192-197. The reference swaps the two buffers; the old current
+// (the rejected accelerated iterate) is dead afterwards - x_update / u_update overwrite all of default -
+// so a one-way copy is equivalent. when = 0: the un-accelerated swap of :243-246, same argument.
+__global__ void k_gs_take_default(double *__restrict__ cur, const double *__restrict__ def, int64_t n,
+                                  const SolveState *st, int when) {
+    if (st->done || (when == 1 && !st->reject)) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) cur[i] = def[i];
+}
+
+__global__ void k_gs_u(const double *__restrict__ u_cur, const double *__restrict__ dx, const double *__restrict__ z,
+                       double *__restrict__ u_def, int64_t n, const SolveState *st) {
+    if (st->done) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        u_def[i] = u_cur[i] + dx[i] - z[i];
+}
+
 }  // namespace
+
+void launch_gs_dx(cudaStream_t s, const GeoConstraints &C, const GeoSoft &S, int zc_hard, const double *x, double *dx,
+                  const SolveState *st, int when) {
+    const int total = C.n + S.n;
+    if (total > 0) k_gs_dx<<<(total + GEO_BLOCK - 1) / GEO_BLOCK, GEO_BLOCK, 0, s>>>(C, S, zc_hard, x, dx, st, when);
+}
+void launch_gs_z(cudaStream_t s, int mode, const GeoConstraints &C, const GeoSoft &S, int zc_hard, double rho,
+                 const double *dx, const double *u, double *z, double *cp_scratch, SolveState *st, double *partials,
+                 double *hist) {
+    (void)cp_scratch;
+    const int total = C.n + S.n;
+    const int grid = max(1, min((total + GEO_BLOCK - 1) / GEO_BLOCK, stream_grid(8)));
+    if (mode == 0)
+        k_gs_z<0><<<grid, GEO_BLOCK, 0, s>>>(C, S, zc_hard, rho, dx, u, z, st, partials, hist);
+    else if (mode == 1)
+        k_gs_z<1><<<grid, GEO_BLOCK, 0, s>>>(C, S, zc_hard, rho, dx, u, z, st, partials, hist);
+    else
+        k_gs_z<2><<<grid, GEO_BLOCK, 0, s>>>(C, S, zc_hard, rho, dx, u, z, st, partials, hist);
+}
+void launch_gs_take_default(cudaStream_t s, double *cur, const double *def, int64_t n, const SolveState *st, int when) {
+    k_gs_take_default<<<stream_grid(4), 256, 0, s>>>(cur, def, n, st, when);
+}
+void launch_gs_u(cudaStream_t s, const double *u_cur, const double *dx, const double *z, double *u_def, int64_t n,
+                 const SolveState *st) {
+    k_gs_u<<<stream_grid(4), 256, 0, s>>>(u_cur, dx, z, u_def, n, st);
+}
 
 void launch_geo_local(cudaStream_t s, const GeoConstraints &C, const double *x, const double *u, double *prev_dx,
                       double *z, const SolveState *st) {

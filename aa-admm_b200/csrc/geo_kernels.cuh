@@ -57,6 +57,21 @@ void launch_geo_u_resid(cudaStream_t s, const GeoConstraints &C, const double *x
 // on accept without acceleration: current = default = new; on reject: current = default
 void launch_geo_select(cudaStream_t s, double *cur, double *def, const double *nw, int64_t n, const SolveState *st,
                        int accel);
+// ---- GeometrySolver<3> (older variant, Geometry/GeometrySolver.h:156-263, ops :383-459) ----------
+// Dx for hard rows (transform) and soft rows (the point itself), rows [0, n_hard cols) then one per soft point
+void launch_gs_dx(cudaStream_t s, const GeoConstraints &C, const GeoSoft &S, int zc_hard, const double *x, double *dx,
+                  const SolveState *st, int when);
+// z = project(Dx + u) (hard) / a (Dx+u) + (1-a) closest(Dx+u) (soft, a = rho/(w+rho)); residual |Dx - z|;
+// mode 0: warm-up turn (no residual); mode 1: decide need_reset = accel && residual > prev (GeometrySolver.h:186-190); mode 2: redo after the swap
+void launch_gs_z(cudaStream_t s, int mode, const GeoConstraints &C, const GeoSoft &S, int zc_hard, double rho,
+                 const double *dx, const double *u, double *z, double *cp_scratch, SolveState *st, double *partials,
+                 double *hist);
+// current = default: when = 1 only after a rejected iterate (:192-197), when = 0 always (:243-246)
+void launch_gs_take_default(cudaStream_t s, double *cur, const double *def, int64_t n, const SolveState *st, int when);
+// default_u = current_u + Dx - z (:450-455)
+void launch_gs_u(cudaStream_t s, const double *u_cur, const double *dx, const double *z, double *u_def, int64_t n,
+                 const SolveState *st);
+
 // unit-parity entry: project n_c constraints given already transformed columns (device arrays)
 void launch_geo_project_only(const GeoConstraints &C, const double *v, double *z);
 void launch_geo_closest_only(const GeoSoft &S, const double *q, double *cp, int *tri_out);

@@ -9,12 +9,12 @@
 namespace aaadmm {
 
 template <unsigned int N>
-ALMGeometrySolver<N>::ALMGeometrySolver() : penalty_parameter_(1.0), solver_initialized_(false) {
+GeometrySolverBase<N>::GeometrySolverBase(int variant) : variant_(variant), penalty_parameter_(1.0), solver_initialized_(false) {
     last_result = aaadmm_step_result();
 }
 
 template <unsigned int N>
-ALMGeometrySolver<N>::~ALMGeometrySolver() {
+GeometrySolverBase<N>::~GeometrySolverBase() {
     // the solver owns the constraints (Geometry/ALMGeometrySolver.h:67-79)
     for (auto *c : hard_constraints_) delete c;
     for (auto *c : soft_constraints_) delete c;
@@ -24,7 +24,7 @@ ALMGeometrySolver<N>::~ALMGeometrySolver() {
 
 // LinearRegularization<N> (Geometry/LinearRegularization.h:47-153)
 template <unsigned int N>
-void ALMGeometrySolver<N>::add_laplacian_helper(const std::vector<int> &indices, const std::vector<double> &coefs,
+void GeometrySolverBase<N>::add_laplacian_helper(const std::vector<int> &indices, const std::vector<double> &coefs,
                                                 double weight, const MatrixNX *ref) {
     const double sw = std::sqrt(weight);
     reg_idx_.push_back(indices);
@@ -38,39 +38,39 @@ void ALMGeometrySolver<N>::add_laplacian_helper(const std::vector<int> &indices,
     for (int r = 0; r < 3; ++r) reg_target_.push_back(t[r] * sw);
 }
 template <unsigned int N>
-void ALMGeometrySolver<N>::add_uniform_laplacian(const std::vector<int> &indices, double weight) {
+void GeometrySolverBase<N>::add_uniform_laplacian(const std::vector<int> &indices, double weight) {
     const int n = (int)indices.size();
     std::vector<double> coefs(1, 1.0);
     coefs.insert(coefs.end(), n - 1, -1.0 / double(n - 1));
     add_laplacian_helper(indices, coefs, weight, nullptr);
 }
 template <unsigned int N>
-void ALMGeometrySolver<N>::add_laplacian(const std::vector<int> &indices, const std::vector<double> coefs, double weight) {
+void GeometrySolverBase<N>::add_laplacian(const std::vector<int> &indices, const std::vector<double> coefs, double weight) {
     add_laplacian_helper(indices, coefs, weight, nullptr);
 }
 template <unsigned int N>
-void ALMGeometrySolver<N>::add_relative_uniform_laplacian(const std::vector<int> &indices, double weight, const MatrixNX &ref) {
+void GeometrySolverBase<N>::add_relative_uniform_laplacian(const std::vector<int> &indices, double weight, const MatrixNX &ref) {
     const int n = (int)indices.size();
     std::vector<double> coefs(1, 1.0);
     coefs.insert(coefs.end(), n - 1, -1.0 / double(n - 1));
     add_laplacian_helper(indices, coefs, weight, &ref);
 }
 template <unsigned int N>
-void ALMGeometrySolver<N>::add_relative_laplacian(const std::vector<int> &indices, const std::vector<double> coefs,
+void GeometrySolverBase<N>::add_relative_laplacian(const std::vector<int> &indices, const std::vector<double> coefs,
                                                   double weight, const MatrixNX &ref) {
     add_laplacian_helper(indices, coefs, weight, &ref);
 }
 template <unsigned int N>
-void ALMGeometrySolver<N>::add_closeness(int idx, double weight, const double *target_pt) {
+void GeometrySolverBase<N>::add_closeness(int idx, double weight, const double *target_pt) {
     const double sw = std::sqrt(weight);
     reg_idx_.push_back(std::vector<int>(1, idx));
     reg_coef_.push_back(std::vector<double>(1, sw));
     for (int r = 0; r < 3; ++r) reg_target_.push_back(target_pt[r] * sw);
 }
 
-// Geometry/ALMGeometrySolver.h:81-161
+// Geometry/ALMGeometrySolver.h:81-161, Geometry/GeometrySolver.h:85-155
 template <unsigned int N>
-bool ALMGeometrySolver<N>::setup_ADMM(int n_points, double penalty_param, SPDSolverType) {
+bool GeometrySolverBase<N>::setup_ADMM(int n_points, double penalty_param, SPDSolverType) {
     penalty_parameter_ = penalty_param;
     n_points_ = n_points;
     const int nh = (int)hard_constraints_.size();
@@ -154,8 +154,32 @@ bool ALMGeometrySolver<N>::setup_ADMM(int n_points, double penalty_param, SPDSol
             soft_point.push_back(p);
             tr.push_back(p);
             tc.push_back(p);
-            tv.push_back(soft_weight);
+            // ALM: weighted identity rows outside the penalty term (ALMGeometrySolver.h:103-112);
+            // GS: unweighted rows of the one D (GeometrySolver.h:106-108,120-121)
+            tv.push_back(variant_ == AAADMM_GEO_GS ? penalty_param : soft_weight);
         }
+    }
+    if (variant_ == AAADMM_GEO_GS && !soft_point.empty()) {
+        // append the soft rows to rho * D^T: point p gets column zc + i with coefficient rho
+        std::vector<std::vector<std::pair<int, double>>> extra(n_points);
+        for (size_t i = 0; i < soft_point.size(); ++i) extra[soft_point[i]].emplace_back(zc + (int)i, penalty_param);
+        std::vector<int64_t> np(n_points + 1, 0);
+        std::vector<int> ncol;
+        std::vector<double> nval;
+        for (int p = 0; p < n_points; ++p) {
+            for (int64_t e = dt_ptr[p]; e < dt_ptr[p + 1]; ++e) {
+                ncol.push_back(dt_col[e]);
+                nval.push_back(dt_val[e]);
+            }
+            for (auto &e : extra[p]) {
+                ncol.push_back(e.first);
+                nval.push_back(e.second);
+            }
+            np[p + 1] = (int64_t)ncol.size();
+        }
+        dt_ptr.swap(np);
+        dt_col.swap(ncol);
+        dt_val.swap(nval);
     }
     std::vector<double> rhs_fixed((size_t)3 * n_points, 0.0);
     for (size_t r = 0; r < reg_idx_.size(); ++r) {
@@ -208,6 +232,8 @@ bool ALMGeometrySolver<N>::setup_ADMM(int n_points, double penalty_param, SPDSol
     d.n_ref_tris = surf ? (int)(surf->tris.size() / 3) : 0;
     d.ref_tris = surf ? surf->tris.data() : nullptr;
     d.rhs_fixed = rhs_fixed.data();
+    d.variant = variant_;
+    d.rho = penalty_param;
     if (aaadmm_geo_create(&geo_, &d, ldlt_) != 0) {
         std::cerr << "Error: " << aaadmm_last_error() << std::endl;
         return false;
@@ -216,9 +242,9 @@ bool ALMGeometrySolver<N>::setup_ADMM(int n_points, double penalty_param, SPDSol
     return true;
 }
 
-// Geometry/ALMGeometrySolver.h:163-283
+// Geometry/ALMGeometrySolver.h:163-283, Geometry/GeometrySolver.h:156-263
 template <unsigned int N>
-void ALMGeometrySolver<N>::solve_ADMM(const MatrixNX &init_x, double, int max_iter, int Anderson_m) {
+void GeometrySolverBase<N>::solve_ADMM(const MatrixNX &init_x, double, int max_iter, int Anderson_m) {
     if (!solver_initialized_) {
         std::cerr << "Error: solver not initialized yet" << std::endl;
         return;
@@ -240,7 +266,7 @@ void ALMGeometrySolver<N>::solve_ADMM(const MatrixNX &init_x, double, int max_it
 }
 
 template <unsigned int N>
-void ALMGeometrySolver<N>::save(int Anderson_m) {
+void GeometrySolverBase<N>::save(int Anderson_m) {
     std::string file = Anderson_m > 0 ? "./result/residual-" + std::to_string(Anderson_m) + ".txt" : "./result/residual-no.txt";
     std::ofstream ofs(file, std::ios::out | std::ios::ate);
     if (!ofs.is_open()) {
@@ -251,6 +277,6 @@ void ALMGeometrySolver<N>::save(int Anderson_m) {
     for (size_t i = 0; i < elapsed_time_.size(); i++) ofs << elapsed_time_[i] << '\t' << function_values_[i] << std::endl;
 }
 
-template class ALMGeometrySolver<3>;
+template class GeometrySolverBase<3>;
 
 }  // namespace aaadmm

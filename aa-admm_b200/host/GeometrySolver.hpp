@@ -6,6 +6,8 @@
 //   ALMGeometrySolver<3>                 Geometry/ALMGeometrySolver.h:52-287: add_hard_constraint,
 //                                        add_soft_constraint, add_closeness, add_*laplacian, setup_ADMM,
 //                                        solve_ADMM, get_solution, function_values_, elapsed_time_
+//   GeometrySolver<3>                    Geometry/GeometrySolver.h:52-267: the older variant with the same
+//                                        interface (soft rows inside z/u, swap-back on a growing residual)
 // Eigen's Matrix3X is replaced by aaadmm::Matrix3X (3 x n, column-major, data()/cols()/size()).
 // User subclasses of Constraint with their own project_impl cannot run on the GPU and are rejected
 // by setup_ADMM (returns false), as SURVEY 8b prescribes.
@@ -114,14 +116,15 @@ public:
 
 enum SPDSolverType { LDLT_SOLVER, LLT_SOLVER, CG_SOLVER };
 
+// Both solver classes of the reference share their interface; the variant picks the setup matrices
+// and the device loop (AAADMM_GEO_ALM / AAADMM_GEO_GS).
 template <unsigned int N>
-class ALMGeometrySolver {
+class GeometrySolverBase {
 public:
     typedef Matrix3X MatrixNX;
-    ALMGeometrySolver();
-    ~ALMGeometrySolver();
-    ALMGeometrySolver(const ALMGeometrySolver &) = delete;
-    ALMGeometrySolver &operator=(const ALMGeometrySolver &) = delete;
+    virtual ~GeometrySolverBase();
+    GeometrySolverBase(const GeometrySolverBase &) = delete;
+    GeometrySolverBase &operator=(const GeometrySolverBase &) = delete;
 
     void add_hard_constraint(Constraint<N> *c) { hard_constraints_.push_back(c); }
     void add_soft_constraint(Constraint<N> *c) { soft_constraints_.push_back(c); }
@@ -142,6 +145,8 @@ public:
     aaadmm_step_result last_result;
 
 protected:
+    explicit GeometrySolverBase(int variant);
+    int variant_;
     std::vector<Constraint<N> *> soft_constraints_, hard_constraints_;
     double penalty_parameter_;
     int n_points_ = 0;
@@ -155,6 +160,18 @@ protected:
     LdltFactor factor_;
     aaadmm_ldlt *ldlt_ = nullptr;
     aaadmm_geo *geo_ = nullptr;
+};
+
+template <unsigned int N>
+class ALMGeometrySolver : public GeometrySolverBase<N> {
+public:
+    ALMGeometrySolver() : GeometrySolverBase<N>(AAADMM_GEO_ALM) {}
+};
+
+template <unsigned int N>
+class GeometrySolver : public GeometrySolverBase<N> {
+public:
+    GeometrySolver() : GeometrySolverBase<N>(AAADMM_GEO_GS) {}
 };
 
 }  // namespace aaadmm

@@ -260,11 +260,17 @@ int aaadmm_host_tet_constants(const double *rest12, double youngs, double poisso
 #include "GeometrySolver.hpp"
 namespace {
 struct GeoHandle {
-    aaadmm::ALMGeometrySolver<3> solver;
+    aaadmm::GeometrySolverBase<3> &solver;
+    explicit GeoHandle(aaadmm::GeometrySolverBase<3> *s) : solver(*s), owner(s) {}
+    std::unique_ptr<aaadmm::GeometrySolverBase<3>> owner;
 };
 }  // namespace
 extern "C" {
-void *aaadmm_host_geo_new(void) { return new GeoHandle(); }
+void *aaadmm_host_geo_new(void) { return new GeoHandle(new aaadmm::ALMGeometrySolver<3>()); }
+void *aaadmm_host_geo_new_variant(int variant) {
+    if (variant == AAADMM_GEO_GS) return new GeoHandle(new aaadmm::GeometrySolver<3>());
+    return new GeoHandle(new aaadmm::ALMGeometrySolver<3>());
+}
 void aaadmm_host_geo_free(void *h) { delete static_cast<GeoHandle *>(h); }
 int aaadmm_host_geo_add_plane(void *h, const int *idx, int k, double weight) {
     static_cast<GeoHandle *>(h)->solver.add_hard_constraint(new aaadmm::PlaneConstraint(std::vector<int>(idx, idx + k), weight));

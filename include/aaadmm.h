@@ -158,6 +158,15 @@ typedef struct aaadmm_geo aaadmm_geo;
 #define AAADMM_GEO_EDGE 1  /* SUBTRACT_FIRST, 1 output column       */
 #define AAADMM_GEO_ANGLE 2 /* SUBTRACT_FIRST, 2 output columns      */
 
+/* Solver variant. ALM: ALMGeometrySolver<3> (soft rows outside z/u, residual |Dx-z|^2 + |Dx-Dx_prev|^2,
+ * reject and re-run, solution = default_x). GS: the older GeometrySolver<3>
+ * (Geometry/GeometrySolver.h:85-263): the soft closest-point rows are part of z/u (columns n_zcols ..
+ * n_zcols+n_soft, unweighted, combined as a v + (1-a) closest(v), a = rho/(w+rho)), dt_* then also
+ * carries those rows, the residual is |Dx-z|, a growing residual swaps back to the un-accelerated
+ * iterate, every turn counts as an iteration and the solution is current_x. */
+#define AAADMM_GEO_ALM 0
+#define AAADMM_GEO_GS 1
+
 typedef struct {
     int n_points;
     int n_hard;             /* hard constraints in insertion order (their output columns follow it)  */
@@ -177,6 +186,8 @@ typedef struct {
     int n_ref_tris;
     const int *ref_tris;    /* 3 per triangle                                                        */
     const double *rhs_fixed; /* 3 per point: L^T * regularisation targets                            */
+    int variant;            /* AAADMM_GEO_ALM or AAADMM_GEO_GS                                        */
+    double rho;             /* penalty parameter (GS: the soft combination needs it; dt_val has it folded in) */
 } aaadmm_geo_desc;
 
 /* `factor` (nrhs = 3, n = n_points) is borrowed. */

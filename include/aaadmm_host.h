@@ -59,6 +59,8 @@ int aaadmm_host_tet_constants(const double *rest12, double youngs, double poisso
  * (Geometry/Constraint.h): planes/edges/angles are hard constraints, the reference-surface closest-point
  * constraint is soft, Laplacian / closeness rows are regularisation. */
 void *aaadmm_host_geo_new(void);
+/* variant: AAADMM_GEO_ALM (ALMGeometrySolver<3>) or AAADMM_GEO_GS (GeometrySolver<3>, Geometry/GeometrySolver.h:52-267) */
+void *aaadmm_host_geo_new_variant(int variant);
 void aaadmm_host_geo_free(void *h);
 int aaadmm_host_geo_add_plane(void *h, const int *idx, int k, double weight);
 int aaadmm_host_geo_add_edge(void *h, int i0, int i1, double weight, double len);
