@@ -43,7 +43,7 @@ def build_cuda(force=False, verbose=False):
     objdir = os.path.join(PKG, "build")
     os.makedirs(objdir, exist_ok=True)
     base = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-            "-Xcompiler", "-fPIC"]
+            "-ccbin", GXX, "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp"]
     if verbose:
         base += ["-Xptxas", "-v"]
     objs, procs = [], []
@@ -59,7 +59,7 @@ def build_cuda(force=False, verbose=False):
             raise RuntimeError("build failed: " + " ".join(cmd))
         if verbose:
             print(out)
-    _run(["nvcc", "-shared", "-o", LIB_CUDA] + objs)
+    _run(["nvcc", "-ccbin", GXX, "-shared", "-Xcompiler", "-fopenmp", "-o", LIB_CUDA] + objs)
     return LIB_CUDA
 
 

@@ -619,7 +619,7 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
         AAADMM_CUDA_OK(cudaMemcpyAsync(Gx, s->xs, sizeof(double) * 3 * NF, cudaMemcpyDeviceToDevice, st));
         // default_(u,x) = curr_(u,x); accelerator->init(curr_u, curr_x)
         AAADMM_CUDA_OK(cudaMemcpyAsync(s->Ubuf, s->Gbuf, sizeof(double) * s->Nt, cudaMemcpyDeviceToDevice, st));
-        L += 6 + 4 * f->n_levels;
+        L += 6 + f->n_launches;
     }
     // ---- the loop: one graph launch (WHILE node, device-side break), or plain launches when profiling ----
     cudaGraphConditionalHandle cond_handle = 0;
@@ -650,7 +650,7 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
         prof->begin(2);
         if (ldlt_dev_apply_permuted(f, s->xs, st, &s->st->done)) return -1;
         prof->end();
-        L += 1 + 4 * f->n_levels;
+        L += 1 + f->n_launches;
         prof->begin(3);
         if (accel)
             launch_update_u_hard(MODE_ITER, gt, st, A, s->xs, Ux, s->z, Uu, Gu, s->st, s->partials, s->hist_prim,
@@ -701,7 +701,7 @@ static int run_xzu(aaadmm_tetscene *s, const aaadmm_step_opts *o, int iters, boo
         launch_contrib(gt, st, A, zz, u, s->contrib, s->st, when);
         launch_rhs_gather(st, NF, s->inc_ptr, s->inc, s->contrib, s->bconst, f->iperm, f->W, s->st, when);
         if (ldlt_dev_apply_permuted(f, xout, st, when ? &s->st->skip_redo : &s->st->done)) return -1;
-        L += 2 + 4 * f->n_levels;
+        L += 2 + f->n_launches;
         return 0;
     };
     // ---- frame init + warm start (Solver.cpp:78-117) ----
@@ -1282,7 +1282,7 @@ static int geo_enqueue_turn(aaadmm_geo *g, int m, int &L) {
                    g->soft_weight, g->cp, f->iperm, f->W, g->st);
     if (ldlt_dev_apply_permuted(f, nx, st, &g->st->done)) return -1;
     launch_geo_u_resid(st, C, nx, cu, g->z, g->prev_dx, nu, g->st, g->partials, g->hist, accel ? 1 : 0);
-    L += 4 + 4 * f->n_levels;
+    L += 4 + f->n_launches;
     if (accel) {
         const int gs = stream_grid(4);
         if (launch_aa_pass1(m, gs, st, g->Nbuf, nullptr, nullptr, g->Ubuf, g->dF, g->dG, g->N, g->N, g->st, g->partials, g->Dbuf))
@@ -1307,7 +1307,7 @@ static int gs_enqueue_x_u(aaadmm_geo *g, const GeoConstraints &C, const GeoSoft 
     if (ldlt_dev_apply_permuted(f, dx, st, &g->st->done)) return -1;
     launch_gs_dx(st, C, S, g->zc, dx, g->prev_dx, g->st, 0);
     launch_gs_u(st, cu, g->prev_dx, g->z, du, NU, g->st);
-    L += 3 + 4 * f->n_levels;
+    L += 3 + f->n_launches;
     return 0;
 }
 static int gs_enqueue_warmup(aaadmm_geo *g, int &L) {

@@ -1,17 +1,19 @@
-// Level-scheduled block triangular solves for a sparse LDL^T factor resident in HBM.
+// Multifrontal triangular solves for a sparse LDL^T factor resident in HBM.
 //
-// Layout (all built once at setup from the CSC factor the host hands over):
-//   * columns are grouped into BLOCKS = maximal elimination-tree chains j -> j+1 whose column
-//     patterns nest (fundamental supernodes; short non-nesting chains are merged too);
-//   * the unit-lower DIAGONAL block of every group is inverted once (FP64, on the GPU) and kept
-//     dense, row-major (forward) and transposed (backward): inside a group the solve is a dense
-//     GEMV with no sequential dependency;
-//   * the OFF-BLOCK entries are kept twice: CSR (forward sweep, one warp gathers one row: no
-//     atomics, fixed summation order) and CSC (backward sweep, one warp per column);
-//   * groups are scheduled by their level in the group dependency DAG: all groups of one level
-//     run in one launch.  Per level: off-block kernel, then diagonal-block kernel.
-// Right-hand sides are interleaved (n x NR, NR = 3 for the xyz-Kronecker system A = Ahat (x) I3):
-// every factor entry is read once per apply and used NR times.
+// The factor's columns are grouped into FRONTS (supernodes: elimination-tree chains j -> j+1; the k
+// rows below the chain's last column contain the rows of all its columns). Per front the setup
+// builds ONE dense column-major matrix
+//        M = [ Linv ]   ns x ns   inverse of the unit-lower diagonal block
+//            [  Q   ]   k  x ns   Q = L_below * Linv
+// so that both sweeps are plain dense products with no dependency inside a front:
+//   forward   [ y ; u_own ] = M w          w = rhs - (updates of the children that land in the front's columns)
+//             u = u_own + (updates of the children that land in the k rows below)      -> handed to the parent
+//   backward  x = M^T [ D^-1 y ; -x(rows below) ]
+// Fronts are scheduled by their height in the supernode tree: one launch per level and sweep,
+// 2 * levels launches per apply. No indices are streamed (8 bytes per factor entry and sweep), every
+// load of M is a coalesced 256-byte segment, the summation order is fixed (no atomics): results are
+// bit-reproducible. Right-hand sides are interleaved (n x NR, NR = 3 for A = Ahat (x) I3): every
+// factor entry is read once per sweep and used NR times.
 #include "ldlt_apply.cuh"
 
 #include <algorithm>
@@ -22,213 +24,263 @@ namespace aaadmm {
 
 namespace {
 
-constexpr int WARPS_PER_CTA = 8;
+constexpr int CTA = 256;
+constexpr int FCH = 2048;  // columns of w staged in shared memory at a time (forward)
+constexpr int BCH = 2048;  // rows of v staged in shared memory at a time (backward)
 
-template <int NR>
-__device__ __forceinline__ void warp_sum(double (&a)[NR]) {
+// Child updates that add into one front row: up to 4 slots inline (-1 = none), the rest (rare) in a CSR.
+__device__ __forceinline__ SweepTask load_task(const SweepTask *t) {
+    union {
+        SweepTask s;
+        int4 v[4];
+    } u;
+    const int4 *p = reinterpret_cast<const int4 *>(t);
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a[r] += __shfl_xor_sync(0xffffffffu, a[r], o);
-    }
+    for (int i = 0; i < 4; ++i) u.v[i] = __ldg(p + i);
+    return u.s;
 }
 
-// Work distribution shared by the four sweep kernels: the first n_long CTAs take one LONG row
-// each (all 8 warps stride over it, fixed-shape combine through shared memory); the remaining
-// CTAs take 8 SHORT rows each, one warp per row. Either way one row is summed by one fixed set
-// of lanes in a fixed order: the result is deterministic and needs no atomics.
-struct RowLists {
-    const int *long_rows;   // one CTA per row
-    int n_long;
-    const int *short_rows;  // one warp per row
-    int n_short;
-    const int *tiny_rows;   // 8 lanes per row (rows of <= TINY_ROW entries: the leaf levels)
-    int n_tiny;
+struct Gather {
+    const int4 *ell;
+    const int64_t *ptr;  // null when no row has more than 4 contributions
+    const int *idx;
 };
-constexpr int TINY_LANES = 8;
-constexpr int TINY_PER_CTA = WARPS_PER_CTA * 32 / TINY_LANES;
 
-__host__ __device__ __forceinline__ int short_ctas(const RowLists &L) { return (L.n_short + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
-
-// cls: 0 long, 1 short, 2 tiny. Inactive lanes of a tiny CTA keep running (their warp still shuffles).
 template <int NR>
-__device__ __forceinline__ bool pick_row(const RowLists &L, int &row, int &tid, int &nthr, int &cls) {
-    const int b = (int)blockIdx.x;
-    if (b < L.n_long) {
-        cls = 0;
-        row = L.long_rows[b];
-        tid = threadIdx.x;
-        nthr = WARPS_PER_CTA * 32;
-        return true;
+__device__ __forceinline__ void gather_add(const Gather &G, int64_t grow, const double *U, double sign, double (&a)[NR]) {
+    const int4 e = __ldg(G.ell + grow);
+    const int s4[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (s4[i] >= 0) {
+            const size_t s = (size_t)s4[i] * NR;
+#pragma unroll
+            for (int q = 0; q < NR; ++q) a[q] += sign * U[s + q];
+        }
     }
-    const int ns = short_ctas(L);
-    if (b < L.n_long + ns) {
-        cls = 1;
-        const int wid = (b - L.n_long) * WARPS_PER_CTA + (threadIdx.x >> 5);
-        tid = threadIdx.x & 31;
-        nthr = 32;
-        if (wid >= L.n_short) return false;
-        row = L.short_rows[wid];
-        return true;
+    if (G.ptr) {
+        const int64_t g1 = G.ptr[grow + 1];
+        for (int64_t g = G.ptr[grow]; g < g1; ++g) {
+            const size_t s = (size_t)G.idx[g] * NR;
+#pragma unroll
+            for (int q = 0; q < NR; ++q) a[q] += sign * U[s + q];
+        }
     }
-    cls = 2;
-    const int gid = (b - L.n_long - ns) * TINY_PER_CTA + (threadIdx.x / TINY_LANES);
-    tid = threadIdx.x & (TINY_LANES - 1);
-    nthr = TINY_LANES;
-    if (gid >= L.n_tiny) return false;
-    row = L.tiny_rows[gid];
-    return true;
 }
 
-// Reduces acc over the lanes that worked on the row; returns true in the one thread holding it.
+// ---- forward: one CTA = RT rows of one front, the columns interleaved over CS = 256 / RT slices ----
+// RT = 256 .. 8 per task (narrow fronts want many rows per CTA, wide ones many slices).
+// The first FPRE loads of M are issued before w is gathered (they do not depend on it).
+constexpr int FPRE = 16, FUB = 8;
 template <int NR>
-__device__ __forceinline__ bool row_reduce(int cls, bool active, double (&acc)[NR]) {
-    if (cls == 2) {
+__global__ void __launch_bounds__(CTA)
+k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
+            Gather G, const double *__restrict__ W, const double *__restrict__ dinv, double *__restrict__ Yd, double *U,
+            const int *skip, int ws_cap) {
+    if (skip && *skip) return;
+    extern __shared__ double sm[];
+    double *ws = sm;                          // [ws_cap][NR]
+    double *part = sm + (size_t)ws_cap * NR;  // [CS][RT][NR]
+    const SweepTask F = load_task(tasks + blockIdx.x);
+    const int lrt = F.shape;
+    const int RT = 1 << lrt, CS = CTA >> lrt;
+    const int r0 = F.start, m = F.ns + F.k;
+    const int lr = threadIdx.x & (RT - 1), cs = threadIdx.x >> lrt;
+    const int row = r0 + lr;
+    const int jneed = min(F.ns, r0 + RT);  // rows of the diagonal block see columns <= row only
+    const int jend = row < F.ns ? row + 1 : (row < m ? F.ns : 0);
+    const double *Mp = M + F.m_off + row;
+    const size_t ld = (size_t)F.ld;
+    double acc[NR], pass[NR];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
+    for (int q = 0; q < NR; ++q) acc[q] = pass[q] = 0.0;
+    // the children's updates of a row below the front are passed on to the parent with the front's own
+    if (cs == 0 && row >= F.ns && row < m) gather_add<NR>(G, F.g_off + row, U, 1.0, pass);
+    double pv[FPRE];
+    {
+        const int je0 = min(jend, ws_cap);
 #pragma unroll
-            for (int o = TINY_LANES / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+        for (int u = 0; u < FPRE; ++u) {
+            const int j = cs + u * CS;
+            pv[u] = j < je0 ? __ldg(Mp + (size_t)j * ld) : 0.0;
         }
-        return active && (threadIdx.x & (TINY_LANES - 1)) == 0;
     }
-    warp_sum<NR>(acc);
-    if (cls == 1) return active && (threadIdx.x & 31) == 0;
-    __shared__ double s_part[WARPS_PER_CTA][NR];
-    const int warp = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) {
+    for (int jc = 0; jc < jneed; jc += ws_cap) {
+        const int jn = min(jneed - jc, ws_cap);
+        if (jc > 0) __syncthreads();
+        // w_j = rhs_j - sum of the child updates that land on column j
+        for (int j = threadIdx.x; j < jn; j += CTA) {
+            const int col = jc + j;
+            double a[NR];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) s_part[warp][r] = acc[r];
+            for (int q = 0; q < NR; ++q) a[q] = W[(size_t)(F.first + col) * NR + q];
+            gather_add<NR>(G, F.g_off + col, U, -1.0, a);
+#pragma unroll
+            for (int q = 0; q < NR; ++q) ws[j * NR + q] = a[q];
+        }
+        __syncthreads();
+        const int je = min(jend, jc + jn);
+        int j = jc + cs;
+        if (jc == 0) {
+#pragma unroll
+            for (int u = 0; u < FPRE; ++u) {
+                const int jj = cs + u * CS;
+                if (jj < je) {
+#pragma unroll
+                    for (int q = 0; q < NR; ++q) acc[q] += pv[u] * ws[jj * NR + q];
+                }
+            }
+            j += FPRE * CS;
+        }
+        for (; j < je; j += FUB * CS) {
+            double v[FUB];
+#pragma unroll
+            for (int u = 0; u < FUB; ++u) {
+                const int jj = j + u * CS;
+                v[u] = jj < je ? __ldg(Mp + (size_t)jj * ld) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < FUB; ++u) {
+                const int jj = min(j + u * CS, je - 1) - jc;
+#pragma unroll
+                for (int q = 0; q < NR; ++q) acc[q] += v[u] * ws[jj * NR + q];
+            }
+        }
     }
+#pragma unroll
+    for (int q = 0; q < NR; ++q) part[(cs * RT + lr) * NR + q] = acc[q];
     __syncthreads();
-    if (threadIdx.x != 0) return false;
+    if (cs != 0 || row >= m) return;
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        double x = 0.0;
+    for (int q = 0; q < NR; ++q) acc[q] = 0.0;
+    for (int c = 0; c < CS; ++c) {
 #pragma unroll
-        for (int w = 0; w < WARPS_PER_CTA; ++w) x += s_part[w][r];
-        acc[r] = x;
+        for (int q = 0; q < NR; ++q) acc[q] += part[(c * RT + lr) * NR + q];
     }
-    return true;
-}
-
-// W[row] -= sum_{off-block cols c} L(row,c) * Y[c]
-template <int NR>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_fwd_off(RowLists L, const int64_t *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val,
-          const double *__restrict__ Y, double *__restrict__ W, const int *skip) {
-    if (skip && *skip) return;
-    int row = 0, tid, nthr, cls;
-    const bool active = pick_row<NR>(L, row, tid, nthr, cls);
-    double acc[NR];
+    if (row < F.ns) {
+        const double di = dinv[F.first + row];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) acc[r] = 0.0;
-    if (active) {
-        const int64_t p0 = ptr[row], p1 = ptr[row + 1];
-#pragma unroll 4
-        for (int64_t p = p0 + tid; p < p1; p += nthr) {
-            const int c = __ldg(col + p);
-            const double v = __ldg(val + p);
+        for (int q = 0; q < NR; ++q) Yd[(size_t)(F.first + row) * NR + q] = acc[q] * di;
+    } else {
+        const size_t o = (size_t)(F.u_off + row - F.ns) * NR;
 #pragma unroll
-            for (int r = 0; r < NR; ++r) acc[r] += v * Y[(size_t)c * NR + r];
-        }
-    }
-    if (row_reduce<NR>(cls, active, acc)) {
-#pragma unroll
-        for (int r = 0; r < NR; ++r) W[(size_t)row * NR + r] -= acc[r];
+        for (int q = 0; q < NR; ++q) U[o + q] = acc[q] + pass[q];
     }
 }
 
-// Y[row] = sum_{j<=i} Linv(i,j) W[first+j]     (dense inverse of the unit-lower diagonal block)
-template <int NR>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_fwd_diag(RowLists L, const int *__restrict__ blk_of, const int *__restrict__ blk_first,
-           const int64_t *__restrict__ linv_off, const double *__restrict__ Linv, const double *__restrict__ W,
-           double *__restrict__ Y, const int *skip) {
+// ---- backward: one CTA = 8 * CW columns of one front, one warp per CW columns, lanes along the rows ----
+// 16 loads of M per thread are in flight; the first 16 are issued before v is staged.
+template <int NR, int CW>
+__global__ void __launch_bounds__(CTA)
+k_bwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
+            const int *__restrict__ rows, const double *__restrict__ Yd, double *X, const int *__restrict__ perm,
+            double *__restrict__ x_out, const int *skip, int v_cap) {
     if (skip && *skip) return;
-    int row = 0, tid, nthr, cls;
-    const bool active = pick_row<NR>(L, row, tid, nthr, cls);
-    double acc[NR];
+    constexpr int UB = 16 / CW;     // rows per lane and batch
+    extern __shared__ double sm[];  // v[v_cap][NR]
+    const SweepTask F = load_task(tasks + blockIdx.x);
+    const int c0 = F.start, m = F.ns + F.k;
+    const int cend = min(F.ns, c0 + F.shape);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool single = (m - c0) <= v_cap;  // v fits at once: staged once, several column passes allowed
+    const double *Mf = M + F.m_off;
+    for (int jb0 = c0; jb0 < cend; jb0 += 8 * CW) {
+        const int jb = jb0 + warp * CW;
+        const bool live = jb < cend;
+        const bool pre = jb0 == c0;
+        const double *Mc[CW];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) acc[r] = 0.0;
-    if (active) {
-        const int b = blk_of[row];
-        const int first = blk_first[b];
-        const int ns = blk_first[b + 1] - first;
-        const int i = row - first;
-        const double *Lrow = Linv + linv_off[b] + (size_t)i * ns;
-#pragma unroll 4
-        for (int j = tid; j <= i; j += nthr) {
-            const double v = __ldg(Lrow + j);
+        for (int c = 0; c < CW; ++c) Mc[c] = Mf + (size_t)min(jb + c, F.ns - 1) * F.ld;
+        double acc[CW][NR];
 #pragma unroll
-            for (int r = 0; r < NR; ++r) acc[r] += v * W[(size_t)(first + j) * NR + r];
+        for (int c = 0; c < CW; ++c)
+#pragma unroll
+            for (int q = 0; q < NR; ++q) acc[c][q] = 0.0;
+        // column j has no entries above row j: start at the 128-byte line that holds the diagonal
+        const int rs = max(c0, jb & ~15);
+        double pa[UB][CW];
+        if (pre) {
+            const int re0 = min(m, c0 + v_cap);
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int r = rs + lane + 32 * u;
+#pragma unroll
+                for (int c = 0; c < CW; ++c) pa[u][c] = (live && r < re0) ? __ldg(Mc[c] + r) : 0.0;
+            }
         }
-    }
-    if (row_reduce<NR>(cls, active, acc)) {
+        for (int rc = c0; rc < m; rc += v_cap) {
+            const int re = min(m, rc + v_cap);
+            if (!(single && !pre)) {
+                if (rc > c0) __syncthreads();
+                // v = [ D^-1 y of the front's columns ; -x of the rows below ]
+                for (int r = rc + threadIdx.x; r < re; r += CTA) {
+                    if (r < F.ns) {
 #pragma unroll
-        for (int r = 0; r < NR; ++r) Y[(size_t)row * NR + r] = acc[r];
-    }
-}
-
-// W[j] = Y[j]/D[j] - sum_{off-block rows i} L(i,j) X[i]
-template <int NR>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_bwd_off(RowLists L, const int64_t *__restrict__ ptr, const int *__restrict__ rowidx, const double *__restrict__ val,
-          const double *__restrict__ dinv, const double *__restrict__ Y, const double *__restrict__ X,
-          double *__restrict__ W, const int *skip) {
-    if (skip && *skip) return;
-    int j = 0, tid, nthr, cls;
-    const bool active = pick_row<NR>(L, j, tid, nthr, cls);
-    double acc[NR];
+                        for (int q = 0; q < NR; ++q) sm[(r - rc) * NR + q] = Yd[(size_t)(F.first + r) * NR + q];
+                    } else {
+                        const size_t i = (size_t)__ldg(rows + F.g_off + r - F.ns) * NR;
 #pragma unroll
-    for (int r = 0; r < NR; ++r) acc[r] = 0.0;
-    if (active) {
-        const int64_t p0 = ptr[j], p1 = ptr[j + 1];
-#pragma unroll 4
-        for (int64_t p = p0 + tid; p < p1; p += nthr) {
-            const int i = __ldg(rowidx + p);
-            const double v = __ldg(val + p);
+                        for (int q = 0; q < NR; ++q) sm[(r - rc) * NR + q] = -X[i + q];
+                    }
+                }
+                __syncthreads();
+            }
+            if (!live) continue;
+            int r = max(rc, rs) + lane;
+            if (pre && rc == c0) {
 #pragma unroll
-            for (int r = 0; r < NR; ++r) acc[r] += v * X[(size_t)i * NR + r];
+                for (int u = 0; u < UB; ++u) {
+                    const int rr = rs + lane + 32 * u;
+                    if (rr < re) {
+#pragma unroll
+                        for (int q = 0; q < NR; ++q) {
+                            const double vv = sm[(rr - rc) * NR + q];
+#pragma unroll
+                            for (int c = 0; c < CW; ++c) acc[c][q] += pa[u][c] * vv;
+                        }
+                    }
+                }
+                r = rs + lane + 32 * UB;
+            }
+            for (; r < re; r += 32 * UB) {
+                double a[UB][CW];
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int rr = r + 32 * u;
+#pragma unroll
+                    for (int c = 0; c < CW; ++c) a[u][c] = rr < re ? __ldg(Mc[c] + rr) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int rr = min(r + 32 * u, re - 1) - rc;
+#pragma unroll
+                    for (int q = 0; q < NR; ++q) {
+                        const double vv = sm[rr * NR + q];
+#pragma unroll
+                        for (int c = 0; c < CW; ++c) acc[c][q] += a[u][c] * vv;
+                    }
+                }
+            }
         }
-    }
-    if (row_reduce<NR>(cls, active, acc)) {
-        const double di = dinv[j];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) W[(size_t)j * NR + r] = Y[(size_t)j * NR + r] * di - acc[r];
-    }
-}
-
-// X[row] = sum_{j>=i} LinvT(i,j) W[first+j]; also scatter to the caller's ordering.
-template <int NR>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_bwd_diag(RowLists L, const int *__restrict__ blk_of, const int *__restrict__ blk_first,
-           const int64_t *__restrict__ linv_off, const double *__restrict__ LinvT, const double *__restrict__ W,
-           double *__restrict__ X, const int *__restrict__ perm, double *__restrict__ x_out, const int *skip) {
-    if (skip && *skip) return;
-    int row = 0, tid, nthr, cls;
-    const bool active = pick_row<NR>(L, row, tid, nthr, cls);
-    double acc[NR];
+        for (int c = 0; c < CW; ++c)
 #pragma unroll
-    for (int r = 0; r < NR; ++r) acc[r] = 0.0;
-    if (active) {
-        const int b = blk_of[row];
-        const int first = blk_first[b];
-        const int ns = blk_first[b + 1] - first;
-        const int i = row - first;
-        const double *Lrow = LinvT + linv_off[b] + (size_t)i * ns;
-#pragma unroll 4
-        for (int j = i + tid; j < ns; j += nthr) {
-            const double v = __ldg(Lrow + j);
+            for (int q = 0; q < NR; ++q)
 #pragma unroll
-            for (int r = 0; r < NR; ++r) acc[r] += v * W[(size_t)(first + j) * NR + r];
-        }
-    }
-    if (row_reduce<NR>(cls, active, acc)) {
-        const int o = perm[row];
+                for (int o = 16; o > 0; o >>= 1) acc[c][q] += __shfl_xor_sync(0xffffffffu, acc[c][q], o);
+        if (lane == 0 && live) {
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            X[(size_t)row * NR + r] = acc[r];
-            x_out[(size_t)o * NR + r] = acc[r];
+            for (int c = 0; c < CW; ++c) {
+                const int j = jb + c;
+                if (j < cend) {
+                    const int o = perm[F.first + j];
+#pragma unroll
+                    for (int q = 0; q < NR; ++q) {
+                        X[(size_t)(F.first + j) * NR + q] = acc[c][q];
+                        x_out[(size_t)o * NR + q] = acc[c][q];
+                    }
+                }
+            }
         }
     }
 }
@@ -243,44 +295,81 @@ __global__ void k_permute_in(const double *__restrict__ b, const int *__restrict
 }
 
 // ---- setup kernels ---------------------------------------------------------------------
-// X = T^-1 for every dense unit-lower diagonal block; one thread per column of X.
+// X = T^-1 for the unit-lower diagonal block of every front (T in A, X into M, both column-major with
+// the front's ld). One thread per row i of X, from X T = I: X(i,j) = -sum_{k=j+1..i} X(i,k) T(k,j), j < i.
+// M must be zero on entry.
 __global__ void __launch_bounds__(128)
-k_invert_unit_lower(const int2 *__restrict__ tasks, const int *__restrict__ blk_first,
-                    const int64_t *__restrict__ linv_off, const double *__restrict__ T, double *__restrict__ X) {
+k_invert_fronts(const int2 *__restrict__ tasks, const FrontDesc *__restrict__ fronts, const double *__restrict__ A,
+                double *__restrict__ M) {
     const int2 task = tasks[blockIdx.x];
-    const int b = task.x, col0 = task.y;
-    const int first = blk_first[b];
-    const int ns = blk_first[b + 1] - first;
-    const int j = col0 + threadIdx.x;
-    const bool active = j < ns;
-    const double *Tb = T + linv_off[b];
-    double *Xb = X + linv_off[b];
-    if (active) {
-        for (int i = 0; i < j; ++i) Xb[(size_t)i * ns + j] = 0.0;
-        Xb[(size_t)j * ns + j] = 1.0;
-    }
-    for (int i = col0 + 1; i < ns; ++i) {
+    const FrontDesc F = fronts[task.x];
+    const int i0 = task.y;
+    const int i = i0 + threadIdx.x;
+    const bool active = i < F.ns;
+    const double *T = A + F.m_off;
+    double *Xm = M + F.m_off;
+    if (active) Xm[(size_t)i * F.ld + i] = 1.0;
+    const int itop = min(i0 + 127, F.ns - 1);
+    for (int j = itop - 1; j >= 0; --j) {
+        if (!active || j >= i) continue;
         double s = 0.0;
-        if (active && i > j) {
-            const double *Trow = Tb + (size_t)i * ns;
-            for (int k = col0; k < i; ++k) s += Trow[k] * Xb[(size_t)k * ns + j];
-            Xb[(size_t)i * ns + j] = -s;
-        }
+        const double *Tj = T + (size_t)j * F.ld;
+        for (int k = j + 1; k <= i; ++k) s += Xm[(size_t)k * F.ld + i] * Tj[k];
+        Xm[(size_t)j * F.ld + i] = -s;
     }
 }
 
-__global__ void __launch_bounds__(128)
-k_transpose_blocks(const int2 *__restrict__ tasks, const int *__restrict__ blk_first,
-                   const int64_t *__restrict__ linv_off, const double *__restrict__ X, double *__restrict__ XT) {
-    const int2 task = tasks[blockIdx.x];
-    const int b = task.x, col0 = task.y;
-    const int first = blk_first[b];
-    const int ns = blk_first[b + 1] - first;
-    const int j = col0 + threadIdx.x;
-    if (j >= ns) return;
-    const double *Xb = X + linv_off[b];
-    double *Tb = XT + linv_off[b];
-    for (int i = 0; i < ns; ++i) Tb[(size_t)i * ns + j] = Xb[(size_t)j * ns + i];
+// Q = P * Linv: P = rows ns.. of A, Linv = rows 0..ns of M, Q -> rows ns.. of M. 64 x 64 tile per CTA,
+// 4 x 4 outputs per thread, 16-deep shared-memory stages.
+__global__ void __launch_bounds__(256)
+k_front_q(const int4 *__restrict__ tasks, const FrontDesc *__restrict__ fronts, const double *__restrict__ A,
+          double *__restrict__ M) {
+    __shared__ double Ps[16][64 + 1], Ls[16][64 + 1];
+    const int4 task = tasks[blockIdx.x];
+    const FrontDesc F = fronts[task.x];
+    const int rt = task.y, jt = task.z;  // first row of the tile (within the k rows) / first column
+    const double *P = A + F.m_off + F.ns;
+    const double *Li = M + F.m_off;
+    double *Q = M + F.m_off + F.ns;
+    const int tr = threadIdx.x & 15, tj = threadIdx.x >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    // Linv(t, j) = 0 for t < j: start at the tile's first column
+    for (int t0 = jt & ~15; t0 < F.ns; t0 += 16) {
+        // Ps[tt][r] = P(rt + r, t0 + tt); Ls[tt][j] = Linv(t0 + tt, jt + j)
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+            const int tt = e >> 6, r = e & 63;
+            Ps[tt][r] = (t0 + tt < F.ns && rt + r < F.k) ? P[(size_t)(t0 + tt) * F.ld + rt + r] : 0.0;
+        }
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+            const int j = e >> 4, tt = e & 15;
+            Ls[tt][j] = (t0 + tt < F.ns && jt + j < F.ns) ? Li[(size_t)(jt + j) * F.ld + t0 + tt] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int tt = 0; tt < 16; ++tt) {
+            double p[4], l[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) p[a] = Ps[tt][tr + 16 * a];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) l[b] = Ls[tt][tj + 16 * b];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] += p[a] * l[b];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int r = rt + tr + 16 * a, j = jt + tj + 16 * b;
+            if (r < F.k && j < F.ns) Q[(size_t)j * F.ld + r] = acc[a][b];
+        }
 }
 
 template <typename T>
@@ -291,28 +380,29 @@ int upload(T **dst, const std::vector<T> &src) {
     return 0;
 }
 
+int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 }  // namespace
 
 void ldlt_dev_destroy(LdltDev *f) {
     if (!f) return;
     cudaFree(f->perm);
     cudaFree(f->iperm);
-    cudaFree(f->blk_of);
-    cudaFree(f->blk_first);
-    cudaFree(f->linv_off);
-    cudaFree(f->Linv);
-    cudaFree(f->LinvT);
     cudaFree(f->dinv);
-    cudaFree(f->fr_ptr);
-    cudaFree(f->fr_col);
-    cudaFree(f->fr_val);
-    cudaFree(f->bc_ptr);
-    cudaFree(f->bc_row);
-    cudaFree(f->bc_val);
-    cudaFree(f->lev_rows);
+    cudaFree(f->fronts);
+    cudaFree(f->M);
+    cudaFree(f->rows);
+    cudaFree(f->gell);
+    cudaFree(f->gptr);
+    cudaFree(f->gidx);
+    cudaFree(f->tasks);
     cudaFree(f->W);
-    cudaFree(f->Y);
+    cudaFree(f->Yd);
     cudaFree(f->X);
+    cudaFree(f->U);
     delete f;
 }
 
@@ -327,11 +417,12 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     f->nrhs = nrhs;
     const int64_t nnz = Lp[n];
 
-    // ---- block partition: elimination-tree chains with nested patterns ----
+    // ---- fronts: elimination-tree chains. Column j joins the front of j-1 when j is the parent of j-1
+    // and either the patterns nest exactly (fundamental supernode) or the front is still small
+    // (relaxed: the rows below j-1 are a subset of those below j; the difference is stored as zeros).
     // tuning knobs (environment overrides are for experiments only)
-    auto env_int = [](const char *name, int dflt) { const char *v = getenv(name); return v ? atoi(v) : dflt; };
-    const int kSmall = env_int("AAADMM_KSMALL", 96), kCap = 6144;
-    std::vector<int> blk_of(n), blk_first;
+    const int kSmall = env_int("AAADMM_KSMALL", 96), kCap = env_int("AAADMM_KCAP", 6144);
+    std::vector<int> blk_of(std::max(n, 1)), blk_first;
     for (int j = 0; j < n; ++j) {
         bool join = false;
         if (j > 0) {
@@ -347,159 +438,307 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     blk_first.push_back(n);
     f->n_blocks = nb;
 
-    // ---- levels of the block DAG ----
-    std::vector<int> level(nb, 0);
+    std::vector<FrontDesc> fr(std::max(nb, 1));
+    std::vector<int> parent(nb, -1), level(nb, 0);
+    int64_t m_tot = 0, r_tot = 0, g_rows = 0;
+    int max_block = 0;
+    int64_t dense_entries = 0;
+    for (int b = 0; b < nb; ++b) {
+        FrontDesc &F = fr[b];
+        const int jl = blk_first[b + 1] - 1;
+        F.first = blk_first[b];
+        F.ns = blk_first[b + 1] - blk_first[b];
+        F.k = (int)(Lp[jl + 1] - Lp[jl]);
+        F.ld = (F.ns + F.k + 3) & ~3;
+        F.m_off = m_tot;
+        F.r_off = r_tot;
+        F.u_off = r_tot;
+        F.g_off = g_rows;
+        F.pad0 = F.pad1 = 0;
+        m_tot += ((int64_t)F.ld * F.ns + 31) & ~(int64_t)31;
+        r_tot += F.k;
+        g_rows += F.ns + F.k;
+        max_block = std::max(max_block, F.ns);
+        dense_entries += (int64_t)F.k * F.ns + (int64_t)F.ns * (F.ns + 1) / 2;
+        if (F.k > 0) parent[b] = blk_of[Li[Lp[jl]]];
+    }
     for (int b = 0; b < nb; ++b)
-        for (int j = blk_first[b]; j < blk_first[b + 1]; ++j)
-            for (int64_t p = Lp[j]; p < Lp[j + 1]; ++p) {
-                const int bi = blk_of[Li[p]];
-                if (bi != b && level[bi] < level[b] + 1) level[bi] = level[b] + 1;
-            }
+        if (parent[b] >= 0) level[parent[b]] = std::max(level[parent[b]], level[b] + 1);
     int nlev = 0;
     for (int b = 0; b < nb; ++b) nlev = std::max(nlev, level[b] + 1);
     f->n_levels = nlev;
+    f->n_launches = 2 * nlev;
 
-    // ---- split entries: dense diagonal blocks / off-block CSC + CSR ----
-    std::vector<int64_t> linv_off(nb + 1, 0);
-    int max_block = 0;
+    // ---- rows below each front, front matrices A = [T ; P] (column-major), child update slots ----
+    std::vector<int> rows((size_t)std::max<int64_t>(r_tot, 1));
     for (int b = 0; b < nb; ++b) {
-        const int64_t ns = blk_first[b + 1] - blk_first[b];
-        linv_off[b + 1] = linv_off[b] + ns * ns;
-        max_block = std::max<int>(max_block, (int)ns);
+        const int jl = blk_first[b + 1] - 1;
+        std::copy(Li + Lp[jl], Li + Lp[jl + 1], rows.begin() + fr[b].r_off);
     }
-    std::vector<double> Tdense((size_t)linv_off[nb], 0.0);
-    std::vector<int64_t> bc_ptr(n + 1, 0), fr_ptr(n + 1, 0);
-    for (int j = 0; j < n; ++j) {
-        const int b = blk_of[j];
-        const int first = blk_first[b];
-        const int64_t ns = blk_first[b + 1] - first;
-        double *Tb = Tdense.data() + linv_off[b];
-        Tb[(size_t)(j - first) * ns + (j - first)] = 1.0;
-        int64_t cnt = 0;
-        for (int64_t p = Lp[j]; p < Lp[j + 1]; ++p) {
-            const int i = Li[p];
-            if (blk_of[i] == b)
-                Tb[(size_t)(i - first) * ns + (j - first)] = Lx[p];
-            else {
-                ++cnt;
-                fr_ptr[i + 1]++;
-            }
-        }
-        bc_ptr[j + 1] = bc_ptr[j] + cnt;
+    std::vector<double> A;
+    try {
+        A.assign((size_t)std::max<int64_t>(m_tot, 1), 0.0);
+    } catch (const std::bad_alloc &) {
+        set_last_error("ldlt: out of host memory for the front matrices");
+        delete f;
+        return -1;
     }
-    for (int i = 0; i < n; ++i) fr_ptr[i + 1] += fr_ptr[i];
-    const int64_t noff = bc_ptr[n];
-    std::vector<int> bc_row((size_t)noff), fr_col((size_t)noff);
-    std::vector<double> bc_val((size_t)noff), fr_val((size_t)noff);
-    {
-        std::vector<int64_t> pos(fr_ptr.begin(), fr_ptr.end() - 1);
-        for (int j = 0; j < n; ++j) {
-            const int b = blk_of[j];
-            int64_t q = bc_ptr[j];
+    int bad = 0;
+    int64_t noff = 0;
+#pragma omp parallel for schedule(dynamic, 8) reduction(+ : bad, noff)
+    for (int b = 0; b < nb; ++b) {
+        const FrontDesc &F = fr[b];
+        double *Ab = A.data() + F.m_off;
+        const int *R = rows.data() + F.r_off;
+        for (int j = F.first; j < F.first + F.ns; ++j) {
+            double *col = Ab + (size_t)(j - F.first) * F.ld;
+            col[j - F.first] = 1.0;
+            int pos = 0;
             for (int64_t p = Lp[j]; p < Lp[j + 1]; ++p) {
                 const int i = Li[p];
-                if (blk_of[i] == b) continue;
-                bc_row[q] = i;
-                bc_val[q] = Lx[p];
-                ++q;
-                const int64_t r = pos[i]++;
-                fr_col[r] = j;  // columns arrive in ascending order: CSR rows are sorted
-                fr_val[r] = Lx[p];
+                if (i < F.first + F.ns) {
+                    col[i - F.first] = Lx[p];
+                    continue;
+                }
+                while (pos < F.k && R[pos] < i) ++pos;
+                if (pos >= F.k || R[pos] != i) {
+                    ++bad;
+                    break;
+                }
+                col[F.ns + pos] = Lx[p];
+                ++noff;
+            }
+        }
+    }
+    if (bad) {
+        set_last_error("ldlt: column patterns of the factor do not nest along the elimination tree");
+        delete f;
+        return -1;
+    }
+    // gather lists: for every front row (columns first, then the rows below) the slots of the children's
+    // update vectors that add into it, children in ascending order
+    std::vector<int64_t> gptr((size_t)g_rows + 1, 0);
+    auto target_row = [&](const FrontDesc &P, int i, int &pos) {  // row of global index i inside front P
+        if (i < P.first + P.ns) return i - P.first;
+        const int *R = rows.data() + P.r_off;
+        while (pos < P.k && R[pos] < i) ++pos;
+        return P.ns + pos;
+    };
+    for (int b = 0; b < nb; ++b) {
+        if (parent[b] < 0) continue;
+        const FrontDesc &C = fr[b], &P = fr[parent[b]];
+        int pos = 0;
+        for (int q = 0; q < C.k; ++q) gptr[P.g_off + target_row(P, rows[C.r_off + q], pos) + 1]++;
+    }
+    // the first 4 contributions of a row sit inline (ELL), the rest in the CSR
+    bool overflow = false;
+    for (int64_t i = 0; i < g_rows; ++i) {
+        const int64_t c = gptr[i + 1];
+        if (c > 4) overflow = true;
+        gptr[i + 1] = gptr[i] + std::max<int64_t>(c - 4, 0);
+    }
+    std::vector<int> gidx((size_t)std::max<int64_t>(gptr[g_rows], 1));
+    std::vector<int4> gell((size_t)std::max<int64_t>(g_rows, 1), make_int4(-1, -1, -1, -1));
+    {
+        std::vector<int64_t> fill(gptr.begin(), gptr.end() - 1);
+        for (int b = 0; b < nb; ++b) {
+            if (parent[b] < 0) continue;
+            const FrontDesc &C = fr[b], &P = fr[parent[b]];
+            int pos = 0;
+            for (int q = 0; q < C.k; ++q) {
+                const int64_t grow = P.g_off + target_row(P, rows[C.r_off + q], pos);
+                const int slot = (int)(C.u_off + q);
+                int4 &e = gell[grow];
+                if (e.x < 0) e.x = slot;
+                else if (e.y < 0) e.y = slot;
+                else if (e.z < 0) e.z = slot;
+                else if (e.w < 0) e.w = slot;
+                else gidx[fill[grow]++] = slot;
             }
         }
     }
 
-    // ---- level lists: per level and per sweep kernel, LONG rows (one CTA each) and SHORT rows ----
-    // kinds: 0 fwd_off (rows with off-block entries), 1 fwd_diag, 2 bwd_off, 3 bwd_diag
-    const int64_t kLong = env_int("AAADMM_KLONG", 1024), kTiny = env_int("AAADMM_KTINY", 64);
-    auto cls_of = [&](int64_t len) { return len > kLong ? 0 : (len > kTiny ? 1 : 2); };
-    std::vector<std::vector<int>> lists((size_t)nlev * 12);
-    for (int j = 0; j < n; ++j) {
-        const int b = blk_of[j];
-        const int l = level[b];
-        const int i = j - blk_first[b], ns = blk_first[b + 1] - blk_first[b];
-        const int64_t fo = fr_ptr[j + 1] - fr_ptr[j], bo = bc_ptr[j + 1] - bc_ptr[j];
-        if (fo > 0) lists[(size_t)l * 12 + 0 + cls_of(fo)].push_back(j);
-        lists[(size_t)l * 12 + 3 + cls_of(i + 1)].push_back(j);
-        lists[(size_t)l * 12 + 6 + cls_of(bo)].push_back(j);
-        lists[(size_t)l * 12 + 9 + cls_of(ns - i)].push_back(j);
+    // ---- level schedule: tile shapes and task lists ----
+    // Forward: a CTA takes RT = 2^lrt rows of a front and splits the columns over 256 / RT slices: narrow
+    // fronts get tall tiles (long CTAs amortise their fixed latency), wide ones many slices. Backward: a
+    // CTA takes `ncols` columns, each warp CW of them at a time. Levels with few fronts are cut finer
+    // until the launch has at least min_ctas CTAs.
+    const int min_ctas = env_int("AAADMM_MIN_CTAS", 296);
+    const int tile_entries = env_int("AAADMM_TILE_ENTRIES", 32768);
+    std::vector<std::vector<int>> by_level(nlev);
+    for (int b = 0; b < nb; ++b) by_level[level[b]].push_back(b);
+    std::vector<SweepTask> tasks;
+    f->ftask_ptr.assign(nlev + 1, 0);
+    f->btask_ptr.assign(nlev + 1, 0);
+    f->fsmem.assign(nlev, 0);
+    f->bsmem.assign(nlev, 0);
+    std::vector<int> bcw(nlev, 4);
+    auto make_task = [&](int b, bool fwd, int start, int shape) {
+        const FrontDesc &F = fr[b];
+        SweepTask t;
+        t.m_off = F.m_off;
+        t.g_off = fwd ? F.g_off : F.r_off;
+        t.u_off = F.u_off;
+        t.first = F.first;
+        t.ns = F.ns;
+        t.k = F.k;
+        t.ld = F.ld;
+        t.start = start;
+        t.shape = shape;
+        t.pad0 = t.pad1 = 0;
+        return t;
+    };
+    auto ceil_log2 = [](int v) {
+        int l = 0;
+        while ((1 << l) < v) ++l;
+        return l;
+    };
+    std::vector<int> lrt(std::max(nb, 1), 8), bcols(std::max(nb, 1), 32);
+    for (int l = 0; l < nlev; ++l) {
+        std::vector<int> &v = by_level[l];
+        std::sort(v.begin(), v.end(), [&](int a, int b2) {
+            const int64_t wa = (int64_t)fr[a].ns * (fr[a].ns + fr[a].k), wb = (int64_t)fr[b2].ns * (fr[b2].ns + fr[b2].k);
+            return wa != wb ? wa > wb : a < b2;
+        });
+        int max_ns = 1, max_m = 1;
+        for (int b : v) {
+            const int ns = fr[b].ns;
+            lrt[b] = ns <= 128 ? 8 : (ns <= 256 ? 7 : (ns <= 512 ? 6 : (ns <= 1024 ? 5 : 4)));
+            max_ns = std::max(max_ns, ns);
+            max_m = std::max(max_m, ns + fr[b].k);
+        }
+        auto count_f = [&]() {
+            int64_t c = 0;
+            for (int b : v) c += (fr[b].ns + fr[b].k + (1 << lrt[b]) - 1) >> lrt[b];
+            return c;
+        };
+        for (int pass = 0; pass < 5 && count_f() < min_ctas; ++pass)
+            for (int b : v)
+                if (lrt[b] > 3 && fr[b].ns >= 4 * (CTA >> (lrt[b] - 1))) lrt[b]--;
+        const int v_cap = std::min(max_m, BCH);
+        int cap = 128;
+        auto set_cols = [&](int cw) {
+            int64_t c = 0;
+            for (int b : v) {
+                const int m = fr[b].ns + fr[b].k, g = 8 * cw;
+                int nc = g;
+                if (m <= v_cap) nc = std::max(g, std::min(cap, tile_entries / std::max(m, 1)) / g * g);
+                bcols[b] = nc;
+                c += (fr[b].ns + nc - 1) / nc;
+            }
+            return c;
+        };
+        while (set_cols(bcw[l]) < min_ctas) {
+            if (cap > 8 * bcw[l])
+                cap /= 2;
+            else if (bcw[l] > 1)
+                bcw[l] /= 2;
+            else
+                break;
+        }
+        f->fsmem[l] = std::min((max_ns + 31) & ~31, FCH);
+        f->bsmem[l] = v_cap;
     }
-    std::vector<int> lev_rows;
-    f->list_ptr.assign((size_t)nlev * 12 + 1, 0);
-    for (size_t k = 0; k < lists.size(); ++k) {
-        lev_rows.insert(lev_rows.end(), lists[k].begin(), lists[k].end());
-        f->list_ptr[k + 1] = (int)lev_rows.size();
+    for (int l = 0; l < nlev; ++l) {
+        for (int b : by_level[l]) {
+            const int m = fr[b].ns + fr[b].k;
+            for (int r0 = 0; r0 < m;) {
+                const int shape = std::min(lrt[b], std::max(3, ceil_log2(m - r0)));
+                tasks.push_back(make_task(b, true, r0, shape));
+                r0 += 1 << shape;
+            }
+        }
+        f->ftask_ptr[l + 1] = (int)tasks.size();
+    }
+    f->btask_base = (int)tasks.size();
+    for (int l = 0; l < nlev; ++l) {
+        for (int b : by_level[l])
+            for (int c0 = 0; c0 < fr[b].ns; c0 += bcols[b]) tasks.push_back(make_task(b, false, c0, bcols[b]));
+        f->btask_ptr[l + 1] = (int)tasks.size() - f->btask_base;
     }
 
-    std::vector<int> permv(perm, perm + n), iperm(n);
+    std::vector<int> permv(perm, perm + n), iperm(std::max(n, 1));
     for (int k = 0; k < n; ++k) iperm[perm[k]] = k;
-    std::vector<double> dinv(n);
+    std::vector<double> dinv(std::max(n, 1));
     for (int k = 0; k < n; ++k) dinv[k] = 1.0 / D[k];
 
     // ---- upload ----
+    double *dA = nullptr;
     int rc = 0;
     rc |= upload(&f->perm, permv);
     rc |= upload(&f->iperm, iperm);
-    rc |= upload(&f->blk_of, blk_of);
-    rc |= upload(&f->blk_first, blk_first);
-    rc |= upload(&f->linv_off, linv_off);
     rc |= upload(&f->dinv, dinv);
-    rc |= upload(&f->fr_ptr, fr_ptr);
-    rc |= upload(&f->fr_col, fr_col);
-    rc |= upload(&f->fr_val, fr_val);
-    rc |= upload(&f->bc_ptr, bc_ptr);
-    rc |= upload(&f->bc_row, bc_row);
-    rc |= upload(&f->bc_val, bc_val);
-    rc |= upload(&f->lev_rows, lev_rows);
-    rc |= upload(&f->LinvT, Tdense);  // holds T until the inversion below has run
-    if (rc) {
-        ldlt_dev_destroy(f);
-        return -1;
+    rc |= upload(&f->fronts, fr);
+    rc |= upload(&f->rows, rows);
+    rc |= upload(&f->gell, gell);
+    if (overflow) {
+        rc |= upload(&f->gptr, gptr);
+        rc |= upload(&f->gidx, gidx);
     }
-    const size_t dense_bytes = std::max<size_t>(Tdense.size(), 1) * sizeof(double);
+    rc |= upload(&f->tasks, tasks);
+    rc |= upload(&dA, A);
+    std::vector<double>().swap(A);
+    const size_t mat_bytes = (size_t)std::max<int64_t>(m_tot, 1) * sizeof(double);
     const size_t vec_bytes = std::max<size_t>((size_t)n * nrhs, 1) * sizeof(double);
-    if (cudaMalloc((void **)&f->Linv, dense_bytes) != cudaSuccess || cudaMalloc((void **)&f->W, vec_bytes) != cudaSuccess ||
-        cudaMalloc((void **)&f->Y, vec_bytes) != cudaSuccess || cudaMalloc((void **)&f->X, vec_bytes) != cudaSuccess) {
+    const size_t u_bytes = std::max<size_t>((size_t)r_tot * nrhs, 1) * sizeof(double);
+    if (rc || cudaMalloc((void **)&f->M, mat_bytes) != cudaSuccess || cudaMalloc((void **)&f->W, vec_bytes) != cudaSuccess ||
+        cudaMalloc((void **)&f->Yd, vec_bytes) != cudaSuccess || cudaMalloc((void **)&f->X, vec_bytes) != cudaSuccess ||
+        cudaMalloc((void **)&f->U, u_bytes) != cudaSuccess) {
         set_last_error("ldlt: cudaMalloc failed");
+        cudaFree(dA);
         ldlt_dev_destroy(f);
         return -1;
     }
-    // ---- invert the diagonal blocks on the device ----
+    // ---- Linv and Q on the device ----
     {
-        std::vector<int2> tasks;
+        std::vector<int2> inv_tasks;
+        std::vector<int4> q_tasks;
         for (int b = 0; b < nb; ++b) {
-            const int ns = blk_first[b + 1] - blk_first[b];
-            for (int c0 = 0; c0 < ns; c0 += 128) tasks.push_back(make_int2(b, c0));
+            for (int i0 = 0; i0 < fr[b].ns; i0 += 128) inv_tasks.push_back(make_int2(b, i0));
+            for (int rt = 0; rt < fr[b].k; rt += 64)
+                for (int jt = 0; jt < fr[b].ns; jt += 64) q_tasks.push_back(make_int4(b, rt, jt, 0));
         }
-        int2 *d_tasks = nullptr;
-        if (upload(&d_tasks, tasks)) {
+        int2 *d_inv = nullptr;
+        int4 *d_q = nullptr;
+        if (upload(&d_inv, inv_tasks) || upload(&d_q, q_tasks)) {
+            cudaFree(dA);
             ldlt_dev_destroy(f);
             return -1;
         }
-        const int nt = (int)tasks.size();
-        if (nt > 0) {
-            k_invert_unit_lower<<<nt, 128>>>(d_tasks, f->blk_first, f->linv_off, f->LinvT, f->Linv);
-            k_transpose_blocks<<<nt, 128>>>(d_tasks, f->blk_first, f->linv_off, f->Linv, f->LinvT);
-        }
+        cudaMemset(f->M, 0, mat_bytes);
+        if (!inv_tasks.empty()) k_invert_fronts<<<(int)inv_tasks.size(), 128>>>(d_inv, f->fronts, dA, f->M);
+        if (!q_tasks.empty()) k_front_q<<<(int)q_tasks.size(), 256>>>(d_q, f->fronts, dA, f->M);
         cudaError_t e = cudaDeviceSynchronize();
-        cudaFree(d_tasks);
+        cudaFree(d_inv);
+        cudaFree(d_q);
+        cudaFree(dA);
         if (e != cudaSuccess) {
-            set_last_error(std::string("ldlt: diagonal-block inversion failed: ") + cudaGetErrorString(e));
+            set_last_error(std::string("ldlt: front setup failed: ") + cudaGetErrorString(e));
             ldlt_dev_destroy(f);
             return -1;
         }
     }
+    const int max_smem = (FCH + CTA) * 3 * (int)sizeof(double);
+    cudaFuncSetAttribute(k_fwd_front<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(k_fwd_front<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(k_bwd_front<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(k_bwd_front<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(k_bwd_front<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(k_bwd_front<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(k_bwd_front<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(k_bwd_front<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    f->bcw = bcw;
     f->stats.n = n;
     f->stats.n_blocks = nb;
     f->stats.n_levels = nlev;
     f->stats.max_block = max_block;
     f->stats.nnz_L = nnz;
     f->stats.nnz_offdiag = noff;
-    f->stats.nnz_diag_dense = linv_off[nb];
-    // per apply: off-block values+indices once per sweep, the dense triangles once per sweep,
-    // the three n x nrhs vectors a few times
-    f->stats.bytes_per_solve = 2.0 * (12.0 * (double)noff + 8.0 * 0.5 * (double)linv_off[nb]) +
-                               8.0 * (double)n * nrhs * 8.0;
+    f->stats.nnz_diag_dense = nnz - noff;
+    f->stats.dense_entries = dense_entries;
+    // per apply: every factor value once per sweep (8 bytes, no indices); rhs in, y out and in, x out twice,
+    // the update vectors out and in
+    f->stats.bytes_per_solve = 2.0 * 8.0 * (double)nnz + 8.0 * nrhs * (5.0 * (double)n + 3.0 * (double)r_tot);
     *out = f;
     return 0;
 }
@@ -507,32 +746,35 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
 template <int NR>
 static int apply_impl(LdltDev *f, double *x_out, cudaStream_t s, const int *skip) {
     const int nlev = f->n_levels;
-    auto lists = [&](int l, int kind) {
-        RowLists L;
-        const int *p = &f->list_ptr[(size_t)l * 12 + 3 * kind];
-        L.long_rows = f->lev_rows + p[0];
-        L.n_long = p[1] - p[0];
-        L.short_rows = f->lev_rows + p[1];
-        L.n_short = p[2] - p[1];
-        L.tiny_rows = f->lev_rows + p[2];
-        L.n_tiny = p[3] - p[2];
-        return L;
-    };
-    auto grid = [](const RowLists &L) { return L.n_long + short_ctas(L) + (L.n_tiny + TINY_PER_CTA - 1) / TINY_PER_CTA; };
-    const int T = WARPS_PER_CTA * 32;
     for (int l = 0; l < nlev; ++l) {
-        RowLists a = lists(l, 0), b = lists(l, 1);
-        if (grid(a) > 0) k_fwd_off<NR><<<grid(a), T, 0, s>>>(a, f->fr_ptr, f->fr_col, f->fr_val, f->Y, f->W, skip);
-        if (grid(b) > 0)
-            k_fwd_diag<NR><<<grid(b), T, 0, s>>>(b, f->blk_of, f->blk_first, f->linv_off, f->Linv, f->W, f->Y, skip);
+        const int nt = f->ftask_ptr[l + 1] - f->ftask_ptr[l];
+        if (nt <= 0) continue;
+        const int ws_cap = f->fsmem[l];
+        const size_t smem = (size_t)(ws_cap + CTA) * NR * sizeof(double);
+        Gather G;
+        G.ell = f->gell;
+        G.ptr = f->gptr;
+        G.idx = f->gidx;
+        k_fwd_front<NR><<<nt, CTA, smem, s>>>(f->tasks + f->ftask_ptr[l], f->M, G, f->W, f->dinv, f->Yd, f->U, skip,
+                                             ws_cap);
     }
     for (int l = nlev - 1; l >= 0; --l) {
-        RowLists a = lists(l, 2), b = lists(l, 3);
-        if (grid(a) > 0)
-            k_bwd_off<NR><<<grid(a), T, 0, s>>>(a, f->bc_ptr, f->bc_row, f->bc_val, f->dinv, f->Y, f->X, f->W, skip);
-        if (grid(b) > 0)
-            k_bwd_diag<NR><<<grid(b), T, 0, s>>>(b, f->blk_of, f->blk_first, f->linv_off, f->LinvT, f->W, f->X,
-                                                 f->perm, x_out, skip);
+        const int nt = f->btask_ptr[l + 1] - f->btask_ptr[l];
+        if (nt <= 0) continue;
+        const int v_cap = f->bsmem[l];
+        const size_t smem = (size_t)v_cap * NR * sizeof(double);
+        const SweepTask *tk = f->tasks + f->btask_base + f->btask_ptr[l];
+        switch (f->bcw[l]) {
+        case 4:
+            k_bwd_front<NR, 4><<<nt, CTA, smem, s>>>(tk, f->M, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
+            break;
+        case 2:
+            k_bwd_front<NR, 2><<<nt, CTA, smem, s>>>(tk, f->M, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
+            break;
+        default:
+            k_bwd_front<NR, 1><<<nt, CTA, smem, s>>>(tk, f->M, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
+            break;
+        }
     }
     AAADMM_CUDA_OK(cudaGetLastError());
     return 0;

@@ -12,34 +12,53 @@ namespace aaadmm {
 struct LdltStats {
     int n = 0, n_blocks = 0, n_levels = 0, max_block = 0;
     int64_t nnz_L = 0, nnz_offdiag = 0, nnz_diag_dense = 0;
-    double bytes_per_solve = 0;  // algorithmic bytes one apply streams (both sweeps)
+    int64_t dense_entries = 0;   // entries of the front matrices one sweep streams (with padding zeros)
+    double bytes_per_solve = 0;  // algorithmic bytes of one apply: every factor value once per sweep + vectors
+};
+
+// One front = one supernode (elimination-tree chain of ns columns with a common set of k rows below).
+struct FrontDesc {
+    int first;      // first column (elimination order)
+    int ns;         // columns
+    int k;          // rows below the diagonal block
+    int ld;         // leading dimension of the front matrix (>= ns + k, multiple of 4)
+    int pad0, pad1;
+    int64_t m_off;  // offset of the front matrix in `M`
+    int64_t r_off;  // offset of the k row ids in `rows`
+    int64_t u_off;  // offset of the update vector in `U`
+    int64_t g_off;  // first entry of this front's ns + k rows in `gptr`
+};
+
+// One CTA's work in a sweep kernel: everything it needs in one 64-byte record (one dependent load).
+struct alignas(16) SweepTask {
+    int64_t m_off;  // front matrix
+    int64_t g_off;  // forward: first gather row of the front; backward: offset of the row ids
+    int64_t u_off;  // forward: update vector of the front
+    int first, ns, k, ld;
+    int start;      // forward: first row of the tile; backward: first column
+    int shape;      // forward: log2(rows per tile); backward: columns of this CTA
+    int pad0, pad1;
 };
 
 struct LdltDev {
     int n = 0, nrhs = 3, n_blocks = 0, n_levels = 0;
-    // permutation
+    int n_launches = 0;  // kernels of one apply
     int *perm = nullptr;   // perm[new] = old
     int *iperm = nullptr;  // iperm[old] = new
-    // block (supernode chain) partition and level schedule
-    int *blk_of = nullptr;     // [n]
-    int *blk_first = nullptr;  // [n_blocks+1]
-    int64_t *linv_off = nullptr;  // [n_blocks+1] offsets of the dense ns x ns inverse blocks
-    double *Linv = nullptr;       // row-major inverse of the unit-lower diagonal blocks
-    double *LinvT = nullptr;      // its transpose (rows of L^-T)
-    double *dinv = nullptr;       // 1/D
-    // forward sweep: CSR of the off-block part; backward sweep: CSC of the same entries
-    int64_t *fr_ptr = nullptr;
-    int *fr_col = nullptr;
-    double *fr_val = nullptr;
-    int64_t *bc_ptr = nullptr;
-    int *bc_row = nullptr;
-    double *bc_val = nullptr;
-    // per level and sweep kernel (fwd_off, fwd_diag, bwd_off, bwd_diag): LONG, SHORT and TINY rows;
-    // list_ptr[(level*4 + kind)*3 + {0,1,2,3}] delimit them inside lev_rows
-    std::vector<int> list_ptr;
-    int *lev_rows = nullptr;
-    // work vectors n x nrhs
-    double *W = nullptr, *Y = nullptr, *X = nullptr;
+    double *dinv = nullptr;  // 1/D
+    FrontDesc *fronts = nullptr;
+    double *M = nullptr;     // front matrices [Linv ; Q], column-major ld x ns each
+    int *rows = nullptr;     // row ids below each front
+    int4 *gell = nullptr;    // per front row: up to 4 child update slots that add into it (-1 = none)
+    int64_t *gptr = nullptr; // further slots (CSR), null when no row has more than 4
+    int *gidx = nullptr;
+    SweepTask *tasks = nullptr;  // per CTA
+    std::vector<int> ftask_ptr, btask_ptr;  // [n_levels+1] into tasks (forward list, then backward list)
+    std::vector<int> fsmem, bsmem;          // staged columns / rows per level (dynamic shared memory)
+    std::vector<int> bcw;                   // backward: columns per warp, per level
+    int btask_base = 0;
+    // work vectors: W = permuted rhs, Yd = D^-1 L^-1 rhs, X = solution (elimination order), U = front updates
+    double *W = nullptr, *Yd = nullptr, *X = nullptr, *U = nullptr;
     LdltStats stats;
 };
 
