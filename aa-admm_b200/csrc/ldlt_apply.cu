@@ -47,6 +47,16 @@ struct Gather {
 };
 
 template <int NR>
+__device__ __forceinline__ void gather_overflow(const Gather &G, int64_t grow, const double *U, double sign, double (&a)[NR]) {
+    const int64_t g1 = G.ptr[grow + 1];
+    for (int64_t g = G.ptr[grow]; g < g1; ++g) {
+        const size_t s = (size_t)G.idx[g] * NR;
+#pragma unroll
+        for (int q = 0; q < NR; ++q) a[q] += sign * U[s + q];
+    }
+}
+
+template <int NR>
 __device__ __forceinline__ void gather_add(const Gather &G, int64_t grow, const double *U, double sign, double (&a)[NR]) {
     const int4 e = __ldg(G.ell + grow);
     const int s4[4] = {e.x, e.y, e.z, e.w};
@@ -58,14 +68,7 @@ __device__ __forceinline__ void gather_add(const Gather &G, int64_t grow, const 
             for (int q = 0; q < NR; ++q) a[q] += sign * U[s + q];
         }
     }
-    if (G.ptr) {
-        const int64_t g1 = G.ptr[grow + 1];
-        for (int64_t g = G.ptr[grow]; g < g1; ++g) {
-            const size_t s = (size_t)G.idx[g] * NR;
-#pragma unroll
-            for (int q = 0; q < NR; ++q) a[q] += sign * U[s + q];
-        }
-    }
+    if (G.ptr) gather_overflow<NR>(G, grow, U, sign, a);
 }
 
 // ---- forward: one CTA = RT rows of one front, the columns interleaved over CS = 256 / RT slices ----
@@ -108,15 +111,42 @@ k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
     for (int jc = 0; jc < jneed; jc += ws_cap) {
         const int jn = min(jneed - jc, ws_cap);
         if (jc > 0) __syncthreads();
-        // w_j = rhs_j - sum of the child updates that land on column j
-        for (int j = threadIdx.x; j < jn; j += CTA) {
-            const int col = jc + j;
-            double a[NR];
+        // w_j = rhs_j - sum of the child updates that land on column j (4 columns per thread in flight)
+        for (int j0 = threadIdx.x; j0 < jn; j0 += 4 * CTA) {
+            double a[4][NR];
+            int4 e[4];
 #pragma unroll
-            for (int q = 0; q < NR; ++q) a[q] = W[(size_t)(F.first + col) * NR + q];
-            gather_add<NR>(G, F.g_off + col, U, -1.0, a);
+            for (int i = 0; i < 4; ++i) {
+                const int j = j0 + i * CTA;
+                if (j < jn) {
+                    e[i] = __ldg(G.ell + F.g_off + jc + j);
 #pragma unroll
-            for (int q = 0; q < NR; ++q) ws[j * NR + q] = a[q];
+                    for (int q = 0; q < NR; ++q) a[i][q] = W[(size_t)(F.first + jc + j) * NR + q];
+                } else {
+                    e[i] = make_int4(-1, -1, -1, -1);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int s4[4] = {e[i].x, e[i].y, e[i].z, e[i].w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (s4[c] >= 0) {
+                        const size_t s = (size_t)s4[c] * NR;
+#pragma unroll
+                        for (int q = 0; q < NR; ++q) a[i][q] -= U[s + q];
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = j0 + i * CTA;
+                if (j < jn) {
+                    if (G.ptr) gather_overflow<NR>(G, F.g_off + jc + j, U, -1.0, a[i]);
+#pragma unroll
+                    for (int q = 0; q < NR; ++q) ws[j * NR + q] = a[i][q];
+                }
+            }
         }
         __syncthreads();
         const int je = min(jend, jc + jn);
@@ -212,15 +242,35 @@ k_bwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
             const int re = min(m, rc + v_cap);
             if (!(single && !pre)) {
                 if (rc > c0) __syncthreads();
-                // v = [ D^-1 y of the front's columns ; -x of the rows below ]
-                for (int r = rc + threadIdx.x; r < re; r += CTA) {
-                    if (r < F.ns) {
+                // v = [ D^-1 y of the front's columns ; -x of the rows below ] (4 rows per thread in flight)
+                for (int r0 = rc + threadIdx.x; r0 < re; r0 += 4 * CTA) {
+                    size_t src[4];
+                    double sg[4];
 #pragma unroll
-                        for (int q = 0; q < NR; ++q) sm[(r - rc) * NR + q] = Yd[(size_t)(F.first + r) * NR + q];
-                    } else {
-                        const size_t i = (size_t)__ldg(rows + F.g_off + r - F.ns) * NR;
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = min(r0 + i * CTA, re - 1);
+                        if (r < F.ns) {
+                            src[i] = (size_t)(F.first + r) * NR;
+                            sg[i] = 1.0;
+                        } else {
+                            src[i] = (size_t)__ldg(rows + F.g_off + r - F.ns) * NR;
+                            sg[i] = -1.0;
+                        }
+                    }
+                    double vv[4][NR];
 #pragma unroll
-                        for (int q = 0; q < NR; ++q) sm[(r - rc) * NR + q] = -X[i + q];
+                    for (int i = 0; i < 4; ++i) {
+                        const double *p = sg[i] > 0.0 ? Yd : X;
+#pragma unroll
+                        for (int q = 0; q < NR; ++q) vv[i][q] = p[src[i] + q];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = r0 + i * CTA;
+                        if (r < re) {
+#pragma unroll
+                            for (int q = 0; q < NR; ++q) sm[(r - rc) * NR + q] = sg[i] * vv[i][q];
+                        }
                     }
                 }
                 __syncthreads();
