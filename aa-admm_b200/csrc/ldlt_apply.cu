@@ -72,9 +72,10 @@ __device__ __forceinline__ void gather_add(const Gather &G, int64_t grow, const 
 }
 
 // ---- forward: one CTA = RT rows of one front, the columns interleaved over CS = 256 / RT slices ----
-// RT = 256 .. 8 per task (narrow fronts want many rows per CTA, wide ones many slices).
-// The first FPRE loads of M are issued before w is gathered (they do not depend on it).
-constexpr int FPRE = 16, FUB = 8;
+// RT = 256 .. 16 per task (narrow fronts want many rows per CTA, wide ones many slices). A thread owns two
+// adjacent rows (16-byte loads). The first FPRE loads of M are issued before w is gathered (they do not
+// depend on it).
+constexpr int FPRE = 8, FUB = 8;
 template <int NR>
 __global__ void __launch_bounds__(CTA)
 k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
@@ -83,29 +84,32 @@ k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
     if (skip && *skip) return;
     extern __shared__ double sm[];
     double *ws = sm;                          // [ws_cap][NR]
-    double *part = sm + (size_t)ws_cap * NR;  // [CS][RT][NR]
+    double *part = sm + (size_t)ws_cap * NR;  // [CS][RT][NR], CS * RT = 512
     const SweepTask F = load_task(tasks + blockIdx.x);
     const int lrt = F.shape;
-    const int RT = 1 << lrt, CS = CTA >> lrt;
+    const int RT = 1 << lrt, CS = (2 * CTA) >> lrt;
     const int r0 = F.start, m = F.ns + F.k;
-    const int lr = threadIdx.x & (RT - 1), cs = threadIdx.x >> lrt;
-    const int row = r0 + lr;
+    const int lp = threadIdx.x & (RT / 2 - 1), cs = threadIdx.x >> (lrt - 1);
+    const int row = r0 + 2 * lp;           // rows row, row + 1
     const int jneed = min(F.ns, r0 + RT);  // rows of the diagonal block see columns <= row only
-    const int jend = row < F.ns ? row + 1 : (row < m ? F.ns : 0);
+    const int jend = row < F.ns ? min(F.ns, row + 2) : (row < m ? F.ns : 0);
     const double *Mp = M + F.m_off + row;
     const size_t ld = (size_t)F.ld;
-    double acc[NR], pass[NR];
+    double acc[2][NR], pass[NR];
 #pragma unroll
-    for (int q = 0; q < NR; ++q) acc[q] = pass[q] = 0.0;
-    // the children's updates of a row below the front are passed on to the parent with the front's own
-    if (cs == 0 && row >= F.ns && row < m) gather_add<NR>(G, F.g_off + row, U, 1.0, pass);
-    double pv[FPRE];
+    for (int q = 0; q < NR; ++q) acc[0][q] = acc[1][q] = pass[q] = 0.0;
+    // thread t < RT finishes row r0 + t; the children's updates of a row below the front are passed on to
+    // the parent together with the front's own
+    const int frow = r0 + (int)threadIdx.x;
+    const bool fin = (int)threadIdx.x < RT && frow < m;
+    if (fin && frow >= F.ns) gather_add<NR>(G, F.g_off + frow, U, 1.0, pass);
+    double2 pv[FPRE];
     {
         const int je0 = min(jend, ws_cap);
 #pragma unroll
         for (int u = 0; u < FPRE; ++u) {
             const int j = cs + u * CS;
-            pv[u] = j < je0 ? __ldg(Mp + (size_t)j * ld) : 0.0;
+            pv[u] = j < je0 ? __ldg(reinterpret_cast<const double2 *>(Mp + (size_t)j * ld)) : make_double2(0.0, 0.0);
         }
     }
     for (int jc = 0; jc < jneed; jc += ws_cap) {
@@ -157,44 +161,55 @@ k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
                 const int jj = cs + u * CS;
                 if (jj < je) {
 #pragma unroll
-                    for (int q = 0; q < NR; ++q) acc[q] += pv[u] * ws[jj * NR + q];
+                    for (int q = 0; q < NR; ++q) {
+                        const double w = ws[jj * NR + q];
+                        acc[0][q] += pv[u].x * w;
+                        acc[1][q] += pv[u].y * w;
+                    }
                 }
             }
             j += FPRE * CS;
         }
         for (; j < je; j += FUB * CS) {
-            double v[FUB];
+            double2 v[FUB];
 #pragma unroll
             for (int u = 0; u < FUB; ++u) {
                 const int jj = j + u * CS;
-                v[u] = jj < je ? __ldg(Mp + (size_t)jj * ld) : 0.0;
+                v[u] = jj < je ? __ldg(reinterpret_cast<const double2 *>(Mp + (size_t)jj * ld)) : make_double2(0.0, 0.0);
             }
 #pragma unroll
             for (int u = 0; u < FUB; ++u) {
                 const int jj = min(j + u * CS, je - 1) - jc;
 #pragma unroll
-                for (int q = 0; q < NR; ++q) acc[q] += v[u] * ws[jj * NR + q];
+                for (int q = 0; q < NR; ++q) {
+                    const double w = ws[jj * NR + q];
+                    acc[0][q] += v[u].x * w;
+                    acc[1][q] += v[u].y * w;
+                }
             }
         }
     }
 #pragma unroll
-    for (int q = 0; q < NR; ++q) part[(cs * RT + lr) * NR + q] = acc[q];
-    __syncthreads();
-    if (cs != 0 || row >= m) return;
+    for (int e = 0; e < 2; ++e)
 #pragma unroll
-    for (int q = 0; q < NR; ++q) acc[q] = 0.0;
+        for (int q = 0; q < NR; ++q) part[(cs * RT + 2 * lp + e) * NR + q] = acc[e][q];
+    __syncthreads();
+    if (!fin) return;
+    double sum[NR];
+#pragma unroll
+    for (int q = 0; q < NR; ++q) sum[q] = 0.0;
     for (int c = 0; c < CS; ++c) {
 #pragma unroll
-        for (int q = 0; q < NR; ++q) acc[q] += part[(c * RT + lr) * NR + q];
+        for (int q = 0; q < NR; ++q) sum[q] += part[(c * RT + (int)threadIdx.x) * NR + q];
     }
-    if (row < F.ns) {
-        const double di = dinv[F.first + row];
+    if (frow < F.ns) {
+        const double di = dinv[F.first + frow];
 #pragma unroll
-        for (int q = 0; q < NR; ++q) Yd[(size_t)(F.first + row) * NR + q] = acc[q] * di;
+        for (int q = 0; q < NR; ++q) Yd[(size_t)(F.first + frow) * NR + q] = sum[q] * di;
     } else {
-        const size_t o = (size_t)(F.u_off + row - F.ns) * NR;
+        const size_t o = (size_t)(F.u_off + frow - F.ns) * NR;
 #pragma unroll
-        for (int q = 0; q < NR; ++q) U[o + q] = acc[q] + pass[q];
+        for (int q = 0; q < NR; ++q) U[o + q] = sum[q] + pass[q];
     }
 }
 
@@ -664,7 +679,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         };
         for (int pass = 0; pass < 5 && count_f() < min_ctas; ++pass)
             for (int b : v)
-                if (lrt[b] > 3 && fr[b].ns >= 4 * (CTA >> (lrt[b] - 1))) lrt[b]--;
+                if (lrt[b] > 4 && fr[b].ns >= 4 * ((2 * CTA) >> (lrt[b] - 1))) lrt[b]--;
         const int v_cap = std::min(max_m, BCH);
         int cap = 128;
         auto set_cols = [&](int cw) {
@@ -693,7 +708,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         for (int b : by_level[l]) {
             const int m = fr[b].ns + fr[b].k;
             for (int r0 = 0; r0 < m;) {
-                const int shape = std::min(lrt[b], std::max(3, ceil_log2(m - r0)));
+                const int shape = std::min(lrt[b], std::max(4, ceil_log2(m - r0)));
                 tasks.push_back(make_task(b, true, r0, shape));
                 r0 += 1 << shape;
             }
@@ -768,7 +783,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
             return -1;
         }
     }
-    const int max_smem = (FCH + CTA) * 3 * (int)sizeof(double);
+    const int max_smem = (FCH + 2 * CTA) * 3 * (int)sizeof(double);
     cudaFuncSetAttribute(k_fwd_front<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(k_fwd_front<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(k_bwd_front<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
@@ -800,7 +815,7 @@ static int apply_impl(LdltDev *f, double *x_out, cudaStream_t s, const int *skip
         const int nt = f->ftask_ptr[l + 1] - f->ftask_ptr[l];
         if (nt <= 0) continue;
         const int ws_cap = f->fsmem[l];
-        const size_t smem = (size_t)(ws_cap + CTA) * NR * sizeof(double);
+        const size_t smem = (size_t)(ws_cap + 2 * CTA) * NR * sizeof(double);
         Gather G;
         G.ell = f->gell;
         G.ptr = f->gptr;
