@@ -73,28 +73,61 @@ __device__ __forceinline__ void gather_add(const Gather &G, int64_t grow, const 
 
 // ---- forward: one CTA = RT rows of one front, the columns interleaved over CS = 256 / RT slices ----
 // RT = 256 .. 16 per task (narrow fronts want many rows per CTA, wide ones many slices). A thread owns two
-// adjacent rows (16-byte loads). The first FPRE loads of M are issued before w is gathered (they do not
-// depend on it).
-constexpr int FPRE = 8, FUB = 8;
-template <int NR>
-__global__ void __launch_bounds__(CTA)
-k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
-            Gather G, const double *__restrict__ W, const double *__restrict__ dinv, double *__restrict__ Yd, double *U,
-            const int *skip, int ws_cap) {
-    if (skip && *skip) return;
-    extern __shared__ double sm[];
+// adjacent rows and streams its 16-byte pieces of M through a private ring in shared memory with cp.async
+// (FST stages of FUB pieces: no registers are held by loads in flight, and the first stages are issued
+// before w is gathered - they do not depend on it).
+constexpr int FUB = 8, FST = 3;
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// One tile; LRT = log2(rows of the tile) is a compile-time constant so that every stride of the streaming
+// loop is an immediate.
+template <int NR, int LRT>
+__device__ __forceinline__ void fwd_tile(const SweepTask &F, const double *__restrict__ M, const Gather &G,
+                                         const double *__restrict__ W, const double *__restrict__ dinv,
+                                         double *__restrict__ Yd, double *U, int ws_cap, double *sm) {
+    constexpr int RT = 1 << LRT, CS = (2 * CTA) >> LRT, STEP = FUB * CS;
     double *ws = sm;                          // [ws_cap][NR]
     double *part = sm + (size_t)ws_cap * NR;  // [CS][RT][NR], CS * RT = 512
-    const SweepTask F = load_task(tasks + blockIdx.x);
-    const int lrt = F.shape;
-    const int RT = 1 << lrt, CS = (2 * CTA) >> lrt;
+    double2 *ring = reinterpret_cast<double2 *>(part + 2 * CTA * NR) + threadIdx.x;  // [FST][FUB][CTA]
     const int r0 = F.start, m = F.ns + F.k;
-    const int lp = threadIdx.x & (RT / 2 - 1), cs = threadIdx.x >> (lrt - 1);
+    const int lp = threadIdx.x & (RT / 2 - 1), cs = threadIdx.x >> (LRT - 1);
     const int row = r0 + 2 * lp;           // rows row, row + 1
     const int jneed = min(F.ns, r0 + RT);  // rows of the diagonal block see columns <= row only
     const int jend = row < F.ns ? min(F.ns, row + 2) : (row < m ? F.ns : 0);
-    const double *Mp = M + F.m_off + row;
     const size_t ld = (size_t)F.ld;
+    const size_t cs_ld = (size_t)CS * ld;
+    // stages of this thread: stage s covers columns cs + s*STEP + u*CS, u < FUB
+    const int nst = jend > cs ? (jend - cs + STEP - 1) / STEP : 0;
+    const double *src = M + F.m_off + row + (size_t)cs * ld;  // next column to fetch
+    int st_issue = 0, slot_i = 0;
+    auto issue = [&]() {
+        if (st_issue < nst) {
+            double2 *slot = ring + slot_i * (FUB * CTA);
+            if (cs + st_issue * STEP + (FUB - 1) * CS < jend) {
+#pragma unroll
+                for (int u = 0; u < FUB; ++u) cp_async16(slot + u * CTA, src + u * cs_ld);
+            } else {
+#pragma unroll
+                for (int u = 0; u < FUB; ++u)
+                    if (cs + st_issue * STEP + u * CS < jend) cp_async16(slot + u * CTA, src + u * cs_ld);
+            }
+            src += FUB * cs_ld;
+        }
+        cp_async_commit();
+        ++st_issue;
+        slot_i = slot_i + 1 == FST ? 0 : slot_i + 1;
+    };
+#pragma unroll
+    for (int i = 0; i < FST - 1; ++i) issue();
     double acc[2][NR], pass[NR];
 #pragma unroll
     for (int q = 0; q < NR; ++q) acc[0][q] = acc[1][q] = pass[q] = 0.0;
@@ -103,15 +136,7 @@ k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
     const int frow = r0 + (int)threadIdx.x;
     const bool fin = (int)threadIdx.x < RT && frow < m;
     if (fin && frow >= F.ns) gather_add<NR>(G, F.g_off + frow, U, 1.0, pass);
-    double2 pv[FPRE];
-    {
-        const int je0 = min(jend, ws_cap);
-#pragma unroll
-        for (int u = 0; u < FPRE; ++u) {
-            const int j = cs + u * CS;
-            pv[u] = j < je0 ? __ldg(reinterpret_cast<const double2 *>(Mp + (size_t)j * ld)) : make_double2(0.0, 0.0);
-        }
-    }
+    int st_done = 0, slot_d = 0;
     for (int jc = 0; jc < jneed; jc += ws_cap) {
         const int jn = min(jneed - jc, ws_cap);
         if (jc > 0) __syncthreads();
@@ -153,42 +178,44 @@ k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
             }
         }
         __syncthreads();
+        // the stages whose columns fall into this chunk (a chunk boundary is a stage boundary)
         const int je = min(jend, jc + jn);
-        int j = jc + cs;
-        if (jc == 0) {
+        const double *wp = ws + (size_t)(cs + st_done * STEP - jc) * NR;
+        while (cs + st_done * STEP < je) {
+            issue();
+            cp_async_wait<FST - 1>();
+            const double2 *slot = ring + slot_d * (FUB * CTA);
+            if (cs + st_done * STEP + (FUB - 1) * CS < je) {
 #pragma unroll
-            for (int u = 0; u < FPRE; ++u) {
-                const int jj = cs + u * CS;
-                if (jj < je) {
+                for (int u = 0; u < FUB; ++u) {
+                    const double2 v = slot[u * CTA];
 #pragma unroll
                     for (int q = 0; q < NR; ++q) {
-                        const double w = ws[jj * NR + q];
-                        acc[0][q] += pv[u].x * w;
-                        acc[1][q] += pv[u].y * w;
+                        const double w = wp[u * CS * NR + q];
+                        acc[0][q] += v.x * w;
+                        acc[1][q] += v.y * w;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < FUB; ++u) {
+                    if (cs + st_done * STEP + u * CS < je) {
+                        const double2 v = slot[u * CTA];
+#pragma unroll
+                        for (int q = 0; q < NR; ++q) {
+                            const double w = wp[u * CS * NR + q];
+                            acc[0][q] += v.x * w;
+                            acc[1][q] += v.y * w;
+                        }
                     }
                 }
             }
-            j += FPRE * CS;
-        }
-        for (; j < je; j += FUB * CS) {
-            double2 v[FUB];
-#pragma unroll
-            for (int u = 0; u < FUB; ++u) {
-                const int jj = j + u * CS;
-                v[u] = jj < je ? __ldg(reinterpret_cast<const double2 *>(Mp + (size_t)jj * ld)) : make_double2(0.0, 0.0);
-            }
-#pragma unroll
-            for (int u = 0; u < FUB; ++u) {
-                const int jj = min(j + u * CS, je - 1) - jc;
-#pragma unroll
-                for (int q = 0; q < NR; ++q) {
-                    const double w = ws[jj * NR + q];
-                    acc[0][q] += v[u].x * w;
-                    acc[1][q] += v[u].y * w;
-                }
-            }
+            wp += STEP * NR;
+            ++st_done;
+            slot_d = slot_d + 1 == FST ? 0 : slot_d + 1;
         }
     }
+    cp_async_wait<0>();
 #pragma unroll
     for (int e = 0; e < 2; ++e)
 #pragma unroll
@@ -198,6 +225,7 @@ k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
     double sum[NR];
 #pragma unroll
     for (int q = 0; q < NR; ++q) sum[q] = 0.0;
+#pragma unroll
     for (int c = 0; c < CS; ++c) {
 #pragma unroll
         for (int q = 0; q < NR; ++q) sum[q] += part[(c * RT + (int)threadIdx.x) * NR + q];
@@ -213,6 +241,23 @@ k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
     }
 }
 
+template <int NR>
+__global__ void __launch_bounds__(CTA)
+k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
+            Gather G, const double *__restrict__ W, const double *__restrict__ dinv, double *__restrict__ Yd, double *U,
+            const int *skip, int ws_cap) {
+    if (skip && *skip) return;
+    extern __shared__ __align__(16) double sm[];
+    const SweepTask F = load_task(tasks + blockIdx.x);
+    switch (F.shape) {
+    case 8: fwd_tile<NR, 8>(F, M, G, W, dinv, Yd, U, ws_cap, sm); break;
+    case 7: fwd_tile<NR, 7>(F, M, G, W, dinv, Yd, U, ws_cap, sm); break;
+    case 6: fwd_tile<NR, 6>(F, M, G, W, dinv, Yd, U, ws_cap, sm); break;
+    case 5: fwd_tile<NR, 5>(F, M, G, W, dinv, Yd, U, ws_cap, sm); break;
+    default: fwd_tile<NR, 4>(F, M, G, W, dinv, Yd, U, ws_cap, sm); break;
+    }
+}
+
 // ---- backward: one CTA = 8 * CW columns of one front, one warp per CW columns, lanes along the rows ----
 // 16 loads of M per thread are in flight; the first 16 are issued before v is staged.
 template <int NR, int CW>
@@ -222,7 +267,7 @@ k_bwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
             double *__restrict__ x_out, const int *skip, int v_cap) {
     if (skip && *skip) return;
     constexpr int UB = 16 / CW;     // rows per lane and batch
-    extern __shared__ double sm[];  // v[v_cap][NR]
+    extern __shared__ __align__(16) double sm[];  // v[v_cap][NR]
     const SweepTask F = load_task(tasks + blockIdx.x);
     const int c0 = F.start, m = F.ns + F.k;
     const int cend = min(F.ns, c0 + F.shape);
@@ -783,7 +828,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
             return -1;
         }
     }
-    const int max_smem = (FCH + 2 * CTA) * 3 * (int)sizeof(double);
+    const int max_smem = (FCH + 2 * CTA) * 3 * (int)sizeof(double) + FST * FUB * CTA * 16;
     cudaFuncSetAttribute(k_fwd_front<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(k_fwd_front<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(k_bwd_front<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
@@ -815,7 +860,7 @@ static int apply_impl(LdltDev *f, double *x_out, cudaStream_t s, const int *skip
         const int nt = f->ftask_ptr[l + 1] - f->ftask_ptr[l];
         if (nt <= 0) continue;
         const int ws_cap = f->fsmem[l];
-        const size_t smem = (size_t)(ws_cap + 2 * CTA) * NR * sizeof(double);
+        const size_t smem = (size_t)(ws_cap + 2 * CTA) * NR * sizeof(double) + (size_t)FST * FUB * CTA * 16;
         Gather G;
         G.ell = f->gell;
         G.ptr = f->gptr;
