@@ -71,63 +71,93 @@ __device__ __forceinline__ void gather_add(const Gather &G, int64_t grow, const 
     if (G.ptr) gather_overflow<NR>(G, grow, U, sign, a);
 }
 
-// ---- forward: one CTA = RT rows of one front, the columns interleaved over CS = 256 / RT slices ----
-// RT = 256 .. 16 per task (narrow fronts want many rows per CTA, wide ones many slices). A thread owns two
-// adjacent rows and streams its 16-byte pieces of M through a private ring in shared memory with cp.async
-// (FST stages of FUB pieces: no registers are held by loads in flight, and the first stages are issued
-// before w is gathered - they do not depend on it).
-constexpr int FUB = 8, FST = 3;
+// ---- bulk-copy pipeline primitives (cp.async.bulk + mbarrier, sm_90+) ----------------------------
+// A 9th warp streams the CTA's part of the factor into a ring of NSTG stages of STG doubles in shared
+// memory (one elected lane issues cp.async.bulk; the bytes signal the stage's `full` barrier); the 8
+// consumer warps wait on `full`, use the stage and release it through `empty`. Loads in flight hold no
+// registers and cost one instruction per copy (up to 16 KB).
+constexpr int NCONS = CTA;          // consumer threads
+constexpr int NTHR = CTA + 32;      // + producer warp
+constexpr int STG = 2048;           // doubles per stage (16 KB)
+constexpr int NSTG = 4;
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
-// One tile; LRT = log2(rows of the tile) is a compile-time constant so that every stride of the streaming
-// loop is an immediate.
-template <int NR, int LRT>
-__device__ __forceinline__ void fwd_tile(const SweepTask &F, const double *__restrict__ M, const Gather &G,
-                                         const double *__restrict__ W, const double *__restrict__ dinv,
-                                         double *__restrict__ Yd, double *U, int ws_cap, double *sm) {
-    constexpr int RT = 1 << LRT, CS = (2 * CTA) >> LRT, STEP = FUB * CS;
-    double *ws = sm;                          // [ws_cap][NR]
-    double *part = sm + (size_t)ws_cap * NR;  // [CS][RT][NR], CS * RT = 512
-    double2 *ring = reinterpret_cast<double2 *>(part + 2 * CTA * NR) + threadIdx.x;  // [FST][FUB][CTA]
-    const int r0 = F.start, m = F.ns + F.k;
-    const int lp = threadIdx.x & (RT / 2 - 1), cs = threadIdx.x >> (LRT - 1);
-    const int row = r0 + 2 * lp;           // rows row, row + 1
-    const int jneed = min(F.ns, r0 + RT);  // rows of the diagonal block see columns <= row only
-    const int jend = row < F.ns ? min(F.ns, row + 2) : (row < m ? F.ns : 0);
-    const size_t ld = (size_t)F.ld;
-    const size_t cs_ld = (size_t)CS * ld;
-    // stages of this thread: stage s covers columns cs + s*STEP + u*CS, u < FUB
-    const int nst = jend > cs ? (jend - cs + STEP - 1) / STEP : 0;
-    const double *src = M + F.m_off + row + (size_t)cs * ld;  // next column to fetch
-    int st_issue = 0, slot_i = 0;
-    auto issue = [&]() {
-        if (st_issue < nst) {
-            double2 *slot = ring + slot_i * (FUB * CTA);
-            if (cs + st_issue * STEP + (FUB - 1) * CS < jend) {
+struct PipeBars {
+    uint64_t full[NSTG], empty[NSTG];
+};
+__device__ __forceinline__ void pipe_init(PipeBars &B) {
+    if (threadIdx.x == 0) {
 #pragma unroll
-                for (int u = 0; u < FUB; ++u) cp_async16(slot + u * CTA, src + u * cs_ld);
-            } else {
-#pragma unroll
-                for (int u = 0; u < FUB; ++u)
-                    if (cs + st_issue * STEP + u * CS < jend) cp_async16(slot + u * CTA, src + u * cs_ld);
-            }
-            src += FUB * cs_ld;
+        for (int i = 0; i < NSTG; ++i) {
+            mbar_init(&B.full[i], 1);
+            mbar_init(&B.empty[i], NCONS / 32);
         }
-        cp_async_commit();
-        ++st_issue;
-        slot_i = slot_i + 1 == FST ? 0 : slot_i + 1;
-    };
-#pragma unroll
-    for (int i = 0; i < FST - 1; ++i) issue();
+        mbar_fence_init();
+    }
+    __syncthreads();
+}
+
+// ---- forward: one CTA = RT rows of one front, the columns interleaved over CS = 512 / RT slices ----
+// RT = 256 .. 16 per task (narrow fronts want many rows per CTA, wide ones many slices). A consumer thread
+// owns two adjacent rows. The tile is stored contiguously (tile-major copy Mf of the front matrices: column
+// j of the tile at offset j * RT), so one stage = STG / RT columns = ONE bulk copy.
+template <int NR, int LRT>
+__device__ __forceinline__ void fwd_tile(const SweepTask &F, const double *__restrict__ Mf, const Gather &G,
+                                         const double *__restrict__ W, const double *__restrict__ dinv,
+                                         double *__restrict__ Yd, double *U, int ws_cap, double *sm, PipeBars &B) {
+    constexpr int RT = 1 << LRT, CS = (2 * CTA) >> LRT, NCS = STG / RT, PER = NCS / CS;
+    static_assert(PER >= 1, "stage narrower than the slices");
+    double *ring = sm;                         // [NSTG][STG]; reused by the final reduction
+    double *ws = sm + (size_t)NSTG * STG;      // [ws_cap][NR]
+    const int r0 = F.start, m = F.ns + F.k;
+    const int ncols = min(F.ns, r0 + RT);      // columns stored for this tile (rows of the diagonal block
+                                               // have nothing to the right of the tile's last row)
+    const int nstages = (ncols + NCS - 1) / NCS;
+    const double *tile = Mf + F.m_off;
+    if (threadIdx.x >= NCONS) {
+        if (threadIdx.x == NCONS) {
+            for (int it = 0; it < nstages; ++it) {
+                const int slot = it % NSTG;
+                mbar_wait(&B.empty[slot], ((it / NSTG) & 1) ^ 1);
+                const unsigned bytes = (unsigned)(min(NCS, ncols - it * NCS) * RT * 8);
+                mbar_expect_tx(&B.full[slot], bytes);
+                bulk_g2s(ring + (size_t)slot * STG, tile + (size_t)it * STG, bytes, &B.full[slot]);
+            }
+        }
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    const int lp = threadIdx.x & (RT / 2 - 1), cs = threadIdx.x >> (LRT - 1);
     double acc[2][NR], pass[NR];
 #pragma unroll
     for (int q = 0; q < NR; ++q) acc[0][q] = acc[1][q] = pass[q] = 0.0;
@@ -136,17 +166,17 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const double *__res
     const int frow = r0 + (int)threadIdx.x;
     const bool fin = (int)threadIdx.x < RT && frow < m;
     if (fin && frow >= F.ns) gather_add<NR>(G, F.g_off + frow, U, 1.0, pass);
-    int st_done = 0, slot_d = 0;
-    for (int jc = 0; jc < jneed; jc += ws_cap) {
-        const int jn = min(jneed - jc, ws_cap);
-        if (jc > 0) __syncthreads();
+    int it = 0;
+    for (int jc = 0; jc < ncols; jc += ws_cap) {
+        const int jn = min(ncols - jc, ws_cap);
+        if (jc > 0) cons_sync();
         // w_j = rhs_j - sum of the child updates that land on column j (4 columns per thread in flight)
-        for (int j0 = threadIdx.x; j0 < jn; j0 += 4 * CTA) {
+        for (int j0 = threadIdx.x; j0 < jn; j0 += 4 * NCONS) {
             double a[4][NR];
             int4 e[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int j = j0 + i * CTA;
+                const int j = j0 + i * NCONS;
                 if (j < jn) {
                     e[i] = __ldg(G.ell + F.g_off + jc + j);
 #pragma unroll
@@ -169,7 +199,7 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const double *__res
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int j = j0 + i * CTA;
+                const int j = j0 + i * NCONS;
                 if (j < jn) {
                     if (G.ptr) gather_overflow<NR>(G, F.g_off + jc + j, U, -1.0, a[i]);
 #pragma unroll
@@ -177,50 +207,53 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const double *__res
                 }
             }
         }
-        __syncthreads();
-        // the stages whose columns fall into this chunk (a chunk boundary is a stage boundary)
-        const int je = min(jend, jc + jn);
-        const double *wp = ws + (size_t)(cs + st_done * STEP - jc) * NR;
-        while (cs + st_done * STEP < je) {
-            issue();
-            cp_async_wait<FST - 1>();
-            const double2 *slot = ring + slot_d * (FUB * CTA);
-            if (cs + st_done * STEP + (FUB - 1) * CS < je) {
+        cons_sync();
+        // the stages whose columns fall into this chunk (ws_cap is a multiple of NCS)
+        const int je = jc + jn;
+        for (; it * NCS < je; ++it) {
+            const int slot = it % NSTG;
+            mbar_wait(&B.full[slot], (it / NSTG) & 1);
+            const double *st = ring + (size_t)slot * STG + 2 * lp;
+            const double *wp = ws + (size_t)(it * NCS - jc) * NR;
+            const int colsin = ncols - it * NCS;
+            if (colsin >= NCS) {
 #pragma unroll
-                for (int u = 0; u < FUB; ++u) {
-                    const double2 v = slot[u * CTA];
+                for (int i = 0; i < PER; ++i) {
+                    const int c = cs + i * CS;
+                    const double2 v = *reinterpret_cast<const double2 *>(st + c * RT);
 #pragma unroll
                     for (int q = 0; q < NR; ++q) {
-                        const double w = wp[u * CS * NR + q];
+                        const double w = wp[c * NR + q];
                         acc[0][q] += v.x * w;
                         acc[1][q] += v.y * w;
                     }
                 }
             } else {
 #pragma unroll
-                for (int u = 0; u < FUB; ++u) {
-                    if (cs + st_done * STEP + u * CS < je) {
-                        const double2 v = slot[u * CTA];
+                for (int i = 0; i < PER; ++i) {
+                    const int c = cs + i * CS;
+                    if (c < colsin) {
+                        const double2 v = *reinterpret_cast<const double2 *>(st + c * RT);
 #pragma unroll
                         for (int q = 0; q < NR; ++q) {
-                            const double w = wp[u * CS * NR + q];
+                            const double w = wp[c * NR + q];
                             acc[0][q] += v.x * w;
                             acc[1][q] += v.y * w;
                         }
                     }
                 }
             }
-            wp += STEP * NR;
-            ++st_done;
-            slot_d = slot_d + 1 == FST ? 0 : slot_d + 1;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&B.empty[slot]);
         }
     }
-    cp_async_wait<0>();
+    cons_sync();  // every consumer is done with the ring
+    double *part = ring;  // [CS][RT][NR], CS * RT = 512
 #pragma unroll
     for (int e = 0; e < 2; ++e)
 #pragma unroll
         for (int q = 0; q < NR; ++q) part[(cs * RT + 2 * lp + e) * NR + q] = acc[e][q];
-    __syncthreads();
+    cons_sync();
     if (!fin) return;
     double sum[NR];
 #pragma unroll
@@ -242,79 +275,95 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const double *__res
 }
 
 template <int NR>
-__global__ void __launch_bounds__(CTA)
-k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
+__global__ void __launch_bounds__(NTHR)
+k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ Mf,
             Gather G, const double *__restrict__ W, const double *__restrict__ dinv, double *__restrict__ Yd, double *U,
             const int *skip, int ws_cap) {
     if (skip && *skip) return;
-    extern __shared__ __align__(16) double sm[];
+    extern __shared__ __align__(128) double sm[];
+    __shared__ PipeBars B;
+    pipe_init(B);
     const SweepTask F = load_task(tasks + blockIdx.x);
     switch (F.shape) {
-    case 8: fwd_tile<NR, 8>(F, M, G, W, dinv, Yd, U, ws_cap, sm); break;
-    case 7: fwd_tile<NR, 7>(F, M, G, W, dinv, Yd, U, ws_cap, sm); break;
-    case 6: fwd_tile<NR, 6>(F, M, G, W, dinv, Yd, U, ws_cap, sm); break;
-    case 5: fwd_tile<NR, 5>(F, M, G, W, dinv, Yd, U, ws_cap, sm); break;
-    default: fwd_tile<NR, 4>(F, M, G, W, dinv, Yd, U, ws_cap, sm); break;
+    case 8: fwd_tile<NR, 8>(F, Mf, G, W, dinv, Yd, U, ws_cap, sm, B); break;
+    case 7: fwd_tile<NR, 7>(F, Mf, G, W, dinv, Yd, U, ws_cap, sm, B); break;
+    case 6: fwd_tile<NR, 6>(F, Mf, G, W, dinv, Yd, U, ws_cap, sm, B); break;
+    case 5: fwd_tile<NR, 5>(F, Mf, G, W, dinv, Yd, U, ws_cap, sm, B); break;
+    default: fwd_tile<NR, 4>(F, Mf, G, W, dinv, Yd, U, ws_cap, sm, B); break;
     }
 }
 
-// ---- backward: one CTA = 8 * CW columns of one front, one warp per CW columns, lanes along the rows ----
-// 16 loads of M per thread are in flight; the first 16 are issued before v is staged.
+// ---- backward: one CTA = `shape` columns of one front, 8 * CW at a time (one warp per CW columns, a lane
+// owns two adjacent rows). A stage = RB rows of those 8 * CW columns: one bulk copy per column out of the
+// column-major front matrix. ----
 template <int NR, int CW>
-__global__ void __launch_bounds__(CTA)
+__global__ void __launch_bounds__(NTHR)
 k_bwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
             const int *__restrict__ rows, const double *__restrict__ Yd, double *X, const int *__restrict__ perm,
             double *__restrict__ x_out, const int *skip, int v_cap) {
     if (skip && *skip) return;
-    constexpr int UB = 16 / CW;     // rows per lane and batch
-    extern __shared__ __align__(16) double sm[];  // v[v_cap][NR]
+    constexpr int NC = 8 * CW, RB = STG / NC;  // columns per pass, rows per stage
+    extern __shared__ __align__(128) double sm[];
+    __shared__ PipeBars B;
+    pipe_init(B);
+    double *ring = sm;                     // [NSTG][NC][RB]
+    double *vs = sm + (size_t)NSTG * STG;  // v[v_cap + RB][NR]
     const SweepTask F = load_task(tasks + blockIdx.x);
     const int c0 = F.start, m = F.ns + F.k;
     const int cend = min(F.ns, c0 + F.shape);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool single = (m - c0) <= v_cap;  // v fits at once: staged once, several column passes allowed
     const double *Mf = M + F.m_off;
-    for (int jb0 = c0; jb0 < cend; jb0 += 8 * CW) {
+    if (threadIdx.x >= NCONS) {
+        const int lane = threadIdx.x - NCONS;
+        int it = 0;
+        for (int jb0 = c0; jb0 < cend; jb0 += NC) {
+            const int rs = max(c0, jb0 & ~15);
+            const int ncol = min(NC, cend - jb0);
+            for (int rr = rs; rr < F.ld; rr += RB, ++it) {
+                const int slot = it % NSTG;
+                const int nrow = min(RB, F.ld - rr);
+                if (lane == 0) {
+                    mbar_wait(&B.empty[slot], ((it / NSTG) & 1) ^ 1);
+                    mbar_expect_tx(&B.full[slot], (unsigned)(ncol * nrow * 8));
+                }
+                __syncwarp();
+                if (lane < ncol)
+                    bulk_g2s(ring + (size_t)slot * STG + lane * RB, Mf + (size_t)(jb0 + lane) * F.ld + rr, (unsigned)(nrow * 8),
+                             &B.full[slot]);
+            }
+        }
+        return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool single = (F.ld - c0) <= v_cap;  // v fits at once: staged once, several column passes allowed
+    int it = 0;
+    for (int jb0 = c0; jb0 < cend; jb0 += NC) {
         const int jb = jb0 + warp * CW;
-        const bool live = jb < cend;
-        const bool pre = jb0 == c0;
-        const double *Mc[CW];
-#pragma unroll
-        for (int c = 0; c < CW; ++c) Mc[c] = Mf + (size_t)min(jb + c, F.ns - 1) * F.ld;
+        const int rs = max(c0, jb0 & ~15);
         double acc[CW][NR];
 #pragma unroll
         for (int c = 0; c < CW; ++c)
 #pragma unroll
             for (int q = 0; q < NR; ++q) acc[c][q] = 0.0;
-        // column j has no entries above row j: start at the 128-byte line that holds the diagonal
-        const int rs = max(c0, jb & ~15);
-        double pa[UB][CW];
-        if (pre) {
-            const int re0 = min(m, c0 + v_cap);
-#pragma unroll
-            for (int u = 0; u < UB; ++u) {
-                const int r = rs + lane + 32 * u;
-#pragma unroll
-                for (int c = 0; c < CW; ++c) pa[u][c] = (live && r < re0) ? __ldg(Mc[c] + r) : 0.0;
-            }
-        }
-        for (int rc = c0; rc < m; rc += v_cap) {
-            const int re = min(m, rc + v_cap);
-            if (!(single && !pre)) {
-                if (rc > c0) __syncthreads();
-                // v = [ D^-1 y of the front's columns ; -x of the rows below ] (4 rows per thread in flight)
-                for (int r0 = rc + threadIdx.x; r0 < re; r0 += 4 * CTA) {
+        for (int rc = c0; rc < F.ld; rc += v_cap) {
+            const int re = min(F.ld, rc + v_cap);
+            if (!(single && jb0 > c0)) {
+                if (rc > c0) cons_sync();
+                // v = [ D^-1 y of the front's columns ; -x of the rows below ; 0 ] (4 rows per thread in flight)
+                for (int r0 = rc + threadIdx.x; r0 < re; r0 += 4 * NCONS) {
                     size_t src[4];
                     double sg[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int r = min(r0 + i * CTA, re - 1);
+                        const int r = min(r0 + i * NCONS, re - 1);
                         if (r < F.ns) {
                             src[i] = (size_t)(F.first + r) * NR;
                             sg[i] = 1.0;
-                        } else {
+                        } else if (r < m) {
                             src[i] = (size_t)__ldg(rows + F.g_off + r - F.ns) * NR;
                             sg[i] = -1.0;
+                        } else {
+                            src[i] = 0;
+                            sg[i] = 0.0;
                         }
                     }
                     double vv[4][NR];
@@ -326,50 +375,45 @@ k_bwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int r = r0 + i * CTA;
+                        const int r = r0 + i * NCONS;
                         if (r < re) {
 #pragma unroll
-                            for (int q = 0; q < NR; ++q) sm[(r - rc) * NR + q] = sg[i] * vv[i][q];
+                            for (int q = 0; q < NR; ++q) vs[(r - rc) * NR + q] = sg[i] * vv[i][q];
                         }
                     }
                 }
-                __syncthreads();
+                cons_sync();
             }
-            if (!live) continue;
-            int r = max(rc, rs) + lane;
-            if (pre && rc == c0) {
+            // stages of this pass inside the chunk (chunk boundaries are stage boundaries)
+            for (int rr = max(rs, rc); rr < re; rr += RB, ++it) {
+                const int slot = it % NSTG;
+                mbar_wait(&B.full[slot], (it / NSTG) & 1);
+                const int nrow = min(RB, F.ld - rr);
+                const double *st = ring + (size_t)slot * STG + (warp * CW) * RB;
+                const double *vp = vs + (size_t)(rr - rc) * NR;
 #pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    const int rr = rs + lane + 32 * u;
-                    if (rr < re) {
+                for (int t = 0; t < RB / 64; ++t) {
+                    const int r = 64 * t + 2 * lane;
+                    if (r < nrow) {
+                        double v0[NR], v1[NR];
 #pragma unroll
                         for (int q = 0; q < NR; ++q) {
-                            const double vv = sm[(rr - rc) * NR + q];
+                            v0[q] = vp[r * NR + q];
+                            v1[q] = vp[(r + 1) * NR + q];
+                        }
 #pragma unroll
-                            for (int c = 0; c < CW; ++c) acc[c][q] += pa[u][c] * vv;
+                        for (int c = 0; c < CW; ++c) {
+                            const double2 a = *reinterpret_cast<const double2 *>(st + c * RB + r);
+#pragma unroll
+                            for (int q = 0; q < NR; ++q) {
+                                acc[c][q] += a.x * v0[q];
+                                acc[c][q] += a.y * v1[q];
+                            }
                         }
                     }
                 }
-                r = rs + lane + 32 * UB;
-            }
-            for (; r < re; r += 32 * UB) {
-                double a[UB][CW];
-#pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    const int rr = r + 32 * u;
-#pragma unroll
-                    for (int c = 0; c < CW; ++c) a[u][c] = rr < re ? __ldg(Mc[c] + rr) : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    const int rr = min(r + 32 * u, re - 1) - rc;
-#pragma unroll
-                    for (int q = 0; q < NR; ++q) {
-                        const double vv = sm[rr * NR + q];
-#pragma unroll
-                        for (int c = 0; c < CW; ++c) acc[c][q] += a[u][c] * vv;
-                    }
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&B.empty[slot]);
             }
         }
 #pragma unroll
@@ -378,7 +422,7 @@ k_bwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
             for (int q = 0; q < NR; ++q)
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc[c][q] += __shfl_xor_sync(0xffffffffu, acc[c][q], o);
-        if (lane == 0 && live) {
+        if (lane == 0) {
 #pragma unroll
             for (int c = 0; c < CW; ++c) {
                 const int j = jb + c;
@@ -392,6 +436,21 @@ k_bwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
                 }
             }
         }
+    }
+}
+
+// Tile-major copy of the front matrices for the forward sweep: one CTA per forward task.
+__global__ void __launch_bounds__(256)
+k_make_tiles(const SweepTask *__restrict__ tasks, const int64_t *__restrict__ src_off, const double *__restrict__ M,
+             double *__restrict__ Mf) {
+    const SweepTask F = tasks[blockIdx.x];
+    const int RT = 1 << F.shape, r0 = F.start;
+    const int ncols = min(F.ns, r0 + RT);
+    const double *src = M + src_off[blockIdx.x];
+    double *dst = Mf + F.m_off;
+    for (int e = threadIdx.x; e < ncols * RT; e += 256) {
+        const int j = e >> F.shape, r = r0 + (e & (RT - 1));
+        dst[e] = r < F.ld ? src[(size_t)j * F.ld + r] : 0.0;
     }
 }
 
@@ -504,6 +563,7 @@ void ldlt_dev_destroy(LdltDev *f) {
     cudaFree(f->dinv);
     cudaFree(f->fronts);
     cudaFree(f->M);
+    cudaFree(f->Mf);
     cudaFree(f->rows);
     cudaFree(f->gell);
     cudaFree(f->gptr);
@@ -725,14 +785,14 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         for (int pass = 0; pass < 5 && count_f() < min_ctas; ++pass)
             for (int b : v)
                 if (lrt[b] > 4 && fr[b].ns >= 4 * ((2 * CTA) >> (lrt[b] - 1))) lrt[b]--;
-        const int v_cap = std::min(max_m, BCH);
+        const int v_cap = std::min((max_m + 3 + 255) & ~255, BCH);
         int cap = 128;
         auto set_cols = [&](int cw) {
             int64_t c = 0;
             for (int b : v) {
                 const int m = fr[b].ns + fr[b].k, g = 8 * cw;
                 int nc = g;
-                if (m <= v_cap) nc = std::max(g, std::min(cap, tile_entries / std::max(m, 1)) / g * g);
+                if (fr[b].ld <= v_cap) nc = std::max(g, std::min(cap, tile_entries / std::max(m, 1)) / g * g);
                 bcols[b] = nc;
                 c += (fr[b].ns + nc - 1) / nc;
             }
@@ -746,7 +806,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
             else
                 break;
         }
-        f->fsmem[l] = std::min((max_ns + 31) & ~31, FCH);
+        f->fsmem[l] = std::min((max_ns + 127) & ~127, FCH);
         f->bsmem[l] = v_cap;
     }
     for (int l = 0; l < nlev; ++l) {
@@ -761,6 +821,16 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         f->ftask_ptr[l + 1] = (int)tasks.size();
     }
     f->btask_base = (int)tasks.size();
+    // tile-major copy for the forward sweep: the tile of a task is contiguous (column j at j * RT)
+    std::vector<int64_t> tile_src(tasks.size());
+    int64_t mf_tot = 0;
+    for (size_t i = 0; i < tasks.size(); ++i) {
+        SweepTask &t = tasks[i];
+        tile_src[i] = t.m_off;
+        t.m_off = mf_tot;
+        const int64_t RT = (int64_t)1 << t.shape;
+        mf_tot += (RT * std::min(t.ns, t.start + (int)RT) + 15) & ~(int64_t)15;
+    }
     for (int l = 0; l < nlev; ++l) {
         for (int b : by_level[l])
             for (int c0 = 0; c0 < fr[b].ns; c0 += bcols[b]) tasks.push_back(make_task(b, false, c0, bcols[b]));
@@ -818,17 +888,23 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         cudaMemset(f->M, 0, mat_bytes);
         if (!inv_tasks.empty()) k_invert_fronts<<<(int)inv_tasks.size(), 128>>>(d_inv, f->fronts, dA, f->M);
         if (!q_tasks.empty()) k_front_q<<<(int)q_tasks.size(), 256>>>(d_q, f->fronts, dA, f->M);
-        cudaError_t e = cudaDeviceSynchronize();
+        cudaFree(dA);  // ordered after the kernels above (same stream)
+        // tile-major copy for the forward sweep
+        int64_t *d_src = nullptr;
+        cudaError_t e = cudaMalloc((void **)&f->Mf, (size_t)std::max<int64_t>(mf_tot, 1) * sizeof(double));
+        if (e == cudaSuccess && upload(&d_src, tile_src) == 0 && f->btask_base > 0)
+            k_make_tiles<<<f->btask_base, 256>>>(f->tasks, d_src, f->M, f->Mf);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
         cudaFree(d_inv);
         cudaFree(d_q);
-        cudaFree(dA);
+        cudaFree(d_src);
         if (e != cudaSuccess) {
             set_last_error(std::string("ldlt: front setup failed: ") + cudaGetErrorString(e));
             ldlt_dev_destroy(f);
             return -1;
         }
     }
-    const int max_smem = (FCH + 2 * CTA) * 3 * (int)sizeof(double) + FST * FUB * CTA * 16;
+    const int max_smem = NSTG * STG * (int)sizeof(double) + (BCH + 256) * 3 * (int)sizeof(double);
     cudaFuncSetAttribute(k_fwd_front<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(k_fwd_front<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(k_bwd_front<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
@@ -860,29 +936,29 @@ static int apply_impl(LdltDev *f, double *x_out, cudaStream_t s, const int *skip
         const int nt = f->ftask_ptr[l + 1] - f->ftask_ptr[l];
         if (nt <= 0) continue;
         const int ws_cap = f->fsmem[l];
-        const size_t smem = (size_t)(ws_cap + 2 * CTA) * NR * sizeof(double) + (size_t)FST * FUB * CTA * 16;
+        const size_t smem = (size_t)NSTG * STG * sizeof(double) + (size_t)ws_cap * NR * sizeof(double);
         Gather G;
         G.ell = f->gell;
         G.ptr = f->gptr;
         G.idx = f->gidx;
-        k_fwd_front<NR><<<nt, CTA, smem, s>>>(f->tasks + f->ftask_ptr[l], f->M, G, f->W, f->dinv, f->Yd, f->U, skip,
+        k_fwd_front<NR><<<nt, NTHR, smem, s>>>(f->tasks + f->ftask_ptr[l], f->Mf, G, f->W, f->dinv, f->Yd, f->U, skip,
                                              ws_cap);
     }
     for (int l = nlev - 1; l >= 0; --l) {
         const int nt = f->btask_ptr[l + 1] - f->btask_ptr[l];
         if (nt <= 0) continue;
         const int v_cap = f->bsmem[l];
-        const size_t smem = (size_t)v_cap * NR * sizeof(double);
+        const size_t smem = (size_t)NSTG * STG * sizeof(double) + (size_t)v_cap * NR * sizeof(double);
         const SweepTask *tk = f->tasks + f->btask_base + f->btask_ptr[l];
         switch (f->bcw[l]) {
         case 4:
-            k_bwd_front<NR, 4><<<nt, CTA, smem, s>>>(tk, f->M, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
+            k_bwd_front<NR, 4><<<nt, NTHR, smem, s>>>(tk, f->M, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
             break;
         case 2:
-            k_bwd_front<NR, 2><<<nt, CTA, smem, s>>>(tk, f->M, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
+            k_bwd_front<NR, 2><<<nt, NTHR, smem, s>>>(tk, f->M, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
             break;
         default:
-            k_bwd_front<NR, 1><<<nt, CTA, smem, s>>>(tk, f->M, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
+            k_bwd_front<NR, 1><<<nt, NTHR, smem, s>>>(tk, f->M, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
             break;
         }
     }
