@@ -294,11 +294,11 @@ k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ Mf,
 }
 
 // ---- backward: one CTA = `shape` columns of one front, 8 * CW at a time (one warp per CW columns, a lane
-// owns two adjacent rows). A stage = RB rows of those 8 * CW columns: one bulk copy per column out of the
-// column-major front matrix. ----
+// owns two adjacent rows). A stage = RB rows of those 8 * CW columns, stored contiguously in Mb (the
+// backward copy of the front matrices, stage blocks in the order they are used): ONE bulk copy. ----
 template <int NR, int CW>
 __global__ void __launch_bounds__(NTHR)
-k_bwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
+k_bwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ Mb,
             const int *__restrict__ rows, const double *__restrict__ Yd, double *X, const int *__restrict__ perm,
             double *__restrict__ x_out, const int *skip, int v_cap) {
     if (skip && *skip) return;
@@ -311,24 +311,22 @@ k_bwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
     const SweepTask F = load_task(tasks + blockIdx.x);
     const int c0 = F.start, m = F.ns + F.k;
     const int cend = min(F.ns, c0 + F.shape);
-    const double *Mf = M + F.m_off;
     if (threadIdx.x >= NCONS) {
-        const int lane = threadIdx.x - NCONS;
-        int it = 0;
-        for (int jb0 = c0; jb0 < cend; jb0 += NC) {
-            const int rs = max(c0, jb0 & ~15);
-            const int ncol = min(NC, cend - jb0);
-            for (int rr = rs; rr < F.ld; rr += RB, ++it) {
-                const int slot = it % NSTG;
-                const int nrow = min(RB, F.ld - rr);
-                if (lane == 0) {
+        if (threadIdx.x == NCONS) {
+            // the task's stage blocks lie one after the other in Mb, in the order they are used
+            const double *src = Mb + F.m_off;
+            int it = 0;
+            for (int jb0 = c0; jb0 < cend; jb0 += NC) {
+                const int rs = max(c0, jb0 & ~15);
+                const int ncol = min(NC, cend - jb0);
+                for (int rr = rs; rr < F.ld; rr += RB, ++it) {
+                    const int slot = it % NSTG;
+                    const unsigned bytes = (unsigned)(ncol * min(RB, F.ld - rr) * 8);
                     mbar_wait(&B.empty[slot], ((it / NSTG) & 1) ^ 1);
-                    mbar_expect_tx(&B.full[slot], (unsigned)(ncol * nrow * 8));
+                    mbar_expect_tx(&B.full[slot], bytes);
+                    bulk_g2s(ring + (size_t)slot * STG, src, bytes, &B.full[slot]);
+                    src += bytes / 8;
                 }
-                __syncwarp();
-                if (lane < ncol)
-                    bulk_g2s(ring + (size_t)slot * STG + lane * RB, Mf + (size_t)(jb0 + lane) * F.ld + rr, (unsigned)(nrow * 8),
-                             &B.full[slot]);
             }
         }
         return;
@@ -389,7 +387,7 @@ k_bwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
                 const int slot = it % NSTG;
                 mbar_wait(&B.full[slot], (it / NSTG) & 1);
                 const int nrow = min(RB, F.ld - rr);
-                const double *st = ring + (size_t)slot * STG + (warp * CW) * RB;
+                const double *st = ring + (size_t)slot * STG + (warp * CW) * nrow;  // block = [ncol][nrow]
                 const double *vp = vs + (size_t)(rr - rc) * NR;
 #pragma unroll
                 for (int t = 0; t < RB / 64; ++t) {
@@ -403,7 +401,7 @@ k_bwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ M,
                         }
 #pragma unroll
                         for (int c = 0; c < CW; ++c) {
-                            const double2 a = *reinterpret_cast<const double2 *>(st + c * RB + r);
+                            const double2 a = *reinterpret_cast<const double2 *>(st + c * nrow + r);
 #pragma unroll
                             for (int q = 0; q < NR; ++q) {
                                 acc[c][q] += a.x * v0[q];
@@ -451,6 +449,30 @@ k_make_tiles(const SweepTask *__restrict__ tasks, const int64_t *__restrict__ sr
     for (int e = threadIdx.x; e < ncols * RT; e += 256) {
         const int j = e >> F.shape, r = r0 + (e & (RT - 1));
         dst[e] = r < F.ld ? src[(size_t)j * F.ld + r] : 0.0;
+    }
+}
+
+// Stage-major copy of the front matrices for the backward sweep: one CTA per backward task, walking the
+// passes and stages exactly like the producer of k_bwd_front.
+__global__ void __launch_bounds__(256)
+k_make_btiles(const SweepTask *__restrict__ tasks, const int64_t *__restrict__ src_off, int cw, const double *__restrict__ M,
+              double *__restrict__ Mb) {
+    const SweepTask F = tasks[blockIdx.x];
+    const int NC = 8 * cw, RB = STG / NC;
+    const int c0 = F.start, cend = min(F.ns, c0 + F.shape);
+    const double *src = M + src_off[blockIdx.x];
+    double *dst = Mb + F.m_off;
+    for (int jb0 = c0; jb0 < cend; jb0 += NC) {
+        const int rs = max(c0, jb0 & ~15);
+        const int ncol = min(NC, cend - jb0);
+        for (int rr = rs; rr < F.ld; rr += RB) {
+            const int nrow = min(RB, F.ld - rr);
+            for (int e = threadIdx.x; e < ncol * nrow; e += 256) {
+                const int c = e / nrow, r = e - c * nrow;
+                dst[e] = src[(size_t)(jb0 + c) * F.ld + rr + r];
+            }
+            dst += ncol * nrow;
+        }
     }
 }
 
@@ -564,6 +586,7 @@ void ldlt_dev_destroy(LdltDev *f) {
     cudaFree(f->fronts);
     cudaFree(f->M);
     cudaFree(f->Mf);
+    cudaFree(f->Mb);
     cudaFree(f->rows);
     cudaFree(f->gell);
     cudaFree(f->gptr);
@@ -831,9 +854,20 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         const int64_t RT = (int64_t)1 << t.shape;
         mf_tot += (RT * std::min(t.ns, t.start + (int)RT) + 15) & ~(int64_t)15;
     }
+    // stage-major copy for the backward sweep
+    int64_t mb_tot = 0;
     for (int l = 0; l < nlev; ++l) {
         for (int b : by_level[l])
-            for (int c0 = 0; c0 < fr[b].ns; c0 += bcols[b]) tasks.push_back(make_task(b, false, c0, bcols[b]));
+            for (int c0 = 0; c0 < fr[b].ns; c0 += bcols[b]) {
+                SweepTask t = make_task(b, false, c0, bcols[b]);
+                tile_src.push_back(t.m_off);
+                t.m_off = mb_tot;
+                const int NC = 8 * bcw[l], cend = std::min(t.ns, c0 + bcols[b]);
+                for (int jb0 = c0; jb0 < cend; jb0 += NC)
+                    mb_tot += (int64_t)std::min(NC, cend - jb0) * (t.ld - std::max(c0, jb0 & ~15));
+                mb_tot = (mb_tot + 15) & ~(int64_t)15;
+                tasks.push_back(t);
+            }
         f->btask_ptr[l + 1] = (int)tasks.size() - f->btask_base;
     }
 
@@ -892,9 +926,17 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         // tile-major copy for the forward sweep
         int64_t *d_src = nullptr;
         cudaError_t e = cudaMalloc((void **)&f->Mf, (size_t)std::max<int64_t>(mf_tot, 1) * sizeof(double));
-        if (e == cudaSuccess && upload(&d_src, tile_src) == 0 && f->btask_base > 0)
-            k_make_tiles<<<f->btask_base, 256>>>(f->tasks, d_src, f->M, f->Mf);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&f->Mb, (size_t)std::max<int64_t>(mb_tot, 1) * sizeof(double));
+        if (e == cudaSuccess && upload(&d_src, tile_src) == 0) {
+            if (f->btask_base > 0) k_make_tiles<<<f->btask_base, 256>>>(f->tasks, d_src, f->M, f->Mf);
+            for (int l = 0; l < nlev; ++l) {
+                const int nt = f->btask_ptr[l + 1] - f->btask_ptr[l], o = f->btask_base + f->btask_ptr[l];
+                if (nt > 0) k_make_btiles<<<nt, 256>>>(f->tasks + o, d_src + o, bcw[l], f->M, f->Mb);
+            }
+        }
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        cudaFree(f->M);  // only the two sweep-ordered copies stay
+        f->M = nullptr;
         cudaFree(d_inv);
         cudaFree(d_q);
         cudaFree(d_src);
@@ -952,13 +994,13 @@ static int apply_impl(LdltDev *f, double *x_out, cudaStream_t s, const int *skip
         const SweepTask *tk = f->tasks + f->btask_base + f->btask_ptr[l];
         switch (f->bcw[l]) {
         case 4:
-            k_bwd_front<NR, 4><<<nt, NTHR, smem, s>>>(tk, f->M, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
+            k_bwd_front<NR, 4><<<nt, NTHR, smem, s>>>(tk, f->Mb, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
             break;
         case 2:
-            k_bwd_front<NR, 2><<<nt, NTHR, smem, s>>>(tk, f->M, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
+            k_bwd_front<NR, 2><<<nt, NTHR, smem, s>>>(tk, f->Mb, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
             break;
         default:
-            k_bwd_front<NR, 1><<<nt, NTHR, smem, s>>>(tk, f->M, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
+            k_bwd_front<NR, 1><<<nt, NTHR, smem, s>>>(tk, f->Mb, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
             break;
         }
     }

@@ -47,8 +47,9 @@ struct LdltDev {
     int *iperm = nullptr;  // iperm[old] = new
     double *dinv = nullptr;  // 1/D
     FrontDesc *fronts = nullptr;
-    double *M = nullptr;     // front matrices [Linv ; Q], column-major ld x ns each (backward sweep)
+    double *M = nullptr;     // front matrices [Linv ; Q], column-major ld x ns each (setup only)
     double *Mf = nullptr;    // the same entries tile by tile in the order the forward sweep streams them
+    double *Mb = nullptr;    // ... and stage by stage in the order the backward sweep streams them
     int *rows = nullptr;     // row ids below each front
     int4 *gell = nullptr;    // per front row: up to 4 child update slots that add into it (-1 = none)
     int64_t *gptr = nullptr; // further slots (CSR), null when no row has more than 4
