@@ -110,6 +110,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// Programmatic dependent launch: the next level's kernel may start (and fill its ring with factor data,
+// which does not depend on the previous level) while this one drains; it must not touch anything a
+// previous kernel wrote before pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
 struct PipeBars {
@@ -127,12 +132,17 @@ __device__ __forceinline__ void pipe_init(PipeBars &B) {
     __syncthreads();
 }
 
+// skip flag set: drain the copies already issued (the CTA's shared memory must not be recycled under them)
+__device__ __forceinline__ void pipe_drain(PipeBars &B, int issued) {
+    for (int i = 0; i < issued; ++i) mbar_wait(&B.full[i], 0);
+}
+
 // ---- forward: one CTA = RT rows of one front, the columns interleaved over CS = 512 / RT slices ----
 // RT = 256 .. 16 per task (narrow fronts want many rows per CTA, wide ones many slices). A consumer thread
 // owns two adjacent rows. The tile is stored contiguously (tile-major copy Mf of the front matrices: column
 // j of the tile at offset j * RT), so one stage = STG / RT columns = ONE bulk copy.
 template <int NR, int LRT>
-__device__ __forceinline__ void fwd_tile(const SweepTask &F, const double *__restrict__ Mf, const Gather &G,
+__device__ __forceinline__ void fwd_tile(const SweepTask &F, const Gather &G,
                                          const double *__restrict__ W, const double *__restrict__ dinv,
                                          double *__restrict__ Yd, double *U, int ws_cap, double *sm, PipeBars &B) {
     constexpr int RT = 1 << LRT, CS = (2 * CTA) >> LRT, NCS = STG / RT, PER = NCS / CS;
@@ -143,19 +153,6 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const double *__res
     const int ncols = min(F.ns, r0 + RT);      // columns stored for this tile (rows of the diagonal block
                                                // have nothing to the right of the tile's last row)
     const int nstages = (ncols + NCS - 1) / NCS;
-    const double *tile = Mf + F.m_off;
-    if (threadIdx.x >= NCONS) {
-        if (threadIdx.x == NCONS) {
-            for (int it = 0; it < nstages; ++it) {
-                const int slot = it % NSTG;
-                mbar_wait(&B.empty[slot], ((it / NSTG) & 1) ^ 1);
-                const unsigned bytes = (unsigned)(min(NCS, ncols - it * NCS) * RT * 8);
-                mbar_expect_tx(&B.full[slot], bytes);
-                bulk_g2s(ring + (size_t)slot * STG, tile + (size_t)it * STG, bytes, &B.full[slot]);
-            }
-        }
-        return;
-    }
     const int lane = threadIdx.x & 31;
     const int lp = threadIdx.x & (RT / 2 - 1), cs = threadIdx.x >> (LRT - 1);
     double acc[2][NR], pass[NR];
@@ -279,17 +276,43 @@ __global__ void __launch_bounds__(NTHR)
 k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ Mf,
             Gather G, const double *__restrict__ W, const double *__restrict__ dinv, double *__restrict__ Yd, double *U,
             const int *skip, int ws_cap) {
-    if (skip && *skip) return;
     extern __shared__ __align__(128) double sm[];
     __shared__ PipeBars B;
     pipe_init(B);
     const SweepTask F = load_task(tasks + blockIdx.x);
+    pdl_launch_dependents();
+    // producer: the tile is one contiguous run of Mf; the first NSTG stages go out before the previous
+    // level is known to be finished
+    const int RT = 1 << F.shape, NCS = STG / RT;
+    const int ncols = min(F.ns, F.start + RT);
+    const int nstages = (ncols + NCS - 1) / NCS;
+    const double *tile = Mf + F.m_off;
+    auto produce = [&](int it) {
+        const int slot = it % NSTG;
+        mbar_wait(&B.empty[slot], ((it / NSTG) & 1) ^ 1);
+        const unsigned bytes = (unsigned)(min(NCS, ncols - it * NCS) * RT * 8);
+        mbar_expect_tx(&B.full[slot], bytes);
+        bulk_g2s(sm + (size_t)slot * STG, tile + (size_t)it * STG, bytes, &B.full[slot]);
+    };
+    const int first = min(nstages, NSTG);
+    if (threadIdx.x == NCONS)
+        for (int it = 0; it < first; ++it) produce(it);
+    pdl_wait();
+    if (skip && *skip) {
+        if (threadIdx.x == NCONS) pipe_drain(B, first);
+        return;
+    }
+    if (threadIdx.x >= NCONS) {
+        if (threadIdx.x == NCONS)
+            for (int it = first; it < nstages; ++it) produce(it);
+        return;
+    }
     switch (F.shape) {
-    case 8: fwd_tile<NR, 8>(F, Mf, G, W, dinv, Yd, U, ws_cap, sm, B); break;
-    case 7: fwd_tile<NR, 7>(F, Mf, G, W, dinv, Yd, U, ws_cap, sm, B); break;
-    case 6: fwd_tile<NR, 6>(F, Mf, G, W, dinv, Yd, U, ws_cap, sm, B); break;
-    case 5: fwd_tile<NR, 5>(F, Mf, G, W, dinv, Yd, U, ws_cap, sm, B); break;
-    default: fwd_tile<NR, 4>(F, Mf, G, W, dinv, Yd, U, ws_cap, sm, B); break;
+    case 8: fwd_tile<NR, 8>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
+    case 7: fwd_tile<NR, 7>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
+    case 6: fwd_tile<NR, 6>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
+    case 5: fwd_tile<NR, 5>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
+    default: fwd_tile<NR, 4>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
     }
 }
 
@@ -301,34 +324,43 @@ __global__ void __launch_bounds__(NTHR)
 k_bwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ Mb,
             const int *__restrict__ rows, const double *__restrict__ Yd, double *X, const int *__restrict__ perm,
             double *__restrict__ x_out, const int *skip, int v_cap) {
-    if (skip && *skip) return;
     constexpr int NC = 8 * CW, RB = STG / NC;  // columns per pass, rows per stage
     extern __shared__ __align__(128) double sm[];
     __shared__ PipeBars B;
     pipe_init(B);
     double *ring = sm;                     // [NSTG][NC][RB]
-    double *vs = sm + (size_t)NSTG * STG;  // v[v_cap + RB][NR]
+    double *vs = sm + (size_t)NSTG * STG;  // v[v_cap][NR]
     const SweepTask F = load_task(tasks + blockIdx.x);
+    pdl_launch_dependents();
     const int c0 = F.start, m = F.ns + F.k;
     const int cend = min(F.ns, c0 + F.shape);
-    if (threadIdx.x >= NCONS) {
-        if (threadIdx.x == NCONS) {
-            // the task's stage blocks lie one after the other in Mb, in the order they are used
-            const double *src = Mb + F.m_off;
-            int it = 0;
-            for (int jb0 = c0; jb0 < cend; jb0 += NC) {
-                const int rs = max(c0, jb0 & ~15);
-                const int ncol = min(NC, cend - jb0);
-                for (int rr = rs; rr < F.ld; rr += RB, ++it) {
-                    const int slot = it % NSTG;
-                    const unsigned bytes = (unsigned)(ncol * min(RB, F.ld - rr) * 8);
-                    mbar_wait(&B.empty[slot], ((it / NSTG) & 1) ^ 1);
-                    mbar_expect_tx(&B.full[slot], bytes);
-                    bulk_g2s(ring + (size_t)slot * STG, src, bytes, &B.full[slot]);
-                    src += bytes / 8;
-                }
+    // producer state: the task's stage blocks lie one after the other in Mb, in the order they are used
+    const double *psrc = Mb + F.m_off;
+    int pit = 0, pjb0 = c0, prr = c0;  // next stage: pass pjb0, first row prr
+    auto produce = [&](int limit) {
+        while (pjb0 < cend && pit < limit) {
+            const int slot = pit % NSTG;
+            const unsigned bytes = (unsigned)(min(NC, cend - pjb0) * min(RB, F.ld - prr) * 8);
+            mbar_wait(&B.empty[slot], ((pit / NSTG) & 1) ^ 1);
+            mbar_expect_tx(&B.full[slot], bytes);
+            bulk_g2s(ring + (size_t)slot * STG, psrc, bytes, &B.full[slot]);
+            psrc += bytes / 8;
+            ++pit;
+            prr += RB;
+            if (prr >= F.ld) {
+                pjb0 += NC;
+                prr = max(c0, pjb0 & ~15);
             }
         }
+    };
+    if (threadIdx.x == NCONS) produce(NSTG);
+    pdl_wait();
+    if (skip && *skip) {
+        if (threadIdx.x == NCONS) pipe_drain(B, pit);
+        return;
+    }
+    if (threadIdx.x >= NCONS) {
+        if (threadIdx.x == NCONS) produce(0x7fffffff);
         return;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -971,6 +1003,23 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     return 0;
 }
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait above).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_sweep(void (*kern)(KArgs...), int grid, size_t smem, cudaStream_t s, Args... args) {
+    static const bool no_pdl = getenv("AAADMM_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NTHR);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int NR>
 static int apply_impl(LdltDev *f, double *x_out, cudaStream_t s, const int *skip) {
     const int nlev = f->n_levels;
@@ -983,8 +1032,8 @@ static int apply_impl(LdltDev *f, double *x_out, cudaStream_t s, const int *skip
         G.ell = f->gell;
         G.ptr = f->gptr;
         G.idx = f->gidx;
-        k_fwd_front<NR><<<nt, NTHR, smem, s>>>(f->tasks + f->ftask_ptr[l], f->Mf, G, f->W, f->dinv, f->Yd, f->U, skip,
-                                             ws_cap);
+        AAADMM_CUDA_OK(launch_sweep(k_fwd_front<NR>, nt, smem, s, f->tasks + f->ftask_ptr[l], f->Mf, G, f->W, f->dinv, f->Yd,
+                                    f->U, skip, ws_cap));
     }
     for (int l = nlev - 1; l >= 0; --l) {
         const int nt = f->btask_ptr[l + 1] - f->btask_ptr[l];
@@ -994,13 +1043,13 @@ static int apply_impl(LdltDev *f, double *x_out, cudaStream_t s, const int *skip
         const SweepTask *tk = f->tasks + f->btask_base + f->btask_ptr[l];
         switch (f->bcw[l]) {
         case 4:
-            k_bwd_front<NR, 4><<<nt, NTHR, smem, s>>>(tk, f->Mb, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
+            AAADMM_CUDA_OK(launch_sweep(k_bwd_front<NR, 4>, nt, smem, s, tk, f->Mb, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap));
             break;
         case 2:
-            k_bwd_front<NR, 2><<<nt, NTHR, smem, s>>>(tk, f->Mb, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
+            AAADMM_CUDA_OK(launch_sweep(k_bwd_front<NR, 2>, nt, smem, s, tk, f->Mb, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap));
             break;
         default:
-            k_bwd_front<NR, 1><<<nt, NTHR, smem, s>>>(tk, f->Mb, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap);
+            AAADMM_CUDA_OK(launch_sweep(k_bwd_front<NR, 1>, nt, smem, s, tk, f->Mb, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap));
             break;
         }
     }
