@@ -646,7 +646,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     // and either the patterns nest exactly (fundamental supernode) or the front is still small
     // (relaxed: the rows below j-1 are a subset of those below j; the difference is stored as zeros).
     // tuning knobs (environment overrides are for experiments only)
-    const int kSmall = env_int("AAADMM_KSMALL", 96), kCap = env_int("AAADMM_KCAP", 6144);
+    const int kSmall = env_int("AAADMM_KSMALL", 64), kCap = env_int("AAADMM_KCAP", 6144);
     std::vector<int> blk_of(std::max(n, 1)), blk_first;
     for (int j = 0; j < n; ++j) {
         bool join = false;
@@ -788,7 +788,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     // fronts get tall tiles (long CTAs amortise their fixed latency), wide ones many slices. Backward: a
     // CTA takes `ncols` columns, each warp CW of them at a time. Levels with few fronts are cut finer
     // until the launch has at least min_ctas CTAs.
-    const int min_ctas = env_int("AAADMM_MIN_CTAS", 296);
+    const int min_ctas = env_int("AAADMM_MIN_CTAS", 148);  // one CTA per SM; each keeps 48 KB of loads in flight
     const int tile_entries = env_int("AAADMM_TILE_ENTRIES", 32768);
     std::vector<std::vector<int>> by_level(nlev);
     for (int b = 0; b < nb; ++b) by_level[level[b]].push_back(b);
