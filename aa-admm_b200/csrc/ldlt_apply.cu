@@ -25,8 +25,8 @@ namespace aaadmm {
 namespace {
 
 constexpr int CTA = 256;
-constexpr int FCH = 2048;  // columns of w staged in shared memory at a time (forward)
-constexpr int BCH = 2048;  // rows of v staged in shared memory at a time (backward)
+constexpr int FCH = 1024;  // columns of w staged in shared memory at a time (forward)
+constexpr int BCH = 1024;  // rows of v staged in shared memory at a time (backward)
 
 // Child updates that add into one front row: up to 4 slots inline (-1 = none), the rest (rare) in a CSR.
 __device__ __forceinline__ SweepTask load_task(const SweepTask *t) {
@@ -52,7 +52,7 @@ __device__ __forceinline__ void gather_overflow(const Gather &G, int64_t grow, c
     for (int64_t g = G.ptr[grow]; g < g1; ++g) {
         const size_t s = (size_t)G.idx[g] * NR;
 #pragma unroll
-        for (int q = 0; q < NR; ++q) a[q] += sign * U[s + q];
+        for (int q = 0; q < NR; ++q) a[q] += sign * __ldcg(U + s + q);
     }
 }
 
@@ -65,7 +65,7 @@ __device__ __forceinline__ void gather_add(const Gather &G, int64_t grow, const 
         if (s4[i] >= 0) {
             const size_t s = (size_t)s4[i] * NR;
 #pragma unroll
-            for (int q = 0; q < NR; ++q) a[q] += sign * U[s + q];
+            for (int q = 0; q < NR; ++q) a[q] += sign * __ldcg(U + s + q);
         }
     }
     if (G.ptr) gather_overflow<NR>(G, grow, U, sign, a);
@@ -115,6 +115,30 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 // previous kernel wrote before pdl_wait().
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+// Dataflow between the tasks of one sweep kernel: a task starts its dependent reads when the counter of the
+// fronts it needs has reached `need`, and bumps its own front's counter when its results are written.
+// Tasks are handed out in topological order through an atomic ticket, so everything a task waits for is
+// already running or finished: the wait cannot deadlock.
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void task_wait(const int *cnt, const SweepTask &F) {
+    if (F.need > 0) {
+        if (threadIdx.x == 0) {
+            while (ld_acquire(cnt + F.wait_idx) < F.need) __nanosleep(40);
+        }
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    }
+}
+// called by all consumer threads after their global writes
+__device__ __forceinline__ void task_signal(int *cnt, const SweepTask &F) {
+    __threadfence();
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    if (threadIdx.x == 0 && F.signal_idx >= 0) atomicAdd(cnt + F.signal_idx, 1);
+}
+
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
 struct PipeBars {
@@ -190,7 +214,7 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const Gather &G,
                     if (s4[c] >= 0) {
                         const size_t s = (size_t)s4[c] * NR;
 #pragma unroll
-                        for (int q = 0; q < NR; ++q) a[i][q] -= U[s + q];
+                        for (int q = 0; q < NR; ++q) a[i][q] -= __ldcg(U + s + q);
                     }
                 }
             }
@@ -251,35 +275,38 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const Gather &G,
 #pragma unroll
         for (int q = 0; q < NR; ++q) part[(cs * RT + 2 * lp + e) * NR + q] = acc[e][q];
     cons_sync();
-    if (!fin) return;
-    double sum[NR];
+    if (fin) {
+        double sum[NR];
 #pragma unroll
-    for (int q = 0; q < NR; ++q) sum[q] = 0.0;
+        for (int q = 0; q < NR; ++q) sum[q] = 0.0;
 #pragma unroll
-    for (int c = 0; c < CS; ++c) {
+        for (int c = 0; c < CS; ++c) {
 #pragma unroll
-        for (int q = 0; q < NR; ++q) sum[q] += part[(c * RT + (int)threadIdx.x) * NR + q];
-    }
-    if (frow < F.ns) {
-        const double di = dinv[F.first + frow];
+            for (int q = 0; q < NR; ++q) sum[q] += part[(c * RT + (int)threadIdx.x) * NR + q];
+        }
+        if (frow < F.ns) {
+            const double di = dinv[F.first + frow];
 #pragma unroll
-        for (int q = 0; q < NR; ++q) Yd[(size_t)(F.first + frow) * NR + q] = sum[q] * di;
-    } else {
-        const size_t o = (size_t)(F.u_off + frow - F.ns) * NR;
+            for (int q = 0; q < NR; ++q) Yd[(size_t)(F.first + frow) * NR + q] = sum[q] * di;
+        } else {
+            const size_t o = (size_t)(F.u_off + frow - F.ns) * NR;
 #pragma unroll
-        for (int q = 0; q < NR; ++q) U[o + q] = sum[q] + pass[q];
+            for (int q = 0; q < NR; ++q) U[o + q] = sum[q] + pass[q];
+        }
     }
 }
 
 template <int NR>
 __global__ void __launch_bounds__(NTHR)
-k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ Mf,
+k_fwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restrict__ Mf,
             Gather G, const double *__restrict__ W, const double *__restrict__ dinv, double *__restrict__ Yd, double *U,
             const int *skip, int ws_cap) {
     extern __shared__ __align__(128) double sm[];
     __shared__ PipeBars B;
+    __shared__ int s_task;
+    if (threadIdx.x == 0) s_task = atomicAdd(ctl, 1);
     pipe_init(B);
-    const SweepTask F = load_task(tasks + blockIdx.x);
+    const SweepTask F = load_task(tasks + s_task);
     pdl_launch_dependents();
     // producer: the tile is one contiguous run of Mf; the first NSTG stages go out before the previous
     // level is known to be finished
@@ -307,6 +334,7 @@ k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ Mf,
             for (int it = first; it < nstages; ++it) produce(it);
         return;
     }
+    task_wait(ctl + 2, F);  // the children's updates are written
     switch (F.shape) {
     case 8: fwd_tile<NR, 8>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
     case 7: fwd_tile<NR, 7>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
@@ -314,55 +342,21 @@ k_fwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ Mf,
     case 5: fwd_tile<NR, 5>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
     default: fwd_tile<NR, 4>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
     }
+    task_signal(ctl + 2, F);
 }
 
 // ---- backward: one CTA = `shape` columns of one front, 8 * CW at a time (one warp per CW columns, a lane
 // owns two adjacent rows). A stage = RB rows of those 8 * CW columns, stored contiguously in Mb (the
 // backward copy of the front matrices, stage blocks in the order they are used): ONE bulk copy. ----
 template <int NR, int CW>
-__global__ void __launch_bounds__(NTHR)
-k_bwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ Mb,
-            const int *__restrict__ rows, const double *__restrict__ Yd, double *X, const int *__restrict__ perm,
-            double *__restrict__ x_out, const int *skip, int v_cap) {
+__device__ __forceinline__ void bwd_task(const SweepTask &F, const int *__restrict__ rows, const double *Yd, double *X,
+                                         const int *__restrict__ perm, double *__restrict__ x_out, int v_cap, double *sm,
+                                         PipeBars &B) {
     constexpr int NC = 8 * CW, RB = STG / NC;  // columns per pass, rows per stage
-    extern __shared__ __align__(128) double sm[];
-    __shared__ PipeBars B;
-    pipe_init(B);
     double *ring = sm;                     // [NSTG][NC][RB]
     double *vs = sm + (size_t)NSTG * STG;  // v[v_cap][NR]
-    const SweepTask F = load_task(tasks + blockIdx.x);
-    pdl_launch_dependents();
     const int c0 = F.start, m = F.ns + F.k;
     const int cend = min(F.ns, c0 + F.shape);
-    // producer state: the task's stage blocks lie one after the other in Mb, in the order they are used
-    const double *psrc = Mb + F.m_off;
-    int pit = 0, pjb0 = c0, prr = c0;  // next stage: pass pjb0, first row prr
-    auto produce = [&](int limit) {
-        while (pjb0 < cend && pit < limit) {
-            const int slot = pit % NSTG;
-            const unsigned bytes = (unsigned)(min(NC, cend - pjb0) * min(RB, F.ld - prr) * 8);
-            mbar_wait(&B.empty[slot], ((pit / NSTG) & 1) ^ 1);
-            mbar_expect_tx(&B.full[slot], bytes);
-            bulk_g2s(ring + (size_t)slot * STG, psrc, bytes, &B.full[slot]);
-            psrc += bytes / 8;
-            ++pit;
-            prr += RB;
-            if (prr >= F.ld) {
-                pjb0 += NC;
-                prr = max(c0, pjb0 & ~15);
-            }
-        }
-    };
-    if (threadIdx.x == NCONS) produce(NSTG);
-    pdl_wait();
-    if (skip && *skip) {
-        if (threadIdx.x == NCONS) pipe_drain(B, pit);
-        return;
-    }
-    if (threadIdx.x >= NCONS) {
-        if (threadIdx.x == NCONS) produce(0x7fffffff);
-        return;
-    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool single = (F.ld - c0) <= v_cap;  // v fits at once: staged once, several column passes allowed
     int it = 0;
@@ -401,7 +395,7 @@ k_bwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ Mb,
                     for (int i = 0; i < 4; ++i) {
                         const double *p = sg[i] > 0.0 ? Yd : X;
 #pragma unroll
-                        for (int q = 0; q < NR; ++q) vv[i][q] = p[src[i] + q];
+                        for (int q = 0; q < NR; ++q) vv[i][q] = __ldcg(p + src[i] + q);
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -469,6 +463,58 @@ k_bwd_front(const SweepTask *__restrict__ tasks, const double *__restrict__ Mb,
     }
 }
 
+template <int NR>
+__global__ void __launch_bounds__(NTHR)
+k_bwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restrict__ Mb,
+            const int *__restrict__ rows, const double *Yd, double *X, const int *__restrict__ perm,
+            double *__restrict__ x_out, const int *skip, int v_cap) {
+    extern __shared__ __align__(128) double sm[];
+    __shared__ PipeBars B;
+    __shared__ int s_task;
+    if (threadIdx.x == 0) s_task = atomicAdd(ctl + 1, 1);
+    pipe_init(B);
+    const SweepTask F = load_task(tasks + s_task);
+    pdl_launch_dependents();
+    const int NC = 8 * F.cw, RB = STG / NC;
+    const int c0 = F.start, cend = min(F.ns, c0 + F.shape);
+    // producer state: the task's stage blocks lie one after the other in Mb, in the order they are used
+    const double *psrc = Mb + F.m_off;
+    int pit = 0, pjb0 = c0, prr = c0;  // next stage: pass pjb0, first row prr
+    auto produce = [&](int limit) {
+        while (pjb0 < cend && pit < limit) {
+            const int slot = pit % NSTG;
+            const unsigned bytes = (unsigned)(min(NC, cend - pjb0) * min(RB, F.ld - prr) * 8);
+            mbar_wait(&B.empty[slot], ((pit / NSTG) & 1) ^ 1);
+            mbar_expect_tx(&B.full[slot], bytes);
+            bulk_g2s(sm + (size_t)slot * STG, psrc, bytes, &B.full[slot]);
+            psrc += bytes / 8;
+            ++pit;
+            prr += RB;
+            if (prr >= F.ld) {
+                pjb0 += NC;
+                prr = max(c0, pjb0 & ~15);
+            }
+        }
+    };
+    if (threadIdx.x == NCONS) produce(NSTG);
+    pdl_wait();
+    if (skip && *skip) {
+        if (threadIdx.x == NCONS) pipe_drain(B, pit);
+        return;
+    }
+    if (threadIdx.x >= NCONS) {
+        if (threadIdx.x == NCONS) produce(0x7fffffff);
+        return;
+    }
+    task_wait(ctl + 2, F);  // the parent's (hence every ancestor's) x is written
+    switch (F.cw) {
+    case 4: bwd_task<NR, 4>(F, rows, Yd, X, perm, x_out, v_cap, sm, B); break;
+    case 2: bwd_task<NR, 2>(F, rows, Yd, X, perm, x_out, v_cap, sm, B); break;
+    default: bwd_task<NR, 1>(F, rows, Yd, X, perm, x_out, v_cap, sm, B); break;
+    }
+    task_signal(ctl + 2, F);
+}
+
 // Tile-major copy of the front matrices for the forward sweep: one CTA per forward task.
 __global__ void __launch_bounds__(256)
 k_make_tiles(const SweepTask *__restrict__ tasks, const int64_t *__restrict__ src_off, const double *__restrict__ M,
@@ -487,10 +533,10 @@ k_make_tiles(const SweepTask *__restrict__ tasks, const int64_t *__restrict__ sr
 // Stage-major copy of the front matrices for the backward sweep: one CTA per backward task, walking the
 // passes and stages exactly like the producer of k_bwd_front.
 __global__ void __launch_bounds__(256)
-k_make_btiles(const SweepTask *__restrict__ tasks, const int64_t *__restrict__ src_off, int cw, const double *__restrict__ M,
+k_make_btiles(const SweepTask *__restrict__ tasks, const int64_t *__restrict__ src_off, const double *__restrict__ M,
               double *__restrict__ Mb) {
     const SweepTask F = tasks[blockIdx.x];
-    const int NC = 8 * cw, RB = STG / NC;
+    const int NC = 8 * F.cw, RB = STG / NC;
     const int c0 = F.start, cend = min(F.ns, c0 + F.shape);
     const double *src = M + src_off[blockIdx.x];
     double *dst = Mb + F.m_off;
@@ -628,6 +674,7 @@ void ldlt_dev_destroy(LdltDev *f) {
     cudaFree(f->Yd);
     cudaFree(f->X);
     cudaFree(f->U);
+    cudaFree(f->ctl);
     delete f;
 }
 
@@ -692,7 +739,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     int nlev = 0;
     for (int b = 0; b < nb; ++b) nlev = std::max(nlev, level[b] + 1);
     f->n_levels = nlev;
-    f->n_launches = 2 * nlev;
+    f->n_launches = 2;
 
     // ---- rows below each front, front matrices A = [T ; P] (column-major), child update slots ----
     std::vector<int> rows((size_t)std::max<int64_t>(r_tot, 1));
@@ -783,21 +830,18 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         }
     }
 
-    // ---- level schedule: tile shapes and task lists ----
-    // Forward: a CTA takes RT = 2^lrt rows of a front and splits the columns over 256 / RT slices: narrow
+    // ---- schedule: tile shapes and task lists ----
+    // Forward: a CTA takes RT = 2^lrt rows of a front and splits the columns over 512 / RT slices: narrow
     // fronts get tall tiles (long CTAs amortise their fixed latency), wide ones many slices. Backward: a
-    // CTA takes `ncols` columns, each warp CW of them at a time. Levels with few fronts are cut finer
-    // until the launch has at least min_ctas CTAs.
+    // CTA takes `ncols` columns, each warp CW of them at a time. Tree levels with few fronts are cut finer
+    // until they have at least min_ctas tasks. One launch per sweep: the tasks are listed in topological
+    // order (forward bottom-up, backward top-down) and synchronise through per-front arrival counters.
     const int min_ctas = env_int("AAADMM_MIN_CTAS", 148);  // one CTA per SM; each keeps 48 KB of loads in flight
     const int tile_entries = env_int("AAADMM_TILE_ENTRIES", 32768);
     std::vector<std::vector<int>> by_level(nlev);
     for (int b = 0; b < nb; ++b) by_level[level[b]].push_back(b);
     std::vector<SweepTask> tasks;
-    f->ftask_ptr.assign(nlev + 1, 0);
-    f->btask_ptr.assign(nlev + 1, 0);
-    f->fsmem.assign(nlev, 0);
-    f->bsmem.assign(nlev, 0);
-    std::vector<int> bcw(nlev, 4);
+    std::vector<int> bcw(std::max(nlev, 1), 4);
     auto make_task = [&](int b, bool fwd, int start, int shape) {
         const FrontDesc &F = fr[b];
         SweepTask t;
@@ -810,7 +854,10 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         t.ld = F.ld;
         t.start = start;
         t.shape = shape;
-        t.pad0 = t.pad1 = 0;
+        t.wait_idx = 0;
+        t.need = 0;
+        t.signal_idx = -1;
+        t.cw = 4;
         return t;
     };
     auto ceil_log2 = [](int v) {
@@ -818,6 +865,15 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         while ((1 << l) < v) ++l;
         return l;
     };
+    int max_ns_all = 1, max_ld_all = 4;
+    for (int b = 0; b < nb; ++b) {
+        max_ns_all = std::max(max_ns_all, fr[b].ns);
+        max_ld_all = std::max(max_ld_all, fr[b].ld);
+    }
+    const int ws_cap = std::min((max_ns_all + 127) & ~127, FCH);
+    const int v_cap = std::min((max_ld_all + 255) & ~255, BCH);
+    f->ws_cap = ws_cap;
+    f->v_cap = v_cap;
     std::vector<int> lrt(std::max(nb, 1), 8), bcols(std::max(nb, 1), 32);
     for (int l = 0; l < nlev; ++l) {
         std::vector<int> &v = by_level[l];
@@ -825,12 +881,9 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
             const int64_t wa = (int64_t)fr[a].ns * (fr[a].ns + fr[a].k), wb = (int64_t)fr[b2].ns * (fr[b2].ns + fr[b2].k);
             return wa != wb ? wa > wb : a < b2;
         });
-        int max_ns = 1, max_m = 1;
         for (int b : v) {
             const int ns = fr[b].ns;
             lrt[b] = ns <= 128 ? 8 : (ns <= 256 ? 7 : (ns <= 512 ? 6 : (ns <= 1024 ? 5 : 4)));
-            max_ns = std::max(max_ns, ns);
-            max_m = std::max(max_m, ns + fr[b].k);
         }
         auto count_f = [&]() {
             int64_t c = 0;
@@ -840,7 +893,6 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         for (int pass = 0; pass < 5 && count_f() < min_ctas; ++pass)
             for (int b : v)
                 if (lrt[b] > 4 && fr[b].ns >= 4 * ((2 * CTA) >> (lrt[b] - 1))) lrt[b]--;
-        const int v_cap = std::min((max_m + 3 + 255) & ~255, BCH);
         int cap = 128;
         auto set_cols = [&](int cw) {
             int64_t c = 0;
@@ -861,21 +913,28 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
             else
                 break;
         }
-        f->fsmem[l] = std::min((max_ns + 127) & ~127, FCH);
-        f->bsmem[l] = v_cap;
     }
+    // counters: [2 + b] forward arrivals at front b (tiles of its children), [2 + nb + b] backward arrivals
+    // of front b (its own column chunks)
+    std::vector<int> ntiles_f(std::max(nb, 1), 0), ntasks_b(std::max(nb, 1), 0), need_f(std::max(nb, 1), 0);
     for (int l = 0; l < nlev; ++l) {
         for (int b : by_level[l]) {
             const int m = fr[b].ns + fr[b].k;
             for (int r0 = 0; r0 < m;) {
                 const int shape = std::min(lrt[b], std::max(4, ceil_log2(m - r0)));
-                tasks.push_back(make_task(b, true, r0, shape));
+                SweepTask t = make_task(b, true, r0, shape);
+                t.wait_idx = b;
+                t.signal_idx = parent[b];
+                tasks.push_back(t);
+                ntiles_f[b]++;
                 r0 += 1 << shape;
             }
         }
-        f->ftask_ptr[l + 1] = (int)tasks.size();
     }
-    f->btask_base = (int)tasks.size();
+    f->n_ftasks = (int)tasks.size();
+    for (int b = 0; b < nb; ++b)
+        if (parent[b] >= 0) need_f[parent[b]] += ntiles_f[b];
+    for (int i = 0; i < f->n_ftasks; ++i) tasks[i].need = need_f[tasks[i].wait_idx];
     // tile-major copy for the forward sweep: the tile of a task is contiguous (column j at j * RT)
     std::vector<int64_t> tile_src(tasks.size());
     int64_t mf_tot = 0;
@@ -888,10 +947,13 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     }
     // stage-major copy for the backward sweep
     int64_t mb_tot = 0;
-    for (int l = 0; l < nlev; ++l) {
+    for (int l = nlev - 1; l >= 0; --l) {
         for (int b : by_level[l])
             for (int c0 = 0; c0 < fr[b].ns; c0 += bcols[b]) {
                 SweepTask t = make_task(b, false, c0, bcols[b]);
+                t.cw = bcw[l];
+                t.wait_idx = nb + std::max(parent[b], 0);
+                t.signal_idx = nb + b;
                 tile_src.push_back(t.m_off);
                 t.m_off = mb_tot;
                 const int NC = 8 * bcw[l], cend = std::min(t.ns, c0 + bcols[b]);
@@ -899,9 +961,15 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
                     mb_tot += (int64_t)std::min(NC, cend - jb0) * (t.ld - std::max(c0, jb0 & ~15));
                 mb_tot = (mb_tot + 15) & ~(int64_t)15;
                 tasks.push_back(t);
+                ntasks_b[b]++;
             }
-        f->btask_ptr[l + 1] = (int)tasks.size() - f->btask_base;
     }
+    f->n_btasks = (int)tasks.size() - f->n_ftasks;
+    for (size_t i = f->n_ftasks; i < tasks.size(); ++i) {
+        const int b = tasks[i].signal_idx - nb;
+        tasks[i].need = parent[b] >= 0 ? ntasks_b[parent[b]] : 0;
+    }
+    f->n_ctl = 2 + 2 * nb;
 
     std::vector<int> permv(perm, perm + n), iperm(std::max(n, 1));
     for (int k = 0; k < n; ++k) iperm[perm[k]] = k;
@@ -929,7 +997,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     const size_t u_bytes = std::max<size_t>((size_t)r_tot * nrhs, 1) * sizeof(double);
     if (rc || cudaMalloc((void **)&f->M, mat_bytes) != cudaSuccess || cudaMalloc((void **)&f->W, vec_bytes) != cudaSuccess ||
         cudaMalloc((void **)&f->Yd, vec_bytes) != cudaSuccess || cudaMalloc((void **)&f->X, vec_bytes) != cudaSuccess ||
-        cudaMalloc((void **)&f->U, u_bytes) != cudaSuccess) {
+        cudaMalloc((void **)&f->U, u_bytes) != cudaSuccess || cudaMalloc((void **)&f->ctl, sizeof(int) * f->n_ctl) != cudaSuccess) {
         set_last_error("ldlt: cudaMalloc failed");
         cudaFree(dA);
         ldlt_dev_destroy(f);
@@ -960,11 +1028,8 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         cudaError_t e = cudaMalloc((void **)&f->Mf, (size_t)std::max<int64_t>(mf_tot, 1) * sizeof(double));
         if (e == cudaSuccess) e = cudaMalloc((void **)&f->Mb, (size_t)std::max<int64_t>(mb_tot, 1) * sizeof(double));
         if (e == cudaSuccess && upload(&d_src, tile_src) == 0) {
-            if (f->btask_base > 0) k_make_tiles<<<f->btask_base, 256>>>(f->tasks, d_src, f->M, f->Mf);
-            for (int l = 0; l < nlev; ++l) {
-                const int nt = f->btask_ptr[l + 1] - f->btask_ptr[l], o = f->btask_base + f->btask_ptr[l];
-                if (nt > 0) k_make_btiles<<<nt, 256>>>(f->tasks + o, d_src + o, bcw[l], f->M, f->Mb);
-            }
+            if (f->n_ftasks > 0) k_make_tiles<<<f->n_ftasks, 256>>>(f->tasks, d_src, f->M, f->Mf);
+            if (f->n_btasks > 0) k_make_btiles<<<f->n_btasks, 256>>>(f->tasks + f->n_ftasks, d_src + f->n_ftasks, f->M, f->Mb);
         }
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
         cudaFree(f->M);  // only the two sweep-ordered copies stay
@@ -981,13 +1046,8 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     const int max_smem = NSTG * STG * (int)sizeof(double) + (BCH + 256) * 3 * (int)sizeof(double);
     cudaFuncSetAttribute(k_fwd_front<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(k_fwd_front<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(k_bwd_front<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(k_bwd_front<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(k_bwd_front<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(k_bwd_front<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(k_bwd_front<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(k_bwd_front<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    f->bcw = bcw;
+    cudaFuncSetAttribute(k_bwd_front<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(k_bwd_front<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     f->stats.n = n;
     f->stats.n_blocks = nb;
     f->stats.n_levels = nlev;
@@ -1022,37 +1082,17 @@ static cudaError_t launch_sweep(void (*kern)(KArgs...), int grid, size_t smem, c
 
 template <int NR>
 static int apply_impl(LdltDev *f, double *x_out, cudaStream_t s, const int *skip) {
-    const int nlev = f->n_levels;
-    for (int l = 0; l < nlev; ++l) {
-        const int nt = f->ftask_ptr[l + 1] - f->ftask_ptr[l];
-        if (nt <= 0) continue;
-        const int ws_cap = f->fsmem[l];
-        const size_t smem = (size_t)NSTG * STG * sizeof(double) + (size_t)ws_cap * NR * sizeof(double);
-        Gather G;
-        G.ell = f->gell;
-        G.ptr = f->gptr;
-        G.idx = f->gidx;
-        AAADMM_CUDA_OK(launch_sweep(k_fwd_front<NR>, nt, smem, s, f->tasks + f->ftask_ptr[l], f->Mf, G, f->W, f->dinv, f->Yd,
-                                    f->U, skip, ws_cap));
-    }
-    for (int l = nlev - 1; l >= 0; --l) {
-        const int nt = f->btask_ptr[l + 1] - f->btask_ptr[l];
-        if (nt <= 0) continue;
-        const int v_cap = f->bsmem[l];
-        const size_t smem = (size_t)NSTG * STG * sizeof(double) + (size_t)v_cap * NR * sizeof(double);
-        const SweepTask *tk = f->tasks + f->btask_base + f->btask_ptr[l];
-        switch (f->bcw[l]) {
-        case 4:
-            AAADMM_CUDA_OK(launch_sweep(k_bwd_front<NR, 4>, nt, smem, s, tk, f->Mb, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap));
-            break;
-        case 2:
-            AAADMM_CUDA_OK(launch_sweep(k_bwd_front<NR, 2>, nt, smem, s, tk, f->Mb, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap));
-            break;
-        default:
-            AAADMM_CUDA_OK(launch_sweep(k_bwd_front<NR, 1>, nt, smem, s, tk, f->Mb, f->rows, f->Yd, f->X, f->perm, x_out, skip, v_cap));
-            break;
-        }
-    }
+    if (f->n_ftasks == 0) return 0;
+    AAADMM_CUDA_OK(cudaMemsetAsync(f->ctl, 0, sizeof(int) * f->n_ctl, s));
+    Gather G;
+    G.ell = f->gell;
+    G.ptr = f->gptr;
+    G.idx = f->gidx;
+    const size_t ring = (size_t)NSTG * STG * sizeof(double);
+    AAADMM_CUDA_OK(launch_sweep(k_fwd_front<NR>, f->n_ftasks, ring + (size_t)f->ws_cap * NR * sizeof(double), s, f->tasks, f->ctl,
+                                f->Mf, G, f->W, f->dinv, f->Yd, f->U, skip, f->ws_cap));
+    AAADMM_CUDA_OK(launch_sweep(k_bwd_front<NR>, f->n_btasks, ring + (size_t)f->v_cap * NR * sizeof(double), s,
+                                f->tasks + f->n_ftasks, f->ctl, f->Mb, f->rows, f->Yd, f->X, f->perm, x_out, skip, f->v_cap));
     AAADMM_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -37,7 +37,10 @@ struct alignas(16) SweepTask {
     int first, ns, k, ld;
     int start;      // forward: first row of the tile; backward: first column
     int shape;      // forward: log2(rows per tile); backward: columns of this CTA
-    int pad0, pad1;
+    int wait_idx;   // dependency counter this task waits on ...
+    int need;       // ... until it reaches this value (0: no dependency)
+    int signal_idx; // counter to bump when the task is done (-1: none)
+    int cw;         // backward: columns per warp
 };
 
 struct LdltDev {
@@ -54,11 +57,11 @@ struct LdltDev {
     int4 *gell = nullptr;    // per front row: up to 4 child update slots that add into it (-1 = none)
     int64_t *gptr = nullptr; // further slots (CSR), null when no row has more than 4
     int *gidx = nullptr;
-    SweepTask *tasks = nullptr;  // per CTA
-    std::vector<int> ftask_ptr, btask_ptr;  // [n_levels+1] into tasks (forward list, then backward list)
-    std::vector<int> fsmem, bsmem;          // staged columns / rows per level (dynamic shared memory)
-    std::vector<int> bcw;                   // backward: columns per warp, per level
-    int btask_base = 0;
+    SweepTask *tasks = nullptr;  // forward tasks (fronts bottom-up), then backward tasks (top-down)
+    int n_ftasks = 0, n_btasks = 0;
+    int ws_cap = 0, v_cap = 0;   // staged columns (forward) / rows (backward) per chunk
+    int *ctl = nullptr;          // [0], [1]: next forward / backward task; then one arrival counter per front and sweep
+    int n_ctl = 0;
     // work vectors: W = permuted rhs, Yd = D^-1 L^-1 rhs, X = solution (elimination order), U = front updates
     double *W = nullptr, *Yd = nullptr, *X = nullptr, *U = nullptr;
     LdltStats stats;
