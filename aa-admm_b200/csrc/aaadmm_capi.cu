@@ -338,6 +338,7 @@ int aaadmm_ldlt_solve(aaadmm_ldlt *h, const double *b, double *x) {
     AAADMM_CUDA_OK(cudaStreamSynchronize(h->stream));
     return 0;
 }
+int aaadmm_ldlt_dump_trace(aaadmm_ldlt *h, const char *path) { return ldlt_dev_dump_trace(h->f, path); }
 int aaadmm_ldlt_stats(aaadmm_ldlt *h, double *s) {
     const LdltStats &t = h->f->stats;
     s[0] = t.n;

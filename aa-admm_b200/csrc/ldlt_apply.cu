@@ -17,6 +17,7 @@
 #include "ldlt_apply.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -79,7 +80,7 @@ __device__ __forceinline__ void gather_add(const Gather &G, int64_t grow, const 
 constexpr int NCONS = CTA;          // consumer threads
 constexpr int NTHR = CTA + 32;      // + producer warp
 constexpr int STG = 2048;           // doubles per stage (16 KB)
-constexpr int NSTG = 4;
+constexpr int NSTG = 3;
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
@@ -119,6 +120,11 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\
 // fronts it needs has reached `need`, and bumps its own front's counter when its results are written.
 // Tasks are handed out in topological order through an atomic ticket, so everything a task waits for is
 // already running or finished: the wait cannot deadlock.
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ int ld_acquire(const int *p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
@@ -300,10 +306,11 @@ template <int NR>
 __global__ void __launch_bounds__(NTHR)
 k_fwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restrict__ Mf,
             Gather G, const double *__restrict__ W, const double *__restrict__ dinv, double *__restrict__ Yd, double *U,
-            const int *skip, int ws_cap) {
+            const int *skip, int ws_cap, unsigned long long *trace) {
     extern __shared__ __align__(128) double sm[];
     __shared__ PipeBars B;
     __shared__ int s_task;
+    const unsigned long long t0 = trace ? gtime() : 0;
     if (threadIdx.x == 0) s_task = atomicAdd(ctl, 1);
     pipe_init(B);
     const SweepTask F = load_task(tasks + s_task);
@@ -334,7 +341,9 @@ k_fwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restr
             for (int it = first; it < nstages; ++it) produce(it);
         return;
     }
+    const unsigned long long t1 = trace ? gtime() : 0;
     task_wait(ctl + 2, F);  // the children's updates are written
+    const unsigned long long t2 = trace ? gtime() : 0;
     switch (F.shape) {
     case 8: fwd_tile<NR, 8>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
     case 7: fwd_tile<NR, 7>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
@@ -343,6 +352,13 @@ k_fwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restr
     default: fwd_tile<NR, 4>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
     }
     task_signal(ctl + 2, F);
+    if (trace && threadIdx.x == 0) {
+        unsigned long long *r = trace + 4 * (size_t)s_task;
+        r[0] = t0;
+        r[1] = t1;
+        r[2] = t2;
+        r[3] = gtime();
+    }
 }
 
 // ---- backward: one CTA = `shape` columns of one front, 8 * CW at a time (one warp per CW columns, a lane
@@ -467,10 +483,11 @@ template <int NR>
 __global__ void __launch_bounds__(NTHR)
 k_bwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restrict__ Mb,
             const int *__restrict__ rows, const double *Yd, double *X, const int *__restrict__ perm,
-            double *__restrict__ x_out, const int *skip, int v_cap) {
+            double *__restrict__ x_out, const int *skip, int v_cap, unsigned long long *trace) {
     extern __shared__ __align__(128) double sm[];
     __shared__ PipeBars B;
     __shared__ int s_task;
+    const unsigned long long t0 = trace ? gtime() : 0;
     if (threadIdx.x == 0) s_task = atomicAdd(ctl + 1, 1);
     pipe_init(B);
     const SweepTask F = load_task(tasks + s_task);
@@ -506,13 +523,22 @@ k_bwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restr
         if (threadIdx.x == NCONS) produce(0x7fffffff);
         return;
     }
+    const unsigned long long t1 = trace ? gtime() : 0;
     task_wait(ctl + 2, F);  // the parent's (hence every ancestor's) x is written
+    const unsigned long long t2 = trace ? gtime() : 0;
     switch (F.cw) {
     case 4: bwd_task<NR, 4>(F, rows, Yd, X, perm, x_out, v_cap, sm, B); break;
     case 2: bwd_task<NR, 2>(F, rows, Yd, X, perm, x_out, v_cap, sm, B); break;
     default: bwd_task<NR, 1>(F, rows, Yd, X, perm, x_out, v_cap, sm, B); break;
     }
     task_signal(ctl + 2, F);
+    if (trace && threadIdx.x == 0) {
+        unsigned long long *r = trace + 4 * (size_t)s_task;
+        r[0] = t0;
+        r[1] = t1;
+        r[2] = t2;
+        r[3] = gtime();
+    }
 }
 
 // Tile-major copy of the front matrices for the forward sweep: one CTA per forward task.
@@ -675,6 +701,7 @@ void ldlt_dev_destroy(LdltDev *f) {
     cudaFree(f->X);
     cudaFree(f->U);
     cudaFree(f->ctl);
+    cudaFree(f->trace);
     delete f;
 }
 
@@ -920,15 +947,23 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     for (int l = 0; l < nlev; ++l) {
         for (int b : by_level[l]) {
             const int m = fr[b].ns + fr[b].k;
+            std::vector<SweepTask> tiles;
             for (int r0 = 0; r0 < m;) {
                 const int shape = std::min(lrt[b], std::max(4, ceil_log2(m - r0)));
                 SweepTask t = make_task(b, true, r0, shape);
                 t.wait_idx = b;
                 t.signal_idx = parent[b];
-                tasks.push_back(t);
+                tiles.push_back(t);
                 ntiles_f[b]++;
                 r0 += 1 << shape;
             }
+            // longest first: a tile of the diagonal block only has the columns up to its last row
+            std::stable_sort(tiles.begin(), tiles.end(), [](const SweepTask &x, const SweepTask &y) {
+                const int64_t wx = (int64_t)std::min(x.ns, x.start + (1 << x.shape)) << x.shape;
+                const int64_t wy = (int64_t)std::min(y.ns, y.start + (1 << y.shape)) << y.shape;
+                return wx > wy;
+            });
+            tasks.insert(tasks.end(), tiles.begin(), tiles.end());
         }
     }
     f->n_ftasks = (int)tasks.size();
@@ -970,6 +1005,14 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         tasks[i].need = parent[b] >= 0 ? ntasks_b[parent[b]] : 0;
     }
     f->n_ctl = 2 + 2 * nb;
+    if (getenv("AAADMM_LDLT_TRACE")) {  // developer aid: per-task time stamps (start, ring primed, dependencies met, done)
+        cudaMalloc((void **)&f->trace, sizeof(unsigned long long) * 4 * tasks.size());
+        cudaMemset(f->trace, 0, sizeof(unsigned long long) * 4 * tasks.size());
+        f->host_tasks = tasks;
+        f->host_level.assign(tasks.size(), 0);
+        for (size_t i = 0; i < tasks.size(); ++i)
+            f->host_level[i] = level[i < (size_t)f->n_ftasks ? tasks[i].wait_idx : tasks[i].signal_idx - nb];
+    }
 
     std::vector<int> permv(perm, perm + n), iperm(std::max(n, 1));
     for (int k = 0; k < n; ++k) iperm[perm[k]] = k;
@@ -1090,10 +1133,34 @@ static int apply_impl(LdltDev *f, double *x_out, cudaStream_t s, const int *skip
     G.idx = f->gidx;
     const size_t ring = (size_t)NSTG * STG * sizeof(double);
     AAADMM_CUDA_OK(launch_sweep(k_fwd_front<NR>, f->n_ftasks, ring + (size_t)f->ws_cap * NR * sizeof(double), s, f->tasks, f->ctl,
-                                f->Mf, G, f->W, f->dinv, f->Yd, f->U, skip, f->ws_cap));
+                                f->Mf, G, f->W, f->dinv, f->Yd, f->U, skip, f->ws_cap, f->trace));
     AAADMM_CUDA_OK(launch_sweep(k_bwd_front<NR>, f->n_btasks, ring + (size_t)f->v_cap * NR * sizeof(double), s,
-                                f->tasks + f->n_ftasks, f->ctl, f->Mb, f->rows, f->Yd, f->X, f->perm, x_out, skip, f->v_cap));
+                                f->tasks + f->n_ftasks, f->ctl, f->Mb, f->rows, f->Yd, f->X, f->perm, x_out, skip, f->v_cap,
+                                f->trace ? f->trace + 4 * (size_t)f->n_ftasks : nullptr));
     AAADMM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int ldlt_dev_dump_trace(LdltDev *f, const char *path) {
+    if (!f->trace) {
+        set_last_error("ldlt trace: set AAADMM_LDLT_TRACE before creating the factor");
+        return -1;
+    }
+    const size_t nt = f->host_tasks.size();
+    std::vector<unsigned long long> t(4 * nt);
+    AAADMM_CUDA_OK(cudaMemcpy(t.data(), f->trace, sizeof(unsigned long long) * 4 * nt, cudaMemcpyDeviceToHost));
+    FILE *fp = fopen(path, "w");
+    if (!fp) {
+        set_last_error("ldlt trace: cannot open the output file");
+        return -1;
+    }
+    fprintf(fp, "task,sweep,level,first,ns,k,start,shape,cw,need,t_start,t_primed,t_deps,t_done\n");
+    for (size_t i = 0; i < nt; ++i) {
+        const SweepTask &k = f->host_tasks[i];
+        fprintf(fp, "%zu,%s,%d,%d,%d,%d,%d,%d,%d,%d,%llu,%llu,%llu,%llu\n", i, i < (size_t)f->n_ftasks ? "fwd" : "bwd", f->host_level[i],
+                k.first, k.ns, k.k, k.start, k.shape, k.cw, k.need, t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
+    }
+    fclose(fp);
     return 0;
 }
 

@@ -62,6 +62,9 @@ struct LdltDev {
     int ws_cap = 0, v_cap = 0;   // staged columns (forward) / rows (backward) per chunk
     int *ctl = nullptr;          // [0], [1]: next forward / backward task; then one arrival counter per front and sweep
     int n_ctl = 0;
+    unsigned long long *trace = nullptr;  // AAADMM_LDLT_TRACE: 4 time stamps per task
+    std::vector<SweepTask> host_tasks;
+    std::vector<int> host_level;
     // work vectors: W = permuted rhs, Yd = D^-1 L^-1 rhs, X = solution (elimination order), U = front updates
     double *W = nullptr, *Yd = nullptr, *X = nullptr, *U = nullptr;
     LdltStats stats;
@@ -71,6 +74,9 @@ struct LdltDev {
 int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, const double *Lx,
                     const double *D, const int *perm, int nrhs);
 void ldlt_dev_destroy(LdltDev *f);
+
+// Developer aid (AAADMM_LDLT_TRACE=1 at creation): per-task time stamps of the last apply as CSV.
+int ldlt_dev_dump_trace(LdltDev *f, const char *path);
 
 // W (permuted rhs, n x nrhs interleaved) must already be filled. Result is written to
 // x_out[perm[i]*nrhs + r] (original order) on `stream`.

@@ -66,6 +66,9 @@ int aaadmm_ldlt_destroy(aaadmm_ldlt *f);
 int aaadmm_ldlt_solve(aaadmm_ldlt *f, const double *b, double *x);          /* host vectors */
 int aaadmm_ldlt_solve_dev(aaadmm_ldlt *f, const double *d_b, double *d_x);  /* device vectors */
 /* stats[0..7] = n, blocks, levels, max_block, nnz_L, nnz_offblock, dense_diag_entries, bytes_per_solve */
+/* Developer aid: with AAADMM_LDLT_TRACE=1 in the environment at creation, writes the per-task time stamps
+ * (globaltimer ns: start, ring primed, dependencies met, done) of the last apply as CSV. */
+int aaadmm_ldlt_dump_trace(aaadmm_ldlt *h, const char *path);
 int aaadmm_ldlt_stats(aaadmm_ldlt *f, double *stats8);
 
 /* ------------------------------------------------------------------------------------------

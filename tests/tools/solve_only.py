@@ -18,3 +18,8 @@ for r in range(reps):
     t0 = time.perf_counter()
     L.aaadmm_ldlt_solve(f, b.ctypes.data_as(A.c_dp), x.ctypes.data_as(A.c_dp))
     print("solve wall ms", 1e3 * (time.perf_counter() - t0))
+
+if os.environ.get("AAADMM_LDLT_TRACE"):
+    os.makedirs("gpurun_out", exist_ok=True)
+    L.aaadmm_ldlt_dump_trace.argtypes = [C.c_void_p, C.c_char_p]
+    print("trace rc", L.aaadmm_ldlt_dump_trace(f, b"gpurun_out/ldlt_trace.csv"))
