@@ -273,8 +273,12 @@ def run_gpu(args):
     phases = {k: v for k, v in prof.items() if k != "total" and v["ms"] > 0}
     dom = max(phases, key=lambda k: phases[k]["ms"])
     ach = phases[dom]["bytes"] / (phases[dom]["ms"] * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of one apply (k_fwd_front + k_bwd_front) from the committed
+    # `ncu --set full` capture of this workload: profiles/r01b_ncu_full_summary.md
+    traffic = NCU_LDLT_TRAFFIC_BYTES if dom == "ldlt_apply" else None
     roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": traffic, "peak_source": peak_src,
+            "kernel_launches": "ldlt_apply = k_fwd_front + k_bwd_front (one launch per sweep)" if dom == "ldlt_apply" else dom,
             "phases": {k: {"ms": round(v["ms"], 4), "algo_GB": round(v["bytes"] / 1e9, 4),
                            "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)} for k, v in phases.items()}}
     cpu = cpu_baseline_leg() if (world == 1 and not args.no_cpu) else None
@@ -297,6 +301,9 @@ def run_gpu(args):
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+NCU_LDLT_TRAFFIC_BYTES = 2.224e9
 
 
 def main():
