@@ -81,6 +81,8 @@ constexpr int NCONS = CTA;          // consumer threads
 constexpr int NTHR = CTA + 32;      // + producer warp
 constexpr int STG = 2048;           // doubles per stage (16 KB)
 constexpr int NSTG = 3;
+constexpr int WCH = 512;            // wide fronts: columns / rows of the assembled vector per half buffer
+constexpr int ACOLS = 256;          // entries one assemble task handles
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
@@ -149,6 +151,7 @@ __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 256;\n" 
 
 struct PipeBars {
     uint64_t full[NSTG], empty[NSTG];
+    uint64_t wfull[2];  // the two halves of the vector buffer of a wide front
 };
 __device__ __forceinline__ void pipe_init(PipeBars &B) {
     if (threadIdx.x == 0) {
@@ -157,6 +160,8 @@ __device__ __forceinline__ void pipe_init(PipeBars &B) {
             mbar_init(&B.full[i], 1);
             mbar_init(&B.empty[i], NCONS / 32);
         }
+        mbar_init(&B.wfull[0], 1);
+        mbar_init(&B.wfull[1], 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -173,7 +178,7 @@ __device__ __forceinline__ void pipe_drain(PipeBars &B, int issued) {
 // j of the tile at offset j * RT), so one stage = STG / RT columns = ONE bulk copy.
 template <int NR, int LRT>
 __device__ __forceinline__ void fwd_tile(const SweepTask &F, const Gather &G,
-                                         const double *__restrict__ W, const double *__restrict__ dinv,
+                                         const double *W, const double *__restrict__ dinv,
                                          double *__restrict__ Yd, double *U, int ws_cap, double *sm, PipeBars &B) {
     constexpr int RT = 1 << LRT, CS = (2 * CTA) >> LRT, NCS = STG / RT, PER = NCS / CS;
     static_assert(PER >= 1, "stage narrower than the slices");
@@ -194,8 +199,30 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const Gather &G,
     const bool fin = (int)threadIdx.x < RT && frow < m;
     if (fin && frow >= F.ns) gather_add<NR>(G, F.g_off + frow, U, 1.0, pass);
     int it = 0;
-    for (int jc = 0; jc < ncols; jc += ws_cap) {
-        const int jn = min(ncols - jc, ws_cap);
+    // Wide fronts (F.cw != 0): w was assembled in place in W by the front's assemble tasks; it arrives in
+    // halves of WCH columns by bulk copy, the next half in flight while this one is used.
+    const bool wide = F.cw != 0;
+    const int chunk = wide ? WCH : ws_cap;
+    constexpr int HALF = WCH * NR + 2;
+    auto issue_w = [&](int c) {
+        const int jc = c * WCH;
+        const size_t idx = (size_t)(F.first + jc) * NR;
+        const int sh = (int)(idx & 1);  // bulk copies want 16-byte aligned sources
+        const unsigned bytes = (unsigned)(((min(ncols - jc, WCH) * NR + sh + 1) & ~1) * 8);
+        mbar_expect_tx(&B.wfull[c & 1], bytes);
+        bulk_g2s(ws + (c & 1) * HALF, W + idx - sh, bytes, &B.wfull[c & 1]);
+    };
+    if (wide && threadIdx.x == 0) {
+        issue_w(0);
+        if (WCH < ncols) issue_w(1);
+    }
+    for (int jc = 0, ci = 0; jc < ncols; jc += chunk, ++ci) {
+        const int jn = min(ncols - jc, chunk);
+        const double *wbase = ws;
+        if (wide) {
+            mbar_wait(&B.wfull[ci & 1], (ci >> 1) & 1);
+            wbase = ws + (ci & 1) * HALF + (((size_t)(F.first + jc) * NR) & 1);
+        } else {
         if (jc > 0) cons_sync();
         // w_j = rhs_j - sum of the child updates that land on column j (4 columns per thread in flight)
         for (int j0 = threadIdx.x; j0 < jn; j0 += 4 * NCONS) {
@@ -235,13 +262,14 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const Gather &G,
             }
         }
         cons_sync();
-        // the stages whose columns fall into this chunk (ws_cap is a multiple of NCS)
+        }
+        // the stages whose columns fall into this chunk (chunks are multiples of NCS)
         const int je = jc + jn;
         for (; it * NCS < je; ++it) {
             const int slot = it % NSTG;
             mbar_wait(&B.full[slot], (it / NSTG) & 1);
             const double *st = ring + (size_t)slot * STG + 2 * lp;
-            const double *wp = ws + (size_t)(it * NCS - jc) * NR;
+            const double *wp = wbase + (size_t)(it * NCS - jc) * NR;
             const int colsin = ncols - it * NCS;
             if (colsin >= NCS) {
 #pragma unroll
@@ -272,6 +300,10 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const Gather &G,
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&B.empty[slot]);
+        }
+        if (wide) {
+            cons_sync();  // everyone is done with this half
+            if (threadIdx.x == 0 && (ci + 2) * WCH < ncols) issue_w(ci + 2);
         }
     }
     cons_sync();  // every consumer is done with the ring
@@ -305,7 +337,7 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const Gather &G,
 template <int NR>
 __global__ void __launch_bounds__(NTHR)
 k_fwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restrict__ Mf,
-            Gather G, const double *__restrict__ W, const double *__restrict__ dinv, double *__restrict__ Yd, double *U,
+            Gather G, double *W, const double *__restrict__ dinv, double *__restrict__ Yd, double *U,
             const int *skip, int ws_cap, unsigned long long *trace) {
     extern __shared__ __align__(128) double sm[];
     __shared__ PipeBars B;
@@ -319,7 +351,7 @@ k_fwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restr
     // level is known to be finished
     const int RT = 1 << F.shape, NCS = STG / RT;
     const int ncols = min(F.ns, F.start + RT);
-    const int nstages = (ncols + NCS - 1) / NCS;
+    const int nstages = F.shape == 0 ? 0 : (ncols + NCS - 1) / NCS;  // shape 0: assemble task, no factor data
     const double *tile = Mf + F.m_off;
     auto produce = [&](int it) {
         const int slot = it % NSTG;
@@ -344,6 +376,18 @@ k_fwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restr
     const unsigned long long t1 = trace ? gtime() : 0;
     task_wait(ctl + 2, F);  // the children's updates are written
     const unsigned long long t2 = trace ? gtime() : 0;
+    if (F.shape == 0) {
+        // assemble task of a wide front: w_j = rhs_j - (child updates landing on column j), in place in W
+        const int j = F.start + (int)threadIdx.x;
+        if ((int)threadIdx.x < ACOLS && j < F.ns) {
+            double a[NR];
+#pragma unroll
+            for (int q = 0; q < NR; ++q) a[q] = __ldcg(W + (size_t)(F.first + j) * NR + q);
+            gather_add<NR>(G, F.g_off + j, U, -1.0, a);
+#pragma unroll
+            for (int q = 0; q < NR; ++q) W[(size_t)(F.first + j) * NR + q] = a[q];
+        }
+    } else
     switch (F.shape) {
     case 8: fwd_tile<NR, 8>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
     case 7: fwd_tile<NR, 7>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
@@ -366,8 +410,8 @@ k_fwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restr
 // backward copy of the front matrices, stage blocks in the order they are used): ONE bulk copy. ----
 template <int NR, int CW>
 __device__ __forceinline__ void bwd_task(const SweepTask &F, const int *__restrict__ rows, const double *Yd, double *X,
-                                         const int *__restrict__ perm, double *__restrict__ x_out, int v_cap, double *sm,
-                                         PipeBars &B) {
+                                         const double *Va, const int *__restrict__ perm, double *__restrict__ x_out,
+                                         int v_cap, double *sm, PipeBars &B) {
     constexpr int NC = 8 * CW, RB = STG / NC;  // columns per pass, rows per stage
     double *ring = sm;                     // [NSTG][NC][RB]
     double *vs = sm + (size_t)NSTG * STG;  // v[v_cap][NR]
@@ -375,6 +419,21 @@ __device__ __forceinline__ void bwd_task(const SweepTask &F, const int *__restri
     const int cend = min(F.ns, c0 + F.shape);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool single = (F.ld - c0) <= v_cap;  // v fits at once: staged once, several column passes allowed
+    // Wide fronts (F.cw & 8): v was assembled once per front in Va by the front's assemble tasks and arrives
+    // in halves of WCH rows by bulk copy, the next half in flight while this one is used.
+    const bool wide = (F.cw & 8) != 0;
+    const int chunk = wide ? WCH : v_cap;
+    constexpr int HALF = WCH * NR + 2;
+    auto issue_v = [&](int c) {
+        const int rc = c0 + c * WCH;
+        const unsigned bytes = (unsigned)(((min(F.ld - rc, WCH) * NR + 1) & ~1) * 8);
+        mbar_expect_tx(&B.wfull[c & 1], bytes);
+        bulk_g2s(vs + (c & 1) * HALF, Va + (size_t)(F.u_off + rc) * NR, bytes, &B.wfull[c & 1]);
+    };
+    if (wide && threadIdx.x == 0) {
+        issue_v(0);
+        if (c0 + WCH < F.ld) issue_v(1);
+    }
     int it = 0;
     for (int jb0 = c0; jb0 < cend; jb0 += NC) {
         const int jb = jb0 + warp * CW;
@@ -384,9 +443,13 @@ __device__ __forceinline__ void bwd_task(const SweepTask &F, const int *__restri
         for (int c = 0; c < CW; ++c)
 #pragma unroll
             for (int q = 0; q < NR; ++q) acc[c][q] = 0.0;
-        for (int rc = c0; rc < F.ld; rc += v_cap) {
-            const int re = min(F.ld, rc + v_cap);
-            if (!(single && jb0 > c0)) {
+        for (int rc = c0, ci = 0; rc < F.ld; rc += chunk, ++ci) {
+            const int re = min(F.ld, rc + chunk);
+            const double *vbase = vs;
+            if (wide) {
+                mbar_wait(&B.wfull[ci & 1], (ci >> 1) & 1);
+                vbase = vs + (ci & 1) * HALF;
+            } else if (!(single && jb0 > c0)) {
                 if (rc > c0) cons_sync();
                 // v = [ D^-1 y of the front's columns ; -x of the rows below ; 0 ] (4 rows per thread in flight)
                 for (int r0 = rc + threadIdx.x; r0 < re; r0 += 4 * NCONS) {
@@ -430,7 +493,7 @@ __device__ __forceinline__ void bwd_task(const SweepTask &F, const int *__restri
                 mbar_wait(&B.full[slot], (it / NSTG) & 1);
                 const int nrow = min(RB, F.ld - rr);
                 const double *st = ring + (size_t)slot * STG + (warp * CW) * nrow;  // block = [ncol][nrow]
-                const double *vp = vs + (size_t)(rr - rc) * NR;
+                const double *vp = vbase + (size_t)(rr - rc) * NR;
 #pragma unroll
                 for (int t = 0; t < RB / 64; ++t) {
                     const int r = 64 * t + 2 * lane;
@@ -454,6 +517,10 @@ __device__ __forceinline__ void bwd_task(const SweepTask &F, const int *__restri
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&B.empty[slot]);
+            }
+            if (wide) {
+                cons_sync();  // everyone is done with this half
+                if (threadIdx.x == 0 && c0 + (ci + 2) * WCH < F.ld) issue_v(ci + 2);
             }
         }
 #pragma unroll
@@ -482,7 +549,7 @@ __device__ __forceinline__ void bwd_task(const SweepTask &F, const int *__restri
 template <int NR>
 __global__ void __launch_bounds__(NTHR)
 k_bwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restrict__ Mb,
-            const int *__restrict__ rows, const double *Yd, double *X, const int *__restrict__ perm,
+            const int *__restrict__ rows, const double *Yd, double *X, double *Va, const int *__restrict__ perm,
             double *__restrict__ x_out, const int *skip, int v_cap, unsigned long long *trace) {
     extern __shared__ __align__(128) double sm[];
     __shared__ PipeBars B;
@@ -492,7 +559,7 @@ k_bwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restr
     pipe_init(B);
     const SweepTask F = load_task(tasks + s_task);
     pdl_launch_dependents();
-    const int NC = 8 * F.cw, RB = STG / NC;
+    const int NC = max(8 * (F.cw & 7), 8), RB = STG / NC;  // cw == 0: assemble task (shape 0: no columns)
     const int c0 = F.start, cend = min(F.ns, c0 + F.shape);
     // producer state: the task's stage blocks lie one after the other in Mb, in the order they are used
     const double *psrc = Mb + F.m_off;
@@ -526,10 +593,30 @@ k_bwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restr
     const unsigned long long t1 = trace ? gtime() : 0;
     task_wait(ctl + 2, F);  // the parent's (hence every ancestor's) x is written
     const unsigned long long t2 = trace ? gtime() : 0;
-    switch (F.cw) {
-    case 4: bwd_task<NR, 4>(F, rows, Yd, X, perm, x_out, v_cap, sm, B); break;
-    case 2: bwd_task<NR, 2>(F, rows, Yd, X, perm, x_out, v_cap, sm, B); break;
-    default: bwd_task<NR, 1>(F, rows, Yd, X, perm, x_out, v_cap, sm, B); break;
+    switch (F.cw & 7) {
+    case 0: {
+        // assemble task of a wide front: v = [ D^-1 y ; -x(rows below) ; 0 ] for rows start .. start + ACOLS
+        const int r = F.start + (int)threadIdx.x;
+        if ((int)threadIdx.x < ACOLS && r < F.ld) {
+            double a[NR];
+#pragma unroll
+            for (int q = 0; q < NR; ++q) a[q] = 0.0;
+            if (r < F.ns) {
+#pragma unroll
+                for (int q = 0; q < NR; ++q) a[q] = __ldcg(Yd + (size_t)(F.first + r) * NR + q);
+            } else if (r < F.ns + F.k) {
+                const size_t i = (size_t)__ldg(rows + F.g_off + r - F.ns) * NR;
+#pragma unroll
+                for (int q = 0; q < NR; ++q) a[q] = -__ldcg(X + i + q);
+            }
+#pragma unroll
+            for (int q = 0; q < NR; ++q) Va[(size_t)(F.u_off + r) * NR + q] = a[q];
+        }
+        break;
+    }
+    case 4: bwd_task<NR, 4>(F, rows, Yd, X, Va, perm, x_out, v_cap, sm, B); break;
+    case 2: bwd_task<NR, 2>(F, rows, Yd, X, Va, perm, x_out, v_cap, sm, B); break;
+    default: bwd_task<NR, 1>(F, rows, Yd, X, Va, perm, x_out, v_cap, sm, B); break;
     }
     task_signal(ctl + 2, F);
     if (trace && threadIdx.x == 0) {
@@ -546,6 +633,7 @@ __global__ void __launch_bounds__(256)
 k_make_tiles(const SweepTask *__restrict__ tasks, const int64_t *__restrict__ src_off, const double *__restrict__ M,
              double *__restrict__ Mf) {
     const SweepTask F = tasks[blockIdx.x];
+    if (F.shape == 0) return;  // assemble task: no factor data
     const int RT = 1 << F.shape, r0 = F.start;
     const int ncols = min(F.ns, r0 + RT);
     const double *src = M + src_off[blockIdx.x];
@@ -562,7 +650,8 @@ __global__ void __launch_bounds__(256)
 k_make_btiles(const SweepTask *__restrict__ tasks, const int64_t *__restrict__ src_off, const double *__restrict__ M,
               double *__restrict__ Mb) {
     const SweepTask F = tasks[blockIdx.x];
-    const int NC = 8 * F.cw, RB = STG / NC;
+    if ((F.cw & 7) == 0) return;  // assemble task: no factor data
+    const int NC = 8 * (F.cw & 7), RB = STG / NC;
     const int c0 = F.start, cend = min(F.ns, c0 + F.shape);
     const double *src = M + src_off[blockIdx.x];
     double *dst = Mb + F.m_off;
@@ -701,6 +790,7 @@ void ldlt_dev_destroy(LdltDev *f) {
     cudaFree(f->X);
     cudaFree(f->U);
     cudaFree(f->ctl);
+    cudaFree(f->Va);
     cudaFree(f->trace);
     delete f;
 }
@@ -863,6 +953,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     // CTA takes `ncols` columns, each warp CW of them at a time. Tree levels with few fronts are cut finer
     // until they have at least min_ctas tasks. One launch per sweep: the tasks are listed in topological
     // order (forward bottom-up, backward top-down) and synchronise through per-front arrival counters.
+    const bool wide_on = env_int("AAADMM_WIDE", 1) != 0;
     const int min_ctas = env_int("AAADMM_MIN_CTAS", 148);  // one CTA per SM; each keeps 48 KB of loads in flight
     const int tile_entries = env_int("AAADMM_TILE_ENTRIES", 32768);
     std::vector<std::vector<int>> by_level(nlev);
@@ -897,8 +988,9 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         max_ns_all = std::max(max_ns_all, fr[b].ns);
         max_ld_all = std::max(max_ld_all, fr[b].ld);
     }
-    const int ws_cap = std::min((max_ns_all + 127) & ~127, FCH);
-    const int v_cap = std::min((max_ld_all + 255) & ~255, BCH);
+    // chunk capacities (the environment overrides, multiples of 128 / 256 not above the defaults, are for tests)
+    const int ws_cap = std::min((max_ns_all + 127) & ~127, std::min(FCH, env_int("AAADMM_FCH", FCH)));
+    const int v_cap = std::min((max_ld_all + 255) & ~255, std::min(BCH, env_int("AAADMM_BCH", BCH)));
     f->ws_cap = ws_cap;
     f->v_cap = v_cap;
     std::vector<int> lrt(std::max(nb, 1), 8), bcols(std::max(nb, 1), 32);
@@ -947,11 +1039,25 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     for (int l = 0; l < nlev; ++l) {
         for (int b : by_level[l]) {
             const int m = fr[b].ns + fr[b].k;
+            // wide fronts: assemble tasks write w once; the tiles wait for them and receive w by bulk copy
+            const bool wide = wide_on && fr[b].ns > ws_cap;
+            int n_asm = 0;
+            if (wide)
+                for (int j0 = 0; j0 < fr[b].ns; j0 += ACOLS, ++n_asm) {
+                    SweepTask t = make_task(b, true, j0, 0);
+                    t.wait_idx = b;
+                    t.need = -1;
+                    t.signal_idx = 2 * nb + b;
+                    t.cw = 0;
+                    tasks.push_back(t);
+                }
             std::vector<SweepTask> tiles;
             for (int r0 = 0; r0 < m;) {
                 const int shape = std::min(lrt[b], std::max(4, ceil_log2(m - r0)));
                 SweepTask t = make_task(b, true, r0, shape);
-                t.wait_idx = b;
+                t.wait_idx = wide ? 2 * nb + b : b;
+                t.need = wide ? n_asm : -1;  // -1: filled in below from the children's tile counts
+                t.cw = wide ? 1 : 0;
                 t.signal_idx = parent[b];
                 tiles.push_back(t);
                 ntiles_f[b]++;
@@ -969,7 +1075,8 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     f->n_ftasks = (int)tasks.size();
     for (int b = 0; b < nb; ++b)
         if (parent[b] >= 0) need_f[parent[b]] += ntiles_f[b];
-    for (int i = 0; i < f->n_ftasks; ++i) tasks[i].need = need_f[tasks[i].wait_idx];
+    for (int i = 0; i < f->n_ftasks; ++i)
+        if (tasks[i].need < 0) tasks[i].need = need_f[tasks[i].wait_idx];
     // tile-major copy for the forward sweep: the tile of a task is contiguous (column j at j * RT)
     std::vector<int64_t> tile_src(tasks.size());
     int64_t mf_tot = 0;
@@ -982,12 +1089,34 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     }
     // stage-major copy for the backward sweep
     int64_t mb_tot = 0;
+    int64_t va_tot = 0;
+    std::vector<int> n_asm_b(std::max(nb, 1), -1);
     for (int l = nlev - 1; l >= 0; --l) {
-        for (int b : by_level[l])
+        for (int b : by_level[l]) {
+            // wide fronts: assemble tasks write v once into Va; the column tasks receive it by bulk copy
+            const bool wide = wide_on && fr[b].ld > v_cap;
+            int64_t va_off = 0;
+            if (wide) {
+                va_off = va_tot;
+                va_tot += (fr[b].ld + 1) & ~1;
+                n_asm_b[b] = 0;
+                for (int r0 = 0; r0 < fr[b].ld; r0 += ACOLS, ++n_asm_b[b]) {
+                    SweepTask t = make_task(b, false, r0, 0);
+                    t.cw = 0;
+                    t.u_off = va_off;
+                    t.wait_idx = nb + std::max(parent[b], 0);
+                    t.need = -1;  // the parent's column chunks, filled in below
+                    t.signal_idx = 3 * nb + b;
+                    tile_src.push_back(0);
+                    tasks.push_back(t);
+                }
+            }
             for (int c0 = 0; c0 < fr[b].ns; c0 += bcols[b]) {
                 SweepTask t = make_task(b, false, c0, bcols[b]);
-                t.cw = bcw[l];
-                t.wait_idx = nb + std::max(parent[b], 0);
+                t.cw = bcw[l] | (wide ? 8 : 0);
+                t.u_off = va_off;
+                t.wait_idx = wide ? 3 * nb + b : nb + std::max(parent[b], 0);
+                t.need = wide ? n_asm_b[b] : -1;
                 t.signal_idx = nb + b;
                 tile_src.push_back(t.m_off);
                 t.m_off = mb_tot;
@@ -998,13 +1127,15 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
                 tasks.push_back(t);
                 ntasks_b[b]++;
             }
+        }
     }
     f->n_btasks = (int)tasks.size() - f->n_ftasks;
     for (size_t i = f->n_ftasks; i < tasks.size(); ++i) {
-        const int b = tasks[i].signal_idx - nb;
+        if (tasks[i].need >= 0) continue;
+        const int b = tasks[i].signal_idx >= 3 * nb ? tasks[i].signal_idx - 3 * nb : tasks[i].signal_idx - nb;
         tasks[i].need = parent[b] >= 0 ? ntasks_b[parent[b]] : 0;
     }
-    f->n_ctl = 2 + 2 * nb;
+    f->n_ctl = 2 + 4 * nb;  // + one 'assembled' counter per front and sweep (wide fronts)
     if (getenv("AAADMM_LDLT_TRACE")) {  // developer aid: per-task time stamps (start, ring primed, dependencies met, done)
         cudaMalloc((void **)&f->trace, sizeof(unsigned long long) * 4 * tasks.size());
         cudaMemset(f->trace, 0, sizeof(unsigned long long) * 4 * tasks.size());
@@ -1036,11 +1167,12 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     rc |= upload(&dA, A);
     std::vector<double>().swap(A);
     const size_t mat_bytes = (size_t)std::max<int64_t>(m_tot, 1) * sizeof(double);
-    const size_t vec_bytes = std::max<size_t>((size_t)n * nrhs, 1) * sizeof(double);
+    const size_t vec_bytes = (std::max<size_t>((size_t)n * nrhs, 1) + 2) * sizeof(double);  // + slack for aligned bulk copies
     const size_t u_bytes = std::max<size_t>((size_t)r_tot * nrhs, 1) * sizeof(double);
     if (rc || cudaMalloc((void **)&f->M, mat_bytes) != cudaSuccess || cudaMalloc((void **)&f->W, vec_bytes) != cudaSuccess ||
         cudaMalloc((void **)&f->Yd, vec_bytes) != cudaSuccess || cudaMalloc((void **)&f->X, vec_bytes) != cudaSuccess ||
-        cudaMalloc((void **)&f->U, u_bytes) != cudaSuccess || cudaMalloc((void **)&f->ctl, sizeof(int) * f->n_ctl) != cudaSuccess) {
+        cudaMalloc((void **)&f->U, u_bytes) != cudaSuccess || cudaMalloc((void **)&f->ctl, sizeof(int) * f->n_ctl) != cudaSuccess ||
+        cudaMalloc((void **)&f->Va, (std::max<size_t>((size_t)va_tot * nrhs, 1) + 2) * sizeof(double)) != cudaSuccess) {
         set_last_error("ldlt: cudaMalloc failed");
         cudaFree(dA);
         ldlt_dev_destroy(f);
@@ -1132,10 +1264,10 @@ static int apply_impl(LdltDev *f, double *x_out, cudaStream_t s, const int *skip
     G.ptr = f->gptr;
     G.idx = f->gidx;
     const size_t ring = (size_t)NSTG * STG * sizeof(double);
-    AAADMM_CUDA_OK(launch_sweep(k_fwd_front<NR>, f->n_ftasks, ring + (size_t)f->ws_cap * NR * sizeof(double), s, f->tasks, f->ctl,
+    AAADMM_CUDA_OK(launch_sweep(k_fwd_front<NR>, f->n_ftasks, ring + (std::max<size_t>((size_t)f->ws_cap * NR, 2 * (WCH * NR + 2)) + 8) * sizeof(double), s, f->tasks, f->ctl,
                                 f->Mf, G, f->W, f->dinv, f->Yd, f->U, skip, f->ws_cap, f->trace));
-    AAADMM_CUDA_OK(launch_sweep(k_bwd_front<NR>, f->n_btasks, ring + (size_t)f->v_cap * NR * sizeof(double), s,
-                                f->tasks + f->n_ftasks, f->ctl, f->Mb, f->rows, f->Yd, f->X, f->perm, x_out, skip, f->v_cap,
+    AAADMM_CUDA_OK(launch_sweep(k_bwd_front<NR>, f->n_btasks, ring + (std::max<size_t>((size_t)f->v_cap * NR, 2 * (WCH * NR + 2)) + 8) * sizeof(double), s,
+                                f->tasks + f->n_ftasks, f->ctl, f->Mb, f->rows, f->Yd, f->X, f->Va, f->perm, x_out, skip, f->v_cap,
                                 f->trace ? f->trace + 4 * (size_t)f->n_ftasks : nullptr));
     AAADMM_CUDA_OK(cudaGetLastError());
     return 0;

@@ -67,6 +67,7 @@ struct LdltDev {
     std::vector<int> host_level;
     // work vectors: W = permuted rhs, Yd = D^-1 L^-1 rhs, X = solution (elimination order), U = front updates
     double *W = nullptr, *Yd = nullptr, *X = nullptr, *U = nullptr;
+    double *Va = nullptr;  // wide fronts: [D^-1 y ; -x(rows below) ; 0] assembled once per front (backward sweep)
     LdltStats stats;
 };
 

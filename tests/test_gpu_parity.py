@@ -113,6 +113,68 @@ def test_ldlt_apply_vs_host_factor(gpu):
         print(dev.stats())
 
 
+def _grid_system(nx, ny, nz, seed):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    n = nx * ny * nz
+    idx = np.arange(n).reshape(nx, ny, nz)
+    coords = np.stack(np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij"), -1).reshape(-1, 3).astype(float)
+    r, c, v = [], [], []
+    diag = rng.uniform(0.1, 1.0, n)
+    # 3-D grid with face diagonals (the vertex adjacency of a 5-tet cube split)
+    for off in [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (1, 0, 1), (0, 1, 1)]:
+        a = idx[: nx - off[0], : ny - off[1], : nz - off[2]].ravel()
+        b = idx[off[0]:, off[1]:, off[2]:].ravel()
+        w = rng.uniform(0.5, 2.0, a.size)
+        r += [a, b]
+        c += [b, a]
+        v += [-w, -w]
+        np.add.at(diag, a, w)
+        np.add.at(diag, b, w)
+    r.append(np.arange(n)); c.append(np.arange(n)); v.append(diag)
+    A = sp.csc_matrix((np.concatenate(v), (np.concatenate(r), np.concatenate(c))), shape=(n, n))
+    L = sp.tril(A, format="csc")
+    return n, coords, A, L
+
+
+@pytest.mark.parametrize("env", [
+    {},                                                                  # product defaults
+    {"AAADMM_FCH": "128", "AAADMM_BCH": "256"},                          # fronts > 128 columns take the assembled-vector path
+    {"AAADMM_FCH": "128", "AAADMM_BCH": "256", "AAADMM_MIN_CTAS": "4000"},  # smallest tiles, one column per warp
+    {"AAADMM_KSMALL": "8", "AAADMM_WIDE": "0"},                          # fundamental supernodes only, chunked gathers
+    {"AAADMM_KSMALL": "200", "AAADMM_MIN_CTAS": "1"},                    # heavily relaxed fronts, largest tiles
+])
+def test_ldlt_apply_front_shapes(gpu, env):
+    """The multifrontal sweeps under every tile shape / chunking / wide-front path: residual of A x = b and
+    agreement with the host substitution on a 24 x 20 x 18 grid (top separator 360 columns)."""
+    import os
+    import scipy.sparse.linalg as spla
+    A = gpu
+    n, coords, Amat, L = _grid_system(24, 20, 18, 5)
+    hf = A.HostFactor(n, L.indptr, L.indices, L.data, coords, leaf_size=32)
+    Lp, Li, Lx, D, perm = hf.arrays()
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        rng = np.random.default_rng(11)
+        for nrhs in (3, 1):
+            dev = A.Ldlt(n, Lp, Li, Lx, D, perm, nrhs)
+            for rep in range(2):  # the second apply reuses the counters / work vectors
+                b = rng.standard_normal(n * nrhs)
+                x = dev.solve(b)
+                xh = hf.solve(b, nrhs)
+                res = Amat @ x.reshape(n, nrhs) - b.reshape(n, nrhs)
+                assert np.abs(res).max() < 1e-10 * np.abs(b).max(), (env, nrhs)
+                assert np.abs(x - xh).max() < 1e-11 * np.abs(xh).max(), (env, nrhs)
+            print(env, dev.stats())
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 @pytest.mark.parametrize("dims,m,accel", [((12, 3, 3), 5, True), ((12, 3, 3), 0, False), ((16, 4, 4), 5, True)])
 def test_hard_step_vs_reference(gpu, ref, dims, m, accel):
     frames = 2
