@@ -1141,8 +1141,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         cudaMemset(f->trace, 0, sizeof(unsigned long long) * 4 * tasks.size());
         f->host_tasks = tasks;
         f->host_level.assign(tasks.size(), 0);
-        for (size_t i = 0; i < tasks.size(); ++i)
-            f->host_level[i] = level[i < (size_t)f->n_ftasks ? tasks[i].wait_idx : tasks[i].signal_idx - nb];
+        for (size_t i = 0; i < tasks.size(); ++i) f->host_level[i] = level[blk_of[tasks[i].first]];
     }
 
     std::vector<int> permv(perm, perm + n), iperm(std::max(n, 1));
