@@ -371,3 +371,26 @@ def test_cfg1_three_material_beams_hard_vs_reference(gpu, ref):
     print("cfg1(hard) rows", len(hg[0]), len(hr[0]), "comb rel first 5", rel[:5])
     assert rel[:3].max() < 1e-6
     assert np.abs(xg[0] - xr[0]).max() / np.abs(xr[0]).max() < 1e-6
+
+
+def test_ensemble_material_sweep_vs_reference(gpu, ref):
+    """cfg 5 in miniature: independent scenes with the material sweep of `ensemble.scene_material`; every scene's
+    residual history against the unmodified reference, and the result-record table."""
+    from aa_admm_b200 import ensemble as E
+    from scenes import beam_arrays, run_product, run_reference
+    recs = []
+    for s in (0, 13, 42, 63):
+        youngs, poisson = E.scene_material(s)
+        scene = beam_arrays(gpu, 12, 3, 3)
+        sp, hp, xp = run_product(gpu, scene, 1, m=5, youngs=youngs, poisson=poisson)
+        scene_r = beam_arrays(gpu, 12, 3, 3)
+        sr, hr, xr = run_reference(ref, gpu, scene_r, 1, m=5, youngs=youngs, poisson=poisson)
+        a, b = hp[0], hr[0]  # product rows: prim, comb, reject; reference rows: ms, prim, comb, reject
+        n = min(len(a), len(b), 8)
+        assert (np.abs(a[:n, 1] - b[:n, 2]) <= 1e-9 * np.abs(b[:n, 2])).all(), s   # first iterations: round-off only
+        assert (np.abs(a[:n, 0] - b[:n, 1]) <= 1e-9 * np.abs(b[:n, 1])).all(), s
+        assert abs(len(a) - len(b)) <= 0.25 * len(b) + 1
+        assert np.abs(xp[0] - xr[0]).max() <= 1e-6 * np.abs(xr[0]).max()
+        recs.append(E.make_record(s, len(a), a[:, 2].sum(), a[-1, 0], a[-1, 1], sp.info()["loop_ms"], 0.0, 0))
+    table = E.gather_records(np.array(recs))
+    assert table.shape == (4, len(E.RECORD_FIELDS)) and list(table[:, 0]) == [0, 13, 42, 63]
