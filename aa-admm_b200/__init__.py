@@ -144,6 +144,7 @@ def host_lib():
         H.aaadmm_host_solver_device_factor.restype = vp
         H.aaadmm_host_solver_device_factor.argtypes = [vp]
         H.aaadmm_host_tet_constants.argtypes = [c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp]
+        H.aaadmm_host_tri_constants.argtypes = [c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp]
         _host = H
     return _host
 
@@ -477,6 +478,40 @@ class Solver:
         by = np.zeros(NPROF)
         _ck(cuda_lib().aaadmm_tetscene_algo_bytes(self._scene(), anderson_m, _dp(by)))
         return {n: dict(ms=float(ms[i]), bytes=float(by[i])) for i, n in enumerate(PROF_NAMES)}
+
+
+def tri_prox(F, variant="hard", limit_min=-100.0, limit_max=100.0):
+    """TriEnergyTerm::prox on (n, 6) column-major 3x2 blocks; variant 'hard' (hard_zxu) or 'xzu'."""
+    L = cuda_lib()
+    L.aaadmm_tri_prox.argtypes = [C.c_int, c_dp, C.c_int64, C.c_double, C.c_double]
+    z = np.ascontiguousarray(F, np.float64).reshape(-1, 6).copy()
+    _ck(L.aaadmm_tri_prox(ORDER_XZU if variant == "xzu" else ORDER_HARD_ZXU, _dp(z), len(z), limit_min, limit_max))
+    return z
+
+
+PASSIVE_TYPES = {"floor": 0, "slide_floor": 1, "sphere": 2, "plane_half_sphere": 3, "cylinder": 4}
+
+
+def collision_prox(objects, pts):
+    """Collision::prox of (n, 3) points against analytic passive objects: a list of
+    (type name, 7 parameters {cx, cy, cz, nx, ny, nz, radius}); Floor uses cx as its height."""
+    L = cuda_lib()
+    L.aaadmm_collision_prox.argtypes = [C.c_int, c_ip, c_dp, c_dp, C.c_int64]
+    types = np.ascontiguousarray([PASSIVE_TYPES[o[0]] for o in objects], np.int32)
+    prm = np.ascontiguousarray([o[1] for o in objects], np.float64).reshape(-1, 7)
+    z = np.ascontiguousarray(pts, np.float64).reshape(-1, 3).copy()
+    _ck(L.aaadmm_collision_prox(len(types), _ip(types), _dp(prm), _dp(z), len(z)))
+    return z
+
+
+def spring_prox(pts, pins, active):
+    L = cuda_lib()
+    L.aaadmm_spring_prox.argtypes = [c_dp, c_dp, c_ip, C.c_int64]
+    z = np.ascontiguousarray(pts, np.float64).reshape(-1, 3).copy()
+    pins = np.ascontiguousarray(pins, np.float64).reshape(-1, 3)
+    act = np.ascontiguousarray(active, np.int32)
+    _ck(L.aaadmm_spring_prox(_dp(z), _dp(pins), _ip(act), len(z)))
+    return z
 
 
 def make_beam_solver(cx, cy, cz, n_beams=1, dt=1.0 / 30.0, iters=100, anderson_m=5, accel=True, penalty=1.0,

@@ -13,6 +13,7 @@
 #include "aa_kernels.cuh"
 #include "common.cuh"
 #include "ldlt_apply.cuh"
+#include "extra_terms.cuh"
 #include "tet_kernels.cuh"
 
 namespace aaadmm {
@@ -919,6 +920,71 @@ int aaadmm_tetscene_algo_bytes(aaadmm_tetscene *s, int m, double *b) {
 // ------------------------------------------------------------------------------------------
 // Batched element kernels (unit parity)
 // ------------------------------------------------------------------------------------------
+// ---- rows I / J: triangle, collision and spring-pin prox batches on host arrays -------------------------
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    int up(const void *src, size_t bytes) {
+        AAADMM_CUDA_OK(cudaMalloc(&p, std::max<size_t>(bytes, 8)));
+        if (bytes) AAADMM_CUDA_OK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+        return 0;
+    }
+};
+}  // namespace
+int aaadmm_tri_prox(int variant, double *z, int64_t n, double limit_min, double limit_max) {
+    if (aaadmm_device_count() <= 0) {
+        set_last_error("no CUDA device (this library has no CPU path)");
+        return -1;
+    }
+    if (!z || n < 0 || (variant != AAADMM_ORDER_HARD_ZXU && variant != AAADMM_ORDER_XZU)) {
+        set_last_error("tri_prox: bad arguments");
+        return -1;
+    }
+    DevBuf d;
+    if (d.up(z, sizeof(double) * 6 * n)) return -1;
+    launch_tri_prox(variant == AAADMM_ORDER_XZU ? 0 : 1, (double *)d.p, n, limit_min, limit_max, nullptr);
+    AAADMM_CUDA_OK(cudaGetLastError());
+    AAADMM_CUDA_OK(cudaMemcpy(z, d.p, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int aaadmm_collision_prox(int n_objs, const int *types, const double *params7, double *z, int64_t n) {
+    if (aaadmm_device_count() <= 0) {
+        set_last_error("no CUDA device (this library has no CPU path)");
+        return -1;
+    }
+    if (!z || n < 0 || n_objs < 0 || (n_objs > 0 && (!types || !params7))) {
+        set_last_error("collision_prox: bad arguments");
+        return -1;
+    }
+    for (int j = 0; j < n_objs; ++j)
+        if (types[j] < AAADMM_PASSIVE_FLOOR || types[j] > AAADMM_PASSIVE_CYLINDER) {
+            set_last_error("collision_prox: unknown passive object type (triangle-mesh obstacles have no device batch)");
+            return -1;
+        }
+    DevBuf d, t, p;
+    if (d.up(z, sizeof(double) * 3 * n) || t.up(types, sizeof(int) * n_objs) || p.up(params7, sizeof(double) * 7 * n_objs)) return -1;
+    launch_collision_prox(n_objs, (const int *)t.p, (const double *)p.p, (double *)d.p, n, nullptr);
+    AAADMM_CUDA_OK(cudaGetLastError());
+    AAADMM_CUDA_OK(cudaMemcpy(z, d.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int aaadmm_spring_prox(double *z, const double *pins, const int *active, int64_t n) {
+    if (aaadmm_device_count() <= 0) {
+        set_last_error("no CUDA device (this library has no CPU path)");
+        return -1;
+    }
+    if (!z || !pins || !active || n < 0) {
+        set_last_error("spring_prox: bad arguments");
+        return -1;
+    }
+    DevBuf d, p, a;
+    if (d.up(z, sizeof(double) * 3 * n) || p.up(pins, sizeof(double) * 3 * n) || a.up(active, sizeof(int) * n)) return -1;
+    launch_spring_prox((double *)d.p, (const double *)p.p, (const int *)a.p, n, nullptr);
+    AAADMM_CUDA_OK(cudaGetLastError());
+    AAADMM_CUDA_OK(cudaMemcpy(z, d.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
 int aaadmm_tet_prox_linear(double *z, int64_t n) {
     if (aaadmm_device_count() <= 0) {
         set_last_error("no CUDA device (this library has no CPU path)");

@@ -249,6 +249,9 @@ void *aaadmm_host_solver_device_scene(void *h) { return static_cast<SolverHandle
 void *aaadmm_host_solver_device_factor(void *h) { return static_cast<SolverHandle *>(h)->solver.device_factor(); }
 
 // Host-only pieces of initialize() for CPU tests: tet constants and the scalar system matrix.
+int aaadmm_host_tri_constants(const double *rest9, double youngs, double poisson, double *rest_pose4, double *area, double *weight) {
+    return aaadmm::tri_constants(rest9, youngs, poisson, rest_pose4, area, weight) ? 0 : -1;
+}
 int aaadmm_host_tet_constants(const double *rest12, double youngs, double poisson, double *binv9, double *vol,
                               double *weight) {
     return aaadmm::tet_constants(rest12, youngs, poisson, binv9, vol, weight) ? 0 : -1;

@@ -36,6 +36,34 @@ inline double det3(const double *m) {
 }
 }  // namespace
 
+bool tri_constants(const double *rest9, double youngs, double poisson, double *rest_pose4, double *area, double *weight) {
+    double e12[3], e13[3], n1[3], n2[3];
+    for (int r = 0; r < 3; ++r) {
+        e12[r] = rest9[3 + r] - rest9[r];
+        e13[r] = rest9[6 + r] - rest9[r];
+    }
+    const double l1 = std::sqrt(e12[0] * e12[0] + e12[1] * e12[1] + e12[2] * e12[2]);
+    for (int r = 0; r < 3; ++r) n1[r] = l1 > 0.0 ? e12[r] / l1 : e12[r];
+    const double d = e13[0] * n1[0] + e13[1] * n1[1] + e13[2] * n1[2];
+    for (int r = 0; r < 3; ++r) n2[r] = e13[r] - d * n1[r];
+    const double l2 = std::sqrt(n2[0] * n2[0] + n2[1] * n2[1] + n2[2] * n2[2]);
+    for (int r = 0; r < 3; ++r) n2[r] = l2 > 0.0 ? n2[r] / l2 : n2[r];
+    // B = basis^T * edges (2x2), rest_pose = B^-1
+    const double b00 = n1[0] * e12[0] + n1[1] * e12[1] + n1[2] * e12[2], b01 = n1[0] * e13[0] + n1[1] * e13[1] + n1[2] * e13[2];
+    const double b10 = n2[0] * e12[0] + n2[1] * e12[1] + n2[2] * e12[2], b11 = n2[0] * e13[0] + n2[1] * e13[1] + n2[2] * e13[2];
+    const double det = b00 * b11 - b01 * b10;
+    const double inv = 1.0 / det;
+    rest_pose4[0] = b11 * inv;   // (0,0)
+    rest_pose4[1] = -b10 * inv;  // (1,0)
+    rest_pose4[2] = -b01 * inv;  // (0,1)
+    rest_pose4[3] = b00 * inv;   // (1,1)
+    *area = 0.5 * det;
+    if (*area < 0) return false;
+    Lame lame(youngs, poisson);
+    *weight = std::sqrt(lame.bulk_modulus() * (*area));
+    return true;
+}
+
 bool tet_constants(const double *rest12, double youngs, double poisson, double *binv9, double *vol, double *weight) {
     double e[9];
     for (int c = 0; c < 3; ++c)

@@ -51,6 +51,9 @@ struct TetSystem {
 
 // TetEnergyTerm ctor constants for one tet (false if the rest tet is inverted).
 bool tet_constants(const double *rest12, double youngs, double poisson, double *binv9, double *vol, double *weight);
+// TriEnergyTerm constructor (hard/src/TriEnergyTerm.cpp:34-56): rest pose inverse (column-major 2x2) in the
+// triangle's own 2-D basis, area, weight = sqrt(bulk modulus * area). False for an inverted rest triangle.
+bool tri_constants(const double *rest9, double youngs, double poisson, double *rest_pose4, double *area, double *weight);
 
 // rest12: the 4 rest vertices of every tet (12 doubles per tet, as handed to the TetEnergyTerm
 // ctor); tets: 4 ints per tet; masses: 1 per vertex; pinned: vertex ids. rho_dt2 = penalty * dt^2.

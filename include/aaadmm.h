@@ -220,6 +220,25 @@ int aaadmm_tet_f_minus_uvt(const double *z, double *out, int64_t n);
 int aaadmm_tet_prox_hyper(int material, double mu, double lambda, double vol, double *z, double *grad, int64_t n);
 int aaadmm_cod_solve(int m, const double *M, const double *rhs, double *x, int *rank);
 
+/* ------------------------------------------------------------------------------------------
+ * Remaining element types, as batches on host arrays (in place):
+ *   tri_prox       TriEnergyTerm::prox on n column-major 3x2 blocks; variant AAADMM_ORDER_XZU:
+ *                  xzu/src/TriEnergyTerm.cpp:77-107, AAADMM_ORDER_HARD_ZXU: hard/src/TriEnergyTerm.cpp:74-105;
+ *                  limit_min / limit_max = Lame::limit_min / limit_max (-100 / 100: no strain limiting)
+ *   collision_prox Collision::prox (hard/src/CollisionEnergyTerm.hpp:79-91) of n points against n_objs analytic
+ *                  passive objects (hard/src/PassiveObject.hpp:32-136); 7 parameters per object:
+ *                  {cx, cy, cz, nx, ny, nz, radius}; Floor uses cx as its height
+ *   spring_prox    SpringPin::prox (hard/src/SpringEnergyTerm.hpp:66-70): z = pin where active
+ * ------------------------------------------------------------------------------------------ */
+#define AAADMM_PASSIVE_FLOOR 0
+#define AAADMM_PASSIVE_SLIDE_FLOOR 1
+#define AAADMM_PASSIVE_SPHERE 2
+#define AAADMM_PASSIVE_PLANE_HALF_SPHERE 3
+#define AAADMM_PASSIVE_CYLINDER 4
+int aaadmm_tri_prox(int variant, double *z, int64_t n, double limit_min, double limit_max);
+int aaadmm_collision_prox(int n_objs, const int *types, const double *params7, double *z, int64_t n);
+int aaadmm_spring_prox(double *z, const double *pins, const int *active, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

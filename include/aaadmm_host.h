@@ -52,6 +52,9 @@ int aaadmm_host_solver_info(void *h, double *out8);
 int aaadmm_host_solver_factor_info(void *h, double *out6);
 void *aaadmm_host_solver_device_scene(void *h);
 void *aaadmm_host_solver_device_factor(void *h);
+/* TriEnergyTerm constructor (hard/src/TriEnergyTerm.cpp:34-56): rest pose inverse (column-major 2x2), area, weight;
+ * -1 for an inverted rest triangle */
+int aaadmm_host_tri_constants(const double *rest9, double youngs, double poisson, double *rest_pose4, double *area, double *weight);
 int aaadmm_host_tet_constants(const double *rest12, double youngs, double poisson, double *binv9, double *vol,
                               double *weight);
 

@@ -23,6 +23,12 @@
 
 #include "Solver.hpp"
 #include "TetEnergyTerm.hpp"
+#include "TriEnergyTerm.hpp"
+#include "PassiveObject.hpp"
+#ifdef REF_HARD
+#include "SpringEnergyTerm.hpp"
+#include "CollisionEnergyTerm.hpp"
+#endif
 #include "MCL/TetMesh.hpp"
 #include "MCL/ShapeFactory.hpp"
 #include "MCL/XForm.hpp"
@@ -52,6 +58,19 @@ struct Handle {
 };
 
 // ProbeTet exposes the protected prox / get_gradient of the LINEAR tet.
+struct ProbeTri : public admm::TriEnergyTerm {
+    using admm::TriEnergyTerm::TriEnergyTerm;
+    void call_prox(double *z6) {
+        VecX zi = Eigen::Map<VecX>(z6, 6);
+        VecX vi = zi;
+        Eigen::Matrix<double, 6, 6> W = Eigen::Matrix<double, 6, 6>::Identity();
+        prox(W, zi, vi);
+        Eigen::Map<VecX>(z6, 6) = zi;
+    }
+    double w() const { return weight; }
+    double ar() const { return area; }
+    const Eigen::Matrix2d &rp() const { return rest_pose; }
+};
 struct ProbeTet : public admm::TetEnergyTerm {
     using admm::TetEnergyTerm::TetEnergyTerm;
     void call_prox(double *z9) {
@@ -378,4 +397,70 @@ int RFN(make_beam)(int cx, int cy, int cz, float y_shift, float density, float *
     return 0;
 }
 
+
+// ---- rows I / J of SURVEY 8: triangle, collision and spring-pin terms --------------------------------
+// TriEnergyTerm::prox on n column-major 3x2 blocks (in place) with the given strain limits.
+void RFN(tri_prox)(double *z, int n, double limit_min, double limit_max) {
+    std::vector<Eigen::Vector3d> v = {Eigen::Vector3d(0, 0, 0), Eigen::Vector3d(1, 0, 0), Eigen::Vector3d(0, 1, 0)};
+    admm::Lame lame(1e7, 0.399);
+    lame.limit_min = limit_min;
+    lame.limit_max = limit_max;
+    ProbeTri t(Eigen::Vector3i(0, 1, 2), v, lame);
+    for (int i = 0; i < n; ++i) t.call_prox(z + 6 * i);
+}
+// TriEnergyTerm constructor: rest_pose (column-major 2x2), area, weight.
+int RFN(tri_constants)(const double *verts9, double youngs, double poisson, double *rest_pose4, double *area, double *weight) {
+    std::vector<Eigen::Vector3d> v(3);
+    for (int i = 0; i < 3; ++i) v[i] = Eigen::Vector3d(verts9[3 * i], verts9[3 * i + 1], verts9[3 * i + 2]);
+    try {
+        ProbeTri t(Eigen::Vector3i(0, 1, 2), v, admm::Lame(youngs, poisson));
+        Eigen::Map<Eigen::Matrix2d> rp_out(rest_pose4);
+        rp_out = t.rp();
+        *area = t.ar();
+        *weight = t.w();
+    } catch (std::exception &) {
+        return -1;
+    }
+    return 0;
+}
+#ifdef REF_HARD
+// SpringPin::prox on n points (in place): z = pin where active (hard_zxu only: the xzu class is abstract).
+void RFN(spring_prox)(double *z, const double *pins, const int *active, int n) {
+    for (int i = 0; i < n; ++i) {
+        admm::SpringPin sp(0, Eigen::Vector3d(pins[3 * i], pins[3 * i + 1], pins[3 * i + 2]));
+        sp.set_active(active[i] != 0);
+        Eigen::VectorXd zi = Eigen::Map<Eigen::VectorXd>(z + 3 * i, 3), vi = zi;
+        Eigen::MatrixXd W = Eigen::Matrix3d::Identity();
+        sp.prox(W, zi, vi);
+        Eigen::Map<Eigen::VectorXd>(z + 3 * i, 3) = zi;
+    }
+}
+// Collision::prox against a list of analytic passive objects (types: 0 Floor{y}, 1 SlideFloor{c,n},
+// 2 Sphere{c,r}, 3 PlaneAndHalfSphere{c,r}, 4 Cylinder{c,r}; 7 parameters per object), n points in place.
+int RFN(collision_prox)(int n_objs, const int *types, const double *prm, double *z, int n) {
+    auto cs = std::make_shared<admm::ConstraintSet>();
+    for (int j = 0; j < n_objs; ++j) {
+        const double *p = prm + 7 * j;
+        Eigen::Vector3d c(p[0], p[1], p[2]), nrm(p[3], p[4], p[5]);
+        std::shared_ptr<admm::PassiveCollision> o;
+        switch (types[j]) {
+        case 0: o = std::make_shared<admm::Floor>(p[0]); break;
+        case 1: o = std::make_shared<admm::SlideFloor>(c, nrm); break;
+        case 2: o = std::make_shared<admm::Sphere>(c, p[6]); break;
+        case 3: o = std::make_shared<admm::PlaneAndHalfSphere>(c, p[6]); break;
+        case 4: o = std::make_shared<admm::Cylinder>(c, p[6]); break;
+        default: return -1;
+        }
+        cs->collider->passive_objs.push_back(o);
+    }
+    admm::Collision col(0, cs);
+    Eigen::MatrixXd W = Eigen::Matrix3d::Identity();
+    for (int i = 0; i < n; ++i) {
+        Eigen::VectorXd zi = Eigen::Map<Eigen::VectorXd>(z + 3 * i, 3), vi = zi;
+        col.prox(W, zi, vi);
+        Eigen::Map<Eigen::VectorXd>(z + 3 * i, 3) = zi;
+    }
+    return 0;
+}
+#endif
 }  // extern "C"

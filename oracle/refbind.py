@@ -209,6 +209,48 @@ def ref_tet_constants(verts4, youngs=1e7, poisson=0.399):
     return w.value, vol.value, binv
 
 
+def ref_tri_prox(F, variant="hard", limit_min=-100.0, limit_max=100.0):
+    """The reference's TriEnergyTerm::prox (hard_zxu or xzu) on (n, 6) column-major 3x2 blocks."""
+    lib = _load("libref_hard.so" if variant == "hard" else "libref_xzu.so")
+    f = getattr(lib, "ref_%s_tri_prox" % variant)
+    f.argtypes = [c_dp, C.c_int, C.c_double, C.c_double]
+    f.restype = None
+    z = np.ascontiguousarray(F, np.float64).reshape(-1, 6).copy()
+    f(_dp(z), len(z), limit_min, limit_max)
+    return z
+
+
+def ref_tri_constants(verts3, youngs=1e7, poisson=0.399, variant="hard"):
+    lib = _load("libref_hard.so" if variant == "hard" else "libref_xzu.so")
+    f = getattr(lib, "ref_%s_tri_constants" % variant)
+    f.argtypes = [c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp]
+    v = np.ascontiguousarray(verts3, np.float64)
+    rp, area, w = np.zeros(4), C.c_double(), C.c_double()
+    if f(_dp(v), youngs, poisson, _dp(rp), C.byref(area), C.byref(w)) != 0:
+        raise RuntimeError("inverted triangle")
+    return rp.reshape(2, 2).T.copy(), area.value, w.value  # rest_pose is stored column-major
+
+
+def ref_collision_prox(types, prm, pts):
+    lib = _load("libref_hard.so")
+    lib.ref_hard_collision_prox.argtypes = [C.c_int, c_ip, c_dp, c_dp, C.c_int]
+    types = np.ascontiguousarray(types, np.int32)
+    prm = np.ascontiguousarray(prm, np.float64).reshape(-1, 7)
+    z = np.ascontiguousarray(pts, np.float64).reshape(-1, 3).copy()
+    if lib.ref_hard_collision_prox(len(types), _ip(types), _dp(prm), _dp(z), len(z)) != 0:
+        raise RuntimeError("unknown passive object")
+    return z
+
+
+def ref_spring_prox(pts, pins, active):
+    lib = _load("libref_hard.so")
+    lib.ref_hard_spring_prox.argtypes = [c_dp, c_dp, c_ip, C.c_int]
+    lib.ref_hard_spring_prox.restype = None
+    z = np.ascontiguousarray(pts, np.float64).reshape(-1, 3).copy()
+    lib.ref_hard_spring_prox(_dp(z), _dp(np.ascontiguousarray(pins, np.float64)), _ip(np.ascontiguousarray(active, np.int32)), len(z))
+    return z
+
+
 class RefAndersonH:
     """hard/src/AndersonAcceleration.h (== Geometry/AndersonAcceleration.h)."""
 

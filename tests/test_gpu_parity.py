@@ -394,3 +394,47 @@ def test_ensemble_material_sweep_vs_reference(gpu, ref):
         recs.append(E.make_record(s, len(a), a[:, 2].sum(), a[-1, 0], a[-1, 1], sp.info()["loop_ms"], 0.0, 0))
     table = E.gather_records(np.array(recs))
     assert table.shape == (4, len(E.RECORD_FIELDS)) and list(table[:, 0]) == [0, 13, 42, 63]
+
+
+# ---- next-tier element types ------------------------------------------------------
+@pytest.mark.parametrize("variant", ["hard", "xzu"])
+@pytest.mark.parametrize("limits", [(-100.0, 100.0), (0.95, 1.05), (0.5, 1.2)])
+def test_tri_prox_vs_reference(gpu, ref, variant, limits):
+    rng = np.random.default_rng(7)
+    n = 4096
+    # deformation gradients of a stretched / sheared / rotated triangle: orthonormal 3x2 frames times a 2x2 stretch
+    Q = np.linalg.qr(rng.standard_normal((n, 3, 3)))[0][:, :, :2]
+    S = np.eye(2) + 0.6 * rng.standard_normal((n, 2, 2))
+    F = Q @ S
+    F6 = np.concatenate([F[:, :, 0], F[:, :, 1]], axis=1)  # column-major 3x2
+    zg = gpu.tri_prox(F6, variant, *limits)
+    zr = ref.ref_tri_prox(F6, variant, *limits)
+    err = np.abs(zg - zr).max(axis=1) / np.maximum(1.0, np.abs(zr).max(axis=1))
+    print(variant, limits, "max err %.2e" % err.max())
+    assert err.max() < 1e-12
+    # the result of the unlimited hard prox has singular values (1 + sigma) / 2
+    if variant == "hard" and limits[0] < 0:
+        sv = np.linalg.svd(np.stack([zg[:, :3], zg[:, 3:]], axis=2), compute_uv=False)
+        sv0 = np.linalg.svd(F, compute_uv=False)
+        assert np.abs(sv - (1 + sv0) / 2).max() < 1e-12
+
+
+def test_collision_and_spring_prox_vs_reference(gpu, ref):
+    rng = np.random.default_rng(9)
+    objs = [("floor", [-0.8, 0, 0, 0, 0, 0, 0]),
+            ("slide_floor", [0.2, -0.5, 0.1, 0.3, 1.0, -0.2, 0]),
+            ("sphere", [0.5, 0.2, -0.3, 0, 0, 0, 0.6]),
+            ("plane_half_sphere", [-0.6, -0.4, 0.5, 0, 0, 0, 0.5]),
+            ("cylinder", [1.0, 0.8, 0.0, 0, 0, 0, 0.35])]
+    pts = rng.uniform(-1.5, 1.5, (20000, 3))
+    for sel in ([0], [1], [2], [3], [4], [0, 2, 4], [0, 1, 2, 3, 4]):
+        use = [objs[i] for i in sel]
+        zg = gpu.collision_prox(use, pts)
+        zr = ref.ref_collision_prox([gpu.PASSIVE_TYPES[o[0]] for o in use], [o[1] for o in use], pts)
+        moved = np.abs(zr - pts).max(axis=1) > 0
+        print(sel, "colliding points", int(moved.sum()), "max diff %.2e" % np.abs(zg - zr).max())
+        assert moved.sum() > 100
+        assert np.abs(zg - zr).max() < 1e-14
+    pins = rng.standard_normal((1000, 3))
+    act = rng.integers(0, 2, 1000)
+    assert np.array_equal(gpu.spring_prox(pts[:1000], pins, act), ref.ref_spring_prox(pts[:1000], pins, act))

@@ -34,6 +34,23 @@ def test_beam_stretch_moves_pins_like_beams_cpp(A):
     assert np.array_equal(p1[:, 1:], p0[:, 1:])
 
 
+def test_tri_constants_match_reference(A):
+    """TriEnergyTerm constructor (rest pose, area, weight) against the compiled reference class."""
+    from oracle import refbind
+    if not refbind.have_ref():
+        pytest.skip("oracle/_ref not present")
+    H = A.host_lib()
+    rng = np.random.default_rng(21)
+    for _ in range(200):
+        v = rng.standard_normal((3, 3))
+        rp, area, w = np.zeros(4), C.c_double(), C.c_double()
+        rc = H.aaadmm_host_tri_constants(v.ctypes.data_as(A.c_dp), 3e6, 0.33, rp.ctypes.data_as(A.c_dp), C.byref(area), C.byref(w))
+        rpr, ar, wr = refbind.ref_tri_constants(v, 3e6, 0.33)
+        assert rc == 0
+        assert np.abs(rp.reshape(2, 2).T - rpr).max() <= 1e-13 * np.abs(rpr).max()
+        assert abs(area.value - ar) <= 1e-14 * ar and abs(w.value - wr) <= 1e-14 * wr
+
+
 def test_tet_constants_match_reference_bitwise(A):
     g = np.load(os.path.join(G, "tet_element.npz"))
     H = A.host_lib()
