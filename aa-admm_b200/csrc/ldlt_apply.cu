@@ -806,19 +806,46 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     f->nrhs = nrhs;
     const int64_t nnz = Lp[n];
 
-    // ---- fronts: elimination-tree chains. Column j joins the front of j-1 when j is the parent of j-1
-    // and either the patterns nest exactly (fundamental supernode) or the front is still small
-    // (relaxed: the rows below j-1 are a subset of those below j; the difference is stored as zeros).
+    // ---- fronts. (1) Small subtrees of the elimination tree whose columns are consecutive (the leaf domains
+    // of a nested-dissection ordering) become ONE front each: the rows below the subtree's root contain the
+    // rows of all its columns that leave the subtree, the rest is stored as explicit zeros. Without this a
+    // surface mesh (SURVEY cfg 3) decomposes into tens of thousands of fronts of 3 columns. (2) Elsewhere
+    // column j joins the front of j-1 when j is the parent of j-1 and either the patterns nest exactly
+    // (fundamental supernode) or the front is still small (relaxed chain).
     // tuning knobs (environment overrides are for experiments only)
     const int kSmall = env_int("AAADMM_KSMALL", 64), kCap = env_int("AAADMM_KCAP", 6144);
+    const int kSubtree = env_int("AAADMM_KSUBTREE", 64);
+    std::vector<int> sub_root(std::max(n, 1), -1);  // root of the maximal small contiguous subtree holding j
+    if (kSubtree > 1) {
+        std::vector<int> par(n, -1), size(n, 1), lo(n);
+        for (int j = 0; j < n; ++j) {
+            lo[j] = j;
+            if (Lp[j + 1] > Lp[j]) par[j] = Li[Lp[j]];
+        }
+        for (int j = 0; j < n; ++j)  // children precede their parents
+            if (par[j] >= 0) {
+                size[par[j]] += size[j];
+                lo[par[j]] = std::min(lo[par[j]], lo[j]);
+            }
+        auto small = [&](int j) { return size[j] <= kSubtree && j - lo[j] + 1 == size[j]; };
+        for (int j = n - 1; j >= 0; --j) {
+            if (sub_root[j] >= 0 || !small(j) || size[j] < 2) continue;
+            if (par[j] >= 0 && small(par[j])) continue;  // the parent's subtree will take it
+            for (int c = lo[j]; c <= j; ++c) sub_root[c] = j;
+        }
+    }
     std::vector<int> blk_of(std::max(n, 1)), blk_first;
     for (int j = 0; j < n; ++j) {
         bool join = false;
         if (j > 0) {
-            const int64_t c0 = Lp[j] - Lp[j - 1], c1 = Lp[j + 1] - Lp[j];
-            const bool chain = c0 > 0 && Li[Lp[j - 1]] == j;
-            const int cur_size = j - blk_first.back();
-            if (chain && cur_size < kCap && (c0 == c1 + 1 || cur_size < kSmall)) join = true;
+            if (sub_root[j] >= 0) {
+                join = sub_root[j - 1] == sub_root[j];  // same subtree; a subtree always starts a front
+            } else {
+                const int64_t c0 = Lp[j] - Lp[j - 1], c1 = Lp[j + 1] - Lp[j];
+                const bool chain = c0 > 0 && Li[Lp[j - 1]] == j;
+                const int cur_size = j - blk_first.back();
+                if (chain && cur_size < kCap && (c0 == c1 + 1 || cur_size < kSmall)) join = true;
+            }
         }
         if (!join) blk_first.push_back(j);
         blk_of[j] = (int)blk_first.size() - 1;
@@ -1222,6 +1249,12 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     cudaFuncSetAttribute(k_fwd_front<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(k_bwd_front<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     cudaFuncSetAttribute(k_bwd_front<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (getenv("AAADMM_LDLT_VERBOSE")) {
+        int64_t small = 0;
+        for (int b = 0; b < nb; ++b) small += fr[b].ns + fr[b].k <= 64;
+        fprintf(stderr, "ldlt: n %d nnz %lld fronts %d (<=64 rows: %lld) levels %d max front %d | fwd tasks %d bwd tasks %d | Mf %.1f MB Mb %.1f MB\n",
+                n, (long long)nnz, nb, (long long)small, nlev, max_block, f->n_ftasks, f->n_btasks, mf_tot * 8e-6, mb_tot * 8e-6);
+    }
     f->stats.n = n;
     f->stats.n_blocks = nb;
     f->stats.n_levels = nlev;
