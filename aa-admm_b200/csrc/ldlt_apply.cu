@@ -1063,8 +1063,30 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     // counters: [2 + b] forward arrivals at front b (tiles of its children), [2 + nb + b] backward arrivals
     // of front b (its own column chunks)
     std::vector<int> ntiles_f(std::max(nb, 1), 0), ntasks_b(std::max(nb, 1), 0), need_f(std::max(nb, 1), 0);
-    for (int l = 0; l < nlev; ++l) {
-        for (int b : by_level[l]) {
+    // Emission order = ticket order. By tree level, or (default) by the estimated time a front becomes ready
+    // (children's ready time + a latency/bandwidth estimate of their duration): tasks then take their tickets
+    // roughly in the order they can start, and fewer CTA slots are held by tasks that only wait.
+    const bool by_ready = env_int("AAADMM_ORDER_BY_LEVEL", 0) == 0;
+    const double est_lat = 0.1 * env_int("AAADMM_EST_LAT_TENTHS_US", 60), est_rate = env_int("AAADMM_EST_RATE_GBS", 25);
+    auto front_dur_us = [&](int b, bool fwd) {
+        const double m = fr[b].ns + fr[b].k;
+        const double tile_bytes = fwd ? 8.0 * (double)(1 << lrt[b]) * fr[b].ns : 8.0 * m * std::min(fr[b].ns, bcols[b]);
+        return est_lat + tile_bytes / (est_rate * 1e3) + ((fwd ? fr[b].ns > ws_cap : fr[b].ld > v_cap) ? est_lat : 0.0);
+    };
+    std::vector<double> ready_f(std::max(nb, 1), 0.0), ready_b(std::max(nb, 1), 0.0);
+    for (int b = 0; b < nb; ++b)  // children have smaller indices than their parents
+        if (parent[b] >= 0) ready_f[parent[b]] = std::max(ready_f[parent[b]], ready_f[b] + front_dur_us(b, true));
+    for (int b = nb - 1; b >= 0; --b)
+        if (parent[b] >= 0) ready_b[b] = ready_b[parent[b]] + front_dur_us(parent[b], false);
+    std::vector<int> order_f, order_b;
+    for (int l = 0; l < nlev; ++l) order_f.insert(order_f.end(), by_level[l].begin(), by_level[l].end());
+    for (int l = nlev - 1; l >= 0; --l) order_b.insert(order_b.end(), by_level[l].begin(), by_level[l].end());
+    if (by_ready) {
+        std::stable_sort(order_f.begin(), order_f.end(), [&](int a, int b2) { return ready_f[a] < ready_f[b2]; });
+        std::stable_sort(order_b.begin(), order_b.end(), [&](int a, int b2) { return ready_b[a] < ready_b[b2]; });
+    }
+    {
+        for (int b : order_f) {
             const int m = fr[b].ns + fr[b].k;
             // wide fronts: assemble tasks write w once; the tiles wait for them and receive w by bulk copy
             const bool wide = wide_on && fr[b].ns > ws_cap;
@@ -1118,8 +1140,9 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     int64_t mb_tot = 0;
     int64_t va_tot = 0;
     std::vector<int> n_asm_b(std::max(nb, 1), -1);
-    for (int l = nlev - 1; l >= 0; --l) {
-        for (int b : by_level[l]) {
+    {
+        for (int b : order_b) {
+            const int l = level[b];
             // wide fronts: assemble tasks write v once into Va; the column tasks receive it by bulk copy
             const bool wide = wide_on && fr[b].ld > v_cap;
             int64_t va_off = 0;
