@@ -377,7 +377,10 @@ class BeamScene:
     def stretch(self, dt):
         """stretch_beams(): returns the new pin targets."""
         self.H.aaadmm_host_beam_stretch(self.h, dt)
-        return self.arrays()[4]
+        npin = self.counts()[2]
+        ppts = np.zeros((npin, 3))
+        self.H.aaadmm_host_beam_copy(self.h, None, None, None, None, _dp(ppts), None)  # only the pin targets move
+        return ppts
 
 
 class Solver:

@@ -101,6 +101,7 @@ bool Solver::initialize(const Settings &settings_) {
     for (int v = 0; v < n_verts; ++v) masses[v] = m_masses[3 * (size_t)v];
     std::vector<int> pinned;
     positive_pin.assign(n_verts, 1);
+    slot_of_node.clear();
     for (auto &kv : m_pins) {
         pinned.push_back(kv.first);
         positive_pin[kv.first] = 0;
@@ -165,14 +166,18 @@ void Solver::step() {
     m_runtime = RuntimeData();
     m_runtime.initialization_ms = init_ms;
 
-    if (std::abs(m_settings.gravity) > 0)
-        for (int i = 0; i < n_nodes; ++i)
-            if (positive_pin[i] > 0) m_v[i * 3 + 1] += dt * m_settings.gravity;
-    int count = 0;
+    if ((int)slot_of_node.size() != n_nodes) {
+        slot_of_node.assign(n_nodes, 0);
+        int nf = 0, np = 0;
+        for (int i = 0; i < n_nodes; ++i) slot_of_node[i] = positive_pin[i] > 0 ? nf++ : np++;
+    }
+    const bool grav = std::abs(m_settings.gravity) > 0;
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < n_nodes; ++i)
         if (positive_pin[i] > 0) {
-            for (int j = 0; j < 3; ++j) m_xbar[3 * (size_t)count + j] = m_x[3 * (size_t)i + j] + dt * m_v[3 * (size_t)i + j];
-            ++count;
+            if (grav) m_v[i * 3 + 1] += dt * m_settings.gravity;
+            const size_t c = (size_t)slot_of_node[i];
+            for (int j = 0; j < 3; ++j) m_xbar[3 * c + j] = m_x[3 * (size_t)i + j] + dt * m_v[3 * (size_t)i + j];
         }
 
     aaadmm_step_opts o;
@@ -193,20 +198,12 @@ void Solver::step() {
         throw std::runtime_error(std::string("aaadmm_tetscene_step: ") + aaadmm_last_error());
 
     // actual_x = S_free x + S_fix x_pin; v = (actual_x - x)/dt
-    count = 0;
-    int pcount = 0;
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < n_nodes; ++i) {
-        double nx[3];
-        if (positive_pin[i] > 0) {
-            for (int j = 0; j < 3; ++j) nx[j] = m_xout[3 * (size_t)count + j];
-            ++count;
-        } else {
-            for (int j = 0; j < 3; ++j) nx[j] = m_x_pin[3 * (size_t)pcount + j];
-            ++pcount;
-        }
+        const double *src = (positive_pin[i] > 0 ? m_xout.data() : m_x_pin.data()) + 3 * (size_t)slot_of_node[i];
         for (int j = 0; j < 3; ++j) {
-            m_v[3 * (size_t)i + j] = (nx[j] - m_x[3 * (size_t)i + j]) * (1.0 / dt);
-            m_x[3 * (size_t)i + j] = nx[j];
+            m_v[3 * (size_t)i + j] = (src[j] - m_x[3 * (size_t)i + j]) * (1.0 / dt);
+            m_x[3 * (size_t)i + j] = src[j];
         }
     }
     step_prim_residual.assign(m_hist_prim.begin(), m_hist_prim.begin() + r.iters_logged);

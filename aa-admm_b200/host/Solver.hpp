@@ -174,6 +174,7 @@ protected:
     std::map<int, Vec3> m_pins;
     std::vector<double> m_x_pin;  // in the order set_pins received them (reference: m_x_pin)
     std::vector<int> positive_pin;
+    std::vector<int> slot_of_node;  // index among the free nodes (positive_pin) or among the pinned ones
     aaadmm::TetSystem m_sys;
     aaadmm::LdltFactor m_factor;
     aaadmm_ldlt *m_ldlt = nullptr;
