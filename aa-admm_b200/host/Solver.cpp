@@ -117,8 +117,16 @@ bool Solver::initialize(const Settings &settings_) {
     for (int k = 0; k < m_sys.n_free; ++k)
         for (int j = 0; j < 3; ++j) coords[3 * (size_t)k + j] = m_x[3 * (size_t)m_sys.dev_to_vert[k] + j];
     const char *leaf_env = getenv("AAADMM_ND_LEAF");  // experiments only
-    std::vector<int> perm = aaadmm::nested_dissection(m_sys.Ahat, coords.data(), leaf_env ? atoi(leaf_env) : m_settings.nd_leaf_size);
-    m_factor = aaadmm::ldlt_factorize(m_sys.Ahat, perm);
+    const char *cache_env = getenv("AAADMM_FACTOR_CACHE");
+    const std::string cache = !m_settings.factor_cache.empty() ? m_settings.factor_cache : std::string(cache_env ? cache_env : "");
+    const uint64_t key = cache.empty() ? 0 : aaadmm::matrix_key(m_sys.Ahat);
+    factor_from_cache = !cache.empty() && aaadmm::ldlt_load(cache, key, m_factor);
+    if (!factor_from_cache) {
+        std::vector<int> perm = aaadmm::nested_dissection(m_sys.Ahat, coords.data(), leaf_env ? atoi(leaf_env) : m_settings.nd_leaf_size);
+        m_factor = aaadmm::ldlt_factorize(m_sys.Ahat, perm);
+        if (m_factor.ok && !cache.empty() && !aaadmm::ldlt_save(m_factor, key, cache))
+            std::cerr << "Solver: could not write the factor cache " << cache << std::endl;
+    }
     if (!m_factor.ok) {
         std::cerr << "\n**Solver Error: LDLT factorization failed" << std::endl;
         return false;

@@ -105,6 +105,7 @@ public:
         Ordering ordering;                 // which reference project's loop to run
         bool write_residual_file;          // save() to ./result/residual-*.txt like the reference
         int nd_leaf_size;                  // nested-dissection leaf size of the setup factorisation
+        std::string factor_cache;          // if not empty: file the LDL^T factor is cached in (keyed by the matrix)
         Settings()
             : timestep_s(1.0 / 30.0), verbose(1), admm_iters(500), gravity(-9.8), constraint_w(-1), Anderson_m(2),
               penalty(1.0), beta(1.0), acceleration_type(NOACC), ordering(HARD_ZXU), write_residual_file(true),
@@ -174,6 +175,7 @@ protected:
     std::map<int, Vec3> m_pins;
     std::vector<double> m_x_pin;  // in the order set_pins received them (reference: m_x_pin)
     std::vector<int> positive_pin;
+    bool factor_from_cache = false;    // the last initialize() took the factor from Settings::factor_cache
     std::vector<int> slot_of_node;  // index among the free nodes (positive_pin) or among the pinned ones
     aaadmm::TetSystem m_sys;
     aaadmm::LdltFactor m_factor;

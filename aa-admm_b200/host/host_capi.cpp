@@ -99,6 +99,30 @@ void *aaadmm_host_factor_new(int n, const int64_t *Ap, const int *Ai, const doub
         return nullptr;
     }
 }
+// Factor cache: save the factor under the key of its matrix; load returns NULL unless the file holds the factor
+// of exactly this matrix.
+int aaadmm_host_factor_save(void *h, int n, const int64_t *Ap, const int *Ai, const double *Ax, const char *path) {
+    aaadmm::SymLower A;
+    A.n = n;
+    A.p.assign(Ap, Ap + n + 1);
+    A.i.assign(Ai, Ai + Ap[n]);
+    A.x.assign(Ax, Ax + Ap[n]);
+    return aaadmm::ldlt_save(static_cast<FactorHandle *>(h)->F, aaadmm::matrix_key(A), path) ? 0 : -1;
+}
+void *aaadmm_host_factor_load(int n, const int64_t *Ap, const int *Ai, const double *Ax, const char *path) {
+    aaadmm::SymLower A;
+    A.n = n;
+    A.p.assign(Ap, Ap + n + 1);
+    A.i.assign(Ai, Ai + Ap[n]);
+    A.x.assign(Ax, Ax + Ap[n]);
+    FactorHandle *f = new FactorHandle();
+    if (!aaadmm::ldlt_load(path, aaadmm::matrix_key(A), f->F) || f->F.n != n) {
+        delete f;
+        g_err = "factor cache: no factor of this matrix in the file";
+        return nullptr;
+    }
+    return f;
+}
 void aaadmm_host_factor_free(void *h) { delete static_cast<FactorHandle *>(h); }
 int64_t aaadmm_host_factor_nnz(void *h) {
     FactorHandle *f = static_cast<FactorHandle *>(h);

@@ -613,4 +613,74 @@ void ldlt_solve_host(const LdltFactor &F, const double *b, double *x, int nrhs) 
         for (int r = 0; r < nrhs; ++r) x[(size_t)F.perm[k] * nrhs + r] = y[(size_t)k * nrhs + r];
 }
 
+
+// ---- on-disk factor cache ----------------------------------------------------------------------------
+namespace {
+inline void fnv(uint64_t &h, const void *p, size_t bytes) {
+    const unsigned char *c = static_cast<const unsigned char *>(p);
+    for (size_t i = 0; i < bytes; ++i) {
+        h ^= c[i];
+        h *= 1099511628211ull;
+    }
+}
+}  // namespace
+
+uint64_t matrix_key(const SymLower &A) {
+    uint64_t h = 1469598103934665603ull;
+    fnv(h, &A.n, sizeof(A.n));
+    fnv(h, A.p.data(), A.p.size() * sizeof(A.p[0]));
+    fnv(h, A.i.data(), A.i.size() * sizeof(A.i[0]));
+    fnv(h, A.x.data(), A.x.size() * sizeof(A.x[0]));
+    return h;
+}
+
+bool ldlt_save(const LdltFactor &F, uint64_t key, const std::string &path) {
+    const std::string tmp = path + ".tmp";
+    FILE *fp = fopen(tmp.c_str(), "wb");
+    if (!fp) return false;
+    const int64_t nnz = F.Lp.empty() ? 0 : F.Lp[F.n];
+    bool ok = fwrite("AAFACT01", 1, 8, fp) == 8 && fwrite(&key, 8, 1, fp) == 1 && fwrite(&F.n, 4, 1, fp) == 1 &&
+              fwrite(&nnz, 8, 1, fp) == 1;
+    ok = ok && fwrite(F.perm.data(), 4, (size_t)F.n, fp) == (size_t)F.n;
+    ok = ok && fwrite(F.Lp.data(), 8, (size_t)F.n + 1, fp) == (size_t)F.n + 1;
+    ok = ok && fwrite(F.Li.data(), 4, (size_t)nnz, fp) == (size_t)nnz;
+    ok = ok && fwrite(F.Lx.data(), 8, (size_t)nnz, fp) == (size_t)nnz;
+    ok = ok && fwrite(F.D.data(), 8, (size_t)F.n, fp) == (size_t)F.n;
+    ok = (fclose(fp) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path.c_str()) != 0) {
+        remove(tmp.c_str());
+        return false;
+    }
+    return true;
+}
+
+bool ldlt_load(const std::string &path, uint64_t key, LdltFactor &F) {
+    FILE *fp = fopen(path.c_str(), "rb");
+    if (!fp) return false;
+    char magic[8];
+    uint64_t k = 0;
+    int n = 0;
+    int64_t nnz = 0;
+    bool ok = fread(magic, 1, 8, fp) == 8 && memcmp(magic, "AAFACT01", 8) == 0 && fread(&k, 8, 1, fp) == 1 && k == key &&
+              fread(&n, 4, 1, fp) == 1 && fread(&nnz, 8, 1, fp) == 1 && n >= 0 && nnz >= 0;
+    if (ok) {
+        LdltFactor G;
+        G.n = n;
+        G.perm.resize(n);
+        G.Lp.resize((size_t)n + 1);
+        G.Li.resize((size_t)nnz);
+        G.Lx.resize((size_t)nnz);
+        G.D.resize(n);
+        ok = fread(G.perm.data(), 4, (size_t)n, fp) == (size_t)n && fread(G.Lp.data(), 8, (size_t)n + 1, fp) == (size_t)n + 1 &&
+             fread(G.Li.data(), 4, (size_t)nnz, fp) == (size_t)nnz && fread(G.Lx.data(), 8, (size_t)nnz, fp) == (size_t)nnz &&
+             fread(G.D.data(), 8, (size_t)n, fp) == (size_t)n && G.Lp[n] == nnz;
+        if (ok) {
+            G.ok = true;
+            F = std::move(G);
+        }
+    }
+    fclose(fp);
+    return ok;
+}
+
 }  // namespace aaadmm

@@ -11,6 +11,7 @@
 // already has Eigen's factor (the reference) can pass that one instead.
 #pragma once
 #include <cstdint>
+#include <string>
 #include <vector>
 
 namespace aaadmm {
@@ -36,6 +37,14 @@ struct LdltFactor {
     double seconds_order = 0, seconds_symbolic = 0, seconds_numeric = 0;
     bool ok = false;  // false if a pivot was zero / non-finite
 };
+
+// On-disk factor cache (at 1M tets the setup dwarfs a short simulation). Little-endian binary:
+//   magic "AAFACT01", uint64 key, int32 n, int64 nnz, perm[n] int32, Lp[n+1] int64, Li[nnz] int32, Lx[nnz] f64,
+//   D[n] f64. `key` = matrix_key(A) of the matrix the factor belongs to (FNV-1a over n, pattern and values): a
+//   cached factor is only used for a bit-identical matrix.
+uint64_t matrix_key(const SymLower &A);
+bool ldlt_save(const LdltFactor &F, uint64_t key, const std::string &path);
+bool ldlt_load(const std::string &path, uint64_t key, LdltFactor &F);
 
 // Builds SymLower from (row, col, value) triplets of the FULL or LOWER part; duplicates are
 // summed; entries with row < col are mirrored into the lower triangle.

@@ -26,6 +26,9 @@ int aaadmm_host_beam_stretch(void *h, double dt);
  * A lower CSC incl. diagonal; coords 3 per node or NULL. */
 void *aaadmm_host_factor_new(int n, const int64_t *Ap, const int *Ai, const double *Ax, const double *coords,
                              int leaf_size, int n_threads);
+/* On-disk factor cache (host/sparse_ldlt.hpp: ldlt_save / ldlt_load), keyed by a hash of the matrix. */
+int aaadmm_host_factor_save(void *h, int n, const int64_t *Ap, const int *Ai, const double *Ax, const char *path);
+void *aaadmm_host_factor_load(int n, const int64_t *Ap, const int *Ai, const double *Ax, const char *path);
 void aaadmm_host_factor_free(void *h);
 int64_t aaadmm_host_factor_nnz(void *h);
 int aaadmm_host_factor_copy(void *h, int64_t *Lp, int *Li, double *Lx, double *D, int *perm);

@@ -438,3 +438,23 @@ def test_collision_and_spring_prox_vs_reference(gpu, ref):
     pins = rng.standard_normal((1000, 3))
     act = rng.integers(0, 2, 1000)
     assert np.array_equal(gpu.spring_prox(pts[:1000], pins, act), ref.ref_spring_prox(pts[:1000], pins, act))
+
+
+def test_solver_factor_cache(gpu, tmp_path):
+    """Settings::factor_cache (here through AAADMM_FACTOR_CACHE): the second initialize() loads the factor from disk
+    and the step is bit-identical."""
+    import os
+    from scenes import beam_arrays, run_product
+    path = str(tmp_path / "beam_factor.bin")
+    os.environ["AAADMM_FACTOR_CACHE"] = path
+    try:
+        _, h1, x1 = run_product(gpu, beam_arrays(gpu, 16, 4, 4), 1, m=5)
+        assert os.path.getsize(path) > 1000
+        t = os.path.getmtime(path)
+        _, h2, x2 = run_product(gpu, beam_arrays(gpu, 16, 4, 4), 1, m=5)
+        assert os.path.getmtime(path) == t          # not rewritten: it was loaded
+        assert np.array_equal(h1[0], h2[0]) and np.array_equal(x1[0], x2[0])
+        _, h3, _ = run_product(gpu, beam_arrays(gpu, 12, 3, 3), 1, m=5)   # another matrix: refactored and replaced
+        assert os.path.getmtime(path) != t or os.path.getsize(path) < 1e9
+    finally:
+        os.environ.pop("AAADMM_FACTOR_CACHE", None)

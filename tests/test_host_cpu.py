@@ -66,6 +66,32 @@ def test_tet_constants_match_reference_bitwise(A):
                                        C.byref(vol), C.byref(w)) != 0
 
 
+def test_factor_cache_round_trip(A, tmp_path):
+    """ldlt_save / ldlt_load: the cached factor comes back bit-identical, and only for the matrix it belongs to."""
+    rng = np.random.default_rng(5)
+    Afull, coords, Ap, Ai, Ax = _grid_spd(6, 5, 4, rng)
+    n = Afull.shape[0]
+    Ap, Ai, Ax = np.array(Ap, np.int64), np.array(Ai, np.int32), np.array(Ax, np.float64)
+    hf = A.HostFactor(n, Ap, Ai, Ax, coords, leaf_size=8)
+    H = A.host_lib()
+    H.aaadmm_host_factor_save.argtypes = [C.c_void_p, C.c_int, A.c_lp, A.c_ip, A.c_dp, C.c_char_p]
+    H.aaadmm_host_factor_load.argtypes = [C.c_int, A.c_lp, A.c_ip, A.c_dp, C.c_char_p]
+    H.aaadmm_host_factor_load.restype = C.c_void_p
+    path = str(tmp_path / "factor.bin").encode()
+    assert H.aaadmm_host_factor_save(hf.h, n, Ap.ctypes.data_as(A.c_lp), Ai.ctypes.data_as(A.c_ip), Ax.ctypes.data_as(A.c_dp), path) == 0
+    h2 = H.aaadmm_host_factor_load(n, Ap.ctypes.data_as(A.c_lp), Ai.ctypes.data_as(A.c_ip), Ax.ctypes.data_as(A.c_dp), path)
+    assert h2
+    g = A.HostFactor.__new__(A.HostFactor)
+    g.H, g.n, g.h = H, n, C.c_void_p(h2)
+    for a, b in zip(hf.arrays(), g.arrays()):
+        assert np.array_equal(a, b)
+    Ax2 = Ax.copy()
+    Ax2[3] *= 1.0000001  # another matrix: the cache must not be used
+    assert not H.aaadmm_host_factor_load(n, Ap.ctypes.data_as(A.c_lp), Ai.ctypes.data_as(A.c_ip), Ax2.ctypes.data_as(A.c_dp), path)
+    open(path.decode(), "r+b").write(b"XXXX")  # damaged header
+    assert not H.aaadmm_host_factor_load(n, Ap.ctypes.data_as(A.c_lp), Ai.ctypes.data_as(A.c_ip), Ax.ctypes.data_as(A.c_dp), path)
+
+
 def _grid_spd(nx, ny, nz, rng):
     n = nx * ny * nz
     idx = np.arange(n).reshape(nx, ny, nz)
