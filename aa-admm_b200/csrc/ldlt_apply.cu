@@ -393,7 +393,8 @@ k_fwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restr
     case 7: fwd_tile<NR, 7>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
     case 6: fwd_tile<NR, 6>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
     case 5: fwd_tile<NR, 5>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
-    default: fwd_tile<NR, 4>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
+    case 4: fwd_tile<NR, 4>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
+    default: fwd_tile<NR, 3>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
     }
     task_signal(ctl + 2, F);
     if (trace && threadIdx.x == 0) {
@@ -983,6 +984,8 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     const bool wide_on = env_int("AAADMM_WIDE", 1) != 0;
     const int min_ctas = env_int("AAADMM_MIN_CTAS", 148);  // one CTA per SM; each keeps 48 KB of loads in flight
     const int tile_entries = env_int("AAADMM_TILE_ENTRIES", 32768);
+    const int min_lrt = env_int("AAADMM_MIN_LRT", 3);  // smallest forward tile: 8 rows
+    const int min_ctas_f = env_int("AAADMM_MIN_CTAS_F", min_ctas);
     std::vector<std::vector<int>> by_level(nlev);
     for (int b = 0; b < nb; ++b) by_level[level[b]].push_back(b);
     std::vector<SweepTask> tasks;
@@ -1036,9 +1039,9 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
             for (int b : v) c += (fr[b].ns + fr[b].k + (1 << lrt[b]) - 1) >> lrt[b];
             return c;
         };
-        for (int pass = 0; pass < 5 && count_f() < min_ctas; ++pass)
+        for (int pass = 0; pass < 6 && count_f() < min_ctas_f; ++pass)
             for (int b : v)
-                if (lrt[b] > 4 && fr[b].ns >= 4 * ((2 * CTA) >> (lrt[b] - 1))) lrt[b]--;
+                if (lrt[b] > min_lrt && fr[b].ns >= 4 * ((2 * CTA) >> (lrt[b] - 1))) lrt[b]--;
         int cap = 128;
         auto set_cols = [&](int cw) {
             int64_t c = 0;
@@ -1102,7 +1105,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
                 }
             std::vector<SweepTask> tiles;
             for (int r0 = 0; r0 < m;) {
-                const int shape = std::min(lrt[b], std::max(4, ceil_log2(m - r0)));
+                const int shape = std::min(lrt[b], std::max(4, ceil_log2(m - r0)));  // tail tiles stay >= 16 rows
                 SweepTask t = make_task(b, true, r0, shape);
                 t.wait_idx = wide ? 2 * nb + b : b;
                 t.need = wide ? n_asm : -1;  // -1: filled in below from the children's tile counts
