@@ -480,6 +480,121 @@ class PortSolver:
 
 
 # ---------------------------------------------------------------------------------------------
+# C restatement of the Geometry path and of the triangle / collision terms (oracle/port/aaadmm_port_geo.c)
+# ---------------------------------------------------------------------------------------------
+class PortGeometrySolver:
+    """Plain-C restatement of ALMGeometrySolver<3> (use_alm=True) / GeometrySolver<3>; same building interface as
+    RefGeometrySolver; dense global solve (small scenes only)."""
+
+    def __init__(self, use_alm=True):
+        self.P = port_lib()
+        P = self.P
+        vp = C.c_void_p
+        P.port_geo_new.restype = vp
+        P.port_geo_new.argtypes = [C.c_int]
+        P.port_geo_free.argtypes = [vp]
+        P.port_geo_add_plane.argtypes = [vp, c_ip, C.c_int, C.c_double]
+        P.port_geo_add_edge.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double]
+        P.port_geo_add_angle.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+        P.port_geo_add_ref_surface.argtypes = [vp, C.c_int, C.c_double, c_dp, C.c_int, c_ip, C.c_int]
+        P.port_geo_add_uniform_laplacian.argtypes = [vp, c_ip, C.c_int, C.c_double, c_dp]
+        P.port_geo_add_closeness.argtypes = [vp, C.c_int, C.c_double, c_dp]
+        P.port_geo_setup.argtypes = [vp, C.c_int, C.c_double]
+        P.port_geo_solve.argtypes = [vp, c_dp, C.c_int, C.c_int, c_dp, c_dp]
+        self.h = vp(P.port_geo_new(int(use_alm)))
+        self.n_points = 0
+
+    def __del__(self):
+        try:
+            self.P.port_geo_free(self.h)
+        except Exception:
+            pass
+
+    def add_plane(self, idx, weight=1.0):
+        idx = np.ascontiguousarray(idx, np.int32)
+        self.P.port_geo_add_plane(self.h, _ip(idx), len(idx), weight)
+
+    def add_edge(self, i0, i1, weight, length):
+        self.P.port_geo_add_edge(self.h, int(i0), int(i1), weight, length)
+
+    def add_angle(self, tip, s1, s2, weight, amin, amax):
+        self.P.port_geo_add_angle(self.h, int(tip), int(s1), int(s2), weight, amin, amax)
+
+    def add_ref_surface(self, n_points, weight, V, F):
+        V = np.ascontiguousarray(V, np.float64)
+        F = np.ascontiguousarray(F, np.int32)
+        self.P.port_geo_add_ref_surface(self.h, n_points, weight, _dp(V), len(V), _ip(F), len(F))
+
+    def add_relative_uniform_laplacian(self, idx, weight, ref_pts):
+        idx = np.ascontiguousarray(idx, np.int32)
+        ref_pts = np.ascontiguousarray(ref_pts, np.float64)
+        self.P.port_geo_add_uniform_laplacian(self.h, _ip(idx), len(idx), weight, _dp(ref_pts))
+
+    def add_uniform_laplacian(self, idx, weight):
+        idx = np.ascontiguousarray(idx, np.int32)
+        self.P.port_geo_add_uniform_laplacian(self.h, _ip(idx), len(idx), weight, None)
+
+    def add_closeness(self, idx, weight, target):
+        target = np.ascontiguousarray(target, np.float64)
+        self.P.port_geo_add_closeness(self.h, int(idx), weight, _dp(target))
+
+    def setup(self, n_points, rho):
+        self.n_points = n_points
+        if self.P.port_geo_setup(self.h, n_points, rho) != 0:
+            raise RuntimeError("port geometry: system matrix not positive definite")
+
+    def solve(self, init_x, max_iter, anderson_m):
+        x0 = np.ascontiguousarray(init_x, np.float64)
+        x = np.zeros((self.n_points, 3))
+        hist = np.zeros(max(1, max_iter))
+        n = self.P.port_geo_solve(self.h, _dp(x0), max_iter, anderson_m, _dp(x), _dp(hist))
+        return hist[:n], x
+
+
+def port_geo_project(kind, cols, params=(0.0, 0.0, 0.0, 0.0)):
+    """cols: (n, k, 3) transformed columns; returns the projections (n, k, 3)."""
+    P = port_lib()
+    P.port_geo_project.argtypes = [C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp]
+    cols = np.ascontiguousarray(cols, np.float64)
+    n, k = cols.shape[0], cols.shape[1]
+    prm = np.ascontiguousarray(np.broadcast_to(np.asarray(params, np.float64), (n, 4)))
+    out = np.zeros_like(cols)
+    P.port_geo_project(kind, n, k, _dp(cols), _dp(prm), _dp(out))
+    return out
+
+
+def port_geo_closest_points(V, F, Q):
+    P = port_lib()
+    P.port_geo_closest_points.argtypes = [c_dp, C.c_int, c_ip, C.c_int, c_dp, C.c_int, c_dp]
+    V = np.ascontiguousarray(V, np.float64)
+    F = np.ascontiguousarray(F, np.int32)
+    Q = np.ascontiguousarray(Q, np.float64)
+    out = np.zeros_like(Q)
+    P.port_geo_closest_points(_dp(V), len(V), _ip(F), len(F), _dp(Q), len(Q), _dp(out))
+    return out
+
+
+def port_tri_prox(F, variant="hard", limit_min=-100.0, limit_max=100.0):
+    P = port_lib()
+    P.port_tri_prox.argtypes = [C.c_int, c_dp, C.c_int, C.c_double, C.c_double]
+    P.port_tri_prox.restype = None
+    z = np.ascontiguousarray(F, np.float64).reshape(-1, 6).copy()
+    P.port_tri_prox(0 if variant == "xzu" else 1, _dp(z), len(z), limit_min, limit_max)
+    return z
+
+
+def port_collision_prox(types, prm, pts):
+    P = port_lib()
+    P.port_collision_prox.argtypes = [C.c_int, c_ip, c_dp, c_dp, C.c_int]
+    P.port_collision_prox.restype = None
+    types = np.ascontiguousarray(types, np.int32)
+    prm = np.ascontiguousarray(prm, np.float64).reshape(-1, 7)
+    z = np.ascontiguousarray(pts, np.float64).reshape(-1, 3).copy()
+    P.port_collision_prox(len(types), _ip(types), _dp(prm), _dp(z), len(z))
+    return z
+
+
+# ---------------------------------------------------------------------------------------------
 # Reference Geometry solver (oracle/_ref/libref_geo.so)
 # ---------------------------------------------------------------------------------------------
 def have_ref_geo():

@@ -101,6 +101,31 @@ def test_gs_solve_vs_reference(gpu, refgeo, kind, m, rho):
     assert np.abs(xg - xr).max() / np.abs(xr).max() < 1e-6
 
 
+@pytest.mark.parametrize("variant", ["alm", "gs"])
+@pytest.mark.parametrize("kind,rho,m", [("planarity", 1e5, 4), ("wiremesh", 1e3, 0), ("wiremesh", 1e3, 4)])
+def test_solve_vs_c_port(gpu, variant, kind, rho, m):
+    """Product against the plain-C restatement (oracle/port/aaadmm_port_geo.c), which needs no compiled reference."""
+    from oracle import refbind
+    nx, ny = 9, 7
+    P, quads, vid = wavy_grid(nx, ny)
+    V, F = ref_surface(nx, ny)
+    build = build_planarity if kind == "planarity" else build_wiremesh
+    g = gpu.GeometrySolver(variant=variant)
+    build(g, P, quads, vid, V, F)
+    g.setup(len(P), rho)
+    hg, xg = g.solve(P, 40, m)
+    p = refbind.PortGeometrySolver(variant == "alm")
+    build(p, P, quads, vid, V, F)
+    p.setup(len(P), rho)
+    hp, xp = p.solve(P, 40, m)
+    assert len(hg) == len(hp) == 40
+    rel = np.abs(hg - hp) / hp
+    floor = np.abs(hg - hp) / hp[0]
+    assert rel[:6].max() < 1e-8
+    assert floor.max() < (1e-9 if m == 0 else 1e-5)
+    assert np.abs(xg - xp).max() / np.abs(xp).max() < 1e-6
+
+
 # ---- the reference's own applications on the shipped meshes (cfg 2 and cfg 3) -------------------
 import os  # noqa: E402
 

@@ -106,3 +106,73 @@ def test_port_vs_compiled_reference_fresh_inputs(ref):
         x, rank = R.port_cod_solve(M, rhs)
         assert rank == ref.ref_cod_rank(M)
         assert np.abs(x - ref.ref_cod_solve(M, rhs)).max() < 1e-9 * max(1.0, np.abs(x).max())
+
+
+# ---- C restatement of the Geometry path and of the triangle / collision terms vs the compiled reference -----
+@pytest.fixture(scope="module")
+def refgeo():
+    if not R.have_ref_geo():
+        pytest.skip("oracle/_ref/libref_geo.so not present")
+    return R
+
+
+def test_port_geo_projections_and_closest_point_vs_reference(refgeo):
+    rng = np.random.default_rng(2)
+    for kind, k, prm in ((0, 4, (0, 0, 0, 0)), (0, 6, (0, 0, 0, 0)), (1, 1, (0.7, 0, 0, 0)),
+                         (2, 2, (0.6, 2.3, np.cos(0.6), np.cos(2.3)))):
+        cols = rng.standard_normal((500, k, 3))
+        if kind == 0:
+            cols -= cols.mean(axis=1, keepdims=True)
+        a = R.port_geo_project(kind, cols, prm)
+        b = refgeo.ref_geo_project(kind, cols, *((0.7, 0.0) if kind == 1 else ((0.6, 2.3) if kind == 2 else ())))
+        assert np.abs(a - b).max() < 1e-11, kind
+    from geo_scenes import ref_surface
+    V, F = ref_surface(9, 7)
+    Q = rng.uniform(-1, 9, (400, 3))
+    cr = refgeo.ref_geo_closest_points(V, F, Q)
+    cr = cr[0] if isinstance(cr, tuple) else cr
+    assert np.abs(R.port_geo_closest_points(V, F, Q) - cr).max() < 1e-12
+
+
+@pytest.mark.parametrize("use_alm", [True, False])
+@pytest.mark.parametrize("kind,rho", [("planarity", 1e5), ("wiremesh", 1e3)])
+@pytest.mark.parametrize("m", [0, 4])
+def test_port_geo_solve_vs_reference(refgeo, use_alm, kind, rho, m):
+    """ALMGeometrySolver / GeometrySolver loops of the C restatement against the unmodified classes."""
+    from geo_scenes import build_planarity, build_wiremesh, ref_surface, wavy_grid
+    nx, ny = 9, 7
+    P, quads, vid = wavy_grid(nx, ny)
+    V, F = ref_surface(nx, ny)
+    build = build_planarity if kind == "planarity" else build_wiremesh
+    p = R.PortGeometrySolver(use_alm)
+    build(p, P, quads, vid, V, F)
+    p.setup(len(P), rho)
+    hp, xp = p.solve(P, 40, m)
+    r = refgeo.RefGeometrySolver(use_alm)
+    build(r, P, quads, vid, V, F)
+    r.setup(len(P), rho)
+    hr, xr = r.solve(P, 40, m)
+    assert len(hp) == len(hr) == 40
+    rel = np.abs(hp - hr) / hr
+    floor = np.abs(hp - hr) / hr[0]
+    assert rel[:6].max() < 1e-8
+    assert floor.max() < (1e-9 if m == 0 else 1e-5)
+    assert np.abs(xp - xr).max() / np.abs(xr).max() < 1e-6
+
+
+def test_port_tri_and_collision_prox_vs_reference(ref):
+    rng = np.random.default_rng(4)
+    n = 2000
+    Q = np.linalg.qr(rng.standard_normal((n, 3, 3)))[0][:, :, :2]
+    F = Q @ (np.eye(2) + 0.6 * rng.standard_normal((n, 2, 2)))
+    F6 = np.concatenate([F[:, :, 0], F[:, :, 1]], axis=1)
+    for variant in ("hard", "xzu"):
+        for lim in ((-100.0, 100.0), (0.9, 1.1)):
+            a = R.port_tri_prox(F6, variant, *lim)
+            b = ref.ref_tri_prox(F6, variant, *lim)
+            assert np.abs(a - b).max() < 1e-11 * max(1.0, np.abs(b).max())
+    types = [0, 1, 2, 3, 4]
+    prm = [[-0.8, 0, 0, 0, 0, 0, 0], [0.2, -0.5, 0.1, 0.3, 1.0, -0.2, 0], [0.5, 0.2, -0.3, 0, 0, 0, 0.6],
+           [-0.6, -0.4, 0.5, 0, 0, 0, 0.5], [1.0, 0.8, 0.0, 0, 0, 0, 0.35]]
+    pts = rng.uniform(-1.5, 1.5, (5000, 3))
+    assert np.abs(R.port_collision_prox(types, prm, pts) - ref.ref_collision_prox(types, prm, pts)).max() < 1e-14
