@@ -574,6 +574,17 @@ def port_geo_closest_points(V, F, Q):
     return out
 
 
+def port_tet_prox_hyper(material, mu, lam, vol, F):
+    """C restatement of HyperElasticTet::prox on (n, 9) column-major blocks: returns (prox, gradient of the inputs)."""
+    P = port_lib()
+    P.port_tet_prox_hyper.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, c_dp, c_dp, C.c_int]
+    P.port_tet_prox_hyper.restype = None
+    z = np.ascontiguousarray(F, np.float64).reshape(-1, 9).copy()
+    g = np.zeros_like(z)
+    P.port_tet_prox_hyper(int(material), mu, lam, vol, _dp(z), _dp(g), len(z))
+    return z, g
+
+
 def port_tri_prox(F, variant="hard", limit_min=-100.0, limit_max=100.0):
     P = port_lib()
     P.port_tri_prox.argtypes = [C.c_int, c_dp, C.c_int, C.c_double, C.c_double]

@@ -176,3 +176,25 @@ def test_port_tri_and_collision_prox_vs_reference(ref):
            [-0.6, -0.4, 0.5, 0, 0, 0, 0.5], [1.0, 0.8, 0.0, 0, 0, 0, 0.35]]
     pts = rng.uniform(-1.5, 1.5, (5000, 3))
     assert np.abs(R.port_collision_prox(types, prm, pts) - ref.ref_collision_prox(types, prm, pts)).max() < 1e-14
+
+
+def test_port_hyper_prox_vs_reference(ref):
+    """C restatement of the per-tet L-BFGS prox (Neo-Hookean, StVK) against the unmodified reference classes."""
+    import ctypes as C
+    L = ref._load("libref_xzu.so")
+    dp = C.POINTER(C.c_double)
+    L.ref_xzu_tet_prox_hyper.argtypes = [C.c_int, dp, C.c_double, C.c_double, dp, dp, C.c_int]
+    verts = np.array([[0, 0, 0], [0.08, 0, 0], [0, 0.09, 0], [0, 0, 0.085]], float).reshape(-1)
+    E, nu = 1e7, 0.399
+    mu, lam = E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu))
+    _, vol, _ = ref.ref_tet_constants(verts.reshape(4, 3), E, nu)
+    rng = np.random.default_rng(0)
+    F = np.eye(3).reshape(1, 9) + 0.15 * rng.standard_normal((1000, 9))
+    for mat in (1, 2):
+        zr, gr = F.copy(), np.zeros_like(F)
+        assert L.ref_xzu_tet_prox_hyper(mat, verts.ctypes.data_as(dp), E, nu, zr.ctypes.data_as(dp), gr.ctypes.data_as(dp), len(F)) == 0
+        zp, gp = R.port_tet_prox_hyper(mat, mu, lam, vol, F)
+        d = np.abs(zr - zp).max(axis=1)
+        # the stopping rules make the iteration count round-off dependent: a few blocks stop one step apart
+        assert np.median(d) < 1e-15 and d.max() < 1e-7
+        assert np.abs(gr - gp).max() <= 1e-13 * np.abs(gr).max()
