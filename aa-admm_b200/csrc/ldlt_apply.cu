@@ -958,6 +958,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     const int tile_entries = env_int("AAADMM_TILE_ENTRIES", 32768);
     const int min_lrt = env_int("AAADMM_MIN_LRT", 3);  // smallest forward tile: 8 rows
     const int min_ctas_f = env_int("AAADMM_MIN_CTAS_F", min_ctas);
+    const int min_ctas_wide_f = env_int("AAADMM_MIN_CTAS_WIDE_F", min_ctas_f), min_ctas_wide_b = env_int("AAADMM_MIN_CTAS_WIDE_B", min_ctas);
     std::vector<std::vector<int>> by_level(nlev);
     for (int b = 0; b < nb; ++b) by_level[level[b]].push_back(b);
     std::vector<SweepTask> tasks;
@@ -1011,7 +1012,15 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
             for (int b : v) c += (fr[b].ns + fr[b].k + (1 << lrt[b]) - 1) >> lrt[b];
             return c;
         };
-        for (int pass = 0; pass < 6 && count_f() < min_ctas_f; ++pass)
+        // levels of wide fronts (their vector arrives by bulk copy: splitting costs no redundant gathers) are cut
+        // finer than the others
+        bool wide_f = false, wide_b = false;
+        for (int b : v) {
+            wide_f = wide_f || (wide_on && fr[b].ns > ws_cap);
+            wide_b = wide_b || (wide_on && fr[b].ld > v_cap);
+        }
+        const int target_f = wide_f ? min_ctas_wide_f : min_ctas_f, target_b = wide_b ? min_ctas_wide_b : min_ctas;
+        for (int pass = 0; pass < 6 && count_f() < target_f; ++pass)
             for (int b : v)
                 if (lrt[b] > min_lrt && fr[b].ns >= 4 * ((2 * CTA) >> (lrt[b] - 1))) lrt[b]--;
         int cap = 128;
@@ -1026,7 +1035,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
             }
             return c;
         };
-        while (set_cols(bcw[l]) < min_ctas) {
+        while (set_cols(bcw[l]) < target_b) {
             if (cap > 8 * bcw[l])
                 cap /= 2;
             else if (bcw[l] > 1)
