@@ -82,7 +82,8 @@ constexpr int NCONS = CTA;          // consumer threads
 constexpr int NTHR = CTA + 32;      // + producer warp
 constexpr int STG = 2048;           // doubles per stage (16 KB)
 constexpr int NSTG = 3;
-constexpr int WCH = 512;            // wide fronts: columns / rows of the assembled vector per half buffer
+constexpr int WCH = 256;            // wide fronts: columns / rows of the assembled vector per buffer
+constexpr int NWB = 4;              // ... and the number of such buffers (NWB - 1 chunks in flight)
 constexpr int ACOLS = 256;          // entries one assemble task handles
 
 // Programmatic dependent launch: the next level's kernel may start (and fill its ring with factor data,
@@ -123,7 +124,7 @@ __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 256;\n" 
 
 struct PipeBars {
     uint64_t full[NSTG], empty[NSTG];
-    uint64_t wfull[2];  // the two halves of the vector buffer of a wide front
+    uint64_t wfull[NWB];  // the buffers of the assembled vector of a wide front
 };
 __device__ __forceinline__ void pipe_init(PipeBars &B) {
     if (threadIdx.x == 0) {
@@ -132,8 +133,8 @@ __device__ __forceinline__ void pipe_init(PipeBars &B) {
             mbar_init(&B.full[i], 1);
             mbar_init(&B.empty[i], NCONS / 32);
         }
-        mbar_init(&B.wfull[0], 1);
-        mbar_init(&B.wfull[1], 1);
+#pragma unroll
+        for (int i = 0; i < NWB; ++i) mbar_init(&B.wfull[i], 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -172,7 +173,7 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const Gather &G,
     if (fin && frow >= F.ns) gather_add<NR>(G, F.g_off + frow, U, 1.0, pass);
     int it = 0;
     // Wide fronts (F.cw != 0): w was assembled in place in W by the front's assemble tasks; it arrives in
-    // halves of WCH columns by bulk copy, the next half in flight while this one is used.
+    // chunks of WCH columns by bulk copy, NWB - 1 chunks in flight while one is used.
     const bool wide = F.cw != 0;
     const int chunk = wide ? WCH : ws_cap;
     constexpr int HALF = WCH * NR + 2;
@@ -181,19 +182,18 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const Gather &G,
         const size_t idx = (size_t)(F.first + jc) * NR;
         const int sh = (int)(idx & 1);  // bulk copies want 16-byte aligned sources
         const unsigned bytes = (unsigned)(((min(ncols - jc, WCH) * NR + sh + 1) & ~1) * 8);
-        mbar_expect_tx(&B.wfull[c & 1], bytes);
-        bulk_g2s(ws + (c & 1) * HALF, W + idx - sh, bytes, &B.wfull[c & 1]);
+        mbar_expect_tx(&B.wfull[c % NWB], bytes);
+        bulk_g2s(ws + (c % NWB) * HALF, W + idx - sh, bytes, &B.wfull[c % NWB]);
     };
     if (wide && threadIdx.x == 0) {
-        issue_w(0);
-        if (WCH < ncols) issue_w(1);
+        for (int c = 0; c < NWB && c * WCH < ncols; ++c) issue_w(c);
     }
     for (int jc = 0, ci = 0; jc < ncols; jc += chunk, ++ci) {
         const int jn = min(ncols - jc, chunk);
         const double *wbase = ws;
         if (wide) {
-            mbar_wait(&B.wfull[ci & 1], (ci >> 1) & 1);
-            wbase = ws + (ci & 1) * HALF + (((size_t)(F.first + jc) * NR) & 1);
+            mbar_wait(&B.wfull[ci % NWB], (ci / NWB) & 1);
+            wbase = ws + (ci % NWB) * HALF + (((size_t)(F.first + jc) * NR) & 1);
         } else {
         if (jc > 0) cons_sync();
         // w_j = rhs_j - sum of the child updates that land on column j (4 columns per thread in flight)
@@ -275,7 +275,7 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const Gather &G,
         }
         if (wide) {
             cons_sync();  // everyone is done with this half
-            if (threadIdx.x == 0 && (ci + 2) * WCH < ncols) issue_w(ci + 2);
+            if (threadIdx.x == 0 && (ci + NWB) * WCH < ncols) issue_w(ci + NWB);
         }
     }
     cons_sync();  // every consumer is done with the ring
@@ -393,19 +393,18 @@ __device__ __forceinline__ void bwd_task(const SweepTask &F, const int *__restri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool single = (F.ld - c0) <= v_cap;  // v fits at once: staged once, several column passes allowed
     // Wide fronts (F.cw & 8): v was assembled once per front in Va by the front's assemble tasks and arrives
-    // in halves of WCH rows by bulk copy, the next half in flight while this one is used.
+    // in chunks of WCH rows by bulk copy, NWB - 1 chunks in flight while one is used.
     const bool wide = (F.cw & 8) != 0;
     const int chunk = wide ? WCH : v_cap;
     constexpr int HALF = WCH * NR + 2;
     auto issue_v = [&](int c) {
         const int rc = c0 + c * WCH;
         const unsigned bytes = (unsigned)(((min(F.ld - rc, WCH) * NR + 1) & ~1) * 8);
-        mbar_expect_tx(&B.wfull[c & 1], bytes);
-        bulk_g2s(vs + (c & 1) * HALF, Va + (size_t)(F.u_off + rc) * NR, bytes, &B.wfull[c & 1]);
+        mbar_expect_tx(&B.wfull[c % NWB], bytes);
+        bulk_g2s(vs + (c % NWB) * HALF, Va + (size_t)(F.u_off + rc) * NR, bytes, &B.wfull[c % NWB]);
     };
     if (wide && threadIdx.x == 0) {
-        issue_v(0);
-        if (c0 + WCH < F.ld) issue_v(1);
+        for (int c = 0; c < NWB && c0 + c * WCH < F.ld; ++c) issue_v(c);
     }
     int it = 0;
     for (int jb0 = c0; jb0 < cend; jb0 += NC) {
@@ -420,8 +419,8 @@ __device__ __forceinline__ void bwd_task(const SweepTask &F, const int *__restri
             const int re = min(F.ld, rc + chunk);
             const double *vbase = vs;
             if (wide) {
-                mbar_wait(&B.wfull[ci & 1], (ci >> 1) & 1);
-                vbase = vs + (ci & 1) * HALF;
+                mbar_wait(&B.wfull[ci % NWB], (ci / NWB) & 1);
+                vbase = vs + (ci % NWB) * HALF;
             } else if (!(single && jb0 > c0)) {
                 if (rc > c0) cons_sync();
                 // v = [ D^-1 y of the front's columns ; -x of the rows below ; 0 ] (4 rows per thread in flight)
@@ -493,7 +492,7 @@ __device__ __forceinline__ void bwd_task(const SweepTask &F, const int *__restri
             }
             if (wide) {
                 cons_sync();  // everyone is done with this half
-                if (threadIdx.x == 0 && c0 + (ci + 2) * WCH < F.ld) issue_v(ci + 2);
+                if (threadIdx.x == 0 && c0 + (ci + NWB) * WCH < F.ld) issue_v(ci + NWB);
             }
         }
 #pragma unroll
@@ -1303,9 +1302,9 @@ static int apply_impl(LdltDev *f, double *x_out, cudaStream_t s, const int *skip
     G.ptr = f->gptr;
     G.idx = f->gidx;
     const size_t ring = (size_t)NSTG * STG * sizeof(double);
-    AAADMM_CUDA_OK(launch_sweep(k_fwd_front<NR>, f->n_ftasks, ring + (std::max<size_t>((size_t)f->ws_cap * NR, 2 * (WCH * NR + 2)) + 8) * sizeof(double), s, f->tasks, f->ctl,
+    AAADMM_CUDA_OK(launch_sweep(k_fwd_front<NR>, f->n_ftasks, ring + (std::max<size_t>((size_t)f->ws_cap * NR, NWB * (WCH * NR + 2)) + 8) * sizeof(double), s, f->tasks, f->ctl,
                                 f->Mf, G, f->W, f->dinv, f->Yd, f->U, skip, f->ws_cap, f->trace));
-    AAADMM_CUDA_OK(launch_sweep(k_bwd_front<NR>, f->n_btasks, ring + (std::max<size_t>((size_t)f->v_cap * NR, 2 * (WCH * NR + 2)) + 8) * sizeof(double), s,
+    AAADMM_CUDA_OK(launch_sweep(k_bwd_front<NR>, f->n_btasks, ring + (std::max<size_t>((size_t)f->v_cap * NR, NWB * (WCH * NR + 2)) + 8) * sizeof(double), s,
                                 f->tasks + f->n_ftasks, f->ctl, f->Mb, f->rows, f->Yd, f->X, f->Va, f->perm, x_out, skip, f->v_cap,
                                 f->trace ? f->trace + 4 * (size_t)f->n_ftasks : nullptr));
     AAADMM_CUDA_OK(cudaGetLastError());
