@@ -470,11 +470,20 @@ __device__ __forceinline__ void bwd_task(const SweepTask &F, const int *__restri
                 for (int t = 0; t < RB / 64; ++t) {
                     const int r = 64 * t + 2 * lane;
                     if (r < nrow) {
+                        // rows r and r + 1 of v: 2 * NR consecutive doubles, 16-byte aligned (r is even) - read as
+                        // 16-byte pieces: 8-byte loads at this 48-byte lane stride run into 4-way bank conflicts
                         double v0[NR], v1[NR];
+                        {
+                            double2 tq[NR];
+                            const double2 *vp2 = reinterpret_cast<const double2 *>(vp + r * NR);
 #pragma unroll
-                        for (int q = 0; q < NR; ++q) {
-                            v0[q] = vp[r * NR + q];
-                            v1[q] = vp[(r + 1) * NR + q];
+                            for (int q = 0; q < NR; ++q) tq[q] = vp2[q];
+                            const double *tf = reinterpret_cast<const double *>(tq);
+#pragma unroll
+                            for (int q = 0; q < NR; ++q) {
+                                v0[q] = tf[q];
+                                v1[q] = tf[NR + q];
+                            }
                         }
 #pragma unroll
                         for (int c = 0; c < CW; ++c) {
