@@ -963,7 +963,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     // order (forward bottom-up, backward top-down) and synchronise through per-front arrival counters.
     const bool wide_on = env_int("AAADMM_WIDE", 1) != 0;
     const int min_ctas = env_int("AAADMM_MIN_CTAS", 148);  // one CTA per SM; each keeps 48 KB of loads in flight
-    const int tile_entries = env_int("AAADMM_TILE_ENTRIES", 32768);
+    const int tile_entries = env_int("AAADMM_TILE_ENTRIES", 65536);
     const int min_lrt = env_int("AAADMM_MIN_LRT", 3);  // smallest forward tile: 8 rows
     const int min_ctas_f = env_int("AAADMM_MIN_CTAS_F", min_ctas);
     const int min_ctas_wide_f = env_int("AAADMM_MIN_CTAS_WIDE_F", min_ctas_f), min_ctas_wide_b = env_int("AAADMM_MIN_CTAS_WIDE_B", min_ctas);
