@@ -528,7 +528,7 @@ __device__ __forceinline__ void bwd_task(const SweepTask &F, const int *__restri
 }
 
 template <int NR>
-__global__ void __launch_bounds__(NTHR)
+__global__ void __launch_bounds__(NTHR, 3)
 k_bwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restrict__ Mb,
             const int *__restrict__ rows, const double *Yd, double *X, double *Va, const int *__restrict__ perm,
             double *__restrict__ x_out, const int *skip, int v_cap, unsigned long long *trace) {
