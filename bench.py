@@ -303,7 +303,7 @@ def run_gpu(args):
     return 0
 
 
-NCU_LDLT_TRAFFIC_BYTES = 2.224e9
+NCU_LDLT_TRAFFIC_BYTES = 2.232e9
 
 
 def main():
