@@ -127,6 +127,8 @@ def host_lib():
         H.aaadmm_host_solver_new.restype = vp
         H.aaadmm_host_solver_free.argtypes = [vp]
         H.aaadmm_host_solver_add_tetmesh.argtypes = [vp, c_fp, C.c_int, c_ip, C.c_int, c_fp, C.c_double, C.c_double, C.c_int]
+        H.aaadmm_host_solver_add_trimesh.argtypes = [vp, c_fp, C.c_int, c_ip, C.c_int, c_fp, C.c_double, C.c_double,
+                                                     C.c_double, C.c_double]
         H.aaadmm_host_solver_set_pins.argtypes = [vp, c_ip, c_dp, C.c_int]
         H.aaadmm_host_solver_initialize.argtypes = [vp, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
                                                     C.c_int, C.c_int]
@@ -145,6 +147,12 @@ def host_lib():
         H.aaadmm_host_solver_device_factor.argtypes = [vp]
         H.aaadmm_host_tet_constants.argtypes = [c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp]
         H.aaadmm_host_tri_constants.argtypes = [c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp]
+        H.aaadmm_host_system_new.restype = vp
+        H.aaadmm_host_system_new.argtypes = [c_fp, C.c_int, c_ip, C.c_int, c_ip, C.c_int, c_fp, C.c_double, C.c_double,
+                                             c_ip, C.c_int, C.c_double]
+        H.aaadmm_host_system_free.argtypes = [vp]
+        H.aaadmm_host_system_counts.argtypes = [vp, c_ip, C.POINTER(C.c_int64)]
+        H.aaadmm_host_system_copy.argtypes = [vp, C.POINTER(C.c_int64), c_ip, c_dp, c_ip]
         _host = H
     return _host
 
@@ -411,6 +419,17 @@ class Solver:
             _hk(r)
         return r
 
+    def add_trimesh(self, verts, tris, masses, youngs=1e7, poisson=0.399, limit_min=-100.0, limit_max=100.0):
+        """binding::add_trimesh: nodes + TriEnergyTerm per triangle (hard_zxu ordering only)."""
+        verts = np.ascontiguousarray(verts, np.float32)
+        tris = np.ascontiguousarray(tris, np.int32)
+        masses = np.ascontiguousarray(masses, np.float32)
+        r = self.H.aaadmm_host_solver_add_trimesh(self.h, _fp(verts), len(verts), _ip(tris), len(tris), _fp(masses),
+                                                  youngs, poisson, limit_min, limit_max)
+        if r < 0:
+            _hk(r)
+        return r
+
     def set_pins(self, idx, pts):
         idx = np.ascontiguousarray(idx, np.int32)
         pts = np.ascontiguousarray(pts, np.float64)
@@ -481,6 +500,39 @@ class Solver:
         by = np.zeros(NPROF)
         _ck(cuda_lib().aaadmm_tetscene_algo_bytes(self._scene(), anderson_m, _dp(by)))
         return {n: dict(ms=float(ms[i]), bytes=float(by[i])) for i, n in enumerate(PROF_NAMES)}
+
+
+def host_system_matrix(verts, tets, tris, masses, pins, rho_dt2, youngs=1e7, poisson=0.399):
+    """Host setup only: scalar system matrix Ahat (A = M + rho dt^2 D^T W^2 D = Ahat (x) I3) of a scene of tets and
+    triangles with the pinned vertices eliminated. Returns (dense lower-filled symmetric n_free x n_free array,
+    dev_to_vert); for tests on small scenes."""
+    H = host_lib()
+    verts = np.ascontiguousarray(verts, np.float32)
+    tets = np.ascontiguousarray(tets, np.int32).reshape(-1, 4)
+    tris = np.ascontiguousarray(tris, np.int32).reshape(-1, 3)
+    masses = np.ascontiguousarray(masses, np.float32)
+    pins = np.ascontiguousarray(pins, np.int32)
+    h = H.aaadmm_host_system_new(_fp(verts), len(verts), _ip(tets), len(tets), _ip(tris), len(tris), _fp(masses),
+                                 youngs, poisson, _ip(pins), len(pins), rho_dt2)
+    if not h:
+        raise AaadmmError(H.aaadmm_host_last_error().decode())
+    try:
+        nf, nnz = C.c_int(0), C.c_int64(0)
+        H.aaadmm_host_system_counts(h, C.byref(nf), C.byref(nnz))
+        Ap = np.zeros(nf.value + 1, np.int64)
+        Ai = np.zeros(nnz.value, np.int32)
+        Ax = np.zeros(nnz.value)
+        d2v = np.zeros(len(verts), np.int32)
+        H.aaadmm_host_system_copy(h, _lp(Ap), _ip(Ai), _dp(Ax), _ip(d2v))
+    finally:
+        H.aaadmm_host_system_free(h)
+    n = nf.value
+    M = np.zeros((n, n))
+    for j in range(n):
+        for p in range(Ap[j], Ap[j + 1]):
+            M[Ai[p], j] = Ax[p]
+            M[j, Ai[p]] = Ax[p]
+    return M, d2v
 
 
 def tri_prox(F, variant="hard", limit_min=-100.0, limit_max=100.0):

@@ -84,6 +84,8 @@ __global__ void k_init_state(SolveState *st, int accel, int m, double eps, int m
     st->aa_skip = 0;
     st->prim2 = 0.0;
     st->hyper_prim2 = 0.0;
+    st->tri_prim2 = 0.0;
+    st->tri_comb = 0.0;
     st->prev_prim = 1e+20;
     st->comb = 0.0;
     st->eps = eps;
@@ -148,6 +150,10 @@ struct aaadmm_tetscene {
     int *material = nullptr, *hyper_ids = nullptr;
     double *mu = nullptr, *lambda = nullptr, *volume = nullptr;
     int n_hyper = 0;
+    // triangle terms (hard_zxu only): u / z planes follow the tets' inside Ubuf / Gbuf / z, contributions behind 12 T
+    int NT = 0;
+    int4 *tri_idx = nullptr;
+    double *tri_rp = nullptr, *tri_w = nullptr, *tri_lmin = nullptr, *tri_lmax = nullptr;
     int64_t *inc_ptr = nullptr;
     int *inc = nullptr;
     // state
@@ -368,6 +374,11 @@ int aaadmm_tetscene_destroy(aaadmm_tetscene *s) {
     cudaFree(s->mu);
     cudaFree(s->lambda);
     cudaFree(s->volume);
+    cudaFree(s->tri_idx);
+    cudaFree(s->tri_rp);
+    cudaFree(s->tri_w);
+    cudaFree(s->tri_lmin);
+    cudaFree(s->tri_lmax);
     cudaFree(s->inc_ptr);
     cudaFree(s->inc);
     cudaFree(s->Ubuf);
@@ -405,8 +416,13 @@ int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *d,
         set_last_error("tetscene_create: no CUDA device (this library has no CPU path)");
         return -1;
     }
-    if (!d || !factor || d->n_tets <= 0 || d->n_free <= 0 || d->n_free > d->n_verts) {
+    if (!d || !factor || d->n_tets < 0 || d->n_tris < 0 || d->n_tets + d->n_tris <= 0 || d->n_free <= 0 ||
+        d->n_free > d->n_verts) {
         set_last_error("tetscene_create: bad arguments");
+        return -1;
+    }
+    if (d->n_tris > 0 && (!d->tri || !d->tri_rest_pose || !d->tri_weight)) {
+        set_last_error("tetscene_create: triangle terms need tri, tri_rest_pose and tri_weight");
         return -1;
     }
     if (factor->f->n != d->n_free || factor->f->nrhs != 3) {
@@ -435,7 +451,9 @@ int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *d,
     s->NP = V - NF;
     s->rho_dt2 = d->rho_dt2;
     s->factor = factor;
-    s->Ne = 9 * (int64_t)T;
+    const int NT = d->n_tris;
+    s->NT = NT;
+    s->Ne = 9 * (int64_t)T + 6 * (int64_t)NT;
     s->Nt = s->Ne + 3 * (int64_t)NF;
     s->Nbuf = s->Ne + 3 * (int64_t)V;
     AAADMM_CUDA_OK(cudaStreamCreate(&s->stream));
@@ -444,13 +462,33 @@ int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *d,
     std::vector<double> binv_soa((size_t)9 * T);
     for (int t = 0; t < T; ++t)
         for (int k = 0; k < 9; ++k) binv_soa[(size_t)k * T + t] = d->binv[9 * (size_t)t + k];
-    AAADMM_CUDA_OK(cudaMalloc((void **)&s->idx, sizeof(int4) * T));
+    if (NT > 0) {
+        std::vector<int> idx4((size_t)4 * NT, 0);
+        std::vector<double> rp_soa((size_t)4 * NT), lmin(NT, -100.0), lmax(NT, 100.0);
+        for (int t = 0; t < NT; ++t) {
+            for (int c = 0; c < 3; ++c) idx4[4 * (size_t)t + c] = d->tri[3 * (size_t)t + c];
+            for (int k = 0; k < 4; ++k) rp_soa[(size_t)k * NT + t] = d->tri_rest_pose[4 * (size_t)t + k];
+            if (d->tri_limit_min) lmin[t] = d->tri_limit_min[t];
+            if (d->tri_limit_max) lmax[t] = d->tri_limit_max[t];
+        }
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->tri_idx, sizeof(int4) * NT));
+        AAADMM_CUDA_OK(cudaMemcpy(s->tri_idx, idx4.data(), sizeof(int4) * NT, cudaMemcpyHostToDevice));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->tri_rp, sizeof(double) * 4 * NT));
+        AAADMM_CUDA_OK(cudaMemcpy(s->tri_rp, rp_soa.data(), sizeof(double) * 4 * NT, cudaMemcpyHostToDevice));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->tri_w, sizeof(double) * NT));
+        AAADMM_CUDA_OK(cudaMemcpy(s->tri_w, d->tri_weight, sizeof(double) * NT, cudaMemcpyHostToDevice));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->tri_lmin, sizeof(double) * NT));
+        AAADMM_CUDA_OK(cudaMemcpy(s->tri_lmin, lmin.data(), sizeof(double) * NT, cudaMemcpyHostToDevice));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->tri_lmax, sizeof(double) * NT));
+        AAADMM_CUDA_OK(cudaMemcpy(s->tri_lmax, lmax.data(), sizeof(double) * NT, cudaMemcpyHostToDevice));
+    }
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->idx, sizeof(int4) * std::max(T, 1)));
     AAADMM_CUDA_OK(cudaMemcpy(s->idx, d->tet, sizeof(int) * 4 * T, cudaMemcpyHostToDevice));
-    AAADMM_CUDA_OK(cudaMalloc((void **)&s->binv, sizeof(double) * 9 * T));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->binv, sizeof(double) * 9 * std::max(T, 1)));
     AAADMM_CUDA_OK(cudaMemcpy(s->binv, binv_soa.data(), sizeof(double) * 9 * T, cudaMemcpyHostToDevice));
-    AAADMM_CUDA_OK(cudaMalloc((void **)&s->w, sizeof(double) * T));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->w, sizeof(double) * std::max(T, 1)));
     AAADMM_CUDA_OK(cudaMemcpy(s->w, d->weight, sizeof(double) * T, cudaMemcpyHostToDevice));
-    AAADMM_CUDA_OK(cudaMalloc((void **)&s->kvol, sizeof(double) * T));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->kvol, sizeof(double) * std::max(T, 1)));
     AAADMM_CUDA_OK(cudaMemcpy(s->kvol, d->kvol, sizeof(double) * T, cudaMemcpyHostToDevice));
     s->n_hyper = (int)hyper_ids.size();
     if (s->n_hyper > 0) {
@@ -475,8 +513,8 @@ int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *d,
     AAADMM_CUDA_OK(cudaMalloc((void **)&s->Ubuf, sizeof(double) * s->Nbuf));
     AAADMM_CUDA_OK(cudaMalloc((void **)&s->Gbuf, sizeof(double) * s->Nbuf));
     AAADMM_CUDA_OK(cudaMalloc((void **)&s->xs, sizeof(double) * 3 * V));
-    AAADMM_CUDA_OK(cudaMalloc((void **)&s->z, sizeof(double) * 9 * T));
-    AAADMM_CUDA_OK(cudaMalloc((void **)&s->contrib, sizeof(double) * 12 * T));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->z, sizeof(double) * s->Ne));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->contrib, sizeof(double) * (12 * (size_t)T + 9 * (size_t)NT)));
     AAADMM_CUDA_OK(cudaMalloc((void **)&s->bconst, sizeof(double) * 3 * NF));
     AAADMM_CUDA_OK(cudaMalloc((void **)&s->xbar, sizeof(double) * 3 * NF));
     AAADMM_CUDA_OK(cudaMalloc((void **)&s->xpin, sizeof(double) * 3 * std::max(1, s->NP)));
@@ -591,7 +629,7 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
     const bool accel = o->accel && o->anderson_m > 0;
     const int m = accel ? o->anderson_m : 1;
     TetArrays A{T, NF, s->V, s->idx, s->binv, s->w, s->kvol, s->rho_dt2, s->material, s->mu, s->lambda, s->volume, s->hyper_ids, s->n_hyper};
-    const int gt = std::min((T + TET_BLOCK - 1) / TET_BLOCK, stream_grid(8));
+    const int gt = std::max(1, std::min((T + TET_BLOCK - 1) / TET_BLOCK, stream_grid(8)));
     const int gv = (NF + 127) / 128;
     const int gs = stream_grid(4);
     double *Uu = s->Ubuf, *Ux = s->Ubuf + s->Ne;
@@ -599,6 +637,26 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
     int &L = s->launches;
     PhaseProf none;
     if (!prof) prof = &none;
+    // triangle terms: their u / z planes and contribution slots follow the tets'
+    const int NT = s->NT;
+    const size_t o9 = 9 * (size_t)T;
+    TriArrays R{NT, NF, s->tri_idx, s->tri_rp, s->tri_w, s->tri_lmin, s->tri_lmax, s->rho_dt2};
+    double *tri_contrib = s->contrib + 12 * (size_t)T;
+    auto update_z = [&](int mode) {
+        if (NT > 0) {
+            launch_tri_update_z_hard(mode, st, R, Ux, Uu + o9, s->z + o9, tri_contrib, s->st, s->partials);
+            ++L;
+        }
+        launch_update_z_hard(mode, gt, st, A, Ux, Uu, s->z, s->contrib, s->st, s->partials);
+    };
+    auto update_u = [&](int mode, double *u_out) {
+        if (NT > 0) {
+            launch_tri_update_u_hard(mode, st, R, s->xs, Ux, s->z + o9, Uu + o9, u_out + o9, s->st, s->partials);
+            ++L;
+        }
+        launch_update_u_hard(mode, gt, st, A, s->xs, Ux, s->z, Uu, u_out, s->st, s->partials, s->hist_prim,
+                             s->hist_comb, s->hist_rej);
+    };
 
     if (init_frame) {
         k_init_state<<<1, 1, 0, st>>>(s->st, accel ? 1 : 0, m, o->eps, iters);
@@ -612,12 +670,15 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
         AAADMM_CUDA_OK(cudaMemcpyAsync(Ux, s->xbar, sizeof(double) * 3 * NF, cudaMemcpyDeviceToDevice, st));
         AAADMM_CUDA_OK(cudaMemsetAsync(Uu, 0, sizeof(double) * s->Ne, st));
         launch_bconst(st, A, s->inc_ptr, s->inc, Ux, s->mass, s->xbar, s->bconst);
+        if (NT > 0) {
+            launch_tri_bconst(st, R, 4 * T, s->inc_ptr, s->inc, Ux, s->bconst);
+            ++L;
+        }
         // warm start (hard/src/Solver.cpp:99-114)
-        launch_update_z_hard(MODE_WARM, gt, st, A, Ux, Uu, s->z, s->contrib, s->st, s->partials);
+        update_z(MODE_WARM);
         launch_rhs_gather(st, NF, s->inc_ptr, s->inc, s->contrib, s->bconst, f->iperm, f->W, s->st);
         if (ldlt_dev_apply_permuted(f, s->xs, st, &s->st->done)) return -1;
-        launch_update_u_hard(MODE_WARM, gt, st, A, s->xs, Ux, s->z, Uu, Gu, s->st, s->partials, s->hist_prim,
-                             s->hist_comb, s->hist_rej);
+        update_u(MODE_WARM, Gu);
         AAADMM_CUDA_OK(cudaMemcpyAsync(Gx, s->xs, sizeof(double) * 3 * NF, cudaMemcpyDeviceToDevice, st));
         // default_(u,x) = curr_(u,x); accelerator->init(curr_u, curr_x)
         AAADMM_CUDA_OK(cudaMemcpyAsync(s->Ubuf, s->Gbuf, sizeof(double) * s->Nt, cudaMemcpyDeviceToDevice, st));
@@ -636,13 +697,13 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
     const int L_before = L;
     for (int it = 0; it < iters; ++it) {
         prof->begin(0);
-        launch_update_z_hard(MODE_ITER, gt, st, A, Ux, Uu, s->z, s->contrib, s->st, s->partials);
+        update_z(MODE_ITER);
         prof->end();
         ++L;
         if (accel) {
             prof->begin(6);
             launch_restore_if_reject(gs, st, s->Ubuf, s->Gbuf, s->Nt, s->st);
-            launch_update_z_hard(MODE_REDO, gt, st, A, Ux, Uu, s->z, s->contrib, s->st, s->partials);
+            update_z(MODE_REDO);
             prof->end();
             L += 2;
         }
@@ -654,12 +715,7 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
         prof->end();
         L += 1 + f->n_launches;
         prof->begin(3);
-        if (accel)
-            launch_update_u_hard(MODE_ITER, gt, st, A, s->xs, Ux, s->z, Uu, Gu, s->st, s->partials, s->hist_prim,
-                                 s->hist_comb, s->hist_rej);
-        else
-            launch_update_u_hard(MODE_ITER, gt, st, A, s->xs, Ux, s->z, Uu, Uu, s->st, s->partials, s->hist_prim,
-                                 s->hist_comb, s->hist_rej);
+        update_u(MODE_ITER, accel ? Gu : Uu);
         prof->end();
         ++L;
         if (accel) {
@@ -784,6 +840,10 @@ static int step_common(aaadmm_tetscene *s, const aaadmm_step_opts *o, bool host_
         return -1;
     }
     const bool xzu = o->ordering == AAADMM_ORDER_XZU;
+    if (xzu && s->NT > 0) {
+        set_last_error("tetscene_step: triangle terms run under the hard_zxu ordering only");
+        return -1;
+    }
     if (xzu && !s->xz_a) {
         AAADMM_CUDA_OK(cudaMalloc((void **)&s->xz_a, sizeof(double) * s->Ne));
         AAADMM_CUDA_OK(cudaMalloc((void **)&s->xz_b, sizeof(double) * s->Ne));
@@ -857,6 +917,7 @@ int aaadmm_tetscene_step_resident(aaadmm_tetscene *s, const aaadmm_step_opts *o,
 }
 
 int aaadmm_tetscene_read_zu(aaadmm_tetscene *s, double *z, double *u) {
+    if (s->T <= 0) return 0;  // tet terms only (reference layout of the tets' z / u)
     double *tmp = nullptr;
     AAADMM_CUDA_OK(cudaMalloc((void **)&tmp, sizeof(double) * 9 * s->T));
     const int g = (s->T + 255) / 256;
@@ -904,12 +965,14 @@ int aaadmm_tetscene_profile(aaadmm_tetscene *s, const aaadmm_step_opts *o, int i
 }
 
 int aaadmm_tetscene_algo_bytes(aaadmm_tetscene *s, int m, double *b) {
-    const double T = s->T, V = s->V, NF = s->NF, Ne = (double)s->Ne, Nt = (double)s->Nt;
-    const double ninc = 4.0 * T;  // upper bound: incidences of free vertices
+    const double T = s->T, V = s->V, NF = s->NF, Ne = (double)s->Ne, Nt = (double)s->Nt, R = s->NT;
+    const double ninc = 4.0 * T + 3.0 * R;  // upper bound: incidences of free vertices
     b[0] = T * (16 + 72 + 8 + 72 + 72 + 96) + 24 * V;           // update_z: idx,B^-1,w,u in; z,contrib out; positions
-    b[1] = T * 96 + 4 * ninc + NF * (8 + 24 + 24 + 4);          // rhs gather: contrib, inc, ptr, bconst, out, iperm
+    b[0] += R * (16 + 32 + 8 + 16 + 48 + 48 + 72);              // triangles: idx,rest pose,w,limits,u in; z,contrib out
+    b[1] = T * 96 + R * 72 + 4 * ninc + NF * (8 + 24 + 24 + 4); // rhs gather: contrib, inc, ptr, bconst, out, iperm
     b[2] = s->factor->f->stats.bytes_per_solve;                 // ldlt apply
     b[3] = T * (16 + 72 + 8 + 72 + 72 + 72) + 2 * 24 * V;       // update_u + residuals
+    b[3] += R * (16 + 32 + 8 + 48 + 48 + 48);
     b[4] = 8.0 * ((m + 2) * Ne + 3 * Nt);                       // aa pass 1
     b[5] = 8.0 * ((m + 3) * Nt + 2 * Ne);                       // aa pass 2
     b[6] = 0;

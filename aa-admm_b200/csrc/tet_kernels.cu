@@ -121,7 +121,7 @@ k_update_z_hard(TetArrays A, const double *__restrict__ pos, const double *__res
     double out[1];
     if (grid_reduce<1, TET_BLOCK>(acc, partials, &st->ticket, out)) {
         if (threadIdx.x == 0) {
-            const double tot = out[0] + st->hyper_prim2;
+            const double tot = out[0] + st->hyper_prim2 + st->tri_prim2;
             const double prim = sqrt(tot);
             st->prim2 = tot;
             if (MODE == MODE_ITER) {
@@ -161,8 +161,8 @@ __global__ void k_rhs_gather(int n_free, const int64_t *__restrict__ inc_ptr, co
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     const int64_t p1 = inc_ptr[v + 1];
     for (int64_t p = inc_ptr[v]; p < p1; ++p) {
-        const int e = inc[p];  // tet*4 + corner
-        const double *q = contrib + (size_t)(e >> 2) * 12 + (e & 3) * 3;
+        const int e = inc[p];  // contribution slot (tets: tet*4 + corner; triangles behind them)
+        const double *q = contrib + 3 * (size_t)e;
         s0 += q[0];
         s1 += q[1];
         s2 += q[2];
@@ -184,6 +184,7 @@ __global__ void k_bconst(TetArrays A, const int64_t *__restrict__ inc_ptr, const
     const int64_t p1 = inc_ptr[v + 1];
     for (int64_t p = inc_ptr[v]; p < p1; ++p) {
         const int e = inc[p];
+        if (e >= 4 * T) continue;  // triangle slot: k_tri_bconst
         const int t = e >> 2, c = e & 3;
         const int4 id = A.idx[t];
         const int ids[4] = {id.x, id.y, id.z, id.w};
@@ -257,7 +258,7 @@ k_update_u_hard(TetArrays A, const double *__restrict__ pos_new, const double *_
     double out[2];
     if (grid_reduce<2, TET_BLOCK>(acc, partials, &st->ticket, out)) {
         if (threadIdx.x == 0) {
-            const double comb = out[0] + out[1];
+            const double comb = out[0] + out[1] + st->tri_comb;
             st->comb = comb;
             if (comb < st->eps) {
                 st->done = 1;

@@ -26,6 +26,16 @@ struct TetArrays {
     int n_hyper;
 };
 
+// Triangle terms (tri_kernels.cu). rest_pose [4][N], u / z [6][N], contributions 9 doubles per triangle.
+struct TriArrays {
+    int n_tris, n_free;
+    const int4 *idx;          // [N] vertex ids in x, y, z
+    const double *rest_pose;  // [4][N] column-major 2x2
+    const double *w;          // [N]
+    const double *limit_min, *limit_max;  // [N]
+    double rho_dt2;
+};
+
 enum { MODE_WARM = 0, MODE_ITER = 1, MODE_REDO = 2 };
 
 // Host launchers (tet_kernels.cu is compiled with -fmad=false: the per-element arithmetic follows
@@ -36,6 +46,13 @@ void launch_update_z_hard(int mode, int grid, cudaStream_t s, const TetArrays &A
 void launch_update_u_hard(int mode, int grid, cudaStream_t s, const TetArrays &A, const double *pos_new,
                           const double *pos_last, const double *z, const double *u_in, double *u_out, SolveState *st,
                           double *partials, double *hist_prim, double *hist_comb, int *hist_rej);
+// Triangle terms: run before the tet launcher of the same phase (residual shares st->tri_prim2 / tri_comb).
+void launch_tri_update_z_hard(int mode, cudaStream_t s, const TriArrays &A, const double *pos, const double *u, double *z,
+                              double *contrib, SolveState *st, double *partials);
+void launch_tri_update_u_hard(int mode, cudaStream_t s, const TriArrays &A, const double *pos_new, const double *pos_last,
+                              const double *z, const double *u_in, double *u_out, SolveState *st, double *partials);
+void launch_tri_bconst(cudaStream_t s, const TriArrays &A, int slot0, const int64_t *inc_ptr, const int *inc,
+                       const double *pos, double *bconst);
 void launch_restore_if_reject(int grid, cudaStream_t s, double *ucur, const double *gdef, int64_t n, SolveState *st);
 void launch_rhs_gather(cudaStream_t s, int n_free, const int64_t *inc_ptr, const int *inc, const double *contrib,
                        const double *bconst, const int *iperm, double *W, const SolveState *st, int when = 0);

@@ -30,6 +30,19 @@ TetEnergyTerm::TetEnergyTerm(const Vec4i &tet_, const std::vector<Vec3> &verts, 
         throw std::runtime_error("**TetEnergyTerm Error: Inverted initial tet");
 }
 
+TriEnergyTerm::TriEnergyTerm(const Vec3i &tri_, const std::vector<Vec3> &verts, const Lame &lame_)
+    : tri(tri_), lame(lame_) {
+    if (lame.limit_min > 1.0) throw std::runtime_error("**TriEnergyTerm Error: Strain limit min should be -inf to 1");
+    if (lame.limit_max < 1.0) throw std::runtime_error("**TriEnergyTerm Error: Strain limit max should be 1 to inf");
+    double rest9[9];
+    for (int k = 0; k < 3; ++k) {
+        rest[k] = verts[k];
+        for (int j = 0; j < 3; ++j) rest9[3 * k + j] = verts[k][j];
+    }
+    if (!aaadmm::tri_constants(rest9, lame.youngs, lame.poisson, rest_pose.data(), &area, &weight))
+        throw std::runtime_error("**TriEnergyTerm Error: Inverted initial pose");
+}
+
 Solver::Solver() : initialized(false) {}
 
 Solver::~Solver() {
@@ -82,21 +95,44 @@ bool Solver::initialize(const Settings &settings_) {
     std::fill(m_v.begin(), m_v.end(), 0.0);
 
     const int n_verts = dof / 3;
-    const int n_tets = (int)energyterms.size();
-    std::vector<double> rest12((size_t)12 * n_tets), youngs(n_tets), poisson(n_tets);
-    std::vector<int> tets((size_t)4 * n_tets), material(n_tets);
-    for (int t = 0; t < n_tets; ++t) {
-        const TetEnergyTerm *e = dynamic_cast<const TetEnergyTerm *>(energyterms[t].get());
-        if (!e) throw std::runtime_error("admm::Solver (B200): only tet energy terms are supported on the device path");
-        if (e->get_weight() <= 0.0) throw std::runtime_error("**EnergyTerm::get_reduction Error: Some weight leq 0");
-        for (int k = 0; k < 4; ++k) {
-            tets[4 * (size_t)t + k] = e->tet[k];
-            for (int j = 0; j < 3; ++j) rest12[12 * (size_t)t + 3 * k + j] = e->rest[k][j];
+    // energy terms -> SoA batches (tets, then triangles; the order inside z does not enter the iteration)
+    std::vector<double> rest12, youngs, poisson, rest9, tri_youngs, tri_poisson, tri_lmin, tri_lmax;
+    std::vector<int> tets, material, tris;
+    for (size_t i = 0; i < energyterms.size(); ++i) {
+        if (energyterms[i]->get_weight() <= 0.0)
+            throw std::runtime_error("**EnergyTerm::get_reduction Error: Some weight leq 0");
+        if (const TetEnergyTerm *e = dynamic_cast<const TetEnergyTerm *>(energyterms[i].get())) {
+            for (int k = 0; k < 4; ++k) {
+                tets.push_back(e->tet[k]);
+                for (int j = 0; j < 3; ++j) rest12.push_back(e->rest[k][j]);
+            }
+            youngs.push_back(e->lame.youngs);
+            poisson.push_back(e->lame.poisson);
+            material.push_back(e->material);
+        } else if (const TriEnergyTerm *e = dynamic_cast<const TriEnergyTerm *>(energyterms[i].get())) {
+            for (int k = 0; k < 3; ++k) {
+                tris.push_back(e->tri[k]);
+                for (int j = 0; j < 3; ++j) rest9.push_back(e->rest[k][j]);
+            }
+            tri_youngs.push_back(e->lame.youngs);
+            tri_poisson.push_back(e->lame.poisson);
+            tri_lmin.push_back(e->lame.limit_min);
+            tri_lmax.push_back(e->lame.limit_max);
+        } else {
+            throw std::runtime_error("admm::Solver (B200): only tet and triangle energy terms are supported on the device path");
         }
-        youngs[t] = e->lame.youngs;
-        poisson[t] = e->lame.poisson;
-        material[t] = e->material;
     }
+    const int n_tets = (int)youngs.size();
+    aaadmm::TriInput tri_in;
+    tri_in.n_tris = (int)tri_youngs.size();
+    tri_in.rest9 = rest9.data();
+    tri_in.tris = tris.data();
+    tri_in.youngs = tri_youngs.data();
+    tri_in.poisson = tri_poisson.data();
+    tri_in.limit_min = tri_lmin.data();
+    tri_in.limit_max = tri_lmax.data();
+    if (tri_in.n_tris > 0 && m_settings.ordering != Settings::HARD_ZXU)
+        throw std::runtime_error("admm::Solver (B200): triangle energy terms run under the hard_zxu ordering only");
     std::vector<double> masses(n_verts);
     for (int v = 0; v < n_verts; ++v) masses[v] = m_masses[3 * (size_t)v];
     std::vector<int> pinned;
@@ -109,7 +145,7 @@ bool Solver::initialize(const Settings &settings_) {
     const double dt2 = m_settings.timestep_s * m_settings.timestep_s;
     const double rho = (m_settings.ordering == Settings::HARD_ZXU) ? m_settings.penalty : 1.0;
     if (!aaadmm::build_tet_system(m_sys, n_verts, rest12.data(), n_tets, tets.data(), material.data(), youngs.data(),
-                                  poisson.data(), masses.data(), pinned, rho * dt2))
+                                  poisson.data(), masses.data(), pinned, rho * dt2, &tri_in))
         throw std::runtime_error(m_sys.error);
 
     // factor Ahat once on the host (nested dissection + multifrontal LDL^T)
@@ -136,7 +172,13 @@ bool Solver::initialize(const Settings &settings_) {
     if (aaadmm_ldlt_create(&m_ldlt, m_factor.n, m_factor.Lp.data(), m_factor.Li.data(), m_factor.Lx.data(),
                            m_factor.D.data(), m_factor.perm.data(), 3) != 0)
         throw std::runtime_error(std::string("aaadmm_ldlt_create: ") + aaadmm_last_error());
-    aaadmm_tetscene_desc d;
+    aaadmm_tetscene_desc d = {};
+    d.n_tris = m_sys.n_tris;
+    d.tri = m_sys.tri_dev.data();
+    d.tri_rest_pose = m_sys.tri_binv.data();
+    d.tri_weight = m_sys.tri_weight.data();
+    d.tri_limit_min = m_sys.tri_limit_min.data();
+    d.tri_limit_max = m_sys.tri_limit_max.data();
     d.n_verts = m_sys.n_verts;
     d.n_free = m_sys.n_free;
     d.n_tets = m_sys.n_tets;

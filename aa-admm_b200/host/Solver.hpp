@@ -24,6 +24,7 @@ namespace admm {
 
 typedef std::array<double, 3> Vec3;
 typedef std::array<int, 4> Vec4i;
+typedef std::array<int, 3> Vec3i;
 
 // admm::Lame (src/EnergyTerm.hpp:33-59)
 class Lame {
@@ -83,6 +84,35 @@ inline void create_tets_from_mesh(std::vector<std::shared_ptr<EnergyTerm>> &ener
             tetverts[k] = {(double)verts[tet[k] * 3 + 0], (double)verts[tet[k] * 3 + 1], (double)verts[tet[k] * 3 + 2]};
         for (int k = 0; k < 4; ++k) tet[k] += vertex_offset;
         energyterms.emplace_back(std::make_shared<TYPE>(tet, tetverts, lame));
+    }
+}
+
+// hard/src/TriEnergyTerm.hpp:53-83: linear-elastic triangle with strain limiting (Lame::limit_min / limit_max).
+class TriEnergyTerm : public EnergyTerm {
+public:
+    Vec3i tri;
+    Lame lame;
+    std::array<Vec3, 3> rest;
+    double area = 0, weight = 0;
+    std::array<double, 4> rest_pose;  // column-major 2x2
+    int get_dim() const { return 6; }
+    double get_weight() const { return weight; }
+    double get_volume() const { return area; }
+    // throws std::runtime_error like the reference ctor (bad strain limits, inverted initial pose)
+    TriEnergyTerm(const Vec3i &tri_, const std::vector<Vec3> &verts, const Lame &lame_);
+};
+
+// hard/src/TriEnergyTerm.hpp:32-47
+template <typename IN_SCALAR, typename TYPE>
+inline void create_tris_from_mesh(std::vector<std::shared_ptr<EnergyTerm>> &energyterms, const IN_SCALAR *verts,
+                                  const int *inds, int n_tris, const Lame &lame, const int vertex_offset) {
+    for (int i = 0; i < n_tris; ++i) {
+        Vec3i tri = {inds[i * 3 + 0], inds[i * 3 + 1], inds[i * 3 + 2]};
+        std::vector<Vec3> triverts(3);
+        for (int k = 0; k < 3; ++k)
+            triverts[k] = {(double)verts[tri[k] * 3 + 0], (double)verts[tri[k] * 3 + 1], (double)verts[tri[k] * 3 + 2]};
+        for (int k = 0; k < 3; ++k) tri[k] += vertex_offset;
+        energyterms.emplace_back(std::make_shared<TYPE>(tri, triverts, lame));
     }
 }
 

@@ -181,6 +181,81 @@ int aaadmm_host_solver_add_tetmesh(void *h, const float *verts, int n_verts, con
     return prev + n_verts;
     HOST_CATCH
 }
+// ---- operator setup alone (no device): the scalar system matrix of a scene of tets and triangles ------------
+struct SystemHandle {
+    aaadmm::TetSystem S;
+};
+void *aaadmm_host_system_new(const float *verts, int n_verts, const int *tets, int n_tets, const int *tris, int n_tris,
+                             const float *masses, double youngs, double poisson, const int *pins, int n_pins,
+                             double rho_dt2) {
+    try {
+        std::vector<double> rest12((size_t)12 * n_tets), rest9((size_t)9 * n_tris), m(n_verts);
+        std::vector<double> ey(std::max(n_tets, 1), youngs), ep(std::max(n_tets, 1), poisson);
+        std::vector<double> ty(std::max(n_tris, 1), youngs), tp(std::max(n_tris, 1), poisson);
+        for (int t = 0; t < n_tets; ++t)
+            for (int k = 0; k < 4; ++k)
+                for (int j = 0; j < 3; ++j) rest12[12 * (size_t)t + 3 * k + j] = (double)verts[3 * (size_t)tets[4 * (size_t)t + k] + j];
+        for (int t = 0; t < n_tris; ++t)
+            for (int k = 0; k < 3; ++k)
+                for (int j = 0; j < 3; ++j) rest9[9 * (size_t)t + 3 * k + j] = (double)verts[3 * (size_t)tris[3 * (size_t)t + k] + j];
+        for (int v = 0; v < n_verts; ++v) m[v] = (double)masses[v];
+        aaadmm::TriInput ti;
+        ti.n_tris = n_tris;
+        ti.rest9 = rest9.data();
+        ti.tris = tris;
+        ti.youngs = ty.data();
+        ti.poisson = tp.data();
+        std::unique_ptr<SystemHandle> h(new SystemHandle());
+        std::vector<int> pinned(pins, pins + n_pins);
+        if (!aaadmm::build_tet_system(h->S, n_verts, rest12.data(), n_tets, tets, nullptr, ey.data(), ep.data(), m.data(),
+                                      pinned, rho_dt2, &ti)) {
+            g_err = h->S.error;
+            return nullptr;
+        }
+        return h.release();
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void aaadmm_host_system_free(void *h) { delete static_cast<SystemHandle *>(h); }
+int aaadmm_host_system_counts(void *h, int *n_free, int64_t *nnz) {
+    const aaadmm::TetSystem &S = static_cast<SystemHandle *>(h)->S;
+    *n_free = S.n_free;
+    *nnz = S.Ahat.p[S.n_free];
+    return 0;
+}
+int aaadmm_host_system_copy(void *h, int64_t *Ap, int *Ai, double *Ax, int *dev_to_vert) {
+    const aaadmm::TetSystem &S = static_cast<SystemHandle *>(h)->S;
+    std::copy(S.Ahat.p.begin(), S.Ahat.p.end(), Ap);
+    std::copy(S.Ahat.i.begin(), S.Ahat.i.end(), Ai);
+    std::copy(S.Ahat.x.begin(), S.Ahat.x.end(), Ax);
+    std::copy(S.dev_to_vert.begin(), S.dev_to_vert.end(), dev_to_vert);
+    return 0;
+}
+
+// binding::add_trimesh (samples/utils/AddMeshes.hpp:180-230): float32 vertices and masses, strain limits in Lame.
+int aaadmm_host_solver_add_trimesh(void *h, const float *verts, int n_verts, const int *tris, int n_tris,
+                                   const float *masses, double youngs, double poisson, double limit_min,
+                                   double limit_max) {
+    HOST_TRY
+    admm::Solver &s = static_cast<SolverHandle *>(h)->solver;
+    const int prev = (int)s.m_x.size() / 3;
+    s.m_x.resize((size_t)(prev + n_verts) * 3);
+    s.m_v.resize((size_t)(prev + n_verts) * 3, 0.0);
+    s.m_masses.resize((size_t)(prev + n_verts) * 3);
+    for (int i = 0; i < n_verts; ++i)
+        for (int j = 0; j < 3; ++j) {
+            s.m_x[(size_t)(prev + i) * 3 + j] = (double)verts[3 * (size_t)i + j];
+            s.m_masses[(size_t)(prev + i) * 3 + j] = (double)masses[i];
+        }
+    admm::Lame lame(youngs, poisson);
+    lame.limit_min = limit_min;
+    lame.limit_max = limit_max;
+    admm::create_tris_from_mesh<float, admm::TriEnergyTerm>(s.energyterms, verts, tris, n_tris, lame, prev);
+    return prev + n_verts;
+    HOST_CATCH
+}
 int aaadmm_host_solver_set_pins(void *h, const int *idx, const double *pts, int n) {
     HOST_TRY
     std::vector<int> inds(idx, idx + n);

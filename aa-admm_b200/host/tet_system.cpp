@@ -78,7 +78,7 @@ bool tet_constants(const double *rest12, double youngs, double poisson, double *
 
 bool build_tet_system(TetSystem &S, int n_verts, const double *rest12, int n_tets, const int *tets,
                       const int *material, const double *youngs, const double *poisson,
-                      const double *masses, const std::vector<int> &pinned, double rho_dt2) {
+                      const double *masses, const std::vector<int> &pinned, double rho_dt2, const TriInput *tri) {
     S = TetSystem();
     S.n_verts = n_verts;
     S.n_tets = n_tets;
@@ -141,16 +141,60 @@ bool build_tet_system(TetSystem &S, int n_verts, const double *rest12, int n_tet
         for (int c = 0; c < 4; ++c) S.tet_dev[4 * (size_t)t + c] = S.vert_to_dev[tv[c]];
     }
 
-    // incidence lists over free vertices
+    const int n_tris = tri ? tri->n_tris : 0;
+    S.n_tris = n_tris;
+    S.tri_dev.resize((size_t)3 * n_tris);
+    S.tri_binv.resize((size_t)4 * n_tris);
+    S.tri_weight.resize(n_tris);
+    S.tri_area.resize(n_tris);
+    S.tri_limit_min.resize(n_tris);
+    S.tri_limit_max.resize(n_tris);
+    for (int t = 0; t < n_tris; ++t) {
+        const double lmin = tri->limit_min ? tri->limit_min[t] : -100.0, lmax = tri->limit_max ? tri->limit_max[t] : 100.0;
+        if (lmin > 1.0) {
+            S.error = "**TriEnergyTerm Error: Strain limit min should be -inf to 1";
+            return false;
+        }
+        if (lmax < 1.0) {
+            S.error = "**TriEnergyTerm Error: Strain limit max should be 1 to inf";
+            return false;
+        }
+        if (!tri_constants(tri->rest9 + 9 * (size_t)t, tri->youngs[t], tri->poisson[t], &S.tri_binv[4 * (size_t)t],
+                           &S.tri_area[t], &S.tri_weight[t])) {
+            S.error = "**TriEnergyTerm Error: Inverted initial pose";
+            return false;
+        }
+        if (!(S.tri_weight[t] > 0.0)) {
+            S.error = "**EnergyTerm::get_reduction Error: Some weight leq 0";
+            return false;
+        }
+        S.tri_limit_min[t] = lmin;
+        S.tri_limit_max[t] = lmax;
+        for (int c = 0; c < 3; ++c) {
+            const int v = tri->tris[3 * (size_t)t + c];
+            if (v < 0 || v >= n_verts) {
+                S.error = "triangle vertex index out of range";
+                return false;
+            }
+            S.tri_dev[3 * (size_t)t + c] = S.vert_to_dev[v];
+        }
+    }
+
+    // incidence lists over free vertices (tet slots first, then the triangle slots)
     S.inc_ptr.assign(nf + 1, 0);
     for (size_t k = 0; k < S.tet_dev.size(); ++k)
         if (S.tet_dev[k] < nf) S.inc_ptr[S.tet_dev[k] + 1]++;
+    for (size_t k = 0; k < S.tri_dev.size(); ++k)
+        if (S.tri_dev[k] < nf) S.inc_ptr[S.tri_dev[k] + 1]++;
     for (int v = 0; v < nf; ++v) S.inc_ptr[v + 1] += S.inc_ptr[v];
     S.inc.resize(S.inc_ptr[nf]);
     {
         std::vector<int64_t> pos(S.inc_ptr.begin(), S.inc_ptr.end() - 1);
         for (size_t k = 0; k < S.tet_dev.size(); ++k)
             if (S.tet_dev[k] < nf) S.inc[pos[S.tet_dev[k]]++] = (int)k;
+        const size_t slot0 = (size_t)4 * n_tets;
+        for (size_t k = 0; k < S.tri_dev.size(); ++k)
+            if (S.tri_dev[k] < nf) S.inc[pos[S.tri_dev[k]]++] = (int)(slot0 + k);
     }
 
     // Ahat = M + rho dt^2 sum_t w_t^2 G_t^T G_t, G_t(r,c) = sum_k Sel(c,k) Binv(k,r)
@@ -186,6 +230,30 @@ bool build_tet_system(TetSystem &S, int n_verts, const double *rest12, int n_tet
                 int rr = std::max(va, vb), cc = std::min(va, vb);
                 tr.push_back(rr);
                 tc.push_back(cc);
+                tv.push_back(s);
+            }
+        }
+    }
+    // triangles: F(:,c) = sum_a Dc(a,c) x_a, Dc = S * rest_pose (hard/src/TriEnergyTerm.cpp:59-72)
+    for (int t = 0; t < n_tris; ++t) {
+        const double *rp = &S.tri_binv[4 * (size_t)t];  // R(k,c) = rp[c*2+k]
+        double G[2][3];
+        for (int c = 0; c < 2; ++c) {
+            G[c][1] = rp[c * 2 + 0];
+            G[c][2] = rp[c * 2 + 1];
+            G[c][0] = -G[c][1] - G[c][2];
+        }
+        const double w = S.tri_weight[t];
+        for (int a = 0; a < 3; ++a) {
+            const int va = S.tri_dev[3 * (size_t)t + a];
+            if (va >= nf) continue;
+            for (int b = 0; b <= a; ++b) {
+                const int vb = S.tri_dev[3 * (size_t)t + b];
+                if (vb >= nf) continue;
+                double s = 0;
+                for (int c = 0; c < 2; ++c) s += (rho_dt2 * (w * G[c][a])) * (w * G[c][b]);
+                tr.push_back(std::max(va, vb));
+                tc.push_back(std::min(va, vb));
                 tv.push_back(s);
             }
         }

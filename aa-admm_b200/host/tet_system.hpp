@@ -42,7 +42,15 @@ struct TetSystem {
     std::vector<int> material;     // per tet
     std::vector<double> mu, lambda;  // per tet (hyper-elastic prox)
     std::vector<double> mass_free;   // per free vertex (scalar; the reference stores it x3)
-    // incidence CSR over free vertices: entries are tet*4 + corner
+    // triangle (cloth) terms, hard/src/TriEnergyTerm.cpp:29-72: 6 rows each, F = [x1-x0, x2-x0] * rest_pose
+    int n_tris = 0;
+    std::vector<int> tri_dev;          // 3 per triangle, device vertex ids
+    std::vector<double> tri_binv;      // 4 per triangle, column-major rest_pose (2x2)
+    std::vector<double> tri_weight;    // sqrt(bulk modulus * area)
+    std::vector<double> tri_area;
+    std::vector<double> tri_limit_min, tri_limit_max;  // Lame::limit_min / limit_max of the term
+    // incidence CSR over free vertices: entries are contribution slots, tet*4 + corner for the tets and
+    // 4*n_tets + tri*3 + corner for the triangles (a slot holds 3 doubles)
     std::vector<int64_t> inc_ptr;
     std::vector<int> inc;
     SymLower Ahat;  // n_free x n_free
@@ -57,8 +65,16 @@ bool tri_constants(const double *rest9, double youngs, double poisson, double *r
 
 // rest12: the 4 rest vertices of every tet (12 doubles per tet, as handed to the TetEnergyTerm
 // ctor); tets: 4 ints per tet; masses: 1 per vertex; pinned: vertex ids. rho_dt2 = penalty * dt^2.
+// Optional triangle terms of the same scene (rest9: the 3 rest vertices of every triangle).
+struct TriInput {
+    int n_tris = 0;
+    const double *rest9 = nullptr;
+    const int *tris = nullptr;
+    const double *youngs = nullptr, *poisson = nullptr, *limit_min = nullptr, *limit_max = nullptr;
+};
 bool build_tet_system(TetSystem &S, int n_verts, const double *rest12, int n_tets, const int *tets,
                       const int *material, const double *youngs, const double *poisson,
-                      const double *masses, const std::vector<int> &pinned, double rho_dt2);
+                      const double *masses, const std::vector<int> &pinned, double rho_dt2,
+                      const TriInput *tri = nullptr);
 
 }  // namespace aaadmm

@@ -93,9 +93,18 @@ typedef struct {
     const double *lambda;    /* n_tets (hyper-elastic only, may be NULL)                       */
     const double *mass_free; /* n_free scalar lumped masses                                    */
     const int64_t *inc_ptr;  /* n_free+1: incidence CSR over free vertices                     */
-    const int *inc;          /* entries tet*4+corner                                           */
+    const int *inc;          /* entries = contribution slots: tet*4+corner, triangles 4*n_tets+tri*3+corner */
     double rho_dt2;          /* penalty * dt^2 (hard) or dt^2 (xzu)                            */
     const double *volume;    /* n_tets rest volumes (hyper-elastic only, may be NULL)          */
+    /* Triangle (cloth) terms of the same scene: TriEnergyTerm, admm_anderson_hard_zxu/src/TriEnergyTerm.cpp:29-105
+     * (6 rows per triangle, F = [x1-x0, x2-x0] * rest_pose). hard_zxu ordering only. n_tris may be 0; a scene
+     * may also consist of triangles only (n_tets = 0). */
+    int n_tris;
+    const int *tri;              /* 3*n_tris vertex ids in the free-first numbering                   */
+    const double *tri_rest_pose; /* 4*n_tris column-major inverse rest matrices (2x2)                 */
+    const double *tri_weight;    /* n_tris ADMM weights sqrt(K area)                                  */
+    const double *tri_limit_min; /* n_tris strain limits Lame::limit_min (NULL = -100, no limiting)   */
+    const double *tri_limit_max; /* n_tris strain limits Lame::limit_max (NULL = +100, no limiting)   */
 } aaadmm_tetscene_desc;
 
 #define AAADMM_ORDER_HARD_ZXU 0

@@ -35,12 +35,27 @@ int aaadmm_host_factor_copy(void *h, int64_t *Lp, int *Li, double *Lx, double *D
 int aaadmm_host_factor_solve(void *h, const double *b, double *x, int nrhs);
 int aaadmm_host_factor_stats(void *h, double *s6);
 
+/* Operator setup alone, no device involved (role of Solver::initialize, hard/src/Solver.cpp:361-491): the scalar
+ * system matrix Ahat of A = M + rho dt^2 D^T W^2 D = Ahat (x) I3 for a scene of tets and triangles with the pinned
+ * vertices eliminated; lower CSC incl. diagonal over the free vertices (dev_to_vert maps them back). */
+void *aaadmm_host_system_new(const float *verts, int n_verts, const int *tets, int n_tets, const int *tris, int n_tris,
+                             const float *masses, double youngs, double poisson, const int *pins, int n_pins,
+                             double rho_dt2);
+void aaadmm_host_system_free(void *h);
+int aaadmm_host_system_counts(void *h, int *n_free, int64_t *nnz);
+int aaadmm_host_system_copy(void *h, int64_t *Ap, int *Ai, double *Ax, int *dev_to_vert);
+
 /* admm::Solver mirror (hard_zxu/src/Solver.hpp:38-261): add_tetmesh = binding::add_tetmesh
  * (samples/utils/AddMeshes.hpp:97-177), set_pins, initialize, step. ordering 0 = hard_zxu, 1 = xzu. */
 void *aaadmm_host_solver_new(void);
 void aaadmm_host_solver_free(void *h);
 int aaadmm_host_solver_add_tetmesh(void *h, const float *verts, int n_verts, const int *tets, int n_tets,
                                    const float *masses, double youngs, double poisson, int material);
+/* binding::add_trimesh (samples/utils/AddMeshes.hpp:180-230) + create_tris_from_mesh (hard/src/TriEnergyTerm.hpp:32-47);
+ * limit_min / limit_max = Lame::limit_min / limit_max (strain limiting). hard_zxu ordering only. */
+int aaadmm_host_solver_add_trimesh(void *h, const float *verts, int n_verts, const int *tris, int n_tris,
+                                   const float *masses, double youngs, double poisson, double limit_min,
+                                   double limit_max);
 int aaadmm_host_solver_set_pins(void *h, const int *idx, const double *pts, int n);
 int aaadmm_host_solver_initialize(void *h, double dt, int iters, double gravity, int anderson_m, int accel,
                                   double penalty, int ordering, int nd_leaf);

@@ -152,6 +152,34 @@ int RFN(add_tetmesh)(void *hp, const float *verts, int n_verts, const int *tets,
     return prev + n_verts;
 }
 
+// Triangle (cloth) mesh: nodes + create_tris_from_mesh<float, TriEnergyTerm>, as binding::add_trimesh
+// (samples/utils/AddMeshes.hpp:180-230) does, with the arrays supplied by the caller; the strain limits of the
+// Lame object are set explicitly (the samples use limit_min / limit_max of Lame, EnergyTerm.hpp:47).
+int RFN(add_trimesh)(void *hp, const float *verts, int n_verts, const int *tris, int n_tris, const float *masses,
+                     double youngs, double poisson, double limit_min, double limit_max) {
+    Handle *h = static_cast<Handle *>(hp);
+    admm::Solver *s = &h->solver;
+    int prev = s->m_x.rows() / 3;
+    s->m_x.conservativeResize(prev * 3 + n_verts * 3);
+    s->m_masses.conservativeResize(prev * 3 + n_verts * 3);
+    for (int i = 0; i < n_verts; ++i) {
+        int idx = i + prev;
+        Eigen::Vector3f v(verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]);
+        s->m_x.segment<3>(idx * 3) = v.cast<double>();
+        s->m_masses.segment<3>(idx * 3) = Eigen::Vector3d(1, 1, 1) * masses[i];
+    }
+    admm::Lame lame(youngs, poisson);
+    lame.limit_min = limit_min;
+    lame.limit_max = limit_max;
+    try {
+        admm::create_tris_from_mesh<float, admm::TriEnergyTerm>(s->energyterms, verts, tris, n_tris, lame, prev);
+    } catch (std::exception &e) {
+        fprintf(stderr, "ref add_trimesh: %s\n", e.what());
+        return -1;
+    }
+    return prev + n_verts;
+}
+
 int RFN(set_pins)(void *hp, const int *idx, const double *pts, int n) {
     Handle *h = static_cast<Handle *>(hp);
     std::vector<int> inds(idx, idx + n);

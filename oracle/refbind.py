@@ -62,6 +62,8 @@ class RefSolver:
         self.h = C.c_void_p(f("new")(workdir.encode()))
         f("free").argtypes = [C.c_void_p]
         f("add_tetmesh").argtypes = [C.c_void_p, c_fp, C.c_int, c_ip, C.c_int, c_fp, C.c_double, C.c_double, C.c_int]
+        f("add_trimesh").argtypes = [C.c_void_p, c_fp, C.c_int, c_ip, C.c_int, c_fp, C.c_double, C.c_double,
+                                     C.c_double, C.c_double]
         f("set_pins").argtypes = [C.c_void_p, c_ip, c_dp, C.c_int]
         f("initialize").argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double]
         f("step").argtypes = [C.c_void_p]
@@ -100,6 +102,16 @@ class RefSolver:
                                    youngs, poisson, material)
         if r < 0:
             raise RuntimeError("reference add_tetmesh failed")
+        return r
+
+    def add_trimesh(self, verts, tris, masses, youngs=1e7, poisson=0.399, limit_min=-100.0, limit_max=100.0):
+        verts = np.ascontiguousarray(verts, np.float32)
+        tris = np.ascontiguousarray(tris, np.int32)
+        masses = np.ascontiguousarray(masses, np.float32)
+        r = self._f("add_trimesh")(self.h, _fp(verts), len(verts), _ip(tris), len(tris), _fp(masses),
+                                   youngs, poisson, limit_min, limit_max)
+        if r < 0:
+            raise RuntimeError("reference add_trimesh failed")
         return r
 
     def set_pins(self, idx, pts):

@@ -75,3 +75,59 @@ def run_cfg1(make_solver, A, frames=1, dims=(12, 3, 3), m=5, accel=True, orderin
         hist.append(s.step())
         xs.append(s.x())
     return hist, xs
+
+
+def cloth_arrays(n=8, size=1.0, y=1.0, seed=3):
+    """Square cloth of n x n cells (two triangles each) hanging in the x-z plane at height y, slightly
+    perturbed out of plane so that no triangle is degenerate in any direction; float32 like the reference's
+    meshes. Returns verts, tris, masses, pinned vertex ids (two corners of one edge)."""
+    rng = np.random.default_rng(seed)
+    g = np.linspace(0.0, size, n + 1)
+    X, Z = np.meshgrid(g, g, indexing="ij")
+    verts = np.stack([X.ravel(), np.full(X.size, y) + 0.01 * size * rng.standard_normal(X.size), Z.ravel()], 1)
+    verts = verts.astype(np.float32)
+    vid = lambda i, j: i * (n + 1) + j
+    tris = []
+    for i in range(n):
+        for j in range(n):
+            tris.append((vid(i, j), vid(i + 1, j), vid(i + 1, j + 1)))
+            tris.append((vid(i, j), vid(i + 1, j + 1), vid(i, j + 1)))
+    tris = np.array(tris, np.int32)
+    masses = np.full(len(verts), 0.02 * size * size / len(verts) * 50.0, np.float32)
+    pins = np.array([vid(0, 0), vid(0, n)], np.int32)
+    return verts, tris, masses, pins
+
+
+def run_cloth(make_solver, frames=2, n=8, m=5, accel=True, iters=60, limits=(-100.0, 100.0), with_beam=None,
+              youngs=1e5, poisson=0.3, dt=1.0 / 30.0, pin_speed=0.3):
+    """Cloth (TriEnergyTerm) scene under the hard_zxu ordering, optionally together with a tet beam in the same
+    solver (`with_beam` = (A, dims)); the two pinned corners move apart by pin_speed*dt per frame.
+    make_solver() -> product Solver or RefSolver."""
+    verts, tris, masses, pins = cloth_arrays(n)
+    s = make_solver()
+    s.add_trimesh(verts, tris, masses, youngs, poisson, limits[0], limits[1])
+    pidx = list(pins)
+    ppts = [verts[p].astype(np.float64) for p in pins]
+    move = [np.array([0.0, 0.0, -1.0]), np.array([0.0, 0.0, 1.0])]
+    if with_beam is not None:
+        A, dims = with_beam
+        bs = A.BeamScene().add(*dims, -1.75)
+        bv, bt, bm, bp, bpts, bside = bs.arrays()
+        off = len(verts)
+        s.add_tetmesh(bv, bt, bm, 1e7, 0.399, 0)
+        for p, q, sd in zip(bp, bpts, bside):
+            pidx.append(int(p) + off)
+            ppts.append(np.array(q, np.float64))
+            move.append(np.array([-1.0 if sd == 0 else 1.0, 0.0, 0.0]))
+    pidx = np.array(pidx, np.int32)
+    ppts = np.array(ppts)
+    move = np.array(move)
+    s.set_pins(pidx, ppts)
+    s.initialize(dt, iters, -9.8, max(m, 1), accel, 1.0)
+    hist, xs = [], []
+    for f in range(frames):
+        ppts = ppts + pin_speed * dt * move
+        s.set_pins(pidx, ppts)
+        hist.append(s.step())
+        xs.append(s.x())
+    return hist, xs

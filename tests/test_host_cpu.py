@@ -230,3 +230,47 @@ def test_reference_style_sample_compiles_against_the_dropin_classes(A, tmp_path)
     r = subprocess.run([exe, "-it", "5", "-frames", "1"], capture_output=True, text=True)
     if A.device_count() <= 0:
         assert r.returncode != 0 and ("CUDA" in (r.stderr + r.stdout) or "aaadmm" in (r.stderr + r.stdout))
+
+
+@pytest.mark.parametrize("with_beam", [False, True])
+def test_system_matrix_with_triangle_terms_matches_reference(A, with_beam):
+    """Host setup of a cloth (TriEnergyTerm) scene, alone and mixed with a tet beam: the scalar matrix Ahat built
+    matrix-free (host/tet_system.cpp) against the reference's solver_termA = M + rho dt^2 D^T W^2 D
+    (hard/src/Solver.cpp:462-467), which must be Ahat (x) I3 with the pinned vertices eliminated."""
+    from oracle import refbind
+    if not refbind.have_ref():
+        pytest.skip("oracle/_ref (compiled reference) not present")
+    from scenes import cloth_arrays
+    verts, tris, masses, pins = cloth_arrays(5)
+    tets = np.zeros((0, 4), np.int32)
+    r = refbind.RefSolver("hard")
+    r.add_trimesh(verts, tris, masses, 1e5, 0.3)
+    allv, allm, pidx = verts, masses, list(pins)
+    if with_beam:
+        bv, bt, bm, bp, _, _ = A.BeamScene().add(4, 2, 2, -1.75).arrays()
+        r.add_tetmesh(bv, bt, bm, 1e5, 0.3, 0)
+        tets = bt + len(verts)
+        allv = np.concatenate([verts, bv])
+        allm = np.concatenate([masses, bm])
+        pidx += [int(p) + len(verts) for p in bp]
+    pidx = np.array(pidx, np.int32)
+    r.set_pins(pidx, allv[pidx].astype(np.float64))
+    dt, rho = 1.0 / 30.0, 2.5
+    r.initialize(dt, 5, -9.8, 5, True, rho)
+    n, rp, ci, v = r.termA()
+    Aref = np.zeros((n, n))
+    for i in range(n):
+        Aref[i, ci[rp[i]:rp[i + 1]]] = v[rp[i]:rp[i + 1]]
+    Ahat, d2v = A.host_system_matrix(allv, tets, tris, allm, pidx, rho * dt * dt, 1e5, 0.3)
+    nf = Ahat.shape[0]
+    assert n == 3 * nf
+    # free vertices keep their ascending order in both
+    free = [i for i in range(len(allv)) if i not in set(pidx.tolist())]
+    assert list(d2v[:nf]) == free
+    scale = np.abs(Aref).max()
+    for c in range(3):
+        assert np.abs(Aref[c::3, c::3] - Ahat).max() < 1e-12 * scale
+    for c in range(3):
+        for e in range(3):
+            if c != e:
+                assert np.abs(Aref[c::3, e::3]).max() == 0.0
