@@ -129,6 +129,8 @@ def host_lib():
         H.aaadmm_host_solver_add_tetmesh.argtypes = [vp, c_fp, C.c_int, c_ip, C.c_int, c_fp, C.c_double, C.c_double, C.c_int]
         H.aaadmm_host_solver_add_trimesh.argtypes = [vp, c_fp, C.c_int, c_ip, C.c_int, c_fp, C.c_double, C.c_double,
                                                      C.c_double, C.c_double]
+        H.aaadmm_host_solver_add_wind.argtypes = [vp, c_ip, C.c_int, c_dp]
+        H.aaadmm_host_wind_project.argtypes = [c_ip, C.c_int, c_dp, C.c_double, c_dp, c_dp, C.c_int]
         H.aaadmm_host_solver_set_pins.argtypes = [vp, c_ip, c_dp, C.c_int]
         H.aaadmm_host_solver_initialize.argtypes = [vp, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
                                                     C.c_int, C.c_int]
@@ -430,6 +432,12 @@ class Solver:
             _hk(r)
         return r
 
+    def add_wind(self, tris, direction):
+        """WindForce over `tris` (global vertex ids), appended to Solver::ext_forces."""
+        tris = np.ascontiguousarray(tris, np.int32)
+        d = np.ascontiguousarray(direction, np.float64)
+        _hk(self.H.aaadmm_host_solver_add_wind(self.h, _ip(tris), len(tris), _dp(d)))
+
     def set_pins(self, idx, pts):
         idx = np.ascontiguousarray(idx, np.int32)
         pts = np.ascontiguousarray(pts, np.float64)
@@ -533,6 +541,17 @@ def host_system_matrix(verts, tets, tris, masses, pins, rho_dt2, youngs=1e7, poi
             M[Ai[p], j] = Ax[p]
             M[j, Ai[p]] = Ax[p]
     return M, d2v
+
+
+def wind_project(tris, direction, dt, x, v):
+    """Host WindForce::project (explicit force of the windyflag scene); returns the new velocities."""
+    H = host_lib()
+    tris = np.ascontiguousarray(tris, np.int32)
+    d = np.ascontiguousarray(direction, np.float64)
+    x = np.ascontiguousarray(x, np.float64)
+    v = np.array(v, np.float64).copy()
+    _hk(H.aaadmm_host_wind_project(_ip(tris), len(tris), _dp(d), dt, _dp(x), _dp(v), x.size // 3))
+    return v
 
 
 def tri_prox(F, variant="hard", limit_min=-100.0, limit_max=100.0):

@@ -43,6 +43,37 @@ TriEnergyTerm::TriEnergyTerm(const Vec3i &tri_, const std::vector<Vec3> &verts, 
         throw std::runtime_error("**TriEnergyTerm Error: Inverted initial pose");
 }
 
+// src/ExplicitForce.cpp:47-105
+void WindForce::project(double dt, std::vector<double> &x, std::vector<double> &v, std::vector<double> &m) const {
+    (void)m;
+    const int n_tris = (int)tris.size() / 3;
+    for (int i = 0; i < n_tris; ++i) {
+        const int idx[3] = {tris[i * 3 + 0] * 3, tris[i * 3 + 1] * 3, tris[i * 3 + 2] * 3};
+        double vr[3], a[3], b[3];
+        for (int j = 0; j < 3; ++j) {
+            vr[j] = ((v[idx[0] + j] + v[idx[1] + j]) + v[idx[2] + j]) / 3.0 - direction[j];
+            a[j] = x[idx[1] + j] - x[idx[0] + j];
+            b[j] = x[idx[2] + j] - x[idx[0] + j];
+        }
+        const double n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+        const double n2 = (n[0] * n[0] + n[1] * n[1]) + n[2] * n[2];
+        const double len = std::sqrt(n2);
+        double normal[3] = {n[0], n[1], n[2]};
+        if (n2 > 0.0)
+            for (int j = 0; j < 3; ++j) normal[j] = n[j] / len;
+        const double area = 0.5 * len;
+        const double alpha_n = 1000.0;
+        const double v_n = (normal[0] * vr[0] + normal[1] * vr[1]) + normal[2] * vr[2];
+        const double s = -alpha_n * area * v_n * std::fabs(v_n);
+        for (int j = 0; j < 3; ++j) {
+            double f = s * normal[j];
+            f *= 0.33;
+            f *= dt;
+            for (int k = 0; k < 3; ++k) v[idx[k] + j] += f;
+        }
+    }
+}
+
 Solver::Solver() : initialized(false) {}
 
 Solver::~Solver() {
@@ -221,6 +252,8 @@ void Solver::step() {
         int nf = 0, np = 0;
         for (int i = 0; i < n_nodes; ++i) slot_of_node[i] = positive_pin[i] > 0 ? nf++ : np++;
     }
+    // explicit forces (e.g. wind) act on the velocities first (hard/src/Solver.cpp:50-54)
+    for (size_t i = 0; i < ext_forces.size(); ++i) ext_forces[i]->project(dt, m_x, m_v, m_masses);
     const bool grav = std::abs(m_settings.gravity) > 0;
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < n_nodes; ++i)

@@ -116,6 +116,23 @@ inline void create_tris_from_mesh(std::vector<std::shared_ptr<EnergyTerm>> &ener
     }
 }
 
+// src/ExplicitForce.hpp:33-46: explicit velocity updates applied on the host at the start of step().
+class ExplicitForce {
+public:
+    virtual ~ExplicitForce() {}
+    virtual void project(double dt, std::vector<double> &x, std::vector<double> &v, std::vector<double> &m) const = 0;
+};
+// Wejchert / Haumann aerodynamic force on a list of triangles (src/ExplicitForce.cpp:47-105). The reference
+// accumulates into v from an OpenMP loop that also reads v; here the triangles are visited in order (what the
+// reference computes with one thread).
+class WindForce : public ExplicitForce {
+public:
+    WindForce(std::vector<int> &tris_) : tris(tris_), direction{0.0, 0.0, 0.0} {}
+    void project(double dt, std::vector<double> &x, std::vector<double> &v, std::vector<double> &m) const;
+    std::vector<int> tris;
+    Vec3 direction;
+};
+
 class Solver {
 public:
     struct Settings {
@@ -161,6 +178,7 @@ public:
 
     std::vector<double> m_x, m_v, m_masses;  // per node x3
     std::vector<std::shared_ptr<EnergyTerm>> energyterms;
+    std::vector<std::shared_ptr<ExplicitForce>> ext_forces;
 
     template <typename T>
     int add_nodes(T *x, T *m, int n_verts) {

@@ -256,6 +256,29 @@ int aaadmm_host_solver_add_trimesh(void *h, const float *verts, int n_verts, con
     return prev + n_verts;
     HOST_CATCH
 }
+// WindForce over the listed triangles, as samples/Asia2019/windyflag.cpp:124-126 adds it to Solver::ext_forces.
+int aaadmm_host_solver_add_wind(void *h, const int *tris, int n_tris, const double *dir3) {
+    HOST_TRY
+    admm::Solver &s = static_cast<SolverHandle *>(h)->solver;
+    std::vector<int> faces(tris, tris + 3 * (size_t)n_tris);
+    std::shared_ptr<admm::WindForce> wind(new admm::WindForce(faces));
+    wind->direction = {dir3[0], dir3[1], dir3[2]};
+    s.ext_forces.push_back(wind);
+    return 0;
+    HOST_CATCH
+}
+int aaadmm_host_wind_project(const int *tris, int n_tris, const double *dir3, double dt, const double *x, double *v,
+                             int n_verts) {
+    HOST_TRY
+    std::vector<int> faces(tris, tris + 3 * (size_t)n_tris);
+    admm::WindForce wind(faces);
+    wind.direction = {dir3[0], dir3[1], dir3[2]};
+    std::vector<double> xx(x, x + 3 * (size_t)n_verts), vv(v, v + 3 * (size_t)n_verts), mm(3 * (size_t)n_verts, 1.0);
+    wind.project(dt, xx, vv, mm);
+    std::copy(vv.begin(), vv.end(), v);
+    return 0;
+    HOST_CATCH
+}
 int aaadmm_host_solver_set_pins(void *h, const int *idx, const double *pts, int n) {
     HOST_TRY
     std::vector<int> inds(idx, idx + n);

@@ -56,6 +56,11 @@ int aaadmm_host_solver_add_tetmesh(void *h, const float *verts, int n_verts, con
 int aaadmm_host_solver_add_trimesh(void *h, const float *verts, int n_verts, const int *tris, int n_tris,
                                    const float *masses, double youngs, double poisson, double limit_min,
                                    double limit_max);
+/* WindForce (src/ExplicitForce.hpp:39-46) over n_tris triangles (global vertex ids) pushed into Solver::ext_forces */
+int aaadmm_host_solver_add_wind(void *h, const int *tris, int n_tris, const double *dir3);
+/* WindForce::project on caller arrays (x, v: 3 per vertex; v updated in place) */
+int aaadmm_host_wind_project(const int *tris, int n_tris, const double *dir3, double dt, const double *x, double *v,
+                             int n_verts);
 int aaadmm_host_solver_set_pins(void *h, const int *idx, const double *pts, int n);
 int aaadmm_host_solver_initialize(void *h, double dt, int iters, double gravity, int anderson_m, int accel,
                                   double penalty, int ordering, int nd_leaf);

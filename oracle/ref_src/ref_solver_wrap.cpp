@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 #include <memory>
+#include <omp.h>
 #include <unistd.h>
 #include <sys/stat.h>
 
@@ -178,6 +179,31 @@ int RFN(add_trimesh)(void *hp, const float *verts, int n_verts, const int *tris,
         return -1;
     }
     return prev + n_verts;
+}
+
+// WindForce over the listed triangles (ExplicitForce.hpp:39-46), pushed into Solver::ext_forces as
+// samples/Asia2019/windyflag.cpp:124-126 does. The reference's project() updates v from an OpenMP loop whose
+// iterations read velocities other iterations write: run it with one thread (RFN(set_threads)) for a
+// reproducible result.
+int RFN(add_wind)(void *hp, const int *tris, int n_tris, const double *dir3) {
+    Handle *h = static_cast<Handle *>(hp);
+    std::vector<int> faces(tris, tris + 3 * n_tris);
+    std::shared_ptr<admm::WindForce> wind(new admm::WindForce(faces));
+    wind->direction = Eigen::Vector3d(dir3[0], dir3[1], dir3[2]);
+    h->solver.ext_forces.push_back(wind);
+    return 0;
+}
+void RFN(set_threads)(int n) { omp_set_num_threads(n); }
+// WindForce::project on caller arrays (x, v: 3 per vertex; v updated in place), one thread.
+void RFN(wind_project)(const int *tris, int n_tris, const double *dir3, double dt, const double *x, double *v, int n_verts) {
+    std::vector<int> faces(tris, tris + 3 * n_tris);
+    admm::WindForce wind(faces);
+    wind.direction = Eigen::Vector3d(dir3[0], dir3[1], dir3[2]);
+    Eigen::VectorXd xx = Eigen::Map<const Eigen::VectorXd>(x, 3 * n_verts), vv = Eigen::Map<const Eigen::VectorXd>(v, 3 * n_verts);
+    Eigen::VectorXd mm = Eigen::VectorXd::Ones(3 * n_verts);
+    omp_set_num_threads(1);
+    wind.project(dt, xx, vv, mm);
+    memcpy(v, vv.data(), sizeof(double) * 3 * n_verts);
 }
 
 int RFN(set_pins)(void *hp, const int *idx, const double *pts, int n) {

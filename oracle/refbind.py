@@ -64,6 +64,8 @@ class RefSolver:
         f("add_tetmesh").argtypes = [C.c_void_p, c_fp, C.c_int, c_ip, C.c_int, c_fp, C.c_double, C.c_double, C.c_int]
         f("add_trimesh").argtypes = [C.c_void_p, c_fp, C.c_int, c_ip, C.c_int, c_fp, C.c_double, C.c_double,
                                      C.c_double, C.c_double]
+        f("add_wind").argtypes = [C.c_void_p, c_ip, C.c_int, c_dp]
+        f("set_threads").argtypes = [C.c_int]
         f("set_pins").argtypes = [C.c_void_p, c_ip, c_dp, C.c_int]
         f("initialize").argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double]
         f("step").argtypes = [C.c_void_p]
@@ -113,6 +115,13 @@ class RefSolver:
         if r < 0:
             raise RuntimeError("reference add_trimesh failed")
         return r
+
+    def add_wind(self, tris, direction):
+        """WindForce over `tris` (global vertex ids); forces one OpenMP thread (the reference's loop races otherwise)."""
+        tris = np.ascontiguousarray(tris, np.int32)
+        d = np.ascontiguousarray(direction, np.float64)
+        self._f("set_threads")(1)
+        self._f("add_wind")(self.h, _ip(tris), len(tris), _dp(d))
 
     def set_pins(self, idx, pts):
         idx = np.ascontiguousarray(idx, np.int32)
@@ -219,6 +228,18 @@ def ref_tet_constants(verts4, youngs=1e7, poisson=0.399):
     if lib.ref_hard_tet_constants(_dp(v), youngs, poisson, C.byref(w), C.byref(vol), _dp(binv)) != 0:
         raise RuntimeError("inverted tet")
     return w.value, vol.value, binv
+
+
+def ref_wind_project(tris, direction, dt, x, v):
+    """Reference WindForce::project (hard_zxu/src/ExplicitForce.cpp:47-105), one thread; returns the new v."""
+    lib = _load("libref_hard.so")
+    tris = np.ascontiguousarray(tris, np.int32)
+    d = np.ascontiguousarray(direction, np.float64)
+    x = np.ascontiguousarray(x, np.float64)
+    v = np.array(v, np.float64).copy()
+    lib.ref_hard_wind_project.argtypes = [c_ip, C.c_int, c_dp, C.c_double, c_dp, c_dp, C.c_int]
+    lib.ref_hard_wind_project(_ip(tris), len(tris), _dp(d), dt, _dp(x), _dp(v), x.size // 3)
+    return v
 
 
 def ref_tri_prox(F, variant="hard", limit_min=-100.0, limit_max=100.0):

@@ -99,13 +99,15 @@ def cloth_arrays(n=8, size=1.0, y=1.0, seed=3):
 
 
 def run_cloth(make_solver, frames=2, n=8, m=5, accel=True, iters=60, limits=(-100.0, 100.0), with_beam=None,
-              youngs=1e5, poisson=0.3, dt=1.0 / 30.0, pin_speed=0.3):
+              youngs=1e5, poisson=0.3, dt=1.0 / 30.0, pin_speed=0.3, wind=None):
     """Cloth (TriEnergyTerm) scene under the hard_zxu ordering, optionally together with a tet beam in the same
     solver (`with_beam` = (A, dims)); the two pinned corners move apart by pin_speed*dt per frame.
     make_solver() -> product Solver or RefSolver."""
     verts, tris, masses, pins = cloth_arrays(n)
     s = make_solver()
     s.add_trimesh(verts, tris, masses, youngs, poisson, limits[0], limits[1])
+    if wind is not None:  # WindForce over all cloth triangles (samples/Asia2019/windyflag.cpp:101-126)
+        s.add_wind(tris, wind)
     pidx = list(pins)
     ppts = [verts[p].astype(np.float64) for p in pins]
     move = [np.array([0.0, 0.0, -1.0]), np.array([0.0, 0.0, 1.0])]

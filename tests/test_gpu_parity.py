@@ -512,15 +512,19 @@ def _check_cloth(hg, xg, comb_ref, rows_ref, rej_ref, x_ref, accel):
         assert xerr < 1e-6
 
 
-@pytest.mark.parametrize("name", ["hard_cloth_8_m5", "hard_cloth_8_noacc_limits", "hard_cloth_6_beam_6x2x2_m5"])
+@pytest.mark.parametrize("name", ["hard_cloth_8_m5", "hard_cloth_8_noacc_limits", "hard_cloth_6_beam_6x2x2_m5",
+                                  "hard_windyflag_10_m5"])
 def test_cloth_step_vs_golden(gpu, name):
     """TriEnergyTerm scenes (cloth alone, strain-limited, cloth + tet beam in one solver) against golden
     trajectories of the unmodified reference (tests/golden/make_golden_cloth.py)."""
     from scenes import run_cloth
     g = np.load(os.path.join(GOLD, name + ".npz"))
     beam = tuple(int(d) for d in g["beam"])
-    hg, xg = run_cloth(gpu.Solver, frames=2, n=int(g["n"]), m=int(g["m"]), accel=bool(g["accel"]), iters=int(g["iters"]),
-                       limits=tuple(float(v) for v in g["limits"]), with_beam=(gpu, beam) if beam[0] else None)
+    wind = tuple(float(v) for v in g["wind"])
+    hg, xg = run_cloth(gpu.Solver, frames=int(g["frames"]), n=int(g["n"]), m=int(g["m"]), accel=bool(g["accel"]),
+                       iters=int(g["iters"]), limits=tuple(float(v) for v in g["limits"]),
+                       with_beam=(gpu, beam) if beam[0] else None, youngs=float(g["youngs"]), poisson=float(g["poisson"]),
+                       wind=wind if any(wind) else None, pin_speed=float(g["pin_speed"]))
     _check_cloth(hg, xg, g["comb"], g["rows"], g["rej"], g["x"], bool(g["accel"]))
 
 

@@ -274,3 +274,20 @@ def test_system_matrix_with_triangle_terms_matches_reference(A, with_beam):
         for e in range(3):
             if c != e:
                 assert np.abs(Aref[c::3, e::3]).max() == 0.0
+
+
+def test_wind_force_matches_reference(A):
+    """Host WindForce::project against the reference class (src/ExplicitForce.cpp:47-105, one thread)."""
+    from oracle import refbind
+    if not refbind.have_ref():
+        pytest.skip("oracle/_ref (compiled reference) not present")
+    from scenes import cloth_arrays
+    verts, tris, _, _ = cloth_arrays(7)
+    rng = np.random.default_rng(5)
+    x = verts.astype(np.float64) + 0.02 * rng.standard_normal(verts.shape)
+    v = rng.standard_normal(verts.shape)
+    d = np.array([25.0, 0.0, 5.0])
+    got = A.wind_project(tris, d, 1.0 / 30.0, x, v)
+    want = refbind.ref_wind_project(tris, d, 1.0 / 30.0, x, v)
+    assert np.abs(got - v).max() > 1e-3
+    assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
