@@ -512,7 +512,7 @@ def _check_cloth(hg, xg, comb_ref, rows_ref, rej_ref, x_ref, accel):
         # 1e-6 (north_star) for a frame that starts from the same state; the wind-driven frames end at max_iter
         # with 30-40 rejected steps and residuals 1e-3 of the initial one, so later frames inherit the
         # previous frame's difference amplified by the un-converged, safeguarded iteration
-        assert xerr < max(1e-6, 1e3 * (bar if bar > 1e-9 else 0.0))
+        assert xerr < max(1e-6, 0.1 * (bar if bar > 1e-9 else 0.0))  # = 100 x the previous frame's difference
 
 
 @pytest.mark.parametrize("name", ["hard_cloth_8_m5", "hard_cloth_8_noacc_limits", "hard_cloth_6_beam_6x2x2_m5",
