@@ -130,6 +130,8 @@ def host_lib():
         H.aaadmm_host_solver_add_trimesh.argtypes = [vp, c_fp, C.c_int, c_ip, C.c_int, c_fp, C.c_double, C.c_double,
                                                      C.c_double, C.c_double]
         H.aaadmm_host_solver_add_wind.argtypes = [vp, c_ip, C.c_int, c_dp]
+        H.aaadmm_host_solver_set_collisions.argtypes = [vp, c_ip, C.c_int]
+        H.aaadmm_host_solver_add_obstacle.argtypes = [vp, C.c_int, c_dp]
         H.aaadmm_host_wind_project.argtypes = [c_ip, C.c_int, c_dp, C.c_double, c_dp, c_dp, C.c_int]
         H.aaadmm_host_solver_set_pins.argtypes = [vp, c_ip, c_dp, C.c_int]
         H.aaadmm_host_solver_initialize.argtypes = [vp, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
@@ -151,7 +153,7 @@ def host_lib():
         H.aaadmm_host_tri_constants.argtypes = [c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp]
         H.aaadmm_host_system_new.restype = vp
         H.aaadmm_host_system_new.argtypes = [c_fp, C.c_int, c_ip, C.c_int, c_ip, C.c_int, c_fp, C.c_double, C.c_double,
-                                             c_ip, C.c_int, C.c_double]
+                                             c_ip, C.c_int, C.c_double, c_ip, C.c_int]
         H.aaadmm_host_system_free.argtypes = [vp]
         H.aaadmm_host_system_counts.argtypes = [vp, c_ip, C.POINTER(C.c_int64)]
         H.aaadmm_host_system_copy.argtypes = [vp, C.POINTER(C.c_int64), c_ip, c_dp, c_ip]
@@ -432,6 +434,17 @@ class Solver:
             _hk(r)
         return r
 
+    def set_collisions(self, idx):
+        """Solver::set_collisions (in place): one Collision energy term per listed vertex at initialize()."""
+        idx = np.ascontiguousarray(idx, np.int32)
+        _hk(self.H.aaadmm_host_solver_set_collisions(self.h, _ip(idx), len(idx)))
+
+    def add_obstacle(self, kind, prm7):
+        """Solver::add_obstacle with an analytic obstacle: kind = PASSIVE_* tag, prm7 = {cx,cy,cz,nx,ny,nz,radius}."""
+        p = np.ascontiguousarray(prm7, np.float64)
+        assert p.size == 7
+        _hk(self.H.aaadmm_host_solver_add_obstacle(self.h, int(kind), _dp(p)))
+
     def add_wind(self, tris, direction):
         """WindForce over `tris` (global vertex ids), appended to Solver::ext_forces."""
         tris = np.ascontiguousarray(tris, np.int32)
@@ -510,7 +523,7 @@ class Solver:
         return {n: dict(ms=float(ms[i]), bytes=float(by[i])) for i, n in enumerate(PROF_NAMES)}
 
 
-def host_system_matrix(verts, tets, tris, masses, pins, rho_dt2, youngs=1e7, poisson=0.399):
+def host_system_matrix(verts, tets, tris, masses, pins, rho_dt2, youngs=1e7, poisson=0.399, collisions=()):
     """Host setup only: scalar system matrix Ahat (A = M + rho dt^2 D^T W^2 D = Ahat (x) I3) of a scene of tets and
     triangles with the pinned vertices eliminated. Returns (dense lower-filled symmetric n_free x n_free array,
     dev_to_vert); for tests on small scenes."""
@@ -520,8 +533,9 @@ def host_system_matrix(verts, tets, tris, masses, pins, rho_dt2, youngs=1e7, poi
     tris = np.ascontiguousarray(tris, np.int32).reshape(-1, 3)
     masses = np.ascontiguousarray(masses, np.float32)
     pins = np.ascontiguousarray(pins, np.int32)
+    col = np.ascontiguousarray(collisions, np.int32)
     h = H.aaadmm_host_system_new(_fp(verts), len(verts), _ip(tets), len(tets), _ip(tris), len(tris), _fp(masses),
-                                 youngs, poisson, _ip(pins), len(pins), rho_dt2)
+                                 youngs, poisson, _ip(pins), len(pins), rho_dt2, _ip(col), len(col))
     if not h:
         raise AaadmmError(H.aaadmm_host_last_error().decode())
     try:

@@ -86,6 +86,8 @@ __global__ void k_init_state(SolveState *st, int accel, int m, double eps, int m
     st->hyper_prim2 = 0.0;
     st->tri_prim2 = 0.0;
     st->tri_comb = 0.0;
+    st->pt_prim2 = 0.0;
+    st->pt_comb = 0.0;
     st->prev_prim = 1e+20;
     st->comb = 0.0;
     st->eps = eps;
@@ -154,6 +156,10 @@ struct aaadmm_tetscene {
     int NT = 0;
     int4 *tri_idx = nullptr;
     double *tri_rp = nullptr, *tri_w = nullptr, *tri_lmin = nullptr, *tri_lmax = nullptr;
+    // collision terms: u / z planes behind the triangles', contributions behind theirs
+    int NC = 0, n_objs = 0;
+    int *pt_vert = nullptr, *obj_type = nullptr;
+    double *pt_w = nullptr, *obj_prm = nullptr;
     int64_t *inc_ptr = nullptr;
     int *inc = nullptr;
     // state
@@ -379,6 +385,10 @@ int aaadmm_tetscene_destroy(aaadmm_tetscene *s) {
     cudaFree(s->tri_w);
     cudaFree(s->tri_lmin);
     cudaFree(s->tri_lmax);
+    cudaFree(s->pt_vert);
+    cudaFree(s->obj_type);
+    cudaFree(s->pt_w);
+    cudaFree(s->obj_prm);
     cudaFree(s->inc_ptr);
     cudaFree(s->inc);
     cudaFree(s->Ubuf);
@@ -417,7 +427,7 @@ int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *d,
         return -1;
     }
     if (!d || !factor || d->n_tets < 0 || d->n_tris < 0 || d->n_tets + d->n_tris <= 0 || d->n_free <= 0 ||
-        d->n_free > d->n_verts) {
+        d->n_free > d->n_verts || d->n_collisions < 0 || d->n_obstacles < 0) {
         set_last_error("tetscene_create: bad arguments");
         return -1;
     }
@@ -428,6 +438,22 @@ int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *d,
     if (factor->f->n != d->n_free || factor->f->nrhs != 3) {
         set_last_error("tetscene_create: factor must be n_free x n_free with nrhs = 3");
         return -1;
+    }
+    if (d->n_collisions > 0) {
+        if (!d->collision_vert || !d->collision_weight || (d->n_obstacles > 0 && (!d->obstacle_type || !d->obstacle_prm))) {
+            set_last_error("tetscene_create: collision terms need collision_vert, collision_weight and the obstacle arrays");
+            return -1;
+        }
+        for (int i = 0; i < d->n_collisions; ++i)
+            if (d->collision_vert[i] < 0 || d->collision_vert[i] >= d->n_free) {
+                set_last_error("tetscene_create: collision terms must sit on free vertices");
+                return -1;
+            }
+        for (int j = 0; j < d->n_obstacles; ++j)
+            if (d->obstacle_type[j] < AAADMM_PASSIVE_FLOOR || d->obstacle_type[j] > AAADMM_PASSIVE_CYLINDER) {
+                set_last_error("tetscene_create: unknown obstacle type");
+                return -1;
+            }
     }
     std::vector<int> hyper_ids;
     if (d->material) {
@@ -453,7 +479,10 @@ int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *d,
     s->factor = factor;
     const int NT = d->n_tris;
     s->NT = NT;
-    s->Ne = 9 * (int64_t)T + 6 * (int64_t)NT;
+    const int NC = d->n_collisions;
+    s->NC = NC;
+    s->n_objs = d->n_obstacles;
+    s->Ne = 9 * (int64_t)T + 6 * (int64_t)NT + 3 * (int64_t)NC;
     s->Nt = s->Ne + 3 * (int64_t)NF;
     s->Nbuf = s->Ne + 3 * (int64_t)V;
     AAADMM_CUDA_OK(cudaStreamCreate(&s->stream));
@@ -481,6 +510,19 @@ int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *d,
         AAADMM_CUDA_OK(cudaMemcpy(s->tri_lmin, lmin.data(), sizeof(double) * NT, cudaMemcpyHostToDevice));
         AAADMM_CUDA_OK(cudaMalloc((void **)&s->tri_lmax, sizeof(double) * NT));
         AAADMM_CUDA_OK(cudaMemcpy(s->tri_lmax, lmax.data(), sizeof(double) * NT, cudaMemcpyHostToDevice));
+    }
+    if (NC > 0) {
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->pt_vert, sizeof(int) * NC));
+        AAADMM_CUDA_OK(cudaMemcpy(s->pt_vert, d->collision_vert, sizeof(int) * NC, cudaMemcpyHostToDevice));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->pt_w, sizeof(double) * NC));
+        AAADMM_CUDA_OK(cudaMemcpy(s->pt_w, d->collision_weight, sizeof(double) * NC, cudaMemcpyHostToDevice));
+        const int no = std::max(1, d->n_obstacles);
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->obj_type, sizeof(int) * no));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->obj_prm, sizeof(double) * 7 * no));
+        if (d->n_obstacles > 0) {
+            AAADMM_CUDA_OK(cudaMemcpy(s->obj_type, d->obstacle_type, sizeof(int) * d->n_obstacles, cudaMemcpyHostToDevice));
+            AAADMM_CUDA_OK(cudaMemcpy(s->obj_prm, d->obstacle_prm, sizeof(double) * 7 * d->n_obstacles, cudaMemcpyHostToDevice));
+        }
     }
     AAADMM_CUDA_OK(cudaMalloc((void **)&s->idx, sizeof(int4) * std::max(T, 1)));
     AAADMM_CUDA_OK(cudaMemcpy(s->idx, d->tet, sizeof(int) * 4 * T, cudaMemcpyHostToDevice));
@@ -514,7 +556,7 @@ int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *d,
     AAADMM_CUDA_OK(cudaMalloc((void **)&s->Gbuf, sizeof(double) * s->Nbuf));
     AAADMM_CUDA_OK(cudaMalloc((void **)&s->xs, sizeof(double) * 3 * V));
     AAADMM_CUDA_OK(cudaMalloc((void **)&s->z, sizeof(double) * s->Ne));
-    AAADMM_CUDA_OK(cudaMalloc((void **)&s->contrib, sizeof(double) * (12 * (size_t)T + 9 * (size_t)NT)));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&s->contrib, sizeof(double) * (12 * (size_t)T + 9 * (size_t)NT + 3 * (size_t)NC)));
     AAADMM_CUDA_OK(cudaMalloc((void **)&s->bconst, sizeof(double) * 3 * NF));
     AAADMM_CUDA_OK(cudaMalloc((void **)&s->xbar, sizeof(double) * 3 * NF));
     AAADMM_CUDA_OK(cudaMalloc((void **)&s->xpin, sizeof(double) * 3 * std::max(1, s->NP)));
@@ -642,7 +684,16 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
     const size_t o9 = 9 * (size_t)T;
     TriArrays R{NT, NF, s->tri_idx, s->tri_rp, s->tri_w, s->tri_lmin, s->tri_lmax, s->rho_dt2};
     double *tri_contrib = s->contrib + 12 * (size_t)T;
+    // collision terms behind the triangles
+    const int NC = s->NC;
+    const size_t o15 = o9 + 6 * (size_t)NT;
+    PointArrays Pt{NC, s->pt_vert, s->pt_w, s->n_objs, s->obj_type, s->obj_prm, s->rho_dt2};
+    double *pt_contrib = tri_contrib + 9 * (size_t)NT;
     auto update_z = [&](int mode) {
+        if (NC > 0) {
+            launch_pt_update_z_hard(mode, st, Pt, Ux, Uu + o15, s->z + o15, pt_contrib, s->st, s->partials);
+            ++L;
+        }
         if (NT > 0) {
             launch_tri_update_z_hard(mode, st, R, Ux, Uu + o9, s->z + o9, tri_contrib, s->st, s->partials);
             ++L;
@@ -650,6 +701,10 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
         launch_update_z_hard(mode, gt, st, A, Ux, Uu, s->z, s->contrib, s->st, s->partials);
     };
     auto update_u = [&](int mode, double *u_out) {
+        if (NC > 0) {
+            launch_pt_update_u_hard(mode, st, Pt, s->xs, Ux, s->z + o15, Uu + o15, u_out + o15, s->st, s->partials);
+            ++L;
+        }
         if (NT > 0) {
             launch_tri_update_u_hard(mode, st, R, s->xs, Ux, s->z + o9, Uu + o9, u_out + o9, s->st, s->partials);
             ++L;
@@ -840,8 +895,8 @@ static int step_common(aaadmm_tetscene *s, const aaadmm_step_opts *o, bool host_
         return -1;
     }
     const bool xzu = o->ordering == AAADMM_ORDER_XZU;
-    if (xzu && s->NT > 0) {
-        set_last_error("tetscene_step: triangle terms run under the hard_zxu ordering only");
+    if (xzu && (s->NT > 0 || s->NC > 0)) {
+        set_last_error("tetscene_step: triangle and collision terms run under the hard_zxu ordering only");
         return -1;
     }
     if (xzu && !s->xz_a) {
@@ -973,6 +1028,10 @@ int aaadmm_tetscene_algo_bytes(aaadmm_tetscene *s, int m, double *b) {
     b[2] = s->factor->f->stats.bytes_per_solve;                 // ldlt apply
     b[3] = T * (16 + 72 + 8 + 72 + 72 + 72) + 2 * 24 * V;       // update_u + residuals
     b[3] += R * (16 + 32 + 8 + 48 + 48 + 48);
+    const double C = s->NC;  // collision terms: vertex id, weight, position, u in; z, contribution out (+ u out)
+    b[0] += C * (4 + 8 + 24 + 24 + 24 + 24);
+    b[1] += C * (24 + 4);
+    b[3] += C * (4 + 8 + 48 + 24 + 24 + 24);
     b[4] = 8.0 * ((m + 2) * Ne + 3 * Nt);                       // aa pass 1
     b[5] = 8.0 * ((m + 3) * Nt + 2 * Ne);                       // aa pass 2
     b[6] = 0;

@@ -55,6 +55,7 @@ struct SolveState {
     int skip_redo;                     // xzu: 1 unless the current iterate was rejected (guards the redo solve)
     int aa_skip;                       // geometry: 1 on a rejected turn (the Anderson passes do not run)
     double tri_prim2, tri_comb;        // residual shares of the triangle terms (0 for tet-only scenes)
+    double pt_prim2, pt_comb;          // residual shares of the collision terms
 };
 
 // ---------------------------------------------------------------------------------------

@@ -2,6 +2,7 @@
 
 #include <cfloat>
 
+#include "collision_prox.cuh"
 #include "tri_prox.cuh"
 
 namespace aaadmm {
@@ -21,88 +22,14 @@ k_tri_prox(int variant, double *__restrict__ z, int64_t n, double lmin, double l
     for (int k = 0; k < 6; ++k) z[6 * i + k] = out[k];
 }
 
-struct Payload {
-    double dx, p[3];
-};
-
-__device__ __forceinline__ double norm3(const double *v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
-
-// PassiveCollision::signed_distance of one object: keeps the smallest signed distance seen so far and
-// the surface point that belongs to it (`if (dx > p.dx) return;`).
-__device__ void signed_distance(int type, const double *q, const double *x, Payload &pl) {
-    const double *c = q;
-    const double rad = q[6];
-    if (type == PASSIVE_FLOOR) {
-        const double dx = x[1] - q[0];
-        if (dx > pl.dx) return;
-        pl.dx = dx;
-        pl.p[0] = x[0];
-        pl.p[1] = q[0];
-        pl.p[2] = x[2];
-    } else if (type == PASSIVE_SLIDE_FLOOR) {
-        double nrm[3] = {q[3], q[4], q[5]};
-        const double nn = norm3(nrm);  // the constructor normalises
-        if (nn > 0.0) {
-            nrm[0] /= nn;
-            nrm[1] /= nn;
-            nrm[2] /= nn;
-        }
-        const double dx = (x[0] - c[0]) * nrm[0] + (x[1] - c[1]) * nrm[1] + (x[2] - c[2]) * nrm[2];
-        if (dx > pl.dx) return;
-        pl.dx = dx;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) pl.p[k] = x[k] - dx * nrm[k];
-    } else if (type == PASSIVE_SPHERE) {
-        double dir[3] = {x[0] - c[0], x[1] - c[1], x[2] - c[2]};
-        const double len = norm3(dir);
-        const double dx = len - rad;
-        if (dx > pl.dx) return;
-        pl.dx = dx;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) pl.p[k] = c[k] + (len > 0.0 ? dir[k] / len : dir[k]) * rad;
-    } else if (type == PASSIVE_PLANE_HALF_SPHERE) {
-        const double px = x[0] - c[0], pz = x[2] - c[2];
-        const double dc = sqrt(px * px + 0.0 * 0.0 + pz * pz) - rad;
-        if (dc > 0.0) {
-            const double dx = x[1] - c[1];
-            if (dx > pl.dx) return;
-            pl.dx = dx;
-            pl.p[0] = x[0];
-            pl.p[1] = c[1];
-            pl.p[2] = x[2];
-        } else {
-            double dir[3] = {x[0] - c[0], x[1] - c[1], x[2] - c[2]};
-            const double len = norm3(dir);
-            const double dx = (x[1] - c[1] > 0.0) ? len + rad : rad - len;
-            if (dx > pl.dx) return;
-            pl.dx = dx;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) pl.p[k] = c[k] + (len > 0.0 ? dir[k] / len : dir[k]) * rad;
-        }
-    } else {  // PASSIVE_CYLINDER: axis along z through `center`
-        double dir[3] = {x[0] - c[0], x[1] - c[1], 0.0 - c[2]};
-        const double len = norm3(dir);
-        const double dx = len - rad;
-        if (dx > pl.dx) return;
-        pl.dx = dx;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) pl.p[k] = c[k] + (len > 0.0 ? dir[k] / len : dir[k]) * rad + (k == 2 ? x[2] : 0.0);
-    }
-}
-
 __global__ void __launch_bounds__(128)
 k_collision_prox(int n_objs, const int *__restrict__ types, const double *__restrict__ prm, double *__restrict__ z, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (i >= n) return;
-    const double x[3] = {z[3 * i], z[3 * i + 1], z[3 * i + 2]};
-    Payload pl;
-    pl.dx = DBL_MAX;
-    pl.p[0] = pl.p[1] = pl.p[2] = 0.0;
-    for (int j = 0; j < n_objs; ++j) signed_distance(types[j], prm + 7 * j, x, pl);
-    if (pl.dx < 0.0) {
+    double x[3] = {z[3 * i], z[3 * i + 1], z[3 * i + 2]};
+    collision_prox_point(n_objs, types, prm, x);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) z[3 * i + k] = pl.p[k];
-    }
+    for (int k = 0; k < 3; ++k) z[3 * i + k] = x[k];
 }
 
 __global__ void k_spring_prox(double *__restrict__ z, const double *__restrict__ pins, const int *__restrict__ active, int64_t n) {

@@ -121,7 +121,7 @@ k_update_z_hard(TetArrays A, const double *__restrict__ pos, const double *__res
     double out[1];
     if (grid_reduce<1, TET_BLOCK>(acc, partials, &st->ticket, out)) {
         if (threadIdx.x == 0) {
-            const double tot = out[0] + st->hyper_prim2 + st->tri_prim2;
+            const double tot = out[0] + st->hyper_prim2 + st->tri_prim2 + st->pt_prim2;
             const double prim = sqrt(tot);
             st->prim2 = tot;
             if (MODE == MODE_ITER) {
@@ -258,7 +258,7 @@ k_update_u_hard(TetArrays A, const double *__restrict__ pos_new, const double *_
     double out[2];
     if (grid_reduce<2, TET_BLOCK>(acc, partials, &st->ticket, out)) {
         if (threadIdx.x == 0) {
-            const double comb = out[0] + out[1] + st->tri_comb;
+            const double comb = out[0] + out[1] + st->tri_comb + st->pt_comb;
             st->comb = comb;
             if (comb < st->eps) {
                 st->done = 1;

@@ -36,6 +36,17 @@ struct TriArrays {
     double rho_dt2;
 };
 
+// Collision terms (tri_kernels.cu): one per constrained free vertex, u / z [3][P], contributions 3 doubles per term.
+struct PointArrays {
+    int n_pts;
+    const int *vert;   // [P] free vertex ids
+    const double *w;   // [P]
+    int n_objs;
+    const int *types;  // [n_objs] PASSIVE_*
+    const double *prm; // [n_objs][7]
+    double rho_dt2;
+};
+
 enum { MODE_WARM = 0, MODE_ITER = 1, MODE_REDO = 2 };
 
 // Host launchers (tet_kernels.cu is compiled with -fmad=false: the per-element arithmetic follows
@@ -51,6 +62,10 @@ void launch_tri_update_z_hard(int mode, cudaStream_t s, const TriArrays &A, cons
                               double *contrib, SolveState *st, double *partials);
 void launch_tri_update_u_hard(int mode, cudaStream_t s, const TriArrays &A, const double *pos_new, const double *pos_last,
                               const double *z, const double *u_in, double *u_out, SolveState *st, double *partials);
+void launch_pt_update_z_hard(int mode, cudaStream_t s, const PointArrays &A, const double *pos, const double *u, double *z,
+                             double *contrib, SolveState *st, double *partials);
+void launch_pt_update_u_hard(int mode, cudaStream_t s, const PointArrays &A, const double *pos_new, const double *pos_last,
+                             const double *z, const double *u_in, double *u_out, SolveState *st, double *partials);
 void launch_tri_bconst(cudaStream_t s, const TriArrays &A, int slot0, const int64_t *inc_ptr, const int *inc,
                        const double *pos, double *bconst);
 void launch_restore_if_reject(int grid, cudaStream_t s, double *ucur, const double *gdef, int64_t n, SolveState *st);

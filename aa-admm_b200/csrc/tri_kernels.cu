@@ -7,6 +7,9 @@
 // contributions 9 doubles per triangle behind the tets' 12 T.
 // These kernels run BEFORE the tet kernel of the same phase and leave their residual share in the control
 // block (tri_prim2 / tri_comb); the tet kernel's finishing CTA adds it and takes the decisions.
+#include <algorithm>
+
+#include "collision_prox.cuh"
 #include "tet_kernels.cuh"
 #include "tri_prox.cuh"
 
@@ -141,7 +144,7 @@ __global__ void k_tri_bconst(TriArrays A, int slot0, const int64_t *__restrict__
     const int64_t p1 = inc_ptr[v + 1];
     for (int64_t p = inc_ptr[v]; p < p1; ++p) {
         const int e = inc[p] - slot0;
-        if (e < 0) continue;  // tet slot
+        if (e < 0 || e >= 3 * N) continue;  // tet slot / collision-term slot
         const int t = e / 3, c = e - 3 * t;
         const int4 id = A.idx[t];
         const int ids[3] = {id.x, id.y, id.z};
@@ -179,6 +182,97 @@ __global__ void k_tri_bconst(TriArrays A, int slot0, const int64_t *__restrict__
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) bconst[3 * (size_t)v + j] += s[j];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Collision terms (hard/src/CollisionEnergyTerm.hpp:40-91, created per vertex by Solver::initialize :386-392
+// from set_collisions): 3 rows, D_i x = w x_idx, prox = projection onto the nearest penetrated passive object.
+// u / z: 3 planes x P behind the triangles' planes; contributions 3 doubles per term.
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(TET_BLOCK)
+k_pt_update_z_hard(PointArrays A, const double *__restrict__ pos, const double *__restrict__ u, double *__restrict__ z,
+                   double *__restrict__ contrib, SolveState *st, double *partials) {
+    if (st->done) return;
+    if (MODE == MODE_REDO && !st->reject) return;
+    const int P = A.n_pts;
+    double acc[1] = {0.0};
+    for (int t = blockIdx.x * TET_BLOCK + threadIdx.x; t < P; t += gridDim.x * TET_BLOCK) {
+        const int v = A.vert[t];
+        const double w = A.w[t], winv = 1.0 / w;
+        double F[3], ui[3], zi[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            ui[k] = u[(size_t)k * P + t];
+            F[k] = w * pos[3 * (size_t)v + k];
+            zi[k] = (F[k] + ui[k]) * winv;
+        }
+        collision_prox_point(A.n_objs, A.types, A.prm, zi);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            z[(size_t)k * P + t] = zi[k];
+            const double wz = w * zi[k];
+            const double d = F[k] - wz;
+            acc[0] += d * d;
+            contrib[3 * (size_t)t + k] = (A.rho_dt2 * w) * (wz - ui[k]);
+        }
+    }
+    double out[1];
+    if (grid_reduce<1, TET_BLOCK>(acc, partials, &st->ticket, out)) {
+        if (threadIdx.x == 0) st->pt_prim2 = out[0];
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TET_BLOCK)
+k_pt_update_u_hard(PointArrays A, const double *__restrict__ pos_new, const double *__restrict__ pos_last,
+                   const double *__restrict__ z, const double *__restrict__ u_in, double *__restrict__ u_out,
+                   SolveState *st, double *partials) {
+    if (st->done) return;
+    const int P = A.n_pts;
+    double acc[2] = {0.0, 0.0};
+    for (int t = blockIdx.x * TET_BLOCK + threadIdx.x; t < P; t += gridDim.x * TET_BLOCK) {
+        const int v = A.vert[t];
+        const double w = A.w[t];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double xn = pos_new[3 * (size_t)v + k];
+            const double d = w * xn - w * z[(size_t)k * P + t];
+            u_out[(size_t)k * P + t] = u_in[(size_t)k * P + t] + d;
+            if (MODE == MODE_ITER) {
+                acc[0] += d * d;
+                const double e = w * (xn - pos_last[3 * (size_t)v + k]);
+                acc[1] += e * e;
+            }
+        }
+    }
+    if (MODE != MODE_ITER) return;
+    double out[2];
+    if (grid_reduce<2, TET_BLOCK>(acc, partials, &st->ticket, out)) {
+        if (threadIdx.x == 0) st->pt_comb = out[0] + out[1];
+    }
+}
+
+static int pt_grid(const PointArrays &A) {
+    return std::max(1, std::min((A.n_pts + TET_BLOCK - 1) / TET_BLOCK, stream_grid(8)));
+}
+void launch_pt_update_z_hard(int mode, cudaStream_t s, const PointArrays &A, const double *pos, const double *u, double *z,
+                             double *contrib, SolveState *st, double *partials) {
+    const int g = pt_grid(A);
+    if (mode == MODE_WARM)
+        k_pt_update_z_hard<MODE_WARM><<<g, TET_BLOCK, 0, s>>>(A, pos, u, z, contrib, st, partials);
+    else if (mode == MODE_ITER)
+        k_pt_update_z_hard<MODE_ITER><<<g, TET_BLOCK, 0, s>>>(A, pos, u, z, contrib, st, partials);
+    else
+        k_pt_update_z_hard<MODE_REDO><<<g, TET_BLOCK, 0, s>>>(A, pos, u, z, contrib, st, partials);
+}
+void launch_pt_update_u_hard(int mode, cudaStream_t s, const PointArrays &A, const double *pos_new, const double *pos_last,
+                             const double *z, const double *u_in, double *u_out, SolveState *st, double *partials) {
+    const int g = pt_grid(A);
+    if (mode == MODE_WARM)
+        k_pt_update_u_hard<MODE_WARM><<<g, TET_BLOCK, 0, s>>>(A, pos_new, pos_last, z, u_in, u_out, st, partials);
+    else
+        k_pt_update_u_hard<MODE_ITER><<<g, TET_BLOCK, 0, s>>>(A, pos_new, pos_last, z, u_in, u_out, st, partials);
 }
 
 static int tri_grid(const TriArrays &A) {

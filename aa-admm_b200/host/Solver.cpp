@@ -108,6 +108,32 @@ void Solver::set_pins(const std::vector<int> &inds, const std::vector<Vec3> &poi
     }
 }
 
+// hard/src/Solver.cpp:318-344
+void Solver::set_collisions(const std::vector<int> &inds, const std::vector<Vec3> &points) {
+    const int dof = (int)m_x.size();
+    const bool in_place = points.size() != inds.size();
+    if ((dof == 0 && in_place) || (in_place && points.size() > 0))
+        throw std::runtime_error("**Solver::set_collisions Error: Bad input.");
+    if (initialized) {
+        // the reference only re-activates the existing terms (:336-343); the set itself is fixed by initialize()
+        bool same = inds.size() == m_collisions.size();
+        for (size_t i = 0; same && i < inds.size(); ++i) same = m_collisions.count(inds[i]) > 0;
+        if (!same) throw std::runtime_error("**Solver::set_collisions Error: collision vertex set changed after initialize.");
+        return;
+    }
+    m_collisions.clear();
+    for (size_t i = 0; i < inds.size(); ++i) {
+        const int idx = inds[i];
+        m_collisions[idx] = in_place ? Vec3{m_x[idx * 3 + 0], m_x[idx * 3 + 1], m_x[idx * 3 + 2]} : points[i];
+    }
+}
+
+// hard/src/Solver.cpp:346-348
+void Solver::add_obstacle(std::shared_ptr<PassiveCollision> obj) {
+    if (initialized) throw std::runtime_error("**Solver::add_obstacle Error: add obstacles before initialize (B200 device scene).");
+    m_obstacles.push_back(obj);
+}
+
 // hard/src/Solver.cpp:361-491 / xzu/src/Solver.cpp:373-498
 bool Solver::initialize(const Settings &settings_) {
     m_settings = settings_;
@@ -164,6 +190,20 @@ bool Solver::initialize(const Settings &settings_) {
     tri_in.limit_max = tri_lmax.data();
     if (tri_in.n_tris > 0 && m_settings.ordering != Settings::HARD_ZXU)
         throw std::runtime_error("admm::Solver (B200): triangle energy terms run under the hard_zxu ordering only");
+    // one Collision term per vertex of set_collisions (hard/src/Solver.cpp:386-392), weight as the Collision ctor
+    // computes it: sqrt(bulk modulus of Lame::soft_rubber() * 2) (CollisionEnergyTerm.hpp:63-69)
+    std::vector<int> col_verts;
+    std::vector<double> col_w;
+    for (auto &kv : m_collisions) {
+        col_verts.push_back(kv.first);
+        col_w.push_back(std::sqrt(Lame::soft_rubber().bulk_modulus() * 2.0));
+    }
+    aaadmm::PointInput pt_in;
+    pt_in.n = (int)col_verts.size();
+    pt_in.verts = col_verts.data();
+    pt_in.weight = col_w.data();
+    if (pt_in.n > 0 && m_settings.ordering != Settings::HARD_ZXU)
+        throw std::runtime_error("admm::Solver (B200): collision terms run under the hard_zxu ordering only");
     std::vector<double> masses(n_verts);
     for (int v = 0; v < n_verts; ++v) masses[v] = m_masses[3 * (size_t)v];
     std::vector<int> pinned;
@@ -176,7 +216,7 @@ bool Solver::initialize(const Settings &settings_) {
     const double dt2 = m_settings.timestep_s * m_settings.timestep_s;
     const double rho = (m_settings.ordering == Settings::HARD_ZXU) ? m_settings.penalty : 1.0;
     if (!aaadmm::build_tet_system(m_sys, n_verts, rest12.data(), n_tets, tets.data(), material.data(), youngs.data(),
-                                  poisson.data(), masses.data(), pinned, rho * dt2, &tri_in))
+                                  poisson.data(), masses.data(), pinned, rho * dt2, &tri_in, &pt_in))
         throw std::runtime_error(m_sys.error);
 
     // factor Ahat once on the host (nested dissection + multifrontal LDL^T)
@@ -210,6 +250,18 @@ bool Solver::initialize(const Settings &settings_) {
     d.tri_weight = m_sys.tri_weight.data();
     d.tri_limit_min = m_sys.tri_limit_min.data();
     d.tri_limit_max = m_sys.tri_limit_max.data();
+    std::vector<int> obj_type;
+    std::vector<double> obj_prm;
+    for (auto &o : m_obstacles) {
+        obj_type.push_back(o->type);
+        obj_prm.insert(obj_prm.end(), o->prm.begin(), o->prm.end());
+    }
+    d.n_collisions = m_sys.n_pts;
+    d.collision_vert = m_sys.pt_dev.data();
+    d.collision_weight = m_sys.pt_weight.data();
+    d.n_obstacles = (int)obj_type.size();
+    d.obstacle_type = obj_type.data();
+    d.obstacle_prm = obj_prm.data();
     d.n_verts = m_sys.n_verts;
     d.n_free = m_sys.n_free;
     d.n_tets = m_sys.n_tets;

@@ -116,6 +116,62 @@ inline void create_tris_from_mesh(std::vector<std::shared_ptr<EnergyTerm>> &ener
     }
 }
 
+// Analytic passive obstacles (hard/src/PassiveObject.hpp:32-136). The reference evaluates signed_distance()
+// through a virtual call per vertex on the CPU; here an obstacle only carries its tag and parameters
+// ({cx, cy, cz, nx, ny, nz, radius}; Floor: cx = y) and the projection runs in the device batch.
+class PassiveCollision {
+public:
+    virtual ~PassiveCollision() {}
+    int type = AAADMM_PASSIVE_FLOOR;
+    std::array<double, 7> prm{{0, 0, 0, 0, 0, 0, 0}};
+};
+class Floor : public PassiveCollision {
+public:
+    double m_y;
+    Floor(double y) : m_y(y) {
+        type = AAADMM_PASSIVE_FLOOR;
+        prm[0] = y;
+    }
+};
+class SlideFloor : public PassiveCollision {
+public:
+    Vec3 center, normal;  // the normal is normalised in the device batch like the reference ctor does
+    SlideFloor(const Vec3 &c, const Vec3 &n) : center(c), normal(n) {
+        type = AAADMM_PASSIVE_SLIDE_FLOOR;
+        for (int j = 0; j < 3; ++j) prm[j] = c[j], prm[3 + j] = n[j];
+    }
+};
+class Sphere : public PassiveCollision {
+public:
+    Vec3 center;
+    double rad;
+    Sphere(const Vec3 &c, double r) : center(c), rad(r) {
+        type = AAADMM_PASSIVE_SPHERE;
+        for (int j = 0; j < 3; ++j) prm[j] = c[j];
+        prm[6] = r;
+    }
+};
+class PlaneAndHalfSphere : public PassiveCollision {
+public:
+    Vec3 center;
+    double rad;
+    PlaneAndHalfSphere(const Vec3 &c, double r) : center(c), rad(r) {
+        type = AAADMM_PASSIVE_PLANE_HALF_SPHERE;
+        for (int j = 0; j < 3; ++j) prm[j] = c[j];
+        prm[6] = r;
+    }
+};
+class Cylinder : public PassiveCollision {
+public:
+    Vec3 center;
+    double rad;
+    Cylinder(const Vec3 &c, double r) : center(c), rad(r) {
+        type = AAADMM_PASSIVE_CYLINDER;
+        for (int j = 0; j < 3; ++j) prm[j] = c[j];
+        prm[6] = r;
+    }
+};
+
 // src/ExplicitForce.hpp:33-46: explicit velocity updates applied on the host at the start of step().
 class ExplicitForce {
 public:
@@ -196,6 +252,10 @@ public:
     }
 
     void set_pins(const std::vector<int> &inds, const std::vector<Vec3> &points = std::vector<Vec3>());
+    // hard/src/Solver.cpp:318-348: the listed vertices get one Collision energy term each at initialize();
+    // obstacles must be added before initialize() (the device scene keeps their parameters).
+    void set_collisions(const std::vector<int> &inds, const std::vector<Vec3> &points = std::vector<Vec3>());
+    void add_obstacle(std::shared_ptr<PassiveCollision> obj);
     bool initialize(const Settings &settings_ = Settings());
     void step();
     const RuntimeData &runtime_data() { return m_runtime; }
@@ -221,6 +281,8 @@ protected:
     RuntimeData m_runtime;
     bool initialized;
     std::map<int, Vec3> m_pins;
+    std::map<int, Vec3> m_collisions;  // ConstraintSet::collisions
+    std::vector<std::shared_ptr<PassiveCollision>> m_obstacles;
     std::vector<double> m_x_pin;  // in the order set_pins received them (reference: m_x_pin)
     std::vector<int> positive_pin;
     bool factor_from_cache = false;    // the last initialize() took the factor from Settings::factor_cache

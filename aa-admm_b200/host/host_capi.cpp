@@ -1,6 +1,7 @@
 // C entry points of libaaadmm_host.so: the host-side mirror classes (admm::Solver, the beam
 // scene builder, the setup factorisation) made callable from ctypes for tests, bench.py and
 // smoke(). The compute entry points live in libaaadmm_b200.so (include/aaadmm.h).
+#include <cmath>
 #include <cstring>
 #include <iostream>
 #include <memory>
@@ -187,7 +188,7 @@ struct SystemHandle {
 };
 void *aaadmm_host_system_new(const float *verts, int n_verts, const int *tets, int n_tets, const int *tris, int n_tris,
                              const float *masses, double youngs, double poisson, const int *pins, int n_pins,
-                             double rho_dt2) {
+                             double rho_dt2, const int *collision_verts, int n_collisions) {
     try {
         std::vector<double> rest12((size_t)12 * n_tets), rest9((size_t)9 * n_tris), m(n_verts);
         std::vector<double> ey(std::max(n_tets, 1), youngs), ep(std::max(n_tets, 1), poisson);
@@ -207,8 +208,14 @@ void *aaadmm_host_system_new(const float *verts, int n_verts, const int *tets, i
         ti.poisson = tp.data();
         std::unique_ptr<SystemHandle> h(new SystemHandle());
         std::vector<int> pinned(pins, pins + n_pins);
+        // weight of the reference's Collision ctor (CollisionEnergyTerm.hpp:63-69)
+        std::vector<double> cw(std::max(n_collisions, 1), std::sqrt(admm::Lame::soft_rubber().bulk_modulus() * 2.0));
+        aaadmm::PointInput pi;
+        pi.n = n_collisions;
+        pi.verts = collision_verts;
+        pi.weight = cw.data();
         if (!aaadmm::build_tet_system(h->S, n_verts, rest12.data(), n_tets, tets, nullptr, ey.data(), ep.data(), m.data(),
-                                      pinned, rho_dt2, &ti)) {
+                                      pinned, rho_dt2, &ti, &pi)) {
             g_err = h->S.error;
             return nullptr;
         }
@@ -264,6 +271,31 @@ int aaadmm_host_solver_add_wind(void *h, const int *tris, int n_tris, const doub
     std::shared_ptr<admm::WindForce> wind(new admm::WindForce(faces));
     wind->direction = {dir3[0], dir3[1], dir3[2]};
     s.ext_forces.push_back(wind);
+    return 0;
+    HOST_CATCH
+}
+// Solver::set_collisions (in place) + Solver::add_obstacle with an analytic obstacle given by tag and parameters.
+int aaadmm_host_solver_set_collisions(void *h, const int *idx, int n) {
+    HOST_TRY
+    std::vector<int> inds(idx, idx + n);
+    static_cast<SolverHandle *>(h)->solver.set_collisions(inds);
+    return 0;
+    HOST_CATCH
+}
+int aaadmm_host_solver_add_obstacle(void *h, int type, const double *prm7) {
+    HOST_TRY
+    admm::Solver &s = static_cast<SolverHandle *>(h)->solver;
+    const admm::Vec3 c = {prm7[0], prm7[1], prm7[2]}, n = {prm7[3], prm7[4], prm7[5]};
+    std::shared_ptr<admm::PassiveCollision> o;
+    switch (type) {
+        case AAADMM_PASSIVE_FLOOR: o = std::make_shared<admm::Floor>(prm7[0]); break;
+        case AAADMM_PASSIVE_SLIDE_FLOOR: o = std::make_shared<admm::SlideFloor>(c, n); break;
+        case AAADMM_PASSIVE_SPHERE: o = std::make_shared<admm::Sphere>(c, prm7[6]); break;
+        case AAADMM_PASSIVE_PLANE_HALF_SPHERE: o = std::make_shared<admm::PlaneAndHalfSphere>(c, prm7[6]); break;
+        case AAADMM_PASSIVE_CYLINDER: o = std::make_shared<admm::Cylinder>(c, prm7[6]); break;
+        default: throw std::runtime_error("add_obstacle: unknown obstacle type");
+    }
+    s.add_obstacle(o);
     return 0;
     HOST_CATCH
 }

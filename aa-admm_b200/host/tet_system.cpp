@@ -78,7 +78,8 @@ bool tet_constants(const double *rest12, double youngs, double poisson, double *
 
 bool build_tet_system(TetSystem &S, int n_verts, const double *rest12, int n_tets, const int *tets,
                       const int *material, const double *youngs, const double *poisson,
-                      const double *masses, const std::vector<int> &pinned, double rho_dt2, const TriInput *tri) {
+                      const double *masses, const std::vector<int> &pinned, double rho_dt2, const TriInput *tri,
+                      const PointInput *pts) {
     S = TetSystem();
     S.n_verts = n_verts;
     S.n_tets = n_tets;
@@ -180,12 +181,35 @@ bool build_tet_system(TetSystem &S, int n_verts, const double *rest12, int n_tet
         }
     }
 
-    // incidence lists over free vertices (tet slots first, then the triangle slots)
+    const int n_pts = pts ? pts->n : 0;
+    S.n_pts = n_pts;
+    S.pt_dev.resize(n_pts);
+    S.pt_weight.resize(n_pts);
+    for (int i = 0; i < n_pts; ++i) {
+        const int v = pts->verts[i];
+        if (v < 0 || v >= n_verts) {
+            S.error = "collision vertex index out of range";
+            return false;
+        }
+        if (is_pin[v]) {
+            S.error = "collision term on a pinned vertex is not supported";
+            return false;
+        }
+        if (!(pts->weight[i] > 0.0)) {
+            S.error = "**EnergyTerm::get_reduction Error: Some weight leq 0";
+            return false;
+        }
+        S.pt_dev[i] = S.vert_to_dev[v];
+        S.pt_weight[i] = pts->weight[i];
+    }
+
+    // incidence lists over free vertices (tet slots first, then the triangle slots, then the collision terms)
     S.inc_ptr.assign(nf + 1, 0);
     for (size_t k = 0; k < S.tet_dev.size(); ++k)
         if (S.tet_dev[k] < nf) S.inc_ptr[S.tet_dev[k] + 1]++;
     for (size_t k = 0; k < S.tri_dev.size(); ++k)
         if (S.tri_dev[k] < nf) S.inc_ptr[S.tri_dev[k] + 1]++;
+    for (int i = 0; i < n_pts; ++i) S.inc_ptr[S.pt_dev[i] + 1]++;
     for (int v = 0; v < nf; ++v) S.inc_ptr[v + 1] += S.inc_ptr[v];
     S.inc.resize(S.inc_ptr[nf]);
     {
@@ -195,6 +219,8 @@ bool build_tet_system(TetSystem &S, int n_verts, const double *rest12, int n_tet
         const size_t slot0 = (size_t)4 * n_tets;
         for (size_t k = 0; k < S.tri_dev.size(); ++k)
             if (S.tri_dev[k] < nf) S.inc[pos[S.tri_dev[k]]++] = (int)(slot0 + k);
+        const size_t slot1 = slot0 + (size_t)3 * n_tris;
+        for (int i = 0; i < n_pts; ++i) S.inc[pos[S.pt_dev[i]]++] = (int)(slot1 + i);
     }
 
     // Ahat = M + rho dt^2 sum_t w_t^2 G_t^T G_t, G_t(r,c) = sum_k Sel(c,k) Binv(k,r)
@@ -257,6 +283,11 @@ bool build_tet_system(TetSystem &S, int n_verts, const double *rest12, int n_tet
                 tv.push_back(s);
             }
         }
+    }
+    for (int i = 0; i < n_pts; ++i) {
+        tr.push_back(S.pt_dev[i]);
+        tc.push_back(S.pt_dev[i]);
+        tv.push_back(rho_dt2 * (S.pt_weight[i] * S.pt_weight[i]));
     }
     S.Ahat = sym_from_triplets(nf, tr, tc, tv, false);
     return true;

@@ -49,8 +49,13 @@ struct TetSystem {
     std::vector<double> tri_weight;    // sqrt(bulk modulus * area)
     std::vector<double> tri_area;
     std::vector<double> tri_limit_min, tri_limit_max;  // Lame::limit_min / limit_max of the term
-    // incidence CSR over free vertices: entries are contribution slots, tet*4 + corner for the tets and
-    // 4*n_tets + tri*3 + corner for the triangles (a slot holds 3 doubles)
+    // collision terms (hard/src/CollisionEnergyTerm.hpp:40-91): 3 rows each, D_i x = w x_idx, free vertices only
+    int n_pts = 0;
+    std::vector<int> pt_dev;        // device vertex id per term
+    std::vector<double> pt_weight;
+    // incidence CSR over free vertices: entries are contribution slots, tet*4 + corner for the tets,
+    // 4*n_tets + tri*3 + corner for the triangles, 4*n_tets + 3*n_tris + term for the collision terms
+    // (a slot holds 3 doubles)
     std::vector<int64_t> inc_ptr;
     std::vector<int> inc;
     SymLower Ahat;  // n_free x n_free
@@ -72,9 +77,15 @@ struct TriInput {
     const int *tris = nullptr;
     const double *youngs = nullptr, *poisson = nullptr, *limit_min = nullptr, *limit_max = nullptr;
 };
+// Optional collision terms: one per listed vertex (must be free), with its weight.
+struct PointInput {
+    int n = 0;
+    const int *verts = nullptr;
+    const double *weight = nullptr;
+};
 bool build_tet_system(TetSystem &S, int n_verts, const double *rest12, int n_tets, const int *tets,
                       const int *material, const double *youngs, const double *poisson,
                       const double *masses, const std::vector<int> &pinned, double rho_dt2,
-                      const TriInput *tri = nullptr);
+                      const TriInput *tri = nullptr, const PointInput *pts = nullptr);
 
 }  // namespace aaadmm

@@ -93,7 +93,8 @@ typedef struct {
     const double *lambda;    /* n_tets (hyper-elastic only, may be NULL)                       */
     const double *mass_free; /* n_free scalar lumped masses                                    */
     const int64_t *inc_ptr;  /* n_free+1: incidence CSR over free vertices                     */
-    const int *inc;          /* entries = contribution slots: tet*4+corner, triangles 4*n_tets+tri*3+corner */
+    const int *inc;          /* entries = contribution slots: tet*4+corner, triangles 4*n_tets+tri*3+corner,
+                                collision terms 4*n_tets+3*n_tris+term                                */
     double rho_dt2;          /* penalty * dt^2 (hard) or dt^2 (xzu)                            */
     const double *volume;    /* n_tets rest volumes (hyper-elastic only, may be NULL)          */
     /* Triangle (cloth) terms of the same scene: TriEnergyTerm, admm_anderson_hard_zxu/src/TriEnergyTerm.cpp:29-105
@@ -105,6 +106,15 @@ typedef struct {
     const double *tri_weight;    /* n_tris ADMM weights sqrt(K area)                                  */
     const double *tri_limit_min; /* n_tris strain limits Lame::limit_min (NULL = -100, no limiting)   */
     const double *tri_limit_max; /* n_tris strain limits Lame::limit_max (NULL = +100, no limiting)   */
+    /* Collision terms: one Collision energy term per listed FREE vertex (Solver::set_collisions +
+     * hard/src/Solver.cpp:386-392, CollisionEnergyTerm.hpp:40-91: 3 rows, D_i x = w x_idx) against the analytic
+     * passive objects added with Solver::add_obstacle (PassiveObject.hpp:32-136). hard_zxu ordering only. */
+    int n_collisions;
+    const int *collision_vert;      /* n_collisions free-first vertex ids (< n_free)                  */
+    const double *collision_weight; /* n_collisions weights (reference: sqrt(K_soft_rubber * 2))      */
+    int n_obstacles;
+    const int *obstacle_type;       /* n_obstacles AAADMM_PASSIVE_*                                   */
+    const double *obstacle_prm;     /* n_obstacles x 7: {cx, cy, cz, nx, ny, nz, radius} (Floor: cx = y) */
 } aaadmm_tetscene_desc;
 
 #define AAADMM_ORDER_HARD_ZXU 0

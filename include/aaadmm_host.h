@@ -37,10 +37,11 @@ int aaadmm_host_factor_stats(void *h, double *s6);
 
 /* Operator setup alone, no device involved (role of Solver::initialize, hard/src/Solver.cpp:361-491): the scalar
  * system matrix Ahat of A = M + rho dt^2 D^T W^2 D = Ahat (x) I3 for a scene of tets and triangles with the pinned
- * vertices eliminated; lower CSC incl. diagonal over the free vertices (dev_to_vert maps them back). */
+ * vertices eliminated; lower CSC incl. diagonal over the free vertices (dev_to_vert maps them back).
+ * collision_verts: vertices that carry a Collision energy term (Solver::set_collisions), may be NULL / 0. */
 void *aaadmm_host_system_new(const float *verts, int n_verts, const int *tets, int n_tets, const int *tris, int n_tris,
                              const float *masses, double youngs, double poisson, const int *pins, int n_pins,
-                             double rho_dt2);
+                             double rho_dt2, const int *collision_verts, int n_collisions);
 void aaadmm_host_system_free(void *h);
 int aaadmm_host_system_counts(void *h, int *n_free, int64_t *nnz);
 int aaadmm_host_system_copy(void *h, int64_t *Ap, int *Ai, double *Ax, int *dev_to_vert);
@@ -58,6 +59,11 @@ int aaadmm_host_solver_add_trimesh(void *h, const float *verts, int n_verts, con
                                    double limit_max);
 /* WindForce (src/ExplicitForce.hpp:39-46) over n_tris triangles (global vertex ids) pushed into Solver::ext_forces */
 int aaadmm_host_solver_add_wind(void *h, const int *tris, int n_tris, const double *dir3);
+/* Solver::set_collisions (vertices constrained in place, hard/src/Solver.cpp:318-344) and Solver::add_obstacle with an
+ * analytic obstacle (PassiveObject.hpp:32-136): type = AAADMM_PASSIVE_*, prm7 = {cx, cy, cz, nx, ny, nz, radius}
+ * (Floor: prm7[0] = y). Both before initialize; hard_zxu ordering only. */
+int aaadmm_host_solver_set_collisions(void *h, const int *idx, int n);
+int aaadmm_host_solver_add_obstacle(void *h, int type, const double *prm7);
 /* WindForce::project on caller arrays (x, v: 3 per vertex; v updated in place) */
 int aaadmm_host_wind_project(const int *tris, int n_tris, const double *dir3, double dt, const double *x, double *v,
                              int n_verts);

@@ -489,6 +489,34 @@ void RFN(spring_prox)(double *z, const double *pins, const int *active, int n) {
         Eigen::Map<Eigen::VectorXd>(z + 3 * i, 3) = zi;
     }
 }
+// Solver::set_collisions (in place) and Solver::add_obstacle with one analytic passive object, as
+// samples/Asia2019/plinkohit.cpp:84-96 and plinkopony.cpp:60-117 use them.
+int RFN(set_collisions)(void *hp, const int *idx, int n) {
+    Handle *h = static_cast<Handle *>(hp);
+    std::vector<int> inds(idx, idx + n);
+    try {
+        h->solver.set_collisions(inds, std::vector<Eigen::Vector3d>());
+    } catch (std::exception &e) {
+        fprintf(stderr, "ref set_collisions: %s\n", e.what());
+        return -1;
+    }
+    return 0;
+}
+int RFN(add_obstacle)(void *hp, int type, const double *p) {
+    Handle *h = static_cast<Handle *>(hp);
+    Eigen::Vector3d c(p[0], p[1], p[2]), nrm(p[3], p[4], p[5]);
+    std::shared_ptr<admm::PassiveCollision> o;
+    switch (type) {
+    case 0: o = std::make_shared<admm::Floor>(p[0]); break;
+    case 1: o = std::make_shared<admm::SlideFloor>(c, nrm); break;
+    case 2: o = std::make_shared<admm::Sphere>(c, p[6]); break;
+    case 3: o = std::make_shared<admm::PlaneAndHalfSphere>(c, p[6]); break;
+    case 4: o = std::make_shared<admm::Cylinder>(c, p[6]); break;
+    default: return -1;
+    }
+    h->solver.add_obstacle(o);
+    return 0;
+}
 // Collision::prox against a list of analytic passive objects (types: 0 Floor{y}, 1 SlideFloor{c,n},
 // 2 Sphere{c,r}, 3 PlaneAndHalfSphere{c,r}, 4 Cylinder{c,r}; 7 parameters per object), n points in place.
 int RFN(collision_prox)(int n_objs, const int *types, const double *prm, double *z, int n) {

@@ -65,6 +65,9 @@ class RefSolver:
         f("add_trimesh").argtypes = [C.c_void_p, c_fp, C.c_int, c_ip, C.c_int, c_fp, C.c_double, C.c_double,
                                      C.c_double, C.c_double]
         f("add_wind").argtypes = [C.c_void_p, c_ip, C.c_int, c_dp]
+        if variant == "hard":
+            f("set_collisions").argtypes = [C.c_void_p, c_ip, C.c_int]
+            f("add_obstacle").argtypes = [C.c_void_p, C.c_int, c_dp]
         f("set_threads").argtypes = [C.c_int]
         f("set_pins").argtypes = [C.c_void_p, c_ip, c_dp, C.c_int]
         f("initialize").argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double]
@@ -115,6 +118,16 @@ class RefSolver:
         if r < 0:
             raise RuntimeError("reference add_trimesh failed")
         return r
+
+    def set_collisions(self, idx):
+        idx = np.ascontiguousarray(idx, np.int32)
+        if self._f("set_collisions")(self.h, _ip(idx), len(idx)) != 0:
+            raise RuntimeError("reference set_collisions failed")
+
+    def add_obstacle(self, kind, prm7):
+        p = np.ascontiguousarray(prm7, np.float64)
+        if self._f("add_obstacle")(self.h, int(kind), _dp(p)) != 0:
+            raise RuntimeError("reference add_obstacle failed")
 
     def add_wind(self, tris, direction):
         """WindForce over `tris` (global vertex ids); forces one OpenMP thread (the reference's loop races otherwise)."""

@@ -133,3 +133,31 @@ def run_cloth(make_solver, frames=2, n=8, m=5, accel=True, iters=60, limits=(-10
         hist.append(s.step())
         xs.append(s.x())
     return hist, xs
+
+
+PLINKO_OBSTACLES = [  # (AAADMM_PASSIVE_* tag, {cx, cy, cz, nx, ny, nz, radius}); Floor: cx = y
+    (0, (-0.45, 0, 0, 0, 0, 0, 0)),                 # Floor just above the beam's lowest vertices
+    (2, (0.0, -1.2, 0.0, 0, 0, 0, 0.8)),            # Sphere under the middle
+    (4, (1.0, -1.0, 0.0, 0, 0, 0, 0.55)),           # Cylinder (axis along z) under one end
+    (3, (-1.2, -0.47, 0.0, 0, 0, 0, 0.3)),          # PlaneAndHalfSphere under the other end
+    (1, (0.0, -0.6, 0.0, 0.2, 1.0, 0.1, 0)),        # SlideFloor, tilted
+]
+
+
+def run_plinko(make_solver, A, frames=3, dims=(8, 2, 2), m=5, accel=True, iters=40, dt=1.0 / 30.0, obstacles=None):
+    """A free tet beam (no pins) dropping onto analytic obstacles with a Collision energy term on every vertex
+    (samples/Asia2019/plinkohit.cpp / plinkopony.cpp pattern: add_obstacle + set_collisions(all vertices)),
+    hard_zxu ordering. The lowest vertices already penetrate several obstacles in the first frame."""
+    bs = A.BeamScene().add(*dims, 0.0)
+    verts, tets, masses, _, _, _ = bs.arrays()
+    s = make_solver()
+    s.add_tetmesh(verts, tets, masses, 1e6, 0.399, 0)
+    for kind, prm in (PLINKO_OBSTACLES if obstacles is None else obstacles):
+        s.add_obstacle(kind, prm)
+    s.set_collisions(np.arange(len(verts), dtype=np.int32))
+    s.initialize(dt, iters, -9.8, max(m, 1), accel, 1.0)
+    hist, xs = [], []
+    for f in range(frames):
+        hist.append(s.step())
+        xs.append(s.x())
+    return hist, xs

@@ -291,3 +291,28 @@ def test_wind_force_matches_reference(A):
     want = refbind.ref_wind_project(tris, d, 1.0 / 30.0, x, v)
     assert np.abs(got - v).max() > 1e-3
     assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+
+
+def test_system_matrix_with_collision_terms_matches_reference(A):
+    """Collision energy terms (Solver::set_collisions, one 3-row term per vertex with the weight of the reference's
+    Collision ctor) add rho dt^2 w^2 to the diagonal: host matrix against the reference's solver_termA, no pins."""
+    from oracle import refbind
+    if not refbind.have_ref():
+        pytest.skip("oracle/_ref (compiled reference) not present")
+    bv, bt, bm, _, _, _ = A.BeamScene().add(4, 2, 2, 0.0).arrays()
+    col = np.arange(0, len(bv), 2, dtype=np.int32)
+    r = refbind.RefSolver("hard")
+    r.add_tetmesh(bv, bt, bm, 1e6, 0.399, 0)
+    r.add_obstacle(0, (-0.45, 0, 0, 0, 0, 0, 0))
+    r.set_collisions(col)
+    dt, rho = 1.0 / 30.0, 1.5
+    r.initialize(dt, 5, -9.8, 5, True, rho)
+    n, rp, ci, v = r.termA()
+    Aref = np.zeros((n, n))
+    for i in range(n):
+        Aref[i, ci[rp[i]:rp[i + 1]]] = v[rp[i]:rp[i + 1]]
+    Ahat, d2v = A.host_system_matrix(bv, bt, np.zeros((0, 3), np.int32), bm, [], rho * dt * dt, 1e6, 0.399, collisions=col)
+    assert n == 3 * Ahat.shape[0] == 3 * len(bv)
+    scale = np.abs(Aref).max()
+    for c in range(3):
+        assert np.abs(Aref[c::3, c::3] - Ahat).max() < 1e-12 * scale
