@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import aa_admm_b200 as A  # noqa: E402  (host-side scene builder only)
 from oracle import refbind as R  # noqa: E402
-from scenes import run_cloth  # noqa: E402
+from scenes import run_cloth, run_plinko  # noqa: E402
 
 CASES = {
     "hard_cloth_8_m5": dict(n=8, m=5, accel=True, limits=(-100.0, 100.0), beam=None),
@@ -41,8 +41,22 @@ def case(n, m, accel, limits, beam, frames=2, iters=60, youngs=1e5, poisson=0.3,
                 pin_speed=pin_speed)
 
 
+def plinko_case(m, accel, dims=(8, 2, 2), frames=3, iters=40):
+    """Free beam on analytic obstacles with a Collision term on every vertex (tests/scenes.py run_plinko)."""
+    hist, xs = run_plinko(lambda: R.RefSolver("hard"), A, frames=frames, dims=dims, m=m, accel=accel, iters=iters)
+    comb, rej, rows = [], [], []
+    for h in hist:
+        c, r = np.zeros(iters), np.zeros(iters)
+        c[:len(h)], r[:len(h)] = h[:, 2], h[:, 3]
+        comb.append(c), rej.append(r), rows.append(len(h))
+    return dict(comb=np.array(comb), rej=np.array(rej), rows=np.array(rows), x=np.array(xs), dims=np.array(dims), m=m,
+                accel=int(accel), frames=frames, iters=iters)
+
+
 if __name__ == "__main__":
     assert R.have_ref(), "build oracle/_ref first (make -C oracle ref)"
+    np.savez_compressed(os.path.join(HERE, "hard_plinko_8x2x2_m5.npz"), **plinko_case(5, True))
+    np.savez_compressed(os.path.join(HERE, "hard_plinko_8x2x2_noacc.npz"), **plinko_case(0, False))
     for name, kw in CASES.items():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **case(**kw))
         print("wrote", name)

@@ -548,3 +548,23 @@ def test_triangle_terms_are_rejected_under_xzu(gpu):
     s.set_pins(pins, verts[pins].astype(np.float64))
     with pytest.raises(Exception):
         s.initialize(1.0 / 30.0, 10, -9.8, 5, True, 1.0, 1)
+
+
+# ---- Collision energy terms + analytic obstacles inside Solver::step (SURVEY 8 row J wired into row D) -------
+@pytest.mark.parametrize("name", ["hard_plinko_8x2x2_m5", "hard_plinko_8x2x2_noacc"])
+def test_plinko_step_vs_golden(gpu, name):
+    """Free beam dropping onto Floor / Sphere / Cylinder / PlaneAndHalfSphere / SlideFloor with a Collision term on
+    every vertex, against golden trajectories of the unmodified reference (tests/golden/make_golden_cloth.py)."""
+    from scenes import run_plinko
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    hg, xg = run_plinko(gpu.Solver, gpu, frames=int(g["frames"]), dims=tuple(int(d) for d in g["dims"]), m=int(g["m"]),
+                        accel=bool(g["accel"]), iters=int(g["iters"]))
+    _check_cloth(hg, xg, g["comb"], g["rows"], g["rej"], g["x"], bool(g["accel"]))
+
+
+def test_plinko_step_vs_reference_larger(gpu, ref):
+    from scenes import run_plinko
+    kw = dict(frames=2, dims=(16, 4, 4), m=5, accel=True, iters=30)
+    hg, xg = run_plinko(gpu.Solver, gpu, **kw)
+    hr, xr = run_plinko(lambda: ref.RefSolver("hard"), gpu, **kw)
+    _check_cloth(hg, xg, [h[:, 2] for h in hr], [len(h) for h in hr], [h[:, 3] for h in hr], xr, True)
