@@ -58,7 +58,8 @@ AAADMM_HD Rot2 make_jacobi(double x, double y, double z) {
     const double t = (tau > 0.0) ? 1.0 / (tau + w) : 1.0 / (tau - w);
     const double sign_t = t > 0.0 ? 1.0 : -1.0;
     const double n = 1.0 / sqrt(t * t + 1.0);
-    r.s = -sign_t * (y / fabs(y)) * fabs(t) * n;
+    // y / |y| of the reference is exactly +-1 for the finite non-zero y that reach this line: no division needed
+    r.s = -sign_t * (y > 0.0 ? 1.0 : -1.0) * fabs(t) * n;
     r.c = n;
     return r;
 }

@@ -18,6 +18,8 @@ With N > 1 (torchrun) every rank runs one independent scene of the same size on 
 """
 import argparse
 import json
+
+import numpy as np
 import os
 import statistics
 import subprocess
@@ -237,7 +239,7 @@ def run_gpu(args):
         t0 = time.perf_counter()
         for _ in range(args.steps):
             solver.set_pins(pidx, scene.stretch(dt))
-            solver.step()
+            last_hist = solver.step()
             info = solver.info()
             iters += info["iter_num"]
             loop_ms += info["loop_ms"]
@@ -282,6 +284,22 @@ def run_gpu(args):
             "phases": {k: {"ms": round(v["ms"], 4), "algo_GB": round(v["bytes"] / 1e9, 4),
                            "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)} for k, v in phases.items()}}
     cpu = cpu_baseline_leg() if (world == 1 and not args.no_cpu) else None
+    # time-to-tolerance of the last timed frame (BASELINE metric): device time until the logged combined
+    # residual first falls below tau. tau = 1e-20 is the reference's own break threshold (hard/src/Solver.cpp:93,188),
+    # the relative thresholds are fractions of the frame's first logged residual.
+    comb = last_hist[:, 1]
+    ms_per_it = info["loop_ms"] / max(1, info["iter_num"])
+
+    def first_below(tau):
+        k = np.nonzero(comb < tau)[0]
+        return None if len(k) == 0 else int(k[0]) + 1
+
+    ttt = {"frame_iterations": int(len(comb)), "comb_first": float(comb[0]), "comb_last": float(comb[-1]),
+           "ms_per_iteration": ms_per_it, "tau": {}}
+    for name, tau in (("abs_1e-20", 1e-20), ("rel_1e-2", 1e-2 * comb[0]), ("rel_1e-4", 1e-4 * comb[0]),
+                      ("rel_1e-6", 1e-6 * comb[0])):
+        k = first_below(tau)
+        ttt["tau"][name] = {"iterations": k, "ms": None if k is None else k * ms_per_it}
     line = {"metric": "admm_anderson_iterations_per_sec_1M_tets", "value": value, "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": max_loop_ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
@@ -294,7 +312,7 @@ def run_gpu(args):
                        "iterations_timed": tot_iters, "rejects": rejects, "setup_s": round(setup_s, 2),
                        "factor": {"nnz_L": finfo["nnz_L"], "numeric_s": round(finfo["seconds_numeric"], 2),
                                   "levels": linfo["levels"], "blocks": linfo["blocks"], "max_block": linfo["max_block"]}},
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "time_to_tol": ttt,
             "e2e": {"value": e2e, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk.summary()}
     print(json.dumps(line))

@@ -568,3 +568,23 @@ def test_plinko_step_vs_reference_larger(gpu, ref):
     hg, xg = run_plinko(gpu.Solver, gpu, **kw)
     hr, xr = run_plinko(lambda: ref.RefSolver("hard"), gpu, **kw)
     _check_cloth(hg, xg, [h[:, 2] for h in hr], [len(h) for h in hr], [h[:, 3] for h in hr], xr, True)
+
+
+def test_windyflag_cpp_sample_runs_on_the_device(gpu, tmp_path):
+    """samples/windyflag.cpp (reference-style C++ against the drop-in classes): cloth + wind + sphere obstacle."""
+    import re
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_host_cpu import _build_sample
+    exe = _build_sample(tmp_path, "windyflag")
+    for extra in ([], ["-sphere"]):
+        r = subprocess.run([exe, "-it", "60", "-a", "1", "-am", "5", "-frames", "3", "-n", "12"] + extra,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr + r.stdout
+        frames = re.findall(r"frame (\d+): (\d+) iterations, (\d+) rejected, combined residual (\S+) -> (\S+),", r.stdout)
+        assert len(frames) == 3
+        for f in frames:
+            assert int(f[1]) > 0 and float(f[4]) < float(f[3])  # the residual goes down within a frame
+        m = re.search(r"checksum of positions (\S+), largest z (\S+)", r.stdout)
+        assert np.isfinite(float(m.group(1))) and float(m.group(2)) > 0.05  # the wind pushes the flag along +z

@@ -213,10 +213,10 @@ def test_ensemble_sharding_and_gather_gloo_world2(A):
         assert np.allclose(t[:, 1], 10 + np.arange(7))
 
 
-def _build_sample(tmp_path):
-    exe = str(tmp_path / "beams")
+def _build_sample(tmp_path, name="beams"):
+    exe = str(tmp_path / name)
     cmd = ["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "aa-admm_b200", "host"),
-           os.path.join(ROOT, "samples", "beams.cpp"), "-L" + os.path.join(ROOT, "aa-admm_b200"), "-laaadmm_host", "-laaadmm_b200",
+           os.path.join(ROOT, "samples", name + ".cpp"), "-L" + os.path.join(ROOT, "aa-admm_b200"), "-laaadmm_host", "-laaadmm_b200",
            "-Wl,-rpath," + os.path.join(ROOT, "aa-admm_b200"), "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
@@ -228,6 +228,15 @@ def test_reference_style_sample_compiles_against_the_dropin_classes(A, tmp_path)
     against the host mirror (source-level drop-in). Without a GPU it stops in initialize()."""
     exe = _build_sample(tmp_path)
     r = subprocess.run([exe, "-it", "5", "-frames", "1"], capture_output=True, text=True)
+    if A.device_count() <= 0:
+        assert r.returncode != 0 and ("CUDA" in (r.stderr + r.stdout) or "aaadmm" in (r.stderr + r.stdout))
+
+
+def test_windyflag_sample_compiles_against_the_dropin_classes(A, tmp_path):
+    """samples/windyflag.cpp: TriEnergyTerm + strain limits + WindForce + obstacle / set_collisions through the
+    reference's own calls; builds against the host mirror. Without a GPU it stops in initialize()."""
+    exe = _build_sample(tmp_path, "windyflag")
+    r = subprocess.run([exe, "-it", "5", "-frames", "1", "-n", "6", "-sphere"], capture_output=True, text=True)
     if A.device_count() <= 0:
         assert r.returncode != 0 and ("CUDA" in (r.stderr + r.stdout) or "aaadmm" in (r.stderr + r.stdout))
 
