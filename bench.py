@@ -292,7 +292,10 @@ def run_gpu(args):
 
     def first_below(tau):
         k = np.nonzero(comb < tau)[0]
-        return None if len(k) == 0 else int(k[0]) + 1
+        if len(k):
+            return int(k[0]) + 1
+        # the iteration that triggers the reference's `break` is not logged (hard/src/Solver.cpp:188-189 vs :210-212)
+        return int(info["iter_num"]) if (tau == 1e-20 and info["iter_num"] > len(comb)) else None
 
     ttt = {"frame_iterations": int(len(comb)), "comb_first": float(comb[0]), "comb_last": float(comb[-1]),
            "ms_per_iteration": ms_per_it, "tau": {}}

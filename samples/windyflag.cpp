@@ -52,7 +52,10 @@ int main(int argc, char **argv) {
 
     admm::Solver solver;
     solver.add_nodes(verts.data(), masses.data(), n_verts);
-    admm::Lame very_soft_rubber(50, 0.1);  // windyflag.cpp:84-86
+    // windyflag.cpp:84-86; with the obstacle the sheet is soft rubber like the plinko solids: the Collision terms
+    // carry the weight of soft rubber (CollisionEnergyTerm.hpp:63-69) and a 50 Pa cloth next to them makes the
+    // reference itself run into NaN in the second frame
+    admm::Lame very_soft_rubber = sphere ? admm::Lame::soft_rubber() : admm::Lame(50, 0.1);
     very_soft_rubber.limit_min = 0.95;
     very_soft_rubber.limit_max = 1.05;
     admm::create_tris_from_mesh<float, admm::TriEnergyTerm>(solver.energyterms, verts.data(), faces.data(),
@@ -65,7 +68,7 @@ int main(int argc, char **argv) {
     solver.ext_forces.push_back(wind);
 
     if (sphere) {  // plinkohit.cpp:84-96 pattern: an obstacle + a collision term on every free vertex
-        solver.add_obstacle(std::make_shared<admm::Sphere>(admm::Vec3{0.7, 1.4, 0.35}, 0.3));
+        solver.add_obstacle(std::make_shared<admm::Sphere>(admm::Vec3{0.7, 1.4, 0.35}, 0.34));
         std::vector<int> all;
         for (int v = 0; v < n_verts; ++v)
             if (v != pins[0] && v != pins[1]) all.push_back(v);

@@ -161,3 +161,34 @@ def run_plinko(make_solver, A, frames=3, dims=(8, 2, 2), m=5, accel=True, iters=
         hist.append(s.step())
         xs.append(s.x())
     return hist, xs
+
+
+def run_flag_with_sphere(make_solver, frames=3, n=12, m=5, accel=True, iters=60, dt=1.0 / 30.0, sphere=True,
+                         youngs=50.0, poisson=0.1, limits=(0.95, 1.05), radius=0.3):
+    """The scene of samples/windyflag.cpp -sphere: vertical flag (windyflag.cpp material, strain limits, wind), two
+    pinned corners, a sphere obstacle and a Collision term on every free vertex (triangles + collision terms + pins
+    in one solver)."""
+    verts = np.array([[i / n, 1.0 + j / n, 0.01 * ((i * 7 + j * 3) % 5)] for i in range(n + 1) for j in range(n + 1)],
+                     np.float32)
+    vid = lambda i, j: i * (n + 1) + j
+    tris = []
+    for i in range(n):
+        for j in range(n):
+            a, b, c, d = vid(i, j), vid(i + 1, j), vid(i + 1, j + 1), vid(i, j + 1)
+            tris += [(a, b, c), (a, c, d)]
+    tris = np.array(tris, np.int32)
+    masses = np.full(len(verts), 1.0 / len(verts), np.float32)
+    pins = np.array([vid(0, 0), vid(0, n)], np.int32)
+    s = make_solver()
+    s.add_trimesh(verts, tris, masses, youngs, poisson, limits[0], limits[1])
+    s.add_wind(tris, (25.0, 0.0, 5.0))
+    s.set_pins(pins, verts[pins].astype(np.float64))
+    if sphere:
+        s.add_obstacle(2, (0.7, 1.4, 0.35, 0, 0, 0, radius))
+        s.set_collisions(np.array([v for v in range(len(verts)) if v not in set(pins.tolist())], np.int32))
+    s.initialize(dt, iters, -9.8, max(m, 1), accel, 1.0)
+    hist, xs = [], []
+    for f in range(frames):
+        hist.append(s.step())
+        xs.append(s.x())
+    return hist, xs

@@ -588,3 +588,13 @@ def test_windyflag_cpp_sample_runs_on_the_device(gpu, tmp_path):
             assert int(f[1]) > 0 and float(f[4]) < float(f[3])  # the residual goes down within a frame
         m = re.search(r"checksum of positions (\S+), largest z (\S+)", r.stdout)
         assert np.isfinite(float(m.group(1))) and float(m.group(2)) > 0.05  # the wind pushes the flag along +z
+
+
+def test_flag_with_sphere_vs_reference(gpu, ref):
+    """Triangles + Collision terms + pins + wind in ONE solver (the scene of samples/windyflag.cpp -sphere) against the
+    compiled reference run on the spot."""
+    from scenes import run_flag_with_sphere
+    kw = dict(frames=2, n=12, m=5, accel=True, iters=60, youngs=1e7, poisson=0.399, limits=(0.95, 1.05), radius=0.34)
+    hg, xg = run_flag_with_sphere(gpu.Solver, **kw)
+    hr, xr = run_flag_with_sphere(lambda: ref.RefSolver("hard"), **kw)
+    _check_cloth(hg, xg, [h[:, 2] for h in hr], [len(h) for h in hr], [h[:, 3] for h in hr], xr, True)
