@@ -151,6 +151,12 @@ def host_lib():
         H.aaadmm_host_solver_device_factor.argtypes = [vp]
         H.aaadmm_host_tet_constants.argtypes = [c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp]
         H.aaadmm_host_tri_constants.argtypes = [c_dp, C.c_double, C.c_double, c_dp, c_dp, c_dp]
+        H.aaadmm_host_mesh_load.restype = vp
+        H.aaadmm_host_mesh_load.argtypes = [C.c_char_p, C.c_int]
+        H.aaadmm_host_mesh_free.argtypes = [vp]
+        H.aaadmm_host_mesh_counts.argtypes = [vp, c_ip, c_ip]
+        H.aaadmm_host_mesh_copy.argtypes = [vp, c_fp, c_ip, c_fp]
+        H.aaadmm_host_mesh_save.argtypes = [vp, C.c_char_p]
         H.aaadmm_host_system_new.restype = vp
         H.aaadmm_host_system_new.argtypes = [c_fp, C.c_int, c_ip, C.c_int, c_ip, C.c_int, c_fp, C.c_double, C.c_double,
                                              c_ip, C.c_int, C.c_double, c_ip, C.c_int]
@@ -521,6 +527,29 @@ class Solver:
         by = np.zeros(NPROF)
         _ck(cuda_lib().aaadmm_tetscene_algo_bytes(self._scene(), anderson_m, _dp(by)))
         return {n: dict(ms=float(ms[i]), bytes=float(by[i])) for i, n in enumerate(PROF_NAMES)}
+
+
+def load_mesh(path, kind="elenode", save_as=None):
+    """mcl::meshio::load_elenode (`path` without extension) / load_obj through the host mirror. Returns float32
+    vertices, int32 elements (4 or 3 per row) and the lumped float32 masses of binding::add_tetmesh / add_trimesh.
+    save_as: also write the mesh back with save_elenode / save_obj."""
+    H = host_lib()
+    k = {"elenode": 0, "obj": 1}[kind]
+    h = H.aaadmm_host_mesh_load(str(path).encode(), k)
+    if not h:
+        raise AaadmmError(H.aaadmm_host_last_error().decode())
+    try:
+        nv, ne = C.c_int(0), C.c_int(0)
+        H.aaadmm_host_mesh_counts(h, C.byref(nv), C.byref(ne))
+        verts = np.zeros((nv.value, 3), np.float32)
+        elems = np.zeros((ne.value, 4 if k == 0 else 3), np.int32)
+        masses = np.zeros(nv.value, np.float32)
+        _hk(H.aaadmm_host_mesh_copy(h, _fp(verts), _ip(elems), _fp(masses)))
+        if save_as is not None:
+            _hk(H.aaadmm_host_mesh_save(h, str(save_as).encode()))
+    finally:
+        H.aaadmm_host_mesh_free(h)
+    return verts, elems, masses
 
 
 def host_system_matrix(verts, tets, tris, masses, pins, rho_dt2, youngs=1e7, poisson=0.399, collisions=()):

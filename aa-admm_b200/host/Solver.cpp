@@ -56,14 +56,14 @@ void WindForce::project(double dt, std::vector<double> &x, std::vector<double> &
             b[j] = x[idx[2] + j] - x[idx[0] + j];
         }
         const double n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
-        const double n2 = (n[0] * n[0] + n[1] * n[1]) + n[2] * n[2];
+        const double n2 = n[0] * n[0] + (n[1] * n[1] + n[2] * n[2]);  // Eigen's 1 + 2 split of a 3-vector reduction
         const double len = std::sqrt(n2);
         double normal[3] = {n[0], n[1], n[2]};
         if (n2 > 0.0)
             for (int j = 0; j < 3; ++j) normal[j] = n[j] / len;
         const double area = 0.5 * len;
         const double alpha_n = 1000.0;
-        const double v_n = (normal[0] * vr[0] + normal[1] * vr[1]) + normal[2] * vr[2];
+        const double v_n = normal[0] * vr[0] + (normal[1] * vr[1] + normal[2] * vr[2]);
         const double s = -alpha_n * area * v_n * std::fabs(v_n);
         for (int j = 0; j < 3; ++j) {
             double f = s * normal[j];

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/aaadmm_host.h"
+#include "MeshIO.hpp"
 #include "Solver.hpp"
 #include "beam_scene.hpp"
 #include "sparse_ldlt.hpp"
@@ -182,6 +183,59 @@ int aaadmm_host_solver_add_tetmesh(void *h, const float *verts, int n_verts, con
     return prev + n_verts;
     HOST_CATCH
 }
+// ---- mesh files (mcl::meshio + the masses binding::add_tetmesh / add_trimesh give the nodes) ----------------
+struct MeshHandle {
+    int kind = 0;  // 0 tet mesh (.ele/.node), 1 triangle mesh (.obj)
+    mcl::TetMesh tet;
+    mcl::TriangleMesh tri;
+};
+void *aaadmm_host_mesh_load(const char *path, int kind) {
+    try {
+        std::unique_ptr<MeshHandle> h(new MeshHandle());
+        h->kind = kind;
+        const bool ok = kind == 0 ? mcl::meshio::load_elenode(&h->tet, path) : mcl::meshio::load_obj(&h->tri, path);
+        if (!ok) {
+            g_err = std::string("could not load mesh ") + path;
+            return nullptr;
+        }
+        return h.release();
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void aaadmm_host_mesh_free(void *h) { delete static_cast<MeshHandle *>(h); }
+int aaadmm_host_mesh_counts(void *hp, int *n_verts, int *n_elems) {
+    MeshHandle *h = static_cast<MeshHandle *>(hp);
+    *n_verts = (int)(h->kind == 0 ? h->tet.vertices.size() : h->tri.vertices.size());
+    *n_elems = (int)(h->kind == 0 ? h->tet.tets.size() : h->tri.faces.size());
+    return 0;
+}
+int aaadmm_host_mesh_copy(void *hp, float *verts, int *elems, float *masses) {
+    HOST_TRY
+    MeshHandle *h = static_cast<MeshHandle *>(hp);
+    std::vector<float> m;
+    if (h->kind == 0) {
+        if (!h->tet.vertices.empty()) memcpy(verts, &h->tet.vertices[0][0], sizeof(float) * 3 * h->tet.vertices.size());
+        if (!h->tet.tets.empty()) memcpy(elems, &h->tet.tets[0][0], sizeof(int) * 4 * h->tet.tets.size());
+        h->tet.weighted_masses(m, 1522.f);  // binding::add_tetmesh
+    } else {
+        if (!h->tri.vertices.empty()) memcpy(verts, &h->tri.vertices[0][0], sizeof(float) * 3 * h->tri.vertices.size());
+        if (!h->tri.faces.empty()) memcpy(elems, &h->tri.faces[0][0], sizeof(int) * 3 * h->tri.faces.size());
+        h->tri.weighted_masses(m, 1.0f);  // binding::add_trimesh
+    }
+    std::copy(m.begin(), m.end(), masses);
+    return 0;
+    HOST_CATCH
+}
+int aaadmm_host_mesh_save(void *hp, const char *path) {
+    HOST_TRY
+    MeshHandle *h = static_cast<MeshHandle *>(hp);
+    const bool ok = h->kind == 0 ? mcl::meshio::save_elenode(&h->tet, path) : mcl::meshio::save_obj(&h->tri, path);
+    return ok ? 0 : -1;
+    HOST_CATCH
+}
+
 // ---- operator setup alone (no device): the scalar system matrix of a scene of tets and triangles ------------
 struct SystemHandle {
     aaadmm::TetSystem S;

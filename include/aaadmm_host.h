@@ -35,6 +35,16 @@ int aaadmm_host_factor_copy(void *h, int64_t *Lp, int *Li, double *Lx, double *D
 int aaadmm_host_factor_solve(void *h, const double *b, double *x, int nrhs);
 int aaadmm_host_factor_stats(void *h, double *s6);
 
+/* Mesh files of the reference's samples (host/MeshIO.hpp = mcl::meshio of deps/mclscene/include/MCL/MeshIO.hpp:55-345):
+ * kind 0 = TetGen ASCII `path`.ele + `path`.node (0- or 1-based, inverted tets re-ordered, float32 vertices),
+ * kind 1 = Wavefront .obj (v / f records, triangles). copy: vertices (3 float per vertex), elements (4 or 3 ints) and the
+ * lumped float32 masses binding::add_tetmesh (1522 kg/m^3) / add_trimesh (1 kg/m^2) give the nodes. */
+void *aaadmm_host_mesh_load(const char *path, int kind);
+void aaadmm_host_mesh_free(void *h);
+int aaadmm_host_mesh_counts(void *h, int *n_verts, int *n_elems);
+int aaadmm_host_mesh_copy(void *h, float *verts, int *elems, float *masses);
+int aaadmm_host_mesh_save(void *h, const char *path);
+
 /* Operator setup alone, no device involved (role of Solver::initialize, hard/src/Solver.cpp:361-491): the scalar
  * system matrix Ahat of A = M + rho dt^2 D^T W^2 D = Ahat (x) I3 for a scene of tets and triangles with the pinned
  * vertices eliminated; lower CSC incl. diagonal over the free vertices (dev_to_vert maps them back).

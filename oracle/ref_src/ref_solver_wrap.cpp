@@ -30,6 +30,7 @@
 #include "SpringEnergyTerm.hpp"
 #include "CollisionEnergyTerm.hpp"
 #endif
+#include "MCL/MeshIO.hpp"
 #include "MCL/TetMesh.hpp"
 #include "MCL/ShapeFactory.hpp"
 #include "MCL/XForm.hpp"
@@ -151,6 +152,42 @@ int RFN(add_tetmesh)(void *hp, const float *verts, int n_verts, const int *tets,
         return -1;
     }
     return prev + n_verts;
+}
+
+// mcl::meshio readers + weighted_masses with the densities of binding::add_tetmesh / add_trimesh
+// (samples/utils/AddMeshes.hpp:105-106,188-189). kind 0: path.ele/.node, 1: .obj. Two calls: sizes, then arrays.
+int RFN(mesh_load)(const char *path, int kind, int *n_verts, int *n_elems, float *verts, int *elems, float *masses) {
+    try {
+        std::vector<float> m;
+        if (kind == 0) {
+            mcl::TetMesh mesh;
+            if (!mcl::meshio::load_elenode(&mesh, path)) return -1;
+            *n_verts = (int)mesh.vertices.size();
+            *n_elems = (int)mesh.tets.size();
+            if (!verts) return 0;
+            mesh.weighted_masses(m, 1522.f);
+            for (int i = 0; i < *n_verts; ++i)
+                for (int j = 0; j < 3; ++j) verts[3 * i + j] = mesh.vertices[i][j];
+            for (int i = 0; i < *n_elems; ++i)
+                for (int j = 0; j < 4; ++j) elems[4 * i + j] = mesh.tets[i][j];
+        } else {
+            mcl::TriangleMesh mesh;
+            if (!mcl::meshio::load_obj(&mesh, path)) return -1;
+            *n_verts = (int)mesh.vertices.size();
+            *n_elems = (int)mesh.faces.size();
+            if (!verts) return 0;
+            mesh.weighted_masses(m, 1.0f);
+            for (int i = 0; i < *n_verts; ++i)
+                for (int j = 0; j < 3; ++j) verts[3 * i + j] = mesh.vertices[i][j];
+            for (int i = 0; i < *n_elems; ++i)
+                for (int j = 0; j < 3; ++j) elems[3 * i + j] = mesh.faces[i][j];
+        }
+        memcpy(masses, m.data(), sizeof(float) * m.size());
+        return 0;
+    } catch (std::exception &e) {
+        fprintf(stderr, "ref mesh_load: %s\n", e.what());
+        return -2;
+    }
 }
 
 // Triangle (cloth) mesh: nodes + create_tris_from_mesh<float, TriEnergyTerm>, as binding::add_trimesh

@@ -243,6 +243,22 @@ def ref_tet_constants(verts4, youngs=1e7, poisson=0.399):
     return w.value, vol.value, binv
 
 
+def ref_load_mesh(path, kind="elenode"):
+    """The reference's mcl::meshio reader + weighted_masses (densities of binding::add_tetmesh / add_trimesh)."""
+    lib = _load("libref_hard.so")
+    k = {"elenode": 0, "obj": 1}[kind]
+    f = lib.ref_hard_mesh_load
+    f.argtypes = [C.c_char_p, C.c_int, c_ip, c_ip, c_fp, c_ip, c_fp]
+    nv, ne = C.c_int(0), C.c_int(0)
+    if f(str(path).encode(), k, C.byref(nv), C.byref(ne), None, None, None) != 0:
+        raise RuntimeError("reference mesh_load failed for %s" % path)
+    verts = np.zeros((nv.value, 3), np.float32)
+    elems = np.zeros((ne.value, 4 if k == 0 else 3), np.int32)
+    masses = np.zeros(nv.value, np.float32)
+    assert f(str(path).encode(), k, C.byref(nv), C.byref(ne), _fp(verts), _ip(elems), _fp(masses)) == 0
+    return verts, elems, masses
+
+
 def ref_wind_project(tris, direction, dt, x, v):
     """Reference WindForce::project (hard_zxu/src/ExplicitForce.cpp:47-105), one thread; returns the new v."""
     lib = _load("libref_hard.so")

@@ -598,3 +598,35 @@ def test_flag_with_sphere_vs_reference(gpu, ref):
     hg, xg = run_flag_with_sphere(gpu.Solver, **kw)
     hr, xr = run_flag_with_sphere(lambda: ref.RefSolver("hard"), **kw)
     _check_cloth(hg, xg, [h[:, 2] for h in hr], [len(h) for h in hr], [h[:, 3] for h in hr], xr, True)
+
+
+def test_plinko_cpp_sample_matches_python_path(gpu, tmp_path):
+    """samples/plinko.cpp reads a TetGen pair with mcl::meshio::load_elenode and adds it with binding::add_tetmesh
+    (masses from weighted_masses); the same mesh through the ctypes path must give the same frames."""
+    import re
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_host_cpu import _build_sample, write_elenode
+    exe = _build_sample(tmp_path, "plinko")
+    v, t, m, _, _, _ = gpu.BeamScene().add(8, 2, 2, 0.0).arrays()
+    write_elenode(str(tmp_path / "beam"), v, t)
+    r = subprocess.run([exe, "-mesh", str(tmp_path / "beam"), "-it", "40", "-a", "1", "-am", "5", "-frames", "3"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    frames = re.findall(r"frame (\d+): (\d+) iterations, (\d+) rejected, combined residual (\S+) -> (\S+),", r.stdout)
+    assert len(frames) == 3
+    lo = float(v[:, 1].min())
+    s = gpu.Solver()
+    s.add_tetmesh(v, t, m, 1e6, 0.399, 0)
+    s.add_obstacle(0, (lo + 0.05, 0, 0, 0, 0, 0, 0))
+    s.add_obstacle(3, (0.0, lo + 0.03, 0.0, 0, 0, 0, 0.3))
+    s.add_obstacle(4, (1.0, lo - 0.5, 0.0, 0, 0, 0, 0.55))
+    s.set_collisions(np.arange(len(v), dtype=np.int32))
+    s.initialize(1.0 / 30.0, 40, -9.8, 5, True, 1.0)
+    for f in frames:
+        h = s.step()
+        assert int(f[1]) == len(h) and int(f[2]) == int(h[:, 2].sum())
+        assert abs(float(f[3]) - h[0, 1]) <= 1e-5 * h[0, 1] and abs(float(f[4]) - h[-1, 1]) <= 1e-5 * h[-1, 1]
+    low = float(re.search(r"lowest y (\S+) ", r.stdout).group(1))
+    assert low > lo - 0.2  # the floor holds the beam
