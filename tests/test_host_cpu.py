@@ -393,3 +393,26 @@ def test_mesh_readers_vs_reference_on_its_sample_data(A):
         for a, b in zip(got, want):
             assert a.shape == b.shape and np.array_equal(a, b), name
         assert got[1].shape[0] > 100
+
+
+def test_triangle_and_collision_error_paths(A):
+    """Error behaviour of the reference's constructors and setters, kept by the host mirror: bad strain limits
+    (TriEnergyTerm.cpp:32-33), collision terms on a pinned vertex (not supported here), bad collision index."""
+    from scenes import cloth_arrays
+    verts, tris, masses, pins = cloth_arrays(3)
+    s = A.Solver()
+    with pytest.raises(A.AaadmmError, match="Strain limit min"):
+        s.add_trimesh(verts, tris, masses, 1e5, 0.3, 1.5, 100.0)
+    s = A.Solver()
+    with pytest.raises(A.AaadmmError, match="Strain limit max"):
+        s.add_trimesh(verts, tris, masses, 1e5, 0.3, -100.0, 0.5)
+    # a collision term on a pinned vertex / out of range is refused by the operator setup
+    with pytest.raises(A.AaadmmError, match="pinned"):
+        A.host_system_matrix(verts, np.zeros((0, 4), np.int32), tris, masses, pins, 1e-3, 1e5, 0.3, collisions=[int(pins[0])])
+    with pytest.raises(A.AaadmmError, match="out of range"):
+        A.host_system_matrix(verts, np.zeros((0, 4), np.int32), tris, masses, pins, 1e-3, 1e5, 0.3, collisions=[10 ** 6])
+    # degenerate (zero-area) rest triangle: weight 0 is refused like EnergyTerm::get_reduction does
+    flat = verts.copy()
+    flat[tris[0]] = flat[tris[0][0]]
+    with pytest.raises(A.AaadmmError):
+        A.host_system_matrix(flat, np.zeros((0, 4), np.int32), tris, masses, pins, 1e-3, 1e5, 0.3)
