@@ -193,6 +193,9 @@ def cpu_baseline_leg():
 
 def run_gpu(args):
     rank, world, local = dist_env()
+    if world > 1 and "OMP_NUM_THREADS" not in os.environ:
+        # the ranks of one box share its host cores for the (untimed) setup factorisation
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
     import aa_admm_b200 as A
     if A.device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
