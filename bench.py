@@ -193,8 +193,9 @@ def cpu_baseline_leg():
 
 def run_gpu(args):
     rank, world, local = dist_env()
-    if world > 1 and "OMP_NUM_THREADS" not in os.environ:
-        # the ranks of one box share its host cores for the (untimed) setup factorisation
+    if world > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        # torchrun exports OMP_NUM_THREADS=1; the ranks of one box share its host cores for the (untimed) setup
+        # factorisation instead (read by the OpenMP runtime when the host library is loaded below)
         os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
     import aa_admm_b200 as A
     if A.device_count() <= 0:
