@@ -95,15 +95,23 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NQ], double *partials /*
     if (!s_last) return false;
     __threadfence();
     // stage 2
+    // (all loads of all quantities are issued before the first use: one L2 round trip instead of NQ)
     const int nb = gridDim.x;
+    double x[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) x[q] = 0.0;
+    for (int b = threadIdx.x; b < nb; b += BLOCK) {
+        double t[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) t[q] = __ldcg(&partials[(size_t)q * nb + b]);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) x[q] += t[q];
+    }
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-        double x = 0.0;
-        for (int b = threadIdx.x; b < nb; b += BLOCK) x += __ldcg(&partials[(size_t)q * nb + b]);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        __syncthreads();
-        if (lane == 0) s_red[q][warp] = x;
+        for (int o = 16; o > 0; o >>= 1) x[q] += __shfl_down_sync(0xffffffffu, x[q], o);
+        if (lane == 0) s_red[q][warp] = x[q];
     }
     __syncthreads();
     if (threadIdx.x == 0) {
