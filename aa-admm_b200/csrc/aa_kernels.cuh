@@ -20,45 +20,61 @@ namespace aaadmm {
 constexpr int AA_BLOCK = 256;
 constexpr int AA_ILP = 2;  // elements per thread and loop turn in the streaming passes
 
-// Runs in thread 0 of the finishing CTA of pass 1. acc[0..M) = <dF_c, dF_j> (acc[c] = |dF_c|^2),
-// acc[M..2M) = <dF_j, F>, all raw.
-template <int M>
-__device__ void aa_finish(SolveState *st, const double *acc) {
+// Shared-memory scratch of the m_k x m_k solve between the two passes.
+struct AaFinishWork {
+    double dots[AA_MAX_M], rhsv[AA_MAX_M];  // <dF_c, dF_j> (dots[c] = |dF_c|^2) and <dF_j, F>, raw
+    double g[AA_MAX_M], rhs[AA_MAX_M], theta[AA_MAX_M], hc[AA_MAX_M];
+    double A[AA_MAX_M * AA_MAX_M];
+    int trans[AA_MAX_M];
+    CodWarpWork qr;
+};
+
+// Runs in warp 0 of the finishing CTA of pass 1 (all 32 lanes): hard/src/AndersonAcceleration.h:174-205 with the
+// scaled Gram matrix (see the header comment). The scalings are one division per lane, the QR is cod_qr_warp, the rest
+// of the complete orthogonal decomposition (cod_finish) runs on lane 0.
+__device__ __forceinline__ void aa_finish_warp(SolveState *st, AaFinishWork &w) {
+    const int lane = threadIdx.x & 31;
     const int iter = st->aa_iter, c = st->aa_col, m = st->aa_m;
-    if (iter == 0) {
-        st->aa_mk = 0;
-        st->aa_iter = 1;
-        return;
-    }
     const double eps = 1e-14;
     const int mk = iter < m ? iter : m;
-    const double nrm2 = acc[c];
+    const double nrm2 = w.dots[c];
     const double scale = fmax(eps, sqrt(nrm2));
-    st->aa_scale[c] = scale;
-    double theta[AA_MAX_M];
+    const double sc = (lane < mk && lane != c) ? st->aa_scale[lane] : scale;  // scale of column `lane`
     if (mk == 1) {
-        theta[0] = 0.0;
-        const double sq = nrm2 / (scale * scale);
-        st->aa_M[0] = sq;
-        const double dF_norm = sqrt(sq);
-        if (dF_norm > eps) theta[0] = ((acc[M + c] / scale) / dF_norm) / dF_norm;
+        if (lane == 0) {
+            w.theta[0] = 0.0;
+            const double sq = nrm2 / (scale * scale);
+            st->aa_M[0] = sq;
+            const double dF_norm = sqrt(sq);
+            if (dF_norm > eps) w.theta[0] = ((w.rhsv[c] / scale) / dF_norm) / dF_norm;
+        }
     } else {
-        double A[AA_MAX_M * AA_MAX_M], rhs[AA_MAX_M];
-        for (int j = 0; j < mk; ++j) {
-            const double g = (j == c) ? nrm2 / (scale * scale) : acc[j] / (scale * st->aa_scale[j]);
-            st->aa_M[c * AA_MAX_M + j] = g;
-            st->aa_M[j * AA_MAX_M + c] = g;
+        if (lane < mk) {
+            const double g = (lane == c) ? nrm2 / (scale * scale) : w.dots[lane] / (scale * sc);
+            st->aa_M[c * AA_MAX_M + lane] = g;
+            st->aa_M[lane * AA_MAX_M + c] = g;
+            w.g[lane] = g;
+            w.rhs[lane] = w.rhsv[lane] / sc;
         }
-        for (int j = 0; j < mk; ++j) {
-            rhs[j] = acc[M + j] / st->aa_scale[j];
-            for (int i = 0; i < mk; ++i) A[j * mk + i] = st->aa_M[j * AA_MAX_M + i];
+        __syncwarp();
+        for (int e = lane; e < mk * mk; e += 32) {
+            const int j = e / mk, i = e - j * mk;
+            w.A[e] = (j == c) ? w.g[i] : (i == c) ? w.g[j] : st->aa_M[j * AA_MAX_M + i];
         }
-        cod_solve(A, mk, rhs, theta);
+        __syncwarp();
+        int nonzero_pivots;
+        double maxpivot;
+        cod_qr_warp(w.A, mk, w.hc, w.trans, nonzero_pivots, maxpivot, w.qr);
+        if (lane == 0) cod_finish(w.A, mk, w.hc, w.trans, nonzero_pivots, maxpivot, w.rhs, w.theta);
     }
-    for (int j = 0; j < mk; ++j) st->aa_coef[j] = theta[j] / st->aa_scale[j];
-    st->aa_mk = mk;
-    st->aa_col = (c + 1) % m;
-    st->aa_iter = iter + 1;
+    __syncwarp();
+    if (lane < mk) st->aa_coef[lane] = w.theta[lane] / sc;
+    if (lane == 0) {
+        st->aa_scale[c] = scale;
+        st->aa_mk = mk;
+        st->aa_col = (c + 1) % m;
+        st->aa_iter = iter + 1;
+    }
 }
 
 // G = [g_u (Ne) | g_x (Nt-Ne)]; when gx_dst != nullptr the x part is also copied there
@@ -93,7 +109,8 @@ k_aa_pass1(const double *__restrict__ g_u, const double *__restrict__ g_x, doubl
             const unsigned int t = atomicAdd(&st->ticket, 1u);
             if (t == gridDim.x - 1) {
                 st->ticket = 0u;
-                aa_finish<M>(st, nullptr);
+                st->aa_mk = 0;  // first call after init / reset: nothing to mix yet
+                st->aa_iter = 1;
             }
         }
         return;
@@ -149,8 +166,17 @@ k_aa_pass1(const double *__restrict__ g_u, const double *__restrict__ g_x, doubl
         dGc[i] += g;
     }
     double out[2 * M];
-    if (grid_reduce<2 * M, AA_BLOCK>(acc, partials, &st->ticket, out)) {
-        if (threadIdx.x == 0) aa_finish<M>(st, out);
+    __shared__ AaFinishWork s_fin;
+    if (grid_reduce<2 * M, AA_BLOCK>(acc, partials, &st->ticket, out)) {  // true in every thread of the last CTA
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int q = 0; q < M; ++q) {
+                s_fin.dots[q] = out[q];
+                s_fin.rhsv[q] = out[M + q];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) aa_finish_warp(st, s_fin);
     }
 }
 

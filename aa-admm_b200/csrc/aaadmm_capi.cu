@@ -62,12 +62,20 @@ int launch_aa_pass2(int m, int grid, cudaStream_t s, const double *g_u, const do
     return 0;
 }
 
+// One warp: the QR through cod_qr_warp (what the Anderson passes use), the rest on lane 0.
 __global__ void k_cod(int m, const double *M, const double *rhs, double *x, int *rank) {
-    double A[AA_MAX_M * AA_MAX_M], b[AA_MAX_M], xx[AA_MAX_M];
-    for (int i = 0; i < m * m; ++i) A[i] = M[i];
-    for (int i = 0; i < m; ++i) b[i] = rhs[i];
-    *rank = cod_solve(A, m, b, xx);
-    for (int i = 0; i < m; ++i) x[i] = xx[i];
+    __shared__ double A[AA_MAX_M * AA_MAX_M], b[AA_MAX_M], xx[AA_MAX_M], hc[AA_MAX_M];
+    __shared__ int trans[AA_MAX_M];
+    __shared__ CodWarpWork w;
+    for (int i = threadIdx.x; i < m * m; i += 32) A[i] = M[i];
+    if (threadIdx.x < m) b[threadIdx.x] = rhs[threadIdx.x];
+    __syncwarp();
+    int nonzero_pivots;
+    double maxpivot;
+    cod_qr_warp(A, m, hc, trans, nonzero_pivots, maxpivot, w);
+    if (threadIdx.x == 0) *rank = cod_finish(A, m, hc, trans, nonzero_pivots, maxpivot, b, xx);
+    __syncwarp();
+    if (threadIdx.x < m) x[threadIdx.x] = xx[threadIdx.x];
 }
 
 // AoS (9 consecutive doubles per tet, reference layout) <-> SoA planes
@@ -1171,7 +1179,7 @@ int aaadmm_cod_solve(int m, const double *M, const double *rhs, double *x, int *
     AAADMM_CUDA_OK(cudaMalloc((void **)&dk, sizeof(int)));
     AAADMM_CUDA_OK(cudaMemcpy(dM, M, sizeof(double) * m * m, cudaMemcpyHostToDevice));
     AAADMM_CUDA_OK(cudaMemcpy(dr, rhs, sizeof(double) * m, cudaMemcpyHostToDevice));
-    k_cod<<<1, 1>>>(m, dM, dr, dx, dk);
+    k_cod<<<1, 32>>>(m, dM, dr, dx, dk);
     AAADMM_CUDA_OK(cudaGetLastError());
     AAADMM_CUDA_OK(cudaMemcpy(x, dx, sizeof(double) * m, cudaMemcpyDeviceToHost));
     if (rank) AAADMM_CUDA_OK(cudaMemcpy(rank, dk, sizeof(int), cudaMemcpyDeviceToHost));

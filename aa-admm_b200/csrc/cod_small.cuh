@@ -46,11 +46,10 @@ AAADMM_HD void make_householder(double *x, int n, int inc, double &tau, double &
     }
 }
 
-// Solves min ||A x - b|| (min-norm x when rank deficient). A is m x m column-major (destroyed),
-// b length m, x length m. Returns the detected rank.
-AAADMM_HD int cod_solve(double *A, int m, const double *b, double *x) {
-    double hc[AA_MAX_M], zc[AA_MAX_M], normU[AA_MAX_M], normD[AA_MAX_M], c[AA_MAX_M], y[AA_MAX_M];
-    int trans[AA_MAX_M];
+// Column-pivoted Householder QR of the m x m matrix A (column-major, overwritten by R and the essential parts of the
+// reflectors) with LAPACK-style norm downdating: Eigen/src/QR/ColPivHouseholderQR.h:480-577. One thread.
+AAADMM_HD void cod_qr(double *A, int m, double *hc, int *trans, int &nonzero_pivots, double &maxpivot) {
+    double normU[AA_MAX_M], normD[AA_MAX_M];
     const int rows = m, cols = m, size = m;
 #define A_(r, cc) A[(cc) * m + (r)]
     double maxnorm = 0.0;
@@ -64,8 +63,8 @@ AAADMM_HD int cod_solve(double *A, int m, const double *b, double *x) {
     const double th0 = maxnorm * DBL_EPSILON;
     const double threshold_helper = (th0 * th0) / (double)rows;
     const double downdate_threshold = sqrt(DBL_EPSILON);
-    int nonzero_pivots = size;
-    double maxpivot = 0.0;
+    nonzero_pivots = size;
+    maxpivot = 0.0;
     for (int k = 0; k < size; ++k) {
         int big = k;
         double bn = normU[k];
@@ -125,6 +124,16 @@ AAADMM_HD int cod_solve(double *A, int m, const double *b, double *x) {
             }
         }
     }
+#undef A_
+}
+
+// Everything after the QR: rank decision, the Z reflectors of the complete orthogonal decomposition when rank < m,
+// c = Q^T b, back substitution, Z^* y and the column permutation. One thread. Returns the rank.
+AAADMM_HD int cod_finish(double *A, int m, const double *hc, const int *trans, int nonzero_pivots, double maxpivot,
+                         const double *b, double *x) {
+    double zc[AA_MAX_M], c[AA_MAX_M], y[AA_MAX_M];
+    const int rows = m, cols = m, size = m;
+#define A_(r, cc) A[(cc) * m + (r)]
     // rank
     const double premult = fabs(maxpivot) * (DBL_EPSILON * (double)size);
     int rank = 0;
@@ -224,5 +233,135 @@ AAADMM_HD int cod_solve(double *A, int m, const double *b, double *x) {
 #undef A_
     return rank;
 }
+
+// Solves min ||A x - b|| (min-norm x when rank deficient). A is m x m column-major (destroyed),
+// b length m, x length m. Returns the detected rank.
+AAADMM_HD int cod_solve(double *A, int m, const double *b, double *x) {
+    double hc[AA_MAX_M];
+    int trans[AA_MAX_M], nonzero_pivots;
+    double maxpivot;
+    cod_qr(A, m, hc, trans, nonzero_pivots, maxpivot);
+    return cod_finish(A, m, hc, trans, nonzero_pivots, maxpivot, b, x);
+}
+
+#ifdef __CUDACC__
+// Warp-cooperative cod_qr: exactly the operations of cod_qr on the same operands and in the same order per result,
+// with the independent ones on different lanes. cod_qr in one thread is a chain of about 60 FP64 division /
+// square-root sequences (35 dependent instructions each) plus the dot products: 22 us for m = 5 while every other SM
+// waits. Per elimination step the column norms' downdates, the reflector applications (one lane per trailing column)
+// and the divisions of the Householder vector (one lane per row, the tau division on one more lane) are independent;
+// quantities every lane needs (pivot, tail sum, beta) are recomputed redundantly on all lanes instead of broadcast.
+// A, hc, trans, w.* live in shared memory; all 32 lanes of ONE converged warp call this. m <= AA_MAX_M <= 32.
+struct CodWarpWork {
+    double normU[AA_MAX_M], normD[AA_MAX_M];
+};
+__device__ __forceinline__ void cod_qr_warp(double *A, int m, double *hc, int *trans, int &nonzero_pivots, double &maxpivot,
+                                            CodWarpWork &w) {
+    const int lane = threadIdx.x & 31;
+#define A_(r, cc) A[(cc) * m + (r)]
+    if (lane < m) {
+        double s = 0.0;
+        for (int i = 0; i < m; ++i) s += A_(i, lane) * A_(i, lane);
+        w.normD[lane] = sqrt(s);
+        w.normU[lane] = w.normD[lane];
+    }
+    __syncwarp();
+    double maxnorm = 0.0;
+    for (int k = 0; k < m; ++k)
+        if (w.normU[k] > maxnorm) maxnorm = w.normU[k];
+    const double th0 = maxnorm * DBL_EPSILON;
+    const double threshold_helper = (th0 * th0) / (double)m;
+    const double downdate_threshold = sqrt(DBL_EPSILON);
+    nonzero_pivots = m;
+    maxpivot = 0.0;
+    for (int k = 0; k < m; ++k) {
+        // pivot column: every lane, from the shared norms (uniform result)
+        int big = k;
+        double bn = w.normU[k];
+        for (int j = k + 1; j < m; ++j)
+            if (w.normU[j] > bn) {
+                bn = w.normU[j];
+                big = j;
+            }
+        const double big_sq = bn * bn;
+        if (nonzero_pivots == m && big_sq < threshold_helper * (double)(m - k)) nonzero_pivots = k;
+        __syncwarp();  // all lanes have read the norms
+        if (lane == 0) trans[k] = big;
+        if (k != big) {
+            if (lane < m) {
+                const double t = A_(lane, k);
+                A_(lane, k) = A_(lane, big);
+                A_(lane, big) = t;
+            }
+            if (lane == 0) {
+                double t = w.normU[k];
+                w.normU[k] = w.normU[big];
+                w.normU[big] = t;
+                t = w.normD[k];
+                w.normD[k] = w.normD[big];
+                w.normD[big] = t;
+            }
+        }
+        __syncwarp();
+        // make_householder on A(k:m-1, k): tail sum and beta on every lane, one division per lane
+        double tailSq = 0.0;
+        for (int i = k + 1; i < m; ++i) tailSq += A_(i, k) * A_(i, k);
+        const double c0 = A_(k, k);
+        double beta, tau;
+        __syncwarp();  // column k has been read by everybody before it is scaled
+        if (tailSq <= DBL_MIN) {
+            tau = 0.0;
+            beta = c0;
+            if (lane > k && lane < m) A_(lane, k) = 0.0;
+        } else {
+            beta = sqrt(c0 * c0 + tailSq);
+            if (c0 >= 0.0) beta = -beta;
+            const double den = c0 - beta;
+            // lanes k+1..m-1: essential part x_i / den; all other lanes: tau = (beta - c0) / beta (same instruction stream)
+            const bool mine = lane > k && lane < m;
+            const double num = mine ? A_(lane, k) : (beta - c0);
+            const double q = num / (mine ? den : beta);
+            if (mine) A_(lane, k) = q;
+            tau = __shfl_sync(0xffffffffu, q, 0);  // lane 0 is never one of the row lanes (0 > k is false)
+        }
+        if (lane == 0) {
+            hc[k] = tau;
+            A_(k, k) = beta;
+        }
+        if (fabs(beta) > maxpivot) maxpivot = fabs(beta);
+        __syncwarp();
+        // reflector on the trailing columns and their norm downdates: one lane per column j
+        const int j = k + 1 + lane;
+        if (j < m) {
+            if (m - k == 1) {
+                A_(k, j) *= (1.0 - tau);
+            } else if (tau != 0.0) {
+                double tmp = 0.0;
+                for (int i = k + 1; i < m; ++i) tmp += A_(i, k) * A_(i, j);
+                tmp += A_(k, j);
+                A_(k, j) -= tau * tmp;
+                for (int i = k + 1; i < m; ++i) A_(i, j) -= tau * A_(i, k) * tmp;
+            }
+            if (w.normU[j] != 0.0) {
+                double temp = fabs(A_(k, j)) / w.normU[j];
+                temp = (1.0 + temp) * (1.0 - temp);
+                temp = temp < 0.0 ? 0.0 : temp;
+                const double r = w.normU[j] / w.normD[j];
+                const double temp2 = temp * (r * r);
+                if (temp2 <= downdate_threshold) {
+                    double s = 0.0;
+                    for (int i = k + 1; i < m; ++i) s += A_(i, j) * A_(i, j);
+                    w.normD[j] = sqrt(s);
+                    w.normU[j] = w.normD[j];
+                } else {
+                    w.normU[j] *= sqrt(temp);
+                }
+            }
+        }
+        __syncwarp();
+    }
+#undef A_
+}
+#endif  // __CUDACC__
 
 }  // namespace aaadmm
