@@ -97,6 +97,27 @@ def dist_env():
     return rank, world, local
 
 
+class _NativeStdoutToStderr:
+    """The reference prints progress lines to the C++ stdout from inside initialize() / step(); stdout of this program
+    carries the ONE JSON line only, so file descriptor 1 points at stderr while the reference runs."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)  # the reference's buffered std::cout / printf output
+        except Exception:
+            pass
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
 def run_reference(args):
     """The reference's own OpenMP CPU path (oracle/_ref = unmodified admm_anderson_hard_zxu) on the
     host cores, on a bounded sample of the workload."""
@@ -113,23 +134,24 @@ def run_reference(args):
     kind = "reference" if refbind.have_ref() else "port"
     if kind == "port":
         cores = 1  # the C restatement is a scalar port
-    r = refbind.RefSolver("hard") if kind == "reference" else refbind.PortSolver("hard")
-    r.add_tetmesh(verts, tets, masses, WORKLOAD["youngs"], WORKLOAD["poisson"], 0)
-    dt = WORKLOAD["dt"]
-    r.set_pins(pidx, scene.stretch(dt))
-    t0 = time.perf_counter()
-    r.initialize(dt, s["iters"], -9.8, WORKLOAD["anderson_m"], True, WORKLOAD["penalty"])
-    setup_s = time.perf_counter() - t0
-    for _ in range(args.warmup):
-        r.set_pins(pidx, scene.stretch(dt))
-        r.step()
-    iters, secs = 0, 0.0
-    for _ in range(args.steps):
+    with _NativeStdoutToStderr():
+        r = refbind.RefSolver("hard") if kind == "reference" else refbind.PortSolver("hard")
+        r.add_tetmesh(verts, tets, masses, WORKLOAD["youngs"], WORKLOAD["poisson"], 0)
+        dt = WORKLOAD["dt"]
         r.set_pins(pidx, scene.stretch(dt))
         t0 = time.perf_counter()
-        h = r.step()
-        secs += time.perf_counter() - t0
-        iters += len(h)
+        r.initialize(dt, s["iters"], -9.8, WORKLOAD["anderson_m"], True, WORKLOAD["penalty"])
+        setup_s = time.perf_counter() - t0
+        for _ in range(args.warmup):
+            r.set_pins(pidx, scene.stretch(dt))
+            r.step()
+        iters, secs = 0, 0.0
+        for _ in range(args.steps):
+            r.set_pins(pidx, scene.stretch(dt))
+            t0 = time.perf_counter()
+            h = r.step()
+            secs += time.perf_counter() - t0
+            iters += len(h)
     sample_tets = len(tets)
     its = iters / secs
     value = its * sample_tets / FULL_TETS
@@ -287,7 +309,10 @@ def run_gpu(args):
             "kernel_launches": "ldlt_apply = k_fwd_front + k_bwd_front (one launch per sweep)" if dom == "ldlt_apply" else dom,
             "phases": {k: {"ms": round(v["ms"], 4), "algo_GB": round(v["bytes"] / 1e9, 4),
                            "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)} for k, v in phases.items()}}
-    cpu = cpu_baseline_leg() if (world == 1 and not args.no_cpu) else None
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        with _NativeStdoutToStderr():
+            cpu = cpu_baseline_leg()
     # time-to-tolerance of the last timed frame (BASELINE metric): device time until the logged combined
     # residual first falls below tau. tau = 1e-20 is the reference's own break threshold (hard/src/Solver.cpp:93,188),
     # the relative thresholds are fractions of the frame's first logged residual.
