@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 import aa_admm_b200 as A  # noqa: E402
 from oracle import refbind as R  # noqa: E402
-from scenes import beam_arrays, run_product, run_reference, run_cfg1  # noqa: E402
+from scenes import beam_arrays, run_product, run_reference, run_cfg1, run_cloth, run_plinko, run_flag_with_sphere  # noqa: E402
 
 out = []
 
@@ -54,6 +54,27 @@ for m, accel in ((5, True), (3, True), (1, False)):
     hr, xr = run_cfg1(lambda: R.RefSolver("xzu"), A, 1, m=m, accel=accel, ordering=None)
     table("cfg 1: xzu, three beams 12x3x3 (LINEAR / Neo-Hookean / StVK), %s" % ("Anderson m=%d" % m if accel else "no acceleration"),
           hg[0], hr[0], xg[0], xr[0], rej_r=3)
+# triangle (cloth), collision and wind terms inside Solver::step, hard_zxu ordering (first frame of each scene)
+for title, kw in (("cloth 8x8 cells (TriEnergyTerm), Anderson m=5", dict(n=8, m=5, accel=True)),
+                  ("cloth 8x8 cells, strain limits 0.95 / 1.05, no acceleration", dict(n=8, m=0, accel=False, limits=(0.95, 1.05))),
+                  ("cloth 40x40 cells, strain limits 0.9 / 1.1, Anderson m=5", dict(n=40, m=5, accel=True, limits=(0.9, 1.1), iters=40)),
+                  ("cloth 6x6 cells + tet beam 6x2x2 in one solver, Anderson m=5", dict(n=6, m=5, accel=True, limits=(0.9, 1.1), with_beam=(A, (6, 2, 2)))),
+                  ("windyflag material (E = 50, nu = 0.1, limits 0.95 / 1.05) + WindForce, 100 iterations, Anderson m=5",
+                   dict(n=10, m=5, accel=True, limits=(0.95, 1.05), youngs=50.0, poisson=0.1, wind=(25.0, 0.0, 5.0), pin_speed=0.0, iters=100))):
+    hg, xg = run_cloth(A.Solver, frames=1, **kw)
+    hr, xr = run_cloth(lambda: R.RefSolver("hard"), frames=1, **kw)
+    table("hard_zxu, " + title, hg[0], hr[0], xg[0], xr[0])
+for title, kw in (("free beam 8x2x2 on Floor / Sphere / Cylinder / PlaneAndHalfSphere / SlideFloor, Collision term on every vertex, Anderson m=5",
+                   dict(dims=(8, 2, 2), m=5, accel=True)),
+                  ("the same, no acceleration", dict(dims=(8, 2, 2), m=0, accel=False)),
+                  ("free beam 16x4x4 on the same obstacles, Anderson m=5", dict(dims=(16, 4, 4), m=5, accel=True, iters=30))):
+    hg, xg = run_plinko(A.Solver, A, frames=1, **kw)
+    hr, xr = run_plinko(lambda: R.RefSolver("hard"), A, frames=1, **kw)
+    table("hard_zxu, " + title, hg[0], hr[0], xg[0], xr[0])
+kw = dict(frames=1, n=12, m=5, accel=True, iters=60, youngs=1e7, poisson=0.399, limits=(0.95, 1.05), radius=0.34)
+hg, xg = run_flag_with_sphere(A.Solver, **kw)
+hr, xr = run_flag_with_sphere(lambda: R.RefSolver("hard"), **kw)
+table("hard_zxu, flag 12x12 cells + sphere obstacle: triangles, Collision terms, pins and wind in one solver, Anderson m=5", hg[0], hr[0], xg[0], xr[0])
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 open(os.path.join(ROOT, "gpurun_out", "parity_report.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out[:40]))
