@@ -160,8 +160,31 @@ __global__ void k_rhs_gather(int n_free, const int64_t *__restrict__ inc_ptr, co
     if (v >= n_free) return;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     const int64_t p1 = inc_ptr[v + 1];
-    for (int64_t p = inc_ptr[v]; p < p1; ++p) {
-        const int e = inc[p];  // contribution slot (tets: tet*4 + corner; triangles behind them)
+    int64_t p = inc_ptr[v];
+    // RHS_BATCH slots at a time: their indices, then all their values, are loaded before the first add (the adds keep
+    // the list order, so the sums are the same numbers as one slot at a time)
+    constexpr int RHS_BATCH = 8;
+    for (; p + RHS_BATCH <= p1; p += RHS_BATCH) {
+        int e[RHS_BATCH];
+#pragma unroll
+        for (int k = 0; k < RHS_BATCH; ++k) e[k] = inc[p + k];  // contribution slot (tets: tet*4 + corner; triangles behind them)
+        double q[RHS_BATCH][3];
+#pragma unroll
+        for (int k = 0; k < RHS_BATCH; ++k) {
+            const double *src = contrib + 3 * (size_t)e[k];
+            q[k][0] = src[0];
+            q[k][1] = src[1];
+            q[k][2] = src[2];
+        }
+#pragma unroll
+        for (int k = 0; k < RHS_BATCH; ++k) {
+            s0 += q[k][0];
+            s1 += q[k][1];
+            s2 += q[k][2];
+        }
+    }
+    for (; p < p1; ++p) {
+        const int e = inc[p];
         const double *q = contrib + 3 * (size_t)e;
         s0 += q[0];
         s1 += q[1];
