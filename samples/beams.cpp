@@ -4,7 +4,7 @@
 //
 //   g++ -std=c++17 -O2 -Iaa-admm_b200/host samples/beams.cpp -Laa-admm_b200 -laaadmm_host -laaadmm_b200 \
 //       -Wl,-rpath,$PWD/aa-admm_b200 -o beams
-//   ./beams -it 100 -a 1 -am 5 [-frames 3] [-dims 12 3 3] [-xzu]
+//   ./beams -it 100 -a 1 -am 5 [-frames 3] [-dims 12 3 3] [-xzu] [-save]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,6 +27,9 @@ int main(int argc, char **argv) {
         if (!strcmp(argv[i], "-dims") && i + 3 < argc)
             for (int k = 0; k < 3; ++k) dims[k] = atoi(argv[i + 1 + k]);
         if (!strcmp(argv[i], "-xzu")) settings.ordering = admm::Solver::Settings::XZU;
+        // -save: Solver::save() writes ./result/residual-<m|no>.txt after every step like the reference (the directory
+        // must exist, as for the reference)
+        if (!strcmp(argv[i], "-save")) settings.write_residual_file = true;
     }
 
     admm::Solver solver;

@@ -630,3 +630,29 @@ def test_plinko_cpp_sample_matches_python_path(gpu, tmp_path):
         assert abs(float(f[3]) - h[0, 1]) <= 1e-5 * h[0, 1] and abs(float(f[4]) - h[-1, 1]) <= 1e-5 * h[-1, 1]
     low = float(re.search(r"lowest y (\S+) ", r.stdout).group(1))
     assert low > lo - 0.2  # the floor holds the beam
+
+
+@pytest.mark.parametrize("xzu", [False, True])
+def test_residual_file_format_of_save(gpu, tmp_path, xzu):
+    """Solver::save() (hard/src/Solver.hpp:126-156, xzu/src/Solver.hpp:126-151): ./result/residual-<m>.txt with one row per
+    logged iteration, tab separated `cumulative_ms  prim  comb [is_reject]` (4 columns under hard_zxu, 3 under xzu),
+    16 significant digits - the file the reference's plotting scripts and oracle/refbind.py read."""
+    import re
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_host_cpu import _build_sample
+    exe = _build_sample(tmp_path, "beams")
+    os.makedirs(str(tmp_path / "result"), exist_ok=True)
+    cmd = [exe, "-it", "40", "-a", "1", "-am", "5", "-frames", "1", "-dims", "8", "2", "2", "-save"] + (["-xzu"] if xzu else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr + r.stdout
+    f = re.search(r"frame 0: (\d+) iterations, (\d+) rejected, combined residual (\S+) -> (\S+),", r.stdout)
+    rows = [line.rstrip("\n").split("\t") for line in open(str(tmp_path / "result" / "residual-5.txt"))]
+    assert len(rows) == int(f.group(1))
+    assert all(len(row) == (3 if xzu else 4) for row in rows)
+    vals = np.array([[float(v) for v in row] for row in rows])
+    assert np.all(np.diff(vals[:, 0]) >= 0) and vals[0, 0] > 0          # cumulative time
+    assert abs(vals[0, 2] - float(f.group(3))) <= 1e-6 * vals[0, 2] and abs(vals[-1, 2] - float(f.group(4))) <= 1e-6 * vals[-1, 2]
+    if not xzu:
+        assert set(np.unique(vals[:, 3])) <= {0.0, 1.0} and int(vals[:, 3].sum()) == int(f.group(2))
