@@ -170,7 +170,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -347,7 +347,7 @@ def run_gpu(args):
             "roofline": roof, "cpu_baseline": cpu, "time_to_tol": ttt,
             "e2e": {"value": e2e, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk.summary()}
-    print(json.dumps(line))
+    _emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -356,7 +356,23 @@ def run_gpu(args):
 NCU_LDLT_TRAFFIC_BYTES = 2.232e9
 
 
+_JSON_OUT = None
+
+
+def _emit(line):
+    """The ONE JSON line, on the real stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries the JSON line only: libraries print there as well (NCCL its version banner, the reference its progress
+    # lines), so file descriptor 1 points at stderr for the whole run and the line goes to a private copy of the real stdout
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
