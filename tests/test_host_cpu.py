@@ -416,3 +416,19 @@ def test_triangle_and_collision_error_paths(A):
     flat[tris[0]] = flat[tris[0][0]]
     with pytest.raises(A.AaadmmError):
         A.host_system_matrix(flat, np.zeros((0, 4), np.int32), tris, masses, pins, 1e-3, 1e5, 0.3)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the reference's own CPU path on a bounded sample): exactly one line on stdout, JSON,
+    with the keys the driver reads; everything the reference itself prints goes to stderr."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.split("\n") if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "admm_anderson_iterations_per_sec_1M_tets" and d["unit"] == "iterations/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["steps"] == 1 and d["warmup"] == 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
