@@ -136,6 +136,7 @@ def host_lib():
         H.aaadmm_host_solver_set_pins.argtypes = [vp, c_ip, c_dp, C.c_int]
         H.aaadmm_host_solver_initialize.argtypes = [vp, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
                                                     C.c_int, C.c_int]
+        H.aaadmm_host_solver_set_factor.argtypes = [vp, C.c_int, c_lp, c_ip, c_dp, c_dp, c_ip]
         H.aaadmm_host_solver_step.argtypes = [vp]
         H.aaadmm_host_solver_set_iters.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         H.aaadmm_host_solver_n_dof.argtypes = [vp]
@@ -467,6 +468,16 @@ class Solver:
         _hk(self.H.aaadmm_host_solver_initialize(self.h, dt, iters, gravity, anderson_m, int(bool(accel)), penalty,
                                                  ordering, nd_leaf))
 
+    def set_external_factor(self, n, Lp, Li, Lx, D, perm):
+        """Solver::set_external_factor: the next initialize() uses this (L, D, perm) instead of factoring itself;
+        n = free vertices (factor of Ahat) or 3 x that (factor of the full system, e.g. Eigen's own)."""
+        Lp = np.ascontiguousarray(Lp, np.int64)
+        Li = np.ascontiguousarray(Li, np.int32)
+        Lx = np.ascontiguousarray(Lx, np.float64)
+        D = np.ascontiguousarray(D, np.float64)
+        perm = np.ascontiguousarray(perm, np.int32)
+        _hk(self.H.aaadmm_host_solver_set_factor(self.h, int(n), _lp(Lp), _ip(Li), _dp(Lx), _dp(D), _ip(perm)))
+
     def set_iters(self, iters, anderson_m, accel):
         self.H.aaadmm_host_solver_set_iters(self.h, iters, anderson_m, int(bool(accel)))
 
@@ -508,6 +519,17 @@ class Solver:
         _ck(L.aaadmm_ldlt_stats(f, _dp(s)))
         return dict(n=int(s[0]), blocks=int(s[1]), levels=int(s[2]), max_block=int(s[3]), nnz_L=int(s[4]),
                     nnz_offblock=int(s[5]), dense_diag_entries=int(s[6]), bytes_per_solve=float(s[7]))
+
+    def solve(self, b):
+        """x = A^-1 b with the device factor of this solver (b: 3 per free vertex, the reference's dof order):
+        LDLTSolver::solve (LinearSolver.hpp:87-90) on an arbitrary right-hand side."""
+        L = cuda_lib()
+        f = C.c_void_p(self.H.aaadmm_host_solver_device_factor(self.h))
+        b = np.ascontiguousarray(b, np.float64)
+        assert b.size == 3 * self.info()["n_free"]
+        x = np.zeros_like(b)
+        _ck(L.aaadmm_ldlt_solve(f, _dp(b), _dp(x)))
+        return x
 
     # --- measurement helpers over the device scene of this solver ---
     def _scene(self):

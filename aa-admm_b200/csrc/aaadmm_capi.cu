@@ -190,6 +190,10 @@ struct aaadmm_tetscene {
     cudaGraphExec_t loop_exec = nullptr;
     int loop_key = -1;  // accel * 64 + m the graph was built for
     int body_launches = 0;
+    // where the last step left the tets' z and u (depends on ordering and acceleration): aaadmm_tetscene_read_zu
+    const double *last_z = nullptr, *last_u = nullptr;
+    double *zu_scratch = nullptr;
+    SolveState *st_h = nullptr;  // pinned host copy of the control block
 };
 
 extern "C" {
@@ -416,6 +420,8 @@ int aaadmm_tetscene_destroy(aaadmm_tetscene *s) {
     cudaFree(s->hist_rej);
     cudaFree(s->partials);
     cudaFree(s->st);
+    cudaFree(s->zu_scratch);
+    if (s->st_h) cudaFreeHost(s->st_h);
     if (s->pin_h) cudaFreeHost(s->pin_h);
     if (s->xbar_h) cudaFreeHost(s->xbar_h);
     if (s->xout_h) cudaFreeHost(s->xout_h);
@@ -443,8 +449,11 @@ int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *d,
         set_last_error("tetscene_create: triangle terms need tri, tri_rest_pose and tri_weight");
         return -1;
     }
-    if (factor->f->n != d->n_free || factor->f->nrhs != 3) {
-        set_last_error("tetscene_create: factor must be n_free x n_free with nrhs = 3");
+    // Ahat (x) I3 as a scalar n_free factor with 3 right-hand sides (this repo's setup), or a factor of the full
+    // 3 n_free system in the reference's degree-of-freedom order 3*vertex + axis with one right-hand side (what
+    // Eigen::SimplicialLDLT gives the reference, LinearSolver.hpp:79-84)
+    if (!((factor->f->n == d->n_free && factor->f->nrhs == 3) || (factor->f->n == 3 * d->n_free && factor->f->nrhs == 1))) {
+        set_last_error("tetscene_create: factor must be n_free x n_free with nrhs = 3, or 3 n_free x 3 n_free with nrhs = 1");
         return -1;
     }
     if (d->n_collisions > 0) {
@@ -478,6 +487,7 @@ int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *d,
         }
     }
     aaadmm_tetscene *s = new aaadmm_tetscene();
+    auto build = [&]() -> int {
     const int T = d->n_tets, V = d->n_verts, NF = d->n_free;
     s->T = T;
     s->V = V;
@@ -574,6 +584,13 @@ int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *d,
     AAADMM_CUDA_OK(cudaMallocHost((void **)&s->pin_h, sizeof(double) * 3 * std::max(1, s->NP)));
     AAADMM_CUDA_OK(cudaMallocHost((void **)&s->xbar_h, sizeof(double) * 3 * NF));
     AAADMM_CUDA_OK(cudaMallocHost((void **)&s->xout_h, sizeof(double) * 3 * NF));
+    AAADMM_CUDA_OK(cudaMallocHost((void **)&s->st_h, sizeof(SolveState)));
+    return 0;
+    };
+    if (build() != 0) {  // nothing of a partially built scene stays behind
+        aaadmm_tetscene_destroy(s);
+        return -1;
+    }
     *out = s;
     return 0;
     API_TRY_END
@@ -649,6 +666,17 @@ static int loop_graph_begin(aaadmm_tetscene *s, int key, cudaGraphConditionalHan
     s->loop_key = key;
     return 0;
 }
+// A launch failed while one loop turn was being captured: leave capture mode and forget the half-built graph, so that
+// the stream is usable and the next step() starts a fresh capture. Returns -1 (the caller's error code).
+static int loop_graph_abort(aaadmm_tetscene *s) {
+    cudaGraph_t dummy = nullptr;
+    cudaStreamEndCapture(s->stream, &dummy);  // the body graph is owned by the conditional node
+    cudaGetLastError();
+    if (s->loop_exec) cudaGraphExecDestroy(s->loop_exec), s->loop_exec = nullptr;
+    if (s->loop_graph) cudaGraphDestroy(s->loop_graph), s->loop_graph = nullptr;
+    s->loop_key = -1;
+    return -1;
+}
 static int loop_graph_end(aaadmm_tetscene *s, cudaGraphConditionalHandle cond_handle, int &L, int L_before) {
     cudaStream_t st = s->stream;
     k_loop_cond<<<1, 1, 0, st>>>(cond_handle, s->st);
@@ -656,6 +684,8 @@ static int loop_graph_end(aaadmm_tetscene *s, cudaGraphConditionalHandle cond_ha
     L = L_before;
     cudaError_t e = cudaStreamEndCapture(st, nullptr);
     if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (s->loop_graph) cudaGraphDestroy(s->loop_graph), s->loop_graph = nullptr;
         s->loop_key = -1;
         set_last_error(std::string("loop graph capture failed: ") + cudaGetErrorString(e));
         return -1;
@@ -739,7 +769,7 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
         }
         // warm start (hard/src/Solver.cpp:99-114)
         update_z(MODE_WARM);
-        launch_rhs_gather(st, NF, s->inc_ptr, s->inc, s->contrib, s->bconst, f->iperm, f->W, s->st);
+        launch_rhs_gather(st, NF, s->inc_ptr, s->inc, s->contrib, s->bconst, f->iperm, f->W, s->st, 0, f->nrhs == 1);
         if (ldlt_dev_apply_permuted(f, s->xs, st, &s->st->done)) return -1;
         update_u(MODE_WARM, Gu);
         AAADMM_CUDA_OK(cudaMemcpyAsync(Gx, s->xs, sizeof(double) * 3 * NF, cudaMemcpyDeviceToDevice, st));
@@ -771,10 +801,10 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
             L += 2;
         }
         prof->begin(1);
-        launch_rhs_gather(st, NF, s->inc_ptr, s->inc, s->contrib, s->bconst, f->iperm, f->W, s->st);
+        launch_rhs_gather(st, NF, s->inc_ptr, s->inc, s->contrib, s->bconst, f->iperm, f->W, s->st, 0, f->nrhs == 1);
         prof->end();
         prof->begin(2);
-        if (ldlt_dev_apply_permuted(f, s->xs, st, &s->st->done)) return -1;
+        if (ldlt_dev_apply_permuted(f, s->xs, st, &s->st->done)) return capturing ? loop_graph_abort(s) : -1;
         prof->end();
         L += 1 + f->n_launches;
         prof->begin(3);
@@ -783,10 +813,10 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
         ++L;
         if (accel) {
             prof->begin(4);
-            if (launch_aa_pass1(m, gs, st, Gu, s->xs, Gx, s->Ubuf, s->dF, s->dG, s->Ne, s->Nt, s->st, s->partials)) return -1;
+            if (launch_aa_pass1(m, gs, st, Gu, s->xs, Gx, s->Ubuf, s->dF, s->dG, s->Ne, s->Nt, s->st, s->partials)) return capturing ? loop_graph_abort(s) : -1;
             prof->end();
             prof->begin(5);
-            if (launch_aa_pass2(m, gs, st, Gu, Gx, s->Ubuf, s->dF, s->dG, s->Ne, s->Nt, s->st)) return -1;
+            if (launch_aa_pass2(m, gs, st, Gu, Gx, s->Ubuf, s->dF, s->dG, s->Ne, s->Nt, s->st)) return capturing ? loop_graph_abort(s) : -1;
             prof->end();
             L += 2;
         } else {
@@ -820,7 +850,7 @@ static int run_xzu(aaadmm_tetscene *s, const aaadmm_step_opts *o, int iters, boo
     int &L = s->launches;
     auto solve = [&](const double *zz, double *xout, int when) -> int {
         launch_contrib(gt, st, A, zz, u, s->contrib, s->st, when);
-        launch_rhs_gather(st, NF, s->inc_ptr, s->inc, s->contrib, s->bconst, f->iperm, f->W, s->st, when);
+        launch_rhs_gather(st, NF, s->inc_ptr, s->inc, s->contrib, s->bconst, f->iperm, f->W, s->st, when, f->nrhs == 1);
         if (ldlt_dev_apply_permuted(f, xout, st, when ? &s->st->skip_redo : &s->st->done)) return -1;
         L += 2 + f->n_launches;
         return 0;
@@ -861,21 +891,21 @@ static int run_xzu(aaadmm_tetscene *s, const aaadmm_step_opts *o, int iters, boo
         } else {
             launch_update_u_plain(gt, st, A, cx, Zcur, u, s->st, 0);                       // :135-141
         }
-        if (solve(Zcur, cx, 0)) return -1;                                                 // :147-149
+        if (solve(Zcur, cx, 0)) return capturing ? loop_graph_abort(s) : -1;                                                 // :147-149
         launch_prim_xzu(MODE_ITER, gt, st, A, cx, Zcur, s->st, s->partials);               // :153-159
         L += 2;
         if (accel) {
             launch_restore_xzu(gs, st, u, du, Zcur, Zdef, NZ, cx, dx, NX, s->st);          // :162-166
             launch_update_u_plain(gt, st, A, cx, Zcur, u, s->st, 1);                       // :168-172
-            if (solve(Zcur, cx, 1)) return -1;                                             // :174-176
+            if (solve(Zcur, cx, 1)) return capturing ? loop_graph_abort(s) : -1;                                             // :174-176
             launch_prim_xzu(MODE_REDO, gt, st, A, cx, Zcur, s->st, s->partials);           // :178-180
             // default_x = curr_x; default_u = curr_u; default_z = update_z(curr_x, curr_u)   :192-201
             launch_copy2_if_not_done(gs, st, dx, cx, NX, du, u, NZ, s->st);
             launch_update_z_plain(gt, st, A, cx, u, Zdef, s->st);
-            if (launch_aa_pass1(m, gs, st, Zdef, nullptr, nullptr, Zcur, s->dF, s->dG, NZ, NZ, s->st, s->partials)) return -1;
-            if (launch_aa_pass2(m, gs, st, Zdef, nullptr, Zcur, s->dF, s->dG, NZ, NZ, s->st)) return -1;
+            if (launch_aa_pass1(m, gs, st, Zdef, nullptr, nullptr, Zcur, s->dF, s->dG, NZ, NZ, s->st, s->partials)) return capturing ? loop_graph_abort(s) : -1;
+            if (launch_aa_pass2(m, gs, st, Zdef, nullptr, Zcur, s->dF, s->dG, NZ, NZ, s->st)) return capturing ? loop_graph_abort(s) : -1;
             // combined residual "for drawing figures": extra solve + local step on copies     :217-233
-            if (solve(Zdef, combx, 0)) return -1;
+            if (solve(Zdef, combx, 0)) return capturing ? loop_graph_abort(s) : -1;
             launch_update_z_plain(gt, st, A, combx, u, combz, s->st);
             launch_comb_xzu(gt, st, A, combx, combz, Zdef, s->st, s->partials, s->hist_prim, s->hist_comb, s->hist_rej);
             L += 10;
@@ -935,16 +965,20 @@ static int step_common(aaadmm_tetscene *s, const aaadmm_step_opts *o, bool host_
     static const bool no_graph = getenv("AAADMM_NO_GRAPH") != nullptr;
     if (xzu ? run_xzu(s, o, o->admm_iters, !no_graph) : run_hard(s, o, nullptr, o->admm_iters, true, !no_graph)) return -1;
     AAADMM_CUDA_OK(cudaEventRecord(s->ev[2], st));
-    SolveState hs;
+    // which buffers hold the tets' u and z now (hard: default_u = Gbuf when accelerated, Ubuf otherwise; xzu: curr_u
+    // lives in s->z and curr_z in Ubuf)
+    s->last_u = xzu ? s->z : (accel ? s->Gbuf : s->Ubuf);
+    s->last_z = xzu ? s->Ubuf : s->z;
     if (host_io) {
         // hard: default_x when ANDERSON, curr_x otherwise (hard/src/Solver.cpp:216-223)
         // xzu: curr_x (xzu/src/Solver.cpp:255)
         const double *xfinal = xzu ? s->xs : (accel ? (s->Gbuf + s->Ne) : s->xs);
         AAADMM_CUDA_OK(cudaMemcpyAsync(s->xout_h, xfinal, sizeof(double) * 3 * NF, cudaMemcpyDeviceToHost, st));
     }
-    AAADMM_CUDA_OK(cudaMemcpyAsync(&hs, s->st, sizeof(SolveState), cudaMemcpyDeviceToHost, st));
+    AAADMM_CUDA_OK(cudaMemcpyAsync(s->st_h, s->st, sizeof(SolveState), cudaMemcpyDeviceToHost, st));
     AAADMM_CUDA_OK(cudaEventRecord(s->ev[3], st));
     AAADMM_CUDA_OK(cudaStreamSynchronize(st));
+    const SolveState hs = *s->st_h;
     if (host_io) {
         memcpy(x_out, s->xout_h, sizeof(double) * 3 * NF);
         const int rows = hs.iter;
@@ -980,22 +1014,30 @@ int aaadmm_tetscene_step_resident(aaadmm_tetscene *s, const aaadmm_step_opts *o,
 }
 
 int aaadmm_tetscene_read_zu(aaadmm_tetscene *s, double *z, double *u) {
+    API_TRY_BEGIN
+    if (!s) {
+        set_last_error("tetscene_read_zu: null scene");
+        return -1;
+    }
     if (s->T <= 0) return 0;  // tet terms only (reference layout of the tets' z / u)
-    double *tmp = nullptr;
-    AAADMM_CUDA_OK(cudaMalloc((void **)&tmp, sizeof(double) * 9 * s->T));
+    if (!s->last_z || !s->last_u) {
+        set_last_error("tetscene_read_zu: call aaadmm_tetscene_step first");
+        return -1;
+    }
+    if (!s->zu_scratch) AAADMM_CUDA_OK(cudaMalloc((void **)&s->zu_scratch, sizeof(double) * 9 * s->T));
     const int g = (s->T + 255) / 256;
     if (z) {
-        k_soa_to_aos9<<<g, 256, 0, s->stream>>>(s->z, tmp, s->T);
-        AAADMM_CUDA_OK(cudaMemcpyAsync(z, tmp, sizeof(double) * 9 * s->T, cudaMemcpyDeviceToHost, s->stream));
+        k_soa_to_aos9<<<g, 256, 0, s->stream>>>(s->last_z, s->zu_scratch, s->T);
+        AAADMM_CUDA_OK(cudaMemcpyAsync(z, s->zu_scratch, sizeof(double) * 9 * s->T, cudaMemcpyDeviceToHost, s->stream));
         AAADMM_CUDA_OK(cudaStreamSynchronize(s->stream));
     }
     if (u) {
-        k_soa_to_aos9<<<g, 256, 0, s->stream>>>(s->Gbuf, tmp, s->T);
-        AAADMM_CUDA_OK(cudaMemcpyAsync(u, tmp, sizeof(double) * 9 * s->T, cudaMemcpyDeviceToHost, s->stream));
+        k_soa_to_aos9<<<g, 256, 0, s->stream>>>(s->last_u, s->zu_scratch, s->T);
+        AAADMM_CUDA_OK(cudaMemcpyAsync(u, s->zu_scratch, sizeof(double) * 9 * s->T, cudaMemcpyDeviceToHost, s->stream));
         AAADMM_CUDA_OK(cudaStreamSynchronize(s->stream));
     }
-    cudaFree(tmp);
     return 0;
+    API_TRY_END
 }
 
 int aaadmm_tetscene_profile(aaadmm_tetscene *s, const aaadmm_step_opts *o, int iters, float *ms) {
@@ -1333,6 +1375,8 @@ struct aaadmm_geo {
     double *Ubuf = nullptr, *Nbuf = nullptr, *Dbuf = nullptr, *z = nullptr, *prev_dx = nullptr, *cp = nullptr;
     double *dF = nullptr, *dG = nullptr, *hist = nullptr, *partials = nullptr;
     int m_cap = 0, hist_cap = 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    SolveState *st_h = nullptr;  // pinned host copy of the control block
     SolveState *st = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
@@ -1344,6 +1388,9 @@ extern "C" {
 
 int aaadmm_geo_destroy(aaadmm_geo *g) {
     if (!g) return 0;
+    for (auto &e : g->ev)
+        if (e) cudaEventDestroy(e);
+    if (g->st_h) cudaFreeHost(g->st_h);
     cudaFree(g->type);
     cudaFree(g->idx_ptr);
     cudaFree(g->idx);
@@ -1413,6 +1460,8 @@ int aaadmm_geo_create(aaadmm_geo **out, const aaadmm_geo_desc *d, aaadmm_ldlt *f
     g->zc_all = zc + (g->variant == AAADMM_GEO_GS ? d->n_soft : 0);
     g->N = 3 * (int64_t)g->zc_all + 3 * (int64_t)g->P;
     AAADMM_CUDA_OK(cudaStreamCreate(&g->stream));
+    for (auto &e : g->ev) AAADMM_CUDA_OK(cudaEventCreate(&e));
+    AAADMM_CUDA_OK(cudaMallocHost((void **)&g->st_h, sizeof(SolveState)));
     int rc = 0;
     rc |= up(&g->type, d->type, d->n_hard);
     rc |= up(&g->idx_ptr, d->idx_ptr, d->n_hard + 1);
@@ -1579,9 +1628,7 @@ int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int ande
         g->graph_key = -1;
     }
     const int64_t NU = 3 * (int64_t)g->zc_all;
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
+    cudaEvent_t e0 = g->ev[0], e1 = g->ev[1];
     // init_variables (ALMGeometrySolver.h:404-409) + aa->init(current_u, current_x)
     AAADMM_CUDA_OK(cudaMemsetAsync(g->Ubuf, 0, sizeof(double) * g->N, st));
     AAADMM_CUDA_OK(cudaMemsetAsync(g->Dbuf, 0, sizeof(double) * g->N, st));
@@ -1591,7 +1638,7 @@ int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int ande
     k_geo_init_state<<<1, 1, 0, st>>>(g->st, m, max_iter);
     int launches = 0;
     static const bool no_graph = getenv("AAADMM_NO_GRAPH") != nullptr;
-    SolveState hs;
+    SolveState &hs = *g->st_h;
     if (max_iter > 0 && !no_graph) {
         // the loop graph is built (once per window size) before the timed region starts
         const int key = m;
@@ -1615,6 +1662,9 @@ int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int ande
             k_geo_loop_cond<<<1, 1, 0, st>>>(h, g->st);
             cudaError_t e = cudaStreamEndCapture(st, nullptr);
             if (rc || e != cudaSuccess) {
+                cudaGetLastError();
+                cudaGraphDestroy(g->graph), g->graph = nullptr;
+                g->graph_key = -1;
                 set_last_error(std::string("geo loop graph capture failed: ") + cudaGetErrorString(e));
                 return -1;
             }
@@ -1650,8 +1700,6 @@ int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int ande
         res->step_ms = res->loop_ms;
         res->kernel_launches = launches + hs.loop_it * g->body_launches;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return 0;
     API_TRY_END
 }

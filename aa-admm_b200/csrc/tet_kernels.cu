@@ -154,7 +154,8 @@ __global__ void k_restore_if_reject(double *__restrict__ ucur, const double *__r
 // b = M x_bar + rho dt^2 D^T (W z + C_fix - u), written in the factor's elimination order.
 __global__ void k_rhs_gather(int n_free, const int64_t *__restrict__ inc_ptr, const int *__restrict__ inc,
                              const double *__restrict__ contrib, const double *__restrict__ bconst,
-                             const int *__restrict__ iperm, double *__restrict__ W, const SolveState *st, int when) {
+                             const int *__restrict__ iperm, double *__restrict__ W, const SolveState *st, int when,
+                             int dof_factor) {
     if (st->done || (when == 1 && !st->reject)) return;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_free) return;
@@ -189,6 +190,14 @@ __global__ void k_rhs_gather(int n_free, const int64_t *__restrict__ inc_ptr, co
         s0 += q[0];
         s1 += q[1];
         s2 += q[2];
+    }
+    if (dof_factor) {
+        // factor of the full 3 n_free x 3 n_free system (e.g. Eigen's own, LinearSolver.hpp:79-84): one permutation
+        // entry per degree of freedom
+        W[iperm[3 * (size_t)v + 0]] = bconst[3 * (size_t)v + 0] + s0;
+        W[iperm[3 * (size_t)v + 1]] = bconst[3 * (size_t)v + 1] + s1;
+        W[iperm[3 * (size_t)v + 2]] = bconst[3 * (size_t)v + 2] + s2;
+        return;
     }
     const size_t o = (size_t)iperm[v] * 3;
     W[o + 0] = bconst[3 * (size_t)v + 0] + s0;
@@ -629,8 +638,8 @@ void launch_restore_if_reject(int grid, cudaStream_t s, double *ucur, const doub
     k_restore_if_reject<<<grid, 256, 0, s>>>(ucur, gdef, n, st);
 }
 void launch_rhs_gather(cudaStream_t s, int n_free, const int64_t *inc_ptr, const int *inc, const double *contrib,
-                       const double *bconst, const int *iperm, double *W, const SolveState *st, int when) {
-    k_rhs_gather<<<(n_free + 127) / 128, 128, 0, s>>>(n_free, inc_ptr, inc, contrib, bconst, iperm, W, st, when);
+                       const double *bconst, const int *iperm, double *W, const SolveState *st, int when, int dof_factor) {
+    k_rhs_gather<<<(n_free + 127) / 128, 128, 0, s>>>(n_free, inc_ptr, inc, contrib, bconst, iperm, W, st, when, dof_factor);
 }
 void launch_bconst(cudaStream_t s, const TetArrays &A, const int64_t *inc_ptr, const int *inc, const double *pos,
                    const double *mass, const double *xbar, double *bconst) {

@@ -70,7 +70,8 @@ void launch_tri_bconst(cudaStream_t s, const TriArrays &A, int slot0, const int6
                        const double *pos, double *bconst);
 void launch_restore_if_reject(int grid, cudaStream_t s, double *ucur, const double *gdef, int64_t n, SolveState *st);
 void launch_rhs_gather(cudaStream_t s, int n_free, const int64_t *inc_ptr, const int *inc, const double *contrib,
-                       const double *bconst, const int *iperm, double *W, const SolveState *st, int when = 0);
+                       const double *bconst, const int *iperm, double *W, const SolveState *st, int when = 0,
+                       int dof_factor = 0);
 void launch_bconst(cudaStream_t s, const TetArrays &A, const int64_t *inc_ptr, const int *inc, const double *pos,
                    const double *mass, const double *xbar, double *bconst);
 void launch_copy_if_not_done(cudaStream_t s, double *dst, const double *src, int64_t n, const SolveState *st);

@@ -134,6 +134,21 @@ void Solver::add_obstacle(std::shared_ptr<PassiveCollision> obj) {
     m_obstacles.push_back(obj);
 }
 
+void Solver::set_external_factor(int n, const int64_t *Lp, const int *Li, const double *Lx, const double *D,
+                                 const int *perm) {
+    if (n <= 0 || !Lp || !D || !perm || (Lp[n] > 0 && (!Li || !Lx)))
+        throw std::runtime_error("Solver::set_external_factor: bad input");
+    m_factor = aaadmm::LdltFactor();
+    m_factor.n = n;
+    m_factor.Lp.assign(Lp, Lp + n + 1);
+    m_factor.Li.assign(Li, Li + Lp[n]);
+    m_factor.Lx.assign(Lx, Lx + Lp[n]);
+    m_factor.D.assign(D, D + n);
+    m_factor.perm.assign(perm, perm + n);
+    m_factor.ok = true;
+    factor_external = true;
+}
+
 // hard/src/Solver.cpp:361-491 / xzu/src/Solver.cpp:373-498
 bool Solver::initialize(const Settings &settings_) {
     m_settings = settings_;
@@ -227,8 +242,13 @@ bool Solver::initialize(const Settings &settings_) {
     const char *cache_env = getenv("AAADMM_FACTOR_CACHE");
     const std::string cache = !m_settings.factor_cache.empty() ? m_settings.factor_cache : std::string(cache_env ? cache_env : "");
     const uint64_t key = cache.empty() ? 0 : aaadmm::matrix_key(m_sys.Ahat);
-    factor_from_cache = !cache.empty() && aaadmm::ldlt_load(cache, key, m_factor);
-    if (!factor_from_cache) {
+    if (factor_external) {
+        if (m_factor.n != m_sys.n_free && m_factor.n != 3 * m_sys.n_free)
+            throw std::runtime_error("Solver::initialize: the external factor has neither n_free nor 3 n_free columns");
+        factor_from_cache = false;
+    } else
+        factor_from_cache = !cache.empty() && aaadmm::ldlt_load(cache, key, m_factor);
+    if (!factor_external && !factor_from_cache) {
         std::vector<int> perm = aaadmm::nested_dissection(m_sys.Ahat, coords.data(), leaf_env ? atoi(leaf_env) : m_settings.nd_leaf_size);
         m_factor = aaadmm::ldlt_factorize(m_sys.Ahat, perm);
         if (m_factor.ok && !cache.empty() && !aaadmm::ldlt_save(m_factor, key, cache))
@@ -241,7 +261,7 @@ bool Solver::initialize(const Settings &settings_) {
     if (m_scene) aaadmm_tetscene_destroy(m_scene), m_scene = nullptr;
     if (m_ldlt) aaadmm_ldlt_destroy(m_ldlt), m_ldlt = nullptr;
     if (aaadmm_ldlt_create(&m_ldlt, m_factor.n, m_factor.Lp.data(), m_factor.Li.data(), m_factor.Lx.data(),
-                           m_factor.D.data(), m_factor.perm.data(), 3) != 0)
+                           m_factor.D.data(), m_factor.perm.data(), m_factor.n == m_sys.n_free ? 3 : 1) != 0)
         throw std::runtime_error(std::string("aaadmm_ldlt_create: ") + aaadmm_last_error());
     aaadmm_tetscene_desc d = {};
     d.n_tris = m_sys.n_tris;

@@ -257,6 +257,12 @@ public:
     void set_collisions(const std::vector<int> &inds, const std::vector<Vec3> &points = std::vector<Vec3>());
     void add_obstacle(std::shared_ptr<PassiveCollision> obj);
     bool initialize(const Settings &settings_ = Settings());
+    // Use a factor computed elsewhere instead of this library's nested-dissection LDL^T at the next initialize():
+    // P A P^T = L D L^T with L strictly lower CSC (unit diagonal implied, rows ascending), perm[new] = old.
+    // n = number of free vertices (factor of Ahat, A = Ahat (x) I3) or 3 x that (factor of the full system in the
+    // reference's degree-of-freedom order, e.g. Eigen::SimplicialLDLT of solver_termA exactly as
+    // LinearSolver.hpp:79-84 computes it). The arrays are copied.
+    void set_external_factor(int n, const int64_t *Lp, const int *Li, const double *Lx, const double *D, const int *perm);
     void step();
     const RuntimeData &runtime_data() { return m_runtime; }
     const Settings &settings() { return m_settings; }
@@ -285,6 +291,7 @@ protected:
     std::vector<std::shared_ptr<PassiveCollision>> m_obstacles;
     std::vector<double> m_x_pin;  // in the order set_pins received them (reference: m_x_pin)
     std::vector<int> positive_pin;
+    bool factor_external = false;      // m_factor was handed in through set_external_factor
     bool factor_from_cache = false;    // the last initialize() took the factor from Settings::factor_cache
     std::vector<int> slot_of_node;  // index among the free nodes (positive_pin) or among the pinned ones
     aaadmm::TetSystem m_sys;

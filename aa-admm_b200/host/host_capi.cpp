@@ -392,6 +392,13 @@ int aaadmm_host_solver_initialize(void *h, double dt, int iters, double gravity,
     return sh->solver.initialize(st) ? 0 : -2;
     HOST_CATCH
 }
+int aaadmm_host_solver_set_factor(void *h, int n, const int64_t *Lp, const int *Li, const double *Lx, const double *D,
+                                  const int *perm) {
+    HOST_TRY
+    static_cast<SolverHandle *>(h)->solver.set_external_factor(n, Lp, Li, Lx, D, perm);
+    return 0;
+    HOST_CATCH
+}
 int aaadmm_host_solver_step(void *h) {
     HOST_TRY
     static_cast<SolverHandle *>(h)->solver.step();

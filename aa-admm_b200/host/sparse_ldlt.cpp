@@ -664,6 +664,12 @@ bool ldlt_load(const std::string &path, uint64_t key, LdltFactor &F) {
     bool ok = fread(magic, 1, 8, fp) == 8 && memcmp(magic, "AAFACT01", 8) == 0 && fread(&k, 8, 1, fp) == 1 && k == key &&
               fread(&n, 4, 1, fp) == 1 && fread(&nnz, 8, 1, fp) == 1 && n >= 0 && nnz >= 0;
     if (ok) {
+        // the header must account for the file's size exactly before anything is allocated from it
+        const int64_t expect = 8 + 8 + 4 + 8 + 4 * (int64_t)n + 8 * ((int64_t)n + 1) + 4 * nnz + 8 * nnz + 8 * (int64_t)n;
+        const long here = ftell(fp);
+        ok = fseek(fp, 0, SEEK_END) == 0 && (int64_t)ftell(fp) == expect && fseek(fp, here, SEEK_SET) == 0;
+    }
+    if (ok) {
         LdltFactor G;
         G.n = n;
         G.perm.resize(n);
@@ -673,7 +679,24 @@ bool ldlt_load(const std::string &path, uint64_t key, LdltFactor &F) {
         G.D.resize(n);
         ok = fread(G.perm.data(), 4, (size_t)n, fp) == (size_t)n && fread(G.Lp.data(), 8, (size_t)n + 1, fp) == (size_t)n + 1 &&
              fread(G.Li.data(), 4, (size_t)nnz, fp) == (size_t)nnz && fread(G.Lx.data(), 8, (size_t)nnz, fp) == (size_t)nnz &&
-             fread(G.D.data(), 8, (size_t)n, fp) == (size_t)n && G.Lp[n] == nnz;
+             fread(G.D.data(), 8, (size_t)n, fp) == (size_t)n && G.Lp[n] == nnz && G.Lp[0] == 0;
+        // structure checks: a damaged or foreign file is a cache miss, never an out-of-bounds index later on
+        if (ok) {
+            std::vector<char> seen((size_t)n, 0);
+            for (int i = 0; ok && i < n; ++i) {
+                const int p = G.perm[i];
+                ok = p >= 0 && p < n && !seen[p];
+                if (ok) seen[p] = 1;
+            }
+        }
+        for (int j = 0; ok && j < n; ++j) {
+            ok = G.Lp[j] <= G.Lp[j + 1] && std::isfinite(G.D[j]) && G.D[j] != 0.0;
+            int prev = j;  // strictly lower triangle, rows ascending
+            for (int64_t q = G.Lp[j]; ok && q < G.Lp[j + 1]; ++q) {
+                ok = G.Li[q] > prev && G.Li[q] < n;
+                prev = G.Li[q];
+            }
+        }
         if (ok) {
             G.ok = true;
             F = std::move(G);

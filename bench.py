@@ -32,7 +32,9 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(cx=148, cy=37, cz=37, anderson_m=5, admm_iters=100, dt=1.0 / 30.0, penalty=1.0,
                 youngs=1e7, poisson=0.399)
-CPU_SAMPLE = dict(cx=12, cy=37, cz=37, iters=10)
+CPU_SAMPLE = dict(cx=12, cy=37, cz=37, iters=10)   # cpu_baseline leg beside the GPU line: about 20 s in all
+# --impl reference: the largest beam of cfg 4's cross-section whose Eigen setup fits "a few minutes" for the whole run
+REF_ARM = dict(cx=24, cy=37, cz=37, iters=10)
 FULL_TETS = 148 * 37 * 37 * 5
 
 
@@ -118,30 +120,51 @@ class _NativeStdoutToStderr:
         return False
 
 
+def _reference_host_threads():
+    """All host cores for the reference's OpenMP loops. torchrun exports OMP_NUM_THREADS=1 to its ranks; under torchrun
+    rank 0 alone runs the CPU arm (the other ranks exit at once), so it takes the whole box. Must run before the first
+    OpenMP library is loaded."""
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    return cores
+
+
+def _reference_solver(dims, iters, cores):
+    """The unmodified reference (oracle/_ref) - or, where it could not be compiled, the C restatement - set up on a beam
+    of `dims` cubes with the workload's material, time step, penalty and Anderson window. The scene comes from
+    oracle/ref_scene.py (numpy): none of this repo's product libraries is loaded on this path."""
+    from oracle import refbind
+    from oracle.ref_scene import RefBeamScene
+    kind = "reference" if refbind.have_ref() else "port"
+    scene = RefBeamScene().add(dims[0], dims[1], dims[2], 0.0)
+    verts, tets, masses, pidx, ppts, pside = scene.arrays()
+    r = refbind.RefSolver("hard") if kind == "reference" else refbind.PortSolver("hard")
+    if kind == "reference":
+        r._f("set_threads")(cores)
+    r.add_tetmesh(verts, tets, masses, WORKLOAD["youngs"], WORKLOAD["poisson"], 0)
+    dt = WORKLOAD["dt"]
+    r.set_pins(pidx, scene.stretch(dt))
+    t0 = time.perf_counter()
+    r.initialize(dt, iters, -9.8, WORKLOAD["anderson_m"], True, WORKLOAD["penalty"])
+    return r, scene, pidx, len(tets), kind, time.perf_counter() - t0
+
+
 def run_reference(args):
-    """The reference's own OpenMP CPU path (oracle/_ref = unmodified admm_anderson_hard_zxu) on the
-    host cores, on a bounded sample of the workload."""
+    """The reference's own OpenMP CPU path (oracle/_ref = unmodified admm_anderson_hard_zxu) on the host cores.
+    `value` is MEASURED: iterations/s of Solver::step on the largest beam of the workload's cross-section whose Eigen
+    AMD + simplicial LDL^T setup fits the run's budget (REF_ARM); nothing is extrapolated into it."""
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
-    from oracle import refbind
-    import aa_admm_b200 as A
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    s = CPU_SAMPLE
-    scene = A.BeamScene().add(s["cx"], s["cy"], s["cz"], 0.0)
-    verts, tets, masses, pidx, ppts, pside = scene.arrays()
-    kind = "reference" if refbind.have_ref() else "port"
-    if kind == "port":
-        cores = 1  # the C restatement is a scalar port
+    cores = _reference_host_threads()
+    s = dict(REF_ARM)
+    if args.ref_dims:
+        s.update(cx=args.ref_dims[0], cy=args.ref_dims[1], cz=args.ref_dims[2])
+    dt = WORKLOAD["dt"]
     with _NativeStdoutToStderr():
-        r = refbind.RefSolver("hard") if kind == "reference" else refbind.PortSolver("hard")
-        r.add_tetmesh(verts, tets, masses, WORKLOAD["youngs"], WORKLOAD["poisson"], 0)
-        dt = WORKLOAD["dt"]
-        r.set_pins(pidx, scene.stretch(dt))
-        t0 = time.perf_counter()
-        r.initialize(dt, s["iters"], -9.8, WORKLOAD["anderson_m"], True, WORKLOAD["penalty"])
-        setup_s = time.perf_counter() - t0
+        r, scene, pidx, sample_tets, kind, setup_s = _reference_solver((s["cx"], s["cy"], s["cz"]), s["iters"], cores)
+        if kind == "port":
+            cores = 1  # the C restatement is a scalar port
         for _ in range(args.warmup):
             r.set_pins(pidx, scene.stretch(dt))
             r.step()
@@ -152,46 +175,54 @@ def run_reference(args):
             h = r.step()
             secs += time.perf_counter() - t0
             iters += len(h)
-    sample_tets = len(tets)
     its = iters / secs
-    value = its * sample_tets / FULL_TETS
-    sample = (("unmodified reference admm_anderson_hard_zxu Solver::step, g++ -O2 -fopenmp" if kind == "reference"
-               else "oracle/port C restatement of hard_zxu Solver::step (oracle/_ref absent), gcc -O2, 1 thread") +
-              ", beam %dx%dx%d = %d tets "
-              "(same cross-section), %d ADMM iterations/frame, m=5; measured %.2f it/s at %d tets, scaled linearly "
-              "by tets to %d tets (favours the CPU: its triangular solve grows superlinearly); Eigen AMD+LDLT setup "
-              "%.1f s excluded") % (s["cx"], s["cy"], s["cz"], sample_tets, s["iters"], its, sample_tets, FULL_TETS, setup_s)
-    line = {"impl": "reference", "metric": "admm_anderson_iterations_per_sec_1M_tets", "value": value,
+    sample = (("unmodified reference admm_anderson_hard_zxu Solver::step, g++ -O2 -fopenmp, %d OpenMP threads" % cores
+               if kind == "reference" else "oracle/port C restatement of hard_zxu Solver::step (oracle/_ref absent), gcc -O2, 1 thread") +
+              "; beam %dx%dx%d = %d tets (cross-section of cfg 4, %.0f %% of its length), m=5, every step = one frame "
+              "of %d ADMM iterations (cfg 4: 100); value = measured iterations/s AT THIS SIZE; Eigen AMD + LDL^T setup "
+              "%.1f s excluded (at the full 1,013,060 tets that setup alone needs about an hour)") % (
+                  s["cx"], s["cy"], s["cz"], sample_tets, 100.0 * s["cx"] / WORKLOAD["cx"], s["iters"], setup_s)
+    line = {"impl": "reference", "metric": "admm_anderson_iterations_per_sec_1M_tets", "value": its,
             "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg4: hard_zxu, linear beam 148x37x37 (1,013,060 tets), m=5, 100 it/frame "
-                                   "(CPU arm: bounded sample, see cpu_baseline.sample)"},
-            "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": kind, "sample": sample},
-            "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "config": {"workload": "hard_zxu, linear beam %dx%dx%d (%d tets: bounded sample of cfg 4 = 148x37x37, "
+                                   "1,013,060 tets), m=5, %d it/frame" % (s["cx"], s["cy"], s["cz"], sample_tets, s["iters"]),
+                       "sample_tets": sample_tets, "full_tets": FULL_TETS, "same_config_as_gpu_arm": False,
+                       "setup_s": round(setup_s, 1)},
+            # the same figure scaled linearly by tets to cfg 4's size (favours the CPU: its triangular solves grow
+            # faster than linearly); an extra key, not the value
+            "value_scaled_to_full_tets": its * sample_tets / FULL_TETS,
+            "cpu_baseline": {"value": its, "unit": "iterations/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": its, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "native_so_loaded": _repo_libraries_loaded()}
     _emit(line)
     return 0
 
 
-def cpu_baseline_leg():
-    """Bounded CPU sample run beside the GPU number (rank 0, N=1)."""
+def _repo_libraries_loaded():
+    """Shared objects of this repository mapped into the process (the CPU arm must show oracle/ only)."""
+    libs = set()
     try:
-        from oracle import refbind
-        import aa_admm_b200 as A
-        kind = "reference" if refbind.have_ref() else "port"
-        cores = (os.cpu_count() or 1) if kind == "reference" else 1
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        with open("/proc/self/maps") as f:
+            for ln in f:
+                path = ln.split()[-1] if ln.strip() else ""
+                if path.startswith(ROOT) and ".so" in os.path.basename(path):
+                    libs.add(os.path.relpath(path, ROOT))
+    except OSError:
+        pass
+    return sorted(libs)
+
+
+def cpu_baseline_leg():
+    """Bounded CPU sample run beside the GPU number (rank 0, N=1): about 20 s of the unmodified reference."""
+    try:
+        cores = _reference_host_threads()
         s = CPU_SAMPLE
-        scene = A.BeamScene().add(s["cx"], s["cy"], s["cz"], 0.0)
-        verts, tets, masses, pidx, ppts, pside = scene.arrays()
-        r = refbind.RefSolver("hard") if kind == "reference" else refbind.PortSolver("hard")
-        r.add_tetmesh(verts, tets, masses, WORKLOAD["youngs"], WORKLOAD["poisson"], 0)
         dt = WORKLOAD["dt"]
-        r.set_pins(pidx, scene.stretch(dt))
-        t0 = time.perf_counter()
-        r.initialize(dt, s["iters"], -9.8, WORKLOAD["anderson_m"], True, WORKLOAD["penalty"])
-        setup_s = time.perf_counter() - t0
+        r, scene, pidx, sample_tets, kind, setup_s = _reference_solver((s["cx"], s["cy"], s["cz"]), s["iters"], cores)
+        if kind == "port":
+            cores = 1
         iters, secs = 0, 0.0
         for f in range(3):
             r.set_pins(pidx, scene.stretch(dt))
@@ -201,13 +232,14 @@ def cpu_baseline_leg():
                 secs += time.perf_counter() - t0
                 iters += len(h)
         its = iters / secs
-        value = its * len(tets) / FULL_TETS
-        return {"value": value, "unit": "iterations/s", "cores": cores, "kind": kind,
+        return {"value": its * sample_tets / FULL_TETS, "unit": "iterations/s", "cores": cores, "kind": kind,
+                "measured": {"iterations_per_s": its, "tets": sample_tets},
                 "sample": ("unmodified reference" if kind == "reference" else "oracle/port C restatement of the reference") +
-                          " hard_zxu Solver::step on beam %dx%dx%d (%d tets), 2 frames x %d "
-                          "iterations after 1 warm-up frame: %.2f it/s, scaled linearly by tets to 1,013,060 "
-                          "(favours the CPU); Eigen setup %.1f s excluded" % (s["cx"], s["cy"], s["cz"], len(tets),
-                                                                              s["iters"], its, setup_s)}
+                          " hard_zxu Solver::step on beam %dx%dx%d (%d tets), 2 frames x %d iterations after 1 warm-up "
+                          "frame: measured %.2f it/s at that size; `value` = that figure scaled linearly by tets to "
+                          "1,013,060 (the metric's size; favours the CPU); Eigen setup %.1f s excluded. The measured "
+                          "same-run reference arm at a larger size is `bench.py --impl reference`" % (
+                              s["cx"], s["cy"], s["cz"], sample_tets, s["iters"], its, setup_s)}
     except Exception as e:  # the baseline is a report, never a reason to lose the GPU line
         return {"value": None, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "reference",
                 "sample": "failed: %r" % (e,)}
@@ -380,6 +412,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--small", action="store_true", help="30,720-tet beam (debugging only; not a bench number)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-dims", type=int, nargs=3, default=None,
+                    help="--impl reference: beam size of the CPU arm (default REF_ARM; smaller sizes are for the CPU test)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

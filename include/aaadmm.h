@@ -139,7 +139,9 @@ typedef struct {
     int kernel_launches;
 } aaadmm_step_result;
 
-/* `factor` is borrowed (must outlive the scene) and must have nrhs == 3 and n == n_free. */
+/* `factor` is borrowed (must outlive the scene). Either n == n_free with nrhs == 3 (A = Ahat (x) I3, one scalar factor
+ * for the three axes) or n == 3*n_free with nrhs == 1: a factor of the full system in the reference's degree-of-freedom
+ * order 3*vertex + axis, e.g. Eigen::SimplicialLDLT's own matrixL / vectorD / permutationP (LinearSolver.hpp:79-84). */
 int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *desc, aaadmm_ldlt *factor);
 int aaadmm_tetscene_destroy(aaadmm_tetscene *s);
 /* One time step of the ADMM loop.

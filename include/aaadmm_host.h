@@ -80,6 +80,10 @@ int aaadmm_host_wind_project(const int *tris, int n_tris, const double *dir3, do
 int aaadmm_host_solver_set_pins(void *h, const int *idx, const double *pts, int n);
 int aaadmm_host_solver_initialize(void *h, double dt, int iters, double gravity, int anderson_m, int accel,
                                   double penalty, int ordering, int nd_leaf);
+/* Solver::set_external_factor: the next initialize() uses this factor (n = free vertices: factor of Ahat; n = 3 x free
+ * vertices: factor of the full system in the reference's dof order, e.g. Eigen's own) instead of factoring itself. */
+int aaadmm_host_solver_set_factor(void *h, int n, const int64_t *Lp, const int *Li, const double *Lx, const double *D,
+                                  const int *perm);
 int aaadmm_host_solver_step(void *h);
 int aaadmm_host_solver_set_iters(void *h, int iters, int anderson_m, int accel);
 int aaadmm_host_solver_n_dof(void *h);

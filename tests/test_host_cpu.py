@@ -88,6 +88,19 @@ def test_factor_cache_round_trip(A, tmp_path):
     Ax2 = Ax.copy()
     Ax2[3] *= 1.0000001  # another matrix: the cache must not be used
     assert not H.aaadmm_host_factor_load(n, Ap.ctypes.data_as(A.c_lp), Ai.ctypes.data_as(A.c_ip), Ax2.ctypes.data_as(A.c_dp), path)
+    # a file whose header is intact but whose arrays are damaged (row index out of range, broken permutation,
+    # truncated) is a cache miss, not an out-of-bounds index later on
+    good = open(path.decode(), "rb").read()
+    nnz = int(np.frombuffer(good[20:28], np.int64)[0])
+    off_perm, off_li = 28, 28 + 4 * n + 8 * (n + 1)
+    for lo, hi, val in ((off_li, off_li + 4, np.int32(n + 5).tobytes()), (off_perm, off_perm + 4, good[off_perm + 4:off_perm + 8])):
+        open(path.decode(), "wb").write(good[:lo] + val + good[hi:])
+        assert not H.aaadmm_host_factor_load(n, Ap.ctypes.data_as(A.c_lp), Ai.ctypes.data_as(A.c_ip), Ax.ctypes.data_as(A.c_dp), path)
+    open(path.decode(), "wb").write(good[:-16])
+    assert not H.aaadmm_host_factor_load(n, Ap.ctypes.data_as(A.c_lp), Ai.ctypes.data_as(A.c_ip), Ax.ctypes.data_as(A.c_dp), path)
+    open(path.decode(), "wb").write(good)
+    assert H.aaadmm_host_factor_load(n, Ap.ctypes.data_as(A.c_lp), Ai.ctypes.data_as(A.c_ip), Ax.ctypes.data_as(A.c_dp), path)
+    assert nnz > 0
     open(path.decode(), "r+b").write(b"XXXX")  # damaged header
     assert not H.aaadmm_host_factor_load(n, Ap.ctypes.data_as(A.c_lp), Ai.ctypes.data_as(A.c_ip), Ax.ctypes.data_as(A.c_dp), path)
 
@@ -422,8 +435,9 @@ def test_bench_reference_arm_prints_one_json_line():
     """bench.py --impl reference (the reference's own CPU path on a bounded sample): exactly one line on stdout, JSON,
     with the keys the driver reads; everything the reference itself prints goes to stderr."""
     import json
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                       capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--ref-dims", "8", "6", "6"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, OMP_NUM_THREADS="1"))  # as torchrun exports it: the arm must override it
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.split("\n") if l.strip()]
     assert len(lines) == 1, r.stdout[:500]
@@ -432,3 +446,9 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["higher_is_better"] is True and d["steps"] == 1 and d["warmup"] == 1
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # a measurement at the stated size, on all host cores, with none of the product's libraries in the process
+    assert d["config"]["sample_tets"] == 8 * 6 * 6 * 5 and "8x6x6" in d["config"]["workload"]
+    assert d["config"]["same_config_as_gpu_arm"] is False
+    if d["cpu_baseline"]["kind"] == "reference":
+        assert d["cpu_baseline"]["cores"] == os.cpu_count()
+    assert d["native_so_loaded"] and all(l.startswith("oracle/") for l in d["native_so_loaded"]), d["native_so_loaded"]
