@@ -166,6 +166,14 @@ bool Solver::initialize(const Settings &settings_) {
     if ((int)m_v.size() != dof) m_v.resize(dof);
     std::fill(m_v.begin(), m_v.end(), 0.0);
 
+    // AAADMM_SETUP_TRACE=1: stage times of the setup on stderr (setup telemetry)
+    static const bool trace = getenv("AAADMM_SETUP_TRACE") != nullptr;
+    double t_stage = now_ms();
+    auto stage = [&](const char *name) {
+        const double t = now_ms();
+        if (trace) std::cerr << "[setup] " << name << " " << (t - t_stage) << " ms" << std::endl;
+        t_stage = t;
+    };
     const int n_verts = dof / 3;
     // energy terms -> SoA batches (tets, then triangles; the order inside z does not enter the iteration)
     std::vector<double> rest12, youngs, poisson, rest9, tri_youngs, tri_poisson, tri_lmin, tri_lmax;
@@ -233,6 +241,7 @@ bool Solver::initialize(const Settings &settings_) {
     if (!aaadmm::build_tet_system(m_sys, n_verts, rest12.data(), n_tets, tets.data(), material.data(), youngs.data(),
                                   poisson.data(), masses.data(), pinned, rho * dt2, &tri_in, &pt_in))
         throw std::runtime_error(m_sys.error);
+    stage("energy terms -> batches, operators, system matrix");
 
     // factor Ahat once on the host (nested dissection + multifrontal LDL^T)
     std::vector<double> coords((size_t)3 * m_sys.n_free);
@@ -250,7 +259,12 @@ bool Solver::initialize(const Settings &settings_) {
         factor_from_cache = !cache.empty() && aaadmm::ldlt_load(cache, key, m_factor);
     if (!factor_external && !factor_from_cache) {
         std::vector<int> perm = aaadmm::nested_dissection(m_sys.Ahat, coords.data(), leaf_env ? atoi(leaf_env) : m_settings.nd_leaf_size);
+        stage("nested dissection");
         m_factor = aaadmm::ldlt_factorize(m_sys.Ahat, perm);
+        if (trace)
+            std::cerr << "[setup]   symbolic " << 1e3 * m_factor.seconds_symbolic << " ms, numeric "
+                      << 1e3 * m_factor.seconds_numeric << " ms" << std::endl;
+        stage("LDL^T factorisation (host)");
         if (m_factor.ok && !cache.empty() && !aaadmm::ldlt_save(m_factor, key, cache))
             std::cerr << "Solver: could not write the factor cache " << cache << std::endl;
     }
@@ -263,6 +277,7 @@ bool Solver::initialize(const Settings &settings_) {
     if (aaadmm_ldlt_create(&m_ldlt, m_factor.n, m_factor.Lp.data(), m_factor.Li.data(), m_factor.Lx.data(),
                            m_factor.D.data(), m_factor.perm.data(), m_factor.n == m_sys.n_free ? 3 : 1) != 0)
         throw std::runtime_error(std::string("aaadmm_ldlt_create: ") + aaadmm_last_error());
+    stage("device factor (fronts, [Linv ; Q], schedules)");
     aaadmm_tetscene_desc d = {};
     d.n_tris = m_sys.n_tris;
     d.tri = m_sys.tri_dev.data();
@@ -299,6 +314,7 @@ bool Solver::initialize(const Settings &settings_) {
     d.volume = m_sys.volume.data();
     if (aaadmm_tetscene_create(&m_scene, &d, m_ldlt) != 0)
         throw std::runtime_error(std::string("aaadmm_tetscene_create: ") + aaadmm_last_error());
+    stage("device scene");
     m_xbar.resize((size_t)3 * m_sys.n_free);
     m_xout.resize((size_t)3 * m_sys.n_free);
     if (m_settings.verbose >= 1)

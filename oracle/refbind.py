@@ -12,6 +12,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
+REF_FMA_DIR = os.path.join(HERE, "_ref_fma")
 
 c_dp = C.POINTER(C.c_double)
 c_fp = C.POINTER(C.c_float)
@@ -38,19 +39,26 @@ def have_ref():
 _libs = {}
 
 
-def _load(name):
-    if name not in _libs:
-        _libs[name] = C.CDLL(os.path.join(REF_DIR, name))
-    return _libs[name]
+def _load(name, fma=False):
+    key = (name, bool(fma))
+    if key not in _libs:
+        _libs[key] = C.CDLL(os.path.join(REF_FMA_DIR if fma else REF_DIR, name))
+    return _libs[key]
+
+
+def have_ref_fma():
+    """The second flavour of the compiled reference (FMA contraction allowed; oracle/Makefile: _ref_fma): noise-floor
+    measurements only, never the parity oracle."""
+    return os.path.exists(os.path.join(REF_FMA_DIR, "libref_hard.so"))
 
 
 class RefSolver:
     """The reference admm::Solver (hard_zxu or xzu ordering), driven headless."""
 
-    def __init__(self, variant="hard", workdir=None):
+    def __init__(self, variant="hard", workdir=None, fma=False):
         assert variant in ("hard", "xzu")
         self.variant = variant
-        self.lib = _load("libref_%s.so" % variant)
+        self.lib = _load("libref_%s.so" % variant, fma)
         self.p = "ref_%s_" % variant
         self._tmp = None
         if workdir is None:
