@@ -453,7 +453,7 @@ __device__ __forceinline__ void bwd_task(const SweepTask &F, const int *__restri
                         const int r = r0 + i * NCONS;
                         if (r < re) {
 #pragma unroll
-                            for (int q = 0; q < NR; ++q) vs[(r - rc) * NR + q] = sg[i] * vv[i][q];
+                            for (int q = 0; q < NR; ++q) vs[(r - rc) * NR + q] = sg[i] != 0.0 ? sg[i] * vv[i][q] : 0.0;  // padding rows: an exact zero, whatever X[0] holds
                         }
                     }
                 }
@@ -1219,6 +1219,13 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         ldlt_dev_destroy(f);
         return -1;
     }
+    // nothing the sweeps read is ever uninitialised (padding entries are multiplied by zeros of the factor: they must
+    // be finite)
+    cudaMemset(f->W, 0, vec_bytes);
+    cudaMemset(f->Yd, 0, vec_bytes);
+    cudaMemset(f->X, 0, vec_bytes);
+    cudaMemset(f->U, 0, u_bytes);
+    cudaMemset(f->Va, 0, (std::max<size_t>((size_t)va_tot * nrhs, 1) + 2) * sizeof(double));
     // ---- Linv and Q on the device ----
     {
         std::vector<int2> inv_tasks;

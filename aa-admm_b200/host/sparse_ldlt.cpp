@@ -376,7 +376,7 @@ struct Symbolic {
 
 }  // namespace
 
-LdltFactor ldlt_factorize(const SymLower &A, const std::vector<int> &perm, int n_threads) {
+static LdltFactor ldlt_factorize_impl(const SymLower &A, const std::vector<int> &perm, int n_threads, bool symbolic_only) {
     LdltFactor out;
     const int n = A.n;
     out.n = n;
@@ -498,13 +498,17 @@ LdltFactor ldlt_factorize(const SymLower &A, const std::vector<int> &perm, int n
     for (int j = 0; j < n; ++j) out.Lp[j + 1] = out.Lp[j] + (below_end(j) - below_begin(j));
     const int64_t nnzL = out.Lp[n];
     out.Li.resize(nnzL);
-    out.Lx.resize(nnzL);
-    out.D.assign(n, 0.0);
 #pragma omp parallel for schedule(dynamic, 64) num_threads(n_threads)
     for (int j = 0; j < n; ++j) std::copy(below_begin(j), below_end(j), out.Li.begin() + out.Lp[j]);
     out.n_supernodes = nsn;
     double t1 = now_s();
     out.seconds_symbolic = t1 - t0;
+    if (symbolic_only) {  // pattern of L only: the numeric phase runs elsewhere (csrc/ldlt_factor.cu)
+        out.ok = true;
+        return out;
+    }
+    out.Lx.resize(nnzL);
+    out.D.assign(n, 0.0);
 
     // ---- numeric multifrontal ----
     std::vector<double> work(nsn, 0.0);
@@ -594,6 +598,14 @@ LdltFactor ldlt_factorize(const SymLower &A, const std::vector<int> &perm, int n
     out.ok = !failed;
     out.seconds_numeric = now_s() - t1;
     return out;
+}
+
+LdltFactor ldlt_factorize(const SymLower &A, const std::vector<int> &perm, int n_threads) {
+    return ldlt_factorize_impl(A, perm, n_threads, false);
+}
+
+LdltFactor ldlt_symbolic(const SymLower &A, const std::vector<int> &perm, int n_threads) {
+    return ldlt_factorize_impl(A, perm, n_threads, true);
 }
 
 void ldlt_solve_host(const LdltFactor &F, const double *b, double *x, int nrhs) {

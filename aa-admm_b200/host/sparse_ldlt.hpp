@@ -58,6 +58,11 @@ std::vector<int> nested_dissection(const SymLower &A, const double *coords, int 
 // Numeric factorisation with the given ordering.
 LdltFactor ldlt_factorize(const SymLower &A, const std::vector<int> &perm, int n_threads = 0);
 
+// Symbolic phase alone: perm, Lp, Li (pattern of L) and the statistics; Lx and D stay empty. The numeric phase then
+// runs on the device from the matrix values (aaadmm_ldlt_create_from_matrix, csrc/ldlt_factor.cu); the pattern is
+// reusable for every matrix with the same sparsity (material sweeps over one mesh).
+LdltFactor ldlt_symbolic(const SymLower &A, const std::vector<int> &perm, int n_threads = 0);
+
 // Reference host solve (used by tests and by the setup self-check): x = A^-1 b for
 // nrhs interleaved right-hand sides (b[i*nrhs + k]).
 void ldlt_solve_host(const LdltFactor &F, const double *b, double *x, int nrhs);

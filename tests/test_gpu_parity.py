@@ -505,7 +505,7 @@ def _check_cloth(hg, xg, comb_ref, rows_ref, rej_ref, x_ref, accel):
             assert len(hg[f]) == rows
             assert floor.max() < bar
         else:
-            assert_iterations_to_tolerance(hg[f][:, 1], g["comb"][f][:rows], (name, f))
+            assert_iterations_to_tolerance(hg[f][:, 1], comb_ref[f][:rows], ("cloth / collision scene", f))
             assert np.array_equal(hg[f][:8, 2], rej_ref[f][:8])
         xerr = np.abs(xg[f] - x_ref[f]).max() / np.abs(x_ref[f]).max()
         print("final position rel err", xerr)
