@@ -87,6 +87,8 @@ def cuda_lib():
         L.aaadmm_aa_compute.argtypes = [vp, c_dp, c_dp, C.c_int64]
         L.aaadmm_aa_state.argtypes = [vp, c_ip, c_ip]
         L.aaadmm_ldlt_create.argtypes = [C.POINTER(vp), C.c_int, c_lp, c_ip, c_dp, c_dp, c_ip, C.c_int]
+        L.aaadmm_ldlt_create_from_matrix.argtypes = [C.POINTER(vp), C.c_int, c_lp, c_ip, c_dp, c_lp, c_ip, c_ip, C.c_int]
+        L.aaadmm_ldlt_refactor.argtypes = [vp, c_dp]
         L.aaadmm_ldlt_destroy.argtypes = [vp]
         L.aaadmm_ldlt_solve.argtypes = [vp, c_dp, c_dp]
         L.aaadmm_ldlt_stats.argtypes = [vp, c_dp]
@@ -251,6 +253,31 @@ class Ldlt:
         perm = np.ascontiguousarray(perm, np.int32)
         self.h = C.c_void_p()
         _ck(self.L.aaadmm_ldlt_create(C.byref(self.h), self.n, _lp(Lp), _ip(Li), _dp(Lx), _dp(D), _ip(perm), self.nrhs))
+
+    @classmethod
+    def from_matrix(cls, n, Ap, Ai, Ax, Lp, Li, perm, nrhs=3):
+        """Numeric factorisation ON THE DEVICE: A lower CSC (incl. diagonal), pattern of L (Lp, Li) and the ordering
+        from a symbolic analysis; aaadmm_ldlt_create_from_matrix."""
+        self = cls.__new__(cls)
+        self.L = cuda_lib()
+        self.n, self.nrhs = int(n), int(nrhs)
+        Ap = np.ascontiguousarray(Ap, np.int64)
+        Ai = np.ascontiguousarray(Ai, np.int32)
+        Ax = np.ascontiguousarray(Ax, np.float64)
+        Lp = np.ascontiguousarray(Lp, np.int64)
+        Li = np.ascontiguousarray(Li, np.int32)
+        perm = np.ascontiguousarray(perm, np.int32)
+        self.nnz_a = int(Ap[n])
+        self.h = C.c_void_p()
+        _ck(self.L.aaadmm_ldlt_create_from_matrix(C.byref(self.h), self.n, _lp(Ap), _ip(Ai), _dp(Ax), _lp(Lp), _ip(Li),
+                                                  _ip(perm), self.nrhs))
+        return self
+
+    def refactor(self, Ax):
+        """Other values, same pattern: aaadmm_ldlt_refactor (no allocation, no analysis)."""
+        Ax = np.ascontiguousarray(Ax, np.float64)
+        assert Ax.size == self.nnz_a
+        _ck(self.L.aaadmm_ldlt_refactor(self.h, _dp(Ax)))
 
     def close(self):
         if self.h:

@@ -341,6 +341,38 @@ int aaadmm_ldlt_create(aaadmm_ldlt **out, int n, const int64_t *Lp, const int *L
     return 0;
     API_TRY_END
 }
+int aaadmm_ldlt_create_from_matrix(aaadmm_ldlt **out, int n, const int64_t *Ap, const int *Ai, const double *Ax,
+                                   const int64_t *Lp, const int *Li, const int *perm, int nrhs) {
+    API_TRY_BEGIN
+    if (aaadmm_device_count() <= 0) {
+        set_last_error("ldlt_create_from_matrix: no CUDA device (this library has no CPU path)");
+        return -1;
+    }
+    if (n <= 0 || !Ap || !Ai || !Ax || !Lp || !perm || (Lp[n] > 0 && !Li)) {
+        set_last_error("ldlt_create_from_matrix: bad arguments");
+        return -1;
+    }
+    aaadmm_ldlt *h = new aaadmm_ldlt();
+    if (ldlt_dev_create_from_matrix(&h->f, n, Ap, Ai, Ax, Lp, Li, perm, nrhs)) {
+        delete h;
+        return -1;
+    }
+    *out = h;  // from here on aaadmm_ldlt_destroy frees everything
+    AAADMM_CUDA_OK(cudaStreamCreate(&h->stream));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&h->b_dev, sizeof(double) * n * nrhs));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&h->x_dev, sizeof(double) * n * nrhs));
+    return 0;
+    API_TRY_END
+}
+int aaadmm_ldlt_refactor(aaadmm_ldlt *h, const double *Ax) {
+    API_TRY_BEGIN
+    if (!h || !Ax) {
+        set_last_error("ldlt_refactor: bad arguments");
+        return -1;
+    }
+    return ldlt_dev_refactor(h->f, Ax, h->stream);
+    API_TRY_END
+}
 int aaadmm_ldlt_destroy(aaadmm_ldlt *h) {
     if (!h) return 0;
     ldlt_dev_destroy(h->f);

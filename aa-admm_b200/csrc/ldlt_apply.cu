@@ -15,6 +15,7 @@
 // bit-reproducible. Right-hand sides are interleaved (n x NR, NR = 3 for A = Ahat (x) I3): every
 // factor entry is read once per sweep and used NR times.
 #include "ldlt_apply.cuh"
+#include "ldlt_factor.cuh"
 #include "pipe.cuh"
 
 #include <algorithm>
@@ -773,11 +774,33 @@ void ldlt_dev_destroy(LdltDev *f) {
     cudaFree(f->ctl);
     cudaFree(f->Va);
     cudaFree(f->trace);
+    cudaFree(f->inv_tasks);
+    cudaFree(f->q_tasks);
+    cudaFree(f->tile_src);
+    cudaFree(f->A);
+    cudaFree(f->D);
+    factor_plan_destroy(f->plan);
+    if (f->setup_stream) cudaStreamDestroy(f->setup_stream);
     delete f;
 }
 
-int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, const double *Lx,
-                    const double *D, const int *perm, int nrhs) {
+namespace {
+// [Linv ; Q] of every front from its [T ; P] (f->A) and the two sweep-ordered copies Mf / Mb; on `s`.
+int finish_numeric(LdltDev *f, cudaStream_t s) {
+    AAADMM_CUDA_OK(cudaMemsetAsync(f->M, 0, (size_t)std::max<int64_t>(f->m_tot, 1) * sizeof(double), s));
+    if (f->n_inv_tasks > 0) k_invert_fronts<<<f->n_inv_tasks, 128, 0, s>>>(f->inv_tasks, f->fronts, f->A, f->M);
+    if (f->n_q_tasks > 0) k_front_q<<<f->n_q_tasks, 256, 0, s>>>(f->q_tasks, f->fronts, f->A, f->M);
+    if (f->n_ftasks > 0) k_make_tiles<<<f->n_ftasks, 256, 0, s>>>(f->tasks, f->tile_src, f->M, f->Mf);
+    if (f->n_btasks > 0) k_make_btiles<<<f->n_btasks, 256, 0, s>>>(f->tasks + f->n_ftasks, f->tile_src + f->n_ftasks, f->M, f->Mb);
+    AAADMM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+}  // namespace
+
+// Structure from the pattern of L; values either from (Lx, D) (a factor computed elsewhere) or - when the pattern of
+// the matrix (Ap, Ai) is given instead - left to the device-side factorisation (f->plan).
+static int build(LdltDev **out, int n, const int64_t *Lp, const int *Li, const double *Lx, const double *D, const int *perm,
+                 int nrhs, const int64_t *Ap, const int *Ai) {
     if (nrhs != 1 && nrhs != 3) {
         set_last_error("ldlt: nrhs must be 1 or 3");
         return -1;
@@ -873,6 +896,8 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         std::copy(Li + Lp[jl], Li + Lp[jl + 1], rows.begin() + fr[b].r_off);
     }
     std::vector<double> A;
+    int64_t noff = 0;
+    if (Lx) {
     try {
         A.assign((size_t)std::max<int64_t>(m_tot, 1), 0.0);
     } catch (const std::bad_alloc &) {
@@ -881,7 +906,6 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         return -1;
     }
     int bad = 0;
-    int64_t noff = 0;
 #pragma omp parallel for schedule(dynamic, 8) reduction(+ : bad, noff)
     for (int b = 0; b < nb; ++b) {
         const FrontDesc &F = fr[b];
@@ -911,6 +935,13 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         set_last_error("ldlt: column patterns of the factor do not nest along the elimination tree");
         delete f;
         return -1;
+    }
+    } else {
+        for (int b = 0; b < nb; ++b) {  // pattern-only statistics
+            const FrontDesc &F = fr[b];
+            for (int j = F.first; j < F.first + F.ns; ++j)
+                for (int64_t p = Lp[j]; p < Lp[j + 1]; ++p) noff += Li[p] >= F.first + F.ns;
+        }
     }
     // gather lists: for every front row (columns first, then the rows below) the slots of the children's
     // update vectors that add into it, children in ascending order
@@ -1188,11 +1219,11 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
 
     std::vector<int> permv(perm, perm + n), iperm(std::max(n, 1));
     for (int k = 0; k < n; ++k) iperm[perm[k]] = k;
-    std::vector<double> dinv(std::max(n, 1));
-    for (int k = 0; k < n; ++k) dinv[k] = 1.0 / D[k];
+    std::vector<double> dinv(std::max(n, 1), 1.0);
+    if (D)
+        for (int k = 0; k < n; ++k) dinv[k] = 1.0 / D[k];
 
     // ---- upload ----
-    double *dA = nullptr;
     int rc = 0;
     rc |= upload(&f->perm, permv);
     rc |= upload(&f->iperm, iperm);
@@ -1205,17 +1236,23 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
         rc |= upload(&f->gidx, gidx);
     }
     rc |= upload(&f->tasks, tasks);
-    rc |= upload(&dA, A);
+    if (Lx) rc |= upload(&f->A, A);
     std::vector<double>().swap(A);
+    f->m_tot = m_tot;
+    f->mf_tot = mf_tot;
+    f->mb_tot = mb_tot;
     const size_t mat_bytes = (size_t)std::max<int64_t>(m_tot, 1) * sizeof(double);
     const size_t vec_bytes = (std::max<size_t>((size_t)n * nrhs, 1) + 2) * sizeof(double);  // + slack for aligned bulk copies
     const size_t u_bytes = std::max<size_t>((size_t)r_tot * nrhs, 1) * sizeof(double);
-    if (rc || cudaMalloc((void **)&f->M, mat_bytes) != cudaSuccess || cudaMalloc((void **)&f->W, vec_bytes) != cudaSuccess ||
+    if (rc || (!Lx && cudaMalloc((void **)&f->A, mat_bytes) != cudaSuccess) ||
+        (!Lx && cudaMalloc((void **)&f->D, sizeof(double) * std::max(n, 1)) != cudaSuccess) ||
+        cudaMalloc((void **)&f->M, mat_bytes) != cudaSuccess || cudaMalloc((void **)&f->W, vec_bytes) != cudaSuccess ||
         cudaMalloc((void **)&f->Yd, vec_bytes) != cudaSuccess || cudaMalloc((void **)&f->X, vec_bytes) != cudaSuccess ||
         cudaMalloc((void **)&f->U, u_bytes) != cudaSuccess || cudaMalloc((void **)&f->ctl, sizeof(int) * f->n_ctl) != cudaSuccess ||
-        cudaMalloc((void **)&f->Va, (std::max<size_t>((size_t)va_tot * nrhs, 1) + 2) * sizeof(double)) != cudaSuccess) {
+        cudaMalloc((void **)&f->Va, (std::max<size_t>((size_t)va_tot * nrhs, 1) + 2) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&f->Mf, (size_t)std::max<int64_t>(mf_tot, 1) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&f->Mb, (size_t)std::max<int64_t>(mb_tot, 1) * sizeof(double)) != cudaSuccess) {
         set_last_error("ldlt: cudaMalloc failed");
-        cudaFree(dA);
         ldlt_dev_destroy(f);
         return -1;
     }
@@ -1226,7 +1263,7 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     cudaMemset(f->X, 0, vec_bytes);
     cudaMemset(f->U, 0, u_bytes);
     cudaMemset(f->Va, 0, (std::max<size_t>((size_t)va_tot * nrhs, 1) + 2) * sizeof(double));
-    // ---- Linv and Q on the device ----
+    // ---- task lists of the numeric setup ([Linv ; Q], sweep-ordered copies) ----
     {
         std::vector<int2> inv_tasks;
         std::vector<int4> q_tasks;
@@ -1235,33 +1272,29 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
             for (int rt = 0; rt < fr[b].k; rt += 64)
                 for (int jt = 0; jt < fr[b].ns; jt += 64) q_tasks.push_back(make_int4(b, rt, jt, 0));
         }
-        int2 *d_inv = nullptr;
-        int4 *d_q = nullptr;
-        if (upload(&d_inv, inv_tasks) || upload(&d_q, q_tasks)) {
-            cudaFree(dA);
+        f->n_inv_tasks = (int)inv_tasks.size();
+        f->n_q_tasks = (int)q_tasks.size();
+        if (upload(&f->inv_tasks, inv_tasks) || upload(&f->q_tasks, q_tasks) || upload(&f->tile_src, tile_src)) {
             ldlt_dev_destroy(f);
             return -1;
         }
-        cudaMemset(f->M, 0, mat_bytes);
-        if (!inv_tasks.empty()) k_invert_fronts<<<(int)inv_tasks.size(), 128>>>(d_inv, f->fronts, dA, f->M);
-        if (!q_tasks.empty()) k_front_q<<<(int)q_tasks.size(), 256>>>(d_q, f->fronts, dA, f->M);
-        cudaFree(dA);  // ordered after the kernels above (same stream)
-        // tile-major copy for the forward sweep
-        int64_t *d_src = nullptr;
-        cudaError_t e = cudaMalloc((void **)&f->Mf, (size_t)std::max<int64_t>(mf_tot, 1) * sizeof(double));
-        if (e == cudaSuccess) e = cudaMalloc((void **)&f->Mb, (size_t)std::max<int64_t>(mb_tot, 1) * sizeof(double));
-        if (e == cudaSuccess && upload(&d_src, tile_src) == 0) {
-            if (f->n_ftasks > 0) k_make_tiles<<<f->n_ftasks, 256>>>(f->tasks, d_src, f->M, f->Mf);
-            if (f->n_btasks > 0) k_make_btiles<<<f->n_btasks, 256>>>(f->tasks + f->n_ftasks, d_src + f->n_ftasks, f->M, f->Mb);
-        }
-        if (e == cudaSuccess) e = cudaDeviceSynchronize();
-        cudaFree(f->M);  // only the two sweep-ordered copies stay
+    }
+    if (Lx) {
+        // values given: [Linv ; Q] and the sweep-ordered copies now; the intermediate matrices are not kept
+        cudaError_t e = finish_numeric(f, 0) == 0 ? cudaDeviceSynchronize() : cudaErrorUnknown;
+        cudaFree(f->M);
         f->M = nullptr;
-        cudaFree(d_inv);
-        cudaFree(d_q);
-        cudaFree(d_src);
+        cudaFree(f->A);
+        f->A = nullptr;
         if (e != cudaSuccess) {
             set_last_error(std::string("ldlt: front setup failed: ") + cudaGetErrorString(e));
+            ldlt_dev_destroy(f);
+            return -1;
+        }
+    } else {
+        std::vector<int> parent_v(parent), level_v(level);
+        if (cudaStreamCreate(&f->setup_stream) != cudaSuccess ||
+            factor_plan_build(&f->plan, n, fr, nb, rows, parent_v, level_v, blk_of, perm, Ap, Ai, m_tot)) {
             ldlt_dev_destroy(f);
             return -1;
         }
@@ -1288,6 +1321,40 @@ int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, cons
     // per apply: every factor value once per sweep (8 bytes, no indices); rhs in, y out and in, x out twice,
     // the update vectors out and in
     f->stats.bytes_per_solve = 2.0 * 8.0 * (double)nnz + 8.0 * nrhs * (5.0 * (double)n + 3.0 * (double)r_tot);
+    *out = f;
+    return 0;
+}
+
+int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, const double *Lx,
+                    const double *D, const int *perm, int nrhs) {
+    if (!Lx && Lp[n] > 0) {
+        set_last_error("ldlt: null values");
+        return -1;
+    }
+    static const double one = 1.0;
+    return build(out, n, Lp, Li, Lx ? Lx : &one, D, perm, nrhs, nullptr, nullptr);
+}
+
+int ldlt_dev_refactor(LdltDev *f, const double *Ax, cudaStream_t stream) {
+    if (!f->plan) {
+        set_last_error("ldlt refactor: this factor was not created from a matrix");
+        return -1;
+    }
+    AAADMM_CUDA_OK(cudaMemcpyAsync(factor_plan_values(f->plan), Ax, sizeof(double) * (size_t)factor_plan_nnz(f->plan),
+                                   cudaMemcpyHostToDevice, stream));
+    if (factor_plan_run(f->plan, f->A, f->D, f->dinv, stream)) return -1;
+    if (finish_numeric(f, stream)) return -1;
+    return factor_plan_check(f->plan, stream);
+}
+
+int ldlt_dev_create_from_matrix(LdltDev **out, int n, const int64_t *Ap, const int *Ai, const double *Ax, const int64_t *Lp,
+                                const int *Li, const int *perm, int nrhs) {
+    LdltDev *f = nullptr;
+    if (build(&f, n, Lp, Li, nullptr, nullptr, perm, nrhs, Ap, Ai)) return -1;
+    if (ldlt_dev_refactor(f, Ax, f->setup_stream)) {
+        ldlt_dev_destroy(f);
+        return -1;
+    }
     *out = f;
     return 0;
 }

@@ -69,12 +69,30 @@ struct LdltDev {
     double *W = nullptr, *Yd = nullptr, *X = nullptr, *U = nullptr;
     double *Va = nullptr;  // wide fronts: [D^-1 y ; -x(rows below) ; 0] assembled once per front (backward sweep)
     LdltStats stats;
+    // ---- kept from the setup so that new VALUES can be loaded into the same structure (ldlt_dev_refactor) ----
+    int64_t m_tot = 0, mf_tot = 0, mb_tot = 0;
+    int2 *inv_tasks = nullptr;   // (front, first row) per 128 rows of a diagonal block
+    int4 *q_tasks = nullptr;     // (front, first row, first column) per 64 x 64 tile of Q
+    int n_inv_tasks = 0, n_q_tasks = 0;
+    int64_t *tile_src = nullptr; // per task: offset of its front matrix in M
+    double *A = nullptr;         // front matrices [T ; P] (only kept by factors created from a matrix)
+    double *D = nullptr;         // pivots
+    struct FactorPlan *plan = nullptr;  // device-side numeric factorisation (ldlt_factor.cu); null for factors given as (L, D)
+    cudaStream_t setup_stream = nullptr;
 };
 
 // Builds the device structure from a strictly-lower CSC factor (rows sorted per column).
 int ldlt_dev_create(LdltDev **out, int n, const int64_t *Lp, const int *Li, const double *Lx,
                     const double *D, const int *perm, int nrhs);
 void ldlt_dev_destroy(LdltDev *f);
+// The same structure from the PATTERN of L (Lp, Li) and of the matrix (Ap, Ai: lower CSC incl. diagonal, original
+// numbering); the values Ax are factored on the device (ldlt_factor.cu). The structure stays allocated:
+// ldlt_dev_refactor loads another matrix with the same pattern without any allocation.
+int ldlt_dev_create_from_matrix(LdltDev **out, int n, const int64_t *Ap, const int *Ai, const double *Ax, const int64_t *Lp,
+                                const int *Li, const int *perm, int nrhs);
+// New values for a factor made by ldlt_dev_create_from_matrix (host array, lower CSC order of Ap / Ai). Enqueued on
+// `stream` (stream-ordered with the applies the caller launches there afterwards); returns after the pivots were checked.
+int ldlt_dev_refactor(LdltDev *f, const double *Ax, cudaStream_t stream);
 
 // Developer aid (AAADMM_LDLT_TRACE=1 at creation): per-task time stamps of the last apply as CSV.
 int ldlt_dev_dump_trace(LdltDev *f, const char *path);

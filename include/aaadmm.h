@@ -62,6 +62,15 @@ int aaadmm_aa_state(aaadmm_aa *aa, int *iter, int *col);
 typedef struct aaadmm_ldlt aaadmm_ldlt;
 int aaadmm_ldlt_create(aaadmm_ldlt **out, int n, const int64_t *Lp, const int *Li, const double *Lx,
                        const double *D, const int *perm, int nrhs);
+/* The same object from the MATRIX instead of a finished factor: A (lower CSC incl. diagonal, rows ascending, original
+ * numbering) with the pattern of L (Lp, Li as above, from a symbolic analysis: aa-admm_b200/host/sparse_ldlt:
+ * ldlt_symbolic) and the ordering. The numeric factorisation runs on the device (multifrontal, FP64, no pivoting) and
+ * replaces the numeric half of Eigen::SimplicialLDLT::compute (LinearSolver.hpp:79-84). aaadmm_ldlt_refactor loads
+ * another matrix with the SAME pattern (a material sweep over one mesh) into the same object: no allocation, no
+ * analysis, stream-ordered on the object's stream. Both fail (-1) on a zero or non-finite pivot. */
+int aaadmm_ldlt_create_from_matrix(aaadmm_ldlt **out, int n, const int64_t *Ap, const int *Ai, const double *Ax,
+                                   const int64_t *Lp, const int *Li, const int *perm, int nrhs);
+int aaadmm_ldlt_refactor(aaadmm_ldlt *f, const double *Ax);
 int aaadmm_ldlt_destroy(aaadmm_ldlt *f);
 int aaadmm_ldlt_solve(aaadmm_ldlt *f, const double *b, double *x);          /* host vectors */
 int aaadmm_ldlt_solve_dev(aaadmm_ldlt *f, const double *d_b, double *d_x);  /* device vectors */
