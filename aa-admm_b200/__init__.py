@@ -139,6 +139,9 @@ def host_lib():
         H.aaadmm_host_solver_initialize.argtypes = [vp, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
                                                     C.c_int, C.c_int]
         H.aaadmm_host_solver_set_factor.argtypes = [vp, C.c_int, c_lp, c_ip, c_dp, c_dp, c_ip]
+        H.aaadmm_host_solver_set_material.argtypes = [vp, C.c_double, C.c_double]
+        H.aaadmm_host_solver_set_x.argtypes = [vp, c_dp]
+        H.aaadmm_host_solver_was_incremental.argtypes = [vp]
         H.aaadmm_host_solver_step.argtypes = [vp]
         H.aaadmm_host_solver_set_iters.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         H.aaadmm_host_solver_n_dof.argtypes = [vp]
@@ -504,6 +507,19 @@ class Solver:
         D = np.ascontiguousarray(D, np.float64)
         perm = np.ascontiguousarray(perm, np.int32)
         _hk(self.H.aaadmm_host_solver_set_factor(self.h, int(n), _lp(Lp), _ip(Li), _dp(Lx), _dp(D), _ip(perm)))
+
+    def set_material(self, youngs, poisson):
+        """Solver::set_material: every energy term gets these Lame parameters; the next initialize() on the unchanged
+        scene is incremental (numeric part only)."""
+        _hk(self.H.aaadmm_host_solver_set_material(self.h, float(youngs), float(poisson)))
+
+    def set_x(self, x):
+        x = np.ascontiguousarray(x, np.float64).reshape(-1)
+        assert x.size == self.H.aaadmm_host_solver_n_dof(self.h)
+        self.H.aaadmm_host_solver_set_x(self.h, _dp(x))
+
+    def was_incremental(self):
+        return bool(self.H.aaadmm_host_solver_was_incremental(self.h))
 
     def set_iters(self, iters, anderson_m, accel):
         self.H.aaadmm_host_solver_set_iters(self.h, iters, anderson_m, int(bool(accel)))

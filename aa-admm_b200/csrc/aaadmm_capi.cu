@@ -628,6 +628,38 @@ int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *d,
     API_TRY_END
 }
 
+int aaadmm_tetscene_update_material(aaadmm_tetscene *s, const double *weight, const double *kvol, const double *mu,
+                                    const double *lambda, const double *tri_weight, const double *tri_limit_min,
+                                    const double *tri_limit_max, double rho_dt2) {
+    API_TRY_BEGIN
+    if (!s || (s->T > 0 && (!weight || !kvol)) || (s->NT > 0 && !tri_weight) || (s->n_hyper > 0 && (!mu || !lambda))) {
+        set_last_error("tetscene_update_material: null array");
+        return -1;
+    }
+    cudaStream_t st = s->stream;
+    if (s->T > 0) {
+        AAADMM_CUDA_OK(cudaMemcpyAsync(s->w, weight, sizeof(double) * s->T, cudaMemcpyHostToDevice, st));
+        AAADMM_CUDA_OK(cudaMemcpyAsync(s->kvol, kvol, sizeof(double) * s->T, cudaMemcpyHostToDevice, st));
+        if (s->n_hyper > 0) {
+            AAADMM_CUDA_OK(cudaMemcpyAsync(s->mu, mu, sizeof(double) * s->T, cudaMemcpyHostToDevice, st));
+            AAADMM_CUDA_OK(cudaMemcpyAsync(s->lambda, lambda, sizeof(double) * s->T, cudaMemcpyHostToDevice, st));
+        }
+    }
+    if (s->NT > 0) {
+        AAADMM_CUDA_OK(cudaMemcpyAsync(s->tri_w, tri_weight, sizeof(double) * s->NT, cudaMemcpyHostToDevice, st));
+        if (tri_limit_min) AAADMM_CUDA_OK(cudaMemcpyAsync(s->tri_lmin, tri_limit_min, sizeof(double) * s->NT, cudaMemcpyHostToDevice, st));
+        if (tri_limit_max) AAADMM_CUDA_OK(cudaMemcpyAsync(s->tri_lmax, tri_limit_max, sizeof(double) * s->NT, cudaMemcpyHostToDevice, st));
+    }
+    if (rho_dt2 != s->rho_dt2) {
+        s->rho_dt2 = rho_dt2;
+        s->loop_key = -1;  // the captured loop body holds rho dt^2 by value: capture again at the next step
+    }
+    s->has_inputs = false;
+    AAADMM_CUDA_OK(cudaStreamSynchronize(st));  // the host arrays may go away
+    return 0;
+    API_TRY_END
+}
+
 static int scene_reserve(aaadmm_tetscene *s, int iters, int m) {
     if (iters > s->hist_cap) {
         cudaFree(s->hist_prim);

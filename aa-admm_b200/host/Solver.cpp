@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
@@ -41,6 +42,27 @@ TriEnergyTerm::TriEnergyTerm(const Vec3i &tri_, const std::vector<Vec3> &verts, 
     }
     if (!aaadmm::tri_constants(rest9, lame.youngs, lame.poisson, rest_pose.data(), &area, &weight))
         throw std::runtime_error("**TriEnergyTerm Error: Inverted initial pose");
+}
+
+void TetEnergyTerm::set_lame(const Lame &l) {
+    lame = l;
+    weight = std::sqrt(lame.bulk_modulus() * volume);
+}
+void TriEnergyTerm::set_lame(const Lame &l) {
+    const double lmin = lame.limit_min, lmax = lame.limit_max;
+    lame = l;
+    lame.limit_min = lmin;
+    lame.limit_max = lmax;
+    weight = std::sqrt(lame.bulk_modulus() * area);
+}
+void Solver::set_material(double youngs, double poisson) {
+    const Lame l(youngs, poisson);
+    for (auto &e : energyterms) {
+        if (TetEnergyTerm *t = dynamic_cast<TetEnergyTerm *>(e.get()))
+            t->set_lame(l);
+        else if (TriEnergyTerm *t = dynamic_cast<TriEnergyTerm *>(e.get()))
+            t->set_lame(l);
+    }
 }
 
 // src/ExplicitForce.cpp:47-105
@@ -238,6 +260,61 @@ bool Solver::initialize(const Settings &settings_) {
     }
     const double dt2 = m_settings.timestep_s * m_settings.timestep_s;
     const double rho = (m_settings.ordering == Settings::HARD_ZXU) ? m_settings.penalty : 1.0;
+    // ---- re-initialisation with the same mesh, terms, pins and collision set (e.g. the next member of a material
+    // sweep): everything that depends on the pattern only - numbering, incidence lists, ordering, symbolic analysis,
+    // fronts and schedules of the device factor, every device buffer - is kept; the element moduli, the VALUES of the
+    // system matrix and its numeric factorisation (on the device) are redone. No allocation, no analysis.
+    uint64_t skey = 1469598103934665603ull;
+    auto mix = [&](const void *p, size_t bytes) {
+        const unsigned char *c = static_cast<const unsigned char *>(p);
+        size_t i = 0;
+        for (; i + 8 <= bytes; i += 8) {
+            uint64_t w;
+            memcpy(&w, c + i, 8);
+            skey = (skey ^ w) * 1099511628211ull;
+            skey ^= skey >> 29;
+        }
+        for (; i < bytes; ++i) skey = (skey ^ c[i]) * 1099511628211ull;
+    };
+    {
+        const int hdr[6] = {n_verts, n_tets, tri_in.n_tris, pt_in.n, (int)m_settings.ordering, (int)m_obstacles.size()};
+        mix(hdr, sizeof(hdr));
+        mix(tets.data(), tets.size() * sizeof(int));
+        mix(material.data(), material.size() * sizeof(int));
+        mix(rest12.data(), rest12.size() * sizeof(double));
+        mix(tris.data(), tris.size() * sizeof(int));
+        mix(rest9.data(), rest9.size() * sizeof(double));
+        mix(masses.data(), masses.size() * sizeof(double));
+        mix(pinned.data(), pinned.size() * sizeof(int));
+        mix(col_verts.data(), col_verts.size() * sizeof(int));
+        mix(col_w.data(), col_w.size() * sizeof(double));
+        for (auto &o : m_obstacles) {
+            mix(&o->type, sizeof(int));
+            mix(o->prm.data(), sizeof(double) * o->prm.size());
+        }
+    }
+    stage("energy terms -> batches, structure key");
+    if (m_scene && m_ldlt && device_numeric && skey == m_structure_key && !factor_external) {
+        if (!aaadmm::update_tet_system_materials(m_sys, youngs.data(), poisson.data(), rho * dt2, &tri_in))
+            throw std::runtime_error(m_sys.error);
+        stage("moduli + values of the system matrix");
+        if (aaadmm_ldlt_refactor(m_ldlt, m_sys.Ahat.x.data()) != 0) {
+            std::cerr << "\n**Solver Error: LDLT factorization failed: " << aaadmm_last_error() << std::endl;
+            initialized = false;
+            return false;
+        }
+        stage("numeric factorisation (device)");
+        if (aaadmm_tetscene_update_material(m_scene, m_sys.weight.data(), m_sys.kvol.data(), m_sys.mu.data(), m_sys.lambda.data(),
+                                            m_sys.tri_weight.data(), m_sys.tri_limit_min.data(), m_sys.tri_limit_max.data(),
+                                            rho * dt2) != 0)
+            throw std::runtime_error(std::string("aaadmm_tetscene_update_material: ") + aaadmm_last_error());
+        stage("device scene: moduli");
+        m_runtime.initialization_ms = now_ms() - t0;
+        reinitialized = true;
+        initialized = true;
+        return true;
+    }
+    reinitialized = false;
     if (!aaadmm::build_tet_system(m_sys, n_verts, rest12.data(), n_tets, tets.data(), material.data(), youngs.data(),
                                   poisson.data(), masses.data(), pinned, rho * dt2, &tri_in, &pt_in))
         throw std::runtime_error(m_sys.error);
@@ -257,7 +334,16 @@ bool Solver::initialize(const Settings &settings_) {
         factor_from_cache = false;
     } else
         factor_from_cache = !cache.empty() && aaadmm::ldlt_load(cache, key, m_factor);
-    if (!factor_external && !factor_from_cache) {
+    // Numeric phase on the device unless a factor cache file or a host factorisation is asked for: the host then only
+    // orders and analyses (pattern of L).
+    static const bool host_env = getenv("AAADMM_HOST_FACTOR") != nullptr;
+    device_numeric = !factor_external && !factor_from_cache && cache.empty() && !m_settings.host_factorization && !host_env;
+    if (device_numeric) {
+        std::vector<int> perm = aaadmm::nested_dissection(m_sys.Ahat, coords.data(), leaf_env ? atoi(leaf_env) : m_settings.nd_leaf_size);
+        stage("nested dissection");
+        m_factor = aaadmm::ldlt_symbolic(m_sys.Ahat, perm);
+        stage("symbolic analysis (pattern of L)");
+    } else if (!factor_external && !factor_from_cache) {
         std::vector<int> perm = aaadmm::nested_dissection(m_sys.Ahat, coords.data(), leaf_env ? atoi(leaf_env) : m_settings.nd_leaf_size);
         stage("nested dissection");
         m_factor = aaadmm::ldlt_factorize(m_sys.Ahat, perm);
@@ -274,10 +360,22 @@ bool Solver::initialize(const Settings &settings_) {
     }
     if (m_scene) aaadmm_tetscene_destroy(m_scene), m_scene = nullptr;
     if (m_ldlt) aaadmm_ldlt_destroy(m_ldlt), m_ldlt = nullptr;
-    if (aaadmm_ldlt_create(&m_ldlt, m_factor.n, m_factor.Lp.data(), m_factor.Li.data(), m_factor.Lx.data(),
-                           m_factor.D.data(), m_factor.perm.data(), m_factor.n == m_sys.n_free ? 3 : 1) != 0)
-        throw std::runtime_error(std::string("aaadmm_ldlt_create: ") + aaadmm_last_error());
-    stage("device factor (fronts, [Linv ; Q], schedules)");
+    if (device_numeric) {
+        if (aaadmm_ldlt_create_from_matrix(&m_ldlt, m_sys.Ahat.n, m_sys.Ahat.p.data(), m_sys.Ahat.i.data(), m_sys.Ahat.x.data(),
+                                           m_factor.Lp.data(), m_factor.Li.data(), m_factor.perm.data(), 3) != 0) {
+            const std::string msg = aaadmm_last_error();
+            if (msg.find("pivot") == std::string::npos) throw std::runtime_error("aaadmm_ldlt_create_from_matrix: " + msg);
+            std::cerr << "\n**Solver Error: LDLT factorization failed: " << msg << std::endl;  // as LinearSolver.hpp:81-83
+            return false;
+        }
+        stage("device factor (fronts, schedules, numeric factorisation, [Linv ; Q])");
+    } else {
+        if (aaadmm_ldlt_create(&m_ldlt, m_factor.n, m_factor.Lp.data(), m_factor.Li.data(), m_factor.Lx.data(),
+                               m_factor.D.data(), m_factor.perm.data(), m_factor.n == m_sys.n_free ? 3 : 1) != 0)
+            throw std::runtime_error(std::string("aaadmm_ldlt_create: ") + aaadmm_last_error());
+        stage("device factor (fronts, [Linv ; Q], schedules)");
+    }
+    m_structure_key = skey;
     aaadmm_tetscene_desc d = {};
     d.n_tris = m_sys.n_tris;
     d.tri = m_sys.tri_dev.data();

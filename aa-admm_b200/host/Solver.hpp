@@ -63,6 +63,8 @@ public:
     double get_volume() const { return volume; }
     // throws std::runtime_error("**TetEnergyTerm Error: Inverted initial tet") like the reference ctor
     TetEnergyTerm(const Vec4i &tet_, const std::vector<Vec3> &verts, const Lame &lame_, int material_ = 0);
+    // another material on the same element (material sweeps re-initialize one Solver, see Solver::initialize)
+    void set_lame(const Lame &l);
 };
 class NeoHookeanTet : public TetEnergyTerm {
 public:
@@ -100,6 +102,7 @@ public:
     double get_volume() const { return area; }
     // throws std::runtime_error like the reference ctor (bad strain limits, inverted initial pose)
     TriEnergyTerm(const Vec3i &tri_, const std::vector<Vec3> &verts, const Lame &lame_);
+    void set_lame(const Lame &l);
 };
 
 // hard/src/TriEnergyTerm.hpp:32-47
@@ -209,10 +212,11 @@ public:
         bool write_residual_file;          // save() to ./result/residual-*.txt like the reference
         int nd_leaf_size;                  // nested-dissection leaf size of the setup factorisation
         std::string factor_cache;          // if not empty: file the LDL^T factor is cached in (keyed by the matrix)
+        bool host_factorization;           // numeric LDL^T on the host cores instead of the device (default: device)
         Settings()
             : timestep_s(1.0 / 30.0), verbose(1), admm_iters(500), gravity(-9.8), constraint_w(-1), Anderson_m(2),
               penalty(1.0), beta(1.0), acceleration_type(NOACC), ordering(HARD_ZXU), write_residual_file(true),
-              nd_leaf_size(96) {}
+              nd_leaf_size(96), host_factorization(false) {}
     };
     struct RuntimeData {
         double global_ms, local_ms, acceleration_ms, initialization_ms;
@@ -256,7 +260,14 @@ public:
     // obstacles must be added before initialize() (the device scene keeps their parameters).
     void set_collisions(const std::vector<int> &inds, const std::vector<Vec3> &points = std::vector<Vec3>());
     void add_obstacle(std::shared_ptr<PassiveCollision> obj);
+    // Calling initialize() again on a Solver whose nodes, elements, pins and collision set are unchanged (only the
+    // elements' Lame parameters, the time step or the penalty differ: the next member of a parameter sweep) keeps the
+    // whole analysis and every device buffer and redoes the numeric part only (system-matrix values, numeric LDL^T on
+    // the device, element moduli): last_initialize_was_incremental() then returns true. Velocities are zeroed as in the
+    // reference; positions are the caller's.
     bool initialize(const Settings &settings_ = Settings());
+    // every energy term gets the material (youngs, poisson); strain limits of triangle terms are kept
+    void set_material(double youngs, double poisson);
     // Use a factor computed elsewhere instead of this library's nested-dissection LDL^T at the next initialize():
     // P A P^T = L D L^T with L strictly lower CSC (unit diagonal implied, rows ascending), perm[new] = old.
     // n = number of free vertices (factor of Ahat, A = Ahat (x) I3) or 3 x that (factor of the full system in the
@@ -280,6 +291,7 @@ public:
     aaadmm_ldlt *device_factor() { return m_ldlt; }
     aaadmm_tetscene *device_scene() { return m_scene; }
     const aaadmm::TetSystem &system() const { return m_sys; }
+    bool last_initialize_was_incremental() const { return reinitialized; }
 
     Settings m_settings;
 
@@ -291,6 +303,9 @@ protected:
     std::vector<std::shared_ptr<PassiveCollision>> m_obstacles;
     std::vector<double> m_x_pin;  // in the order set_pins received them (reference: m_x_pin)
     std::vector<int> positive_pin;
+    bool device_numeric = false;       // the factor's values were computed on the device (re-initialisation can refactor)
+    bool reinitialized = false;        // the last initialize() took the fast path (same structure, new moduli)
+    uint64_t m_structure_key = 0;      // hash of mesh, terms, pins, collision set of the last full initialize()
     bool factor_external = false;      // m_factor was handed in through set_external_factor
     bool factor_from_cache = false;    // the last initialize() took the factor from Settings::factor_cache
     std::vector<int> slot_of_node;  // index among the free nodes (positive_pin) or among the pinned ones

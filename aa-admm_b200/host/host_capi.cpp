@@ -279,6 +279,23 @@ void *aaadmm_host_system_new(const float *verts, int n_verts, const int *tets, i
         return nullptr;
     }
 }
+// update_tet_system_materials on the handle: another (uniform) material and rho dt^2 on the same mesh
+int aaadmm_host_system_update(void *h, double youngs, double poisson, double rho_dt2) {
+    HOST_TRY
+    aaadmm::TetSystem &S = static_cast<SystemHandle *>(h)->S;
+    std::vector<double> ey(std::max(S.n_tets, 1), youngs), ep(std::max(S.n_tets, 1), poisson);
+    std::vector<double> ty(std::max(S.n_tris, 1), youngs), tp(std::max(S.n_tris, 1), poisson);
+    aaadmm::TriInput ti;
+    ti.n_tris = S.n_tris;
+    ti.youngs = ty.data();
+    ti.poisson = tp.data();
+    if (!aaadmm::update_tet_system_materials(S, ey.data(), ep.data(), rho_dt2, &ti)) {
+        g_err = S.error;
+        return -1;
+    }
+    return 0;
+    HOST_CATCH
+}
 void aaadmm_host_system_free(void *h) { delete static_cast<SystemHandle *>(h); }
 int aaadmm_host_system_counts(void *h, int *n_free, int64_t *nnz) {
     const aaadmm::TetSystem &S = static_cast<SystemHandle *>(h)->S;
@@ -398,6 +415,20 @@ int aaadmm_host_solver_set_factor(void *h, int n, const int64_t *Lp, const int *
     static_cast<SolverHandle *>(h)->solver.set_external_factor(n, Lp, Li, Lx, D, perm);
     return 0;
     HOST_CATCH
+}
+int aaadmm_host_solver_set_material(void *h, double youngs, double poisson) {
+    HOST_TRY
+    static_cast<SolverHandle *>(h)->solver.set_material(youngs, poisson);
+    return 0;
+    HOST_CATCH
+}
+int aaadmm_host_solver_set_x(void *h, const double *x) {
+    admm::Solver &s = static_cast<SolverHandle *>(h)->solver;
+    memcpy(s.m_x.data(), x, s.m_x.size() * sizeof(double));
+    return 0;
+}
+int aaadmm_host_solver_was_incremental(void *h) {
+    return static_cast<SolverHandle *>(h)->solver.last_initialize_was_incremental() ? 1 : 0;
 }
 int aaadmm_host_solver_step(void *h) {
     HOST_TRY

@@ -76,6 +76,61 @@ bool tet_constants(const double *rest12, double youngs, double poisson, double *
     return true;
 }
 
+// Every contribution to the lower triangle of Ahat = M + rho dt^2 sum_t w_t^2 G_t^T G_t (+ triangle and collision
+// terms) as (row, column, value), in ONE fixed order: masses, tets, triangles, collision terms.
+// G_t(r,c) = sum_k Sel(c,k) Binv(k,r).
+template <typename F>
+static void for_each_contribution(const TetSystem &S, double rho_dt2, F emit) {
+    const int nf = S.n_free, n_tets = S.n_tets, n_tris = S.n_tris, n_pts = S.n_pts;
+    for (int v = 0; v < nf; ++v) emit(v, v, S.mass_free[v]);
+    for (int t = 0; t < n_tets; ++t) {
+        const double *bi = &S.binv[9 * (size_t)t];
+        double G[3][4];
+        for (int r = 0; r < 3; ++r) {
+            // Binv column-major: Binv(k,r) = bi[r*3+k]
+            G[r][1] = bi[r * 3 + 0];
+            G[r][2] = bi[r * 3 + 1];
+            G[r][3] = bi[r * 3 + 2];
+            G[r][0] = -G[r][1] - G[r][2] - G[r][3];
+        }
+        const double w = S.weight[t];
+        for (int a = 0; a < 4; ++a) {
+            const int va = S.tet_dev[4 * (size_t)t + a];
+            if (va >= nf) continue;
+            for (int b = 0; b <= a; ++b) {
+                const int vb = S.tet_dev[4 * (size_t)t + b];
+                if (vb >= nf) continue;
+                double s = 0;
+                for (int r = 0; r < 3; ++r) s += (rho_dt2 * (w * G[r][a])) * (w * G[r][b]);
+                emit(std::max(va, vb), std::min(va, vb), s);
+            }
+        }
+    }
+    // triangles: F(:,c) = sum_a Dc(a,c) x_a, Dc = S * rest_pose (hard/src/TriEnergyTerm.cpp:59-72)
+    for (int t = 0; t < n_tris; ++t) {
+        const double *rp = &S.tri_binv[4 * (size_t)t];  // R(k,c) = rp[c*2+k]
+        double G[2][3];
+        for (int c = 0; c < 2; ++c) {
+            G[c][1] = rp[c * 2 + 0];
+            G[c][2] = rp[c * 2 + 1];
+            G[c][0] = -G[c][1] - G[c][2];
+        }
+        const double w = S.tri_weight[t];
+        for (int a = 0; a < 3; ++a) {
+            const int va = S.tri_dev[3 * (size_t)t + a];
+            if (va >= nf) continue;
+            for (int b = 0; b <= a; ++b) {
+                const int vb = S.tri_dev[3 * (size_t)t + b];
+                if (vb >= nf) continue;
+                double s = 0;
+                for (int c = 0; c < 2; ++c) s += (rho_dt2 * (w * G[c][a])) * (w * G[c][b]);
+                emit(std::max(va, vb), std::min(va, vb), s);
+            }
+        }
+    }
+    for (int i = 0; i < n_pts; ++i) emit(S.pt_dev[i], S.pt_dev[i], rho_dt2 * (S.pt_weight[i] * S.pt_weight[i]));
+}
+
 bool build_tet_system(TetSystem &S, int n_verts, const double *rest12, int n_tets, const int *tets,
                       const int *material, const double *youngs, const double *poisson,
                       const double *masses, const std::vector<int> &pinned, double rho_dt2, const TriInput *tri,
@@ -229,68 +284,56 @@ bool build_tet_system(TetSystem &S, int n_verts, const double *rest12, int n_tet
     tr.reserve((size_t)10 * n_tets + nf);
     tc.reserve((size_t)10 * n_tets + nf);
     tv.reserve((size_t)10 * n_tets + nf);
-    for (int v = 0; v < nf; ++v) {
-        tr.push_back(v);
-        tc.push_back(v);
-        tv.push_back(S.mass_free[v]);
-    }
-    for (int t = 0; t < n_tets; ++t) {
-        const double *bi = &S.binv[9 * (size_t)t];
-        double G[3][4];
-        for (int r = 0; r < 3; ++r) {
-            // Binv column-major: Binv(k,r) = bi[r*3+k]
-            G[r][1] = bi[r * 3 + 0];
-            G[r][2] = bi[r * 3 + 1];
-            G[r][3] = bi[r * 3 + 2];
-            G[r][0] = -G[r][1] - G[r][2] - G[r][3];
-        }
-        const double w = S.weight[t];
-        for (int a = 0; a < 4; ++a) {
-            const int va = S.tet_dev[4 * (size_t)t + a];
-            if (va >= nf) continue;
-            for (int b = 0; b <= a; ++b) {
-                const int vb = S.tet_dev[4 * (size_t)t + b];
-                if (vb >= nf) continue;
-                double s = 0;
-                for (int r = 0; r < 3; ++r) s += (rho_dt2 * (w * G[r][a])) * (w * G[r][b]);
-                int rr = std::max(va, vb), cc = std::min(va, vb);
-                tr.push_back(rr);
-                tc.push_back(cc);
-                tv.push_back(s);
-            }
-        }
-    }
-    // triangles: F(:,c) = sum_a Dc(a,c) x_a, Dc = S * rest_pose (hard/src/TriEnergyTerm.cpp:59-72)
-    for (int t = 0; t < n_tris; ++t) {
-        const double *rp = &S.tri_binv[4 * (size_t)t];  // R(k,c) = rp[c*2+k]
-        double G[2][3];
-        for (int c = 0; c < 2; ++c) {
-            G[c][1] = rp[c * 2 + 0];
-            G[c][2] = rp[c * 2 + 1];
-            G[c][0] = -G[c][1] - G[c][2];
-        }
-        const double w = S.tri_weight[t];
-        for (int a = 0; a < 3; ++a) {
-            const int va = S.tri_dev[3 * (size_t)t + a];
-            if (va >= nf) continue;
-            for (int b = 0; b <= a; ++b) {
-                const int vb = S.tri_dev[3 * (size_t)t + b];
-                if (vb >= nf) continue;
-                double s = 0;
-                for (int c = 0; c < 2; ++c) s += (rho_dt2 * (w * G[c][a])) * (w * G[c][b]);
-                tr.push_back(std::max(va, vb));
-                tc.push_back(std::min(va, vb));
-                tv.push_back(s);
-            }
-        }
-    }
-    for (int i = 0; i < n_pts; ++i) {
-        tr.push_back(S.pt_dev[i]);
-        tc.push_back(S.pt_dev[i]);
-        tv.push_back(rho_dt2 * (S.pt_weight[i] * S.pt_weight[i]));
-    }
+    for_each_contribution(S, rho_dt2, [&](int rr, int cc, double v) {
+        tr.push_back(rr);
+        tc.push_back(cc);
+        tv.push_back(v);
+    });
     S.Ahat = sym_from_triplets(nf, tr, tc, tv, false);
+    // where every contribution lands in Ahat.x (same emission order): update_tet_system_materials refills the values of
+    // another material on the same mesh without sorting anything
+    S.contrib_dst.resize(tr.size());
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < (int64_t)tr.size(); ++k) {
+        const int *b0 = S.Ahat.i.data() + S.Ahat.p[tc[k]], *b1 = S.Ahat.i.data() + S.Ahat.p[tc[k] + 1];
+        S.contrib_dst[k] = (int64_t)(std::lower_bound(b0, b1, tr[k]) - S.Ahat.i.data());
+    }
     return true;
+}
+
+bool update_tet_system_materials(TetSystem &S, const double *youngs, const double *poisson, double rho_dt2,
+                                 const TriInput *tri) {
+    for (int t = 0; t < S.n_tets; ++t) {
+        Lame lame(youngs[t], poisson[t]);
+        const double k = lame.bulk_modulus();
+        const double w = std::sqrt(k * S.volume[t]);  // tet_constants
+        if (!(w > 0.0)) {
+            S.error = "**EnergyTerm::get_reduction Error: Some weight leq 0";
+            return false;
+        }
+        S.weight[t] = w;
+        S.kvol[t] = k * S.volume[t];
+        S.mu[t] = lame.mu;
+        S.lambda[t] = lame.lambda;
+    }
+    for (int t = 0; t < S.n_tris; ++t) {
+        Lame lame(tri->youngs[t], tri->poisson[t]);
+        const double w = std::sqrt(lame.bulk_modulus() * S.tri_area[t]);  // tri_constants
+        if (!(w > 0.0)) {
+            S.error = "**EnergyTerm::get_reduction Error: Some weight leq 0";
+            return false;
+        }
+        S.tri_weight[t] = w;
+        if (tri->limit_min) S.tri_limit_min[t] = tri->limit_min[t];
+        if (tri->limit_max) S.tri_limit_max[t] = tri->limit_max[t];
+    }
+    // the same sums in the same order as sym_from_triplets forms them (duplicates are added in emission order)
+    std::fill(S.Ahat.x.begin(), S.Ahat.x.end(), 0.0);
+    int64_t k = 0;
+    double *x = S.Ahat.x.data();
+    const int64_t *dst = S.contrib_dst.data();
+    for_each_contribution(S, rho_dt2, [&](int, int, double v) { x[dst[k++]] += v; });
+    return k == (int64_t)S.contrib_dst.size();
 }
 
 }  // namespace aaadmm

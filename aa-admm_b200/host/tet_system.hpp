@@ -59,6 +59,7 @@ struct TetSystem {
     std::vector<int64_t> inc_ptr;
     std::vector<int> inc;
     SymLower Ahat;  // n_free x n_free
+    std::vector<int64_t> contrib_dst;  // per contribution (fixed emission order): its entry of Ahat.x
     std::string error;
 };
 
@@ -87,5 +88,11 @@ bool build_tet_system(TetSystem &S, int n_verts, const double *rest12, int n_tet
                       const int *material, const double *youngs, const double *poisson,
                       const double *masses, const std::vector<int> &pinned, double rho_dt2,
                       const TriInput *tri = nullptr, const PointInput *pts = nullptr);
+
+// Another material on the SAME mesh, pins and terms (a member of a material sweep): per-element weights / moduli and
+// the values of Ahat are recomputed in place - bit-identical to what build_tet_system gives for these inputs - while
+// numbering, incidence lists, B^-1 and the pattern of Ahat stay. youngs / poisson: per tet; tri: per triangle.
+bool update_tet_system_materials(TetSystem &S, const double *youngs, const double *poisson, double rho_dt2,
+                                 const TriInput *tri = nullptr);
 
 }  // namespace aaadmm

@@ -57,7 +57,7 @@ class ClockSampler:
 
     def _run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
         while not self.stop:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
@@ -77,7 +77,7 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
+        sm, mx, reasons, util = [], 0, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
@@ -86,10 +86,12 @@ class ClockSampler:
                 for n, v in zip(names, r[2:6]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
+                util.append(float(r[6]))
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "gpu_util_pct_mean": (sum(util) / len(util)) if util else None}
 
 
 def dist_env():
@@ -214,11 +216,12 @@ def _repo_libraries_loaded():
     return sorted(libs)
 
 
-def cpu_baseline_leg():
+def cpu_baseline_leg(sample=None, full_tets=None):
     """Bounded CPU sample run beside the GPU number (rank 0, N=1): about 20 s of the unmodified reference."""
     try:
         cores = _reference_host_threads()
-        s = CPU_SAMPLE
+        s = sample or CPU_SAMPLE
+        FULL = full_tets or FULL_TETS
         dt = WORKLOAD["dt"]
         r, scene, pidx, sample_tets, kind, setup_s = _reference_solver((s["cx"], s["cy"], s["cz"]), s["iters"], cores)
         if kind == "port":
@@ -232,14 +235,14 @@ def cpu_baseline_leg():
                 secs += time.perf_counter() - t0
                 iters += len(h)
         its = iters / secs
-        return {"value": its * sample_tets / FULL_TETS, "unit": "iterations/s", "cores": cores, "kind": kind,
+        return {"value": its * sample_tets / FULL, "unit": "iterations/s", "cores": cores, "kind": kind,
                 "measured": {"iterations_per_s": its, "tets": sample_tets},
                 "sample": ("unmodified reference" if kind == "reference" else "oracle/port C restatement of the reference") +
                           " hard_zxu Solver::step on beam %dx%dx%d (%d tets), 2 frames x %d iterations after 1 warm-up "
                           "frame: measured %.2f it/s at that size; `value` = that figure scaled linearly by tets to "
-                          "1,013,060 (the metric's size; favours the CPU); Eigen setup %.1f s excluded. The measured "
+                          "%d (the workload's scene size; favours the CPU); Eigen setup %.1f s excluded. The measured "
                           "same-run reference arm at a larger size is `bench.py --impl reference`" % (
-                              s["cx"], s["cy"], s["cz"], sample_tets, s["iters"], its, setup_s)}
+                              s["cx"], s["cy"], s["cz"], sample_tets, s["iters"], its, FULL, setup_s)}
     except Exception as e:  # the baseline is a report, never a reason to lose the GPU line
         return {"value": None, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "reference",
                 "sample": "failed: %r" % (e,)}
@@ -385,6 +388,123 @@ def run_gpu(args):
     return 0
 
 
+CFG5 = dict(scenes=64, cx=88, cy=22, cz=22, frames=1, admm_iters=100, anderson_m=5, slots=2)
+CFG5_CPU_SAMPLE = dict(cx=24, cy=22, cz=22, iters=10)
+
+
+def run_cfg5(args):
+    """BASELINE configs[4] (SURVEY 8e cfg 5): 64 independent scenes 88x22x22 (212,960 tets) with the material sweep of
+    aa_admm_b200.ensemble.scene_material, scene s on GPU s mod N, no data-path collective, one NCCL gather of the result
+    records. A bench step = ONE PASS over the whole ensemble (every scene: material -> system-matrix values -> numeric
+    LDL^T on the device -> one frame of <= 100 ADMM iterations). Per GPU `slots` scenes are resident and pipelined by
+    one host thread each. Strong scaling: the ensemble is fixed, N GPUs share it."""
+    rank, world, local = dist_env()
+    c = dict(CFG5)
+    if args.small:
+        c.update(scenes=8, cx=24, cy=6, cz=6)
+    c["slots"] = args.slots or c["slots"]
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(max(1, cores // (world * c["slots"])))
+    import aa_admm_b200 as A
+    from aa_admm_b200 import ensemble as E
+    if A.device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    dev = local if world > 1 else 0
+    A.set_device(dev)
+    dist = device = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        device = torch.device("cuda", local)
+        dist.init_process_group("nccl", device_id=device)
+    dims = (c["cx"], c["cy"], c["cz"])
+    mine = E.scenes_of_rank(c["scenes"], rank, world)
+    slots = [E.SceneSlot(A, dims, iters=c["admm_iters"], anderson_m=c["anderson_m"], device=dev) for _ in range(c["slots"])]
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    t0 = time.perf_counter()
+    recs, setups = E.run_sweep(A, dims, mine, slots, c["frames"], rank)   # first pass: includes the one-time analysis
+    first_pass_s = time.perf_counter() - t0
+    full_setup_ms = [ms for _, ms, inc in setups if not inc]
+    for _ in range(max(0, args.warmup - 1)):
+        E.run_sweep(A, dims, mine, slots, c["frames"], rank)
+    barrier()
+    iters = 0.0
+    loop_ms_sum = 0.0
+    inc_setup_ms = []
+    with ClockSampler(dev) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            recs, setups = E.run_sweep(A, dims, mine, slots, c["frames"], rank)
+            iters += recs[:, 1].sum()
+            loop_ms_sum += recs[:, 5].sum()
+            inc_setup_ms += [ms for _, ms, inc in setups if inc]
+        barrier()
+        wall_s = time.perf_counter() - t0
+    loop_ms = float(loop_ms_sum) / max(1, len(slots))  # device time of the loops per resident-scene slot (the slots overlap)
+    table = E.gather_records(recs, dist, device)  # the only collective: per-scene result records of the last pass
+    tot_iters, max_wall, max_loop = iters, wall_s, loop_ms
+    if dist is not None:
+        import torch
+        t = torch.tensor([iters, wall_s, loop_ms], dtype=torch.float64, device="cuda")
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        g = torch.stack(g).cpu()
+        tot_iters, max_wall, max_loop = float(g[:, 0].sum()), float(g[:, 1].max()), float(g[:, 2].max())
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    s0 = slots[0].solver
+    info = s0.info()
+    peak, peak_src = measured_peaks()
+    prof = s0.profile(20, c["anderson_m"], True)
+    phases = {k: v for k, v in prof.items() if k != "total" and v["ms"] > 0}
+    dom = max(phases, key=lambda k: phases[k]["ms"])
+    ach = phases[dom]["bytes"] / (phases[dom]["ms"] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "peak_source": peak_src, "note": "one scene alone on the device (profile of slot 0); in the timed passes the loops of the resident scenes overlap",
+            "phases": {k: {"ms": round(v["ms"], 4), "algo_GB": round(v["bytes"] / 1e9, 4),
+                           "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)} for k, v in phases.items()}}
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        with _NativeStdoutToStderr():
+            cpu = cpu_baseline_leg(CFG5_CPU_SAMPLE, c["cx"] * c["cy"] * c["cz"] * 5)
+    n_free, n_pin = info["n_free"], len(slots[0].pidx)
+    scenes_timed = c["scenes"] * args.steps
+    line = {"metric": "admm_anderson_iterations_per_sec_ensemble", "value": tot_iters / (max_loop * 1e-3), "unit": "iterations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * max_wall / max(1, args.steps),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg5: ensemble of %d independent scenes, beam %dx%dx%d = %d tets each, material sweep E = 1e6..1e8, "
+                                   "nu = 0.30..0.44, hard_zxu ordering, Anderson m=%d, %d frame(s) x <= %d ADMM iterations per scene; scene s on "
+                                   "GPU s mod N, %d resident scenes (host threads) per GPU; one step = one pass over the ensemble, per-scene "
+                                   "numeric setup (system-matrix values, numeric LDL^T on the device, moduli) inside the timed region"
+                                   % (c["scenes"], *dims, info["n_tets"], c["anderson_m"], c["frames"], c["admm_iters"], c["slots"]),
+                       "l2": "two resident scenes of 0.6 GB each per GPU: larger than the 126 MB L2",
+                       "iterations_timed": tot_iters, "scenes_timed": scenes_timed,
+                       "first_pass_s": round(first_pass_s, 3), "full_setup_ms_per_slot": [round(x, 1) for x in full_setup_ms],
+                       "incremental_setup_ms_mean": round(sum(inc_setup_ms) / max(1, len(inc_setup_ms)), 2)},
+            "scenes_per_s": scenes_timed / max_wall,
+            "value_definition": "iterations / device time of the ADMM loops (CUDA events per frame, summed per resident-scene slot, max over ranks)",
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": tot_iters / max_wall, "unit": "iterations/s",
+                    "definition": "iterations / wall time of the timed passes: per scene Solver::set_material + initialize() (values, H2D of the "
+                                  "matrix, numeric factorisation) + set_pins + step() with host buffers",
+                    "h2d_bytes_per_step": int(len(mine) * (8 * 3 * (n_free + n_pin) + 8 * 3.7e6)), "d2h_bytes_per_step": int(len(mine) * 8 * 3 * n_free)},
+            "gpu_launches": int(len(mine) * args.steps * (info["kernel_launches"] + 60)), "clocks": clk.summary(),
+            "records_last_pass": {"fields": list(E.RECORD_FIELDS), "rows": table.tolist()}}
+    _emit(line)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 NCU_LDLT_TRAFFIC_BYTES = 2.232e9
 
 
@@ -412,11 +532,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--small", action="store_true", help="30,720-tet beam (debugging only; not a bench number)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", default="cfg4", choices=["cfg4", "cfg5"],
+                    help="cfg4 (default, the headline): one 1M-tet beam; cfg5: ensemble of 64 x 213k-tet scenes (material sweep)")
+    ap.add_argument("--slots", type=int, default=0, help="cfg5: resident scenes (host threads) per GPU (default 2)")
     ap.add_argument("--ref-dims", type=int, nargs=3, default=None,
                     help="--impl reference: beam size of the CPU arm (default REF_ARM; smaller sizes are for the CPU test)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "cfg5":
+        return run_cfg5(args)
     return run_gpu(args)
 
 

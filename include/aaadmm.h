@@ -153,6 +153,13 @@ typedef struct {
  * order 3*vertex + axis, e.g. Eigen::SimplicialLDLT's own matrixL / vectorD / permutationP (LinearSolver.hpp:79-84). */
 int aaadmm_tetscene_create(aaadmm_tetscene **out, const aaadmm_tetscene_desc *desc, aaadmm_ldlt *factor);
 int aaadmm_tetscene_destroy(aaadmm_tetscene *s);
+/* Another material on the same scene (a member of a material sweep; the factor object is refreshed separately with
+ * aaadmm_ldlt_refactor): per-tet weight / K vol / mu / lambda (n_tets each; mu, lambda may be NULL for linear scenes),
+ * per-triangle weight and strain limits (NULL when the scene has no triangles) and rho_dt2. Nothing is allocated;
+ * element connectivity, rest shapes, incidence lists and all state buffers stay. */
+int aaadmm_tetscene_update_material(aaadmm_tetscene *s, const double *weight, const double *kvol, const double *mu,
+                                    const double *lambda, const double *tri_weight, const double *tri_limit_min,
+                                    const double *tri_limit_max, double rho_dt2);
 /* One time step of the ADMM loop.
  *   x_bar   3*n_free  predicted free positions x + dt v (host)
  *   x_pin   3*(n_verts-n_free) pinned positions (host)

@@ -52,6 +52,8 @@ int aaadmm_host_mesh_save(void *h, const char *path);
 void *aaadmm_host_system_new(const float *verts, int n_verts, const int *tets, int n_tets, const int *tris, int n_tris,
                              const float *masses, double youngs, double poisson, const int *pins, int n_pins,
                              double rho_dt2, const int *collision_verts, int n_collisions);
+/* another uniform material / rho dt^2 on the same mesh: values only (update_tet_system_materials) */
+int aaadmm_host_system_update(void *h, double youngs, double poisson, double rho_dt2);
 void aaadmm_host_system_free(void *h);
 int aaadmm_host_system_counts(void *h, int *n_free, int64_t *nnz);
 int aaadmm_host_system_copy(void *h, int64_t *Ap, int *Ai, double *Ax, int *dev_to_vert);
@@ -84,6 +86,12 @@ int aaadmm_host_solver_initialize(void *h, double dt, int iters, double gravity,
  * vertices: factor of the full system in the reference's dof order, e.g. Eigen's own) instead of factoring itself. */
 int aaadmm_host_solver_set_factor(void *h, int n, const int64_t *Lp, const int *Li, const double *Lx, const double *D,
                                   const int *perm);
+/* Parameter sweeps on one Solver: set_material gives every energy term the Lame parameters (youngs, poisson), set_x
+ * overwrites the node positions (3 per node), and the next aaadmm_host_solver_initialize with unchanged mesh / pins /
+ * terms keeps the analysis and all device buffers and redoes the numeric part only (was_incremental() = 1). */
+int aaadmm_host_solver_set_material(void *h, double youngs, double poisson);
+int aaadmm_host_solver_set_x(void *h, const double *x);
+int aaadmm_host_solver_was_incremental(void *h);
 int aaadmm_host_solver_step(void *h);
 int aaadmm_host_solver_set_iters(void *h, int iters, int anderson_m, int accel);
 int aaadmm_host_solver_n_dof(void *h);

@@ -694,3 +694,91 @@ def test_device_factorisation_vs_host_factor(gpu, grid, leaf, nrhs):
     bad[:] = 0.0
     with pytest.raises(A.AaadmmError):
         dev.refactor(bad)
+
+
+def test_reinitialize_with_another_material_is_incremental_and_exact(gpu, ref):
+    """A material sweep on ONE Solver: set_material + initialize() on the unchanged scene keeps the
+    analysis and all device buffers and redoes the numeric part only (values of the system matrix, numeric LDL^T on the
+    device, element moduli). The frame that follows is bit-identical to the one a freshly built Solver computes for
+    that material, and matches the reference."""
+    from aa_admm_b200 import ensemble as E
+    dims, dt = (16, 4, 4), 1.0 / 30.0
+    scene = beam_arrays(gpu, *dims)
+    verts, tets, masses, pidx, ppts, pside = scene.arrays()
+    rest = verts.astype(np.float64).reshape(-1)
+    s = gpu.Solver()
+    s.add_tetmesh(verts, tets, masses, *E.scene_material(0), 0)
+    s.set_pins(pidx, ppts)
+    s.initialize(dt, 100, -9.8, 5, True, 1.0)
+    assert not s.was_incremental()
+    for k in (0, 63, 21, 0):
+        youngs, poisson = E.scene_material(k)
+        sc = beam_arrays(gpu, *dims)
+        s.set_material(youngs, poisson)
+        s.set_x(rest)
+        s.set_pins(pidx, ppts)
+        s.initialize(dt, 100, -9.8, 5, True, 1.0)
+        assert s.was_incremental()
+        s.set_pins(pidx, sc.stretch(dt))
+        h1, x1 = s.step(), s.x()
+        _, h2, x2 = run_product(gpu, beam_arrays(gpu, *dims), 1, m=5, accel=True, youngs=youngs, poisson=poisson)
+        assert np.array_equal(h1, h2[0]) and np.array_equal(x1, x2[0]), k
+        _, hr, xr = run_reference(ref, gpu, beam_arrays(gpu, *dims), 1, m=5, accel=True, youngs=youngs, poisson=poisson)
+        n = min(len(h1), len(hr[0]))
+        rel = np.abs(h1[:n, 1] - hr[0][:n, 2]) / hr[0][:n, 2]
+        print("scene material", k, "rows", len(h1), len(hr[0]), "rel8 %.2e" % rel[:8].max())
+        assert rel[:8].max() < 1e-9
+        assert np.abs(x1 - xr[0]).max() / np.abs(xr[0]).max() < 1e-6
+    # a changed pin set is a different structure: full initialisation again
+    s2 = gpu.Solver()
+    s2.add_tetmesh(verts, tets, masses, 1e7, 0.399, 0)
+    s2.set_pins(pidx[:-1], ppts[:-1])
+    s2.initialize(dt, 10, -9.8, 5, True, 1.0)
+    s2.initialize(dt, 10, -9.8, 5, True, 2.0)   # same structure, another penalty: incremental
+    assert s2.was_incremental()
+    s2.set_pins(pidx[:-1], ppts[:-1])
+    assert len(s2.step()) > 0
+
+
+def test_host_and_device_factorisation_give_the_same_frames(gpu):
+    """AAADMM_HOST_FACTOR (numeric LDL^T on the host cores, the round-1 path) against the default device-side numeric
+    factorisation: same ordering and pattern, values equal to round-off, trajectories equal over the first iterations."""
+    import os
+    _, hd, xd = run_product(gpu, beam_arrays(gpu, 16, 8, 8), 1, m=5, accel=True)
+    os.environ["AAADMM_HOST_FACTOR"] = "1"
+    try:
+        import subprocess, sys, json
+        code = ("import sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r); import aa_admm_b200 as A; "
+                "from scenes import beam_arrays, run_product; _, h, x = run_product(A, beam_arrays(A, 16, 8, 8), 1, m=5, accel=True); "
+                "print(json.dumps([h[0][:, 1].tolist(), x[0].tolist()]))") % (
+                    os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        comb_h, x_h = json.loads(r.stdout.strip().split("\n")[-1])
+    finally:
+        os.environ.pop("AAADMM_HOST_FACTOR", None)
+    comb_h, x_h = np.array(comb_h), np.array(x_h)
+    n = min(len(comb_h), len(hd[0]), 8)
+    rel = np.abs(hd[0][:n, 1] - comb_h[:n]) / comb_h[:n]
+    print("device vs host numeric factorisation, first 8 iterations %.2e" % rel.max())
+    assert rel.max() < 1e-9
+    assert np.abs(xd[0] - x_h).max() / np.abs(x_h).max() < 1e-6
+
+
+def test_pipelined_sweep_on_resident_scene_slots(gpu):
+    """ensemble.run_sweep: 7 members of the material sweep on 2 resident scene slots of one GPU (one host thread per
+    slot, incremental re-initialisation per member). Every record equals the one a freshly built Solver gives for that
+    scene - the pipelining changes when things run, not what is computed."""
+    from aa_admm_b200 import ensemble as E
+    dims = (12, 3, 3)
+    slots = [E.SceneSlot(gpu, dims, iters=60, anderson_m=5, device=0) for _ in range(2)]
+    ids = [0, 9, 18, 27, 36, 45, 63]
+    for _pass in range(2):
+        recs, setups = E.run_sweep(gpu, dims, ids, slots, frames=1, rank=0)
+        assert sorted(int(r[0]) for r in recs) == ids
+        assert sum(1 for _, _, inc in setups if not inc) == (2 if _pass == 0 else 0)  # one full setup per slot, once
+        for r in recs:
+            youngs, poisson = E.scene_material(int(r[0]))
+            _, h, _ = run_product(gpu, beam_arrays(gpu, *dims), 1, iters=60, m=5, accel=True, youngs=youngs, poisson=poisson)
+            assert int(r[1]) == len(h[0]) and int(r[2]) == int(h[0][:, 2].sum())
+            assert r[3] == h[0][-1, 0] and r[4] == h[0][-1, 1]

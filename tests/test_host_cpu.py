@@ -452,3 +452,45 @@ def test_bench_reference_arm_prints_one_json_line():
     if d["cpu_baseline"]["kind"] == "reference":
         assert d["cpu_baseline"]["cores"] == os.cpu_count()
     assert d["native_so_loaded"] and all(l.startswith("oracle/") for l in d["native_so_loaded"]), d["native_so_loaded"]
+
+
+def test_material_update_of_the_system_matrix_is_bit_identical(A):
+    """update_tet_system_materials (the values-only path a re-initialisation of a Solver takes for the next member of a
+    material sweep) gives bit for bit the matrix a fresh build_tet_system gives for that material: tets + triangles +
+    collision terms, another material AND another rho dt^2."""
+    from scenes import cloth_arrays
+    H = A.host_lib()
+    H.aaadmm_host_system_update.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+    verts, tris, masses, pins = cloth_arrays(5)
+    bv, bt, bm, bp, _, _ = A.BeamScene().add(5, 2, 3, -1.75).arrays()
+    tets = (bt + len(verts)).astype(np.int32)
+    allv = np.concatenate([verts, bv]).astype(np.float32)
+    allm = np.concatenate([masses, bm]).astype(np.float32)
+    pidx = np.array(list(pins) + [int(p) + len(verts) for p in bp], np.int32)
+    col = np.array([len(verts) + 7, len(verts) + 9], np.int32)
+    col = np.array([c for c in col if c not in set(pidx.tolist())], np.int32)
+
+    def build(youngs, poisson, rho_dt2):
+        h = H.aaadmm_host_system_new(allv.ctypes.data_as(A.c_fp), len(allv), tets.ctypes.data_as(A.c_ip), len(tets),
+                                     tris.ctypes.data_as(A.c_ip), len(tris), allm.ctypes.data_as(A.c_fp), youngs, poisson,
+                                     pidx.ctypes.data_as(A.c_ip), len(pidx), rho_dt2, col.ctypes.data_as(A.c_ip), len(col))
+        assert h
+        return C.c_void_p(h)
+
+    def values(h):
+        nf, nnz = C.c_int(0), C.c_int64(0)
+        H.aaadmm_host_system_counts(h, C.byref(nf), C.byref(nnz))
+        Ap, Ai, Ax = np.zeros(nf.value + 1, np.int64), np.zeros(nnz.value, np.int32), np.zeros(nnz.value)
+        d2v = np.zeros(len(allv), np.int32)
+        H.aaadmm_host_system_copy(h, Ap.ctypes.data_as(A.c_lp), Ai.ctypes.data_as(A.c_ip), Ax.ctypes.data_as(A.c_dp),
+                                  d2v.ctypes.data_as(A.c_ip))
+        return Ap, Ai, Ax
+
+    h0 = build(1e7, 0.399, 1.0 / 900.0)
+    for youngs, poisson, rho_dt2 in ((1e6, 0.30, 1.0 / 900.0), (3.7e8, 0.44, 2.5 / 576.0), (1e7, 0.399, 1.0 / 900.0)):
+        assert H.aaadmm_host_system_update(h0, youngs, poisson, rho_dt2) == 0
+        h1 = build(youngs, poisson, rho_dt2)
+        for a, b in zip(values(h0), values(h1)):
+            assert np.array_equal(a, b)
+        H.aaadmm_host_system_free(h1)
+    H.aaadmm_host_system_free(h0)
