@@ -685,6 +685,124 @@ k_invert_fronts(const int2 *__restrict__ tasks, const FrontDesc *__restrict__ fr
     }
 }
 
+// ---- blocked inverse of the unit-lower diagonal blocks (replaces the row-serial k_invert_fronts for everything but the
+// 64 x 64 blocks on the diagonal): X = T^-1 by block distance r = i - j,
+//     X(i,i) = T(i,i)^-1,      X(i,j) = -X(i,i) * sum_{k=j}^{i-1} T(i,k) X(k,j)   (i > j),
+// every block at distance r depends on blocks of smaller distance in its own block column only: one launch per
+// distance over all fronts, each CTA one 64 x 64 block (two chained products, 4 x 4 outputs per thread). The critical
+// path of a 2,888-column front is 45 launches instead of 4 M dependent iterations of one thread.
+constexpr int IB = 64;
+__global__ void __launch_bounds__(IB)
+k_invert_diag_blocks(const int2 *__restrict__ tasks, const FrontDesc *__restrict__ fronts, const double *__restrict__ A,
+                     double *__restrict__ M) {
+    __shared__ double Ts[IB][IB + 1];
+    const int2 task = tasks[blockIdx.x];
+    const FrontDesc F = fronts[task.x];
+    const int d0 = task.y * IB, nb = min(IB, F.ns - d0);
+    const double *T = A + F.m_off + (size_t)d0 * F.ld + d0;
+    double *X = M + F.m_off + (size_t)d0 * F.ld + d0;
+    const int i = threadIdx.x;
+    for (int c = 0; c < nb; ++c) Ts[i][c] = (i < nb && i > c) ? T[(size_t)c * F.ld + i] : 0.0;
+    __syncthreads();
+    if (i >= nb) return;
+    // row i of X from X T = I: X(i,j) = -sum_{k=j+1..i} X(i,k) T(k,j); the row lives in this thread's registers
+    double x[IB];
+#pragma unroll
+    for (int j = 0; j < IB; ++j) x[j] = j == i ? 1.0 : 0.0;
+#pragma unroll
+    for (int j = IB - 2; j >= 0; --j) {
+        if (j < i) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = j + 1; k < IB; ++k)
+                if (k <= i) s += x[k] * Ts[k][j];
+            x[j] = -s;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < IB; ++j)
+        if (j <= i) X[(size_t)j * F.ld + i] = x[j];
+}
+
+__global__ void __launch_bounds__(256)
+k_invert_offdiag(const int2 *__restrict__ tasks, int r, const FrontDesc *__restrict__ fronts, const double *__restrict__ A,
+                 double *__restrict__ M) {
+    extern __shared__ __align__(16) double ism[];
+    double (*As)[IB + 1] = reinterpret_cast<double (*)[IB + 1]>(ism);                   // sum_k T(i,k) X(k,j)
+    double (*Xd)[IB + 1] = reinterpret_cast<double (*)[IB + 1]>(ism + IB * (IB + 1));   // X(i,i); staging before
+    double (*Ps)[IB + 1] = Xd;                                                          // [16][65] rows of T(i, .)
+    double (*Ls)[IB + 1] = reinterpret_cast<double (*)[IB + 1]>(ism + IB * (IB + 1) + 16 * (IB + 1));  // [16][65] X(., j)
+    const int2 task = tasks[blockIdx.x];
+    const FrontDesc F = fronts[task.x];
+    const int jb = task.y, ib = jb + r;
+    const int i0 = ib * IB, j0 = jb * IB;
+    const double *T = A + F.m_off;
+    double *X = M + F.m_off;
+    const int tr = threadIdx.x & 15, tj = threadIdx.x >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int t0 = j0; t0 < i0; t0 += 16) {
+        for (int e = threadIdx.x; e < 16 * IB; e += 256) {
+            const int tt = e >> 6, q = e & 63;
+            Ps[tt][q] = (i0 + q < F.ns) ? T[(size_t)(t0 + tt) * F.ld + i0 + q] : 0.0;   // T(i0 + q, t0 + tt)
+        }
+        for (int e = threadIdx.x; e < 16 * IB; e += 256) {
+            const int c = e >> 4, tt = e & 15;
+            Ls[tt][c] = X[(size_t)(j0 + c) * F.ld + t0 + tt];                          // X(t0 + tt, j0 + c)
+        }
+        __syncthreads();
+#pragma unroll
+        for (int tt = 0; tt < 16; ++tt) {
+            double p[4], l[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) p[a] = Ps[tt][tr + 16 * a];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) l[b] = Ls[tt][tj + 16 * b];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] += p[a] * l[b];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) As[tr + 16 * a][tj + 16 * b] = acc[a][b];
+    for (int e = threadIdx.x; e < IB * IB; e += 256) {
+        const int c = e >> 6, q = e & 63;   // X(i0 + q, i0 + c)
+        Xd[q][c] = (i0 + q < F.ns && i0 + c < F.ns && q >= c) ? X[(size_t)(i0 + c) * F.ld + i0 + q] : 0.0;
+    }
+    __syncthreads();
+    // X(i,j) = -X(i,i) * As
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 8
+    for (int t = 0; t < IB; ++t) {
+        double p[4], l[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) p[a] = Xd[tr + 16 * a][t];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) l[b] = As[t][tj + 16 * b];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] += p[a] * l[b];
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int q = i0 + tr + 16 * a, c = j0 + tj + 16 * b;
+            if (q < F.ns) X[(size_t)c * F.ld + q] = -acc[a][b];
+        }
+}
+
 // Q = P * Linv: P = rows ns.. of A, Linv = rows 0..ns of M, Q -> rows ns.. of M. 64 x 64 tile per CTA,
 // 4 x 4 outputs per thread, 16-deep shared-memory stages.
 __global__ void __launch_bounds__(256)
@@ -775,6 +893,8 @@ void ldlt_dev_destroy(LdltDev *f) {
     cudaFree(f->Va);
     cudaFree(f->trace);
     cudaFree(f->inv_tasks);
+    cudaFree(f->invd_tasks);
+    cudaFree(f->invo_tasks);
     cudaFree(f->q_tasks);
     cudaFree(f->tile_src);
     cudaFree(f->A);
@@ -788,7 +908,17 @@ namespace {
 // [Linv ; Q] of every front from its [T ; P] (f->A) and the two sweep-ordered copies Mf / Mb; on `s`.
 int finish_numeric(LdltDev *f, cudaStream_t s) {
     AAADMM_CUDA_OK(cudaMemsetAsync(f->M, 0, (size_t)std::max<int64_t>(f->m_tot, 1) * sizeof(double), s));
-    if (f->n_inv_tasks > 0) k_invert_fronts<<<f->n_inv_tasks, 128, 0, s>>>(f->inv_tasks, f->fronts, f->A, f->M);
+    static const bool serial_inverse = getenv("AAADMM_INV_SERIAL") != nullptr;  // the row-serial kernel (experiments)
+    if (serial_inverse) {
+        if (f->n_inv_tasks > 0) k_invert_fronts<<<f->n_inv_tasks, 128, 0, s>>>(f->inv_tasks, f->fronts, f->A, f->M);
+    } else {
+        if (f->n_invd_tasks > 0) k_invert_diag_blocks<<<f->n_invd_tasks, IB, 0, s>>>(f->invd_tasks, f->fronts, f->A, f->M);
+        const size_t ism = sizeof(double) * 2 * IB * (IB + 1);
+        for (size_t r = 1; r < f->invo_off.size(); ++r) {
+            const int cnt = f->invo_off[r] - f->invo_off[r - 1];
+            if (cnt > 0) k_invert_offdiag<<<cnt, 256, ism, s>>>(f->invo_tasks + f->invo_off[r - 1], (int)r, f->fronts, f->A, f->M);
+        }
+    }
     if (f->n_q_tasks > 0) k_front_q<<<f->n_q_tasks, 256, 0, s>>>(f->q_tasks, f->fronts, f->A, f->M);
     if (f->n_ftasks > 0) k_make_tiles<<<f->n_ftasks, 256, 0, s>>>(f->tasks, f->tile_src, f->M, f->Mf);
     if (f->n_btasks > 0) k_make_btiles<<<f->n_btasks, 256, 0, s>>>(f->tasks + f->n_ftasks, f->tile_src + f->n_ftasks, f->M, f->Mb);
@@ -1274,6 +1404,28 @@ static int build(LdltDev **out, int n, const int64_t *Lp, const int *Li, const d
         }
         f->n_inv_tasks = (int)inv_tasks.size();
         f->n_q_tasks = (int)q_tasks.size();
+        // blocked inverse: diagonal blocks, then the off-diagonal blocks by block distance
+        std::vector<int2> invd, invo;
+        int max_nbk = 0;
+        for (int b = 0; b < nb; ++b) {
+            const int nbk = (fr[b].ns + IB - 1) / IB;
+            max_nbk = std::max(max_nbk, nbk);
+            for (int d = 0; d < nbk; ++d) invd.push_back(make_int2(b, d));
+        }
+        f->invo_off.assign(1, 0);
+        for (int r = 1; r < max_nbk; ++r) {
+            for (int b = 0; b < nb; ++b) {
+                const int nbk = (fr[b].ns + IB - 1) / IB;
+                for (int j = 0; j + r < nbk; ++j) invo.push_back(make_int2(b, j));
+            }
+            f->invo_off.push_back((int)invo.size());
+        }
+        f->n_invd_tasks = (int)invd.size();
+        cudaFuncSetAttribute(k_invert_offdiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 2 * IB * (IB + 1)));
+        if (upload(&f->invd_tasks, invd) || upload(&f->invo_tasks, invo)) {
+            ldlt_dev_destroy(f);
+            return -1;
+        }
         if (upload(&f->inv_tasks, inv_tasks) || upload(&f->q_tasks, q_tasks) || upload(&f->tile_src, tile_src)) {
             ldlt_dev_destroy(f);
             return -1;
@@ -1340,11 +1492,29 @@ int ldlt_dev_refactor(LdltDev *f, const double *Ax, cudaStream_t stream) {
         set_last_error("ldlt refactor: this factor was not created from a matrix");
         return -1;
     }
+    static const bool trace = getenv("AAADMM_SETUP_TRACE") != nullptr;  // setup telemetry: device times of the numeric phases
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (trace)
+        for (auto &e : ev) cudaEventCreate(&e);
+    if (trace) cudaEventRecord(ev[0], stream);
     AAADMM_CUDA_OK(cudaMemcpyAsync(factor_plan_values(f->plan), Ax, sizeof(double) * (size_t)factor_plan_nnz(f->plan),
                                    cudaMemcpyHostToDevice, stream));
+    if (trace) cudaEventRecord(ev[1], stream);
     if (factor_plan_run(f->plan, f->A, f->D, f->dinv, stream)) return -1;
+    if (trace) cudaEventRecord(ev[2], stream);
     if (finish_numeric(f, stream)) return -1;
-    return factor_plan_check(f->plan, stream);
+    if (trace) cudaEventRecord(ev[3], stream);
+    const int rc = factor_plan_check(f->plan, stream);
+    if (trace) {
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, ev[0], ev[1]);
+        cudaEventElapsedTime(&b, ev[1], ev[2]);
+        cudaEventElapsedTime(&c, ev[2], ev[3]);
+        fprintf(stderr, "[setup]   device numeric: matrix H2D %.2f ms, multifrontal LDL^T %.2f ms (%d launches), [Linv ; Q] + sweep copies %.2f ms\n",
+                a, b, factor_plan_launches(f->plan), c);
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
+    return rc;
 }
 
 int ldlt_dev_create_from_matrix(LdltDev **out, int n, const int64_t *Ap, const int *Ai, const double *Ax, const int64_t *Lp,

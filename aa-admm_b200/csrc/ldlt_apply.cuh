@@ -74,6 +74,9 @@ struct LdltDev {
     int2 *inv_tasks = nullptr;   // (front, first row) per 128 rows of a diagonal block
     int4 *q_tasks = nullptr;     // (front, first row, first column) per 64 x 64 tile of Q
     int n_inv_tasks = 0, n_q_tasks = 0;
+    int2 *invd_tasks = nullptr, *invo_tasks = nullptr;  // blocked inverse: (front, diagonal block) / (front, block column) by distance
+    int n_invd_tasks = 0;
+    std::vector<int> invo_off;   // first task of block distance r + 1
     int64_t *tile_src = nullptr; // per task: offset of its front matrix in M
     double *A = nullptr;         // front matrices [T ; P] (only kept by factors created from a matrix)
     double *D = nullptr;         // pivots

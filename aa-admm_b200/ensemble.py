@@ -72,10 +72,11 @@ class SceneSlot:
             self.solver.set_material(youngs, poisson)
             self.solver.set_x(self.rest)
         s = self.solver
-        s.set_pins(self.pidx, self.ppts)
+        # the sample's call sequence (beams.cpp: stretch_beams before initialize and at the start of every frame)
+        p = self._pins_of_frame(self.ppts.copy())
+        s.set_pins(self.pidx, p)
         s.initialize(self.dt, self.iters, -9.8, self.m, True, self.penalty, A.ORDER_HARD_ZXU)
         t1 = time.perf_counter()
-        p = self.ppts.copy()
         iters = rejects = 0
         loop_ms = 0.0
         last = None
