@@ -833,3 +833,104 @@ def geo_closest_points(V, F, Q):
     tri = np.zeros(len(Q), np.int32)
     _ck(L.aaadmm_geo_closest_points(_dp(V), len(V), _ip(F), len(F), _dp(Q), len(Q), _dp(Cp), _ip(tri)))
     return Cp, tri
+
+
+# ---------------------------------------------------------------------------------------------
+# Geometry front-end (host/GeometryApps.hpp)
+# ---------------------------------------------------------------------------------------------
+class PolyMesh:
+    """Polygon mesh numbered as OpenMesh numbers it (vertices / faces in file order, edges by first appearance)."""
+
+    def __init__(self, handle):
+        self.H = host_lib()
+        self.h = C.c_void_p(handle)
+
+    @staticmethod
+    def _lib():
+        H = host_lib()
+        if not getattr(H, "_poly_ready", False):
+            vp = C.c_void_p
+            H.aaadmm_host_polymesh_load.restype = vp
+            H.aaadmm_host_polymesh_load.argtypes = [C.c_char_p]
+            H.aaadmm_host_polymesh_new.restype = vp
+            H.aaadmm_host_polymesh_new.argtypes = [c_dp, C.c_int, c_ip, c_ip, C.c_int]
+            H.aaadmm_host_polymesh_free.argtypes = [vp]
+            H.aaadmm_host_polymesh_save.argtypes = [vp, C.c_char_p]
+            H.aaadmm_host_polymesh_counts.argtypes = [vp, c_ip, c_dp]
+            H.aaadmm_host_polymesh_copy.argtypes = [vp, c_dp, c_ip, c_ip, c_ip]
+            H.aaadmm_host_polymesh_subdivide_and_smooth.restype = vp
+            H.aaadmm_host_polymesh_subdivide_and_smooth.argtypes = [vp]
+            H.aaadmm_host_geoapp_optimize.argtypes = [C.c_int, vp, vp, C.c_int, C.c_int, c_dp, c_dp, c_ip, c_dp, c_dp]
+            H._poly_ready = True
+        return H
+
+    @classmethod
+    def load(cls, path):
+        H = cls._lib()
+        h = H.aaadmm_host_polymesh_load(str(path).encode())
+        if not h:
+            raise AaadmmError(H.aaadmm_host_last_error().decode())
+        return cls(h)
+
+    @classmethod
+    def from_arrays(cls, verts, faces):
+        """faces: list of vertex-id lists (or an (n, k) array; -1 pads shorter faces)."""
+        H = cls._lib()
+        verts = np.ascontiguousarray(verts, np.float64).reshape(-1, 3)
+        fl = [[int(i) for i in f if i >= 0] for f in faces]
+        ptr = np.zeros(len(fl) + 1, np.int32)
+        ptr[1:] = np.cumsum([len(f) for f in fl])
+        idx = np.array([i for f in fl for i in f], np.int32)
+        h = H.aaadmm_host_polymesh_new(_dp(verts), len(verts), _ip(ptr), _ip(idx), len(fl))
+        if not h:
+            raise AaadmmError(H.aaadmm_host_last_error().decode())
+        return cls(h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.H.aaadmm_host_polymesh_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def counts(self):
+        c = np.zeros(4, np.int32)
+        el = C.c_double(0.0)
+        _hk(self.H.aaadmm_host_polymesh_counts(self.h, _ip(c), C.byref(el)))
+        return dict(vertices=int(c[0]), faces=int(c[1]), corners=int(c[2]), edges=int(c[3]), average_edge_length=el.value)
+
+    def arrays(self):
+        """verts (n, 3), faces (list of lists), edges (ne, 2) = halfedge 0 of every edge."""
+        c = self.counts()
+        V = np.zeros((c["vertices"], 3))
+        ptr = np.zeros(c["faces"] + 1, np.int32)
+        idx = np.zeros(max(c["corners"], 1), np.int32)
+        E = np.zeros((max(c["edges"], 1), 2), np.int32)
+        _hk(self.H.aaadmm_host_polymesh_copy(self.h, _dp(V), _ip(ptr), _ip(idx), _ip(E)))
+        faces = [idx[ptr[f]:ptr[f + 1]].tolist() for f in range(c["faces"])]
+        return V, faces, E[:c["edges"]]
+
+    def save(self, path):
+        _hk(self.H.aaadmm_host_polymesh_save(self.h, str(path).encode()))
+
+    def subdivide_and_smooth(self):
+        h = self.H.aaadmm_host_polymesh_subdivide_and_smooth(self.h)
+        if not h:
+            raise AaadmmError(self.H.aaadmm_host_last_error().decode())
+        return PolyMesh(h)
+
+
+def geoapp_optimize(app, mesh, ref_mesh, max_iter, anderson_m, prm):
+    """The reference's optimize_mesh of PlanarityOpt (app 'planarity', prm = penalty, closeness_w, laplacian_w,
+    relative_laplacian_w) or WireMeshOpt (app 'wiremesh', prm = penalty, min_angle, max_angle, edge_length, closeness_w,
+    laplacian_w) on the device-backed ALMGeometrySolver. Returns (residual history, solution (n, 3), info)."""
+    H = PolyMesh._lib()
+    prm = np.ascontiguousarray(prm, np.float64)
+    hist = np.zeros(max(1, max_iter))
+    n = C.c_int(0)
+    sol = np.zeros((mesh.counts()["vertices"], 3))
+    info = np.zeros(3)
+    _hk(H.aaadmm_host_geoapp_optimize(0 if app == "planarity" else 1, mesh.h, ref_mesh.h, max_iter, anderson_m, _dp(prm),
+                                      _dp(hist), C.byref(n), _dp(sol), _dp(info)))
+    return hist[:n.value], sol, dict(loop_ms=info[0], resets=int(info[1]))

@@ -16,8 +16,8 @@ CUDA_SOURCES = ["aaadmm_capi.cu", "ldlt_apply.cu", "ldlt_factor.cu", "tet_kernel
 # per-element local-step math follows the reference operation by operation: no FMA contraction
 CUDA_NO_FMAD = {"tet_kernels.cu", "tri_kernels.cu", "geo_kernels.cu", "extra_terms.cu"}
 CUDA_HEADERS = ["common.cuh", "svd3.cuh", "cod_small.cuh", "aa_kernels.cuh", "tet_kernels.cuh", "ldlt_apply.cuh", "geo_kernels.cuh", "extra_terms.cuh", "pipe.cuh", "tri_prox.cuh", "lbfgs_prox.cuh", "collision_prox.cuh", "ldlt_factor.cuh"]
-HOST_SOURCES = ["beam_scene.cpp", "sparse_ldlt.cpp", "tet_system.cpp", "Solver.cpp", "MeshIO.cpp", "GeometrySolver.cpp", "host_capi.cpp"]
-HOST_HEADERS = ["beam_scene.hpp", "sparse_ldlt.hpp", "tet_system.hpp", "Solver.hpp", "AndersonAcceleration.hpp", "GeometrySolver.hpp", "MeshIO.hpp"]
+HOST_SOURCES = ["beam_scene.cpp", "sparse_ldlt.cpp", "tet_system.cpp", "Solver.cpp", "MeshIO.cpp", "GeometrySolver.cpp", "GeometryApps.cpp", "host_capi.cpp"]
+HOST_HEADERS = ["beam_scene.hpp", "sparse_ldlt.hpp", "tet_system.hpp", "Solver.hpp", "AndersonAcceleration.hpp", "GeometrySolver.hpp", "GeometryApps.hpp", "MeshIO.hpp"]
 
 
 def _stale(target, deps):

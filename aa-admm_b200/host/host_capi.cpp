@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/aaadmm_host.h"
+#include "GeometryApps.hpp"
 #include "MeshIO.hpp"
 #include "Solver.hpp"
 #include "beam_scene.hpp"
@@ -587,5 +588,100 @@ int aaadmm_host_geo_info(void *h, double *out4) {
     out4[2] = g->solver.last_result.rejects;
     out4[3] = g->solver.last_result.iters_logged;
     return 0;
+}
+// ---- Geometry front-end (host/GeometryApps.hpp): polygon meshes, subdivision, the two applications ----------------
+struct PolyHandle {
+    aaadmm::geoapp::PolyMesh mesh;
+};
+void *aaadmm_host_polymesh_load(const char *path) {
+    try {
+        std::unique_ptr<PolyHandle> h(new PolyHandle());
+        if (!aaadmm::geoapp::read_obj(path, h->mesh)) {
+            g_err = std::string("unable to read mesh from file ") + path;
+            return nullptr;
+        }
+        return h.release();
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void *aaadmm_host_polymesh_new(const double *verts, int n_verts, const int *face_ptr, const int *face_idx, int n_faces) {
+    try {
+        std::unique_ptr<PolyHandle> h(new PolyHandle());
+        h->mesh.V.assign(verts, verts + 3 * (size_t)n_verts);
+        h->mesh.face_ptr.assign(face_ptr, face_ptr + n_faces + 1);
+        h->mesh.face_idx.assign(face_idx, face_idx + face_ptr[n_faces]);
+        return h.release();
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void aaadmm_host_polymesh_free(void *h) { delete static_cast<PolyHandle *>(h); }
+int aaadmm_host_polymesh_save(void *h, const char *path) {
+    return aaadmm::geoapp::write_obj(static_cast<PolyHandle *>(h)->mesh, path) ? 0 : -1;
+}
+// counts[0..3] = vertices, faces, face corners, edges; avg_edge_length as MeshTypes.h:147-161
+int aaadmm_host_polymesh_counts(void *h, int *counts4, double *avg_edge_length) {
+    HOST_TRY
+    const aaadmm::geoapp::PolyMesh &m = static_cast<PolyHandle *>(h)->mesh;
+    aaadmm::geoapp::Connectivity C(m);
+    counts4[0] = m.n_vertices();
+    counts4[1] = m.n_faces();
+    counts4[2] = (int)m.face_idx.size();
+    counts4[3] = C.n_edges;
+    if (avg_edge_length) *avg_edge_length = aaadmm::geoapp::average_edge_length(m);
+    return 0;
+    HOST_CATCH
+}
+// edges: 2 per edge (halfedge 0: from, to), in OpenMesh's edge order
+int aaadmm_host_polymesh_copy(void *h, double *verts, int *face_ptr, int *face_idx, int *edges) {
+    HOST_TRY
+    const aaadmm::geoapp::PolyMesh &m = static_cast<PolyHandle *>(h)->mesh;
+    if (verts) std::copy(m.V.begin(), m.V.end(), verts);
+    if (face_ptr) std::copy(m.face_ptr.begin(), m.face_ptr.end(), face_ptr);
+    if (face_idx) std::copy(m.face_idx.begin(), m.face_idx.end(), face_idx);
+    if (edges) {
+        aaadmm::geoapp::Connectivity C(m);
+        for (int e = 0; e < C.n_edges; ++e) edges[2 * e] = C.edge_from[e], edges[2 * e + 1] = C.edge_to[e];
+    }
+    return 0;
+    HOST_CATCH
+}
+void *aaadmm_host_polymesh_subdivide_and_smooth(void *h) {
+    try {
+        std::unique_ptr<PolyHandle> o(new PolyHandle());
+        o->mesh = aaadmm::geoapp::subdivide_and_smooth_mesh(static_cast<PolyHandle *>(h)->mesh);
+        return o.release();
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+// app 0: PlanarityOpt optimize_mesh (prm = {penalty, closeness_w, laplacian_w, relative_laplacian_w});
+// app 1: WireMeshOpt optimize_mesh (prm = {penalty, min_angle, max_angle, edge_length, closeness_w, laplacian_w}).
+// hist: max_iter residuals (n_hist = rows written), solution: 3 per vertex, info3 = {loop_ms, resets, kernel launches}.
+int aaadmm_host_geoapp_optimize(int app, void *mesh_h, void *ref_h, int max_iter, int anderson_m, const double *prm,
+                                double *hist, int *n_hist, double *solution, double *info3) {
+    HOST_TRY
+    const aaadmm::geoapp::PolyMesh &m = static_cast<PolyHandle *>(mesh_h)->mesh, &r = static_cast<PolyHandle *>(ref_h)->mesh;
+    aaadmm::geoapp::OptimizeResult R =
+        app == 0 ? aaadmm::geoapp::planarity_optimize(m, r, max_iter, anderson_m, prm[0], prm[1], prm[2], prm[3], false)
+                 : aaadmm::geoapp::wiremesh_optimize(m, r, max_iter, anderson_m, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], false);
+    if (!R.ok) {
+        g_err = "geoapp: unable to initialize solver";
+        return -1;
+    }
+    *n_hist = (int)R.function_values.size();
+    std::copy(R.function_values.begin(), R.function_values.end(), hist);
+    std::copy(R.mesh.V.begin(), R.mesh.V.end(), solution);
+    if (info3) {
+        info3[0] = R.elapsed_time.empty() ? 0.0 : 1e3 * R.elapsed_time.back();
+        info3[1] = R.resets;
+        info3[2] = 0;
+    }
+    return 0;
+    HOST_CATCH
 }
 }  // extern "C"

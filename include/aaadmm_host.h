@@ -129,6 +129,20 @@ int aaadmm_host_geo_history(void *h, double *values);
 int aaadmm_host_geo_solution(void *h, double *x, int n_points);
 int aaadmm_host_geo_info(void *h, double *out4);
 
+/* Geometry front-end (aa-admm_b200/host/GeometryApps.hpp): polygon meshes from Wavefront .obj numbered as OpenMesh numbers
+ * them, subdivide_and_smooth_mesh (Geometry/MeshTypes.h:214-342) and the constraint recipes of the two applications
+ * (Geometry/PlanarityOpt.cpp:134-246: app 0, prm = {penalty, closeness_w, laplacian_w, relative_laplacian_w};
+ *  Geometry/WireMeshOpt.cpp:226-289: app 1, prm = {penalty, min_angle, max_angle, edge_length, closeness_w, laplacian_w}). */
+void *aaadmm_host_polymesh_load(const char *path);
+void *aaadmm_host_polymesh_new(const double *verts, int n_verts, const int *face_ptr, const int *face_idx, int n_faces);
+void aaadmm_host_polymesh_free(void *h);
+int aaadmm_host_polymesh_save(void *h, const char *path);
+int aaadmm_host_polymesh_counts(void *h, int *counts4, double *avg_edge_length); /* vertices, faces, corners, edges */
+int aaadmm_host_polymesh_copy(void *h, double *verts, int *face_ptr, int *face_idx, int *edges);
+void *aaadmm_host_polymesh_subdivide_and_smooth(void *h);
+int aaadmm_host_geoapp_optimize(int app, void *mesh, void *ref_mesh, int max_iter, int anderson_m, const double *prm,
+                                double *hist, int *n_hist, double *solution, double *info3);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,8 +63,10 @@ def main():
         E = np.zeros((ne.value, 2), np.int32)
         L.ref_app_edges(quad.encode(), E.ctypes.data_as(C.c_void_p), C.byref(ne))
         Vr, Fr = read_obj(tgt)
+        P0, F0 = read_obj(quad)  # the coarse input mesh itself: the product's own front-end subdivides it in the tests
         os.makedirs(os.path.join(ROOT, "tests", "golden_large"), exist_ok=True)
         np.savez_compressed(os.path.join(ROOT, "tests", "golden_large", "geo_maletorso.npz"), P=P, quads=Q, edges=E, edge_length=el.value,
+                            P0=P0, quads0=np.array(F0, np.int32),
                             Vref=Vr, Fref=np.array(Fr, np.int32), hist=hist[:, 1], secs=hist[:, 0], solution=Vsol)
         print("cfg3 MaleTorso:", len(P), "points", len(Q), "quads", len(E), "edges", "residual", hist[0, 1], "->", hist[-1, 1], "ref secs", hist[-1, 0])
 

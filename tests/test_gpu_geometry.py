@@ -179,3 +179,81 @@ def test_cfg3_wiremesh_maletorso_vs_reference_app(gpu):
     assert len(hist) == len(ref) == 100
     assert rel[:2].max() < 1e-8 and rel[:10].max() < 1e-4
     assert abs(np.log10(hist[-1] / ref[-1])) < 1.0
+
+
+# ---- the product's own front-end (host/GeometryApps: OBJ reader, connectivity, subdivision, constraint recipes) ----
+def _write_obj(path, V, faces):
+    with open(path, "w") as f:
+        for v in V:
+            f.write("v %.17g %.17g %.17g\n" % tuple(v))
+        for fc in faces:
+            f.write("f " + " ".join(str(int(i) + 1) for i in fc if i >= 0) + "\n")
+
+
+def _build_geo_sample(tmp_path, name):
+    from test_host_cpu import _build_sample
+    return _build_sample(tmp_path, name)
+
+
+def test_cfg2_planarity_sample_on_costa2k(gpu, tmp_path):
+    """samples/planarity.cpp (the reference's PlanarityOpt main on the product's front-end, no OpenMesh, no Python recipe):
+    <INPUT_MESH> <REFERENCE_MESH> <OPTION_FILES> <OUTPUT_MESH> on costa2k, against the unmodified application's residual
+    file and output mesh (tests/golden/geo_costa2k.npz)."""
+    import subprocess
+    g = np.load(os.path.join(HERE, "golden", "geo_costa2k.npz"))
+    _write_obj(tmp_path / "poly.obj", g["P"], g["faces"])
+    _write_obj(tmp_path / "tri.obj", g["Vref"], g["Fref"])
+    (tmp_path / "Options.txt").write_text("## options\nIterations  100\nAndersonM  5\nSquareElasticity 5000000\nTimeStep 0.033\n")
+    os.makedirs(tmp_path / "result")
+    exe = _build_geo_sample(tmp_path, "planarity")
+    r = subprocess.run([exe, "poly.obj", "tri.obj", "Options.txt", "out.obj"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    hist = np.loadtxt(tmp_path / "result" / "residual-5.txt")
+    ref = g["hist"]
+    assert hist.shape == (100, 2)
+    rel = np.abs(hist[:, 1] - ref) / ref
+    print("cfg2 sample: rel first 8 %.2e, max %.2e, final %.3e vs %.3e" % (rel[:8].max(), rel.max(), hist[-1, 1], ref[-1]))
+    print(r.stdout[-600:])
+    assert rel[:8].max() < 1e-8
+    assert abs(np.log10(hist[-1, 1] / ref[-1])) < 1.0
+    from geo_recipes import read_obj
+    V, F = read_obj(str(tmp_path / "out.obj"))
+    assert [list(f) for f in F] == [[int(i) for i in f if i >= 0] for f in g["faces"]]
+    assert np.abs(V - g["solution"]).max() < 1e-3 * np.abs(g["P"]).max()
+    # the library entry point gives the same run
+    mesh = gpu.PolyMesh.load(tmp_path / "poly.obj")
+    refm = gpu.PolyMesh.load(tmp_path / "tri.obj")
+    h2, x2, info = gpu.geoapp_optimize("planarity", mesh, refm, 100, 5, [1e5, 1.0, 0.0, 0.1])
+    assert np.array_equal(h2, hist[:, 1])
+
+
+def test_cfg3_wiremesh_sample_on_maletorso(gpu, tmp_path):
+    """samples/wiremesh.cpp on the coarse MaleTorso mesh: the product's subdivide_and_smooth_mesh, edge list, angle / edge
+    constraints and closest-point constraint against the unmodified application (golden_large/geo_maletorso.npz)."""
+    import subprocess
+    p = os.path.join(HERE, "golden_large", "geo_maletorso.npz")
+    if not os.path.exists(p):
+        pytest.skip("tests/golden_large/geo_maletorso.npz not generated (make_golden_geo.py --large)")
+    g = np.load(p)
+    if "P0" not in g:
+        pytest.skip("golden without the coarse mesh (regenerate with make_golden_geo.py --large)")
+    _write_obj(tmp_path / "quad.obj", g["P0"], g["quads0"])
+    _write_obj(tmp_path / "target.obj", g["Vref"], g["Fref"])
+    (tmp_path / "Options.txt").write_text("Iterations  100\nAndersonM  5\n")
+    os.makedirs(tmp_path / "result")
+    # front-end alone: the subdivided and smoothed mesh is the reference's
+    sub = gpu.PolyMesh.load(tmp_path / "quad.obj").subdivide_and_smooth()
+    V, F, E = sub.arrays()
+    assert np.array_equal(np.array(F), g["quads"]) and np.array_equal(E, g["edges"])
+    assert np.abs(V - g["P"]).max() < 1e-9 * np.abs(g["P"]).max()
+    exe = _build_geo_sample(tmp_path, "wiremesh")
+    r = subprocess.run([exe, "quad.obj", "target.obj", "Options.txt", "out.obj"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    hist = np.loadtxt(tmp_path / "result" / "residual-5.txt")
+    ref = g["hist"]
+    rel = np.abs(hist[:, 1] - ref) / ref
+    print("cfg3 sample: rel first 10", rel[:10], "max %.2e, final %.3e vs %.3e" % (rel.max(), hist[-1, 1], ref[-1]))
+    print(r.stdout[-400:])
+    assert len(hist) == 100
+    assert rel[:2].max() < 1e-8 and rel[:10].max() < 1e-4
+    assert abs(np.log10(hist[-1, 1] / ref[-1])) < 1.0

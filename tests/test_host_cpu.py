@@ -494,3 +494,69 @@ def test_material_update_of_the_system_matrix_is_bit_identical(A):
             assert np.array_equal(a, b)
         H.aaadmm_host_system_free(h1)
     H.aaadmm_host_system_free(h0)
+
+
+def _quad_patch_obj(path, nx, ny, closed=False, seed=2):
+    """Wavy quad patch (or, closed = True, a quad torus without boundary) as .obj with a/b/c face tokens in some rows."""
+    rng = np.random.default_rng(seed)
+    if closed:
+        V = [[(2 + np.cos(2 * np.pi * j / ny)) * np.cos(2 * np.pi * i / nx), (2 + np.cos(2 * np.pi * j / ny)) * np.sin(2 * np.pi * i / nx),
+              np.sin(2 * np.pi * j / ny)] for i in range(nx) for j in range(ny)]
+        vid = lambda i, j: (i % nx) * ny + (j % ny)
+        F = [[vid(i, j), vid(i + 1, j), vid(i + 1, j + 1), vid(i, j + 1)] for i in range(nx) for j in range(ny)]
+    else:
+        V = [[i + 0.1 * rng.standard_normal(), j + 0.1 * rng.standard_normal(), 0.3 * np.sin(0.7 * i) * np.cos(0.5 * j)]
+             for i in range(nx + 1) for j in range(ny + 1)]
+        vid = lambda i, j: i * (ny + 1) + j
+        F = [[vid(i, j), vid(i + 1, j), vid(i + 1, j + 1), vid(i, j + 1)] for i in range(nx) for j in range(ny)]
+    with open(path, "w") as f:
+        f.write("# test mesh\n")
+        for v in V:
+            f.write("v %.9f %.9f %.9f\n" % tuple(v))
+        for k, q in enumerate(F):
+            f.write("f " + " ".join(("%d/%d/%d" % (i + 1, i + 1, i + 1)) if k % 3 == 0 else str(i + 1) for i in q) + "\n")
+    return np.array([[float("%.9f" % c) for c in v] for v in V]), F   # the coordinates as the file holds them
+
+
+@pytest.mark.parametrize("closed", [False, True])
+def test_geometry_front_end_vs_openmesh(A, tmp_path, closed):
+    """host/GeometryApps: the OBJ reader (single-precision coordinates as OpenMesh's), the edge numbering, the
+    average edge length and subdivide_and_smooth_mesh against the reference's own code on OpenMesh
+    (oracle/_ref/libref_wiremesh.so: MeshTypes.h:147-161, 214-342): connectivity identical, positions to round-off."""
+    from oracle import refbind
+    if not refbind.have_ref_geo() or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_wiremesh.so")):
+        pytest.skip("oracle/_ref (compiled reference) not present")
+    path = str(tmp_path / "quads.obj")
+    V0, F0 = _quad_patch_obj(path, 7, 5, closed)
+    L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_wiremesh.so"))
+    nv, nq, ne, el = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+    assert L.ref_app_subdivided(path.encode(), None, None, C.byref(nv), C.byref(nq), C.byref(el)) == 0
+    P, Q = np.zeros((nv.value, 3)), np.zeros((nq.value, 4), np.int32)
+    L.ref_app_subdivided(path.encode(), P.ctypes.data_as(C.c_void_p), Q.ctypes.data_as(C.c_void_p), C.byref(nv), C.byref(nq), C.byref(el))
+    L.ref_app_edges(path.encode(), None, C.byref(ne))
+    E = np.zeros((ne.value, 2), np.int32)
+    L.ref_app_edges(path.encode(), E.ctypes.data_as(C.c_void_p), C.byref(ne))
+    m = A.PolyMesh.load(path)
+    V, F, _ = m.arrays()
+    assert np.array_equal(V, V0.astype(np.float32).astype(np.float64)) and F == F0
+    assert 0.5 * m.counts()["average_edge_length"] == el.value
+    s = m.subdivide_and_smooth()
+    Vs, Fs, Es = s.arrays()
+    assert np.array_equal(np.array(Fs), Q) and np.array_equal(Es, E)
+    assert np.abs(Vs - P).max() < 1e-10 * np.abs(P).max()
+    # write / read round trip (16 significant digits; the reader keeps single precision like OpenMesh's)
+    s.save(tmp_path / "sub.obj")
+    V2, F2, E2 = A.PolyMesh.load(tmp_path / "sub.obj").arrays()
+    assert F2 == Fs and np.array_equal(E2, Es) and np.array_equal(V2, Vs.astype(np.float32).astype(np.float64))
+    # a face that re-uses a directed edge is refused like OpenMesh's add_face does (complex edge)
+    with pytest.raises(A.AaadmmError):
+        A.PolyMesh.from_arrays(V0, F0 + [F0[0]]).counts()
+
+
+@pytest.mark.parametrize("name", ["planarity", "wiremesh"])
+def test_geometry_samples_compile_and_report_missing_files(A, tmp_path, name):
+    exe = _build_sample(tmp_path, name)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage" in r.stdout
+    r = subprocess.run([exe, "nothing.obj", "nothing.obj", "nothing.txt", "out.obj"], capture_output=True, text=True)
+    assert r.returncode == 1 and "unable to read" in r.stderr
