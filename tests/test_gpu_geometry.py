@@ -214,8 +214,10 @@ def test_cfg2_planarity_sample_on_costa2k(gpu, tmp_path):
     rel = np.abs(hist[:, 1] - ref) / ref
     print("cfg2 sample: rel first 8 %.2e, max %.2e, final %.3e vs %.3e" % (rel[:8].max(), rel.max(), hist[-1, 1], ref[-1]))
     print(r.stdout[-600:])
-    assert rel[:8].max() < 1e-8
-    assert abs(np.log10(hist[-1, 1] / ref[-1])) < 1.0
+    # with the product's own reader (single-precision coordinates like OpenMesh's) the whole 100-iteration history follows the
+    # reference application closely (measured: 1.3e-10 over the first 8 iterations, 1.8e-8 over all 100)
+    assert rel[:8].max() < 1e-9
+    assert rel.max() < 1e-6
     from geo_recipes import read_obj
     V, F = read_obj(str(tmp_path / "out.obj"))
     assert [list(f) for f in F] == [[int(i) for i in f if i >= 0] for f in g["faces"]]
@@ -224,7 +226,7 @@ def test_cfg2_planarity_sample_on_costa2k(gpu, tmp_path):
     mesh = gpu.PolyMesh.load(tmp_path / "poly.obj")
     refm = gpu.PolyMesh.load(tmp_path / "tri.obj")
     h2, x2, info = gpu.geoapp_optimize("planarity", mesh, refm, 100, 5, [1e5, 1.0, 0.0, 0.1])
-    assert np.array_equal(h2, hist[:, 1])
+    assert np.allclose(h2, hist[:, 1], rtol=1e-14, atol=0.0)   # the file holds 16 significant digits
 
 
 def test_cfg3_wiremesh_sample_on_maletorso(gpu, tmp_path):
@@ -253,7 +255,10 @@ def test_cfg3_wiremesh_sample_on_maletorso(gpu, tmp_path):
     ref = g["hist"]
     rel = np.abs(hist[:, 1] - ref) / ref
     print("cfg3 sample: rel first 10", rel[:10], "max %.2e, final %.3e vs %.3e" % (rel.max(), hist[-1, 1], ref[-1]))
+    print("cfg3 sample: rel every 10th", rel[::10])
     print(r.stdout[-400:])
     assert len(hist) == 100
-    assert rel[:2].max() < 1e-8 and rel[:10].max() < 1e-4
+    # measured 6.7e-13, 2.5e-12, 4.0e-10, 4.3e-9 over the first four iterations; later iterations separate through ties
+    # of the closest-point search (a point equally far from two triangles of the target mesh)
+    assert rel[:2].max() < 1e-10 and rel[:4].max() < 1e-7 and rel[:10].max() < 1e-4
     assert abs(np.log10(hist[-1, 1] / ref[-1])) < 1.0
