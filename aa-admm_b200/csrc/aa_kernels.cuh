@@ -180,11 +180,10 @@ k_aa_pass1(const double *__restrict__ g_u, const double *__restrict__ g_x, doubl
     }
 }
 
-// i_begin > 0: the rows before it are mixed elsewhere (the tets' rows inside the next local step, k_update_z_hard)
 template <int M>
 __global__ void __launch_bounds__(AA_BLOCK)
 k_aa_pass2(const double *__restrict__ g_u, const double *__restrict__ g_x, double *__restrict__ ucur,
-           double *__restrict__ dF, double *__restrict__ dG, int64_t Ne, int64_t Nt, const SolveState *st, int64_t i_begin) {
+           double *__restrict__ dF, double *__restrict__ dG, int64_t Ne, int64_t Nt, const SolveState *st) {
     if (st->done || st->aa_skip) return;
     const int mk = st->aa_mk;
     if (mk == 0) return;
@@ -193,7 +192,7 @@ k_aa_pass2(const double *__restrict__ g_u, const double *__restrict__ g_x, doubl
 #pragma unroll
     for (int j = 0; j < M; ++j) coef[j] = (j < mk) ? st->aa_coef[j] : 0.0;
     const int64_t stride = (int64_t)gridDim.x * AA_BLOCK;
-    for (int64_t base = i_begin + (int64_t)blockIdx.x * AA_BLOCK + threadIdx.x; base < Nt; base += stride * AA_ILP) {
+    for (int64_t base = (int64_t)blockIdx.x * AA_BLOCK + threadIdx.x; base < Nt; base += stride * AA_ILP) {
         double g[AA_ILP], uc[AA_ILP], s[AA_ILP];
 #pragma unroll
         for (int e = 0; e < AA_ILP; ++e) {
@@ -224,6 +223,6 @@ int launch_aa_pass1(int m, int grid, cudaStream_t s, const double *g_u, const do
                     double *ucur, double *dF, double *dG, int64_t Ne, int64_t Nt, SolveState *st, double *partials,
                     double *g_copy = nullptr);
 int launch_aa_pass2(int m, int grid, cudaStream_t s, const double *g_u, const double *g_x, double *ucur,
-                    double *dF, double *dG, int64_t Ne, int64_t Nt, const SolveState *st, int64_t i_begin = 0);
+                    double *dF, double *dG, int64_t Ne, int64_t Nt, const SolveState *st);
 
 }  // namespace aaadmm

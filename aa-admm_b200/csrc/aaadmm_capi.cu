@@ -56,9 +56,8 @@ int launch_aa_pass1(int m, int grid, cudaStream_t s, const double *g_u, const do
     return 0;
 }
 int launch_aa_pass2(int m, int grid, cudaStream_t s, const double *g_u, const double *g_x, double *ucur,
-                    double *dF, double *dG, int64_t Ne, int64_t Nt, const SolveState *st, int64_t i_begin) {
-    if (i_begin > 0) grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, (Nt - i_begin + AA_BLOCK * AA_ILP - 1) / (AA_BLOCK * AA_ILP)));
-    AA_DISPATCH(m, (k_aa_pass2<MM><<<grid, AA_BLOCK, 0, s>>>(g_u, g_x, ucur, dF, dG, Ne, Nt, st, i_begin)));
+                    double *dF, double *dG, int64_t Ne, int64_t Nt, const SolveState *st) {
+    AA_DISPATCH(m, (k_aa_pass2<MM><<<grid, AA_BLOCK, 0, s>>>(g_u, g_x, ucur, dF, dG, Ne, Nt, st)));
     AAADMM_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -792,17 +791,6 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
     const size_t o15 = o9 + 6 * (size_t)NT;
     PointArrays Pt{NC, s->pt_vert, s->pt_w, s->n_objs, s->obj_type, s->obj_prm, s->rho_dt2};
     double *pt_contrib = tri_contrib + 9 * (size_t)NT;
-    // The tets' rows of the Anderson mixing step (pass 2) are finished by the next local step (k_update_z_hard), which
-    // is FP64-bound and leaves the memory system idle; pass 2 itself then covers the triangle / collision rows and x only.
-    // Not with hyper-elastic tets (k_hyper reads u before the linear kernel runs). AAADMM_NO_FUSE_MIX=1: two full passes.
-    static const bool no_fuse = getenv("AAADMM_NO_FUSE_MIX") != nullptr;
-    const bool fuse_mix = accel && !no_fuse && s->n_hyper == 0 && T > 0;
-    AaMix mix;
-    mix.g_u = Gu;
-    mix.dF = s->dF;
-    mix.dG = s->dG;
-    mix.Ne = s->Ne;
-    mix.Nt = s->Nt;
     auto update_z = [&](int mode) {
         if (NC > 0) {
             launch_pt_update_z_hard(mode, st, Pt, Ux, Uu + o15, s->z + o15, pt_contrib, s->st, s->partials);
@@ -812,7 +800,7 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
             launch_tri_update_z_hard(mode, st, R, Ux, Uu + o9, s->z + o9, tri_contrib, s->st, s->partials);
             ++L;
         }
-        launch_update_z_hard(mode, gt, st, A, Ux, Uu, s->z, s->contrib, s->st, s->partials, (mode == MODE_ITER && fuse_mix) ? &mix : nullptr);
+        launch_update_z_hard(mode, gt, st, A, Ux, Uu, s->z, s->contrib, s->st, s->partials);
     };
     auto update_u = [&](int mode, double *u_out) {
         if (NC > 0) {
@@ -892,8 +880,7 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
             if (launch_aa_pass1(m, gs, st, Gu, s->xs, Gx, s->Ubuf, s->dF, s->dG, s->Ne, s->Nt, s->st, s->partials)) return capturing ? loop_graph_abort(s) : -1;
             prof->end();
             prof->begin(5);
-            if (launch_aa_pass2(m, gs, st, Gu, Gx, s->Ubuf, s->dF, s->dG, s->Ne, s->Nt, s->st, fuse_mix ? 9 * (int64_t)T : 0))
-                return capturing ? loop_graph_abort(s) : -1;
+            if (launch_aa_pass2(m, gs, st, Gu, Gx, s->Ubuf, s->dF, s->dG, s->Ne, s->Nt, s->st)) return capturing ? loop_graph_abort(s) : -1;
             prof->end();
             L += 2;
         } else {

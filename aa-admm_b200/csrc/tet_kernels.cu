@@ -72,21 +72,14 @@ __device__ __forceinline__ void corner_contrib(const double (&b)[9], double w, d
 //   z = prox((D x - c + u)/w), prim^2 = |D x - W z - c|^2, and the per-corner D^T W(Wz - u)
 //   contributions for the following x-update.  The finishing CTA takes the accept/reject
 //   decision of hard/src/Solver.cpp:146 on the device.
-// With `mix` set (MODE_ITER of an accelerated loop) the kernel first finishes the Anderson step the previous iteration
-// prepared (hard/src/AndersonAcceleration.h:200-209) for ITS OWN rows: u_cur = G - dG(:, 0:mk) coef, and the next
-// history column starts with -F / -G - what k_aa_pass2 does, element by element in the same order and with the same
-// fused multiply-adds, but read and written here while the Jacobi sweeps keep the FP64 pipe busy (this kernel uses a
-// seventh of the DRAM bandwidth, pass 2 all of it). k_aa_pass2 then only covers the rows behind the tets'.
 template <int MODE>
 __global__ void __launch_bounds__(TET_BLOCK, 4)
-k_update_z_hard(TetArrays A, const double *__restrict__ pos, double *u, double *__restrict__ z,
-                double *__restrict__ contrib, SolveState *st, double *partials, AaMix mix) {
+k_update_z_hard(TetArrays A, const double *__restrict__ pos, const double *__restrict__ u, double *__restrict__ z,
+                double *__restrict__ contrib, SolveState *st, double *partials) {
     if (st->done) return;
     if (MODE == MODE_REDO && !st->reject) return;
     const int T = A.n_tets;
     double acc[1] = {0.0};
-    const int mix_mk = (MODE == MODE_ITER && mix.dG != nullptr && !st->aa_skip) ? st->aa_mk : 0;
-    const int mix_cn = st->aa_col;  // already advanced by pass 1
     // B^-1 and u are parked in shared memory while the Jacobi SVD runs: 36 fewer live registers
     __shared__ double s_park[18][TET_BLOCK];
     for (int t = blockIdx.x * TET_BLOCK + threadIdx.x; t < T; t += gridDim.x * TET_BLOCK) {
@@ -100,36 +93,9 @@ k_update_z_hard(TetArrays A, const double *__restrict__ pos, double *u, double *
             for (int k = 0; k < 9; ++k) b[k] = A.binv[(size_t)k * T + t];
             deformation_gradient(pos, id, b, F);
             const double winv = 1.0 / w;
-            double um[9];
-            if (MODE == MODE_ITER && mix_mk > 0) {
-                double g[9], sacc[9];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    g[k] = mix.g_u[(size_t)k * T + t];
-                    um[k] = u[(size_t)k * T + t];
-                    sacc[k] = 0.0;
-                }
-                for (int j = 0; j < mix_mk; ++j) {
-                    const double cj = st->aa_coef[j];
-                    const double *col = mix.dG + (size_t)j * mix.Nt + t;
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) sacc[k] = __fma_rn(col[(size_t)k * T], cj, sacc[k]);
-                }
-                double *dFn = mix.dF + (size_t)mix_cn * mix.Ne + t, *dGn = mix.dG + (size_t)mix_cn * mix.Nt + t;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    dFn[(size_t)k * T] = -(g[k] - um[k]);
-                    dGn[(size_t)k * T] = -g[k];
-                    um[k] = g[k] - sacc[k];
-                    u[(size_t)k * T + t] = um[k];
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 9; ++k) um[k] = u[(size_t)k * T + t];
-            }
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                const double ui = um[k];
+                const double ui = u[(size_t)k * T + t];
                 F[k] = w * F[k];              // D_i x - c_i
                 zi[k] = (F[k] + ui) * winv;   // W^-1 (D_i x + u_i - c_i)
                 s_park[k][threadIdx.x] = b[k];
@@ -647,17 +613,16 @@ __global__ void k_prox_hyper_batch(HyperParams P, double *z, double *g, int64_t 
 }
 
 // ---- host launchers (this translation unit is compiled with -fmad=false) ----
-void launch_update_z_hard(int mode, int grid, cudaStream_t s, const TetArrays &A, const double *pos, double *u,
-                          double *z, double *contrib, SolveState *st, double *partials, const AaMix *mix) {
+void launch_update_z_hard(int mode, int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *u,
+                          double *z, double *contrib, SolveState *st, double *partials) {
     if (A.n_hyper > 0)
         k_hyper<0><<<(A.n_hyper + TET_BLOCK - 1) / TET_BLOCK, TET_BLOCK, 0, s>>>(A, pos, u, z, contrib, st, partials, mode);
-    const AaMix none = AaMix();
     if (mode == MODE_WARM)
-        k_update_z_hard<MODE_WARM><<<grid, TET_BLOCK, 0, s>>>(A, pos, u, z, contrib, st, partials, none);
+        k_update_z_hard<MODE_WARM><<<grid, TET_BLOCK, 0, s>>>(A, pos, u, z, contrib, st, partials);
     else if (mode == MODE_ITER)
-        k_update_z_hard<MODE_ITER><<<grid, TET_BLOCK, 0, s>>>(A, pos, u, z, contrib, st, partials, mix ? *mix : none);
+        k_update_z_hard<MODE_ITER><<<grid, TET_BLOCK, 0, s>>>(A, pos, u, z, contrib, st, partials);
     else
-        k_update_z_hard<MODE_REDO><<<grid, TET_BLOCK, 0, s>>>(A, pos, u, z, contrib, st, partials, none);
+        k_update_z_hard<MODE_REDO><<<grid, TET_BLOCK, 0, s>>>(A, pos, u, z, contrib, st, partials);
 }
 void launch_update_u_hard(int mode, int grid, cudaStream_t s, const TetArrays &A, const double *pos_new,
                           const double *pos_last, const double *z, const double *u_in, double *u_out, SolveState *st,

@@ -26,14 +26,6 @@ struct TetArrays {
     int n_hyper;
 };
 
-// Pending Anderson mixing step of the hard_zxu loop, finished by the local step for its own rows (k_update_z_hard):
-// default iterate G (u part), history dF (Ne per column) / dG (Nt per column).
-struct AaMix {
-    const double *g_u = nullptr;
-    double *dF = nullptr, *dG = nullptr;
-    int64_t Ne = 0, Nt = 0;
-};
-
 // Triangle terms (tri_kernels.cu). rest_pose [4][N], u / z [6][N], contributions 9 doubles per triangle.
 struct TriArrays {
     int n_tris, n_free;
@@ -60,9 +52,8 @@ enum { MODE_WARM = 0, MODE_ITER = 1, MODE_REDO = 2 };
 // Host launchers (tet_kernels.cu is compiled with -fmad=false: the per-element arithmetic follows
 // the reference operation by operation, and fused multiply-adds would change its rounding and,
 // for degenerate elements, its branch decisions).
-// `mix` (may be null): the tets' share of the Anderson mixing step runs inside the MODE_ITER kernel (see k_update_z_hard)
-void launch_update_z_hard(int mode, int grid, cudaStream_t s, const TetArrays &A, const double *pos, double *u,
-                          double *z, double *contrib, SolveState *st, double *partials, const AaMix *mix = nullptr);
+void launch_update_z_hard(int mode, int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *u,
+                          double *z, double *contrib, SolveState *st, double *partials);
 void launch_update_u_hard(int mode, int grid, cudaStream_t s, const TetArrays &A, const double *pos_new,
                           const double *pos_last, const double *z, const double *u_in, double *u_out, SolveState *st,
                           double *partials, double *hist_prim, double *hist_comb, int *hist_rej);

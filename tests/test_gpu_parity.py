@@ -782,27 +782,3 @@ def test_pipelined_sweep_on_resident_scene_slots(gpu):
             _, h, _ = run_product(gpu, beam_arrays(gpu, *dims), 1, iters=60, m=5, accel=True, youngs=youngs, poisson=poisson)
             assert int(r[1]) == len(h[0]) and int(r[2]) == int(h[0][:, 2].sum())
             assert r[3] == h[0][-1, 0] and r[4] == h[0][-1, 1]
-
-
-def test_fused_anderson_mixing_is_bit_identical_to_the_two_pass_form(gpu):
-    """The tets' rows of Anderson pass 2 run inside the next local step (k_update_z_hard); AAADMM_NO_FUSE_MIX=1 keeps
-    the two full streaming passes. Same operations in the same order: histories and positions equal to the last bit,
-    with tets only and with tets + triangles + rejected steps in one solver."""
-    import json
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = ("import sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r); import numpy as np; import aa_admm_b200 as A; "
-            "from scenes import beam_arrays, run_product, run_cloth; "
-            "_, h, x = run_product(A, beam_arrays(A, 16, 8, 8), 2, m=5, accel=True); "
-            "hc, xc = run_cloth(A.Solver, frames=2, n=6, m=5, accel=True, limits=(0.9, 1.1), with_beam=(A, (6, 2, 2))); "
-            "print(json.dumps([[a.tolist() for a in h], [a.tolist() for a in x], [a.tolist() for a in hc], [a.tolist() for a in xc]]))"
-            ) % (root, os.path.join(root, "tests"))
-    outs = []
-    for env in ({}, {"AAADMM_NO_FUSE_MIX": "1"}):
-        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
-        assert r.returncode == 0, r.stderr[-2000:]
-        outs.append(json.loads(r.stdout.strip().split("\n")[-1]))
-    assert outs[0] == outs[1]
-    assert sum(row[2] for row in outs[0][2][0]) + sum(row[2] for row in outs[0][2][1]) >= 0  # reject flags present in the log
