@@ -110,6 +110,8 @@ __global__ void k_init_state(SolveState *st, int accel, int m, double eps, int m
     st->aa_mk = 0;
     st->ticket = 0u;
 }
+// The iteration loop begins here (after the warm start): time base of the per-iteration time stamps.
+__global__ void k_mark_loop_start(SolveState *st) { st->t0 = global_timer_ns(); }
 // Tail of one loop turn inside the graph WHILE node: advance the device-side iteration counter and
 // decide whether the body runs again (hard/src/Solver.cpp:130 `for` bound and :188 `break`).
 __global__ void k_loop_cond(cudaGraphConditionalHandle h, SolveState *st) {
@@ -194,6 +196,7 @@ struct aaadmm_tetscene {
     const double *last_z = nullptr, *last_u = nullptr;
     double *zu_scratch = nullptr;
     SolveState *st_h = nullptr;  // pinned host copy of the control block
+    int last_rows = 0, last_max_iters = 0;  // of the last step (aaadmm_tetscene_iteration_times)
 };
 
 extern "C" {
@@ -666,7 +669,7 @@ static int scene_reserve(aaadmm_tetscene *s, int iters, int m) {
         cudaFree(s->hist_comb);
         cudaFree(s->hist_rej);
         AAADMM_CUDA_OK(cudaMalloc((void **)&s->hist_prim, sizeof(double) * iters));
-        AAADMM_CUDA_OK(cudaMalloc((void **)&s->hist_comb, sizeof(double) * iters));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&s->hist_comb, sizeof(double) * 2 * iters));  // residuals | time stamps
         AAADMM_CUDA_OK(cudaMalloc((void **)&s->hist_rej, sizeof(int) * iters));
         s->hist_cap = iters;
         s->loop_key = -1;
@@ -840,6 +843,8 @@ static int run_hard(aaadmm_tetscene *s, const aaadmm_step_opts *o, PhaseProf *pr
         // default_(u,x) = curr_(u,x); accelerator->init(curr_u, curr_x)
         AAADMM_CUDA_OK(cudaMemcpyAsync(s->Ubuf, s->Gbuf, sizeof(double) * s->Nt, cudaMemcpyDeviceToDevice, st));
         L += 6 + f->n_launches;
+        k_mark_loop_start<<<1, 1, 0, st>>>(s->st);
+        ++L;
     }
     // ---- the loop: one graph launch (WHILE node, device-side break), or plain launches when profiling ----
     cudaGraphConditionalHandle cond_handle = 0;
@@ -937,7 +942,8 @@ static int run_xzu(aaadmm_tetscene *s, const aaadmm_step_opts *o, int iters, boo
     AAADMM_CUDA_OK(cudaMemcpyAsync(Zdef, Zcur, sizeof(double) * NZ, cudaMemcpyDeviceToDevice, st));
     AAADMM_CUDA_OK(cudaMemcpyAsync(dx, cx, sizeof(double) * NX, cudaMemcpyDeviceToDevice, st));
     AAADMM_CUDA_OK(cudaMemsetAsync(du, 0, sizeof(double) * NZ, st));
-    L += 5;
+    k_mark_loop_start<<<1, 1, 0, st>>>(s->st);
+    L += 6;
 
     cudaGraphConditionalHandle cond_handle = 0;
     bool capturing = false;
@@ -1043,6 +1049,8 @@ static int step_common(aaadmm_tetscene *s, const aaadmm_step_opts *o, bool host_
     AAADMM_CUDA_OK(cudaEventRecord(s->ev[3], st));
     AAADMM_CUDA_OK(cudaStreamSynchronize(st));
     const SolveState hs = *s->st_h;
+    s->last_rows = hs.iter;
+    s->last_max_iters = hs.max_iters;
     if (host_io) {
         memcpy(x_out, s->xout_h, sizeof(double) * 3 * NF);
         const int rows = hs.iter;
@@ -1074,6 +1082,18 @@ int aaadmm_tetscene_step(aaadmm_tetscene *s, const aaadmm_step_opts *o, const do
 int aaadmm_tetscene_step_resident(aaadmm_tetscene *s, const aaadmm_step_opts *o, aaadmm_step_result *res) {
     API_TRY_BEGIN
     return step_common(s, o, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, res);
+    API_TRY_END
+}
+
+int aaadmm_tetscene_iteration_times(aaadmm_tetscene *s, double *ms, int n) {
+    API_TRY_BEGIN
+    if (!s || !ms || n < 0 || n > s->last_rows) {
+        set_last_error("tetscene_iteration_times: bad arguments (n must not exceed the rows of the last step)");
+        return -1;
+    }
+    if (n > 0) AAADMM_CUDA_OK(cudaMemcpy(ms, s->hist_comb + s->last_max_iters, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) ms[i] *= 1e-6;
+    return 0;
     API_TRY_END
 }
 
@@ -1441,6 +1461,7 @@ struct aaadmm_geo {
     int m_cap = 0, hist_cap = 0;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     SolveState *st_h = nullptr;  // pinned host copy of the control block
+    int last_iters = 0, last_max_iter = 0;  // of the last solve (aaadmm_geo_reset_flags)
     SolveState *st = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
@@ -1679,7 +1700,7 @@ int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int ande
     cudaStream_t st = g->stream;
     if (max_iter > g->hist_cap) {
         cudaFree(g->hist);
-        AAADMM_CUDA_OK(cudaMalloc((void **)&g->hist, sizeof(double) * std::max(1, max_iter)));
+        AAADMM_CUDA_OK(cudaMalloc((void **)&g->hist, sizeof(double) * 2 * std::max(1, max_iter)));  // residuals | reset flags
         g->hist_cap = max_iter;
         g->graph_key = -1;
     }
@@ -1756,6 +1777,8 @@ int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int ande
     AAADMM_CUDA_OK(cudaMemcpyAsync(&hs, g->st, sizeof(SolveState), cudaMemcpyDeviceToHost, st));
     AAADMM_CUDA_OK(cudaStreamSynchronize(st));
     if (hist && hs.iter > 0) AAADMM_CUDA_OK(cudaMemcpy(hist, g->hist, sizeof(double) * hs.iter, cudaMemcpyDeviceToHost));
+    g->last_iters = hs.iter;
+    g->last_max_iter = max_iter;
     if (res) {
         res->iters_logged = hs.iter;
         res->rejects = hs.n_rejects;
@@ -1764,6 +1787,19 @@ int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int ande
         res->step_ms = res->loop_ms;
         res->kernel_launches = launches + hs.loop_it * g->body_launches;
     }
+    return 0;
+    API_TRY_END
+}
+
+int aaadmm_geo_reset_flags(aaadmm_geo *g, int *flags, int n) {
+    API_TRY_BEGIN
+    if (!g || !flags || n < 0 || n > g->last_iters) {
+        set_last_error("geo_reset_flags: bad arguments (n must not exceed the iterations of the last solve)");
+        return -1;
+    }
+    std::vector<double> f((size_t)std::max(n, 1));
+    if (n > 0) AAADMM_CUDA_OK(cudaMemcpy(f.data(), g->hist + g->last_max_iter, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) flags[i] = f[i] != 0.0;
     return 0;
     API_TRY_END
 }

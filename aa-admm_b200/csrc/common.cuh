@@ -54,9 +54,16 @@ struct SolveState {
     int loop_it, max_iters;            // device-side loop control of the graph WHILE node
     int skip_redo;                     // xzu: 1 unless the current iterate was rejected (guards the redo solve)
     int aa_skip;                       // geometry: 1 on a rejected turn (the Anderson passes do not run)
+    unsigned long long t0;             // %globaltimer when the iteration loop began (per-iteration time stamps of the log)
     double tri_prim2, tri_comb;        // residual shares of the triangle terms (0 for tet-only scenes)
     double pt_prim2, pt_comb;          // residual shares of the collision terms
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+    return t;
+}
 
 // ---------------------------------------------------------------------------------------
 // Deterministic grid reduction of NQ doubles per thread.

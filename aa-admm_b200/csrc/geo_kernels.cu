@@ -411,6 +411,7 @@ k_geo_u_resid(GeoConstraints C, const double *__restrict__ x_new, const double *
             if (accept) {
                 const int it = st->iter;
                 hist[it] = r;
+                hist[st->max_iters + it] = st->reject ? 1.0 : 0.0;  // this iteration follows a reset of the accelerator
                 st->iter = it + 1;
                 st->prev_prim = r;
                 st->reject = 0;   // reset = false
@@ -520,6 +521,7 @@ k_gs_z(GeoConstraints C, GeoSoft S, int zc_hard, double rho, const double *__res
             if (log) {
                 const int it = st->iter;
                 hist[it] = res;
+                hist[st->max_iters + it] = MODE == 2 ? 1.0 : 0.0;  // logged after the redo of a rejected iterate
                 st->iter = it + 1;
                 st->prev_prim = res;
                 if (st->iter >= st->max_iters) st->done = 1;  // end_iteration: the rest of this turn is skipped

@@ -298,6 +298,7 @@ k_update_u_hard(TetArrays A, const double *__restrict__ pos_new, const double *_
                 const int it = st->iter;
                 hist_prim[it] = st->prev_prim;
                 hist_comb[it] = comb;
+                hist_comb[st->max_iters + it] = (double)(global_timer_ns() - st->t0);  // ns since the loop began
                 hist_rej[it] = st->reject;
                 st->iter = it + 1;
             }
@@ -499,6 +500,7 @@ k_comb_xzu(TetArrays A, const double *__restrict__ pos, const double *__restrict
             const int it = st->iter;
             hist_prim[it] = st->prev_prim;
             hist_comb[it] = comb;
+            hist_comb[st->max_iters + it] = (double)(global_timer_ns() - st->t0);  // ns since the loop began
             hist_rej[it] = st->reject;
             st->iter = it + 1;
             st->reject = 0;

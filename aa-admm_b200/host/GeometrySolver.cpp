@@ -250,6 +250,8 @@ void GeometrySolverBase<N>::solve_ADMM(const MatrixNX &init_x, double, int max_i
         return;
     }
     default_x_ = init_x;
+    // (the reference defines clear_iteration_history, ALMGeometrySolver.h:398-402, but never calls it: a second solve
+    // appends to the history; so does this one)
     std::vector<double> hist(std::max(1, max_iter));
     const auto t0 = std::chrono::steady_clock::now();
     if (aaadmm_geo_solve(geo_, init_x.data(), max_iter, Anderson_m, default_x_.data(), hist.data(), &last_result) != 0) {
@@ -258,11 +260,27 @@ void GeometrySolverBase<N>::solve_ADMM(const MatrixNX &init_x, double, int max_i
     }
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const int n = last_result.iters_logged;
+    std::vector<int> flags(std::max(1, n), 0);
+    if (n > 0 && aaadmm_geo_reset_flags(geo_, flags.data(), n) != 0) std::cerr << "Error: " << aaadmm_last_error() << std::endl;
     for (int i = 0; i < n; ++i) {
         function_values_.push_back(hist[i]);
         elapsed_time_.push_back(secs * (i + 1) / n);
+        Anderson_reset_.push_back(flags[i] != 0);
     }
     reset_count = last_result.rejects;
+}
+
+template <unsigned int N>
+void GeometrySolverBase<N>::output_iteration_history(SolverType solver_type) {
+    const int n_iter = (int)function_values_.size();
+    for (int i = 0; i < n_iter; ++i) {
+        std::cout << "Iteration " << i << ": ";
+        std::cout << std::setprecision(6) << elapsed_time_[i] << " secs, ";
+        std::cout << " target value " << std::setprecision(16) << function_values_[i];
+        if (solver_type == AA_SOLVER && i < (int)Anderson_reset_.size() && Anderson_reset_[i]) std::cout << " (reject accelerator)";
+        std::cout << std::endl;
+    }
+    std::cout << std::endl;
 }
 
 template <unsigned int N>

@@ -13,6 +13,7 @@
 // by setup_ADMM (returns false), as SURVEY 8b prescribes.
 #pragma once
 #include <cmath>
+#include <deque>
 #include <memory>
 #include <string>
 #include <vector>
@@ -115,6 +116,8 @@ public:
 };
 
 enum SPDSolverType { LDLT_SOLVER, LLT_SOLVER, CG_SOLVER };
+// Geometry/SolverCommon.h:41-44
+enum SolverType { SHAPE_UP_SOLVER, AA_SOLVER };
 
 // Both solver classes of the reference share their interface; the variant picks the setup matrices
 // and the device loop (AAADMM_GEO_ALM / AAADMM_GEO_GS).
@@ -140,6 +143,12 @@ public:
     const MatrixNX &get_solution() { return default_x_; }
     void save(int Anderson_m);
 
+    // Geometry/ALMGeometrySolver.h:322-340: one line per logged iteration (time, residual, "(reject accelerator)")
+    void output_iteration_history(SolverType solver_type);
+
+    // History of iterations (Geometry/ALMGeometrySolver.h:391-393). Anderson_reset_[i]: iteration i was logged right after
+    // a reset of the accelerator (the reference declares the member but never fills it).
+    std::deque<bool> Anderson_reset_;
     std::vector<double> function_values_, elapsed_time_;
     int reset_count = 0;
     aaadmm_step_result last_result;

@@ -1,5 +1,7 @@
 #include "MeshIO.hpp"
 
+#include <algorithm>
+
 #include <cmath>
 #include <cstdio>
 #include <fstream>
@@ -229,6 +231,35 @@ bool save_elenode(const TetMesh *mesh, std::string file) {
 namespace binding {
 
 // AddMeshes.hpp:97-177
+}  // namespace binding
+
+namespace mcl {
+void TetMesh::surface_inds(std::vector<int> &surf_inds) {
+    // a face is on the surface when it belongs to one tet only
+    std::vector<std::array<int, 3>> faces;
+    faces.reserve(tets.size() * 4);
+    static const int fc[4][3] = {{0, 1, 2}, {0, 1, 3}, {0, 2, 3}, {1, 2, 3}};
+    for (const Vec4i &t : tets)
+        for (int f = 0; f < 4; ++f) {
+            std::array<int, 3> k = {t[fc[f][0]], t[fc[f][1]], t[fc[f][2]]};
+            std::sort(k.begin(), k.end());
+            faces.push_back(k);
+        }
+    std::sort(faces.begin(), faces.end());
+    std::vector<char> on(vertices.size(), 0);
+    for (size_t i = 0; i < faces.size();) {
+        size_t j = i + 1;
+        while (j < faces.size() && faces[j] == faces[i]) ++j;
+        if (j - i == 1)
+            for (int v : faces[i]) on[v] = 1;
+        i = j;
+    }
+    for (size_t v = 0; v < on.size(); ++v)
+        if (on[v]) surf_inds.push_back((int)v);
+}
+}  // namespace mcl
+
+namespace binding {
 void add_tetmesh(admm::Solver *solver, std::shared_ptr<mcl::TetMesh> &mesh, const admm::Lame &lame, bool verbose) {
     const int num_tet_verts = (int)mesh->vertices.size();
     const int prev_tet_verts = (int)solver->m_x.size() / 3;
@@ -245,6 +276,11 @@ void add_tetmesh(admm::Solver *solver, std::shared_ptr<mcl::TetMesh> &mesh, cons
             solver->m_x[(size_t)(i + prev_tet_verts) * 3 + j] = (double)mesh->vertices[i][j];
             solver->m_masses[(size_t)(i + prev_tet_verts) * 3 + j] = (double)masses[i];
         }
+    {  // AddMeshes.hpp:130-136
+        std::vector<int> surf_inds;
+        mesh->surface_inds(surf_inds);
+        for (int i : surf_inds) solver->surface_inds.emplace_back(i + prev_tet_verts);
+    }
     const float *verts = num_tet_verts ? &mesh->vertices[0][0] : nullptr;
     const int *tets = num_tets ? &mesh->tets[0][0] : nullptr;
     if ((mesh->flags & LINEAR) || mesh->flags == 0)

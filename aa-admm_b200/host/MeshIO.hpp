@@ -32,6 +32,8 @@ public:
     std::vector<Vec4i> tets;
     int flags = 0;
     void weighted_masses(std::vector<float> &m, float density_kgm3 = 1100.0f);
+    // vertices of the faces that belong to exactly one tet (MCL/TetMesh.hpp:317-342; ascending here, hash order there)
+    void surface_inds(std::vector<int> &surf_inds);
     void clear() {
         vertices.clear();
         tets.clear();

@@ -156,6 +156,23 @@ void Solver::add_obstacle(std::shared_ptr<PassiveCollision> obj) {
     m_obstacles.push_back(obj);
 }
 
+void Solver::add_dynamic_collider(std::shared_ptr<PassiveCollision>) {
+    throw std::runtime_error("admm::Solver (B200): dynamic (triangle-mesh) colliders are not part of the device path");
+}
+
+void Solver::save_matrix(const std::string &filename) {
+    if (!initialized) throw std::runtime_error("**Solver::save_matrix Error: not initialized");
+    const aaadmm::SymLower &A = m_sys.Ahat;
+    const int64_t n3 = 3 * (int64_t)A.n, nnz3 = 3 * A.p[A.n];
+    std::cout << "Saving matrix (" << n3 << "x" << n3 << ") to " << filename << std::endl;
+    std::ofstream ofs(filename.c_str());
+    ofs << "%%MatrixMarket matrix coordinate real symmetric\n% solver_termA = Ahat (x) I3, lower triangle, dof = 3 * free vertex + axis\n";
+    ofs << n3 << " " << n3 << " " << nnz3 << "\n" << std::setprecision(17);
+    for (int j = 0; j < A.n; ++j)
+        for (int64_t p = A.p[j]; p < A.p[j + 1]; ++p)
+            for (int c = 0; c < 3; ++c) ofs << 3 * (int64_t)A.i[p] + c + 1 << " " << 3 * (int64_t)j + c + 1 << " " << A.x[p] << "\n";
+}
+
 void Solver::set_external_factor(int n, const int64_t *Lp, const int *Li, const double *Lx, const double *D,
                                  const int *perm) {
     if (n <= 0 || !Lp || !D || !perm || (Lp[n] > 0 && (!Li || !Lx)))
@@ -486,8 +503,11 @@ void Solver::step() {
     // the device loop is not split into the reference's three timers; report it as one figure
     m_runtime.global_ms = 0;
     m_runtime.local_ms = r.loop_ms;
+    // cumulative device time at which every logged iteration finished (globaltimer stamps of the logging CTA), as the
+    // reference logs it (hard/src/Solver.cpp:210-212): a rejected iteration shows its extra local step and solve
     m_runtime.step_time.assign(r.iters_logged, 0.0);
-    for (int i = 0; i < r.iters_logged; ++i) m_runtime.step_time[i] = r.loop_ms * (i + 1) / std::max(1, r.iters_logged);
+    if (r.iters_logged > 0 && aaadmm_tetscene_iteration_times(m_scene, m_runtime.step_time.data(), r.iters_logged) != 0)
+        throw std::runtime_error(std::string("aaadmm_tetscene_iteration_times: ") + aaadmm_last_error());
     (void)t0;
     if (m_settings.verbose > 0) m_runtime.print(m_settings);
     if (m_settings.write_residual_file) save();

@@ -14,6 +14,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/aaadmm.h"
@@ -236,7 +237,35 @@ public:
     Solver(const Solver &) = delete;
     Solver &operator=(const Solver &) = delete;
 
-    std::vector<double> m_x, m_v, m_masses;  // per node x3
+    // Node data, scaled x3. The reference's VecX (Eigen::VectorXd) is a std::vector<double> with the handful of Eigen
+    // members its samples use on these three vectors: segment<3>(i), rows(), setZero().
+    class VecX : public std::vector<double> {
+    public:
+        using std::vector<double>::vector;
+        using std::vector<double>::operator=;
+        template <int N>
+        struct Segment {
+            double *p;
+            double &operator[](int k) { return p[k]; }
+            double operator[](int k) const { return p[k]; }
+            template <typename V>
+            Segment &operator=(const V &v) {
+                for (int k = 0; k < N; ++k) p[k] = v[k];
+                return *this;
+            }
+            operator std::array<double, N>() const {
+                std::array<double, N> a;
+                for (int k = 0; k < N; ++k) a[k] = p[k];
+                return a;
+            }
+        };
+        template <int N>
+        Segment<N> segment(int i) { return Segment<N>{data() + i}; }
+        int rows() const { return (int)size(); }
+        void setZero() { std::fill(begin(), end(), 0.0); }
+    };
+    VecX m_x, m_v, m_masses;         // per node x3
+    std::vector<int> surface_inds;   // indices of surface vertices (filled by binding::add_tetmesh)
     std::vector<std::shared_ptr<EnergyTerm>> energyterms;
     std::vector<std::shared_ptr<ExplicitForce>> ext_forces;
 
@@ -256,10 +285,25 @@ public:
     }
 
     void set_pins(const std::vector<int> &inds, const std::vector<Vec3> &points = std::vector<Vec3>());
+    // any other 3-vector type with operator[] (the reference passes std::vector<Eigen::Vector3d>)
+    template <typename V3, typename = typename std::enable_if<!std::is_same<V3, Vec3>::value>::type>
+    void set_pins(const std::vector<int> &inds, const std::vector<V3> &points) {
+        std::vector<Vec3> p(points.size());
+        for (size_t i = 0; i < points.size(); ++i) p[i] = {(double)points[i][0], (double)points[i][1], (double)points[i][2]};
+        set_pins(inds, p);
+    }
     // hard/src/Solver.cpp:318-348: the listed vertices get one Collision energy term each at initialize();
     // obstacles must be added before initialize() (the device scene keeps their parameters).
     void set_collisions(const std::vector<int> &inds, const std::vector<Vec3> &points = std::vector<Vec3>());
     void add_obstacle(std::shared_ptr<PassiveCollision> obj);
+    // hard/src/Solver.hpp:113: a dynamic obstacle has its vertices in m_x and is updated every frame. Triangle-mesh
+    // obstacles (DynamicCollision / PassiveMesh and the BVH behind them) are outside the device path:
+    // throws std::runtime_error, nothing is silently ignored.
+    void add_dynamic_collider(std::shared_ptr<PassiveCollision> obj);
+    // hard/src/Solver.hpp:125, Solver.cpp:493-498: writes solver_termA = M + rho dt^2 D^T W^2 D of the last initialize()
+    // (3 n_free x 3 n_free, = Ahat (x) I3) as a Matrix Market coordinate file (symmetric, lower triangle; the reference
+    // streams Eigen's text dump of the same matrix)
+    void save_matrix(const std::string &filename);
     // Calling initialize() again on a Solver whose nodes, elements, pins and collision set are unchanged (only the
     // elements' Lame parameters, the time step or the penalty differ: the next member of a parameter sweep) keeps the
     // whole analysis and every device buffer and redoes the numeric part only (system-matrix values, numeric LDL^T on

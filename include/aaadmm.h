@@ -171,6 +171,10 @@ int aaadmm_tetscene_step(aaadmm_tetscene *s, const aaadmm_step_opts *opts, const
 /* Same loop with inputs already resident (the x_bar / x_pin of the last aaadmm_tetscene_step
  * call are reused) and nothing copied back: used to time the HBM-resident rate. */
 int aaadmm_tetscene_step_resident(aaadmm_tetscene *s, const aaadmm_step_opts *opts, aaadmm_step_result *result);
+/* Device time stamps of the last step's logged iterations: ms[i] = milliseconds from the start of the iteration loop
+ * (after the warm start) to the moment iteration i was logged (%globaltimer in the CTA that writes the log), the
+ * cumulative times the reference writes to ./result/residual-*.txt (hard/src/Solver.cpp:210-212). n <= rows logged. */
+int aaadmm_tetscene_iteration_times(aaadmm_tetscene *s, double *ms, int n);
 /* Debug/parity access: copies z (9*n_tets, reference layout: 9 consecutive doubles per tet)
  * and u of the last step to the host. */
 int aaadmm_tetscene_read_zu(aaadmm_tetscene *s, double *z, double *u);
@@ -237,6 +241,9 @@ int aaadmm_geo_destroy(aaadmm_geo *g);
  * anderson_m <= 0 runs plain ADMM. result->iters_logged = accepted iterations, ->rejects = resets. */
 int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int anderson_m, double *x_out, double *hist,
                      aaadmm_step_result *result);
+/* Per logged iteration of the last aaadmm_geo_solve: 1 if it follows a reset of the accelerator (the iterate before it
+ * was rejected), the flag the reference's solvers keep in Anderson_reset_ (Geometry/ALMGeometrySolver.h:391). */
+int aaadmm_geo_reset_flags(aaadmm_geo *g, int *flags, int n);
 /* unit parity: project `n` constraints of one type on already transformed columns (3 per column, host) */
 int aaadmm_geo_project(int type, int n, int k, const double *cols, const double *param4, double *out);
 /* unit parity: nearest points on a triangle mesh for nq host queries */

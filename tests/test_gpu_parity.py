@@ -782,3 +782,29 @@ def test_pipelined_sweep_on_resident_scene_slots(gpu):
             _, h, _ = run_product(gpu, beam_arrays(gpu, *dims), 1, iters=60, m=5, accel=True, youngs=youngs, poisson=poisson)
             assert int(r[1]) == len(h[0]) and int(r[2]) == int(h[0][:, 2].sum())
             assert r[3] == h[0][-1, 0] and r[4] == h[0][-1, 1]
+
+
+def test_save_matrix_and_iteration_time_stamps(gpu, ref, tmp_path):
+    """Solver::save_matrix (solver_termA as Matrix Market, equal to the reference's solver_termA) and the cumulative
+    per-iteration device times of RuntimeData::step_time (globaltimer stamps of the logging CTA)."""
+    import subprocess
+    import scipy.io
+    from test_host_cpu import _build_harness
+    exe = _build_harness(tmp_path, "solver_surface_harness")
+    path = str(tmp_path / "A.mtx")
+    r = subprocess.run([exe, "6", path], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    print(r.stdout)
+    Amm = scipy.io.mmread(path).toarray()
+    scene = beam_arrays(gpu, 6, 2, 2)
+    verts, tets, masses, pidx, ppts, pside = scene.arrays()
+    rs = ref.RefSolver("hard")
+    rs.add_tetmesh(verts, tets, masses, 1e7, 0.399, 0)
+    rs.set_pins(pidx, ppts)
+    rs.initialize(1.0 / 30.0, 40, -9.8, 5, True, 1.0)
+    n, rp, ci, v = rs.termA()
+    Aref = np.zeros((n, n))
+    for i in range(n):
+        Aref[i, ci[rp[i]:rp[i + 1]]] = v[rp[i]:rp[i + 1]]
+    assert Amm.shape == Aref.shape
+    assert np.abs(Amm - Aref).max() <= 1e-12 * np.abs(Aref).max()

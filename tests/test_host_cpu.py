@@ -560,3 +560,23 @@ def test_geometry_samples_compile_and_report_missing_files(A, tmp_path, name):
     assert r.returncode == 1 and "Usage" in r.stdout
     r = subprocess.run([exe, "nothing.obj", "nothing.obj", "nothing.txt", "out.obj"], capture_output=True, text=True)
     assert r.returncode == 1 and "unable to read" in r.stderr
+
+
+def _build_harness(tmp_path, name):
+    exe = str(tmp_path / name)
+    cmd = ["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "aa-admm_b200", "host"),
+           os.path.join(ROOT, "tests", "tools", name + ".cpp"), "-L" + os.path.join(ROOT, "aa-admm_b200"), "-laaadmm_host", "-laaadmm_b200",
+           "-Wl,-rpath," + os.path.join(ROOT, "aa-admm_b200"), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_solver_public_members_beyond_the_hot_path(A, tmp_path):
+    """surface_inds (binding::add_tetmesh), Eigen-style m_x access, set_pins with a foreign 3-vector type,
+    add_dynamic_collider (throws): tests/tools/solver_surface_harness.cpp. With a GPU the same program also checks
+    save_matrix and the per-iteration device time stamps (tests/test_gpu_parity.py)."""
+    exe = _build_harness(tmp_path, "solver_surface_harness")
+    r = subprocess.run([exe, "5", str(tmp_path / "A.mtx")], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "surface_inds" in r.stdout
