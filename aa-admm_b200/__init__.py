@@ -934,3 +934,46 @@ def geoapp_optimize(app, mesh, ref_mesh, max_iter, anderson_m, prm):
     _hk(H.aaadmm_host_geoapp_optimize(0 if app == "planarity" else 1, mesh.h, ref_mesh.h, max_iter, anderson_m, _dp(prm),
                                       _dp(hist), C.byref(n), _dp(sol), _dp(info)))
     return hist[:n.value], sol, dict(loop_ms=info[0], resets=int(info[1]))
+
+
+class GeoApp:
+    """geoapp::GeoApp: one of the two Geometry applications with the setup kept (constraints, system matrix,
+    factorisation, device upload once); solve() runs solve_ADMM from the mesh's own positions."""
+
+    def __init__(self, app, mesh, ref_mesh, prm):
+        H = PolyMesh._lib()
+        H.aaadmm_host_geoapp_new.restype = C.c_void_p
+        H.aaadmm_host_geoapp_new.argtypes = [C.c_int, C.c_void_p, C.c_void_p, c_dp]
+        H.aaadmm_host_geoapp_free.argtypes = [C.c_void_p]
+        H.aaadmm_host_geoapp_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, c_dp, c_ip, c_dp, c_dp]
+        H.aaadmm_host_geoapp_stats.argtypes = [C.c_void_p, c_dp]
+        self.H = H
+        prm = np.ascontiguousarray(prm, np.float64)
+        self.n_points = mesh.counts()["vertices"]
+        h = H.aaadmm_host_geoapp_new(0 if app == "planarity" else 1, mesh.h, ref_mesh.h, _dp(prm))
+        if not h:
+            raise AaadmmError(H.aaadmm_host_last_error().decode())
+        self.h = C.c_void_p(h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.H.aaadmm_host_geoapp_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def solve(self, max_iter, anderson_m, want_solution=True):
+        hist = np.zeros(max(1, max_iter))
+        n = C.c_int(0)
+        sol = np.zeros((self.n_points, 3)) if want_solution else None
+        info = np.zeros(4)
+        _hk(self.H.aaadmm_host_geoapp_solve(self.h, max_iter, anderson_m, _dp(hist), C.byref(n), _dp(sol) if want_solution else None,
+                                            _dp(info)))
+        return hist[:n.value], sol, dict(loop_ms=info[0], resets=int(info[1]), kernel_launches=int(info[2]), wall_ms=info[3])
+
+    def stats(self):
+        s = np.zeros(8)
+        self.H.aaadmm_host_geoapp_stats(self.h, _dp(s))
+        return dict(points=int(s[0]), hard_constraints=int(s[1]), z_columns=int(s[2]), soft_constraints=int(s[3]),
+                    nnz_L=int(s[4]), fronts=int(s[5]), levels=int(s[6]), bytes_per_apply=float(s[7]))

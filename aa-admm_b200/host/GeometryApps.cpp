@@ -343,12 +343,9 @@ void boundary_fan(const Connectivity &C, int n_vertices, std::vector<std::vector
 }
 }  // namespace
 
-OptimizeResult planarity_optimize(const PolyMesh &mesh, const PolyMesh &ref_mesh, int max_iter, int Anderson_m, double penalty,
-                                  double closeness_weight, double laplacian_weight, double relative_laplacian_weight,
-                                  bool save_history) {
-    Matrix3X p;
-    to_matrix(mesh, p);
-    ALMGeometrySolver<3> solver;
+namespace {
+void planarity_constraints(ALMGeometrySolver<3> &solver, const PolyMesh &mesh, const PolyMesh &ref_mesh, const Matrix3X &p,
+                           double closeness_weight, double laplacian_weight, double relative_laplacian_weight) {
     std::shared_ptr<TriMeshAABB> aabb = std::make_shared<TriMeshAABB>();
     aabb->verts = ref_mesh.V;
     aabb->tris = triangles_of(ref_mesh);
@@ -379,16 +376,25 @@ OptimizeResult planarity_optimize(const PolyMesh &mesh, const PolyMesh &ref_mesh
     for (int f = 0; f < mesh.n_faces(); ++f)
         if (mesh.valence(f) > 3)
             solver.add_hard_constraint(new PlaneConstraint(std::vector<int>(mesh.face(f), mesh.face(f) + mesh.valence(f)), 1.0));
+}
+}  // namespace
+
+OptimizeResult planarity_optimize(const PolyMesh &mesh, const PolyMesh &ref_mesh, int max_iter, int Anderson_m, double penalty,
+                                  double closeness_weight, double laplacian_weight, double relative_laplacian_weight,
+                                  bool save_history) {
+    Matrix3X p;
+    to_matrix(mesh, p);
+    ALMGeometrySolver<3> solver;
+    planarity_constraints(solver, mesh, ref_mesh, p, closeness_weight, laplacian_weight, relative_laplacian_weight);
     return finish(solver, mesh, p, penalty, max_iter, Anderson_m, save_history);
 }
 
-OptimizeResult wiremesh_optimize(const PolyMesh &mesh, const PolyMesh &ref_mesh, int max_iter, int Anderson_m, double penalty,
-                                 double min_angle_radian, double max_angle_radian, double edge_length, double closeness_weight,
-                                 double laplacian_weight, bool save_history) {
-    Matrix3X p, ref_pts;
-    to_matrix(mesh, p);
+namespace {
+void wiremesh_constraints(ALMGeometrySolver<3> &solver, const PolyMesh &mesh, const PolyMesh &ref_mesh, const Matrix3X &p,
+                          double min_angle_radian, double max_angle_radian, double edge_length, double closeness_weight,
+                          double laplacian_weight) {
+    Matrix3X ref_pts;
     to_matrix(ref_mesh, ref_pts);
-    ALMGeometrySolver<3> solver;
     if (closeness_weight > 0)
         solver.add_soft_constraint(new ReferenceSurfceConstraint(p.cols(), closeness_weight, ref_pts, triangles_of(ref_mesh)));
     for (int f = 0; f < mesh.n_faces(); ++f) {
@@ -422,7 +428,53 @@ OptimizeResult wiremesh_optimize(const PolyMesh &mesh, const PolyMesh &ref_mesh,
             }
         }
     }
+}
+}  // namespace
+
+OptimizeResult wiremesh_optimize(const PolyMesh &mesh, const PolyMesh &ref_mesh, int max_iter, int Anderson_m, double penalty,
+                                 double min_angle_radian, double max_angle_radian, double edge_length, double closeness_weight,
+                                 double laplacian_weight, bool save_history) {
+    Matrix3X p;
+    to_matrix(mesh, p);
+    ALMGeometrySolver<3> solver;
+    wiremesh_constraints(solver, mesh, ref_mesh, p, min_angle_radian, max_angle_radian, edge_length, closeness_weight, laplacian_weight);
     return finish(solver, mesh, p, penalty, max_iter, Anderson_m, save_history);
+}
+
+GeoApp::GeoApp(Kind kind, const PolyMesh &mesh, const PolyMesh &ref_mesh, const double *prm) : mesh_(mesh) {
+    to_matrix(mesh_, p_);
+    if (kind == PLANARITY)
+        planarity_constraints(solver_, mesh_, ref_mesh, p_, prm[1], prm[2], prm[3]);
+    else
+        wiremesh_constraints(solver_, mesh_, ref_mesh, p_, prm[1], prm[2], prm[3], prm[4], prm[5]);
+    ok_ = solver_.setup_ADMM(p_.cols(), prm[0]);
+    if (!ok_) std::cerr << "Error: unable to initialize solver" << std::endl;
+}
+
+void GeoApp::stats(double *out8) {
+    for (int i = 0; i < 4; ++i) out8[i] = solver_.setup_counts[i];
+    double st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (solver_.device_factor()) aaadmm_ldlt_stats(solver_.device_factor(), st);
+    out8[4] = st[4];
+    out8[5] = st[1];
+    out8[6] = st[2];
+    out8[7] = st[7];
+}
+
+OptimizeResult GeoApp::solve(int max_iter, int Anderson_m, bool save_history) {
+    OptimizeResult R;
+    if (!ok_) return R;
+    const size_t before = solver_.function_values_.size();
+    solver_.solve_ADMM(p_, 1e-8 * average_edge_length(mesh_), max_iter, Anderson_m);
+    if (save_history) solver_.save(Anderson_m);
+    R.ok = true;
+    R.function_values.assign(solver_.function_values_.begin() + before, solver_.function_values_.end());
+    R.elapsed_time.assign(solver_.elapsed_time_.begin() + before, solver_.elapsed_time_.end());
+    R.resets = solver_.reset_count;
+    R.mesh = mesh_;
+    const Matrix3X &x = solver_.get_solution();
+    std::copy(x.data(), x.data() + x.size(), R.mesh.V.begin());
+    return R;
 }
 
 // ---- reports --------------------------------------------------------------------------------------------------------

@@ -84,6 +84,27 @@ OptimizeResult wiremesh_optimize(const PolyMesh &mesh, const PolyMesh &ref_mesh,
                                  double edge_length, double closeness_weight, double laplacian_weight,
                                  bool save_history = true);
 
+// The same two recipes with the setup kept: build once (constraints, setup_ADMM = system matrix + factorisation + device
+// upload), then solve any number of times from the mesh's own positions (what a bench step or a parameter study does).
+class GeoApp {
+public:
+    enum Kind { PLANARITY = 0, WIREMESH = 1 };
+    // prm: PLANARITY {penalty, closeness_w, laplacian_w, relative_laplacian_w};
+    //      WIREMESH  {penalty, min_angle, max_angle, edge_length, closeness_w, laplacian_w}
+    GeoApp(Kind kind, const PolyMesh &mesh, const PolyMesh &ref_mesh, const double *prm);
+    bool ok() const { return ok_; }
+    OptimizeResult solve(int max_iter, int Anderson_m, bool save_history = false);
+    const aaadmm_step_result &last_result() const { return solver_.last_result; }
+    // out8 = points, hard constraints, columns of z / u, soft constraints (one per point or one batch), nnz(L), fronts,
+    // tree levels, algorithmic bytes of one factor apply
+    void stats(double *out8);
+private:
+    ALMGeometrySolver<3> solver_;
+    PolyMesh mesh_;
+    Matrix3X p_;
+    bool ok_ = false;
+};
+
 // Reports of the reference's mains (normalised by the average edge length): per-face planarity error
 // (PlanarityOpt.cpp:57-107) and distance to the reference surface (PlanarityOpt.cpp:109-132; needs the GPU library).
 void planarity_error(const PolyMesh &mesh, std::vector<double> &per_face, double *max_err, double *mean_err);

@@ -238,6 +238,10 @@ bool GeometrySolverBase<N>::setup_ADMM(int n_points, double penalty_param, SPDSo
         std::cerr << "Error: " << aaadmm_last_error() << std::endl;
         return false;
     }
+    setup_counts[0] = n_points;
+    setup_counts[1] = nh;
+    setup_counts[2] = zc;
+    setup_counts[3] = (int)soft_constraints_.size();
     solver_initialized_ = true;
     return true;
 }

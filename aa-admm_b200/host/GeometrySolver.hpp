@@ -151,6 +151,9 @@ public:
     std::deque<bool> Anderson_reset_;
     std::vector<double> function_values_, elapsed_time_;
     int reset_count = 0;
+    // sizes of the last setup_ADMM (measurement reports): points, hard constraints, columns of z / u, soft constraints
+    aaadmm_ldlt *device_factor() { return ldlt_; }
+    int setup_counts[4] = {0, 0, 0, 0};
     aaadmm_step_result last_result;
 
 protected:

@@ -214,9 +214,91 @@ bool Solver::initialize(const Settings &settings_) {
         t_stage = t;
     };
     const int n_verts = dof / 3;
+    const double dt2_ = m_settings.timestep_s * m_settings.timestep_s;
+    const double rho_ = (m_settings.ordering == Settings::HARD_ZXU) ? m_settings.penalty : 1.0;
+    // numeric part of a re-initialisation: element moduli, VALUES of the system matrix, numeric LDL^T on the device
+    auto refresh_numeric = [&](const double *ey, const double *ep, const aaadmm::TriInput *ti) -> bool {
+        if (!aaadmm::update_tet_system_materials(m_sys, ey, ep, rho_ * dt2_, ti)) throw std::runtime_error(m_sys.error);
+        stage("moduli + values of the system matrix");
+        if (aaadmm_ldlt_refactor(m_ldlt, m_sys.Ahat.x.data()) != 0) {
+            std::cerr << "\n**Solver Error: LDLT factorization failed: " << aaadmm_last_error() << std::endl;
+            initialized = false;
+            return false;
+        }
+        stage("numeric factorisation (device)");
+        if (aaadmm_tetscene_update_material(m_scene, m_sys.weight.data(), m_sys.kvol.data(), m_sys.mu.data(), m_sys.lambda.data(),
+                                            m_sys.tri_weight.data(), m_sys.tri_limit_min.data(), m_sys.tri_limit_max.data(),
+                                            rho_ * dt2_) != 0)
+            throw std::runtime_error(std::string("aaadmm_tetscene_update_material: ") + aaadmm_last_error());
+        stage("device scene: moduli");
+        m_runtime.initialization_ms = now_ms() - t0;
+        reinitialized = true;
+        initialized = true;
+        return true;
+    };
+    // ---- the very same objects as at the last initialize() (energy-term pointers, masses, pin / collision sets,
+    // obstacles, ordering): nothing structural can have changed (the geometry of an energy term is fixed by its
+    // constructor), only the terms' Lame parameters, the time step or the penalty. No batch is rebuilt.
+    uint64_t ikey = 1469598103934665603ull;
+    auto imix = [&](const void *p, size_t bytes) {
+        const unsigned char *c = static_cast<const unsigned char *>(p);
+        size_t i = 0;
+        for (; i + 8 <= bytes; i += 8) {
+            uint64_t w;
+            memcpy(&w, c + i, 8);
+            ikey = (ikey ^ w) * 1099511628211ull;
+            ikey ^= ikey >> 29;
+        }
+        for (; i < bytes; ++i) ikey = (ikey ^ c[i]) * 1099511628211ull;
+    };
+    {
+        const int hdr[4] = {n_verts, (int)energyterms.size(), (int)m_settings.ordering, (int)m_obstacles.size()};
+        imix(hdr, sizeof(hdr));
+        for (auto &e : energyterms) {
+            const void *ptr = e.get();
+            imix(&ptr, sizeof(ptr));
+        }
+        imix(m_masses.data(), m_masses.size() * sizeof(double));
+        for (auto &kv : m_pins) imix(&kv.first, sizeof(int));
+        const int sep = -1;
+        imix(&sep, sizeof(int));
+        for (auto &kv : m_collisions) imix(&kv.first, sizeof(int));
+        for (auto &o : m_obstacles) {
+            imix(&o->type, sizeof(int));
+            imix(o->prm.data(), sizeof(double) * o->prm.size());
+        }
+    }
+    if (m_scene && m_ldlt && device_numeric && !factor_external && ikey == m_identity_key &&
+        m_term_is_tri.size() == energyterms.size()) {
+        std::vector<double> ey((size_t)std::max(m_sys.n_tets, 1)), ep((size_t)std::max(m_sys.n_tets, 1));
+        std::vector<double> ty((size_t)std::max(m_sys.n_tris, 1)), tp(ty.size()), tmin(ty.size()), tmax(ty.size());
+        int nt = 0, ntri = 0;
+        for (size_t i = 0; i < energyterms.size(); ++i) {
+            if (!m_term_is_tri[i]) {
+                const TetEnergyTerm *e = static_cast<const TetEnergyTerm *>(energyterms[i].get());
+                ey[nt] = e->lame.youngs;
+                ep[nt++] = e->lame.poisson;
+            } else {
+                const TriEnergyTerm *e = static_cast<const TriEnergyTerm *>(energyterms[i].get());
+                ty[ntri] = e->lame.youngs;
+                tp[ntri] = e->lame.poisson;
+                tmin[ntri] = e->lame.limit_min;
+                tmax[ntri++] = e->lame.limit_max;
+            }
+        }
+        aaadmm::TriInput ti;
+        ti.n_tris = m_sys.n_tris;
+        ti.youngs = ty.data();
+        ti.poisson = tp.data();
+        ti.limit_min = tmin.data();
+        ti.limit_max = tmax.data();
+        stage("element moduli (same energy-term objects as before)");
+        return refresh_numeric(ey.data(), ep.data(), &ti);
+    }
     // energy terms -> SoA batches (tets, then triangles; the order inside z does not enter the iteration)
     std::vector<double> rest12, youngs, poisson, rest9, tri_youngs, tri_poisson, tri_lmin, tri_lmax;
     std::vector<int> tets, material, tris;
+    m_term_is_tri.assign(energyterms.size(), 0);
     for (size_t i = 0; i < energyterms.size(); ++i) {
         if (energyterms[i]->get_weight() <= 0.0)
             throw std::runtime_error("**EnergyTerm::get_reduction Error: Some weight leq 0");
@@ -229,6 +311,7 @@ bool Solver::initialize(const Settings &settings_) {
             poisson.push_back(e->lame.poisson);
             material.push_back(e->material);
         } else if (const TriEnergyTerm *e = dynamic_cast<const TriEnergyTerm *>(energyterms[i].get())) {
+            m_term_is_tri[i] = 1;
             for (int k = 0; k < 3; ++k) {
                 tris.push_back(e->tri[k]);
                 for (int j = 0; j < 3; ++j) rest9.push_back(e->rest[k][j]);
@@ -312,24 +395,8 @@ bool Solver::initialize(const Settings &settings_) {
     }
     stage("energy terms -> batches, structure key");
     if (m_scene && m_ldlt && device_numeric && skey == m_structure_key && !factor_external) {
-        if (!aaadmm::update_tet_system_materials(m_sys, youngs.data(), poisson.data(), rho * dt2, &tri_in))
-            throw std::runtime_error(m_sys.error);
-        stage("moduli + values of the system matrix");
-        if (aaadmm_ldlt_refactor(m_ldlt, m_sys.Ahat.x.data()) != 0) {
-            std::cerr << "\n**Solver Error: LDLT factorization failed: " << aaadmm_last_error() << std::endl;
-            initialized = false;
-            return false;
-        }
-        stage("numeric factorisation (device)");
-        if (aaadmm_tetscene_update_material(m_scene, m_sys.weight.data(), m_sys.kvol.data(), m_sys.mu.data(), m_sys.lambda.data(),
-                                            m_sys.tri_weight.data(), m_sys.tri_limit_min.data(), m_sys.tri_limit_max.data(),
-                                            rho * dt2) != 0)
-            throw std::runtime_error(std::string("aaadmm_tetscene_update_material: ") + aaadmm_last_error());
-        stage("device scene: moduli");
-        m_runtime.initialization_ms = now_ms() - t0;
-        reinitialized = true;
-        initialized = true;
-        return true;
+        m_identity_key = ikey;
+        return refresh_numeric(youngs.data(), poisson.data(), &tri_in);
     }
     reinitialized = false;
     if (!aaadmm::build_tet_system(m_sys, n_verts, rest12.data(), n_tets, tets.data(), material.data(), youngs.data(),
@@ -393,6 +460,7 @@ bool Solver::initialize(const Settings &settings_) {
         stage("device factor (fronts, [Linv ; Q], schedules)");
     }
     m_structure_key = skey;
+    m_identity_key = ikey;
     aaadmm_tetscene_desc d = {};
     d.n_tris = m_sys.n_tris;
     d.tri = m_sys.tri_dev.data();

@@ -350,6 +350,8 @@ protected:
     bool device_numeric = false;       // the factor's values were computed on the device (re-initialisation can refactor)
     bool reinitialized = false;        // the last initialize() took the fast path (same structure, new moduli)
     uint64_t m_structure_key = 0;      // hash of mesh, terms, pins, collision set of the last full initialize()
+    uint64_t m_identity_key = 0;       // hash of the energy-term POINTERS, masses, pin / collision sets of the last initialize()
+    std::vector<char> m_term_is_tri;   // per energy term: 0 tet, 1 triangle (as found at the last full pass over the terms)
     bool factor_external = false;      // m_factor was handed in through set_external_factor
     bool factor_from_cache = false;    // the last initialize() took the factor from Settings::factor_cache
     std::vector<int> slot_of_node;  // index among the free nodes (positive_pin) or among the pinned ones

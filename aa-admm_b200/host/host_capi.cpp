@@ -684,4 +684,46 @@ int aaadmm_host_geoapp_optimize(int app, void *mesh_h, void *ref_h, int max_iter
     return 0;
     HOST_CATCH
 }
+// GeoApp: setup once, solve repeatedly (bench steps). kind 0 planarity, 1 wiremesh; prm as aaadmm_host_geoapp_optimize.
+void *aaadmm_host_geoapp_new(int kind, void *mesh_h, void *ref_h, const double *prm) {
+    try {
+        std::unique_ptr<aaadmm::geoapp::GeoApp> g(new aaadmm::geoapp::GeoApp(
+            kind == 0 ? aaadmm::geoapp::GeoApp::PLANARITY : aaadmm::geoapp::GeoApp::WIREMESH, static_cast<PolyHandle *>(mesh_h)->mesh,
+            static_cast<PolyHandle *>(ref_h)->mesh, prm));
+        if (!g->ok()) {
+            g_err = "geoapp: unable to initialize solver";
+            return nullptr;
+        }
+        return g.release();
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+void aaadmm_host_geoapp_free(void *h) { delete static_cast<aaadmm::geoapp::GeoApp *>(h); }
+int aaadmm_host_geoapp_stats(void *h, double *out8) {
+    static_cast<aaadmm::geoapp::GeoApp *>(h)->stats(out8);
+    return 0;
+}
+// info4 = {device loop ms, resets, kernel launches, wall ms of solve_ADMM}
+int aaadmm_host_geoapp_solve(void *h, int max_iter, int anderson_m, double *hist, int *n_hist, double *solution, double *info4) {
+    HOST_TRY
+    aaadmm::geoapp::GeoApp *g = static_cast<aaadmm::geoapp::GeoApp *>(h);
+    aaadmm::geoapp::OptimizeResult R = g->solve(max_iter, anderson_m, false);
+    if (!R.ok) {
+        g_err = "geoapp: solve failed";
+        return -1;
+    }
+    *n_hist = (int)R.function_values.size();
+    std::copy(R.function_values.begin(), R.function_values.end(), hist);
+    if (solution) std::copy(R.mesh.V.begin(), R.mesh.V.end(), solution);
+    if (info4) {
+        info4[0] = g->last_result().loop_ms;
+        info4[1] = g->last_result().rejects;
+        info4[2] = g->last_result().kernel_launches;
+        info4[3] = R.elapsed_time.empty() ? 0.0 : 1e3 * R.elapsed_time.back();
+    }
+    return 0;
+    HOST_CATCH
+}
 }  // extern "C"

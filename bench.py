@@ -505,6 +505,220 @@ def run_cfg5(args):
     return 0
 
 
+def _golden(path_rel):
+    p = os.path.join(ROOT, path_rel)
+    if not os.path.exists(p):
+        raise SystemExit("bench.py: %s is missing (generated by tests/golden/make_golden_geo.py in the build container; it travels with the snapshot)" % path_rel)
+    return np.load(p)
+
+
+def _write_obj(path, V, faces):
+    with open(path, "w") as f:
+        for v in V:
+            f.write("v %.17g %.17g %.17g\n" % tuple(v))
+        for fc in faces:
+            f.write("f " + " ".join(str(int(i) + 1) for i in fc if i >= 0) + "\n")
+
+
+def _geo_cpu_baseline(which, files, iters, full_iters):
+    """The unmodified reference application (oracle/_ref/libref_planarity.so / libref_wiremesh.so: PlanarityOpt.cpp /
+    WireMeshOpt.cpp main()) on the same mesh files, `iters` iterations, all host cores."""
+    import ctypes as C
+    import tempfile
+    try:
+        cores = _reference_host_threads()
+        lib = os.path.join(ROOT, "oracle", "_ref", "libref_planarity.so" if which == "cfg2" else "libref_wiremesh.so")
+        if not os.path.exists(lib):
+            return {"value": None, "unit": "iterations/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref absent"}
+        L = C.CDLL(lib)
+        with tempfile.TemporaryDirectory() as d:
+            os.makedirs(os.path.join(d, "result"))
+            with open(os.path.join(d, "Options.txt"), "w") as f:
+                f.write("Iterations  %d\nAndersonM  5\n" % iters)
+            argv = [b"app", files[0].encode(), files[1].encode(), os.path.join(d, "Options.txt").encode(), os.path.join(d, "out.obj").encode()]
+            arr = (C.c_char_p * len(argv))(*argv)
+            cwd = os.getcwd()
+            os.chdir(d)
+            try:
+                t0 = time.perf_counter()
+                rc = L.ref_app_main(len(argv), arr)
+                wall = time.perf_counter() - t0
+            finally:
+                os.chdir(cwd)
+            hist = np.loadtxt(os.path.join(d, "result", "residual-5.txt")).reshape(-1, 2)
+        loop_s = float(hist[-1, 0])
+        return {"value": len(hist) / loop_s, "unit": "iterations/s", "cores": cores, "kind": "reference",
+                "sample": "unmodified reference application (%s main) on the same mesh files, %d of the workload's %d iterations, m=5: "
+                          "solve_ADMM loop %.3f s (the application's own timer; its setup and file handling %.1f s excluded), rc %d"
+                          % ("PlanarityOpt" if which == "cfg2" else "WireMeshOpt", len(hist), full_iters, loop_s, wall - loop_s, rc)}
+    except Exception as e:
+        return {"value": None, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (e,)}
+
+
+def run_cfg_geo(args, which):
+    """BASELINE configs[1] / configs[2] (SURVEY 8d cfg 2 / cfg 3): the reference's PlanarityOpt on costa2k_poly (planar
+    quads) and WireMeshOpt on MaleTorso (one subdivision: 230,400 points, 1.38 M hard constraints), 100 iterations, m=5.
+    The meshes come from the golden fixtures (arrays of the reference's shipped files); the product's own front-end
+    (host/GeometryApps) reads them as .obj, subdivides, builds the constraints and sets up once. A bench step = one
+    solve_ADMM of 100 iterations from the input positions."""
+    import tempfile
+    import aa_admm_b200 as A
+    if A.device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    A.set_device(0)
+    iters, m = 100, 5
+    tmp = tempfile.mkdtemp(prefix="aaadmm_bench_")
+    if which == "cfg2":
+        g = _golden("tests/golden/geo_costa2k.npz")
+        files = (os.path.join(tmp, "poly.obj"), os.path.join(tmp, "tri.obj"))
+        _write_obj(files[0], g["P"], g["faces"])
+        _write_obj(files[1], g["Vref"], g["Fref"])
+        name = "cfg2: PlanarityOpt costa2k_poly.obj costa2k_tri.obj (planar quads, closeness, relative Laplacians), rho = 1e5"
+        t0 = time.perf_counter()
+        mesh, ref = A.PolyMesh.load(files[0]), A.PolyMesh.load(files[1])
+        app = A.GeoApp("planarity", mesh, ref, [1e5, 1.0, 0.0, 0.1])
+    else:
+        g = _golden("tests/golden_large/geo_maletorso.npz")
+        files = (os.path.join(tmp, "quad.obj"), os.path.join(tmp, "target.obj"))
+        _write_obj(files[0], g["P0"], g["quads0"])
+        _write_obj(files[1], g["Vref"], g["Fref"])
+        name = "cfg3: WireMeshOpt MaleTorso.obj MaleTorso_target.obj (one subdivision + smoothing, angle / edge-length constraints, closeness), rho = 1e3"
+        t0 = time.perf_counter()
+        coarse, ref = A.PolyMesh.load(files[0]), A.PolyMesh.load(files[1])
+        el = 0.5 * coarse.counts()["average_edge_length"]
+        mesh = coarse.subdivide_and_smooth()
+        app = A.GeoApp("wiremesh", mesh, ref, [1e3, 0.25 * np.pi, 0.75 * np.pi, el, 1.0, -1.0])
+    setup_s = time.perf_counter() - t0
+    st = app.stats()
+    for _ in range(args.warmup):
+        app.solve(iters, m, False)
+    tot_it, loop_ms, wall_s, launches, resets = 0, 0.0, 0.0, 0, 0
+    with ClockSampler(0) as clk:
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            hist, x, info = app.solve(iters, m, True)
+            wall_s += time.perf_counter() - t0
+            tot_it += len(hist)
+            loop_ms += info["loop_ms"]
+            launches += info["kernel_launches"]
+            resets += info["resets"]
+    # algorithmic bytes of one loop turn: the factor apply (every factor value once per sweep + vectors), the hard
+    # constraints (indices, gathered points, z, u, Dx_prev read and written), the right-hand side (rho D^T entries) and the
+    # Anderson passes over [u | x]; the closest-point search adds data-dependent BVH traffic that is not counted
+    P, H, Z = st["points"], st["hard_constraints"], st["z_columns"]
+    N = 3.0 * (Z + P)
+    turn_bytes = st["bytes_per_apply"] + H * 16.0 + Z * 24.0 * 7 + Z * 12.0 * 2 + P * 24.0 * 4 + 8.0 * ((m + 2) * N + 3 * N) + 8.0 * ((m + 3) * N + 2 * N)
+    turns = tot_it + resets
+    ms_turn = loop_ms / max(1, turns)
+    peak, peak_src = measured_peaks()
+    ach = turn_bytes / (ms_turn * 1e-3) / 1e9
+    cpu = None
+    if not args.no_cpu:
+        with _NativeStdoutToStderr():
+            cpu = _geo_cpu_baseline(which, files, 100 if which == "cfg2" else 10, iters)
+    line = {"metric": "admm_anderson_iterations_per_sec_geometry", "value": tot_it / (loop_ms * 1e-3), "unit": "iterations/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": loop_ms / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (arrays of the reference's shipped mesh)",
+            "config": {"workload": name + ", %d iterations, Anderson m=%d; ALMGeometrySolver<3>::solve_ADMM on the device" % (iters, m),
+                       "l2": ("working set of cfg 2 (a few MB) is L2-resident: launch-latency bound" if which == "cfg2" else
+                              "factor + constraint state of cfg 3 (0.3 GB per turn) is larger than the 126 MB L2"),
+                       "sizes": st, "setup_s": round(setup_s, 2), "iterations_timed": tot_it, "rejected_turns": resets,
+                       "final_residual": float(hist[-1])},
+            "roofline": {"bound": "hbm", "kernel": "one loop turn (k_geo_local + k_geo_soft + k_geo_rhs + ldlt_apply + k_geo_u_resid + Anderson passes)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "ms_per_turn": ms_turn, "algo_GB_per_turn": turn_bytes / 1e9,
+                         "per_kernel": "profiles/r02_%s_launches.md (ncu launch list of this command)" % which},
+            "cpu_baseline": cpu,
+            "e2e": {"value": tot_it / wall_s, "unit": "iterations/s", "h2d_bytes_per_step": 24 * P, "d2h_bytes_per_step": 24 * P + 8 * iters},
+            "gpu_launches": launches, "clocks": clk.summary()}
+    _emit(line)
+    return 0
+
+
+def run_cfg1(args):
+    """BASELINE configs[0] (SURVEY 8d cfg 1): admm_anderson_xzu on the sample's three beams 12x3x3 (LINEAR / Neo-Hookean /
+    StVK), Anderson m=5, 100 iterations per frame. 1,620 tets: everything is L2-resident and launch-latency bound; the
+    line exists for coverage of the xzu loop and the per-tet L-BFGS prox."""
+    import aa_admm_b200 as A
+    if A.device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    A.set_device(0)
+    dims, dt, iters, m = (12, 3, 3), 1.0 / 30.0, 100, 5
+
+    def build(make):
+        s = make()
+        scene = A.BeamScene()
+        for shift, mat in ((1.75, 0), (0.0, 1), (-1.75, 2)):
+            v, t, mm, _, _, _ = A.BeamScene().add(*dims, shift).arrays()
+            s.add_tetmesh(v, t, mm, 1e7, 0.399, mat)
+            scene.add(*dims, shift)
+        pidx = scene.arrays()[3]
+        s.set_pins(pidx, scene.stretch(dt))
+        return s, scene, pidx
+
+    s, scene, pidx = build(A.Solver)
+    s.initialize(dt, iters, -9.8, m, True, 1.0, A.ORDER_XZU)
+    for _ in range(args.warmup):
+        s.set_pins(pidx, scene.stretch(dt))
+        s.step()
+    tot_it, loop_ms, launches, rejects = 0, 0.0, 0, 0
+    with ClockSampler(0) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            s.set_pins(pidx, scene.stretch(dt))
+            s.step()
+            info = s.info()
+            tot_it += info["iter_num"]
+            loop_ms += info["loop_ms"]
+            launches += info["kernel_launches"]
+            rejects += info["rejects"]
+        wall_s = time.perf_counter() - t0
+    cpu = None
+    if not args.no_cpu:
+        try:
+            with _NativeStdoutToStderr():
+                cores = _reference_host_threads()
+                from oracle import refbind
+                r, rscene, rp = build(lambda: refbind.RefSolver("xzu"))
+                r._f("set_threads")(cores)
+                r.initialize(dt, iters, -9.8, m, True, 1.0)
+                its, secs = 0, 0.0
+                for f in range(4):
+                    r.set_pins(rp, rscene.stretch(dt))
+                    t0 = time.perf_counter()
+                    h = r.step()
+                    if f > 0:
+                        secs += time.perf_counter() - t0
+                        its += len(h)
+            cpu = {"value": its / secs, "unit": "iterations/s", "cores": cores, "kind": "reference",
+                   "sample": "unmodified reference admm_anderson_xzu Solver::step on the same three beams, 3 frames x 100 iterations after 1 warm-up frame (the whole workload)"}
+        except Exception as e:
+            cpu = {"value": None, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (e,)}
+    by = np.zeros(8)
+    A.cuda_lib().aaadmm_tetscene_algo_bytes(s._scene(), m, by.ctypes.data_as(A.c_dp))
+    turn_bytes = 3 * by[0] + 3 * (by[1] + by[2]) + by[3] + by[4] + by[5]  # 3 local steps, 3 solves (one only logs), u, Anderson
+    ms_it = loop_ms / max(1, tot_it)
+    peak, peak_src = measured_peaks()
+    ach = turn_bytes / (ms_it * 1e-3) / 1e9
+    n_free = info["n_free"]
+    line = {"metric": "admm_anderson_iterations_per_sec_xzu_sample", "value": tot_it / (loop_ms * 1e-3), "unit": "iterations/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": loop_ms / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg1: admm_anderson_xzu ordering, three beams 12x3x3 (LINEAR, Neo-Hookean, StVK; %d tets, %d free vertices), "
+                                   "Anderson m=%d, %d iterations per frame" % (info["n_tets"], n_free, m, iters),
+                       "l2": "the whole state (0.5 MB) is L2-resident: this configuration is bound by launch latency (about 22 kernels per iteration), not by HBM",
+                       "iterations_timed": tot_it, "rejects": rejects},
+            "roofline": {"bound": "hbm", "kernel": "one xzu iteration (3 local steps incl. the per-tet L-BFGS prox, 3 solves, Anderson passes)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "ms_per_iteration": ms_it, "algo_GB_per_iteration": turn_bytes / 1e9,
+                         "per_kernel": "profiles/r02_cfg1_launches.md (ncu launch list of this command)"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": tot_it / wall_s, "unit": "iterations/s", "h2d_bytes_per_step": 24 * (n_free + len(pidx)), "d2h_bytes_per_step": 24 * n_free + 20 * iters},
+            "gpu_launches": launches, "clocks": clk.summary()}
+    _emit(line)
+    return 0
+
+
 NCU_LDLT_TRAFFIC_BYTES = 2.232e9
 
 
@@ -532,8 +746,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--small", action="store_true", help="30,720-tet beam (debugging only; not a bench number)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--config", default="cfg4", choices=["cfg4", "cfg5"],
-                    help="cfg4 (default, the headline): one 1M-tet beam; cfg5: ensemble of 64 x 213k-tet scenes (material sweep)")
+    ap.add_argument("--config", default="cfg4", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="cfg4 (default, the headline): one 1M-tet beam; cfg5: ensemble of 64 x 213k-tet scenes (material sweep); "
+                         "cfg1: xzu sample (three beams); cfg2 / cfg3: Geometry PlanarityOpt / WireMeshOpt (one GPU)")
     ap.add_argument("--slots", type=int, default=0, help="cfg5: resident scenes (host threads) per GPU (default 2)")
     ap.add_argument("--ref-dims", type=int, nargs=3, default=None,
                     help="--impl reference: beam size of the CPU arm (default REF_ARM; smaller sizes are for the CPU test)")
@@ -542,6 +757,11 @@ def main():
         return run_reference(args)
     if args.config == "cfg5":
         return run_cfg5(args)
+    if args.config in ("cfg1", "cfg2", "cfg3"):
+        rank, world, _ = dist_env()
+        if rank != 0:  # one coupled problem: one GPU
+            return 0
+        return run_cfg1(args) if args.config == "cfg1" else run_cfg_geo(args, args.config)
     return run_gpu(args)
 
 

@@ -143,6 +143,14 @@ void *aaadmm_host_polymesh_subdivide_and_smooth(void *h);
 int aaadmm_host_geoapp_optimize(int app, void *mesh, void *ref_mesh, int max_iter, int anderson_m, const double *prm,
                                 double *hist, int *n_hist, double *solution, double *info3);
 
+/* The same recipes with the setup kept (constraints, system matrix, factorisation, device upload once; any number of
+ * solves from the mesh's own positions): info4 = {device loop ms, resets, kernel launches, wall ms of solve_ADMM}. */
+void *aaadmm_host_geoapp_new(int kind, void *mesh, void *ref_mesh, const double *prm);
+void aaadmm_host_geoapp_free(void *h);
+/* out8 = points, hard constraints, z / u columns, soft constraints, nnz(L), fronts, tree levels, bytes of one apply */
+int aaadmm_host_geoapp_stats(void *h, double *out8);
+int aaadmm_host_geoapp_solve(void *h, int max_iter, int anderson_m, double *hist, int *n_hist, double *solution, double *info4);
+
 #ifdef __cplusplus
 }
 #endif

@@ -202,7 +202,14 @@ def test_ensemble_sharding_and_gather_gloo_world2(A):
     import socket
     import torch.multiprocessing as mp
     from aa_admm_b200 import ensemble as E
-    assert E.scenes_of_rank(64, 3, 8) == list(range(3, 64, 8))
+    # static, balanced scene -> GPU map: a partition of the ensemble in which every GPU gets each stiffness group (s // 8)
+    # and each Poisson ratio (s mod 8) equally often
+    for world in (1, 2, 4, 8):
+        parts = [E.scenes_of_rank(64, r, world) for r in range(world)]
+        assert sorted(s for p in parts for s in p) == list(range(64)) and all(len(p) == 64 // world for p in parts)
+        for p in parts:
+            assert sorted(np.bincount([s // 8 for s in p], minlength=8)) == [8 // world] * 8
+            assert sorted(np.bincount([s % 8 for s in p], minlength=8)) == [8 // world] * 8
     e0, n0 = E.scene_material(0)
     e63, n63 = E.scene_material(63)
     assert e0 == 1e6 and abs(n0 - 0.30) < 1e-15 and abs(e63 - 1e8) < 1e-3 and abs(n63 - 0.44) < 1e-12
@@ -222,7 +229,7 @@ def test_ensemble_sharding_and_gather_gloo_world2(A):
         t = res[r]
         assert t.shape == (7, 8)
         assert list(t[:, 0]) == list(range(7))
-        assert list(t[:, 7]) == [s % 2 for s in range(7)]
+        assert list(t[:, 7]) == [(s + s // 8) % 2 for s in range(7)]
         assert np.allclose(t[:, 1], 10 + np.arange(7))
 
 
