@@ -447,6 +447,7 @@ GeoApp::GeoApp(Kind kind, const PolyMesh &mesh, const PolyMesh &ref_mesh, const 
         planarity_constraints(solver_, mesh_, ref_mesh, p_, prm[1], prm[2], prm[3]);
     else
         wiremesh_constraints(solver_, mesh_, ref_mesh, p_, prm[1], prm[2], prm[3], prm[4], prm[5]);
+    rel_residual_eps_ = 1e-8 * average_edge_length(mesh_);
     ok_ = solver_.setup_ADMM(p_.cols(), prm[0]);
     if (!ok_) std::cerr << "Error: unable to initialize solver" << std::endl;
 }
@@ -465,7 +466,7 @@ OptimizeResult GeoApp::solve(int max_iter, int Anderson_m, bool save_history) {
     OptimizeResult R;
     if (!ok_) return R;
     const size_t before = solver_.function_values_.size();
-    solver_.solve_ADMM(p_, 1e-8 * average_edge_length(mesh_), max_iter, Anderson_m);
+    solver_.solve_ADMM(p_, rel_residual_eps_, max_iter, Anderson_m);
     if (save_history) solver_.save(Anderson_m);
     R.ok = true;
     R.function_values.assign(solver_.function_values_.begin() + before, solver_.function_values_.end());

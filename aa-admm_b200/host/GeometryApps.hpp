@@ -102,6 +102,7 @@ private:
     ALMGeometrySolver<3> solver_;
     PolyMesh mesh_;
     Matrix3X p_;
+    double rel_residual_eps_ = 0.0;
     bool ok_ = false;
 };
 
