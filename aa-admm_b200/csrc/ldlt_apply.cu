@@ -1459,8 +1459,10 @@ static int build(LdltDev **out, int n, const int64_t *Lp, const int *Li, const d
     if (getenv("AAADMM_LDLT_VERBOSE")) {
         int64_t small = 0;
         for (int b = 0; b < nb; ++b) small += fr[b].ns + fr[b].k <= 64;
-        fprintf(stderr, "ldlt: n %d nnz %lld fronts %d (<=64 rows: %lld) levels %d max front %d | fwd tasks %d bwd tasks %d | Mf %.1f MB Mb %.1f MB\n",
-                n, (long long)nnz, nb, (long long)small, nlev, max_block, f->n_ftasks, f->n_btasks, mf_tot * 8e-6, mb_tot * 8e-6);
+        fprintf(stderr, "ldlt: n %d nnz %lld fronts %d (<=64 rows: %lld) levels %d max front %d | fwd tasks %d bwd tasks %d | Mf %.1f MB Mb %.1f MB | "
+                "entries: L %.2f M, dense fronts (relaxed zeros incl.) %.2f M, forward tiles %.2f M, backward stages %.2f M\n",
+                n, (long long)nnz, nb, (long long)small, nlev, max_block, f->n_ftasks, f->n_btasks, mf_tot * 8e-6, mb_tot * 8e-6,
+                nnz * 1e-6, dense_entries * 1e-6, mf_tot * 1e-6, mb_tot * 1e-6);
     }
     f->stats.n = n;
     f->stats.n_blocks = nb;
