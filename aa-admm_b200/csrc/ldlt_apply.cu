@@ -1579,11 +1579,11 @@ int ldlt_dev_dump_trace(LdltDev *f, const char *path) {
         set_last_error("ldlt trace: cannot open the output file");
         return -1;
     }
-    fprintf(fp, "task,sweep,level,first,ns,k,start,shape,cw,need,t_start,t_primed,t_deps,t_done\n");
+    fprintf(fp, "task,sweep,level,first,ns,k,start,shape,cw,need,wait_idx,signal_idx,t_start,t_primed,t_deps,t_done\n");
     for (size_t i = 0; i < nt; ++i) {
         const SweepTask &k = f->host_tasks[i];
-        fprintf(fp, "%zu,%s,%d,%d,%d,%d,%d,%d,%d,%d,%llu,%llu,%llu,%llu\n", i, i < (size_t)f->n_ftasks ? "fwd" : "bwd", f->host_level[i],
-                k.first, k.ns, k.k, k.start, k.shape, k.cw, k.need, t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
+        fprintf(fp, "%zu,%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%llu,%llu,%llu,%llu\n", i, i < (size_t)f->n_ftasks ? "fwd" : "bwd", f->host_level[i],
+                k.first, k.ns, k.k, k.start, k.shape, k.cw, k.need, k.wait_idx, k.signal_idx, t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
     }
     fclose(fp);
     return 0;
