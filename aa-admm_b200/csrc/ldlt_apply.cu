@@ -968,7 +968,13 @@ static int build(LdltDev **out, int n, const int64_t *Lp, const int *Li, const d
             for (int c = lo[j]; c <= j; ++c) sub_root[c] = j;
         }
     }
+    // (3) A column whose pattern is ALMOST that of the chain below it (it has a second child, so its pattern is a union,
+    // typically one or two rows more) also joins when the explicit zeros this costs stay below relax_pct percent of the
+    // front: otherwise it becomes a front of one column between two big fronts - two more hops of the dependency chain
+    // in every sweep for a few KB of data.
+    const int relax_pct = env_int("AAADMM_RELAX_PCT", 5);
     std::vector<int> blk_of(std::max(n, 1)), blk_first;
+    int64_t front_zeros = 0;  // explicit zeros the relaxed joins have put into the current front
     for (int j = 0; j < n; ++j) {
         bool join = false;
         if (j > 0) {
@@ -978,10 +984,22 @@ static int build(LdltDev **out, int n, const int64_t *Lp, const int *Li, const d
                 const int64_t c0 = Lp[j] - Lp[j - 1], c1 = Lp[j + 1] - Lp[j];
                 const bool chain = c0 > 0 && Li[Lp[j - 1]] == j;
                 const int cur_size = j - blk_first.back();
-                if (chain && cur_size < kCap && (c0 == c1 + 1 || cur_size < kSmall)) join = true;
+                if (chain && cur_size < kCap) {
+                    const int64_t extra = std::max<int64_t>(c1 + 1 - c0, 0) * cur_size;  // zeros this join adds
+                    const int64_t entries = (int64_t)(cur_size + 1) * (c1 + (cur_size + 2) / 2);
+                    if (c0 == c1 + 1 || cur_size < kSmall) {
+                        join = true;
+                    } else if (sub_root[j - 1] < 0 && (front_zeros + extra) * 100 <= (int64_t)relax_pct * entries) {
+                        join = true;
+                        front_zeros += extra;
+                    }
+                }
             }
         }
-        if (!join) blk_first.push_back(j);
+        if (!join) {
+            blk_first.push_back(j);
+            front_zeros = 0;
+        }
         blk_of[j] = (int)blk_first.size() - 1;
     }
     const int nb = (int)blk_first.size();
@@ -1165,7 +1183,9 @@ static int build(LdltDev **out, int n, const int64_t *Lp, const int *Li, const d
     const int v_cap = std::min((max_ld_all + 255) & ~255, std::min(BCH, env_int("AAADMM_BCH", BCH)));
     f->ws_cap = ws_cap;
     f->v_cap = v_cap;
-    std::vector<int> lrt(std::max(nb, 1), 8), bcols(std::max(nb, 1), 32);
+    std::vector<int> lrt(std::max(nb, 1), 8), bcols(std::max(nb, 1), 32), bcw_f(std::max(nb, 1), 4);
+    const int task_slots = env_int("AAADMM_TASK_SLOTS", 200);                       // 0: no per-front cap
+    const int64_t task_min_entries = (int64_t)env_int("AAADMM_TASK_MIN_KENTRIES", 8) * 1024;
     for (int l = 0; l < nlev; ++l) {
         std::vector<int> &v = by_level[l];
         std::sort(v.begin(), v.end(), [&](int a, int b2) {
@@ -1212,6 +1232,33 @@ static int build(LdltDev **out, int n, const int64_t *Lp, const int *Li, const d
             else
                 break;
         }
+        // Per-front cap on the size of a task. A task streams its part of the factor at the rate one CTA's ring sustains
+        // (about 28 GB/s), and near the root a level is one to eight big fronts whose tasks all start together: the level
+        // then lasts as long as its biggest task (the per-task trace shows 15-25 us for 45-90 k entries per task there).
+        // A level's entries are therefore spread over about `slots` tasks (what the device holds at once), never
+        // below e_min entries per task (the fixed cost of a task is a few us).
+        {
+            int64_t level_entries = 0;
+            for (int b : v) level_entries += (int64_t)fr[b].ns * (fr[b].ns / 2 + fr[b].k);
+            const int64_t e_star = std::max<int64_t>(task_min_entries, level_entries / std::max(task_slots, 1));
+            for (int b : v) {
+                const int ns = fr[b].ns, m = fr[b].ns + fr[b].k;
+                if (task_slots > 0) {
+                    while (lrt[b] > min_lrt && ((int64_t)ns << lrt[b]) > e_star && ns >= 4 * ((2 * CTA) >> (lrt[b] - 1))) lrt[b]--;
+                }
+                int cw = bcw[l];
+                if (task_slots > 0) {
+                    const int64_t nc_des = std::max<int64_t>(8, e_star / std::max(m, 1));
+                    cw = std::min(cw, nc_des >= 32 ? 4 : (nc_des >= 16 ? 2 : 1));
+                    const int g = 8 * cw;
+                    if (fr[b].ld <= v_cap)
+                        bcols[b] = std::max(g, (int)std::min<int64_t>(bcols[b], nc_des) / g * g);
+                    else
+                        bcols[b] = g;
+                }
+                bcw_f[b] = cw;
+            }
+        }
     }
     // counters: [2 + b] forward arrivals at front b (tiles of its children), [2 + nb + b] backward arrivals
     // of front b (its own column chunks)
@@ -1219,7 +1266,10 @@ static int build(LdltDev **out, int n, const int64_t *Lp, const int *Li, const d
     // Emission order = ticket order. By tree level, or (default) by the estimated time a front becomes ready
     // (children's ready time + a latency/bandwidth estimate of their duration): tasks then take their tickets
     // roughly in the order they can start, and fewer CTA slots are held by tasks that only wait.
-    const bool by_ready = env_int("AAADMM_ORDER_BY_LEVEL", 0) == 0;
+    // Measured (profiles/r02_ldlt_schedule_sweeps.log): with wide fronts near the root (volume meshes: their assemble steps
+    // and slot-limited streams are what the duration estimate models worst) plain level order is 2.5 % faster, on the
+    // deep trees of small fronts of a surface mesh the ready-time order is 1.5 % faster.
+    const bool by_ready = env_int("AAADMM_ORDER_BY_LEVEL", (wide_on && max_ns_all > ws_cap) ? 1 : 0) == 0;
     const double est_lat = 0.1 * env_int("AAADMM_EST_LAT_TENTHS_US", 60), est_rate = env_int("AAADMM_EST_RATE_GBS", 25);
     auto front_dur_us = [&](int b, bool fwd) {
         const double m = fr[b].ns + fr[b].k;
@@ -1316,14 +1366,14 @@ static int build(LdltDev **out, int n, const int64_t *Lp, const int *Li, const d
             }
             for (int c0 = 0; c0 < fr[b].ns; c0 += bcols[b]) {
                 SweepTask t = make_task(b, false, c0, bcols[b]);
-                t.cw = bcw[l] | (wide ? 8 : 0);
+                t.cw = bcw_f[b] | (wide ? 8 : 0);
                 t.u_off = va_off;
                 t.wait_idx = wide ? 3 * nb + b : nb + std::max(parent[b], 0);
                 t.need = wide ? n_asm_b[b] : -1;
                 t.signal_idx = nb + b;
                 tile_src.push_back(t.m_off);
                 t.m_off = mb_tot;
-                const int NC = 8 * bcw[l], cend = std::min(t.ns, c0 + bcols[b]);
+                const int NC = 8 * bcw_f[b], cend = std::min(t.ns, c0 + bcols[b]);
                 for (int jb0 = c0; jb0 < cend; jb0 += NC)
                     mb_tot += (int64_t)std::min(NC, cend - jb0) * (t.ld - std::max(c0, jb0 & ~15));
                 mb_tot = (mb_tot + 15) & ~(int64_t)15;

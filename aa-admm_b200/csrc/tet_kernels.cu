@@ -529,15 +529,12 @@ __global__ void k_copy2_if_not_done(double *__restrict__ d0, const double *__res
 template <int KIND>
 __global__ void __launch_bounds__(TET_BLOCK)
 k_hyper(TetArrays A, const double *__restrict__ pos, const double *__restrict__ uz_in, double *__restrict__ out,
-        double *__restrict__ contrib, SolveState *st, double *partials, int mode, int lanes) {
+        double *__restrict__ contrib, SolveState *st, double *partials, int mode) {
     if (st->done) return;
     if (KIND == 0 && mode == MODE_REDO && !st->reject) return;
     const int T = A.n_tets;
     double acc[1] = {0.0};
-    // Only the first `lanes` lanes of a warp carry a tet (hyper_lanes below): the L-BFGS iteration count differs from
-    // tet to tet and a warp runs as long as its slowest lane, so a small batch is spread over many short warps.
-    const int lane = threadIdx.x & 31, gwarp = (blockIdx.x * TET_BLOCK + threadIdx.x) >> 5, nwarps = gridDim.x * (TET_BLOCK / 32);
-    for (int h = gwarp * lanes + lane; lane < lanes && h < A.n_hyper; h += nwarps * lanes) {
+    for (int h = blockIdx.x * TET_BLOCK + threadIdx.x; h < A.n_hyper; h += gridDim.x * TET_BLOCK) {
         const int t = A.hyper_ids[h];
         HyperParams P;
         P.mu = A.mu[t];
@@ -618,28 +615,10 @@ __global__ void k_prox_hyper_batch(HyperParams P, double *z, double *g, int64_t 
 }
 
 // ---- host launchers (this translation unit is compiled with -fmad=false) ----
-// k_hyper: tets per warp. One thread runs one serial L-BFGS (a chain of dependent FP64 operations, 1 ... 100
-// iterations); with few hyper-elastic tets the device is filled with warps of 1, 2, 4 ... active lanes (about two
-// warps per SM sub-partition) instead of a handful of full warps that each wait for their slowest lane.
-static int hyper_lanes(int n_hyper) {
-    static const int target_warps = 148 * 4 * 2;
-    int l = 1;
-    while (l < 32 && (int64_t)l * target_warps < n_hyper) l <<= 1;
-    return l;
-}
-static int hyper_grid(int n_hyper, int lanes) {
-    const int per_cta = lanes * (TET_BLOCK / 32);
-    return std::max(1, std::min(RED_MAX_BLOCKS, (n_hyper + per_cta - 1) / per_cta));
-}
-#define HYPER_LAUNCH(KIND, ...)                                                                                   \
-    do {                                                                                                          \
-        const int hl_ = hyper_lanes(A.n_hyper);                                                                   \
-        k_hyper<KIND><<<hyper_grid(A.n_hyper, hl_), TET_BLOCK, 0, s>>>(__VA_ARGS__, hl_);                          \
-    } while (0)
 void launch_update_z_hard(int mode, int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *u,
                           double *z, double *contrib, SolveState *st, double *partials) {
     if (A.n_hyper > 0)
-        HYPER_LAUNCH(0, A, pos, u, z, contrib, st, partials, mode);
+        k_hyper<0><<<(A.n_hyper + TET_BLOCK - 1) / TET_BLOCK, TET_BLOCK, 0, s>>>(A, pos, u, z, contrib, st, partials, mode);
     if (mode == MODE_WARM)
         k_update_z_hard<MODE_WARM><<<grid, TET_BLOCK, 0, s>>>(A, pos, u, z, contrib, st, partials);
     else if (mode == MODE_ITER)
@@ -682,7 +661,8 @@ void launch_fmuvt_batch(const double *d_z, double *d_out, int64_t n) {
 
 void launch_grad_u_xzu(int grid, cudaStream_t s, const TetArrays &A, const double *z, double *u, const SolveState *st) {
     if (A.n_hyper > 0)
-        HYPER_LAUNCH(2, A, nullptr, z, u, nullptr, const_cast<SolveState *>(st), nullptr, 0);
+        k_hyper<2><<<(A.n_hyper + TET_BLOCK - 1) / TET_BLOCK, TET_BLOCK, 0, s>>>(A, nullptr, z, u, nullptr,
+                                                                               const_cast<SolveState *>(st), nullptr, 0);
     k_grad_u_xzu<<<grid, TET_BLOCK, 0, s>>>(A, z, u, st);
 }
 void launch_z_from_x(int grid, cudaStream_t s, const TetArrays &A, const double *pos, double *z) {
@@ -706,7 +686,8 @@ void launch_restore_xzu(int grid, cudaStream_t s, double *u, const double *u_def
 void launch_update_z_plain(int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *u,
                            double *z_out, const SolveState *st) {
     if (A.n_hyper > 0)
-        HYPER_LAUNCH(1, A, pos, u, z_out, nullptr, const_cast<SolveState *>(st), nullptr, 0);
+        k_hyper<1><<<(A.n_hyper + TET_BLOCK - 1) / TET_BLOCK, TET_BLOCK, 0, s>>>(A, pos, u, z_out, nullptr,
+                                                                               const_cast<SolveState *>(st), nullptr, 0);
     k_update_z_plain<<<grid, TET_BLOCK, 0, s>>>(A, pos, u, z_out, st);
 }
 void launch_update_u_plain(int grid, cudaStream_t s, const TetArrays &A, const double *pos, const double *z, double *u,
