@@ -347,19 +347,47 @@ k_fwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restr
         return;
     }
     const unsigned long long t1 = trace ? gtime() : 0;
-    task_wait(ctl + 2, F);  // the children's updates are written
-    const unsigned long long t2 = trace ? gtime() : 0;
     if (F.shape == 0) {
-        // assemble task of a wide front: w_j = rhs_j - (child updates landing on column j), in place in W
+        // assemble task of a wide front: w_j = rhs_j - (child updates landing on column j), in place in W. It sits on
+        // the dependency chain of the sweep: what does not depend on the children (the slot list, the right-hand side)
+        // is fetched before the wait.
         const int j = F.start + (int)threadIdx.x;
-        if ((int)threadIdx.x < ACOLS && j < F.ns) {
-            double a[NR];
+        const bool act = (int)threadIdx.x < ACOLS && j < F.ns;
+        double a[NR];
+        int4 e = make_int4(-1, -1, -1, -1);
+        if (act) {
+            e = __ldg(G.ell + F.g_off + j);
 #pragma unroll
             for (int q = 0; q < NR; ++q) a[q] = __ldcg(W + (size_t)(F.first + j) * NR + q);
-            gather_add<NR>(G, F.g_off + j, U, -1.0, a);
+        }
+        task_wait(ctl + 2, F);  // the children's updates are written
+        if (act) {
+            const int s4[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (s4[i] >= 0) {
+                    const size_t so = (size_t)s4[i] * NR;
+#pragma unroll
+                    for (int q = 0; q < NR; ++q) a[q] += -1.0 * __ldcg(U + so + q);
+                }
+            }
+            if (G.ptr) gather_overflow<NR>(G, F.g_off + j, U, -1.0, a);
 #pragma unroll
             for (int q = 0; q < NR; ++q) W[(size_t)(F.first + j) * NR + q] = a[q];
         }
+        task_signal(ctl + 2, F);
+        if (trace && threadIdx.x == 0) {
+            unsigned long long *r = trace + 4 * (size_t)s_task;
+            r[0] = t0;
+            r[1] = t1;
+            r[2] = t1;
+            r[3] = gtime();
+        }
+        return;
+    }
+    task_wait(ctl + 2, F);  // the children's updates are written
+    const unsigned long long t2 = trace ? gtime() : 0;
+    if (false) {
     } else
     switch (F.shape) {
     case 8: fwd_tile<NR, 8>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
@@ -573,29 +601,44 @@ k_bwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restr
         return;
     }
     const unsigned long long t1 = trace ? gtime() : 0;
-    task_wait(ctl + 2, F);  // the parent's (hence every ancestor's) x is written
-    const unsigned long long t2 = trace ? gtime() : 0;
-    switch (F.cw & 7) {
-    case 0: {
-        // assemble task of a wide front: v = [ D^-1 y ; -x(rows below) ; 0 ] for rows start .. start + ACOLS
+    if ((F.cw & 7) == 0) {
+        // assemble task of a wide front: v = [ D^-1 y ; -x(rows below) ; 0 ] for rows start .. start + ACOLS. On the
+        // dependency chain of the sweep: y (the forward sweep is complete) and the row ids are fetched before the wait.
         const int r = F.start + (int)threadIdx.x;
-        if ((int)threadIdx.x < ACOLS && r < F.ld) {
-            double a[NR];
+        const bool act = (int)threadIdx.x < ACOLS && r < F.ld;
+        double a[NR];
 #pragma unroll
-            for (int q = 0; q < NR; ++q) a[q] = 0.0;
-            if (r < F.ns) {
+        for (int q = 0; q < NR; ++q) a[q] = 0.0;
+        size_t xi = 0;
+        const bool below = act && r >= F.ns && r < F.ns + F.k;
+        if (act && r < F.ns) {
 #pragma unroll
-                for (int q = 0; q < NR; ++q) a[q] = __ldcg(Yd + (size_t)(F.first + r) * NR + q);
-            } else if (r < F.ns + F.k) {
-                const size_t i = (size_t)__ldg(rows + F.g_off + r - F.ns) * NR;
+            for (int q = 0; q < NR; ++q) a[q] = __ldcg(Yd + (size_t)(F.first + r) * NR + q);
+        } else if (below) {
+            xi = (size_t)__ldg(rows + F.g_off + r - F.ns) * NR;
+        }
+        task_wait(ctl + 2, F);  // the parent's (hence every ancestor's) x is written
+        if (below) {
 #pragma unroll
-                for (int q = 0; q < NR; ++q) a[q] = -__ldcg(X + i + q);
-            }
+            for (int q = 0; q < NR; ++q) a[q] = -__ldcg(X + xi + q);
+        }
+        if (act) {
 #pragma unroll
             for (int q = 0; q < NR; ++q) Va[(size_t)(F.u_off + r) * NR + q] = a[q];
         }
-        break;
+        task_signal(ctl + 2, F);
+        if (trace && threadIdx.x == 0) {
+            unsigned long long *tr = trace + 4 * (size_t)s_task;
+            tr[0] = t0;
+            tr[1] = t1;
+            tr[2] = t1;
+            tr[3] = gtime();
+        }
+        return;
     }
+    task_wait(ctl + 2, F);  // the parent's (hence every ancestor's) x is written
+    const unsigned long long t2 = trace ? gtime() : 0;
+    switch (F.cw & 7) {
     case 4: bwd_task<NR, 4>(F, rows, Yd, X, Va, perm, x_out, v_cap, sm, B); break;
     case 2: bwd_task<NR, 2>(F, rows, Yd, X, Va, perm, x_out, v_cap, sm, B); break;
     default: bwd_task<NR, 1>(F, rows, Yd, X, Va, perm, x_out, v_cap, sm, B); break;
