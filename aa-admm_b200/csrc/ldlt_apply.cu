@@ -116,6 +116,7 @@ __device__ __forceinline__ void task_wait(const int *cnt, const SweepTask &F) {
 }
 // called by all consumer threads after their global writes
 __device__ __forceinline__ void task_signal(int *cnt, const SweepTask &F) {
+    if (F.signal_idx < 0) return;  // nobody waits for this task (root forward, leaf fronts backward)
     __threadfence();
     asm volatile("bar.sync 1, 256;\n" ::: "memory");
     if (threadIdx.x == 0 && F.signal_idx >= 0) atomicAdd(cnt + F.signal_idx, 1);
@@ -1430,6 +1431,17 @@ static int build(LdltDev **out, int n, const int64_t *Lp, const int *Li, const d
         if (tasks[i].need >= 0) continue;
         const int b = tasks[i].signal_idx >= 3 * nb ? tasks[i].signal_idx - 3 * nb : tasks[i].signal_idx - nb;
         tasks[i].need = parent[b] >= 0 ? ntasks_b[parent[b]] : 0;
+    }
+    {
+        // leaf fronts have no children: nothing waits for their backward tasks (1,168 of 6,000 tasks at cfg 4, the tail of
+        // the sweep): no fence, no barrier, no atomic at their end
+        std::vector<char> has_child(std::max(nb, 1), 0);
+        for (int b = 0; b < nb; ++b)
+            if (parent[b] >= 0) has_child[parent[b]] = 1;
+        for (size_t i = f->n_ftasks; i < tasks.size(); ++i) {
+            const int si = tasks[i].signal_idx;
+            if (si >= nb && si < 2 * nb && !has_child[si - nb]) tasks[i].signal_idx = -1;
+        }
     }
     f->n_ctl = 2 + 4 * nb;  // + one 'assembled' counter per front and sweep (wide fronts)
     if (getenv("AAADMM_LDLT_TRACE")) {  // developer aid: per-task time stamps (start, ring primed, dependencies met, done)
