@@ -1450,13 +1450,15 @@ struct aaadmm_geo {
     aaadmm_ldlt *factor = nullptr;
     cudaStream_t stream = nullptr;
     int *type = nullptr, *idx_ptr = nullptr, *idx = nullptr, *col0 = nullptr, *dt_col = nullptr, *soft_point = nullptr,
-        *soft_of_point = nullptr, *last_tri = nullptr;
+        *soft_of_point = nullptr, *last_tri = nullptr, *soft_order = nullptr;
+    std::vector<int> soft_point_h;  // host copy: the first solve sorts the soft points along a Morton curve
+    bool soft_order_built = false;
     int64_t *dt_ptr = nullptr;
     double *param = nullptr, *dt_val = nullptr, *rhs_fixed = nullptr;
     double soft_weight = 0, rho = 1.0;
     RefMeshDev mesh;
     int64_t N = 0;  // 3 zc + 3 P: the Anderson variable (u | x)
-    double *Ubuf = nullptr, *Nbuf = nullptr, *Dbuf = nullptr, *z = nullptr, *prev_dx = nullptr, *cp = nullptr;
+    double *Ubuf = nullptr, *Nbuf = nullptr, *Dbuf = nullptr, *z = nullptr, *zmu = nullptr, *prev_dx = nullptr, *cp = nullptr;
     double *dF = nullptr, *dG = nullptr, *hist = nullptr, *partials = nullptr;
     int m_cap = 0, hist_cap = 0;
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -1484,6 +1486,7 @@ int aaadmm_geo_destroy(aaadmm_geo *g) {
     cudaFree(g->soft_point);
     cudaFree(g->soft_of_point);
     cudaFree(g->last_tri);
+    cudaFree(g->soft_order);
     cudaFree(g->dt_ptr);
     cudaFree(g->param);
     cudaFree(g->dt_val);
@@ -1493,6 +1496,7 @@ int aaadmm_geo_destroy(aaadmm_geo *g) {
     cudaFree(g->Nbuf);
     cudaFree(g->Dbuf);
     cudaFree(g->z);
+    cudaFree(g->zmu);
     cudaFree(g->prev_dx);
     cudaFree(g->cp);
     cudaFree(g->dF);
@@ -1558,6 +1562,12 @@ int aaadmm_geo_create(aaadmm_geo **out, const aaadmm_geo_desc *d, aaadmm_ldlt *f
     rc |= up(&g->dt_val, d->dt_val, (size_t)d->dt_ptr[g->P]);
     rc |= up(&g->rhs_fixed, d->rhs_fixed, (size_t)3 * g->P);
     rc |= up(&g->soft_point, d->soft_point, d->n_soft);
+    if (d->n_soft > 0) {
+        g->soft_point_h.assign(d->soft_point, d->soft_point + d->n_soft);
+        std::vector<int> ident(d->n_soft);
+        for (int i = 0; i < d->n_soft; ++i) ident[i] = i;
+        rc |= up(&g->soft_order, ident.data(), d->n_soft);
+    }
     std::vector<int> sop(g->P, -1), lt(std::max(d->n_soft, 1), -1);
     for (int i = 0; i < d->n_soft; ++i) sop[d->soft_point[i]] = i;
     rc |= up(&g->soft_of_point, sop.data(), g->P);
@@ -1571,6 +1581,8 @@ int aaadmm_geo_create(aaadmm_geo **out, const aaadmm_geo_desc *d, aaadmm_ldlt *f
     AAADMM_CUDA_OK(cudaMalloc((void **)&g->Nbuf, sizeof(double) * g->N));
     AAADMM_CUDA_OK(cudaMalloc((void **)&g->Dbuf, sizeof(double) * g->N));
     AAADMM_CUDA_OK(cudaMalloc((void **)&g->z, sizeof(double) * 3 * std::max(g->zc_all, 1)));
+    AAADMM_CUDA_OK(cudaMalloc((void **)&g->zmu, sizeof(double) * 3 * std::max(g->zc_all, 1)));
+    AAADMM_CUDA_OK(cudaMemset(g->zmu, 0, sizeof(double) * 3 * std::max(g->zc_all, 1)));
     AAADMM_CUDA_OK(cudaMalloc((void **)&g->prev_dx, sizeof(double) * 3 * std::max(g->zc_all, 1)));
     AAADMM_CUDA_OK(cudaMalloc((void **)&g->cp, sizeof(double) * 3 * std::max(d->n_soft, 1)));
     AAADMM_CUDA_OK(cudaMalloc((void **)&g->partials, sizeof(double) * RED_MAX_Q * RED_MAX_BLOCKS));
@@ -1595,6 +1607,7 @@ static void geo_views(aaadmm_geo *g, GeoConstraints &C, GeoSoft &S) {
     S.tri_order = g->mesh.order;
     S.tri = g->mesh.tri;
     S.last_tri = g->last_tri;
+    S.order = g->soft_order;
 }
 
 // one turn of the while loop of ALMGeometrySolver.h:197-268
@@ -1607,9 +1620,9 @@ static int geo_enqueue_turn(aaadmm_geo *g, int m, int &L) {
     const int64_t NU = 3 * (int64_t)g->zc;
     double *cu = g->Ubuf, *cx = g->Ubuf + NU, *nu = g->Nbuf, *nx = g->Nbuf + NU;
     const bool accel = m > 0;
-    launch_geo_local(st, C, cx, cu, g->prev_dx, g->z, g->st);
+    launch_geo_local(st, C, cx, cu, g->prev_dx, g->z, g->zmu, g->st);
     launch_geo_soft(st, S, cx, g->cp, g->st);
-    launch_geo_rhs(st, g->P, g->dt_ptr, g->dt_col, g->dt_val, g->z, cu, g->rhs_fixed, g->n_soft ? g->soft_of_point : nullptr,
+    launch_geo_rhs(st, g->P, g->dt_ptr, g->dt_col, g->dt_val, g->zmu, nullptr, g->rhs_fixed, g->n_soft ? g->soft_of_point : nullptr,
                    g->soft_weight, g->cp, f->iperm, f->W, g->st);
     if (ldlt_dev_apply_permuted(f, nx, st, &g->st->done)) return -1;
     launch_geo_u_resid(st, C, nx, cu, g->z, g->prev_dx, nu, g->st, g->partials, g->hist, accel ? 1 : 0);
@@ -1720,6 +1733,36 @@ int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int ande
     AAADMM_CUDA_OK(cudaMemcpyAsync(g->Ubuf + NU, init_x, sizeof(double) * 3 * g->P, cudaMemcpyHostToDevice, st));
     AAADMM_CUDA_OK(cudaMemcpyAsync(g->Dbuf + NU, init_x, sizeof(double) * 3 * g->P, cudaMemcpyHostToDevice, st));
     if (g->n_soft) AAADMM_CUDA_OK(cudaMemsetAsync(g->last_tri, 0xff, sizeof(int) * g->n_soft, st));
+    if (g->n_soft >= 1024 && !g->soft_order_built) {
+        // processing order of the closest-point queries: Morton order of the first positions (the points move little
+        // during a solve); results do not depend on it
+        const int n = g->n_soft;
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int i = 0; i < n; ++i)
+            for (int r = 0; r < 3; ++r) {
+                const double c = init_x[3 * (size_t)g->soft_point_h[i] + r];
+                lo[r] = std::min(lo[r], c);
+                hi[r] = std::max(hi[r], c);
+            }
+        std::vector<std::pair<uint64_t, int>> key(n);
+        for (int i = 0; i < n; ++i) {
+            uint64_t code = 0;
+            uint32_t q[3];
+            for (int r = 0; r < 3; ++r) {
+                const double c = init_x[3 * (size_t)g->soft_point_h[i] + r], w = hi[r] - lo[r];
+                q[r] = w > 0 ? (uint32_t)std::min(2097151.0, (c - lo[r]) / w * 2097152.0) : 0u;
+            }
+            for (int bit = 20; bit >= 0; --bit)
+                for (int r = 0; r < 3; ++r) code = (code << 1) | ((q[r] >> bit) & 1u);
+            key[i] = {code, i};
+        }
+        std::sort(key.begin(), key.end());
+        std::vector<int> ord(n);
+        for (int i = 0; i < n; ++i) ord[i] = key[i].second;
+        AAADMM_CUDA_OK(cudaMemcpyAsync(g->soft_order, ord.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+        AAADMM_CUDA_OK(cudaStreamSynchronize(st));  // `ord` is a local
+        g->soft_order_built = true;
+    }
     k_geo_init_state<<<1, 1, 0, st>>>(g->st, m, max_iter);
     int launches = 0;
     static const bool no_graph = getenv("AAADMM_NO_GRAPH") != nullptr;
@@ -1862,6 +1905,7 @@ int aaadmm_geo_closest_points(const double *verts, int nv, const int *tris, int 
     GeoSoft S;
     S.n = nq;
     S.point = nullptr;
+    S.order = nullptr;
     S.weight = 1.0;
     S.nodes = M.nodes;
     S.tri_order = M.order;

@@ -165,7 +165,7 @@ __device__ __forceinline__ void geo_project(int type, const double *v, int kc, c
 
 __global__ void __launch_bounds__(GEO_BLOCK)
 k_geo_local(GeoConstraints C, const double *__restrict__ x, const double *__restrict__ u, double *__restrict__ prev_dx,
-            double *__restrict__ z, const SolveState *st) {
+            double *__restrict__ z, double *__restrict__ zmu, const SolveState *st) {
     if (st->done) return;
     const int c = blockIdx.x * GEO_BLOCK + threadIdx.x;
     if (c >= C.n) return;
@@ -179,6 +179,10 @@ k_geo_local(GeoConstraints C, const double *__restrict__ x, const double *__rest
     }
     geo_project(type, v, kc, C.param + 4 * (size_t)c, zz);
     for (int j = 0; j < kc * 3; ++j) z[o + j] = zz[j];
+    // z - u for the right-hand side gather of the same turn (k_geo_rhs then reads one array instead of two; the same
+    // subtraction, the same bits)
+    if (zmu)
+        for (int j = 0; j < kc * 3; ++j) zmu[o + j] = zz[j] - u[o + j];
 }
 
 __global__ void __launch_bounds__(GEO_BLOCK)
@@ -329,8 +333,11 @@ __device__ void bvh_closest(const GeoSoft &S, const double *p, int hint, double 
 __global__ void __launch_bounds__(GEO_BLOCK)
 k_geo_soft(GeoSoft S, const double *__restrict__ x, double *__restrict__ cp, const SolveState *st) {
     if (st && st->done) return;
-    const int i = blockIdx.x * GEO_BLOCK + threadIdx.x;
-    if (i >= S.n) return;
+    const int j = blockIdx.x * GEO_BLOCK + threadIdx.x;
+    if (j >= S.n) return;
+    // neighbouring lanes take neighbouring points (Morton order of the first positions): their descents visit the same
+    // nodes (ncu before: 13 of 32 lanes active per instruction with the points in mesh order)
+    const int i = S.order ? S.order[j] : j;
     const int pt = S.point ? S.point[i] : i;
     double p[3] = {x[3 * (size_t)pt], x[3 * (size_t)pt + 1], x[3 * (size_t)pt + 2]}, c[3];
     int tri;
@@ -365,11 +372,31 @@ k_geo_rhs(int n_points, const int64_t *__restrict__ dt_ptr, const int *__restric
     double s[3] = {rhs_fixed[3 * (size_t)p], rhs_fixed[3 * (size_t)p + 1], rhs_fixed[3 * (size_t)p + 2]};
     double a[3] = {0.0, 0.0, 0.0};
     const int64_t e1 = dt_ptr[p + 1];
-    for (int64_t e = dt_ptr[p]; e < e1; ++e) {
-        const size_t o = 3 * (size_t)dt_col[e];
-        const double v = dt_val[e];
+    // the entries of a row are summed in their order; the loads of four entries (column, value, then z and u of that
+    // column) are issued before the first use: the kernel is a latency-bound gather (ncu: 255 warps stalled on
+    // long_scoreboard per issue, 3 % issue utilisation)
+    for (int64_t e = dt_ptr[p]; e < e1; e += 4) {
+        size_t o[4];
+        double v[4], zz[4][3], uu[4][3];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) a[r] += v * (z[o + r] - u[o + r]);
+        for (int i = 0; i < 4; ++i) {
+            const bool in = e + i < e1;
+            o[i] = in ? 3 * (size_t)dt_col[e + i] : 0;
+            v[i] = in ? dt_val[e + i] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                zz[i][r] = z[o[i] + r];
+                uu[i][r] = u ? u[o[i] + r] : 0.0;  // u == null: `z` already holds z - u (k_geo_local)
+            }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (e + i < e1) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) a[r] += v[i] * (u ? zz[i][r] - uu[i][r] : zz[i][r]);
+            }
     }
     const int si = soft_of_point ? soft_of_point[p] : -1;
 #pragma unroll
@@ -577,8 +604,8 @@ void launch_gs_u(cudaStream_t s, const double *u_cur, const double *dx, const do
 }
 
 void launch_geo_local(cudaStream_t s, const GeoConstraints &C, const double *x, const double *u, double *prev_dx,
-                      double *z, const SolveState *st) {
-    if (C.n > 0) k_geo_local<<<(C.n + GEO_BLOCK - 1) / GEO_BLOCK, GEO_BLOCK, 0, s>>>(C, x, u, prev_dx, z, st);
+                      double *z, double *zmu, const SolveState *st) {
+    if (C.n > 0) k_geo_local<<<(C.n + GEO_BLOCK - 1) / GEO_BLOCK, GEO_BLOCK, 0, s>>>(C, x, u, prev_dx, z, zmu, st);
 }
 void launch_geo_soft(cudaStream_t s, const GeoSoft &S, const double *x, double *cp, const SolveState *st) {
     if (S.n > 0) k_geo_soft<<<(S.n + GEO_BLOCK - 1) / GEO_BLOCK, GEO_BLOCK, 0, s>>>(S, x, cp, st);

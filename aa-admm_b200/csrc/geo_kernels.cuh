@@ -36,14 +36,16 @@ struct GeoSoft {
     const int *tri_order;   // leaf triangle ids
     const double *tri;      // [n_tris][9] corner coordinates a, b, c
     int *last_tri;          // [n] closest triangle of the previous call (search bound), -1 initially
+    const int *order;       // [n] thread j handles constraint order[j] (spatially sorted: coherent BVH descents), or null
 };
 
 // Geometry loop state that rides in SolveState's generic fields:
 //   prev_prim = prev_residual, reject = reset flag, iter = accepted iterations, done = loop finished
 
 // current x -> Dx (kept as prev_Dx), v = Dx + u, z = project(v)       (ALMGeometrySolver.h:200-205,425-435)
+// zmu (may be null): also z - u, for launch_geo_rhs(z = zmu, u = null) of the same turn
 void launch_geo_local(cudaStream_t s, const GeoConstraints &C, const double *x, const double *u, double *prev_dx,
-                      double *z, const SolveState *st);
+                      double *z, double *zmu, const SolveState *st);
 // closest point on the reference surface for every soft point          (:436-439, Constraint.h:340-345,377-383)
 void launch_geo_soft(cudaStream_t s, const GeoSoft &S, const double *x, double *cp, const SolveState *st);
 // rhs = rhs_fixed + rho D_hard^T (z - u) + D_soft^T z_soft, in elimination order   (:442-450)
