@@ -804,6 +804,12 @@ class GeometrySolver:
         self.H.aaadmm_host_geo_solution(self.h, _dp(x), self.n_points)
         return hist[:n], x
 
+    def elapsed(self, n):
+        """elapsed_time_ of the last solve's n logged iterations (cumulative seconds, device time stamps)."""
+        t = np.zeros(max(n, 1))
+        self.H.aaadmm_host_geo_elapsed(self.h, _dp(t))
+        return t[:n]
+
     def info(self):
         s = np.zeros(4)
         self.H.aaadmm_host_geo_info(self.h, _dp(s))

@@ -1431,6 +1431,7 @@ __global__ void k_geo_init_state(SolveState *st, int m, int max_iters) {
     st->aa_m = m > 0 ? m : 1;
     st->aa_mk = 0;
     st->ticket = 0u;
+    st->t0 = global_timer_ns();  // per-iteration time stamps of the log count from here
     st->loop_it = 0;
     st->max_iters = max_iters;
     st->skip_redo = 1;
@@ -1713,7 +1714,7 @@ int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int ande
     cudaStream_t st = g->stream;
     if (max_iter > g->hist_cap) {
         cudaFree(g->hist);
-        AAADMM_CUDA_OK(cudaMalloc((void **)&g->hist, sizeof(double) * 2 * std::max(1, max_iter)));  // residuals | reset flags
+        AAADMM_CUDA_OK(cudaMalloc((void **)&g->hist, sizeof(double) * 3 * std::max(1, max_iter)));  // residuals | reset flags | ms
         g->hist_cap = max_iter;
         g->graph_key = -1;
     }
@@ -1843,6 +1844,17 @@ int aaadmm_geo_reset_flags(aaadmm_geo *g, int *flags, int n) {
     std::vector<double> f((size_t)std::max(n, 1));
     if (n > 0) AAADMM_CUDA_OK(cudaMemcpy(f.data(), g->hist + g->last_max_iter, sizeof(double) * n, cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; ++i) flags[i] = f[i] != 0.0;
+    return 0;
+    API_TRY_END
+}
+
+int aaadmm_geo_iteration_times(aaadmm_geo *g, double *ms, int n) {
+    API_TRY_BEGIN
+    if (!g || !ms || n < 0 || n > g->last_iters) {
+        set_last_error("geo_iteration_times: bad arguments (n must not exceed the iterations of the last solve)");
+        return -1;
+    }
+    if (n > 0) AAADMM_CUDA_OK(cudaMemcpy(ms, g->hist + 2 * (size_t)g->last_max_iter, sizeof(double) * n, cudaMemcpyDeviceToHost));
     return 0;
     API_TRY_END
 }

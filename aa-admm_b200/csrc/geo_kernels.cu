@@ -439,6 +439,7 @@ k_geo_u_resid(GeoConstraints C, const double *__restrict__ x_new, const double *
                 const int it = st->iter;
                 hist[it] = r;
                 hist[st->max_iters + it] = st->reject ? 1.0 : 0.0;  // this iteration follows a reset of the accelerator
+                hist[2 * st->max_iters + it] = 1e-6 * (double)(global_timer_ns() - st->t0);  // ms since the loop began
                 st->iter = it + 1;
                 st->prev_prim = r;
                 st->reject = 0;   // reset = false
@@ -549,6 +550,7 @@ k_gs_z(GeoConstraints C, GeoSoft S, int zc_hard, double rho, const double *__res
                 const int it = st->iter;
                 hist[it] = res;
                 hist[st->max_iters + it] = MODE == 2 ? 1.0 : 0.0;  // logged after the redo of a rejected iterate
+                hist[2 * st->max_iters + it] = 1e-6 * (double)(global_timer_ns() - st->t0);  // ms since the loop began
                 st->iter = it + 1;
                 st->prev_prim = res;
                 if (st->iter >= st->max_iters) st->done = 1;  // end_iteration: the rest of this turn is skipped

@@ -266,9 +266,14 @@ void GeometrySolverBase<N>::solve_ADMM(const MatrixNX &init_x, double, int max_i
     const int n = last_result.iters_logged;
     std::vector<int> flags(std::max(1, n), 0);
     if (n > 0 && aaadmm_geo_reset_flags(geo_, flags.data(), n) != 0) std::cerr << "Error: " << aaadmm_last_error() << std::endl;
+    // measured on the device when each iteration was logged (a rejected turn makes its iteration longer), plus the
+    // host time before the loop started (uploads)
+    std::vector<double> ms(std::max(1, n), 0.0);
+    const bool stamped = n > 0 && aaadmm_geo_iteration_times(geo_, ms.data(), n) == 0;
+    const double before = stamped ? std::max(0.0, secs - 1e-3 * last_result.loop_ms) : 0.0;
     for (int i = 0; i < n; ++i) {
         function_values_.push_back(hist[i]);
-        elapsed_time_.push_back(secs * (i + 1) / n);
+        elapsed_time_.push_back(stamped ? before + 1e-3 * ms[i] : secs * (i + 1) / n);
         Anderson_reset_.push_back(flags[i] != 0);
     }
     reset_count = last_result.rejects;

@@ -576,6 +576,12 @@ int aaadmm_host_geo_history(void *h, double *values) {
     memcpy(values, g->solver.function_values_.data(), sizeof(double) * g->solver.function_values_.size());
     return 0;
 }
+// elapsed_time_ of the logged iterations (seconds, cumulative; measured on the device per iteration)
+int aaadmm_host_geo_elapsed(void *h, double *secs) {
+    GeoHandle *g = static_cast<GeoHandle *>(h);
+    memcpy(secs, g->solver.elapsed_time_.data(), sizeof(double) * g->solver.elapsed_time_.size());
+    return 0;
+}
 int aaadmm_host_geo_solution(void *h, double *x, int n_points) {
     memcpy(x, static_cast<GeoHandle *>(h)->solver.get_solution().data(), sizeof(double) * 3 * n_points);
     return 0;

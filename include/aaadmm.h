@@ -244,6 +244,10 @@ int aaadmm_geo_solve(aaadmm_geo *g, const double *init_x, int max_iter, int ande
 /* Per logged iteration of the last aaadmm_geo_solve: 1 if it follows a reset of the accelerator (the iterate before it
  * was rejected), the flag the reference's solvers keep in Anderson_reset_ (Geometry/ALMGeometrySolver.h:391). */
 int aaadmm_geo_reset_flags(aaadmm_geo *g, int *flags, int n);
+/* Device time stamps of the last aaadmm_geo_solve: ms[i] = milliseconds from the start of the loop to the moment logged
+ * iteration i was accepted (%globaltimer in the CTA that writes the log): the elapsed_time_ column of the reference's
+ * ./result/residual-*.txt (Geometry/ALMGeometrySolver.h:262-266). n <= iterations logged. */
+int aaadmm_geo_iteration_times(aaadmm_geo *g, double *ms, int n);
 /* unit parity: project `n` constraints of one type on already transformed columns (3 per column, host) */
 int aaadmm_geo_project(int type, int n, int k, const double *cols, const double *param4, double *out);
 /* unit parity: nearest points on a triangle mesh for nq host queries */

@@ -126,6 +126,7 @@ int aaadmm_host_geo_add_closeness(void *h, int idx, double weight, const double 
 int aaadmm_host_geo_setup(void *h, int n_points, double rho);
 int aaadmm_host_geo_solve(void *h, const double *init_x, int n_points, int max_iter, int anderson_m);
 int aaadmm_host_geo_history(void *h, double *values);
+int aaadmm_host_geo_elapsed(void *h, double *secs); /* elapsed_time_ of the same iterations (cumulative seconds) */
 int aaadmm_host_geo_solution(void *h, double *x, int n_points);
 int aaadmm_host_geo_info(void *h, double *out4);
 

@@ -70,6 +70,13 @@ def test_alm_solve_vs_reference(gpu, refgeo, kind, m, rho):
     assert rel[:8].max() < 1e-9
     assert floor.max() < 1e-9 if m == 0 else floor.max() < 1e-6
     assert np.abs(xg - xr).max() / np.abs(xr).max() < 1e-6
+    # elapsed_time_ (the first column of ./result/residual-*.txt): measured per iteration on the device, cumulative, and
+    # consistent with the loop's event time; not an even split (a turn with a rejected iterate is longer)
+    t = g.elapsed(len(hg))
+    assert np.all(np.diff(t) > 0) and t[0] > 0
+    assert abs((t[-1] - t[0]) - 1e-3 * g.info()["loop_ms"]) < 0.5e-3 * g.info()["loop_ms"] + 1e-4
+    if g.info()["rejects"] > 0:
+        assert np.diff(t).max() > 1.3 * np.median(np.diff(t))
 
 
 @pytest.mark.parametrize("kind,m,rho", [("planarity", 5, 1e5), ("planarity", 0, 1e5), ("wiremesh", 5, 1e3), ("wiremesh", 0, 1e3),
