@@ -18,6 +18,24 @@ def scenes_of_rank(n_scenes, rank, world):
     return [s for s in range(n_scenes) if (s + s // 8) % world == rank]
 
 
+def scenes_by_cost(table, rank, world):
+    """Scene -> GPU map of the NEXT pass of a sweep from the gathered records of the previous one (gather_records: every
+    rank holds the same table). The scenes of a sweep share one mesh, so any resident slot can run any member; their cost
+    (iterations to the tolerance, 36 ... 100 at cfg 5) repeats from pass to pass. Longest-processing-time-first: the scenes
+    in descending order of their measured device-loop time, each to the GPU with the least load so far (ties: lowest
+    rank). Deterministic: every rank computes the same partition. A rank's list stays in descending order, so its slot
+    threads finish the pass on the short members."""
+    table = np.asarray(table, dtype=np.float64).reshape(-1, len(RECORD_FIELDS))
+    order = sorted(range(table.shape[0]), key=lambda i: (-table[i, 5], table[i, 0]))
+    load = [0.0] * world
+    parts = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        load[r] += table[i, 5]
+        parts[r].append(int(table[i, 0]))
+    return parts[rank]
+
+
 def make_record(scene_id, iters, rejects, final_prim, final_comb, loop_ms, wall_ms, rank):
     return np.array([scene_id, iters, rejects, final_prim, final_comb, loop_ms, wall_ms, rank], dtype=np.float64)
 

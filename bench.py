@@ -336,11 +336,12 @@ def run_gpu(args):
     phases = {k: v for k, v in prof.items() if k != "total" and v["ms"] > 0}
     dom = max(phases, key=lambda k: phases[k]["ms"])
     ach = phases[dom]["bytes"] / (phases[dom]["ms"] * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of one apply (k_fwd_front + k_bwd_front) from the committed
-    # `ncu --set full` capture of this workload: profiles/r01b_ncu_full_summary.md
-    traffic = NCU_LDLT_TRAFFIC_BYTES if dom == "ldlt_apply" else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of one apply (k_fwd_front + k_bwd_front): taken from the committed ncu
+    # launch list of this very command (profiles/ldlt_dram_traffic.json, written by tests/tools/ldlt_traffic_from_launches.py);
+    # a bench run has no profiler attached, so the figure is read, not re-measured - `traffic_source` says from where
+    traffic, traffic_src = _ldlt_traffic() if dom == "ldlt_apply" else (None, None)
     roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": traffic, "peak_source": peak_src,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "kernel_launches": "ldlt_apply = k_fwd_front + k_bwd_front (one launch per sweep)" if dom == "ldlt_apply" else dom,
             "phases": {k: {"ms": round(v["ms"], 4), "algo_GB": round(v["bytes"] / 1e9, 4),
                            "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)} for k, v in phases.items()}}
@@ -394,7 +395,7 @@ CFG5_CPU_SAMPLE = dict(cx=24, cy=22, cz=22, iters=10)
 
 def run_cfg5(args):
     """BASELINE configs[4] (SURVEY 8e cfg 5): 64 independent scenes 88x22x22 (212,960 tets) with the material sweep of
-    aa_admm_b200.ensemble.scene_material, scene s on GPU s mod N, no data-path collective, one NCCL gather of the result
+    aa_admm_b200.ensemble.scene_material, scene -> GPU map static in the first pass and balanced by measured cost afterwards, no data-path collective, one NCCL gather of the result
     records. A bench step = ONE PASS over the whole ensemble (every scene: material -> system-matrix values -> numeric
     LDL^T on the device -> one frame of <= 100 ADMM iterations). Per GPU `slots` scenes are resident and pipelined by
     one host thread each. Strong scaling: the ensemble is fixed, N GPUs share it."""
@@ -405,6 +406,8 @@ def run_cfg5(args):
     c["slots"] = args.slots or c["slots"]
     cores = os.cpu_count() or 1
     os.environ["OMP_NUM_THREADS"] = str(max(1, cores // (world * c["slots"])))
+    if args.blocking_sync:
+        os.environ["AAADMM_BLOCKING_SYNC"] = "1"
     import aa_admm_b200 as A
     from aa_admm_b200 import ensemble as E
     if A.device_count() <= 0:
@@ -432,6 +435,11 @@ def run_cfg5(args):
     recs, setups = E.run_sweep(A, dims, mine, slots, c["frames"], rank)   # first pass: includes the one-time analysis
     first_pass_s = time.perf_counter() - t0
     full_setup_ms = [ms for _, ms, inc in setups if not inc]
+    # the members' costs repeat from pass to pass: the map of the following passes balances the measured loop times
+    # (one gather of the first pass' records; still no collective on the data path)
+    static_map = list(mine)
+    if not args.static_map:
+        mine = E.scenes_by_cost(E.gather_records(recs, dist, device), rank, world)
     for _ in range(max(0, args.warmup - 1)):
         E.run_sweep(A, dims, mine, slots, c["frames"], rank)
     barrier()
@@ -482,8 +490,9 @@ def run_cfg5(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * max_wall / max(1, args.steps),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "cfg5: ensemble of %d independent scenes, beam %dx%dx%d = %d tets each, material sweep E = 1e6..1e8, "
-                                   "nu = 0.30..0.44, hard_zxu ordering, Anderson m=%d, %d frame(s) x <= %d ADMM iterations per scene; scene s on "
-                                   "GPU s mod N, %d resident scenes (host threads) per GPU; one step = one pass over the ensemble, per-scene "
+                                   "nu = 0.30..0.44, hard_zxu ordering, Anderson m=%d, %d frame(s) x <= %d ADMM iterations per scene; first pass: scene s on "
+                                   "GPU (s + s/8) mod N, timed passes: " + ("the same static map" if args.static_map else "scenes spread over the GPUs by the loop "
+                                   "times measured in the first pass (longest first; one gather of result records)") + ", %d resident scenes (host threads) per GPU; one step = one pass over the ensemble, per-scene "
                                    "numeric setup (system-matrix values, numeric LDL^T on the device, moduli) inside the timed region"
                                    % (c["scenes"], *dims, info["n_tets"], c["anderson_m"], c["frames"], c["admm_iters"], c["slots"]),
                        "l2": "two resident scenes of 0.6 GB each per GPU: larger than the 126 MB L2",
@@ -719,7 +728,13 @@ def run_cfg1(args):
     return 0
 
 
-NCU_LDLT_TRAFFIC_BYTES = 2.232e9
+def _ldlt_traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "ldlt_dram_traffic.json")) as f:
+            d = json.load(f)
+        return float(d["bytes_per_apply"]), d["source"]
+    except (OSError, ValueError, KeyError):
+        return None, None
 
 
 _JSON_OUT = None
@@ -750,6 +765,10 @@ def main():
                     help="cfg4 (default, the headline): one 1M-tet beam; cfg5: ensemble of 64 x 213k-tet scenes (material sweep); "
                          "cfg1: xzu sample (three beams); cfg2 / cfg3: Geometry PlanarityOpt / WireMeshOpt (one GPU)")
     ap.add_argument("--slots", type=int, default=0, help="cfg5: resident scenes (host threads) per GPU (default 2)")
+    ap.add_argument("--blocking-sync", action="store_true",
+                    help="cfg5: host threads sleep while they wait for the device (cudaDeviceScheduleBlockingSync)")
+    ap.add_argument("--static-map", action="store_true",
+                    help="cfg5: keep the static scene -> GPU map for every pass (default: passes after the first are balanced by the measured cost of the members)")
     ap.add_argument("--ref-dims", type=int, nargs=3, default=None,
                     help="--impl reference: beam size of the CPU arm (default REF_ARM; smaller sizes are for the CPU test)")
     args = ap.parse_args()

@@ -143,6 +143,9 @@ def _grid_system(nx, ny, nz, seed):
     {"AAADMM_FCH": "128", "AAADMM_BCH": "256", "AAADMM_MIN_CTAS": "4000"},  # smallest tiles, one column per warp
     {"AAADMM_KSMALL": "8", "AAADMM_WIDE": "0"},                          # fundamental supernodes only, chunked gathers
     {"AAADMM_KSMALL": "200", "AAADMM_MIN_CTAS": "1"},                    # heavily relaxed fronts, largest tiles
+    {"AAADMM_RELAX_PCT": "0", "AAADMM_TASK_SLOTS": "0", "AAADMM_ORDER_BY_LEVEL": "0"},  # round-1 fronts and schedule
+    {"AAADMM_RELAX_PCT": "40", "AAADMM_TASK_SLOTS": "4000", "AAADMM_TASK_MIN_KENTRIES": "1",
+     "AAADMM_FCH": "128", "AAADMM_BCH": "256", "AAADMM_ORDER_BY_LEVEL": "1"},  # near-chains merged freely, smallest capped tasks
 ])
 def test_ldlt_apply_front_shapes(gpu, env):
     """The multifrontal sweeps under every tile shape / chunking / wide-front path: residual of A x = b and

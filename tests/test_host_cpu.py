@@ -194,7 +194,7 @@ def _ensemble_worker(rank, world, port, q):
     mine = E.scenes_of_rank(7, rank, world)
     recs = [E.make_record(s, 10 + s, s % 2, 1e-3 * s, 1e-6 * s, 2.0 * s, 3.0 * s, rank) for s in mine]
     table = E.gather_records(np.array(recs).reshape(-1, 8), dist)
-    q.put((rank, table))
+    q.put((rank, table, E.scenes_by_cost(table, rank, world)))
     dist.destroy_process_group()
 
 
@@ -222,9 +222,16 @@ def test_ensemble_sharding_and_gather_gloo_world2(A):
     ps = [ctx.Process(target=_ensemble_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in ps:
         p.start()
-    res = dict(q.get(timeout=120) for _ in ps)
+    got = [q.get(timeout=120) for _ in ps]
+    res = {g[0]: g[1] for g in got}
+    nxt = {g[0]: g[2] for g in got}
     for p in ps:
         p.join(timeout=60)
+    # the cost-balanced map of the next pass: a partition, the same on every rank, heavier scenes first, loads within one
+    # scene of each other (loop_ms of scene s is 2 s in the worker: 0, 2, ..., 12 -> 6+5+... split 22 / 20)
+    assert sorted(nxt[0] + nxt[1]) == list(range(7)) and nxt[0][0] == 6 and nxt[1][0] == 5
+    assert abs(sum(2.0 * s for s in nxt[0]) - sum(2.0 * s for s in nxt[1])) <= 2.0 * 6
+    assert nxt[0] == sorted(nxt[0], reverse=True) and nxt[1] == sorted(nxt[1], reverse=True)
     for r in (0, 1):
         t = res[r]
         assert t.shape == (7, 8)
