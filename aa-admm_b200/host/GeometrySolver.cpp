@@ -1,6 +1,7 @@
 #include "GeometrySolver.hpp"
 
 #include <chrono>
+#include <cstdlib>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
@@ -195,6 +196,12 @@ bool GeometrySolverBase<N>::setup_ADMM(int n_points, double penalty_param, SPDSo
             std::cerr << "Error: SPD solver initialization failed (point " << j << " is unconstrained)" << std::endl;
             return false;
         }
+    if (const char *dump = getenv("AAADMM_GEO_DUMP_MATRIX")) {  // developer aid: the global matrix (lower CSC) as text
+        std::ofstream ofs(dump);
+        ofs << std::setprecision(17) << G.n << " " << G.p[G.n] << "\n";
+        for (int j = 0; j < G.n; ++j)
+            for (int64_t e = G.p[j]; e < G.p[j + 1]; ++e) ofs << G.i[e] << " " << j << " " << G.x[e] << "\n";
+    }
     std::vector<int> perm = nested_dissection(G, nullptr, 64);
     factor_ = ldlt_factorize(G, perm);
     if (!factor_.ok) {

@@ -18,6 +18,14 @@ from geo_recipes import read_obj  # noqa: E402
 GEO = "/root/reference/Geometry"
 
 
+def read_obj_as_the_apps_do(path):
+    """OpenMesh's OBJ reader parses vertex coordinates as float (Core/IO/reader/OBJReader.cc:294) and the applications'
+    meshes then hold them as double: the arrays of the fixtures must be these float-rounded values, or every comparison
+    with the applications' histories starts from inputs that differ by 6e-8 relative."""
+    V, F = read_obj(path)
+    return V.astype(np.float32).astype(np.float64), F
+
+
 def run_app(lib, args):
     L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", lib))
     with tempfile.TemporaryDirectory() as d:
@@ -42,8 +50,8 @@ def main():
     poly = os.path.join(GEO, "Geometry_model/PQMeshData/polymesh/costa2k_poly.obj")
     tri = os.path.join(GEO, "Geometry_model/PQMeshData/trimesh/costa2k_tri.obj")
     hist, Vsol, _ = run_app("libref_planarity.so", [poly, tri, opts])
-    P, faces = read_obj(poly)
-    Vr, Fr = read_obj(tri)
+    P, faces = read_obj_as_the_apps_do(poly)
+    Vr, Fr = read_obj_as_the_apps_do(tri)
     fl = np.full((len(faces), max(len(f) for f in faces)), -1, np.int32)
     for i, f in enumerate(faces):
         fl[i, :len(f)] = f
@@ -62,8 +70,8 @@ def main():
         L.ref_app_edges(quad.encode(), None, C.byref(ne))
         E = np.zeros((ne.value, 2), np.int32)
         L.ref_app_edges(quad.encode(), E.ctypes.data_as(C.c_void_p), C.byref(ne))
-        Vr, Fr = read_obj(tgt)
-        P0, F0 = read_obj(quad)  # the coarse input mesh itself: the product's own front-end subdivides it in the tests
+        Vr, Fr = read_obj_as_the_apps_do(tgt)
+        P0, F0 = read_obj_as_the_apps_do(quad)  # the coarse input mesh itself: the product's own front-end subdivides it in the tests
         os.makedirs(os.path.join(ROOT, "tests", "golden_large"), exist_ok=True)
         np.savez_compressed(os.path.join(ROOT, "tests", "golden_large", "geo_maletorso.npz"), P=P, quads=Q, edges=E, edge_length=el.value,
                             P0=P0, quads0=np.array(F0, np.int32),

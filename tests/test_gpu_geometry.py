@@ -157,10 +157,50 @@ def test_cfg2_planarity_costa2k_vs_reference_app(gpu):
     print("cfg2: iters", len(hist), len(ref), "rel first 8 %.2e" % rel[:8].max(), "max %.2e" % rel.max(),
           "final %.3e vs %.3e" % (hist[-1], ref[-1]), info, "reference CPU loop %.3f s" % g["secs"][-1])
     assert len(hist) == len(ref) == 100
-    assert rel[:8].max() < 1e-8
-    assert abs(np.log10(hist[-1] / ref[-1])) < 1.0
+    # the reference's own FMA build differs from the reference by 7e-12 over the first 20 iterations and 9e-9 over all
+    # 100 (tests/tools/geo_noise_floor.py); measured here 1.3e-10 / 3.1e-8 (summation order of the Anderson Gram dots,
+    # profiles/r02_geo_parity_probe.txt)
+    assert rel[:8].max() < 1e-9
+    assert rel.max() < 1e-6
+    assert abs(hist[-1] / ref[-1] - 1.0) < 1e-6
     # both runs end on the same surface: positions agree far below the mesh's edge length
     assert np.abs(x - g["solution"]).max() < 1e-3 * np.abs(g["P"]).max()
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3"])
+def test_unaccelerated_loop_on_the_real_meshes_vs_reference_class(gpu, refgeo, cfg):
+    """Without Anderson mixing nothing amplifies round-off: on the meshes of cfg 2 / cfg 3 the product's loop and the
+    unmodified solver class (oracle/_ref, same constraint recipe) agree far below the 1e-9 bar (measured 6e-14 / 7e-12,
+    profiles/r02_geo_parity_probe.txt), and so do the positions."""
+    if cfg == "cfg2":
+        g = np.load(os.path.join(HERE, "golden", "geo_costa2k.npz"))
+        faces = [[int(v) for v in f if v >= 0] for f in g["faces"]]
+
+        def build(s):
+            planarity_recipe(s, g["P"], faces, g["Vref"], g["Fref"])
+        rho, iters, bar = 1e5, 40, 1e-11
+    else:
+        p = os.path.join(HERE, "golden_large", "geo_maletorso.npz")
+        if not os.path.exists(p):
+            pytest.skip("tests/golden_large/geo_maletorso.npz not generated (make_golden_geo.py --large)")
+        g = np.load(p)
+
+        def build(s):
+            wiremesh_recipe(s, g["P"], g["quads"], g["edges"], g["Vref"], g["Fref"], float(g["edge_length"]))
+        rho, iters, bar = 1e3, 8, 1e-10
+    s = gpu.GeometrySolver()
+    build(s)
+    s.setup(len(g["P"]), rho)
+    hg, xg = s.solve(g["P"], iters, 0)
+    r = refgeo.RefGeometrySolver(True)
+    build(r)
+    r.setup(len(g["P"]), rho)
+    hr, xr = r.solve(g["P"], iters, 0)
+    rel = np.abs(hg - hr) / hr
+    print(cfg, "no acceleration: rel", rel.max(), "positions", np.abs(xg - xr).max() / np.abs(xr).max())
+    assert len(hg) == len(hr) == iters
+    assert rel.max() < bar
+    assert np.abs(xg - xr).max() / np.abs(xr).max() < bar
 
 
 def test_cfg3_wiremesh_maletorso_vs_reference_app(gpu):
@@ -184,8 +224,13 @@ def test_cfg3_wiremesh_maletorso_vs_reference_app(gpu):
           "reference CPU loop %.1f s" % g["secs"][-1])
     print('rel[:20]', rel[:20])
     assert len(hist) == len(ref) == 100
-    assert rel[:2].max() < 1e-8 and rel[:10].max() < 1e-4
-    assert abs(np.log10(hist[-1] / ref[-1])) < 1.0
+    # the reference's own FMA build: 3e-13 over the first 2 iterations, 4.5e-10 over 10, 1e-7 over 50, 3.5e-4 over all 100
+    # (tests/tools/geo_noise_floor.py); measured here 2.5e-12 / 4.3e-9 / - / 6.5e-5: the Anderson step amplifies the
+    # summation-order difference of its Gram dot products, the un-accelerated run agrees to 7e-12
+    # (profiles/r02_geo_parity_probe.txt)
+    assert rel[:2].max() < 1e-10 and rel[:10].max() < 1e-7
+    assert rel.max() < 3.5e-3  # 10 x the reference's FMA noise
+    assert abs(hist[-1] / ref[-1] - 1.0) < 1e-2
 
 
 # ---- the product's own front-end (host/GeometryApps: OBJ reader, connectivity, subdivision, constraint recipes) ----
@@ -254,7 +299,7 @@ def test_cfg3_wiremesh_sample_on_maletorso(gpu, tmp_path):
     sub = gpu.PolyMesh.load(tmp_path / "quad.obj").subdivide_and_smooth()
     V, F, E = sub.arrays()
     assert np.array_equal(np.array(F), g["quads"]) and np.array_equal(E, g["edges"])
-    assert np.abs(V - g["P"]).max() < 1e-9 * np.abs(g["P"]).max()
+    assert np.abs(V - g["P"]).max() < 1e-13 * np.abs(g["P"]).max()  # measured 9e-15 (summation order of the smoothing)
     exe = _build_geo_sample(tmp_path, "wiremesh")
     r = subprocess.run([exe, "quad.obj", "target.obj", "Options.txt", "out.obj"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr + r.stdout
@@ -267,5 +312,5 @@ def test_cfg3_wiremesh_sample_on_maletorso(gpu, tmp_path):
     assert len(hist) == 100
     # measured 6.7e-13, 2.5e-12, 4.0e-10, 4.3e-9 over the first four iterations; later iterations separate through ties
     # of the closest-point search (a point equally far from two triangles of the target mesh)
-    assert rel[:2].max() < 1e-10 and rel[:4].max() < 1e-7 and rel[:10].max() < 1e-4
-    assert abs(np.log10(hist[-1, 1] / ref[-1])) < 1.0
+    assert rel[:2].max() < 1e-10 and rel[:10].max() < 1e-7 and rel.max() < 3.5e-3  # see the test above
+    assert abs(hist[-1, 1] / ref[-1] - 1.0) < 1e-2
