@@ -212,12 +212,6 @@ int aaadmm_device_count(void) {
     return n;
 }
 int aaadmm_set_device(int device) {
-    // AAADMM_BLOCKING_SYNC=1 (ensemble runs: several host threads per GPU and several ranks per box share the host
-    // cores): a thread that waits for the device sleeps instead of spinning. Takes effect when set before the device's
-    // context exists.
-    static const bool blocking = getenv("AAADMM_BLOCKING_SYNC") && atoi(getenv("AAADMM_BLOCKING_SYNC")) != 0;
-    if (blocking) cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync);  // an error here (context already active) is not fatal
-    cudaGetLastError();
     AAADMM_CUDA_OK(cudaSetDevice(device));
     return 0;
 }

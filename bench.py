@@ -406,8 +406,6 @@ def run_cfg5(args):
     c["slots"] = args.slots or c["slots"]
     cores = os.cpu_count() or 1
     os.environ["OMP_NUM_THREADS"] = str(max(1, cores // (world * c["slots"])))
-    if args.blocking_sync:
-        os.environ["AAADMM_BLOCKING_SYNC"] = "1"
     import aa_admm_b200 as A
     from aa_admm_b200 import ensemble as E
     if A.device_count() <= 0:
@@ -435,10 +433,9 @@ def run_cfg5(args):
     recs, setups = E.run_sweep(A, dims, mine, slots, c["frames"], rank)   # first pass: includes the one-time analysis
     first_pass_s = time.perf_counter() - t0
     full_setup_ms = [ms for _, ms, inc in setups if not inc]
-    # the members' costs repeat from pass to pass: the map of the following passes balances the measured loop times
-    # (one gather of the first pass' records; still no collective on the data path)
-    static_map = list(mine)
-    if not args.static_map:
+    # optional: the members' costs repeat from pass to pass, so the map of the following passes can balance the measured
+    # loop times (one gather of the first pass' records; still no collective on the data path)
+    if args.balance_by_cost:
         mine = E.scenes_by_cost(E.gather_records(recs, dist, device), rank, world)
     for _ in range(max(0, args.warmup - 1)):
         E.run_sweep(A, dims, mine, slots, c["frames"], rank)
@@ -489,12 +486,15 @@ def run_cfg5(args):
     line = {"metric": "admm_anderson_iterations_per_sec_ensemble", "value": tot_iters / (max_loop * 1e-3), "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * max_wall / max(1, args.steps),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg5: ensemble of %d independent scenes, beam %dx%dx%d = %d tets each, material sweep E = 1e6..1e8, "
-                                   "nu = 0.30..0.44, hard_zxu ordering, Anderson m=%d, %d frame(s) x <= %d ADMM iterations per scene; first pass: scene s on "
-                                   "GPU (s + s/8) mod N, timed passes: " + ("the same static map" if args.static_map else "scenes spread over the GPUs by the loop "
-                                   "times measured in the first pass (longest first; one gather of result records)") + ", %d resident scenes (host threads) per GPU; one step = one pass over the ensemble, per-scene "
-                                   "numeric setup (system-matrix values, numeric LDL^T on the device, moduli) inside the timed region"
-                                   % (c["scenes"], *dims, info["n_tets"], c["anderson_m"], c["frames"], c["admm_iters"], c["slots"]),
+            "config": {"workload": ("cfg5: ensemble of %d independent scenes, beam %dx%dx%d = %d tets each, material sweep E = 1e6..1e8, "
+                                    "nu = 0.30..0.44, hard_zxu ordering, Anderson m=%d, %d frame(s) x <= %d ADMM iterations per scene; first pass: "
+                                    "scene s on GPU (s + s/8) mod N, timed passes: %s, %d resident scenes (host threads) per GPU; one step = one "
+                                    "pass over the ensemble, per-scene numeric setup (system-matrix values, numeric LDL^T on the device, moduli) "
+                                    "inside the timed region")
+                                   % (c["scenes"], dims[0], dims[1], dims[2], info["n_tets"], c["anderson_m"], c["frames"], c["admm_iters"],
+                                      "the same static map" if not args.balance_by_cost else
+                                      "scenes spread over the GPUs by the loop times measured in the first pass (longest first; one gather of result records)",
+                                      c["slots"]),
                        "l2": "two resident scenes of 0.6 GB each per GPU: larger than the 126 MB L2",
                        "iterations_timed": tot_iters, "scenes_timed": scenes_timed,
                        "first_pass_s": round(first_pass_s, 3), "full_setup_ms_per_slot": [round(x, 1) for x in full_setup_ms],
@@ -765,10 +765,9 @@ def main():
                     help="cfg4 (default, the headline): one 1M-tet beam; cfg5: ensemble of 64 x 213k-tet scenes (material sweep); "
                          "cfg1: xzu sample (three beams); cfg2 / cfg3: Geometry PlanarityOpt / WireMeshOpt (one GPU)")
     ap.add_argument("--slots", type=int, default=0, help="cfg5: resident scenes (host threads) per GPU (default 2)")
-    ap.add_argument("--blocking-sync", action="store_true",
-                    help="cfg5: host threads sleep while they wait for the device (cudaDeviceScheduleBlockingSync)")
-    ap.add_argument("--static-map", action="store_true",
-                    help="cfg5: keep the static scene -> GPU map for every pass (default: passes after the first are balanced by the measured cost of the members)")
+    ap.add_argument("--balance-by-cost", action="store_true",
+                    help="cfg5: the passes after the first spread the scenes over the GPUs by their measured loop times (longest first) "
+                         "instead of the static diagonal map; measured at 8 GPUs: 200 against 206 scenes/s, so off by default")
     ap.add_argument("--ref-dims", type=int, nargs=3, default=None,
                     help="--impl reference: beam size of the CPU arm (default REF_ARM; smaller sizes are for the CPU test)")
     args = ap.parse_args()
