@@ -707,6 +707,8 @@ void *aaadmm_host_geoapp_new(int kind, void *mesh_h, void *ref_h, const double *
     }
 }
 void aaadmm_host_geoapp_free(void *h) { delete static_cast<aaadmm::geoapp::GeoApp *>(h); }
+// developer aid (per-task trace of the applies of a Geometry solve: aaadmm_ldlt_dump_trace)
+void *aaadmm_host_geoapp_device_factor(void *h) { return static_cast<aaadmm::geoapp::GeoApp *>(h)->device_factor(); }
 int aaadmm_host_geoapp_stats(void *h, double *out8) {
     static_cast<aaadmm::geoapp::GeoApp *>(h)->stats(out8);
     return 0;

@@ -150,6 +150,7 @@ void *aaadmm_host_geoapp_new(int kind, void *mesh, void *ref_mesh, const double 
 void aaadmm_host_geoapp_free(void *h);
 /* out8 = points, hard constraints, z / u columns, soft constraints, nnz(L), fronts, tree levels, bytes of one apply */
 int aaadmm_host_geoapp_stats(void *h, double *out8);
+void *aaadmm_host_geoapp_device_factor(void *h); /* aaadmm_ldlt* of the application's solver (developer aid: trace dump) */
 int aaadmm_host_geoapp_solve(void *h, int max_iter, int anderson_m, double *hist, int *n_hist, double *solution, double *info4);
 
 #ifdef __cplusplus
