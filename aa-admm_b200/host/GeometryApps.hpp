@@ -98,6 +98,7 @@ public:
     // out8 = points, hard constraints, columns of z / u, soft constraints (one per point or one batch), nnz(L), fronts,
     // tree levels, algorithmic bytes of one factor apply
     void stats(double *out8);
+    aaadmm_ldlt *device_factor() { return solver_.device_factor(); }  // developer aid: per-task trace of the applies
 private:
     ALMGeometrySolver<3> solver_;
     PolyMesh mesh_;
