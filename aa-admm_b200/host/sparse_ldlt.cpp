@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <numeric>
@@ -376,10 +377,83 @@ struct Symbolic {
 
 }  // namespace
 
-static LdltFactor ldlt_factorize_impl(const SymLower &A, const std::vector<int> &perm, int n_threads, bool symbolic_only) {
+// Postorder of the elimination tree of P A P^T, composed with P. It changes neither the fill nor the tree, only the
+// numbering: every subtree becomes a run of consecutive columns. The dissection above numbers the nodes of a leaf domain
+// along a coordinate, which is a topological order of the tree but not a postorder; the device-side setup merges a small
+// subtree into ONE front only when its columns are consecutive (csrc/ldlt_apply.cu, rule 1), and on a surface mesh
+// (cfg 3) most leaf domains otherwise fall apart into chains of fronts of 1-10 columns, seven tree levels deep.
+static std::vector<int> etree_postorder(const SymLower &A, const std::vector<int> &perm) {
+    const int n = A.n;
+    std::vector<int> iperm(n);
+    for (int k = 0; k < n; ++k) iperm[perm[k]] = k;
+    // rows of the strictly lower triangle of B = P A P^T: row r lists the columns c < r
+    std::vector<int64_t> rp(n + 1, 0);
+    for (int j = 0; j < n; ++j)
+        for (int64_t p = A.p[j]; p < A.p[j + 1]; ++p) {
+            const int r = iperm[A.i[p]], c = iperm[j];
+            if (r != c) rp[std::max(r, c) + 1]++;
+        }
+    for (int j = 0; j < n; ++j) rp[j + 1] += rp[j];
+    std::vector<int> ri(rp[n]);
+    {
+        std::vector<int64_t> pos(rp.begin(), rp.end() - 1);
+        for (int j = 0; j < n; ++j)
+            for (int64_t p = A.p[j]; p < A.p[j + 1]; ++p) {
+                const int r = iperm[A.i[p]], c = iperm[j];
+                if (r != c) ri[pos[std::max(r, c)]++] = std::min(r, c);
+            }
+    }
+    // Liu's algorithm with path compression
+    std::vector<int> parent(n, -1), anc(n, -1);
+    for (int j = 0; j < n; ++j)
+        for (int64_t p = rp[j]; p < rp[j + 1]; ++p) {
+            int k = ri[p];
+            while (anc[k] != -1 && anc[k] != j) {
+                const int t = anc[k];
+                anc[k] = j;
+                k = t;
+            }
+            if (anc[k] == -1) {
+                anc[k] = j;
+                parent[k] = j;
+            }
+        }
+    // depth-first postorder, children in ascending order (chains keep their order)
+    std::vector<int> head(n, -1), next(n, -1);
+    for (int j = n - 1; j >= 0; --j)
+        if (parent[j] >= 0) {
+            next[j] = head[parent[j]];
+            head[parent[j]] = j;
+        }
+    std::vector<int> post;
+    post.reserve(n);
+    std::vector<int> stack;
+    for (int root = 0; root < n; ++root) {
+        if (parent[root] >= 0) continue;
+        stack.push_back(root);
+        while (!stack.empty()) {
+            const int v = stack.back();
+            const int c = head[v];
+            if (c >= 0) {
+                head[v] = next[c];
+                stack.push_back(c);
+            } else {
+                post.push_back(v);
+                stack.pop_back();
+            }
+        }
+    }
+    std::vector<int> out(n);
+    for (int k = 0; k < n; ++k) out[k] = perm[post[k]];
+    return out;
+}
+
+static LdltFactor ldlt_factorize_impl(const SymLower &A, const std::vector<int> &perm_in, int n_threads, bool symbolic_only) {
     LdltFactor out;
     const int n = A.n;
     out.n = n;
+    static const bool no_postorder = getenv("AAADMM_NO_POSTORDER") != nullptr;  // experiments
+    const std::vector<int> perm = no_postorder ? perm_in : etree_postorder(A, perm_in);
     out.perm = perm;
     if (n_threads <= 0) n_threads = omp_get_max_threads();
     double t0 = now_s();
