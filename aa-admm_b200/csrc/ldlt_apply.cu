@@ -991,17 +991,11 @@ static int build(LdltDev **out, int n, const int64_t *Lp, const int *Li, const d
     // column j joins the front of j-1 when j is the parent of j-1 and either the patterns nest exactly
     // (fundamental supernode) or the front is still small (relaxed chain).
     // tuning knobs (environment overrides are for experiments only)
-    // Factors whose largest fundamental supernode stays below the chunk size of the sweeps (surface meshes, 2-D
-    // separators: cfg 3) are deep trees of small fronts; every level costs about 5 us per sweep whatever it holds, so
-    // they merge twice as much (measured on cfg 3: 0.876 -> 0.830 ms per loop turn; on the volume meshes the larger caps
-    // only add zeros: cfg 4 0.481 -> 0.488 ms).
-    int max_fund = 0;
-    for (int j = 0, run = 0; j < n; ++j) {
-        const bool chain = j > 0 && Lp[j] - Lp[j - 1] > 0 && Li[Lp[j - 1]] == j && (Lp[j] - Lp[j - 1]) == (Lp[j + 1] - Lp[j]) + 1;
-        run = chain ? run + 1 : 1;
-        max_fund = std::max(max_fund, run);
-    }
-    const int merge_cap = max_fund <= FCH ? 128 : 64;
+    // Factors with little fill per column (surface meshes, 2-D separators: cfg 3 has nnz(L) / n = 39, a 2 M-triangle
+    // cloth 58; the volume meshes of cfg 4 / cfg 5 513 / 279) are deep trees of small fronts; every level costs about 5 us
+    // per sweep whatever it holds, so they merge twice as much (measured: cfg 3 0.876 -> 0.836 ms per loop turn, cloth
+    // apply 0.899 -> 0.868 ms; on the volume meshes the larger caps only add zeros: cfg 4 0.481 -> 0.488 ms).
+    const int merge_cap = nnz < (int64_t)128 * std::max(n, 1) ? 128 : 64;
     const int kSmall = env_int("AAADMM_KSMALL", merge_cap), kCap = env_int("AAADMM_KCAP", 6144);
     const int kSubtree = env_int("AAADMM_KSUBTREE", merge_cap);
     std::vector<int> sub_root(std::max(n, 1), -1);  // root of the maximal small contiguous subtree holding j
