@@ -147,6 +147,14 @@ __device__ __forceinline__ void pipe_drain(PipeBars &B, int issued) {
     for (int i = 0; i < issued; ++i) mbar_wait(&B.full[i], 0);
 }
 
+// rows a forward tile of 2^shape rows stores per column when `left` rows of the front remain at its first row: a tile
+// that reaches past the front's last row (the only or last tile of a front, e.g. 176 rows in a 256-row tile) is stored
+// - in HBM and in the stages - with its real (even) row count as column stride, so no padding rows are streamed
+__host__ __device__ __forceinline__ int fwd_rows_stored(int shape, int left) {
+    const int rt = 1 << shape, r = (left + 1) & ~1;
+    return r < rt ? r : rt;
+}
+
 // ---- forward: one CTA = RT rows of one front, the columns interleaved over CS = 512 / RT slices ----
 // RT = 256 .. 16 per task (narrow fronts want many rows per CTA, wide ones many slices). A consumer thread
 // owns two adjacent rows. The tile is stored contiguously (tile-major copy Mf of the front matrices: column
@@ -163,6 +171,7 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const Gather &G,
     const int ncols = min(F.ns, r0 + RT);      // columns stored for this tile (rows of the diagonal block
                                                // have nothing to the right of the tile's last row)
     const int nstages = (ncols + NCS - 1) / NCS;
+    const int RTS = fwd_rows_stored(LRT, m - r0);  // column stride of the stored tile (== RT unless the tile ends the front)
     const int lane = threadIdx.x & 31;
     const int lp = threadIdx.x & (RT / 2 - 1), cs = threadIdx.x >> (LRT - 1);
     double acc[2][NR], pass[NR];
@@ -249,7 +258,7 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const Gather &G,
 #pragma unroll
                 for (int i = 0; i < PER; ++i) {
                     const int c = cs + i * CS;
-                    const double2 v = *reinterpret_cast<const double2 *>(st + c * RT);
+                    const double2 v = *reinterpret_cast<const double2 *>(st + c * RTS);
 #pragma unroll
                     for (int q = 0; q < NR; ++q) {
                         const double w = wp[c * NR + q];
@@ -262,7 +271,7 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const Gather &G,
                 for (int i = 0; i < PER; ++i) {
                     const int c = cs + i * CS;
                     if (c < colsin) {
-                        const double2 v = *reinterpret_cast<const double2 *>(st + c * RT);
+                        const double2 v = *reinterpret_cast<const double2 *>(st + c * RTS);
 #pragma unroll
                         for (int q = 0; q < NR; ++q) {
                             const double w = wp[c * NR + q];
@@ -309,7 +318,7 @@ __device__ __forceinline__ void fwd_tile(const SweepTask &F, const Gather &G,
 }
 
 template <int NR>
-__global__ void __launch_bounds__(NTHR)
+__global__ void __launch_bounds__(NTHR, 3)
 k_fwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restrict__ Mf,
             Gather G, double *W, const double *__restrict__ dinv, double *__restrict__ Yd, double *U,
             const int *skip, int ws_cap, unsigned long long *trace) {
@@ -327,12 +336,13 @@ k_fwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restr
     const int ncols = min(F.ns, F.start + RT);
     const int nstages = F.shape == 0 ? 0 : (ncols + NCS - 1) / NCS;  // shape 0: assemble task, no factor data
     const double *tile = Mf + F.m_off;
+    const int RTS = fwd_rows_stored(F.shape, F.ns + F.k - F.start);
     auto produce = [&](int it) {
         const int slot = it % NSTG;
         mbar_wait(&B.empty[slot], ((it / NSTG) & 1) ^ 1);
-        const unsigned bytes = (unsigned)(min(NCS, ncols - it * NCS) * RT * 8);
+        const unsigned bytes = (unsigned)(min(NCS, ncols - it * NCS) * RTS * 8);
         mbar_expect_tx(&B.full[slot], bytes);
-        bulk_g2s(sm + (size_t)slot * STG, tile + (size_t)it * STG, bytes, &B.full[slot]);
+        bulk_g2s(sm + (size_t)slot * STG, tile + (size_t)it * NCS * RTS, bytes, &B.full[slot]);
     };
     const int first = min(nstages, NSTG);
     if (threadIdx.x == NCONS)
@@ -662,10 +672,11 @@ k_make_tiles(const SweepTask *__restrict__ tasks, const int64_t *__restrict__ sr
     if (F.shape == 0) return;  // assemble task: no factor data
     const int RT = 1 << F.shape, r0 = F.start;
     const int ncols = min(F.ns, r0 + RT);
+    const int RTS = fwd_rows_stored(F.shape, F.ns + F.k - r0);
     const double *src = M + src_off[blockIdx.x];
     double *dst = Mf + F.m_off;
-    for (int e = threadIdx.x; e < ncols * RT; e += 256) {
-        const int j = e >> F.shape, r = r0 + (e & (RT - 1));
+    for (int e = threadIdx.x; e < ncols * RTS; e += 256) {
+        const int j = e / RTS, r = r0 + (e - j * RTS);
         dst[e] = r < F.ld ? src[(size_t)j * F.ld + r] : 0.0;
     }
 }
@@ -1386,7 +1397,7 @@ static int build(LdltDev **out, int n, const int64_t *Lp, const int *Li, const d
         tile_src[i] = t.m_off;
         t.m_off = mf_tot;
         const int64_t RT = (int64_t)1 << t.shape;
-        mf_tot += (RT * std::min(t.ns, t.start + (int)RT) + 15) & ~(int64_t)15;
+        mf_tot += ((int64_t)fwd_rows_stored(t.shape, t.ns + t.k - t.start) * std::min(t.ns, t.start + (int)RT) + 15) & ~(int64_t)15;
     }
     // stage-major copy for the backward sweep
     int64_t mb_tot = 0;
