@@ -149,6 +149,30 @@ def test_host_nested_dissection_ldlt(A, with_coords):
         assert np.abs(x.reshape(n, nrhs) - np.linalg.solve(Afull, b.reshape(n, nrhs))).max() < 1e-10
 
 
+def test_host_ordering_is_a_postorder_of_the_elimination_tree(A):
+    """host/sparse_ldlt.cpp: etree_postorder - every subtree of the elimination tree of the returned factor is a run of
+    consecutive columns (what the device-side front builder needs to merge a small subtree into one front), with and
+    without coordinates (geometric / BFS bisection)."""
+    rng = np.random.default_rng(7)
+    for dims, with_coords in (((9, 8, 7), True), ((23, 19, 1), False), ((23, 19, 1), True)):
+        Afull, coords, Ap, Ai, Ax = _grid_spd(*dims, rng)
+        n = Afull.shape[0]
+        hf = A.HostFactor(n, Ap, Ai, Ax, coords if with_coords else None, leaf_size=16)
+        Lp, Li, Lx, D, perm = hf.arrays()
+        assert sorted(perm) == list(range(n))
+        parent = np.array([Li[Lp[j]] if Lp[j + 1] > Lp[j] else -1 for j in range(n)])
+        assert np.all((parent == -1) | (parent > np.arange(n)))
+        size = np.ones(n, int)
+        lo = np.arange(n)
+        for j in range(n):  # children precede their parents
+            if parent[j] >= 0:
+                size[parent[j]] += size[j]
+                lo[parent[j]] = min(lo[parent[j]], lo[j])
+        assert np.all(np.arange(n) - lo + 1 == size), dims
+        b = rng.standard_normal(n)
+        assert np.abs(hf.solve(b, 1) - np.linalg.solve(Afull, b)).max() < 1e-10
+
+
 def _declared(header):
     txt = open(os.path.join(ROOT, "include", header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
