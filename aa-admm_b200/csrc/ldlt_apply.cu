@@ -117,9 +117,11 @@ __device__ __forceinline__ void task_wait(const int *cnt, const SweepTask &F) {
 // called by all consumer threads after their global writes
 __device__ __forceinline__ void task_signal(int *cnt, const SweepTask &F) {
     if (F.signal_idx < 0) return;  // nobody waits for this task (root forward, leaf fronts backward)
-    __threadfence();
+    // the CTA's writes are ordered before the barrier, the barrier before thread 0's release at device scope (the
+    // semaphore idiom: one release instead of a device-wide fence in every thread); the waiting side reads the counter
+    // with ld.acquire.gpu
     asm volatile("bar.sync 1, 256;\n" ::: "memory");
-    if (threadIdx.x == 0 && F.signal_idx >= 0) atomicAdd(cnt + F.signal_idx, 1);
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;\n" ::"l"(cnt + F.signal_idx) : "memory");
 }
 
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
