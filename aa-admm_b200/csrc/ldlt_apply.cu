@@ -1247,6 +1247,7 @@ static int build(LdltDev **out, int n, const int64_t *Lp, const int *Li, const d
     f->v_cap = v_cap;
     std::vector<int> lrt(std::max(nb, 1), 8), bcols(std::max(nb, 1), 32), bcw_f(std::max(nb, 1), 4);
     const int task_slots = env_int("AAADMM_TASK_SLOTS", 200);                       // 0: no per-front cap
+    const int task_slots_f = env_int("AAADMM_TASK_SLOTS_F", task_slots), task_slots_b = env_int("AAADMM_TASK_SLOTS_B", task_slots);
     const int64_t task_min_entries = (int64_t)env_int("AAADMM_TASK_MIN_KENTRIES", 8) * 1024;
     for (int l = 0; l < nlev; ++l) {
         std::vector<int> &v = by_level[l];
@@ -1302,7 +1303,8 @@ static int build(LdltDev **out, int n, const int64_t *Lp, const int *Li, const d
         {
             int64_t level_entries = 0;
             for (int b : v) level_entries += (int64_t)fr[b].ns * (fr[b].ns / 2 + fr[b].k);
-            const int64_t e_star = std::max<int64_t>(task_min_entries, level_entries / std::max(task_slots, 1));
+            const int64_t e_star = std::max<int64_t>(task_min_entries, level_entries / std::max(task_slots_f, 1));
+            const int64_t e_star_b = std::max<int64_t>(task_min_entries, level_entries / std::max(task_slots_b, 1));
             for (int b : v) {
                 const int ns = fr[b].ns, m = fr[b].ns + fr[b].k;
                 if (task_slots > 0) {
@@ -1310,7 +1312,7 @@ static int build(LdltDev **out, int n, const int64_t *Lp, const int *Li, const d
                 }
                 int cw = bcw[l];
                 if (task_slots > 0) {
-                    const int64_t nc_des = std::max<int64_t>(8, e_star / std::max(m, 1));
+                    const int64_t nc_des = std::max<int64_t>(8, e_star_b / std::max(m, 1));
                     cw = std::min(cw, nc_des >= 32 ? 4 : (nc_des >= 16 ? 2 : 1));
                     const int g = 8 * cw;
                     if (fr[b].ld <= v_cap)
