@@ -400,8 +400,6 @@ k_fwd_front(const SweepTask *__restrict__ tasks, int *ctl, const double *__restr
     }
     task_wait(ctl + 2, F);  // the children's updates are written
     const unsigned long long t2 = trace ? gtime() : 0;
-    if (false) {
-    } else
     switch (F.shape) {
     case 8: fwd_tile<NR, 8>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
     case 7: fwd_tile<NR, 7>(F, G, W, dinv, Yd, U, ws_cap, sm, B); break;
