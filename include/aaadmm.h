@@ -176,7 +176,10 @@ int aaadmm_tetscene_step_resident(aaadmm_tetscene *s, const aaadmm_step_opts *op
  * cumulative times the reference writes to ./result/residual-*.txt (hard/src/Solver.cpp:210-212). n <= rows logged. */
 int aaadmm_tetscene_iteration_times(aaadmm_tetscene *s, double *ms, int n);
 /* Debug/parity access: copies z (9*n_tets, reference layout: 9 consecutive doubles per tet)
- * and u of the last step to the host. */
+ * and u of the last step to the host. Both are locals of the reference's Solver::step (hard/src/Solver.cpp:84-86) and
+ * do not survive it there. One difference on a frame that ends through the break test `comb < 1e-20`
+ * (hard/src/Solver.cpp:188-189): the reference leaves the loop before its last update of u, here the kernel that
+ * evaluates the test has already written that update; x is the same. */
 int aaadmm_tetscene_read_zu(aaadmm_tetscene *s, double *z, double *u);
 /* Per-kernel device timings of the last profiled step (see aaadmm_tetscene_profile). */
 #define AAADMM_NPROF 8
