@@ -9,9 +9,10 @@
 //   forward   [ y ; u_own ] = M w          w = rhs - (updates of the children that land in the front's columns)
 //             u = u_own + (updates of the children that land in the k rows below)      -> handed to the parent
 //   backward  x = M^T [ D^-1 y ; -x(rows below) ]
-// Fronts are scheduled by their height in the supernode tree: one launch per level and sweep,
-// 2 * levels launches per apply. No indices are streamed (8 bytes per factor entry and sweep), every
-// load of M is a coalesced 256-byte segment, the summation order is fixed (no atomics): results are
+// One kernel launch per sweep: the fronts are cut into tasks (row tiles forward, column chunks backward), the tasks
+// are handed out in topological order through a ticket and synchronise through per-front arrival counters; every
+// task streams its part of M through a cp.async.bulk + mbarrier ring (see k_fwd_front / k_bwd_front). No indices are
+// streamed (8 bytes per factor entry and sweep), the summation order is fixed (no atomics on data): results are
 // bit-reproducible. Right-hand sides are interleaved (n x NR, NR = 3 for A = Ahat (x) I3): every
 // factor entry is read once per sweep and used NR times.
 #include "ldlt_apply.cuh"
